@@ -1,0 +1,118 @@
+/* C ABI of the B200-native Watch-Attend-and-Parse hot path (libwap_b200.so).
+ *
+ * The reference (wwjwhen/Watch-Attend-and-Parse-tensorflow-version) has no FFI: its boundary is
+ * the TensorFlow session.run feed/fetch contract of model-single-GPU.py.  Each entry point below
+ * names the reference call site it replaces (S = model-single-GPU.py, D = model-distributed.py).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; wap_last_error() gives a thread-local message;
+ *   - all tensor arguments are CALLER-OWNED DEVICE pointers (fp32, row-major / NHWC, contiguous,
+ *     16-byte aligned); the library allocates no device memory;
+ *   - work is enqueued asynchronously on `stream` (a cudaStream_t passed as void*); the only calls
+ *     that synchronise the host are documented as such (wap_greedy_decode with check_every > 0);
+ *   - `params` / `grads` / optimiser state are FLAT fp32 buffers of wap_param_floats() elements whose
+ *     layout is described by wap_param_info(); moving batch-norm statistics live in a second flat
+ *     buffer of wap_moving_floats() elements;
+ *   - dropout uses a counter-based hash RNG keyed by (seed, site, element index); tests reproduce
+ *     the masks bit-exactly on the host.
+ */
+#ifndef WAP_ABI_H_
+#define WAP_ABI_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WAP_ABI_VERSION 1
+
+int wap_abi_version(void);
+const char* wap_last_error(void);
+
+/* ---- parameter layout (variables of S:562-607 under their TF names: conv2d[_k]/kernel,
+ *      batch_normalization[_k]/{gamma,beta,moving_mean,moving_variance}, U_f ... bo) */
+int wap_param_count(void);
+/* flags: bit0 = receives the L2 term (S:596-598); bit1 = moving statistic (offset into the moving buffer) */
+int wap_param_info(int index, char* name, int name_cap, int64_t* offset, int* ndim, int64_t dims[4], int* flags);
+int64_t wap_param_floats(void);   /* flat trainable buffer (each tensor padded to a multiple of 4 floats) */
+int64_t wap_decay_floats(void);   /* elements [0, decay) of the flat buffer get the L2 term */
+int64_t wap_moving_floats(void);
+
+/* ---- geometry helpers: 'SAME' sizes of the annotation grid (S:78-86,128-130) */
+int wap_annotation_hw(int H, int W, int* h, int* w);
+/* a_mask[b,i,j] = x_mask[b,16i,16j]   (S:80,86,130: four [:,0::2,0::2] slices) */
+int wap_mask_subsample(void* stream, const float* x_mask, int B, int H, int W, float* a_mask);
+
+/* ---- Watcher_train.dense_net (S:73-132)
+ * x [B,H,W,1]; annotation [B,h,w,684].  training != 0: batch statistics (+ moving-stat update,
+ * S:604-607) and activations saved in `workspace` for wap_encoder_backward; dropout != 0 enables
+ * the rate-0.2 dropout sites with `seed`. */
+int64_t wap_encoder_workspace_floats(int B, int H, int W, int training);
+int wap_encoder_forward(void* stream, const float* params, float* moving, const float* x, int B, int H, int W,
+                        int training, int dropout, uint32_t seed, float* annotation, float* workspace);
+/* gradient of dense_net: grads += d params ; d_annotation is clobbered. */
+int wap_encoder_backward(void* stream, const float* params, float* grads, const float* x, int B, int H, int W,
+                         int dropout, uint32_t seed, const float* annotation, float* d_annotation, float* workspace);
+
+/* ---- Attender precompute: watch = annotation*U_a + U_a_b (S:177, hoisted out of the scan),
+ *      qfused = alpha_past_filter*U_f (S:171-173 fused), h0 = tanh(mean(annotation)*Wa2h + ba2h)
+ *      (S:345-347 with a_mask, S:590 with a_mask = NULL).  Any of watch/h0/qfused may be NULL.
+ *      scratch: B*684 floats. */
+int wap_attn_precompute(void* stream, const float* params, const float* annotation, const float* a_mask,
+                        int B, int h, int w, float* watch, float* h0, float* qfused, float* scratch);
+
+/* ---- WAP.get_word (S:379-439): one decode step for Bn hypotheses.
+ * y[Bn] int32 (y<0 => zero embedding, S:381-384); shared != 0: all rows share annotation/watch
+ * of ONE image (the reference tiles ctx0, S:463).  probs [Bn,111], word [Bn] (argmax), either may be NULL. */
+int64_t wap_decoder_step_workspace_floats(int Bn, int h, int w);
+int wap_decoder_step(void* stream, const float* params, const float* annotation, const float* watch,
+                     const float* qfused, int shared, int Bn, int h, int w, const int32_t* y,
+                     const float* h_prev, const float* alpha_past, float* probs, int32_t* word,
+                     float* h_new, float* alpha_past_new, float* workspace);
+
+/* ---- greedy decode (intended semantics of the dead branch S:475-483) of Bn images at once.
+ * tokens [Bn,maxlen] int32, lengths [Bn] int32 (tokens written incl. the final <eol>=0 if emitted).
+ * check_every > 0: synchronises the host every that many steps to stop early. */
+int64_t wap_greedy_workspace_floats(int Bn, int h, int w);
+int wap_greedy_decode(void* stream, const float* params, const float* annotation, int Bn, int h, int w,
+                      int maxlen, int check_every, int32_t* tokens, int32_t* lengths, float* workspace,
+                      int* steps_run);
+
+/* ---- WAP.get_cost (S:337-375) forward over the whole caption (tf.scan of Parser.one_time_step,
+ *      S:246-308) and its gradient.  y int32 [T,B], y_mask [T,B], a_mask [B,h,w].
+ *      cost (device double) = mean_B sum_T mask*CE  (no L2 term; see wap_adadelta_l2_step).
+ *      backward: grads += d params (decoder tensors), d_annotation [B,h,w,684] is written. */
+int64_t wap_decoder_train_workspace_floats(int B, int h, int w, int T);
+int wap_decoder_train_forward(void* stream, const float* params, const float* annotation, const float* a_mask,
+                              const int32_t* y, const float* y_mask, int B, int h, int w, int T,
+                              int dropout, uint32_t seed, double* cost, float* workspace);
+int wap_decoder_train_backward(void* stream, const float* params, float* grads, const float* annotation,
+                               const float* a_mask, const int32_t* y, const float* y_mask, int B, int h, int w,
+                               int T, int dropout, uint32_t seed, float* d_annotation, float* workspace);
+
+/* ---- L2 (S:594-598) + tf.train.AdadeltaOptimizer(lr) (S:602-607; rho .95, eps 1e-8) on the flat
+ *      buffers, with the data-parallel 1/world_size mean of the summed replica gradients
+ *      (SyncReplicasOptimizer, D:704-717) folded in.  g = grad_scale*grads + 2*l2*p (decayed part).
+ *      l2_cost (device double, may be NULL) receives l2 * sum(p^2) of the pre-update parameters. */
+int wap_adadelta_l2_step(void* stream, float* params, const float* grads, float* accum, float* accum_update,
+                         int64_t n, int64_t n_decay, float lr, float rho, float eps, float l2, float grad_scale,
+                         double* l2_cost);
+
+/* ---- fp32 GEMM primitives (exported for the kernel-level parity tests) */
+int wap_gemm_nn(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                const float* bias, int accumulate);
+int wap_gemm_nt(void* stream, const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                const float* bias, int accumulate);
+int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K);
+/* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
+int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);
+/* byte offsets (in floats) of selected encoder-workspace regions, for tests: what = 0 stem_raw,
+ * 1 block buffer b (arg), 2 y1 of conv k (arg), 3 a1 of conv k, 4 y2 of conv k, 5 raw transition b */
+int64_t wap_encoder_workspace_offset(int B, int H, int W, int training, int what, int arg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WAP_ABI_H_ */

@@ -1,0 +1,43 @@
+"""Shared helpers for the parity tests (engine vs CPU oracle)."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import wap_oracle as O  # noqa: E402
+
+REL_TOL = 1e-3      # north_star: "within 1e-3 relative fp32 tolerance"
+
+
+def rel_err(a, b) -> float:
+    """max |a-b| / max |b|  (b = oracle)."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (a.shape, b.shape)
+    d = float(np.max(np.abs(a - b))) if a.size else 0.0
+    return d / max(float(np.max(np.abs(b))) if b.size else 0.0, 1e-30)
+
+
+def rel_l2(a, b) -> float:
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def make_batch(seed, B, H, W, cap_len, ragged=False):
+    imgs, caps = O.synth_batch(seed, B, H, W, cap_len, ragged=ragged)
+    return O.prepare_data(imgs, caps)
+
+
+def engine_with(P_np):
+    import wap_b200
+    eng = wap_b200.WAPEngine(init=False)
+    eng.P.load(P_np)
+    return eng
+
+
+def t64(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float64)

@@ -1,0 +1,314 @@
+"""Parity of the sm_100a path (through the C ABI) against the CPU oracle.  `-m gpu` only.
+
+Tolerance: 1e-3 relative (max|engine-oracle| / max|oracle|) — BASELINE.json north_star; greedy
+token sequences must be identical.  Oracle side runs in float64.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, REL_TOL, engine_with, make_batch, rel_err, rel_l2, t64
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(report, test, name, got, ref, tol=REL_TOL, fails=None):
+    e = rel_err(got, ref)
+    report.add(test, name, e, tol, extra=dict(rel_l2=rel_l2(got, ref), ref_max=float(np.max(np.abs(ref))) if np.size(ref) else 0.0))
+    if not (e <= tol) and fails is not None:
+        fails.append((name, e))
+    return e
+
+
+def _lib():
+    import wap_b200
+    return wap_b200._lib
+
+
+# --------------------------------------------------------------------------------------
+def test_gemm_primitives(report):
+    lib = _lib(); L = lib.lib()
+    dev = torch.device("cuda")
+    g = torch.Generator(device="cpu").manual_seed(0)
+    fails = []
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    p = lambda t: C.c_void_p(t.data_ptr())  # noqa: E731
+    for (M, N, K) in [(8, 256, 256), (300, 96, 72), (130, 111, 128), (257, 512, 684), (1000, 24, 864), (64, 684, 512)]:
+        A = torch.randn(M, K, generator=g).to(dev); B = torch.randn(K, N, generator=g).to(dev)
+        bias = torch.randn(N, generator=g).to(dev)
+        Cm = torch.zeros(M, N, device=dev)
+        lib.check(L.wap_gemm_nn(st, p(A), K, p(B), N, p(Cm), N, M, N, K, p(bias), 0), "gemm_nn")
+        ref = (A.double() @ B.double() + bias.double()).cpu().numpy()
+        _check(report, "gemm", f"nn_{M}x{N}x{K}", Cm.cpu().numpy(), ref, 1e-5, fails)
+        Wt = B.t().contiguous()
+        C2 = torch.ones(M, N, device=dev)
+        lib.check(L.wap_gemm_nt(st, p(A), K, p(Wt), K, p(C2), N, M, N, K, None, 1), "gemm_nt")
+        _check(report, "gemm", f"nt_acc_{M}x{N}x{K}", C2.cpu().numpy(), (A.double() @ B.double() + 1).cpu().numpy(), 1e-5, fails)
+    for (M, N, K) in [(72, 96, 5000), (256, 512, 41), (684, 256, 328), (864, 24, 4097)]:
+        A = torch.randn(K, M, generator=g).to(dev); B = torch.randn(K, N, generator=g).to(dev)
+        Cm = torch.zeros(M, N, device=dev)
+        lib.check(L.wap_gemm_tn_atomic(st, p(A), M, p(B), N, p(Cm), N, M, N, K), "gemm_tn")
+        _check(report, "gemm", f"tn_{M}x{N}x{K}", Cm.cpu().numpy(), (A.double().t() @ B.double()).cpu().numpy(), 1e-5, fails)
+    assert not fails, fails
+
+
+def test_dropout_hash_matches_numpy(report):
+    lib = _lib(); L = lib.lib()
+    n = 100003
+    for seed, site in [(1234, 5), (0xFFFFFFF0, 99), (7, 0)]:
+        m = torch.empty(n, device="cuda")
+        lib.check(L.wap_dropout_mask(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_uint32(seed), C.c_uint32(site), n,
+                                     C.c_void_p(m.data_ptr())), "dropout_mask")
+        ref = O.drop_hash_keep(seed, site, n)
+        assert np.array_equal(m.cpu().numpy(), ref)
+        assert abs(ref.mean() - 0.8) < 0.01
+    report.add("dropout", "hash_bit_exact", 0.0, 0.0)
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,H,W,ragged", [(1, 64, 256, False), (2, 37, 75, True), (3, 48, 80, True)])
+def test_encoder_inference(report, B, H, W, ragged):
+    x, xm, _, _ = make_batch(11 + B, B, H, W, 4, ragged)
+    P = O.calibrate_moving(O.lively_params(3), x, xm)
+    eng = engine_with(P)
+    ann, am = eng.dense_net(x, xm, training=False)
+    taps = {}
+    Pt = O.to_torch(P)
+    ref, ref_m, _ = O.dense_net(Pt, t64(x), t64(xm), False, taps=taps)
+    fails = []
+    tag = f"enc_infer_B{B}_{H}x{W}"
+    _check(report, tag, "annotation", ann.cpu().numpy(), ref.numpy(), REL_TOL, fails)
+    _check(report, tag, "mask", am.cpu().numpy(), ref_m.numpy(), 0.0, fails)
+    # intermediate block buffers (diagnostics; same tolerance)
+    lib = _lib(); L = lib.lib()
+    ws = eng._ws[("enc", B, H, W, False)]
+    hw = [(taps["block0"].shape[1], taps["block0"].shape[2]), (taps["block1"].shape[1], taps["block1"].shape[2])]
+    for b in range(2):
+        off = L.wap_encoder_workspace_offset(B, H, W, 0, 1, b)
+        h, w = hw[b]; Ct = taps[f"block{b}"].shape[3]
+        got = ws[off: off + B * h * w * Ct].view(B, h, w, Ct).cpu().numpy()
+        _check(report, tag, f"block{b}", got, taps[f"block{b}"].numpy(), REL_TOL, fails)
+    assert not fails, fails
+
+
+@pytest.mark.parametrize("B,H,W,drop", [(2, 40, 72, False), (2, 40, 72, True), (3, 33, 65, True)])
+def test_encoder_training_forward(report, B, H, W, drop):
+    x, xm, _, _ = make_batch(21 + B, B, H, W, 4, True)
+    P = O.lively_params(4)
+    eng = engine_with(P)
+    seed = 4242
+    ann, _ = eng.dense_net(x, xm, training=True, dropout=drop, seed=seed)
+    Pt = O.to_torch(P)
+    ref, _, new_moving = O.dense_net(Pt, t64(x), t64(xm), True, O.hash_drop_fn(seed) if drop else None)
+    fails = []
+    tag = f"enc_train_B{B}_{H}x{W}_drop{int(drop)}"
+    _check(report, tag, "annotation", ann.cpu().numpy(), ref.numpy(), REL_TOL, fails)
+    sd = eng.P.state_dict()
+    worst_m = max(rel_err(sd[n], v.numpy()) for n, v in new_moving.items() if n.endswith("moving_mean"))
+    worst_v = max(rel_err(sd[n], v.numpy()) for n, v in new_moving.items() if n.endswith("moving_variance"))
+    report.add(tag, "moving_mean_worst", worst_m, REL_TOL); report.add(tag, "moving_var_worst", worst_v, REL_TOL)
+    assert worst_m <= REL_TOL and worst_v <= REL_TOL, (worst_m, worst_v)
+    assert not fails, fails
+
+
+# --------------------------------------------------------------------------------------
+def _rand_annotation(seed, B, h, w):
+    rs = np.random.RandomState(seed)
+    return np.maximum(rs.randn(B, h, w, O.ANNOT_C), 0).astype(np.float32)      # post-ReLU-like
+
+
+@pytest.mark.parametrize("k,h,w,shared", [(1, 4, 16, False), (3, 5, 9, False), (10, 8, 32, True), (17, 3, 7, True)])
+def test_get_word_step(report, k, h, w, shared):
+    P = O.lively_params(5)
+    eng = engine_with(P)
+    Bn_ann = 1 if shared else k
+    ann = _rand_annotation(7, Bn_ann, h, w)
+    rs = np.random.RandomState(8)
+    hp = np.tanh(rs.randn(k, 256)).astype(np.float32)
+    ap = (rs.rand(k, h, w) * 0.3).astype(np.float32)
+    y = rs.randint(0, 111, size=(k,)).astype(np.int64)
+    ann_d = torch.as_tensor(ann).cuda()
+    fails = []
+    tag = f"get_word_k{k}_{h}x{w}_shared{int(shared)}"
+    for first in (False, True):
+        yy = np.full((k,), -1, np.int64) if first else y
+        probs, word, hn, apn = eng.get_word(yy, hp, ap, ann_d)
+        Pt = O.to_torch(P)
+        ann_ref = t64(ann).expand(k, -1, -1, -1) if shared else t64(ann)
+        rp, rh, rap, _ = O.get_word(Pt, torch.as_tensor(yy), t64(hp), t64(ap), ann_ref)
+        s = "_first" if first else ""
+        _check(report, tag, "probs" + s, probs.cpu().numpy(), rp.numpy(), REL_TOL, fails)
+        _check(report, tag, "h" + s, hn.cpu().numpy(), rh.numpy(), REL_TOL, fails)
+        _check(report, tag, "alpha_past" + s, apn.cpu().numpy(), rap.numpy(), REL_TOL, fails)
+        assert np.array_equal(word.cpu().numpy(), rp.numpy().argmax(1)), "argmax word differs"
+    assert not fails, fails
+
+
+def test_hidden_state_0_and_precompute(report):
+    P = O.lively_params(5)
+    eng = engine_with(P)
+    ann = _rand_annotation(9, 3, 5, 11)
+    am = np.ones((3, 5, 11), np.float32); am[1, 3:, :] = 0; am[2, :, 7:] = 0
+    ann_d = torch.as_tensor(ann).cuda(); am_d = torch.as_tensor(am).cuda()
+    Pt = O.to_torch(P)
+    fails = []
+    _check(report, "precompute", "h0_unmasked", eng.hidden_state_0(ann_d).cpu().numpy(), O.hidden_state_0(Pt, t64(ann)).numpy(), REL_TOL, fails)
+    watch, h0, qf = eng.precompute(ann_d, am_d)
+    mean = (t64(ann) * t64(am)[..., None]).sum((1, 2)) / t64(am).sum((1, 2))[:, None]
+    _check(report, "precompute", "h0_masked", h0.cpu().numpy(), torch.tanh(mean @ Pt["Wa2h"] + Pt["ba2h"]).numpy(), REL_TOL, fails)
+    _check(report, "precompute", "watch", watch.cpu().numpy(), (torch.tensordot(t64(ann), Pt["U_a"], dims=1) + Pt["U_a_b"]).numpy(), REL_TOL, fails)
+    _check(report, "precompute", "qfused", qf.cpu().numpy(), (Pt["alpha_past_filter"].reshape(121, 512) @ Pt["U_f"]).numpy(), REL_TOL, fails)
+    assert not fails, fails
+
+
+def test_greedy_and_beam_sequences_identical(report):
+    P = O.lively_params(6)
+    eng = engine_with(P)
+    fails = []
+    for i, (h, w) in enumerate([(4, 16), (6, 10), (3, 5)]):
+        ann = _rand_annotation(30 + i, 1, h, w)
+        ann_d = torch.as_tensor(ann).cuda()
+        Pt = O.to_torch(P)
+        ref = O.greedy_decode(Pt, t64(ann), 25)
+        toks, lens, _ = eng.greedy_decode(ann_d, 25, check_every=4)
+        got = toks[0, : int(lens[0])].cpu().tolist()
+        ok = got == ref
+        report.add("greedy", f"img{i}", 0.0 if ok else 1.0, 0.0, extra=dict(got=got, ref=ref))
+        if not ok:
+            fails.append(("greedy", got, ref))
+        bref = O.beam_decode(Pt, t64(ann), 10, 12)[0]
+        bgot = eng.get_sample(ann_d, 10, 12)[0]
+        okb = list(bgot) == list(bref)
+        report.add("beam", f"img{i}", 0.0 if okb else 1.0, 0.0, extra=dict(got=list(map(int, bgot)), ref=list(map(int, bref))))
+        if not okb:
+            fails.append(("beam", bgot, bref))
+    # batched greedy == per-image greedy
+    anns = np.concatenate([_rand_annotation(40 + i, 1, 4, 8) for i in range(5)], 0)
+    toks, lens, _ = eng.greedy_decode(torch.as_tensor(anns).cuda(), 15, check_every=0)
+    for i in range(5):
+        ref = O.greedy_decode(O.to_torch(P), t64(anns[i: i + 1]), 15)
+        got = toks[i, : int(lens[i])].cpu().tolist()
+        report.add("greedy_batched", f"img{i}", 0.0 if got == ref else 1.0, 0.0, extra=dict(got=got, ref=ref))
+        if got != ref:
+            fails.append(("greedy_batched", i, got, ref))
+    assert not fails, fails
+
+
+# --------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,h,w,T,drop", [(2, 3, 5, 4, False), (3, 4, 7, 6, True)])
+def test_get_cost_forward(report, B, h, w, T, drop):
+    P = O.lively_params(7)
+    eng = engine_with(P)
+    rs = np.random.RandomState(12)
+    ann = _rand_annotation(13, B, h, w)
+    am = np.ones((B, h, w), np.float32); am[-1, :, w - 2:] = 0
+    lens = rs.randint(1, T, size=B); lens[0] = T - 1
+    y = np.zeros((T, B), np.int64); ym = np.zeros((T, B), np.float32)
+    for b in range(B):
+        y[: lens[b], b] = rs.randint(1, 111, size=lens[b]); ym[: lens[b] + 1, b] = 1
+    seed = 99
+    cost = eng.get_cost(torch.as_tensor(ann).cuda(), y, torch.as_tensor(am).cuda(), ym, dropout=drop, seed=seed)
+    Pt = O.to_torch(P)
+    ref = O.get_cost(Pt, t64(ann), torch.as_tensor(y), t64(am), t64(ym), O.hash_drop_fn(seed) if drop else None)
+    e = abs(float(cost) - float(ref)) / abs(float(ref))
+    report.add("get_cost", f"B{B}_{h}x{w}_T{T}_drop{int(drop)}", e, REL_TOL, extra=dict(got=float(cost), ref=float(ref)))
+    assert e <= REL_TOL, (float(cost), float(ref))
+
+
+@pytest.mark.parametrize("B,H,W,cap,drop", [(2, 32, 48, 3, False), (2, 40, 72, 5, True)])
+def test_full_gradients(report, B, H, W, cap, drop):
+    """Every one of the 329 parameter gradients of cost (no L2) vs fp64 autograd of the oracle."""
+    x, xm, y, ym = make_batch(50 + B, B, H, W, cap, True)
+    P = O.lively_params(8)
+    eng = engine_with(P)
+    seed = 777
+    cost = eng.forward_backward(x, y, xm, ym, dropout=drop, seed=seed)
+    Pt = O.to_torch(P, torch.float64, requires_grad=True)
+    dfn = O.hash_drop_fn(seed) if drop else None
+    ann, am, _ = O.dense_net(Pt, t64(x), t64(xm), True, dfn)
+    ref_cost = O.get_cost(Pt, ann, torch.as_tensor(y), am, t64(ym), dfn)
+    names = O.trainable_names(Pt)
+    grads = torch.autograd.grad(ref_cost, [Pt[n] for n in names])
+    tag = f"grads_B{B}_{H}x{W}_T{cap + 1}_drop{int(drop)}"
+    e = abs(float(cost) - float(ref_cost)) / abs(float(ref_cost))
+    report.add(tag, "cost", e, REL_TOL, extra=dict(got=float(cost), ref=float(ref_cost)))
+    fails = [] if e <= REL_TOL else [("cost", e)]
+    table = {n: (off, shape) for n, off, shape, fl in eng.P.table if not fl & 2}
+    gflat = eng.grads.cpu().numpy()
+    gmax = max(float(g.abs().max()) for g in grads)
+    for n, g in zip(names, grads):
+        off, shape = table[n]
+        got = gflat[off: off + int(np.prod(shape))].reshape(shape)
+        ref = g.numpy()
+        # per-tensor relative error; tensors whose gradient is tiny relative to the largest one are
+        # compared on the global scale (they are dominated by fp32 rounding of large cancelling sums)
+        scale = max(float(np.max(np.abs(ref))), 1e-4 * gmax)
+        err = float(np.max(np.abs(got - ref))) / scale
+        report.add(tag, n, err, 2e-3, extra=dict(ref_max=float(np.max(np.abs(ref)))))
+        if err > 2e-3:
+            fails.append((n, err))
+    assert not fails, fails[:20]
+
+
+def test_adadelta_l2_step(report):
+    lib = _lib(); L = lib.lib()
+    n, nd = 4096, 3000 - 3000 % 4
+    rs = np.random.RandomState(3)
+    p = rs.randn(n).astype(np.float32); g = rs.randn(n).astype(np.float32) * 0.1
+    a = (rs.rand(n) * 0.01).astype(np.float32); u = (rs.rand(n) * 0.001).astype(np.float32)
+    pt, gt, at, ut = [torch.as_tensor(v).cuda() for v in (p, g, a, u)]
+    l2c = torch.zeros(1, dtype=torch.float64, device="cuda")
+    f = C.c_float
+    lib.check(L.wap_adadelta_l2_step(C.c_void_p(torch.cuda.current_stream().cuda_stream), C.c_void_p(pt.data_ptr()), C.c_void_p(gt.data_ptr()),
+                                     C.c_void_p(at.data_ptr()), C.c_void_p(ut.data_ptr()), n, nd, f(0.5), f(0.95), f(1e-8), f(1e-4), f(0.25),
+                                     C.c_void_p(l2c.data_ptr())), "adadelta")
+    gg = g.astype(np.float64) * 0.25; gg[:nd] += 2e-4 * p[:nd].astype(np.float64)
+    a2 = 0.95 * a + 0.05 * gg * gg
+    upd = np.sqrt(u + 1e-8) / np.sqrt(a2 + 1e-8) * gg
+    u2 = 0.95 * u + 0.05 * upd * upd
+    p2 = p - 0.5 * upd
+    fails = []
+    _check(report, "adadelta", "params", pt.cpu().numpy(), p2, 1e-5, fails)
+    _check(report, "adadelta", "accum", at.cpu().numpy(), a2, 1e-5, fails)
+    _check(report, "adadelta", "accum_update", ut.cpu().numpy(), u2, 1e-5, fails)
+    _check(report, "adadelta", "l2_cost", l2c.cpu().numpy(), np.array([1e-4 * np.sum(p[:nd].astype(np.float64) ** 2)]), 1e-5, fails)
+    assert not fails, fails
+
+
+def test_train_steps_match_oracle(report):
+    """Two full optimiser steps (cost incl. L2, updated weights, moving statistics) vs the oracle."""
+    B, H, W, cap = 2, 32, 48, 3
+    P = O.lively_params(9)
+    eng = engine_with(P)
+    names = O.trainable_names(P)
+    acc = {n: np.zeros(P[n].shape, np.float64) for n in names}
+    accd = {n: np.zeros(P[n].shape, np.float64) for n in names}
+    Pn = dict(P)
+    fails = []
+    for step in range(2):
+        x, xm, y, ym = make_batch(60 + step, B, H, W, cap, True)
+        seed = 500 + step
+        cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
+        ref_cost, _, Pn, acc, accd = O.train_step(Pn, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
+        e = abs(cost - ref_cost) / abs(ref_cost)
+        report.add("train_step", f"cost_step{step}", e, REL_TOL, extra=dict(got=cost, ref=ref_cost))
+        if e > REL_TOL:
+            fails.append(("cost", step, cost, ref_cost))
+        sd = eng.P.state_dict()
+        # Adadelta's first steps are ~ sqrt(eps)*sign(g): elements whose gradient is rounding noise may
+        # flip sign, so compare the parameter *change* on the 99.5 % quantile of elements.
+        diffs = []
+        for n in names:
+            d_got = sd[n].astype(np.float64) - P[n]; d_ref = Pn[n].astype(np.float64) - P[n]
+            diffs.append((np.abs(d_got - d_ref) / max(float(np.max(np.abs(d_ref))), 1e-12)).ravel())
+        q = float(np.quantile(np.concatenate(diffs), 0.995))
+        report.add("train_step", f"param_delta_q995_step{step}", q, 2e-2)
+        if q > 2e-2:
+            fails.append(("delta", step, q))
+        mv = max(rel_err(sd[n], Pn[n]) for n in P if n.endswith("moving_variance") or n.endswith("moving_mean"))
+        report.add("train_step", f"moving_stats_step{step}", mv, 5e-3)
+        if mv > 5e-3:
+            fails.append(("moving", step, mv))
+    assert not fails, fails

@@ -1,0 +1,166 @@
+// extern "C" surface of libwap_b200.so (declared in include/wap_abi.h).
+#include <stdarg.h>
+
+#include "../../include/wap_abi.h"
+#include "gemm.cuh"
+#include "model.h"
+
+namespace wap {
+
+static thread_local char g_err[1024] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap; va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int encoder_forward(cudaStream_t st, const float* params, float* moving, const float* x, int B, int H, int W,
+                    int training, int dropout, uint32_t seed, float* annotation, float* wsp);
+int encoder_backward(cudaStream_t st, const float* params, float* grads, const float* x, int B, int H, int W,
+                     int dropout, uint32_t seed, const float* annotation, float* d_annotation, float* wsp);
+int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
+                    float* watch, float* h0, float* qf, float* mean_scratch);
+size_t step_ws_floats(int Bn, int L);
+size_t greedy_ws_floats(int Bn, int L);
+size_t decoder_train_ws_floats(int B, int L, int T);
+int decoder_word_step(cudaStream_t st, const float* params, const float* ann, const float* watch, const float* qf,
+                      const float* a_mask, int shared, int Bn, int h, int w, const int* y, const float* h_prev,
+                      const float* ap_in, float* probs, int* word, float* h_new, float* ap_out, float* wsp);
+int greedy_decode(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen,
+                  int check_every, int* tokens, int* lengths, float* wsp, int* steps_run);
+int decoder_train_forward(cudaStream_t st, const float* params, const float* ann, const float* a_mask, const int* y,
+                          const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
+                          double* cost_out, float* wsp);
+int decoder_train_backward(cudaStream_t st, const float* params, float* grads, const float* ann, const float* a_mask,
+                           const int* y, const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
+                           float* d_ann, float* wsp);
+int adadelta_l2_step(cudaStream_t st, float* p, const float* g, float* acc, float* accu, size_t n, size_t n_decay,
+                     float lr, float rho, float eps, float l2, float gscale, double* l2_cost);
+int mask_subsample(cudaStream_t st, const float* xm, int B, int H, int W, int h, int w, float* am);
+int dropout_mask(cudaStream_t st, uint32_t seed, uint32_t site, size_t n, float* mask);
+
+}  // namespace wap
+
+using namespace wap;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int wap_abi_version(void) { return WAP_ABI_VERSION; }
+const char* wap_last_error(void) { return g_err; }
+
+int wap_param_count(void) { return (int)layout().tensors.size(); }
+int wap_param_info(int index, char* name, int name_cap, int64_t* offset, int* ndim, int64_t dims[4], int* flags) {
+  const ParamLayout& L = layout();
+  WAP_REQUIRE(index >= 0 && index < (int)L.tensors.size(), "wap_param_info: index %d out of range", index);
+  const TensorInfo& t = L.tensors[index];
+  if (name != nullptr && name_cap > 0) { strncpy(name, t.name.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+  if (offset) *offset = (int64_t)t.offset;
+  if (ndim) *ndim = t.ndim;
+  if (dims) for (int i = 0; i < 4; ++i) dims[i] = t.dims[i];
+  if (flags) *flags = t.flags;
+  return 0;
+}
+int64_t wap_param_floats(void) { return (int64_t)layout().n_total; }
+int64_t wap_decay_floats(void) { return (int64_t)layout().n_decay; }
+int64_t wap_moving_floats(void) { return (int64_t)layout().n_moving; }
+
+int wap_annotation_hw(int H, int W, int* h, int* w) {
+  WAP_REQUIRE(H > 0 && W > 0, "wap_annotation_hw: bad size %dx%d", H, W);
+  const EncGeom g = make_geom(1, H, W);
+  if (h) *h = g.h[kBlocks - 1];
+  if (w) *w = g.w[kBlocks - 1];
+  return 0;
+}
+int wap_mask_subsample(void* stream, const float* x_mask, int B, int H, int W, float* a_mask) {
+  const EncGeom g = make_geom(B, H, W);
+  return mask_subsample(ST(stream), x_mask, B, H, W, g.h[kBlocks - 1], g.w[kBlocks - 1], a_mask);
+}
+
+int64_t wap_encoder_workspace_floats(int B, int H, int W, int training) {
+  return (int64_t)make_enc_workspace(make_geom(B, H, W), training != 0).total;
+}
+int wap_encoder_forward(void* stream, const float* params, float* moving, const float* x, int B, int H, int W,
+                        int training, int dropout, uint32_t seed, float* annotation, float* workspace) {
+  WAP_REQUIRE(params && moving && x && workspace && B > 0 && H > 0 && W > 0, "wap_encoder_forward: bad arguments");
+  return encoder_forward(ST(stream), params, moving, x, B, H, W, training, dropout, seed, annotation, workspace);
+}
+int wap_encoder_backward(void* stream, const float* params, float* grads, const float* x, int B, int H, int W,
+                         int dropout, uint32_t seed, const float* annotation, float* d_annotation, float* workspace) {
+  WAP_REQUIRE(params && grads && x && d_annotation && workspace, "wap_encoder_backward: bad arguments");
+  return encoder_backward(ST(stream), params, grads, x, B, H, W, dropout, seed, annotation, d_annotation, workspace);
+}
+
+int wap_attn_precompute(void* stream, const float* params, const float* annotation, const float* a_mask,
+                        int B, int h, int w, float* watch, float* h0, float* qfused, float* scratch) {
+  WAP_REQUIRE(params && annotation && (h0 == nullptr || scratch != nullptr), "wap_attn_precompute: bad arguments");
+  return attn_precompute(ST(stream), params, annotation, a_mask, B, h, w, watch, h0, qfused, scratch);
+}
+
+int64_t wap_decoder_step_workspace_floats(int Bn, int h, int w) { return (int64_t)step_ws_floats(Bn, h * w); }
+int wap_decoder_step(void* stream, const float* params, const float* annotation, const float* watch,
+                     const float* qfused, int shared, int Bn, int h, int w, const int32_t* y,
+                     const float* h_prev, const float* alpha_past, float* probs, int32_t* word,
+                     float* h_new, float* alpha_past_new, float* workspace) {
+  WAP_REQUIRE(params && annotation && watch && qfused && y && h_prev && alpha_past && h_new && alpha_past_new && workspace,
+              "wap_decoder_step: bad arguments");
+  return decoder_word_step(ST(stream), params, annotation, watch, qfused, nullptr, shared, Bn, h, w, y, h_prev, alpha_past,
+                           probs, word, h_new, alpha_past_new, workspace);
+}
+
+int64_t wap_greedy_workspace_floats(int Bn, int h, int w) { return (int64_t)greedy_ws_floats(Bn, h * w); }
+int wap_greedy_decode(void* stream, const float* params, const float* annotation, int Bn, int h, int w,
+                      int maxlen, int check_every, int32_t* tokens, int32_t* lengths, float* workspace, int* steps_run) {
+  WAP_REQUIRE(params && annotation && tokens && lengths && workspace && maxlen > 0, "wap_greedy_decode: bad arguments");
+  return greedy_decode(ST(stream), params, annotation, Bn, h, w, maxlen, check_every, tokens, lengths, workspace, steps_run);
+}
+
+int64_t wap_decoder_train_workspace_floats(int B, int h, int w, int T) { return (int64_t)decoder_train_ws_floats(B, h * w, T); }
+int wap_decoder_train_forward(void* stream, const float* params, const float* annotation, const float* a_mask,
+                              const int32_t* y, const float* y_mask, int B, int h, int w, int T,
+                              int dropout, uint32_t seed, double* cost, float* workspace) {
+  WAP_REQUIRE(params && annotation && y && y_mask && workspace && T > 0, "wap_decoder_train_forward: bad arguments");
+  return decoder_train_forward(ST(stream), params, annotation, a_mask, y, y_mask, B, h, w, T, dropout, seed, cost, workspace);
+}
+int wap_decoder_train_backward(void* stream, const float* params, float* grads, const float* annotation,
+                               const float* a_mask, const int32_t* y, const float* y_mask, int B, int h, int w,
+                               int T, int dropout, uint32_t seed, float* d_annotation, float* workspace) {
+  WAP_REQUIRE(params && grads && annotation && y && y_mask && d_annotation && workspace, "wap_decoder_train_backward: bad arguments");
+  return decoder_train_backward(ST(stream), params, grads, annotation, a_mask, y, y_mask, B, h, w, T, dropout, seed, d_annotation, workspace);
+}
+
+int wap_adadelta_l2_step(void* stream, float* params, const float* grads, float* accum, float* accum_update,
+                         int64_t n, int64_t n_decay, float lr, float rho, float eps, float l2, float grad_scale,
+                         double* l2_cost) {
+  WAP_REQUIRE(params && grads && accum && accum_update && n > 0, "wap_adadelta_l2_step: bad arguments");
+  return adadelta_l2_step(ST(stream), params, grads, accum, accum_update, (size_t)n, (size_t)n_decay, lr, rho, eps, l2, grad_scale, l2_cost);
+}
+
+int wap_gemm_nn(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
+                const float* bias, int accumulate) {
+  return gemm_nn(ST(stream), A, lda, B, ldb, C, ldc, M, N, K, bias, accumulate != 0);
+}
+int wap_gemm_nt(void* stream, const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
+                const float* bias, int accumulate) {
+  return gemm_nt(ST(stream), A, lda, W, ldw, C, ldc, M, N, K, bias, accumulate != 0);
+}
+int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
+  return gemm_tn_atomic(ST(stream), A, lda, B, ldb, C, ldc, M, N, K);
+}
+int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
+  return dropout_mask(ST(stream), seed, site, (size_t)n, mask);
+}
+int64_t wap_encoder_workspace_offset(int B, int H, int W, int training, int what, int arg) {
+  const EncWorkspace ws = make_enc_workspace(make_geom(B, H, W), training != 0);
+  switch (what) {
+    case 0: return (int64_t)ws.stem_raw;
+    case 1: return (arg >= 0 && arg < kBlocks) ? (int64_t)ws.buf[arg] : -1;
+    case 2: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.y1[arg] : -1;
+    case 3: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.a1[arg] : -1;
+    case 4: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.y2[arg] : -1;
+    case 5: return (arg >= 0 && arg < kBlocks - 1) ? (int64_t)ws.ytr[arg] : -1;
+  }
+  return -1;
+}
+
+}  // extern "C"

@@ -1,0 +1,65 @@
+// Decoder ("Attender" + "Parser" + WAP head) building blocks shared by the inference step,
+// the greedy loop and the training scan.  Reference: model-single-GPU.py:166-206 (get_context),
+// :260-308 (one_time_step), :337-375 (get_cost), :379-439 (get_word).
+#pragma once
+#include "gemm.cuh"
+#include "model.h"
+
+namespace wap {
+
+// ---------------------------------------------------------------- skinny GEMM (few rows, streamed weights)
+//   out_s[b, n] += sum_k X[b,k] * W_s[k,n]      for up to 4 weight "segments" sharing the same X.
+// Grid = (column tiles of 256 over all segments) x (K chunks of 16): every CTA streams a distinct
+// 16x256 weight block exactly once with 16 independent 128-bit loads per thread in flight, and
+// adds its partial products with fp32 atomics into outputs pre-initialised with the bias.
+constexpr int kSkRows = 16, kSkKC = 16, kSkCols = 256;
+struct SkinnySeg { const float* W; int ldw, N; float* out; int ldo; };
+struct SkinnyArgs {
+  const float* X; int ldx;      // X[b*ldx + k]   (or gathered rows: table + ids[b]*ldx, zero row if ids[b] < 0)
+  const int* ids;
+  int Bn, K, nseg;
+  SkinnySeg seg[4];
+  int tile0[5];
+};
+int skinny_gemm(cudaStream_t st, SkinnyArgs a);
+
+// ---------------------------------------------------------------- one decoder time step
+struct StepCtx {
+  int Bn, h, w, L;
+  const float* params;
+  const float* ann;     // [Bn,L,684]  (or [1,L,684] when shared)
+  const float* watch;   // [Bn,L,512]  (or [1,L,512] when shared): U_a a + U_a_b, hoisted out of the scan
+  int shared;           // beam search: all rows share one image
+  const float* qf;      // fused coverage filter Q' = Q[121,512] * U_f[512,512]
+  const float* a_mask;  // [Bn,L] or null
+  const float* y_mask;  // [Bn] or null
+  const float* h_prev;  // [Bn,256]
+  const float* ap_in;   // [Bn,L]   alpha_past before this step
+  // activations (saved per step in training)
+  float* G1;            // [Bn,768] in: emb*W_yz_yr+b | emb*W_yh+b ; out: r1 | z1 | (unchanged E_h)
+  float* UH;            // [Bn,256] h*U_rh
+  float* prop1;         // [Bn,256]
+  float* pre_h;         // [Bn,256]
+  float* SP;            // [Bn,512] speller
+  float* G2;            // [Bn,512] r2 | z2
+  float* PH2;           // [Bn,256] pre_h*U_rh_nl + b
+  float* CH;            // [Bn,256] ctx*W_c_h_nl
+  float* prop2;         // [Bn,256]
+  float* COV;           // [Bn*L,512] coverage scratch
+  float* TANH;          // [Bn*L,512] tanh(cov+watch+speller) (may alias COV when not training)
+  float* E;             // [Bn,L]
+  float* alpha;         // [Bn,L]
+  float* ap_out;        // [Bn,L]
+  float* ctx;           // [Bn,684]
+  float* h_new;         // [Bn,256]
+  // optional extra segment on the ctx GEMM (inference logits: ctx*Wc -> LG)
+  SkinnySeg extra_ctx; int has_extra_ctx;
+};
+int decoder_step(cudaStream_t st, const StepCtx& c);
+
+// fills up to 8 row-broadcast segments: dst[b*ld + j] = bias ? bias[j] : 0
+struct FillSeg { float* dst; int ld, n; const float* bias; };
+struct FillArgs { int rows, nseg; FillSeg seg[8]; };
+int fill_rows(cudaStream_t st, const FillArgs& a);
+
+}  // namespace wap

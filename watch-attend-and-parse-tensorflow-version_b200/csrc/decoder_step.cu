@@ -1,0 +1,281 @@
+// Decoder time-step kernels (forward).  See decoder.cuh for the data flow.
+#include "decoder.cuh"
+
+namespace wap {
+
+// =====================================================================================
+// skinny GEMM
+// =====================================================================================
+__global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
+  __shared__ float xs[kSkRows][kSkKC];
+  int s = 0;
+  while (s + 1 < a.nseg && (int)blockIdx.x >= a.tile0[s + 1]) ++s;
+  const SkinnySeg sg = a.seg[s];
+  const int n = ((int)blockIdx.x - a.tile0[s]) * kSkCols + threadIdx.x * 4;
+  const int k0 = blockIdx.y * kSkKC;
+  const bool vec = ((sg.ldw & 3) == 0) && (n + 3 < sg.N);
+  float4 wv[kSkKC];
+#pragma unroll
+  for (int kk = 0; kk < kSkKC; ++kk) {
+    const int k = k0 + kk;
+    float4 v = make4(0.f);
+    if (k < a.K && n < sg.N) {
+      const float* q = sg.W + (size_t)k * sg.ldw + n;
+      if (vec) v = ldg4(q);
+      else {
+        v.x = __ldg(q);
+        if (n + 1 < sg.N) v.y = __ldg(q + 1);
+        if (n + 2 < sg.N) v.z = __ldg(q + 2);
+        if (n + 3 < sg.N) v.w = __ldg(q + 3);
+      }
+    }
+    wv[kk] = v;
+  }
+  for (int b0 = 0; b0 < a.Bn; b0 += kSkRows) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < kSkRows * kSkKC; i += 64) {
+      const int bb = i / kSkKC, kk = i % kSkKC;
+      const int b = b0 + bb, k = k0 + kk;
+      float v = 0.f;
+      if (b < a.Bn && k < a.K) {
+        if (a.ids != nullptr) { const int id = a.ids[b]; if (id >= 0) v = __ldg(a.X + (size_t)id * a.ldx + k); }
+        else v = __ldg(a.X + (size_t)b * a.ldx + k);
+      }
+      xs[bb][kk] = v;
+    }
+    __syncthreads();
+    if (n < sg.N) {
+#pragma unroll 4
+      for (int bb = 0; bb < kSkRows; ++bb) {
+        if (b0 + bb >= a.Bn) break;
+        float4 acc = make4(0.f);
+#pragma unroll
+        for (int kk = 0; kk < kSkKC; ++kk) {
+          const float x = xs[bb][kk];
+          acc.x = fmaf(x, wv[kk].x, acc.x); acc.y = fmaf(x, wv[kk].y, acc.y);
+          acc.z = fmaf(x, wv[kk].z, acc.z); acc.w = fmaf(x, wv[kk].w, acc.w);
+        }
+        float* o = sg.out + (size_t)(b0 + bb) * sg.ldo + n;
+        atomicAdd(o, acc.x);
+        if (n + 1 < sg.N) atomicAdd(o + 1, acc.y);
+        if (n + 2 < sg.N) atomicAdd(o + 2, acc.z);
+        if (n + 3 < sg.N) atomicAdd(o + 3, acc.w);
+      }
+    }
+  }
+}
+
+int skinny_gemm(cudaStream_t st, SkinnyArgs a) {
+  WAP_REQUIRE(a.nseg >= 1 && a.nseg <= 4, "skinny_gemm: nseg=%d", a.nseg);
+  a.tile0[0] = 0;
+  for (int s = 0; s < a.nseg; ++s) a.tile0[s + 1] = a.tile0[s] + cdiv(a.seg[s].N, kSkCols);
+  dim3 grid(a.tile0[a.nseg], cdiv(a.K, kSkKC));
+  skinny_gemm_kernel<<<grid, 64, 0, st>>>(a);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================
+// row-broadcast fill (bias initialisation of the atomically-accumulated outputs)
+// =====================================================================================
+__global__ void __launch_bounds__(256) fill_rows_kernel(const FillArgs a) {
+  const FillSeg sg = a.seg[blockIdx.y];
+  const int total = a.rows * sg.n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / sg.n, j = i - b * sg.n;
+    sg.dst[(size_t)b * sg.ld + j] = sg.bias != nullptr ? __ldg(sg.bias + j) : 0.f;
+  }
+}
+int fill_rows(cudaStream_t st, const FillArgs& a) {
+  int mx = 1;
+  for (int s = 0; s < a.nseg; ++s) mx = max(mx, a.rows * a.seg[s].n);
+  dim3 grid(min(cdiv(mx, 256), 64), a.nseg);
+  fill_rows_kernel<<<grid, 256, 0, st>>>(a);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================
+// GRU-1 gates (S:273-289): r1|z1 = sigmoid(G1[:, :512]); prop = tanh(UH*r1 + E_h);
+// pre_h = z1*h + (1-z1)*prop, blended with the caption mask.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+gru1_gate_kernel(float* __restrict__ G1, const float* __restrict__ UH, const float* __restrict__ h_prev,
+                 const float* __restrict__ y_mask, float* __restrict__ prop1, float* __restrict__ pre_h, int Bn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * kN) return;
+  const int b = i / kN, j = i - b * kN;
+  float* g = G1 + (size_t)b * 3 * kN;
+  const float r = sigmoidf_(g[j]), z = sigmoidf_(g[kN + j]);
+  g[j] = r; g[kN + j] = z;
+  const float p = tanhf(fmaf(UH[i], r, g[2 * kN + j]));
+  const float h = h_prev[i];
+  float ph = z * h + (1.f - z) * p;
+  if (y_mask != nullptr) { const float m = y_mask[b]; ph = m * ph + (1.f - m) * h; }
+  prop1[i] = p; pre_h[i] = ph;
+}
+
+// GRU-2 gates (S:292-306)
+__global__ void __launch_bounds__(256)
+gru2_gate_kernel(float* __restrict__ G2, const float* __restrict__ PH2, const float* __restrict__ CH,
+                 const float* __restrict__ pre_h, const float* __restrict__ y_mask,
+                 float* __restrict__ prop2, float* __restrict__ h_new, int Bn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * kN) return;
+  const int b = i / kN, j = i - b * kN;
+  float* g = G2 + (size_t)b * 2 * kN;
+  const float r = sigmoidf_(g[j]), z = sigmoidf_(g[kN + j]);
+  g[j] = r; g[kN + j] = z;
+  const float p = tanhf(fmaf(PH2[i], r, CH[i]));
+  const float ph = pre_h[i];
+  float h = z * ph + (1.f - z) * p;
+  if (y_mask != nullptr) { const float m = y_mask[b]; h = m * h + (1.f - m) * ph; }
+  prop2[i] = p; h_new[i] = h;
+}
+
+// =====================================================================================
+// attention energies (S:185-188): e[b,l] = V_a . tanh(cov[b,l,:] + watch[b,l,:] + speller[b,:]) + V_a_b
+// one warp per annotation position; 128-bit loads; warp-shuffle reduction.
+// =====================================================================================
+__global__ void __launch_bounds__(256)
+energy_kernel(const float* COV, const float* __restrict__ watch, const float* __restrict__ SP,
+              const float* __restrict__ Va, const float* __restrict__ Vab, float* TANH,
+              float* __restrict__ E, int Bn, int L, int shared) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Bn * L) return;
+  const int b = warp / L, l = warp - b * L;
+  const float* cv = COV + (size_t)warp * kNA;
+  const float* wt = watch + (size_t)(shared ? l : warp) * kNA;
+  const float* sp = SP + (size_t)b * kNA;
+  float* th = TANH + (size_t)warp * kNA;
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < kNA / 128; ++q) {
+    const int c = q * 128 + lane * 4;
+    const float4 a = *reinterpret_cast<const float4*>(cv + c);
+    const float4 w4 = ldg4(wt + c), p4 = ldg4(sp + c), v4 = ldg4(Va + c);
+    float4 t;
+    t.x = tanhf(a.x + w4.x + p4.x); t.y = tanhf(a.y + w4.y + p4.y);
+    t.z = tanhf(a.z + w4.z + p4.z); t.w = tanhf(a.w + w4.w + p4.w);
+    *reinterpret_cast<float4*>(th + c) = t;
+    s = fmaf(t.x, v4.x, s); s = fmaf(t.y, v4.y, s); s = fmaf(t.z, v4.z, s); s = fmaf(t.w, v4.w, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) E[warp] = s + __ldg(Vab);
+}
+
+// =====================================================================================
+// masked softmax over the L positions of one image + alpha_past update + context (S:190-203)
+// grid = (ceil(684/64), Bn); every CTA recomputes the (cheap) softmax and owns 64 context channels.
+// =====================================================================================
+constexpr int kCtxChunk = 64;
+__global__ void __launch_bounds__(256)
+softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask, const float* __restrict__ ap_in,
+                   const float* __restrict__ ann, float* __restrict__ alpha, float* __restrict__ ap_out,
+                   float* __restrict__ ctx, int L, int shared) {
+  extern __shared__ float sm[];          // alpha[L] | red[64] | part[16][64]
+  float* s_alpha = sm;
+  float* red = sm + L;
+  float* part = red + 64;
+  const int b = blockIdx.y, tid = threadIdx.x;
+  const float* e = E + (size_t)b * L;
+  const float* mk = a_mask != nullptr ? a_mask + (size_t)b * L : nullptr;
+  float mx = -INFINITY;
+  for (int l = tid; l < L; l += 256) if (mk == nullptr || mk[l] != 0.f) mx = fmaxf(mx, e[l]);
+  mx = block_max(mx, red);
+  float sum = 0.f;
+  for (int l = tid; l < L; l += 256) {
+    float u = 0.f;
+    if (mk == nullptr) u = expf(e[l] - mx);
+    else if (mk[l] != 0.f) u = expf(e[l] - mx) * mk[l];
+    s_alpha[l] = u; sum += u;
+  }
+  sum = block_sum(sum, red);
+  const float inv = 1.f / sum;
+  for (int l = tid; l < L; l += 256) {
+    const float al = s_alpha[l] * inv;
+    s_alpha[l] = al;
+    if (blockIdx.x == 0) { alpha[(size_t)b * L + l] = al; ap_out[(size_t)b * L + l] = ap_in[(size_t)b * L + l] + al; }
+  }
+  __syncthreads();
+  const int c0 = blockIdx.x * kCtxChunk;
+  const int cq = tid & 15, lg = tid >> 4;            // 16 float4 lanes x 16 position groups
+  const int c = c0 + cq * 4;
+  float4 acc = make4(0.f);
+  if (c < kD) {
+    const float* base = ann + (size_t)(shared ? 0 : b) * L * kD + c;
+    for (int l = lg; l < L; l += 16) {
+      const float4 v = ldg4(base + (size_t)l * kD);
+      const float al = s_alpha[l];
+      acc.x = fmaf(al, v.x, acc.x); acc.y = fmaf(al, v.y, acc.y); acc.z = fmaf(al, v.z, acc.z); acc.w = fmaf(al, v.w, acc.w);
+    }
+  }
+  *reinterpret_cast<float4*>(&part[lg * 64 + cq * 4]) = acc;
+  __syncthreads();
+  if (tid < kCtxChunk && c0 + tid < kD) {
+    float s = 0.f;
+#pragma unroll
+    for (int g = 0; g < 16; ++g) s += part[g * 64 + tid];
+    ctx[(size_t)b * kD + c0 + tid] = s;
+  }
+}
+
+// =====================================================================================
+// one full decoder step
+// =====================================================================================
+int decoder_step(cudaStream_t st, const StepCtx& c) {
+  const ParamLayout& P = layout();
+  const float* p = c.params;
+  const int Bn = c.Bn, L = c.L;
+  {   // bias-initialise the atomically accumulated buffers of this step
+    FillArgs f; f.rows = Bn; f.nseg = 5;
+    f.seg[0] = {c.UH, kN, kN, nullptr};
+    f.seg[1] = {c.SP, kNA, kNA, p + P.W_a_b};
+    f.seg[2] = {c.G2, 2 * kN, 2 * kN, p + P.b_hz_hr_nl};
+    f.seg[3] = {c.PH2, kN, kN, p + P.b_rh_nl};
+    f.seg[4] = {c.CH, kN, kN, nullptr};
+    WAP_TRY(fill_rows(st, f));
+  }
+  {   // h_prev * [U_hz_hr | U_rh]
+    SkinnyArgs a; a.X = c.h_prev; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 2;
+    a.seg[0] = {p + P.U_hz_hr, 2 * kN, 2 * kN, c.G1, 3 * kN};
+    a.seg[1] = {p + P.U_rh, kN, kN, c.UH, kN};
+    WAP_TRY(skinny_gemm(st, a));
+  }
+  gru1_gate_kernel<<<cdiv(Bn * kN, 256), 256, 0, st>>>(c.G1, c.UH, c.h_prev, c.y_mask, c.prop1, c.pre_h, Bn);
+  WAP_LAUNCH_CHECK();
+  {   // pre_h * [W_a | U_hz_hr_nl | U_rh_nl]
+    SkinnyArgs a; a.X = c.pre_h; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 3;
+    a.seg[0] = {p + P.W_a, kNA, kNA, c.SP, kNA};
+    a.seg[1] = {p + P.U_hz_hr_nl, 2 * kN, 2 * kN, c.G2, 2 * kN};
+    a.seg[2] = {p + P.U_rh_nl, kN, kN, c.PH2, kN};
+    WAP_TRY(skinny_gemm(st, a));
+  }
+  {   // coverage: COV[Bn*L,512] = patches(alpha_past)[Bn*L,121] * Q'[121,512]   (+ U_f_b)
+    ACovPatch A{c.ap_in, Bn, c.h, c.w};
+    BRowMajor Bq{c.qf, kNA, kCovTaps, kNA};
+    EpiStore e{c.COV, kNA, p + P.U_f_b, false, nullptr};
+    WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bq, e, Bn * L, kNA, 124)));
+  }
+  energy_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(c.COV, c.watch, c.SP, p + P.V_a, p + P.V_a_b, c.TANH, c.E, Bn, L, c.shared);
+  WAP_LAUNCH_CHECK();
+  {
+    const size_t smem = sizeof(float) * (L + 64 + 16 * 64);
+    WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large for softmax_ctx_kernel: L=%d", L);
+    dim3 grid(cdiv(kD, kCtxChunk), Bn);
+    softmax_ctx_kernel<<<grid, 256, smem, st>>>(c.E, c.a_mask, c.ap_in, c.ann, c.alpha, c.ap_out, c.ctx, L, c.shared);
+    WAP_LAUNCH_CHECK();
+  }
+  {   // ctx * [W_c_z_r | W_c_h_nl (| Wc)]
+    SkinnyArgs a; a.X = c.ctx; a.ldx = kD; a.ids = nullptr; a.Bn = Bn; a.K = kD; a.nseg = 2;
+    a.seg[0] = {p + P.W_c_z_r, 2 * kN, 2 * kN, c.G2, 2 * kN};
+    a.seg[1] = {p + P.W_c_h_nl, kN, kN, c.CH, kN};
+    if (c.has_extra_ctx) { a.seg[2] = c.extra_ctx; a.nseg = 3; }
+    WAP_TRY(skinny_gemm(st, a));
+  }
+  gru2_gate_kernel<<<cdiv(Bn * kN, 256), 256, 0, st>>>(c.G2, c.PH2, c.CH, c.pre_h, c.y_mask, c.prop2, c.h_new, Bn);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wap

@@ -1,0 +1,524 @@
+// Training-side decoder: WAP.get_cost forward (model-single-GPU.py:337-375: embedding shift, h0,
+// tf.scan over Parser.one_time_step, logits/maxout/dropout/softmax-CE) and its backward (BPTT
+// through the coverage attention).
+//
+// Formulation differences from the reference graph that do not change the mathematics:
+//   * U_a*a (+b) is hoisted out of the scan (the reference recomputes it every step, S:177);
+//   * coverage conv (S:171) and U_f projection (S:173) are fused into one 121-tap filter
+//     Q' = Q*U_f, recomputed from the current weights at every call; gradients are mapped back
+//     with dQ = dQ'*U_f^T, dU_f = Q^T*dQ';
+//   * every weight gradient is ONE GEMM over all T*B rows after the time loop instead of T
+//     rank-B updates inside it; only the data gradients stay in the sequential loop.
+#include <algorithm>
+
+#include "decoder.cuh"
+
+namespace wap {
+
+size_t step_ws_floats(int Bn, int L);
+int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
+                    float* watch, float* h0, float* qf, float* mean_scratch);
+
+// ------------------------------------------------------------------------------------ workspace
+struct DecTrainWs {
+  // forward (saved)
+  float *EMB, *G1, *H, *UH, *PROP1, *PREH, *SP, *G2, *PH2, *CH, *PROP2, *TANH, *ALPHA, *AP, *CTX;
+  float *watch, *qf, *mean, *COV, *E, *LG, *MO, *LO;
+  double* cost;
+  // backward
+  float *dLG, *dMO, *dHlog, *dCTX, *dEMB, *dG1, *dEh, *dUH, *dSP, *dG2, *dCH, *dPH2, *DZ, *dWatch, *DF;
+  float *dAP0, *dAP1, *dalpha, *de, *dh0, *dh1, *dpre_h, *dQf, *dmean;
+  float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
+};
+static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
+  DecTrainWs w; size_t o = 0;
+  auto take = [&](size_t n) { float* p = base + o; o += (n + 3) & ~(size_t)3; return p; };
+  const size_t TB = (size_t)T * B, BL = (size_t)B * L;
+  w.cost = reinterpret_cast<double*>(take(4));
+  w.EMB = take(TB * kMw); w.G1 = take(TB * 3 * kN); w.H = take((TB + B) * kN); w.UH = take(TB * kN);
+  w.PROP1 = take(TB * kN); w.PREH = take(TB * kN); w.SP = take(TB * kNA); w.G2 = take(TB * 2 * kN);
+  w.PH2 = take(TB * kN); w.CH = take(TB * kN); w.PROP2 = take(TB * kN); w.TANH = take(TB * L * kNA);
+  w.ALPHA = take(TB * L); w.AP = take((TB + B) * L); w.CTX = take(TB * kD);
+  w.watch = take(BL * kNA); w.qf = take((size_t)kCovTaps * kNA); w.mean = take((size_t)B * kD);
+  w.COV = take(BL * kNA); w.E = take(BL); w.LG = take(TB * kMw); w.MO = take(TB * kMw / 2); w.LO = take(TB * kVocab);
+  w.dLG = take(TB * kMw); w.dMO = take(TB * kMw / 2); w.dHlog = take(TB * kN); w.dCTX = take(TB * kD); w.dEMB = take(TB * kMw);
+  w.dG1 = take(TB * 2 * kN); w.dEh = take(TB * kN); w.dUH = take(TB * kN); w.dSP = take(TB * kNA); w.dG2 = take(TB * 2 * kN);
+  w.dCH = take(TB * kN); w.dPH2 = take(TB * kN); w.DZ = take(TB * L * kNA); w.dWatch = take(BL * kNA); w.DF = take(BL * 124);
+  w.dAP0 = take(BL); w.dAP1 = take(BL); w.dalpha = take(BL); w.de = take(BL);
+  w.dh0 = take((size_t)B * kN); w.dh1 = take((size_t)B * kN); w.dpre_h = take((size_t)B * kN);
+  w.dQf = take((size_t)kCovTaps * kNA); w.dmean = take((size_t)B * kD);
+  w.T_Wczr = take((size_t)2 * kN * kD); w.T_Wchnl = take((size_t)kN * kD); w.T_Uhzhrnl = take((size_t)2 * kN * kN);
+  w.T_Urhnl = take((size_t)kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
+  if (total != nullptr) *total = o;
+  return w;
+}
+size_t decoder_train_ws_floats(int B, int L, int T) { size_t t; carve_train(nullptr, B, L, T, &t); return t; }
+
+// ------------------------------------------------------------------------------------ small kernels
+// EMB[t,b,:] = t == 0 ? 0 : embed[y[t-1,b]]   (S:340-343)
+__global__ void emb_shift_kernel(const float* __restrict__ embed, const int* __restrict__ y, float* __restrict__ EMB, int T, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * B * kMw) return;
+  const int j = i % kMw, r = i / kMw, t = r / B;
+  EMB[i] = (t == 0) ? 0.f : __ldg(embed + (size_t)y[r - B] * kMw + j);
+}
+__global__ void emb_scatter_kernel(const float* __restrict__ dEMB, const int* __restrict__ y, float* __restrict__ dembed, int T, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T * B * kMw) return;
+  const int j = i % kMw, r = i / kMw, t = r / B;
+  if (t > 0) atomicAdd(dembed + (size_t)y[r - B] * kMw + j, dEMB[i]);
+}
+__global__ void bias3_rows_kernel(float* LG, int rows, const float* by, const float* bc, const float* bh) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < rows * kMw) { const int j = i % kMw; LG[i] = by[j] + bc[j] + bh[j]; }
+}
+// maxout over adjacent pairs + dropout (site kNumConv) (S:359-362)
+__global__ void maxout_drop_kernel(const float* __restrict__ LG, float* __restrict__ MO, int rows, int dropout, uint32_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (kMw / 2)) return;
+  const float2 v = *reinterpret_cast<const float2*>(LG + 2 * (size_t)i);
+  float m = fmaxf(v.x, v.y);
+  if (dropout) m = drop_keep(seed, kNumConv, (uint32_t)i) ? m * (1.f / (1.f - kDropRate)) : 0.f;
+  MO[i] = m;
+}
+__global__ void maxout_drop_bwd_kernel(const float* __restrict__ LG, const float* __restrict__ dMO, float* __restrict__ dLG,
+                                       int rows, int dropout, uint32_t seed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (kMw / 2)) return;
+  const float2 v = *reinterpret_cast<const float2*>(LG + 2 * (size_t)i);
+  float g = dMO[i];
+  if (dropout) g = drop_keep(seed, kNumConv, (uint32_t)i) ? g * (1.f / (1.f - kDropRate)) : 0.f;
+  float2 o = (v.x >= v.y) ? make_float2(g, 0.f) : make_float2(0.f, g);
+  *reinterpret_cast<float2*>(dLG + 2 * (size_t)i) = o;
+}
+// LO[r,j] = bo[j] + sum_i MO[r,i] Wo[i,j]
+__global__ void wo_fwd_kernel(const float* __restrict__ MO, const float* __restrict__ Wo, const float* __restrict__ bo,
+                              float* __restrict__ LO, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * kVocab) return;
+  const int r = i / kVocab, j = i - r * kVocab;
+  float s = __ldg(bo + j);
+  const float* m = MO + (size_t)r * (kMw / 2);
+#pragma unroll 8
+  for (int k = 0; k < kMw / 2; ++k) s = fmaf(m[k], __ldg(Wo + k * kVocab + j), s);
+  LO[i] = s;
+}
+__global__ void wo_bwd_data_kernel(const float* __restrict__ dLO, const float* __restrict__ Wo, float* __restrict__ dMO, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * (kMw / 2)) return;
+  const int r = i / (kMw / 2), k = i - r * (kMw / 2);
+  const float* d = dLO + (size_t)r * kVocab; const float* wr = Wo + (size_t)k * kVocab;
+  float s = 0.f;
+  for (int j = 0; j < kVocab; ++j) s = fmaf(d[j], __ldg(wr + j), s);
+  dMO[i] = s;
+}
+__global__ void wo_bwd_weight_kernel(const float* __restrict__ MO, const float* __restrict__ dLO, float* __restrict__ dWo,
+                                     float* __restrict__ dbo, int rows) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (kMw / 2 + 1) * kVocab) return;
+  const int k = i / kVocab, j = i - k * kVocab;
+  float s = 0.f;
+  if (k < kMw / 2) { for (int r = 0; r < rows; ++r) s = fmaf(MO[(size_t)r * (kMw / 2) + k], dLO[(size_t)r * kVocab + j], s); dWo[i] += s; }
+  else { for (int r = 0; r < rows; ++r) s += dLO[(size_t)r * kVocab + j]; dbo[j] += s; }
+}
+// softmax cross-entropy (S:368-374): cost += mask*CE/B ; dLO = mask/B*(softmax - onehot) in place.  warp per row.
+__global__ void __launch_bounds__(256)
+ce_kernel(float* __restrict__ LO, const int* __restrict__ y, const float* __restrict__ y_mask, double* __restrict__ cost,
+          int rows, int B, float grad_scale) {
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float* lo = LO + (size_t)r * kVocab;
+  float v[4]; float mx = -INFINITY;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const int j = q * 32 + lane; v[q] = j < kVocab ? lo[j] : -INFINITY; mx = fmaxf(mx, v[q]); }
+  mx = warp_max(mx);
+  float s = 0.f;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const int j = q * 32 + lane; if (j < kVocab) s += expf(v[q] - mx); }
+  s = warp_sum(s);
+  const float lse = mx + logf(s);
+  const int tgt = y[r];
+  const float m = y_mask[r];
+  if (lane == 0) atomicAdd(cost, (double)(m * (lse - lo[tgt]) / (float)B));
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int j = q * 32 + lane;
+    if (j < kVocab) lo[j] = grad_scale * m / (float)B * (expf(v[q] - lse) - (j == tgt ? 1.f : 0.f));
+  }
+}
+// column sums: out[j] += sum_r X[r*ld + j]
+__global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int rows, int n, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
+  float s = 0.f;
+  for (int r = r0; r < r1; ++r) s += X[(size_t)r * ld + j];
+  atomicAdd(out + j, s);
+}
+static int colsum(cudaStream_t st, const float* X, int ld, int rows, int n, float* out) {
+  colsum_kernel<<<dim3(cdiv(n, 256), cdiv(rows, 64)), 256, 0, st>>>(X, ld, rows, n, out);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+  __shared__ float t[32][33];
+  const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) if (r0 + i < R && c < C) t[i][threadIdx.x] = src[(size_t)(r0 + i) * C + c];
+  __syncthreads();
+  const int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8) if (c0 + i < C && r < R) dst[(size_t)(c0 + i) * R + r] = t[threadIdx.x][i];
+}
+static int transpose(cudaStream_t st, const float* src, float* dst, int R, int C) {
+  transpose_kernel<<<dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(src, dst, R, C);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+__global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] = src[i];
+}
+__global__ void add_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dst[i] += src[i];
+}
+
+// ------------------------------------------------------------------------------------ forward
+int decoder_train_forward(cudaStream_t st, const float* params, const float* ann, const float* a_mask, const int* y,
+                          const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
+                          double* cost_out, float* wsp) {
+  const ParamLayout& P = layout();
+  const int L = h * w, TB = T * B;
+  DecTrainWs W = carve_train(wsp, B, L, T, nullptr);
+  WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, W.watch, W.H, W.qf, W.mean));   // H[0] = h0 (masked mean, S:345-347)
+  emb_shift_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(params + P.embed, y, W.EMB, T, B);
+  WAP_LAUNCH_CHECK();
+  // emb-dependent GRU-1 pre-activations for all steps at once
+  WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yz_yr, 2 * kN, W.G1, 3 * kN, TB, 2 * kN, kMw, params + P.b_yz_yr, false));
+  WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yh, kN, W.G1 + 2 * kN, 3 * kN, TB, kN, kMw, params + P.b_yh, false));
+  WAP_CHECK(cudaMemsetAsync(W.AP, 0, sizeof(float) * B * L, st));
+  for (int t = 0; t < T; ++t) {
+    const size_t r = (size_t)t * B;
+    StepCtx c;
+    c.Bn = B; c.h = h; c.w = w; c.L = L; c.params = params; c.ann = ann; c.watch = W.watch; c.shared = 0; c.qf = W.qf;
+    c.a_mask = a_mask; c.y_mask = y_mask + r; c.h_prev = W.H + r * kN; c.ap_in = W.AP + r * L;
+    c.G1 = W.G1 + r * 3 * kN; c.UH = W.UH + r * kN; c.prop1 = W.PROP1 + r * kN; c.pre_h = W.PREH + r * kN;
+    c.SP = W.SP + r * kNA; c.G2 = W.G2 + r * 2 * kN; c.PH2 = W.PH2 + r * kN; c.CH = W.CH + r * kN; c.prop2 = W.PROP2 + r * kN;
+    c.COV = W.COV; c.TANH = W.TANH + r * L * kNA; c.E = W.E; c.alpha = W.ALPHA + r * L; c.ap_out = W.AP + (r + B) * L;
+    c.ctx = W.CTX + r * kD; c.h_new = W.H + (r + B) * kN; c.has_extra_ctx = 0;
+    WAP_TRY(decoder_step(st, c));
+  }
+  // logits for all steps (S:354-364)
+  bias3_rows_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(W.LG, TB, params + P.by, params + P.bc, params + P.bh);
+  WAP_LAUNCH_CHECK();
+  WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
+  WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
+  WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.Wy, kMw, W.LG, kMw, TB, kMw, kMw, nullptr, true));
+  maxout_drop_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.MO, TB, dropout, seed);
+  WAP_LAUNCH_CHECK();
+  wo_fwd_kernel<<<cdiv(TB * kVocab, 256), 256, 0, st>>>(W.MO, params + P.Wo, params + P.bo, W.LO, TB);
+  WAP_LAUNCH_CHECK();
+  WAP_CHECK(cudaMemsetAsync(W.cost, 0, sizeof(double), st));
+  ce_kernel<<<cdiv(TB * 32, 256), 256, 0, st>>>(W.LO, y, y_mask, W.cost, TB, B, 1.f);
+  WAP_LAUNCH_CHECK();
+  if (cost_out != nullptr) WAP_CHECK(cudaMemcpyAsync(cost_out, W.cost, sizeof(double), cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------ backward kernels
+// GRU-2 backward (elementwise).  dh_in: carry; dHlog: logit-path gradient of h_t.
+__global__ void __launch_bounds__(256)
+gru2_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dHlog, const float* __restrict__ G2,
+                const float* __restrict__ prop2, const float* __restrict__ PH2, const float* __restrict__ pre_h,
+                const float* __restrict__ y_mask, float* __restrict__ dG2, float* __restrict__ dCH, float* __restrict__ dPH2,
+                float* __restrict__ dpre_h, int Bn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * kN) return;
+  const int b = i / kN, j = i - b * kN;
+  const float m = y_mask != nullptr ? y_mask[b] : 1.f;
+  const float dh = dh_in[i] + dHlog[i];
+  const float r = G2[(size_t)b * 2 * kN + j], z = G2[(size_t)b * 2 * kN + kN + j];
+  const float p = prop2[i], ph = pre_h[i];
+  const float dhn = m * dh;
+  const float dz = dhn * (ph - p), dp = dhn * (1.f - z);
+  const float dpp = dp * (1.f - p * p);
+  dCH[i] = dpp;
+  dPH2[i] = dpp * r;
+  const float dr = dpp * PH2[i];
+  dG2[(size_t)b * 2 * kN + j] = dr * r * (1.f - r);
+  dG2[(size_t)b * 2 * kN + kN + j] = dz * z * (1.f - z);
+  dpre_h[i] = (1.f - m) * dh + dhn * z;
+}
+// GRU-1 backward (elementwise)
+__global__ void __launch_bounds__(256)
+gru1_bwd_kernel(const float* __restrict__ dpre_h, const float* __restrict__ G1, const float* __restrict__ prop1,
+                const float* __restrict__ UH, const float* __restrict__ h_prev, const float* __restrict__ y_mask,
+                float* __restrict__ dG1, float* __restrict__ dEh, float* __restrict__ dUH, float* __restrict__ dh_out, int Bn) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * kN) return;
+  const int b = i / kN, j = i - b * kN;
+  const float m = y_mask != nullptr ? y_mask[b] : 1.f;
+  const float d = dpre_h[i];
+  const float r = G1[(size_t)b * 3 * kN + j], z = G1[(size_t)b * 3 * kN + kN + j];
+  const float p = prop1[i], h = h_prev[i];
+  const float dp_ = m * d;
+  const float dz = dp_ * (h - p), dprop = dp_ * (1.f - z);
+  const float dpp = dprop * (1.f - p * p);
+  dEh[i] = dpp;
+  dUH[i] = dpp * r;
+  const float dr = dpp * UH[i];
+  dG1[(size_t)b * 2 * kN + j] = dr * r * (1.f - r);
+  dG1[(size_t)b * 2 * kN + kN + j] = dz * z * (1.f - z);
+  dh_out[i] = (1.f - m) * d + dp_ * z;
+}
+// d alpha[b,l] = a[b,l,:] . dctx[b,:] + dAP[b,l]    (warp per position)
+__global__ void __launch_bounds__(256)
+dalpha_kernel(const float* __restrict__ ann, const float* __restrict__ dctx, const float* __restrict__ dAP,
+              float* __restrict__ dalpha, int Bn, int L) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= Bn * L) return;
+  const int b = warp / L;
+  const float* a = ann + (size_t)warp * kD; const float* d = dctx + (size_t)b * kD;
+  float s = 0.f;
+  for (int c = lane * 4; c < kD; c += 128) {
+    const float4 av = ldg4(a + c), dv = ldg4(d + c);
+    s = fmaf(av.x, dv.x, s); s = fmaf(av.y, dv.y, s); s = fmaf(av.z, dv.z, s); s = fmaf(av.w, dv.w, s);
+  }
+  s = warp_sum(s);
+  if (lane == 0) dalpha[warp] = s + dAP[warp];
+}
+// softmax backward per image: de = alpha * (dalpha - sum(alpha*dalpha))
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha, float* __restrict__ de, int L) {
+  __shared__ float red[33];
+  const int b = blockIdx.x;
+  float s = 0.f;
+  for (int l = threadIdx.x; l < L; l += 256) s = fmaf(alpha[(size_t)b * L + l], dalpha[(size_t)b * L + l], s);
+  s = block_sum(s, red);
+  for (int l = threadIdx.x; l < L; l += 256) { const float a = alpha[(size_t)b * L + l]; de[(size_t)b * L + l] = a * (dalpha[(size_t)b * L + l] - s); }
+}
+// dz[b,l,c] = de[b,l] * V_a[c] * (1 - tanh^2)  -> DZ, dWatch += dz, dSP[b,c] += sum_l dz, dV_a[c] += sum de*tanh, dV_a_b += sum de
+constexpr int kDzPix = 8;
+__global__ void __launch_bounds__(128)
+dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const float* __restrict__ Va,
+          float* __restrict__ DZ, float* __restrict__ dWatch, float* __restrict__ dSP, float* __restrict__ dVa,
+          float* __restrict__ dVab, int L) {
+  const int b = blockIdx.y, l0 = blockIdx.x * kDzPix, c = threadIdx.x * 4;
+  const float4 va = ldg4(Va + c);
+  float4 sp = make4(0.f), dv = make4(0.f);
+  float sde = 0.f;
+  for (int l = l0; l < min(L, l0 + kDzPix); ++l) {
+    const size_t row = (size_t)b * L + l;
+    const float d = de[row];
+    const float4 t = ldg4(TANH + row * kNA + c);
+    float4 z;
+    z.x = d * va.x * (1.f - t.x * t.x); z.y = d * va.y * (1.f - t.y * t.y);
+    z.z = d * va.z * (1.f - t.z * t.z); z.w = d * va.w * (1.f - t.w * t.w);
+    *reinterpret_cast<float4*>(DZ + row * kNA + c) = z;
+    float4 wv = *reinterpret_cast<float4*>(dWatch + row * kNA + c);
+    wv.x += z.x; wv.y += z.y; wv.z += z.z; wv.w += z.w;
+    *reinterpret_cast<float4*>(dWatch + row * kNA + c) = wv;
+    sp.x += z.x; sp.y += z.y; sp.z += z.z; sp.w += z.w;
+    dv.x = fmaf(d, t.x, dv.x); dv.y = fmaf(d, t.y, dv.y); dv.z = fmaf(d, t.z, dv.z); dv.w = fmaf(d, t.w, dv.w);
+    sde += d;
+  }
+  float* s = dSP + (size_t)b * kNA + c;
+  atomicAdd(s, sp.x); atomicAdd(s + 1, sp.y); atomicAdd(s + 2, sp.z); atomicAdd(s + 3, sp.w);
+  atomicAdd(dVa + c, dv.x); atomicAdd(dVa + c + 1, dv.y); atomicAdd(dVa + c + 2, dv.z); atomicAdd(dVa + c + 3, dv.w);
+  if (threadIdx.x == 0) atomicAdd(dVab, sde);
+}
+// dAP_out[b,l'] = dalpha_total... transposed 11x11 stencil:  dAP_out = dAP_in + sum_tap DF[b, l'-off(tap), tap]
+__global__ void __launch_bounds__(256)
+cov_bwd_gather_kernel(const float* __restrict__ DF, const float* __restrict__ dAP_in, float* __restrict__ dAP_out,
+                      int Bn, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * H * W) return;
+  const int x = i % W, t = i / W, y = t % H, b = t / H;
+  float s = dAP_in[i];
+  for (int tap = 0; tap < kCovTaps; ++tap) {
+    const int dy = tap / kCovK - kCovK / 2, dx = tap % kCovK - kCovK / 2;
+    const int ys = y - dy, xs = x - dx;     // source position l with l + off(tap) = l'
+    if ((unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W)
+      s += DF[((size_t)(b * H + ys) * W + xs) * 124 + tap];
+  }
+  dAP_out[i] = s;
+}
+// d ann[b,l,c] += sum_t alpha[t,b,l] * dctx[t,b,c]
+__global__ void __launch_bounds__(256)
+dann_ctx_kernel(const float* __restrict__ ALPHA, const float* __restrict__ DCTX, float* __restrict__ dann, int T, int B, int L) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int C4 = kD / 4;
+  if (i >= (size_t)B * L * C4) return;
+  const int c = (int)(i % C4) * 4; const size_t row = i / C4; const int b = (int)(row / L);
+  float4 acc = *reinterpret_cast<float4*>(dann + row * kD + c);
+  for (int t = 0; t < T; ++t) {
+    const float al = ALPHA[(size_t)t * B * L + row];
+    const float4 d = ldg4(DCTX + ((size_t)t * B + b) * kD + c);
+    acc.x = fmaf(al, d.x, acc.x); acc.y = fmaf(al, d.y, acc.y); acc.z = fmaf(al, d.z, acc.z); acc.w = fmaf(al, d.w, acc.w);
+  }
+  *reinterpret_cast<float4*>(dann + row * kD + c) = acc;
+}
+// h0 = tanh(mean*Wa2h + b): dpre = dh * (1 - h0^2)
+__global__ void tanh_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ dpre, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dpre[i] = dh[i] * (1.f - h[i] * h[i]);
+}
+// d ann[b,l,:] += mask[b,l]/sum(mask[b]) * dmean[b,:]
+__global__ void __launch_bounds__(256)
+dann_mean_kernel(const float* __restrict__ dmean, const float* __restrict__ a_mask, float* __restrict__ dann, int B, int L) {
+  __shared__ float red[33];
+  const int b = blockIdx.y;
+  float s = 0.f;
+  for (int l = threadIdx.x; l < L; l += 256) s += a_mask != nullptr ? a_mask[(size_t)b * L + l] : 1.f;
+  s = block_sum(s, red);
+  const int C4 = kD / 4;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < L * C4; i += gridDim.x * 256) {
+    const int c = (i % C4) * 4, l = i / C4;
+    const float m = (a_mask != nullptr ? a_mask[(size_t)b * L + l] : 1.f) / s;
+    if (m == 0.f) continue;
+    const float4 d = ldg4(dmean + (size_t)b * kD + c);
+    float4* o = reinterpret_cast<float4*>(dann + ((size_t)b * L + l) * kD + c);
+    float4 v = *o; v.x = fmaf(m, d.x, v.x); v.y = fmaf(m, d.y, v.y); v.z = fmaf(m, d.z, v.z); v.w = fmaf(m, d.w, v.w); *o = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------ backward
+// grads (flat) accumulated (+=); d_ann [B,L,684] is written (=).
+int decoder_train_backward(cudaStream_t st, const float* params, float* grads, const float* ann, const float* a_mask,
+                           const int* y, const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
+                           float* d_ann, float* wsp) {
+  const ParamLayout& P = layout();
+  const int L = h * w, TB = T * B;
+  DecTrainWs W = carve_train(wsp, B, L, T, nullptr);
+  const float* p = params; float* g = grads;
+  // transposed copies for the in-loop data gradients
+  WAP_TRY(transpose(st, p + P.W_c_z_r, W.T_Wczr, kD, 2 * kN));
+  WAP_TRY(transpose(st, p + P.W_c_h_nl, W.T_Wchnl, kD, kN));
+  WAP_TRY(transpose(st, p + P.U_hz_hr_nl, W.T_Uhzhrnl, kN, 2 * kN));
+  WAP_TRY(transpose(st, p + P.U_rh_nl, W.T_Urhnl, kN, kN));
+  WAP_TRY(transpose(st, p + P.W_a, W.T_Wa, kN, kNA));
+  WAP_TRY(transpose(st, p + P.U_hz_hr, W.T_Uhzhr, kN, 2 * kN));
+  WAP_TRY(transpose(st, p + P.U_rh, W.T_Urh, kN, kN));
+  // ---- head (LO holds dLO after the forward CE kernel)
+  wo_bwd_data_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LO, p + P.Wo, W.dMO, TB);
+  WAP_LAUNCH_CHECK();
+  wo_bwd_weight_kernel<<<cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, st>>>(W.MO, W.LO, g + P.Wo, g + P.bo, TB);
+  WAP_LAUNCH_CHECK();
+  maxout_drop_bwd_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.dMO, W.dLG, TB, dropout, seed);
+  WAP_LAUNCH_CHECK();
+  WAP_TRY(gemm_tn_atomic(st, W.H + (size_t)B * kN, kN, W.dLG, kMw, g + P.Wh, kMw, kN, kMw, TB));
+  WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dLG, kMw, g + P.Wc, kMw, kD, kMw, TB));
+  WAP_TRY(gemm_tn_atomic(st, W.EMB, kMw, W.dLG, kMw, g + P.Wy, kMw, kMw, kMw, TB));
+  WAP_TRY(colsum(st, W.dLG, kMw, TB, kMw, g + P.bh));
+  WAP_TRY(colsum(st, W.dLG, kMw, TB, kMw, g + P.bc));
+  WAP_TRY(colsum(st, W.dLG, kMw, TB, kMw, g + P.by));
+  WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wh, kMw, W.dHlog, kN, TB, kN, kMw, nullptr, false));
+  WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wc, kMw, W.dCTX, kD, TB, kD, kMw, nullptr, false));
+  WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wy, kMw, W.dEMB, kMw, TB, kMw, kMw, nullptr, false));
+  // ---- BPTT
+  WAP_CHECK(cudaMemsetAsync(W.dh0, 0, sizeof(float) * B * kN, st));
+  WAP_CHECK(cudaMemsetAsync(W.dAP0, 0, sizeof(float) * B * L, st));
+  WAP_CHECK(cudaMemsetAsync(W.dWatch, 0, sizeof(float) * B * L * kNA, st));
+  WAP_CHECK(cudaMemsetAsync(W.dSP, 0, sizeof(float) * TB * kNA, st));
+  float* dh_in = W.dh0; float* dh_out = W.dh1; float* dAP_in = W.dAP0; float* dAP_out = W.dAP1;
+  for (int t = T - 1; t >= 0; --t) {
+    const size_t r = (size_t)t * B;
+    const float* ym = y_mask + r;
+    float* dctx = W.dCTX + r * kD;                 // holds the logit-path part already
+    gru2_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(dh_in, W.dHlog + r * kN, W.G2 + r * 2 * kN, W.PROP2 + r * kN, W.PH2 + r * kN,
+                                                        W.PREH + r * kN, ym, W.dG2 + r * 2 * kN, W.dCH + r * kN, W.dPH2 + r * kN, W.dpre_h, B);
+    WAP_LAUNCH_CHECK();
+    {   // dctx += dG2*W_c_z_r^T + dCH*W_c_h_nl^T ; dpre_h += dG2*U_hz_hr_nl^T + dPH2*U_rh_nl^T
+      SkinnyArgs a; a.ids = nullptr; a.Bn = B;
+      a.X = W.dG2 + r * 2 * kN; a.ldx = 2 * kN; a.K = 2 * kN; a.nseg = 2;
+      a.seg[0] = {W.T_Wczr, kD, kD, dctx, kD};
+      a.seg[1] = {W.T_Uhzhrnl, kN, kN, W.dpre_h, kN};
+      WAP_TRY(skinny_gemm(st, a));
+      a.X = W.dCH + r * kN; a.ldx = kN; a.K = kN; a.nseg = 1;
+      a.seg[0] = {W.T_Wchnl, kD, kD, dctx, kD};
+      WAP_TRY(skinny_gemm(st, a));
+      a.X = W.dPH2 + r * kN; a.seg[0] = {W.T_Urhnl, kN, kN, W.dpre_h, kN};
+      WAP_TRY(skinny_gemm(st, a));
+    }
+    dalpha_kernel<<<cdiv(B * L * 32, 256), 256, 0, st>>>(ann, dctx, dAP_in, W.dalpha, B, L);
+    WAP_LAUNCH_CHECK();
+    softmax_bwd_kernel<<<B, 256, 0, st>>>(W.ALPHA + r * L, W.dalpha, W.de, L);
+    WAP_LAUNCH_CHECK();
+    float* DZt = W.DZ + r * L * kNA;
+    dz_kernel<<<dim3(cdiv(L, kDzPix), B), 128, 0, st>>>(W.TANH + r * L * kNA, W.de, p + P.V_a, DZt, W.dWatch, W.dSP + r * kNA,
+                                                         g + P.V_a, g + P.V_a_b, L);
+    WAP_LAUNCH_CHECK();
+    {   // dpre_h += dSP*W_a^T
+      SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dSP + r * kNA; a.ldx = kNA; a.K = kNA; a.nseg = 1;
+      a.seg[0] = {W.T_Wa, kN, kN, W.dpre_h, kN};
+      WAP_TRY(skinny_gemm(st, a));
+    }
+    // coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
+    WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
+    cov_bwd_gather_kernel<<<cdiv(B * L, 256), 256, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w);
+    WAP_LAUNCH_CHECK();
+    gru1_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
+                                                        W.dG1 + r * 2 * kN, W.dEh + r * kN, W.dUH + r * kN, dh_out, B);
+    WAP_LAUNCH_CHECK();
+    {   // dh_prev += dG1*U_hz_hr^T + dUH*U_rh^T
+      SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dG1 + r * 2 * kN; a.ldx = 2 * kN; a.K = 2 * kN; a.nseg = 1;
+      a.seg[0] = {W.T_Uhzhr, kN, kN, dh_out, kN};
+      WAP_TRY(skinny_gemm(st, a));
+      a.X = W.dUH + r * kN; a.ldx = kN; a.K = kN; a.seg[0] = {W.T_Urh, kN, kN, dh_out, kN};
+      WAP_TRY(skinny_gemm(st, a));
+    }
+    std::swap(dh_in, dh_out); std::swap(dAP_in, dAP_out);
+  }
+  // ---- batched weight gradients over all T*B rows
+  const float* Hprev = W.H;   // H[0..T-1]
+  WAP_TRY(gemm_tn_atomic(st, W.EMB, kMw, W.dG1, 2 * kN, g + P.W_yz_yr, 2 * kN, kMw, 2 * kN, TB));
+  WAP_TRY(colsum(st, W.dG1, 2 * kN, TB, 2 * kN, g + P.b_yz_yr));
+  WAP_TRY(gemm_tn_atomic(st, W.EMB, kMw, W.dEh, kN, g + P.W_yh, kN, kMw, kN, TB));
+  WAP_TRY(colsum(st, W.dEh, kN, TB, kN, g + P.b_yh));
+  WAP_TRY(gemm_tn_atomic(st, Hprev, kN, W.dG1, 2 * kN, g + P.U_hz_hr, 2 * kN, kN, 2 * kN, TB));
+  WAP_TRY(gemm_tn_atomic(st, Hprev, kN, W.dUH, kN, g + P.U_rh, kN, kN, kN, TB));
+  WAP_TRY(gemm_tn_atomic(st, W.PREH, kN, W.dSP, kNA, g + P.W_a, kNA, kN, kNA, TB));
+  WAP_TRY(colsum(st, W.dSP, kNA, TB, kNA, g + P.W_a_b));
+  WAP_TRY(colsum(st, W.dSP, kNA, TB, kNA, g + P.U_f_b));
+  WAP_TRY(colsum(st, W.dSP, kNA, TB, kNA, g + P.U_a_b));
+  WAP_TRY(gemm_tn_atomic(st, W.PREH, kN, W.dG2, 2 * kN, g + P.U_hz_hr_nl, 2 * kN, kN, 2 * kN, TB));
+  WAP_TRY(colsum(st, W.dG2, 2 * kN, TB, 2 * kN, g + P.b_hz_hr_nl));
+  WAP_TRY(gemm_tn_atomic(st, W.PREH, kN, W.dPH2, kN, g + P.U_rh_nl, kN, kN, kN, TB));
+  WAP_TRY(colsum(st, W.dPH2, kN, TB, kN, g + P.b_rh_nl));
+  WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dG2, 2 * kN, g + P.W_c_z_r, 2 * kN, kD, 2 * kN, TB));
+  WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dCH, kN, g + P.W_c_h_nl, kN, kD, kN, TB));
+  // embedding: dEMB = dLG*Wy^T (already) + dG1*W_yz_yr^T + dEh*W_yh^T ; scatter-add into the table
+  WAP_TRY(gemm_nt(st, W.dG1, 2 * kN, p + P.W_yz_yr, 2 * kN, W.dEMB, kMw, TB, kMw, 2 * kN, nullptr, true));
+  WAP_TRY(gemm_nt(st, W.dEh, kN, p + P.W_yh, kN, W.dEMB, kMw, TB, kMw, kN, nullptr, true));
+  emb_scatter_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(W.dEMB, y, g + P.embed, T, B);
+  WAP_LAUNCH_CHECK();
+  // fused coverage filter: dQ' = sum_t patches(AP_t)^T * DZ_t  (one GEMM over T*B images)
+  {
+    WAP_CHECK(cudaMemsetAsync(W.dQf, 0, sizeof(float) * kCovTaps * kNA, st));
+    ACovPatchT A{W.AP, T * B, h, w};
+    BRowMajor Bd{W.DZ, kNA, TB * L, kNA};
+    EpiAtomic e{W.dQf, kNA};
+    const int K = ((TB * L + 3) / 4) * 4;
+    WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, kCovTaps, kNA, K, std::max(1, std::min(cdiv(K, 64), 148)))));
+    // dQ += dQ' * U_f^T ; dU_f += Q^T * dQ'
+    WAP_TRY(gemm_nt(st, W.dQf, kNA, p + P.U_f, kNA, g + P.Q, kNA, kCovTaps, kNA, kNA, nullptr, true));
+    WAP_TRY(gemm_tn_atomic(st, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
+  }
+  // watch path: dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
+  WAP_TRY(gemm_tn_atomic(st, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));
+  WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
+  // context path
+  dann_ctx_kernel<<<(unsigned)cdivz((size_t)B * L * (kD / 4), 256), 256, 0, st>>>(W.ALPHA, W.dCTX, d_ann, T, B, L);
+  WAP_LAUNCH_CHECK();
+  // h0 path: dh_in now holds d h0
+  tanh_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(dh_in, W.H, W.dpre_h, B * kN);
+  WAP_LAUNCH_CHECK();
+  WAP_TRY(gemm_tn_atomic(st, W.mean, kD, W.dpre_h, kN, g + P.Wa2h, kN, kD, kN, B));
+  WAP_TRY(colsum(st, W.dpre_h, kN, B, kN, g + P.ba2h));
+  WAP_TRY(gemm_nt(st, W.dpre_h, kN, p + P.Wa2h, kN, W.dmean, kD, B, kD, kN, nullptr, false));
+  dann_mean_kernel<<<dim3(std::min(cdiv(L * (kD / 4), 256), 64), B), 256, 0, st>>>(W.dmean, a_mask, d_ann, B, L);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace wap

@@ -1,0 +1,546 @@
+// DenseNet "Watcher" encoder: forward (training / inference) and backward.
+// Reference semantics: model-single-GPU.py:73-132 (Watcher_train.dense_net) with TF-1.6 'SAME'
+// padding, fused batch-norm (batch statistics incl. padded pixels, Bessel-corrected moving
+// variance), ReLU, dropout(0.2) and 2x2 SAME max/avg pooling.
+//
+// Data layout: NHWC fp32.  Each dense block owns ONE buffer [B*h*w, Ctot] (Ctot = 432/600/684);
+// level j reads channels [0,C_j) in place and its 24 new channels are written at [C_j, C_j+24):
+// the reference's tf.concat (S:111) costs nothing here.
+#include <algorithm>
+
+#include "gemm.cuh"
+#include "model.h"
+
+namespace wap {
+
+using Cfg128x32 = TileCfg<128, 32, 1, 1>;
+
+// =====================================================================================
+// stem: 7x7 stride-2 SAME conv, Cin = 1, Cout = 48 (S:78-79) + per-channel batch statistics
+// =====================================================================================
+constexpr int kStemTile = 16, kStemPatch = kStemTile * 2 + 5;   // 37
+
+__global__ void __launch_bounds__(256)
+stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
+                 double* __restrict__ stats, int H, int W, int Hs, int Ws, int pt, int pl) {
+  __shared__ float patch[kStemPatch][kStemPatch + 1];
+  __shared__ __align__(16) float ws[49 * kStemC];
+  __shared__ float s_stat[2 * kStemC];
+  const int b = blockIdx.z, oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int tid = threadIdx.x, tx = tid % kStemTile, ty = tid / kStemTile;
+  for (int i = tid; i < 49 * kStemC; i += 256) ws[i] = __ldg(w + i);
+  if (tid < 2 * kStemC) s_stat[tid] = 0.f;
+  const int iy0 = oy0 * 2 - pt, ix0 = ox0 * 2 - pl;
+  for (int i = tid; i < kStemPatch * kStemPatch; i += 256) {
+    const int r = i / kStemPatch, c = i % kStemPatch;
+    const int iy = iy0 + r, ix = ix0 + c;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((size_t)b * H + iy) * W + ix);
+    patch[r][c] = v;
+  }
+  __syncthreads();
+  float acc[kStemC];
+#pragma unroll
+  for (int c = 0; c < kStemC; ++c) acc[c] = 0.f;
+#pragma unroll 1
+  for (int ky = 0; ky < 7; ++ky)
+#pragma unroll
+    for (int kx = 0; kx < 7; ++kx) {
+      const float v = patch[ty * 2 + ky][tx * 2 + kx];
+      const float4* wr = reinterpret_cast<const float4*>(&ws[(ky * 7 + kx) * kStemC]);
+#pragma unroll
+      for (int q = 0; q < kStemC / 4; ++q) {
+        const float4 ww = wr[q];
+        acc[q * 4 + 0] = fmaf(v, ww.x, acc[q * 4 + 0]); acc[q * 4 + 1] = fmaf(v, ww.y, acc[q * 4 + 1]);
+        acc[q * 4 + 2] = fmaf(v, ww.z, acc[q * 4 + 2]); acc[q * 4 + 3] = fmaf(v, ww.w, acc[q * 4 + 3]);
+      }
+    }
+  const int oy = oy0 + ty, ox = ox0 + tx;
+  const bool valid = oy < Hs && ox < Ws;
+  if (valid) {
+    float4* o = reinterpret_cast<float4*>(out + (((size_t)b * Hs + oy) * Ws + ox) * kStemC);
+#pragma unroll
+    for (int q = 0; q < kStemC / 4; ++q) o[q] = make_float4(acc[q * 4], acc[q * 4 + 1], acc[q * 4 + 2], acc[q * 4 + 3]);
+  }
+  if (stats != nullptr) {
+#pragma unroll
+    for (int c = 0; c < kStemC; ++c) {
+      const float v = valid ? acc[c] : 0.f;
+      const float s = warp_sum(v), q = warp_sum(v * v);
+      if ((tid & 31) == 0) { atomicAdd(&s_stat[c], s); atomicAdd(&s_stat[kStemC + c], q); }
+    }
+    __syncthreads();
+    if (tid < 2 * kStemC) atomicAdd(stats + tid, (double)s_stat[tid]);
+  }
+}
+
+// dW[49][48] += sum over output pixels of x_patch[tap] * dy[pix][c]
+__global__ void __launch_bounds__(256)
+stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                  int H, int W, int Hs, int Ws, int pt, int pl) {
+  constexpr int kHalf = kStemTile * kStemTile / 2;         // 128 output pixels per pass
+  constexpr int kOutPerThread = (49 * kStemC + 255) / 256;  // 10
+  __shared__ float patch[kStemPatch][kStemPatch + 1];
+  __shared__ float dys[kHalf][kStemC + 1];
+  const int b = blockIdx.z, oy0 = blockIdx.y * kStemTile, ox0 = blockIdx.x * kStemTile;
+  const int tid = threadIdx.x;
+  const int iy0 = oy0 * 2 - pt, ix0 = ox0 * 2 - pl;
+  for (int i = tid; i < kStemPatch * kStemPatch; i += 256) {
+    const int r = i / kStemPatch, c = i % kStemPatch;
+    const int iy = iy0 + r, ix = ix0 + c;
+    float v = 0.f;
+    if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W) v = __ldg(x + ((size_t)b * H + iy) * W + ix);
+    patch[r][c] = v;
+  }
+  float s[kOutPerThread];
+#pragma unroll
+  for (int i = 0; i < kOutPerThread; ++i) s[i] = 0.f;
+  for (int half = 0; half < 2; ++half) {
+    __syncthreads();
+    for (int i = tid; i < kHalf * kStemC; i += 256) {
+      const int p = i / kStemC + half * kHalf, c = i % kStemC;
+      const int oy = oy0 + p / kStemTile, ox = ox0 + p % kStemTile;
+      float v = 0.f;
+      if (oy < Hs && ox < Ws) v = __ldg(dy + (((size_t)b * Hs + oy) * Ws + ox) * kStemC + c);
+      dys[p - half * kHalf][c] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < kOutPerThread; ++i) {
+      const int o = tid + i * 256;
+      if (o < 49 * kStemC) {
+        const int tap = o / kStemC, c = o % kStemC, ky = tap / 7, kx = tap % 7;
+        float acc = s[i];
+#pragma unroll 4
+        for (int pp = 0; pp < kHalf; ++pp) {
+          const int p = pp + half * kHalf;
+          acc = fmaf(patch[(p / kStemTile) * 2 + ky][(p % kStemTile) * 2 + kx], dys[pp][c], acc);
+        }
+        s[i] = acc;
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kOutPerThread; ++i) {
+    const int o = tid + i * 256;
+    if (o < 49 * kStemC) atomicAdd(dw + o, s[i]);
+  }
+}
+
+// =====================================================================================
+// batch-norm (+ReLU +dropout +optional 2x2 SAME pool) forward
+// =====================================================================================
+struct BnActArgs {
+  const float* raw; int B, Hi, Wi, C;        // raw conv output [B,Hi,Wi,C]
+  float* out; int Ho, Wo, ld_out;            // destination pixels [B,Ho,Wo] x channel slice (row stride ld_out)
+  const double* stats;                       // [2][C] sum / sum of squares (training), else null
+  float* mmean; float* mvar;                 // moving statistics (read when !training; updated when training)
+  const float* gamma; const float* beta;
+  float* saved;                              // [2][kMaxBnC]: mean, invstd (training) or null
+  int training, dropout; uint32_t seed, site;
+};
+
+__device__ __forceinline__ void bn_prologue(const BnActArgs& a, float* s_scale, float* s_shift) {
+  const double cnt = (double)a.B * a.Hi * a.Wi;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    double mean, var;
+    if (a.training) {
+      mean = a.stats[c] / cnt;
+      var = a.stats[a.C + c] / cnt - mean * mean;
+      if (var < 0.0) var = 0.0;
+    } else {
+      mean = a.mmean[c]; var = a.mvar[c];
+    }
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    const float sc = __ldg(a.gamma + c) * invstd;
+    s_scale[c] = sc;
+    s_shift[c] = __ldg(a.beta + c) - (float)mean * sc;
+    if (a.training && blockIdx.x == 0) {
+      if (a.saved != nullptr) { a.saved[c] = (float)mean; a.saved[kMaxBnC + c] = invstd; }
+      const double unb = var * (cnt / fmax(cnt - 1.0, 1.0));      // FusedBatchNorm: Bessel-corrected moving variance
+      a.mmean[c] = a.mmean[c] * kBnMomentum + (float)mean * (1.f - kBnMomentum);
+      a.mvar[c] = a.mvar[c] * kBnMomentum + (float)unb * (1.f - kBnMomentum);
+    }
+  }
+}
+
+__device__ __forceinline__ float bn_relu_drop(float v, float sc, float sh, bool dropout, uint32_t seed, uint32_t site, uint32_t idx) {
+  float y = fmaxf(fmaf(v, sc, sh), 0.f);
+  if (dropout) y = drop_keep(seed, site, idx) ? y * (1.f / (1.f - kDropRate)) : 0.f;
+  return y;
+}
+
+// POOL: 0 none, 1 max 2x2 SAME, 2 avg 2x2 SAME (valid-count divisor)
+template <int POOL>
+__global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
+  bn_prologue(a, s_scale, s_shift);
+  __syncthreads();
+  const int C4 = a.C / 4;
+  const size_t total = (size_t)a.B * a.Ho * a.Wo * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const size_t po = i / C4;
+    float r[4];
+    if (POOL == 0) {
+      const float4 v = ldg4(a.raw + po * a.C + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        r[j] = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, a.seed, a.site, (uint32_t)(po * a.C + c + j));
+    } else {
+      const int xo = (int)(po % a.Wo); const size_t t = po / a.Wo; const int yo = (int)(t % a.Ho); const int b = (int)(t / a.Ho);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = (POOL == 1) ? -INFINITY : 0.f;
+      int cnt = 0;
+#pragma unroll
+      for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int yi = yo * 2 + dy, xi = xo * 2 + dx;
+          if (yi < a.Hi && xi < a.Wi) {
+            const size_t pi = ((size_t)b * a.Hi + yi) * a.Wi + xi;
+            const float4 v = ldg4(a.raw + pi * a.C + c);
+            const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float y = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, a.seed, a.site, (uint32_t)(pi * a.C + c + j));
+              r[j] = (POOL == 1) ? fmaxf(r[j], y) : r[j] + y;
+            }
+            ++cnt;
+          }
+        }
+      if (POOL == 2) {
+        const float inv = 1.f / (float)cnt;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) r[j] *= inv;
+      }
+    }
+    *reinterpret_cast<float4*>(a.out + po * a.ld_out + c) = make_float4(r[0], r[1], r[2], r[3]);
+  }
+}
+
+// =====================================================================================
+// batch-norm (+ReLU +dropout +pool) backward: pass 1 = upstream gradient at the BN output (g) and
+// the two per-channel reductions; pass 2 = d raw in place, d gamma / d beta.
+// =====================================================================================
+struct BnBwdArgs {
+  const float* raw; int B, Hi, Wi, C;
+  const float* dout; int Ho, Wo, ld_dout;    // gradient wrt the (pooled) activated output, channel slice
+  const float* saved; const float* gamma; const float* beta;
+  float* g;                                  // [B*Hi*Wi, C]
+  double* red;                               // [2][C]: sum g, sum g*xhat
+  float* dgamma; float* dbeta;               // += (pass 2)
+  int dropout; uint32_t seed, site;
+};
+
+template <int POOL>
+__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, const int pix_per_cta) {
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC];
+  __shared__ float s_sg[kMaxBnC], s_sgx[kMaxBnC];
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float mean = a.saved[c], inv = a.saved[kMaxBnC + c];
+    const float sc = __ldg(a.gamma + c) * inv;
+    s_scale[c] = sc; s_shift[c] = __ldg(a.beta + c) - mean * sc; s_mean[c] = mean; s_inv[c] = inv;
+    s_sg[c] = 0.f; s_sgx[c] = 0.f;
+  }
+  __syncthreads();
+  const int C4 = a.C / 4, rows = blockDim.x / C4;
+  const int c = (threadIdx.x % C4) * 4, prow = threadIdx.x / C4;
+  const size_t npix = (size_t)a.B * a.Hi * a.Wi;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
+  const size_t p1 = min(npix, p0 + (size_t)pix_per_cta);
+  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (prow < rows) {
+    for (size_t p = p0 + prow; p < p1; p += rows) {
+      const float4 v = ldg4(a.raw + p * a.C + c);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      float up[4];
+      if (POOL == 0) {
+        const float4 d = ldg4(a.dout + p * a.ld_dout + c);
+        up[0] = d.x; up[1] = d.y; up[2] = d.z; up[3] = d.w;
+      } else {
+        const int xi = (int)(p % a.Wi); const size_t t = p / a.Wi; const int yi = (int)(t % a.Hi); const int b = (int)(t / a.Hi);
+        const int yo = yi >> 1, xo = xi >> 1;
+        const float4 d = ldg4(a.dout + (((size_t)b * a.Ho + yo) * a.Wo + xo) * a.ld_dout + c);
+        const float dd[4] = {d.x, d.y, d.z, d.w};
+        if (POOL == 2) {
+          const int cnt = min(2, a.Hi - yo * 2) * min(2, a.Wi - xo * 2);
+          const float inv = 1.f / (float)cnt;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) up[j] = dd[j] * inv;
+        } else {
+          // max pool: the gradient goes to the first window cell (row-major) attaining the maximum
+#pragma unroll
+          for (int j = 0; j < 4; ++j) up[j] = 0.f;
+          float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+          int arg[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int wy = 0; wy < 2; ++wy)
+#pragma unroll
+            for (int wx = 0; wx < 2; ++wx) {
+              const int y2 = yo * 2 + wy, x2 = xo * 2 + wx;
+              if (y2 < a.Hi && x2 < a.Wi) {
+                const float4 q = ldg4(a.raw + (((size_t)b * a.Hi + y2) * a.Wi + x2) * a.C + c);
+                const float qq[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float y = fmaxf(fmaf(qq[j], s_scale[c + j], s_shift[c + j]), 0.f);
+                  if (y > best[j]) { best[j] = y; arg[j] = wy * 2 + wx; }
+                }
+              }
+            }
+          const int me = (yi & 1) * 2 + (xi & 1);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) if (arg[j] == me) up[j] = dd[j];
+        }
+      }
+      float gg[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pre = fmaf(vv[j], s_scale[c + j], s_shift[c + j]);
+        float gj = (pre > 0.f) ? up[j] : 0.f;
+        if (a.dropout) gj = drop_keep(a.seed, a.site, (uint32_t)(p * a.C + c + j)) ? gj * (1.f / (1.f - kDropRate)) : 0.f;
+        gg[j] = gj;
+        sg[j] += gj;
+        sgx[j] = fmaf(gj, (vv[j] - s_mean[c + j]) * s_inv[c + j], sgx[j]);
+      }
+      *reinterpret_cast<float4*>(a.g + p * a.C + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(&s_sg[c + j], sg[j]); atomicAdd(&s_sgx[c + j], sgx[j]); }
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < a.C; cc += blockDim.x) {
+    atomicAdd(a.red + cc, (double)s_sg[cc]);
+    atomicAdd(a.red + a.C + cc, (double)s_sgx[cc]);
+  }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  __shared__ float s_k[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC], s_mg[kMaxBnC], s_mgx[kMaxBnC];
+  const double cnt = (double)a.B * a.Hi * a.Wi;
+  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
+    const float inv = a.saved[kMaxBnC + c];
+    s_mean[c] = a.saved[c]; s_inv[c] = inv; s_k[c] = __ldg(a.gamma + c) * inv;
+    s_mg[c] = (float)(a.red[c] / cnt); s_mgx[c] = (float)(a.red[a.C + c] / cnt);
+    if (blockIdx.x == 0) { a.dbeta[c] += (float)a.red[c]; a.dgamma[c] += (float)a.red[a.C + c]; }
+  }
+  __syncthreads();
+  const int C4 = a.C / 4;
+  const size_t total = (size_t)a.B * a.Hi * a.Wi * C4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    const size_t p = i / C4;
+    const float4 v = ldg4(a.raw + p * a.C + c);
+    float4 g = *reinterpret_cast<const float4*>(a.g + p * a.C + c);
+    const float vv[4] = {v.x, v.y, v.z, v.w};
+    float gg[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float xh = (vv[j] - s_mean[c + j]) * s_inv[c + j];
+      gg[j] = s_k[c + j] * (gg[j] - s_mg[c + j] - xh * s_mgx[c + j]);
+    }
+    *reinterpret_cast<float4*>(a.g + p * a.C + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+  }
+}
+
+// =====================================================================================
+// host orchestration
+// =====================================================================================
+static inline int ew_grid(size_t total_vec) {
+  return (int)std::min<size_t>(cdivz(total_vec, 256), 148 * 8);
+}
+
+static int run_bn_act(cudaStream_t st, int pool, const BnActArgs& a) {
+  const size_t total = (size_t)a.B * a.Ho * a.Wo * (a.C / 4);
+  const int grid = ew_grid(total);
+  if (pool == 0) bn_act_kernel<0><<<grid, 256, 0, st>>>(a);
+  else if (pool == 1) bn_act_kernel<1><<<grid, 256, 0, st>>>(a);
+  else bn_act_kernel<2><<<grid, 256, 0, st>>>(a);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
+  WAP_CHECK(cudaMemsetAsync(a.red, 0, sizeof(double) * 2 * a.C, st));
+  const size_t npix = (size_t)a.B * a.Hi * a.Wi;
+  int ppc = (int)std::max<size_t>(64, cdivz(npix, 148 * 4));
+  const int grid = (int)cdivz(npix, ppc);
+  if (pool == 0) bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(a, ppc);
+  else if (pool == 1) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(a, ppc);
+  else bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(a, ppc);
+  WAP_LAUNCH_CHECK();
+  bn_bwd_apply_kernel<<<ew_grid(npix * (a.C / 4)), 256, 0, st>>>(a);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+static void stem_pad(int n_in, int n_out, int* before) {
+  const int total = std::max((n_out - 1) * 2 + 7 - n_in, 0);
+  *before = total / 2;
+}
+
+int encoder_forward(cudaStream_t st, const float* params, float* moving, const float* x, int B, int H, int W,
+                    int training, int dropout, uint32_t seed, float* annotation, float* wsp) {
+  const ParamLayout& L = layout();
+  const EncGeom g = make_geom(B, H, W);
+  const EncWorkspace ws = make_enc_workspace(g, training != 0);
+  double* stats = reinterpret_cast<double*>(wsp + ws.stats);
+  float* saved = wsp + ws.saved;
+  if (training) WAP_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * kNumConv * 2 * kMaxBnC, st));
+  float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
+  auto bn_args = [&](int k, const float* raw, int Hi, int Wi, float* out, int Ho, int Wo, int ld_out, bool drop) {
+    const ConvLayer& c = L.conv[k];
+    BnActArgs a;
+    a.raw = raw; a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = c.cout;
+    a.out = out; a.Ho = Ho; a.Wo = Wo; a.ld_out = ld_out;
+    a.stats = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
+    a.mmean = moving + c.mmean; a.mvar = moving + c.mvar;
+    a.gamma = params + c.gamma; a.beta = params + c.beta;
+    a.saved = training ? saved + (size_t)k * 2 * kMaxBnC : nullptr;
+    a.training = training; a.dropout = (training && dropout && drop) ? 1 : 0; a.seed = seed; a.site = (uint32_t)k;
+    return a;
+  };
+  // ---- stem (S:76-88)
+  {
+    int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
+    dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
+    stem_conv_kernel<<<grid, 256, 0, st>>>(x, params + L.conv[0].w, wsp + ws.stem_raw, training ? stats : nullptr,
+                                           H, W, g.Hs, g.Ws, pt, pl);
+    WAP_LAUNCH_CHECK();
+    WAP_TRY(run_bn_act(st, 1, bn_args(0, wsp + ws.stem_raw, g.Hs, g.Ws, buf[0], g.h[0], g.w[0], g.Ctot[0], false)));
+  }
+  // ---- dense blocks + transitions (S:91-130)
+  int k = 1;
+  for (int b = 0; b < kBlocks; ++b) {
+    const int M = g.M[b], h = g.h[b], w = g.w[b], ld = g.Ctot[b];
+    int C = g.Cin0[b];
+    for (int j = 0; j < kLevels; ++j, k += 2) {
+      const ConvLayer& c1 = L.conv[k];
+      const ConvLayer& c3 = L.conv[k + 1];
+      float* y1 = wsp + ws.y1[k]; float* a1 = wsp + ws.a1[k]; float* y2 = wsp + ws.y2[k + 1];
+      {   // 1x1 bottleneck  C -> 96
+        ARowMajor A{buf[b], ld, M, C};
+        BRowMajor Bw{params + c1.w, kBottle, C, kBottle};
+        EpiStore e{y1, kBottle, nullptr, false, training ? stats + (size_t)k * 2 * kMaxBnC : nullptr};
+        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, C)));
+        WAP_TRY(run_bn_act(st, 0, bn_args(k, y1, h, w, a1, h, w, kBottle, true)));
+      }
+      {   // 3x3 growth  96 -> 24, written in place at channel offset C
+        AIm2col3 A{a1, kBottle, B, h, w, kBottle, false};
+        BRowMajor Bw{params + c3.w, kGrowth, 9 * kBottle, kGrowth};
+        EpiStore e{y2, kGrowth, nullptr, false, training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr};
+        WAP_TRY((launch_gemm<Cfg256x24>(st, A, Bw, e, M, kGrowth, 9 * kBottle)));
+        WAP_TRY(run_bn_act(st, 0, bn_args(k + 1, y2, h, w, buf[b] + C, h, w, ld, true)));
+      }
+      C += kGrowth;
+    }
+    if (b < kBlocks - 1) {   // transition: 1x1 C -> C/2, BN, ReLU, dropout, avgpool (S:116-130)
+      const ConvLayer& ct = L.conv[k];
+      float* yt = wsp + ws.ytr[b];
+      ARowMajor A{buf[b], ld, M, C};
+      BRowMajor Bw{params + ct.w, ct.cout, C, ct.cout};
+      EpiStore e{yt, ct.cout, nullptr, false, training ? stats + (size_t)k * 2 * kMaxBnC : nullptr};
+      WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, ct.cout, C)));
+      WAP_TRY(run_bn_act(st, 2, bn_args(k, yt, h, w, buf[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], true)));
+      ++k;
+    }
+  }
+  return 0;
+}
+
+// d_annotation [B,h2,w2,684] is the gradient wrt the encoder output; it is used as the gradient
+// buffer of block 2 and is clobbered.  grads (flat, same layout as params) is accumulated (+=).
+int encoder_backward(cudaStream_t st, const float* params, float* grads, const float* x, int B, int H, int W,
+                     int dropout, uint32_t seed, const float* annotation, float* d_annotation, float* wsp) {
+  const ParamLayout& L = layout();
+  const EncGeom g = make_geom(B, H, W);
+  const EncWorkspace ws = make_enc_workspace(g, true);
+  float* saved = wsp + ws.saved;
+  double* red = reinterpret_cast<double*>(wsp + ws.red);
+  const float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
+  float* G[kBlocks] = {wsp + ws.gbuf[0], wsp + ws.gbuf[1], d_annotation};
+  float* dy1 = wsp + ws.dy1; float* da1 = wsp + ws.da1; float* dy2 = wsp + ws.dy2; float* dytr = wsp + ws.dytr;
+  auto bwd_args = [&](int k, const float* raw, int Hi, int Wi, const float* dout, int Ho, int Wo, int ld_dout, float* gbuf, bool drop) {
+    const ConvLayer& c = L.conv[k];
+    BnBwdArgs a;
+    a.raw = raw; a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = c.cout;
+    a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
+    a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
+    a.g = gbuf; a.red = red; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
+    a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.site = (uint32_t)k;
+    return a;
+  };
+  int k = kNumConv - 1;     // 98: last 3x3
+  for (int b = kBlocks - 1; b >= 0; --b) {
+    const int M = g.M[b], h = g.h[b], w = g.w[b], ld = g.Ctot[b];
+    if (b < kBlocks - 1) {   // transition b -> b+1 (conv index k)
+      const ConvLayer& ct = L.conv[k];
+      const int C = ld;
+      WAP_TRY(run_bn_bwd(st, 2, bwd_args(k, wsp + ws.ytr[b], h, w, G[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], dytr, true)));
+      {   // wgrad  dW[C, C/2] += buf^T * dy
+        AColMajor A{buf[b], ld, C, M};
+        BRowMajor Bd{dytr, ct.cout, M, ct.cout};
+        EpiAtomic e{grads + ct.w, ct.cout};
+        const int tiles = cdiv(C, 128) * cdiv(ct.cout, 128);
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))))));
+      }
+      {   // dgrad  G[b] = dy * W^T   (initialises the whole gradient buffer of block b)
+        ARowMajor A{dytr, ct.cout, M, ct.cout};
+        BColMajor Bw{params + ct.w, ct.cout, ct.cout, C};
+        EpiStore e{G[b], ld, nullptr, false, nullptr};
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, ct.cout)));
+      }
+      --k;
+    }
+    int C = ld - kGrowth;    // input channels of the last level's 1x1
+    for (int j = kLevels - 1; j >= 0; --j, k -= 2, C -= kGrowth) {
+      const int k3 = k, k1 = k - 1;
+      const ConvLayer& c3 = L.conv[k3];
+      const ConvLayer& c1 = L.conv[k1];
+      const float* y1 = wsp + ws.y1[k1]; const float* a1 = wsp + ws.a1[k1]; const float* y2 = wsp + ws.y2[k3];
+      // BN/ReLU/dropout backward of the 3x3 output
+      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k3, y2, h, w, G[b] + C, h, w, ld, dy2, true)));
+      {   // wgrad 3x3: dW[864,24] += im2col(a1)^T * dy2
+        AIm2col3T A{a1, kBottle, B, h, w, kBottle};
+        BRowMajor Bd{dy2, kGrowth, M, kGrowth};
+        EpiAtomic e{grads + c3.w, kGrowth};
+        const int tiles = cdiv(9 * kBottle, 128);
+        WAP_TRY((launch_gemm<Cfg128x32>(st, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))))));
+      }
+      {   // dgrad 3x3: d a1[M,96]
+        AIm2col3 A{dy2, kGrowth, B, h, w, kGrowth, false};
+        BDgrad3 Bw{params + c3.w, kBottle, kGrowth};
+        EpiStore e{da1, kBottle, nullptr, false, nullptr};
+        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, 9 * kGrowth)));
+      }
+      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, true)));
+      {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
+        AColMajor A{buf[b], ld, C, M};
+        BRowMajor Bd{dy1, kBottle, M, kBottle};
+        EpiAtomic e{grads + c1.w, kBottle};
+        const int tiles = cdiv(C, 128);
+        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))))));
+      }
+      {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
+        ARowMajor A{dy1, kBottle, M, kBottle};
+        BColMajor Bw{params + c1.w, kBottle, kBottle, C};
+        EpiStore e{G[b], ld, nullptr, true, nullptr};
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, kBottle)));
+      }
+    }
+  }
+  // ---- stem: maxpool + ReLU + BN backward, then the 7x7 weight gradient (no dgrad: input is the image)
+  {
+    float* gstem = wsp + ws.gstem;
+    WAP_TRY(run_bn_bwd(st, 1, bwd_args(0, wsp + ws.stem_raw, g.Hs, g.Ws, G[0], g.h[0], g.w[0], g.Ctot[0], gstem, false)));
+    int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
+    dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
+    stem_wgrad_kernel<<<grid, 256, 0, st>>>(x, gstem, grads + L.conv[0].w, H, W, g.Hs, g.Ws, pt, pl);
+    WAP_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+}  // namespace wap

@@ -1,0 +1,74 @@
+// Host-side description of the WAP model: flat parameter layout (TF variable names of the
+// reference graph) and per-input-shape encoder geometry.  Pure C++ (no CUDA).
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+namespace wap {
+
+enum ConvKind { kStem = 0, kC1 = 1, kC3 = 2, kTr = 3 };
+
+struct ConvLayer {
+  int k;                 // TF index: conv2d_k / batch_normalization_k
+  int kind, cin, cout, ks, block;
+  size_t w, gamma, beta; // offsets (floats) into the flat trainable buffer
+  size_t mmean, mvar;    // offsets (floats) into the moving-statistics buffer
+};
+
+struct TensorInfo {
+  std::string name;
+  size_t offset;         // floats
+  int ndim;
+  int64_t dims[4];
+  int flags;             // bit0: receives L2 (model-single-GPU.py:596-598); bit1: moving statistic (separate buffer)
+  size_t numel() const { size_t n = 1; for (int i = 0; i < ndim; ++i) n *= (size_t)dims[i]; return n; }
+};
+
+struct ParamLayout {
+  ConvLayer conv[kNumConv];
+  // Attender (model-single-GPU.py:149-163)
+  size_t U_f, U_f_b, U_a, U_a_b, W_a, W_a_b, V_a, V_a_b, Q;
+  // Parser (:218-242)
+  size_t W_yz_yr, b_yz_yr, U_hz_hr, W_yh, b_yh, U_rh, U_hz_hr_nl, b_hz_hr_nl, W_c_z_r, U_rh_nl, b_rh_nl, W_c_h_nl;
+  // WAP (:319-333)
+  size_t embed, Wa2h, ba2h, Wc, bc, Wh, bh, Wy, by, Wo, bo;
+  size_t n_decay;        // flat elements [0, n_decay) get the L2 term; BN gamma/beta follow
+  size_t n_total;        // flat trainable floats (each tensor padded to a multiple of 4)
+  size_t n_moving;       // floats in the moving-statistics buffer
+  std::vector<TensorInfo> tensors;
+};
+
+const ParamLayout& layout();      // singleton, built on first use
+
+// SAME-padding geometry for one (B,H,W) input batch
+struct EncGeom {
+  int B, H, W;
+  int Hs, Ws;            // after the 7x7 s2 stem conv
+  int h[kBlocks], w[kBlocks];   // spatial size of dense block b (after maxpool / avgpools)
+  int M[kBlocks];        // B*h*w
+  int Ctot[kBlocks];     // channels of the block buffer: 432, 600, 684
+  int Cin0[kBlocks];     // channels entering the block: 48, 216, 300
+};
+EncGeom make_geom(int B, int H, int W);
+
+// Encoder workspace (floats unless noted) for one geometry.
+struct EncWorkspace {
+  size_t stem_raw;                       // [B,Hs,Ws,48]
+  size_t buf[kBlocks];                   // block buffers; buf[2] unused when the caller passes `annotation`
+  size_t y1[kNumConv], a1[kNumConv], y2[kNumConv];   // indexed by the TF conv index of the 1x1 layer (y1,a1) / 3x3 (y2)
+  size_t ytr[kBlocks - 1];               // raw transition outputs
+  size_t stats;                          // doubles: [99][2][kMaxBnC]   (byte offset is stats*4, 8-aligned)
+  size_t saved;                          // floats:  [99][2][kMaxBnC]   mean, invstd
+  // backward scratch
+  size_t gbuf[kBlocks - 1];              // d block buffer 0,1
+  size_t dy1, da1, dy2, dytr, gstem;     // largest-block sized scratch
+  size_t red;                            // doubles [2][kMaxBnC]
+  size_t total;                          // floats
+};
+EncWorkspace make_enc_workspace(const EncGeom& g, bool training);
+
+}  // namespace wap

@@ -1,0 +1,130 @@
+"""Loader with the reference's data.py interface (/root/reference/data.py:7-122):
+
+    dataIterator(feature_file, label_file, dictionary, batch_size, batch_Imagesize, maxlen, maxImagesize)
+        -> (list[(images, labels)], uidList)
+    load_dict(dictFile) -> {token: id}
+    prepare_data(images_x, seqs_y) -> (x, x_mask, y, y_mask)
+
+Same inputs (.pkl dict uid -> uint8 [1,H,W]; caption file `uid tok tok ...`; dictionary.txt), same
+outputs and the same bucketing decisions, re-implemented (not copied).  `prepare_data` additionally
+accepts `pinned=True` to fill page-locked torch buffers for the asynchronous host->device copy.
+"""
+from __future__ import annotations
+
+import pickle
+import sys
+from typing import Dict, List, Sequence, Tuple
+
+import numpy as np
+
+
+def load_dict(dictFile: str) -> Dict[str, int]:
+    """dictionary.txt: one `token id` pair per line (data.py:87-97)."""
+    lexicon: Dict[str, int] = {}
+    with open(dictFile) as fh:
+        for line in fh:
+            parts = line.split()
+            if len(parts) >= 2:
+                lexicon[parts[0]] = int(parts[1])
+    print('total words/phones', len(lexicon))
+    return lexicon
+
+
+def _read_captions(label_file: str, dictionary: Dict[str, int]) -> Dict[str, List[int]]:
+    targets: Dict[str, List[int]] = {}
+    with open(label_file) as fh:
+        for line in fh:
+            parts = line.strip().split()
+            if not parts:
+                continue
+            uid, words = parts[0], parts[1:]
+            ids = []
+            for wd in words:
+                if wd not in dictionary:                      # data.py:26-28: hard exit on OOV
+                    print('a word not in the dictionary !! sentence ', uid, 'word ', wd)
+                    sys.exit()
+                ids.append(dictionary[wd])
+            targets[uid] = ids
+    return targets
+
+
+def _load_features(feature_file: str):
+    with open(feature_file, 'rb') as fh:
+        try:
+            return pickle.load(fh)
+        except UnicodeDecodeError:                            # python-2 pickles of the original CROHME dumps
+            fh.seek(0)
+            return pickle.load(fh, encoding='latin1')
+
+
+def bucket_by_area(features: Dict[str, np.ndarray], targets: Dict[str, List[int]], batch_size: int,
+                   batch_Imagesize: int, maxlen: int, maxImagesize: int):
+    """Area-sorted greedy bucketing with the reference's exact decisions (data.py:33-84):
+    a batch closes when (largest area so far) x (count+1) exceeds `batch_Imagesize` or when it
+    already holds `batch_size` images; over-long captions / over-large images are dropped, but
+    still advance the running maximum, as in the reference."""
+    order = sorted(((uid, im.shape[1] * im.shape[2]) for uid, im in features.items()), key=lambda kv: kv[1])
+    batches: List[Tuple[list, list]] = []
+    uid_list: List[str] = []
+    cur_x: list = []
+    cur_y: list = []
+    biggest = 0
+    for uid, area in order:
+        biggest = max(biggest, area)
+        projected = biggest * (len(cur_x) + 1)
+        label = targets[uid]
+        if len(label) > maxlen:
+            print('sentence', uid, 'length bigger than', maxlen, 'ignore')
+            continue
+        if area > maxImagesize:
+            print('image', uid, 'size bigger than', maxImagesize, 'ignore')
+            continue
+        uid_list.append(uid)
+        if projected > batch_Imagesize or len(cur_x) == batch_size:
+            batches.append((cur_x, cur_y))
+            cur_x, cur_y, biggest = [], [], area
+        cur_x.append(features[uid])
+        cur_y.append(label)
+    batches.append((cur_x, cur_y))
+    return batches, uid_list
+
+
+def dataIterator(feature_file, label_file, dictionary, batch_size, batch_Imagesize, maxlen, maxImagesize):
+    features = _load_features(feature_file)
+    targets = _read_captions(label_file, dictionary)
+    batches, uid_list = bucket_by_area(features, targets, batch_size, batch_Imagesize, maxlen, maxImagesize)
+    print('total ', len(batches), 'batch data loaded')
+    return batches, uid_list
+
+
+def prepare_data(images_x: Sequence[np.ndarray], seqs_y: Sequence[Sequence[int]], n_words_src=30000, n_words=30000,
+                 pinned: bool = False):
+    """Pad to the batch maximum, scale to [0,1], build masks (data.py:100-122).
+
+    x [B,H,W,1] f32, x_mask [B,H,W] f32, y [T,B] int64 (trailing 0 = <eol>), y_mask [T,B] f32 with
+    T = max caption length + 1 and y_mask covering len+1 positions."""
+    B = len(images_x)
+    H = max(im.shape[1] for im in images_x)
+    W = max(im.shape[2] for im in images_x)
+    T = max(len(s) for s in seqs_y) + 1
+    if pinned:
+        import torch
+        tx = torch.zeros((B, H, W, 1), dtype=torch.float32).pin_memory()
+        txm = torch.zeros((B, H, W), dtype=torch.float32).pin_memory()
+        ty = torch.zeros((T, B), dtype=torch.int64).pin_memory()
+        tym = torch.zeros((T, B), dtype=torch.float32).pin_memory()
+        x, x_mask, y, y_mask = tx.numpy(), txm.numpy(), ty.numpy(), tym.numpy()
+    else:
+        x = np.zeros((B, H, W, 1), np.float32)
+        x_mask = np.zeros((B, H, W), np.float32)
+        y = np.zeros((T, B), np.int64)
+        y_mask = np.zeros((T, B), np.float32)
+    for b, (im, seq) in enumerate(zip(images_x, seqs_y)):
+        hh, ww, n = im.shape[1], im.shape[2], len(seq)
+        x[b, :hh, :ww, 0] = im[0] / 255.
+        x_mask[b, :hh, :ww] = 1.
+        y[:n, b] = seq
+        y_mask[:n + 1, b] = 1.
+    if pinned:
+        return tx, txm, ty, tym
+    return x, x_mask, y, y_mask

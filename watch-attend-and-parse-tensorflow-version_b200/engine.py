@@ -1,0 +1,377 @@
+"""Host-side mirror of the reference model classes over the C ABI (include/wap_abi.h).
+
+Reference interface being mirrored (file:line in /root/reference/model-single-GPU.py):
+    Watcher_train.dense_net(input_x, mask_x)                      :73-132
+    Attender / Parser / WAP constructors (hyper-parameters)       :136-163, :209-242, :311-334
+    WAP.get_cost(annotation, y, a_mask, y_mask)                   :337-375
+    WAP.get_word(y, h_pre, alpha_past_pre, annotation)            :379-439
+    WAP.get_sample(..., k, maxlen, stochastic, ...)               :442-542
+    hidden_state_0                                                :590
+    one optimiser step  sess.run([cost, trainer], feed_dict)      :640-641 (L2 :594-598, Adadelta :602-607)
+
+torch is used for device memory, streams and torch.distributed only; every FLOP of the model runs
+in libwap_b200.so.  There is no CPU / eager fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None   # noqa: E731
+
+ADADELTA_RHO, ADADELTA_EPS, L2_COEF = 0.95, 1e-8, 1e-4   # TF defaults (S:602) / S:598
+VOCAB, DIM_DEC, DIM_WORD, DIM_ATT, ANNOT_C = 111, 256, 256, 512, 684
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class ParamStore:
+    """Flat fp32 device buffers + named views (TF variable names of the reference graph)."""
+
+    def __init__(self, device: torch.device):
+        self.device = device
+        L = _lib.lib()
+        self.table = _lib.param_table()
+        self.n = int(L.wap_param_floats())
+        self.n_decay = int(L.wap_decay_floats())
+        self.n_moving = int(L.wap_moving_floats())
+        self.flat = torch.zeros(self.n, dtype=torch.float32, device=device)
+        self.moving = torch.zeros(self.n_moving, dtype=torch.float32, device=device)
+        self.views: Dict[str, torch.Tensor] = {}
+        for name, off, shape, flags in self.table:
+            src = self.moving if flags & 2 else self.flat
+            self.views[name] = src[off: off + int(np.prod(shape))].view(*shape)
+        for name, _, _, flags in self.table:
+            if name.endswith("moving_variance"):
+                self.views[name].fill_(1.0)
+
+    def names(self, trainable_only: bool = False):
+        return [n for n, _, _, f in self.table if not (trainable_only and f & 2)]
+
+    def load(self, values: Dict[str, np.ndarray]) -> None:
+        missing = [n for n in self.names() if n not in values]
+        if missing:
+            raise KeyError(f"missing variables: {missing[:5]} ...")
+        for name in self.names():
+            v = torch.as_tensor(np.asarray(values[name], dtype=np.float32))
+            self.views[name].copy_(v.reshape(self.views[name].shape))
+
+    def state_dict(self) -> Dict[str, np.ndarray]:
+        return {n: self.views[n].detach().cpu().numpy().copy() for n in self.names()}
+
+    def init_reference(self, seed: int = 0) -> None:
+        """Reference initialisers (S:25-42 norm_weight / conv_norm_weight / ortho_weight; conv limits
+        from Watcher_train.bound S:67-70; gamma ~ U(+-1/sqrt(C)) S:81; biases 0)."""
+        rs = np.random.RandomState(seed)
+        vals: Dict[str, np.ndarray] = {}
+        for name, _, shape, flags in self.table:
+            if name.endswith("kernel"):
+                kh, kw, cin, cout = shape
+                fin = cout if (kh == 1 and cout not in (96,)) else cin     # transition quirk (S:120-121)
+                lim = math.sqrt(6.0 / (fin * kh * kw + cout * kh * kw))
+                vals[name] = rs.uniform(-lim, lim, size=shape)
+            elif name.endswith("gamma"):
+                g = 1.0 / math.sqrt(shape[0])
+                vals[name] = rs.uniform(-g, g, size=shape)
+            elif name.endswith("moving_variance"):
+                vals[name] = np.ones(shape)
+            elif name.endswith(("beta", "moving_mean")) or (len(shape) == 1):
+                vals[name] = np.zeros(shape)
+            elif name == "alpha_past_filter":
+                lim = math.sqrt(6.0 / (121 * 1 + 121 * shape[3]))
+                vals[name] = rs.uniform(-lim, lim, size=shape)
+            elif name in ("U_hz_hr", "U_hz_hr_nl"):
+                vals[name] = np.concatenate([np.linalg.svd(rs.randn(DIM_DEC, DIM_DEC))[0] for _ in range(2)], 1)
+            elif name in ("U_rh", "U_rh_nl"):
+                vals[name] = np.linalg.svd(rs.randn(DIM_DEC, DIM_DEC))[0]
+            elif name == "W_yz_yr":
+                lim = math.sqrt(6.0 / (DIM_WORD + DIM_DEC))
+                vals[name] = rs.uniform(-lim, lim, size=shape)
+            else:
+                lim = math.sqrt(6.0 / (shape[0] + shape[1]))
+                vals[name] = rs.uniform(-lim, lim, size=shape)
+        self.load(vals)
+
+
+class WAPEngine:
+    """Owns parameters, optimiser state and workspaces of one GPU replica."""
+
+    def __init__(self, device: Optional[torch.device] = None, seed: int = 0, init: bool = True):
+        if not torch.cuda.is_available():
+            raise _lib.WapError("WAPEngine needs a CUDA device (B200, sm_100a); there is no CPU path")
+        self.device = device or torch.device("cuda", torch.cuda.current_device())
+        self.L = _lib.lib()
+        self.P = ParamStore(self.device)
+        if init:
+            self.P.init_reference(seed)
+        self.grads = torch.zeros_like(self.P.flat)
+        self.accum = torch.zeros_like(self.P.flat)
+        self.accum_update = torch.zeros_like(self.P.flat)
+        self._ws: Dict[tuple, torch.Tensor] = {}
+        self._cost = torch.zeros(2, dtype=torch.float64, device=self.device)   # [CE cost, L2 cost]
+        self.step_count = 0
+        self.dropout_seed = 1234
+        self.world_size = 1
+        self.launches_last_step = 0
+
+    # ------------------------------------------------------------------ helpers
+    def _buf(self, key: tuple, n: int, dtype=torch.float32) -> torch.Tensor:
+        t = self._ws.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(int(n), 4), dtype=dtype, device=self.device)
+            self._ws[key] = t
+        return t
+
+    def annotation_hw(self, H: int, W: int):
+        h, w = C.c_int(), C.c_int()
+        _lib.check(self.L.wap_annotation_hw(H, W, C.byref(h), C.byref(w)), "wap_annotation_hw")
+        return h.value, w.value
+
+    def _dev(self, a, dtype) -> torch.Tensor:
+        if isinstance(a, torch.Tensor):
+            return a.to(self.device, dtype=dtype, non_blocking=True).contiguous()
+        return torch.as_tensor(np.ascontiguousarray(a)).to(self.device, dtype=dtype, non_blocking=True)
+
+    # ------------------------------------------------------------------ Watcher
+    def mask_subsample(self, x_mask: torch.Tensor) -> torch.Tensor:
+        B, H, W = x_mask.shape
+        h, w = self.annotation_hw(H, W)
+        a_mask = torch.empty((B, h, w), dtype=torch.float32, device=self.device)
+        _lib.check(self.L.wap_mask_subsample(_stream(), _p(x_mask), B, H, W, _p(a_mask)), "wap_mask_subsample")
+        return a_mask
+
+    def dense_net(self, x, x_mask=None, training: bool = False, dropout: bool = True, seed: Optional[int] = None):
+        """Watcher_train.dense_net (S:73-132): x [B,H,W,1] -> annotation [B,h,w,684], mask [B,h,w]."""
+        x = self._dev(x, torch.float32)
+        B, H, W = x.shape[0], x.shape[1], x.shape[2]
+        h, w = self.annotation_hw(H, W)
+        ws = self._buf(("enc", B, H, W, bool(training)), self.L.wap_encoder_workspace_floats(B, H, W, int(training)))
+        ann = torch.empty((B, h, w, ANNOT_C), dtype=torch.float32, device=self.device)
+        sd = self.dropout_seed if seed is None else seed
+        _lib.check(self.L.wap_encoder_forward(_stream(), _p(self.P.flat), _p(self.P.moving), _p(x), B, H, W, int(training),
+                                              int(bool(dropout) and bool(training)), C.c_uint32(sd & 0xFFFFFFFF), _p(ann), _p(ws)),
+                   "wap_encoder_forward")
+        a_mask = None
+        if x_mask is not None:
+            a_mask = self.mask_subsample(self._dev(x_mask, torch.float32))
+        return ann, a_mask
+
+    # ------------------------------------------------------------------ decode
+    def precompute(self, ann: torch.Tensor, a_mask: Optional[torch.Tensor] = None):
+        B, h, w, _ = ann.shape
+        watch = torch.empty((B, h, w, DIM_ATT), dtype=torch.float32, device=self.device)
+        h0 = torch.empty((B, DIM_DEC), dtype=torch.float32, device=self.device)
+        qf = torch.empty((121, DIM_ATT), dtype=torch.float32, device=self.device)
+        scratch = self._buf(("mean", B), B * ANNOT_C)
+        _lib.check(self.L.wap_attn_precompute(_stream(), _p(self.P.flat), _p(ann), _p(a_mask), B, h, w, _p(watch), _p(h0), _p(qf),
+                                              _p(scratch)), "wap_attn_precompute")
+        return watch, h0, qf
+
+    def hidden_state_0(self, anno: torch.Tensor) -> torch.Tensor:
+        """S:590 (unmasked mean)."""
+        B, h, w, _ = anno.shape
+        h0 = torch.empty((B, DIM_DEC), dtype=torch.float32, device=self.device)
+        scratch = self._buf(("mean", B), B * ANNOT_C)
+        _lib.check(self.L.wap_attn_precompute(_stream(), _p(self.P.flat), _p(anno), None, B, h, w, None, _p(h0), None, _p(scratch)),
+                   "wap_attn_precompute")
+        return h0
+
+    def get_word(self, y, h_pre, alpha_past_pre, annotation, watch=None, qf=None):
+        """WAP.get_word (S:379-439).  annotation may be [1,h,w,684] shared by all k rows (beam)."""
+        y = self._dev(y, torch.int32)
+        k = y.shape[0]
+        _, h, w, _ = annotation.shape
+        shared = int(annotation.shape[0] == 1 and k > 1)
+        if watch is None or qf is None:
+            watch, _, qf = self.precompute(annotation)
+        h_pre = self._dev(h_pre, torch.float32); alpha_past_pre = self._dev(alpha_past_pre, torch.float32)
+        probs = torch.empty((k, VOCAB), dtype=torch.float32, device=self.device)
+        word = torch.empty((k,), dtype=torch.int32, device=self.device)
+        h_new = torch.empty((k, DIM_DEC), dtype=torch.float32, device=self.device)
+        ap_new = torch.empty((k, h, w), dtype=torch.float32, device=self.device)
+        ws = self._buf(("step", k, h, w), self.L.wap_decoder_step_workspace_floats(k, h, w))
+        _lib.check(self.L.wap_decoder_step(_stream(), _p(self.P.flat), _p(annotation), _p(watch), _p(qf), shared, k, h, w, _p(y),
+                                           _p(h_pre), _p(alpha_past_pre), _p(probs), _p(word), _p(h_new), _p(ap_new), _p(ws)),
+                   "wap_decoder_step")
+        return probs, word, h_new, ap_new
+
+    def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8):
+        """Greedy decode of every image in the batch; returns (tokens [B,maxlen] int32, lengths [B] int32, steps)."""
+        B, h, w, _ = annotation.shape
+        tokens = torch.zeros((B, maxlen), dtype=torch.int32, device=self.device)
+        lengths = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        ws = self._buf(("greedy", B, h, w), self.L.wap_greedy_workspace_floats(B, h, w))
+        steps = C.c_int(0)
+        _lib.check(self.L.wap_greedy_decode(_stream(), _p(self.P.flat), _p(annotation), B, h, w, maxlen, check_every, _p(tokens),
+                                            _p(lengths), _p(ws), C.byref(steps)), "wap_greedy_decode")
+        return tokens, lengths, steps.value
+
+    def get_sample(self, annotation: torch.Tensor, k: int = 10, maxlen: int = 100):
+        """Beam search of WAP.get_sample(stochastic=False) (S:442-542) + the length-normalised pick
+        (S:671-672) for ONE image [1,h,w,684].  The step runs on the GPU for all live hypotheses at
+        once (shared annotation); the k x 111 candidate bookkeeping follows the reference on the host."""
+        assert annotation.shape[0] == 1
+        watch, h0, qf = self.precompute(annotation)
+        _, h, w, _ = annotation.shape
+        sample, sample_score = [], []
+        live_k, dead_k = 1, 0
+        hyp_samples = [[]]
+        hyp_scores = np.zeros(1, np.float32)
+        next_w = torch.full((1,), -1, dtype=torch.int32, device=self.device)
+        next_state = h0
+        next_ap = torch.zeros((1, h, w), dtype=torch.float32, device=self.device)
+        for _ in range(maxlen):
+            p, _, st, ap = self.get_word(next_w, next_state, next_ap, annotation, watch, qf)
+            next_p = p.cpu().numpy()
+            cand = hyp_scores[:, None] - np.log(next_p)
+            flat = cand.flatten()
+            ranks = flat.argsort()[: (k - dead_k)]
+            ti, wi = ranks // VOCAB, ranks % VOCAB
+            costs = flat[ranks]
+            new_samples = [hyp_samples[t] + [int(v)] for t, v in zip(ti, wi)]
+            hyp_samples, scores, keep = [], [], []
+            for i, s in enumerate(new_samples):
+                if s[-1] == 0:
+                    sample.append(s); sample_score.append(np.float32(costs[i])); dead_k += 1
+                else:
+                    hyp_samples.append(s); scores.append(np.float32(costs[i])); keep.append(int(ti[i]))
+            hyp_scores = np.array(scores, np.float32)
+            live_k = len(hyp_samples)
+            if live_k < 1 or dead_k >= k:
+                break
+            idx = torch.as_tensor(keep, device=self.device, dtype=torch.long)
+            next_w = torch.as_tensor([s[-1] for s in hyp_samples], dtype=torch.int32, device=self.device)
+            next_state = st.index_select(0, idx).contiguous()
+            next_ap = ap.index_select(0, idx).contiguous()
+        if live_k > 0:
+            for i in range(live_k):
+                sample.append(hyp_samples[i]); sample_score.append(hyp_scores[i])
+        score = np.array(sample_score) / np.array([len(s) for s in sample])
+        return sample[int(score.argmin())], sample, sample_score
+
+    # ------------------------------------------------------------------ training
+    def get_cost(self, annotation, y, a_mask, y_mask, dropout: bool = False, seed: Optional[int] = None) -> torch.Tensor:
+        """WAP.get_cost (S:337-375): returns the CE cost (device float64 scalar, no L2 term)."""
+        B, h, w, _ = annotation.shape
+        y = self._dev(y, torch.int32); y_mask = self._dev(y_mask, torch.float32)
+        T = y.shape[0]
+        ws = self._buf(("dec", B, h, w, T), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
+        sd = self.dropout_seed if seed is None else seed
+        _lib.check(self.L.wap_decoder_train_forward(_stream(), _p(self.P.flat), _p(annotation), _p(a_mask), _p(y), _p(y_mask), B, h, w, T,
+                                                    int(dropout), C.c_uint32(sd & 0xFFFFFFFF), _p(self._cost), _p(ws)),
+                   "wap_decoder_train_forward")
+        return self._cost[0]
+
+    def forward_backward(self, x, y, x_mask, y_mask, dropout: bool = True, seed: Optional[int] = None):
+        """Forward + backward of cost (no L2 term, no update): fills self.grads; returns device cost."""
+        x = self._dev(x, torch.float32); x_mask = self._dev(x_mask, torch.float32)
+        y = self._dev(y, torch.int32); y_mask = self._dev(y_mask, torch.float32)
+        B, H, W = x.shape[0], x.shape[1], x.shape[2]
+        T = y.shape[0]
+        sd = (self.dropout_seed + 7919 * self.step_count) if seed is None else seed
+        sd_c = C.c_uint32(sd & 0xFFFFFFFF)
+        h, w = self.annotation_hw(H, W)
+        st = _stream()
+        a_mask = self.mask_subsample(x_mask)
+        ews = self._buf(("enc", B, H, W, True), self.L.wap_encoder_workspace_floats(B, H, W, 1))
+        dws = self._buf(("dec", B, h, w, T), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
+        ann = self._buf(("ann", B, h, w), B * h * w * ANNOT_C)
+        d_ann = self._buf(("dann", B, h, w), B * h * w * ANNOT_C)
+        self.grads.zero_()
+        _lib.check(self.L.wap_encoder_forward(st, _p(self.P.flat), _p(self.P.moving), _p(x), B, H, W, 1, int(dropout), sd_c, _p(ann), _p(ews)),
+                   "wap_encoder_forward")
+        _lib.check(self.L.wap_decoder_train_forward(st, _p(self.P.flat), _p(ann), _p(a_mask), _p(y), _p(y_mask), B, h, w, T, int(dropout), sd_c,
+                                                    _p(self._cost), _p(dws)), "wap_decoder_train_forward")
+        _lib.check(self.L.wap_decoder_train_backward(st, _p(self.P.flat), _p(self.grads), _p(ann), _p(a_mask), _p(y), _p(y_mask), B, h, w, T,
+                                                     int(dropout), sd_c, _p(d_ann), _p(dws)), "wap_decoder_train_backward")
+        _lib.check(self.L.wap_encoder_backward(st, _p(self.P.flat), _p(self.grads), _p(x), B, H, W, int(dropout), sd_c, _p(ann), _p(d_ann), _p(ews)),
+                   "wap_encoder_backward")
+        return self._cost[0]
+
+    def apply_update(self, lr: float) -> torch.Tensor:
+        """L2 (S:594-598) + Adadelta (S:602-607) on the flat buffers; returns device L2 cost."""
+        n = self.P.n
+        l2_ptr = C.c_void_p(self._cost.data_ptr() + 8)
+        _lib.check(self.L.wap_adadelta_l2_step(_stream(), _p(self.P.flat), _p(self.grads), _p(self.accum), _p(self.accum_update), n,
+                                               self.P.n_decay, C.c_float(lr), C.c_float(ADADELTA_RHO), C.c_float(ADADELTA_EPS),
+                                               C.c_float(L2_COEF), C.c_float(1.0 / self.world_size), l2_ptr), "wap_adadelta_l2_step")
+        return self._cost[1]
+
+    def train_step(self, x, y, x_mask, y_mask, lr: float = 1.0, dropout: bool = True, seed: Optional[int] = None) -> torch.Tensor:
+        """One `sess.run([cost, trainer])` (S:640-641): returns cost incl. the L2 term (device float64)."""
+        self.forward_backward(x, y, x_mask, y_mask, dropout, seed)
+        if self.world_size > 1:
+            torch.distributed.all_reduce(self.grads)      # NCCL sum over NVLink; 1/N folded into the optimiser kernel
+        self.apply_update(lr)
+        self.step_count += 1
+        return self._cost.sum()
+
+
+# --------------------------------------------------------------------------------------
+# reference-named facades (constructor signatures of model-single-GPU.py)
+# --------------------------------------------------------------------------------------
+class Watcher_train:
+    def __init__(self, blocks, level, growth_rate, training, dropout_rate=0.2, dense_channels=0, transition=0.5,
+                 input_conv_filters=48, input_conv_stride=2, input_conv_kernel=(7, 7), engine: Optional[WAPEngine] = None):
+        if (blocks, level, growth_rate, float(dropout_rate), float(transition), input_conv_filters, input_conv_stride,
+                tuple(input_conv_kernel)) != (3, 16, 24, 0.2, 0.5, 48, 2, (7, 7)):
+            raise ValueError("the sm_100a kernels are specialised for the reference configuration "
+                             "(blocks=3, level=16, growth_rate=24, S:574)")
+        self.training = training
+        self.engine = engine or WAPEngine()
+        self.dense_channels = ANNOT_C
+
+    def dense_net(self, input_x, mask_x):
+        training = self.training() if callable(self.training) else bool(self.training)
+        return self.engine.dense_net(input_x, mask_x, training=training)
+
+
+class Attender:
+    def __init__(self, channels, dim_decoder, dim_attend, engine: Optional[WAPEngine] = None):
+        if (channels, dim_decoder, dim_attend) != (ANNOT_C, DIM_DEC, DIM_ATT):
+            raise ValueError("Attender is specialised for (684, 256, 512) (S:584)")
+        self.channels, self.dim_decoder, self.dim_attend = channels, dim_decoder, dim_attend
+        self.coverage_kernel = [11, 11]
+        self.engine = engine
+
+
+class Parser:
+    def __init__(self, hidden_dim, word_dim, attender, context_dim, engine: Optional[WAPEngine] = None):
+        if (hidden_dim, word_dim, context_dim) != (DIM_DEC, DIM_WORD, ANNOT_C):
+            raise ValueError("Parser is specialised for (256, 256, 684) (S:586)")
+        self.attender, self.hidden_dim, self.word_dim, self.context_dim = attender, hidden_dim, word_dim, context_dim
+        self.engine = engine or attender.engine
+
+
+class WAP:
+    def __init__(self, watcher, attender, parser, hidden_dim, word_dim, context_dim, target_dim, training):
+        if target_dim != VOCAB:
+            raise ValueError("target_dim must be 111 (S:490)")
+        self.watcher, self.attender, self.parser, self.training = watcher, attender, parser, training
+        self.engine: WAPEngine = watcher.engine
+        attender.engine = attender.engine or self.engine
+        parser.engine = parser.engine or self.engine
+
+    def get_cost(self, cost_annotation, cost_y, a_m, y_m):
+        training = self.training() if callable(self.training) else bool(self.training)
+        return self.engine.get_cost(cost_annotation, cost_y, a_m, y_m, dropout=training)
+
+    def get_word(self, sample_y, sample_h_pre, alpha_past_pre, sample_annotation):
+        p, w, h, ap = self.engine.get_word(sample_y, sample_h_pre, alpha_past_pre, sample_annotation)
+        return p, w, h, ap
+
+    def get_sample(self, ctx0, h_0=None, k=10, maxlen=100, stochastic=False):
+        if stochastic:
+            toks, lens, _ = self.engine.greedy_decode(ctx0, maxlen)
+            n = int(lens[0])
+            return [toks[0, :n].tolist()], [0.0]
+        best, sample, score = self.engine.get_sample(ctx0, k, maxlen)
+        return sample, score
