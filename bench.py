@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""bench.py — train images/s of the WAP hot path (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --gpus N --steps K --warmup W   (CPU arm: the oracle port, rank 0 only)
+
+One "step" = one full optimiser step of the reference's `sess.run([cost, trainer])`
+(model-single-GPU.py:640): DenseNet forward (batch-norm in batch-statistics mode, dropout 0.2),
+coverage-attention GRU scan over the caption, softmax-CE, backward through both, L2 + Adadelta
+update (and, for N>1, the NCCL all-reduce of the 5.4 M gradients), on BASELINE.json configs[1]:
+batch 8 synthetic 128x512 images with 40-token captions per GPU (configs[3] = the same at 8 GPUs).
+
+value  : images/s with the batch resident in HBM (device-timed, CUDA events, max over ranks)
+e2e    : same metric through WAPEngine.train_step() with pinned HOST buffers: H2D of x / masks /
+         captions and a D2H read of the cost inside every timed step
+roofline: dominant GEMM class, algorithmic FLOPs / CUDA-event time, vs the measured bf16 peak
+cpu_baseline: the CPU oracle (torch-CPU fp32 port of the TF graph) on a bounded sample
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "train images/sec (device-timed)"
+B_PER_GPU, IMG_H, IMG_W, CAP_LEN = 8, 128, 512, 40          # BASELINE.json configs[1]
+PROF_NAMES = ["conv1x1_fwd", "conv3x3_fwd", "transition_fwd", "conv3x3_wgrad", "conv3x3_dgrad", "conv1x1_wgrad",
+              "conv1x1_dgrad", "transition_bwd", "coverage_gemm", "other_gemm"]
+
+
+def make_workload(seed, B):
+    import wap_b200
+    from wap_b200 import synth
+    imgs, caps = synth.synth_batch(seed, B, IMG_H, IMG_W, CAP_LEN)
+    return wap_b200.prepare_data(imgs, caps)
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            p = json.load(fh)
+        return dict(hbm_gbs=p["hbm_gbs"], tf=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured (MEASURED_PEAKS.json, sustained)")
+    except Exception:
+        return dict(hbm_gbs=6650.0, tf=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(len(r) > 3 + i and r[3 + i].lower().startswith("active") for r in self.rows)]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons, samples=len(sm))
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def host_cores():
+    """CPU cores this process may actually use: affinity mask capped by the cgroup CPU quota."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as fh:
+            q, per = fh.read().split()
+        if q != "max":
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return n
+
+
+def cpu_oracle_images_per_s(B, steps, warmup, budget_s=90.0):
+    """Reference arm / cpu_baseline: the oracle port (same op sequence and redundancies as the TF
+    graph) doing full training steps in torch-CPU fp32 on the usable host cores.  Stops early once
+    `budget_s` of wall-clock is spent (at least one timed step)."""
+    import numpy as np
+    import torch
+    from oracle import wap_oracle as O
+    cores = host_cores()
+    torch.set_num_threads(cores)
+    P = O.init_params(0)
+    x, xm, y, ym = make_workload(2, B)
+    names = O.trainable_names(P)
+    acc = {n: np.zeros(P[n].shape, np.float32) for n in names}
+    accd = {n: np.zeros(P[n].shape, np.float32) for n in names}
+    ts, t_start = [], time.perf_counter()
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, _, P, acc, accd = O.train_step(P, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(100 + i), dtype=torch.float32)
+        ts.append(time.perf_counter() - t0)
+        log(f"cpu oracle step {i}: {ts[-1]:.2f} s ({cores} threads)")
+        if time.perf_counter() - t_start > budget_s and len(ts) > min(warmup, 1):
+            break
+    ts = ts[min(warmup, len(ts) - 1):]
+    return B * len(ts) / sum(ts), cores, sum(ts) / len(ts), len(ts)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Bs = 2   # bounded sample per step: 2 of the 8 images of the config (same H x W, same caption length)
+    v, cores, sps, nrun = cpu_oracle_images_per_s(Bs, args.steps, args.warmup, budget_s=240.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"WAP train step, {B_PER_GPU}x{IMG_H}x{IMG_W} images, {CAP_LEN}-token captions (BASELINE configs[1])",
+                   "sample_batch": Bs},
+        "cpu_baseline": {"value": v, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{nrun} training steps of {Bs} images {IMG_H}x{IMG_W}, T={CAP_LEN + 1} (oracle port of the TF-1.6 graph, "
+                                   f"torch-CPU fp32; TensorFlow 1.6 is not installable here)"},
+        "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import wap_b200
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_NET_DISABLE", "1")          # single node: NVLink / NVSwitch only
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    L = wap_b200._lib.lib()
+    eng = wap_b200.WAPEngine(device=dev, seed=0, init=True)    # same seed on every rank: replicated weights
+    eng.world_size = world
+    B = B_PER_GPU
+    x, xm, y, ym = make_workload(4 + rank, B)                   # per-rank shard of the global batch
+    xd = torch.as_tensor(x).to(dev); xmd = torch.as_tensor(xm).to(dev)
+    yd = torch.as_tensor(y).to(dev, dtype=torch.int32); ymd = torch.as_tensor(ym).to(dev)
+    # pinned host copies for the e2e leg
+    xp, xmp = torch.as_tensor(x).pin_memory(), torch.as_tensor(xm).pin_memory()
+    yp, ymp = torch.as_tensor(y).to(torch.int32).pin_memory(), torch.as_tensor(ym).pin_memory()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if dist is not None:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    step_res = lambda: eng.train_step(xd, yd, xmd, ymd, lr=1.0, dropout=True)                   # noqa: E731
+    step_e2e = lambda: float(eng.train_step(xp, yp, xmp, ymp, lr=1.0, dropout=True))            # noqa: E731  (H2D + D2H of cost)
+    nwarm = args.warmup if args.profile_run else max(args.warmup, 3)
+    for _ in range(nwarm):
+        step_res()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    log("warm-up done")
+    n0 = L.wap_launch_count()
+    ms = timed(step_res, args.steps)
+    log(f"resident leg: {ms / args.steps:.3f} ms/step")
+    launches = int(L.wap_launch_count() - n0)
+    clocks = sampler.stop() if rank == 0 else None
+    if args.profile_run:
+        print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms / args.steps, "gpu_launches": launches}))
+        return
+    for _ in range(2):
+        step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+    log(f"e2e leg: {ms_e2e / args.steps:.3f} ms/step")
+    cost = float(eng._cost.sum())
+    # roofline pass: the same steps again with every GEMM launch bracketed by CUDA events
+    prof = {}
+    L.wap_profile_reset(); L.wap_profile_enable(1)
+    psteps = min(args.steps, 3)
+    for _ in range(psteps):
+        step_res()
+    torch.cuda.synchronize()
+    L.wap_profile_enable(0)
+    t, n, f = C.c_double(), C.c_int64(), C.c_double()
+    for cls, name in enumerate(PROF_NAMES):
+        wap_b200._lib.check(L.wap_profile_read(cls, C.byref(t), C.byref(n), C.byref(f)), "wap_profile_read")
+        if n.value:
+            prof[name] = dict(ms_per_step=t.value / psteps, launches_per_step=n.value // psteps, gflop_per_step=f.value / psteps / 1e9,
+                              tflops=f.value / (t.value * 1e-3) / 1e12 if t.value > 0 else 0.0)
+    L.wap_profile_reset()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    top = max((k for k in prof if k != "other_gemm"), key=lambda k: prof[k]["ms_per_step"])
+    gemm_ms = sum(v["ms_per_step"] for v in prof.values())
+    roof = {"bound": "tensor", "kernel": f"gemm_kernel<{top}> (fp32 FFMA implicit GEMM)", "achieved": prof[top]["tflops"], "peak": pk["tf"],
+            "unit": "TFLOP/s", "frac": prof[top]["tflops"] / pk["tf"], "traffic": None, "peak_source": pk["src"],
+            "share_of_step": prof[top]["ms_per_step"] / (ms / args.steps),
+            "all_gemm_share_of_step": gemm_ms / (ms / args.steps), "classes": prof,
+            "note": "fp32 CUDA-core path measured against the bf16 tensor-core peak; per-launch CUDA events over a second pass of the same steps"}
+    log("gpu legs done; cpu baseline ...")
+    cpu_v, cores, cpu_sps, cpu_n = cpu_oracle_images_per_s(B, 2, 1, 60.0) if (world == 1 and not args.no_cpu_baseline) else (None, None, None, 0)
+    h2d = sum(t_.numel() * t_.element_size() for t_ in (xp, xmp, yp, ymp))
+    line = {
+        "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": nwarm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"WAP train step (fwd+bwd+L2/Adadelta), {B}x{IMG_H}x{IMG_W} images/GPU, {CAP_LEN}-token captions "
+                               f"(BASELINE configs[1]; configs[3] at 8 GPUs)", "global_batch": world * B,
+                   "parallelism": f"dp{world}" + (" (NCCL all-reduce of 5.4M fp32 grads)" if world > 1 else ""),
+                   "l2_flush": "none needed: per-step working set (~1.3 GB of saved activations) exceeds the 126 MB L2",
+                   "dropout": 0.2, "final_cost": cost},
+        "clocks": clocks,
+        "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": launches,
+        "roofline": roof,
+    }
+    if cpu_v is not None:
+        line["cpu_baseline"] = {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
+                                "sample": f"{cpu_n} training step(s) (after 1 warm-up) of the full {B}x{IMG_H}x{IMG_W}, T={CAP_LEN + 1} batch; "
+                                          f"oracle port of the TF-1.6 graph in torch-CPU fp32 ({cpu_sps:.2f} s/step)"}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="under ncu: honour --warmup exactly, skip e2e/roofline/cpu legs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -100,6 +100,17 @@ int wap_adadelta_l2_step(void* stream, float* params, const float* grads, float*
                          int64_t n, int64_t n_decay, float lr, float rho, float eps, float l2, float grad_scale,
                          double* l2_cost);
 
+/* ---- instrumentation for bench.py
+ * wap_launch_count: kernels launched by this library since load (cumulative).
+ * wap_profile_*: when enabled, every GEMM / implicit-GEMM launch is bracketed by cudaEvents on its
+ * stream; wap_profile_read sums device time (ms), launches and algorithmic FLOPs (2*M*N*K) of class
+ * `cls`: 0 conv1x1 fwd, 1 conv3x3 fwd, 2 transition fwd, 3 conv3x3 wgrad, 4 conv3x3 dgrad,
+ * 5 conv1x1 wgrad, 6 conv1x1 dgrad, 7 transition bwd, 8 coverage GEMM, 9 other GEMMs. */
+uint64_t wap_launch_count(void);
+int wap_profile_enable(int on);
+int wap_profile_read(int cls, double* ms, int64_t* launches, double* flops);
+int wap_profile_reset(void);
+
 /* ---- fp32 GEMM primitives (exported for the kernel-level parity tests) */
 int wap_gemm_nn(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K,
                 const float* bias, int accumulate);

@@ -465,7 +465,7 @@ def train_step(P_np, acc, acc_delta, x, x_mask, y, y_mask, lr: float, drop: Drop
         newP[n] = (P_np[n].astype(np.float64) - lr * d).astype(P_np[n].dtype)
     for n, v in new_moving.items():
         newP[n] = v.detach().numpy().astype(P_np[n].dtype)
-    return float(cost), G, newP, newA, newD
+    return float(cost.detach()), G, newP, newA, newD
 
 
 # --------------------------------------------------------------------------------------

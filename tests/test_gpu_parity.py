@@ -278,7 +278,10 @@ def test_adadelta_l2_step(report):
 
 
 def test_train_steps_match_oracle(report):
-    """Two full optimiser steps (cost incl. L2, updated weights, moving statistics) vs the oracle."""
+    """Two full optimiser steps (cost incl. L2, updated weights, Adadelta state, moving statistics).
+    Before each step the engine is synchronised to the oracle's state, so each step is compared from
+    identical inputs (Adadelta's early updates are ~sqrt(eps)*sign(g): elements whose gradient is
+    rounding noise may legitimately flip sign, hence the sign-stable subset + quantile criteria)."""
     B, H, W, cap = 2, 32, 48, 3
     P = O.lively_params(9)
     eng = engine_with(P)
@@ -290,25 +293,33 @@ def test_train_steps_match_oracle(report):
     for step in range(2):
         x, xm, y, ym = make_batch(60 + step, B, H, W, cap, True)
         seed = 500 + step
+        eng.P.load(Pn); eng.P.pack_into(eng.accum, acc); eng.P.pack_into(eng.accum_update, accd)
+        Pprev = Pn
         cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
-        ref_cost, _, Pn, acc, accd = O.train_step(Pn, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
+        ref_cost, G, Pn, acc, accd = O.train_step(Pprev, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
         e = abs(cost - ref_cost) / abs(ref_cost)
         report.add("train_step", f"cost_step{step}", e, REL_TOL, extra=dict(got=cost, ref=ref_cost))
         if e > REL_TOL:
             fails.append(("cost", step, cost, ref_cost))
         sd = eng.P.state_dict()
-        # Adadelta's first steps are ~ sqrt(eps)*sign(g): elements whose gradient is rounding noise may
-        # flip sign, so compare the parameter *change* on the 99.5 % quantile of elements.
-        diffs = []
+        acc_e = eng.P.unpack(eng.accum)
+        diffs, stable_worst, acc_worst = [], 0.0, 0.0
         for n in names:
-            d_got = sd[n].astype(np.float64) - P[n]; d_ref = Pn[n].astype(np.float64) - P[n]
-            diffs.append((np.abs(d_got - d_ref) / max(float(np.max(np.abs(d_ref))), 1e-12)).ravel())
-        q = float(np.quantile(np.concatenate(diffs), 0.995))
-        report.add("train_step", f"param_delta_q995_step{step}", q, 2e-2)
-        if q > 2e-2:
-            fails.append(("delta", step, q))
+            d_got = sd[n].astype(np.float64) - Pprev[n]; d_ref = Pn[n].astype(np.float64) - Pprev[n]
+            dn = np.abs(d_got - d_ref) / max(float(np.max(np.abs(d_ref))), 1e-12)
+            diffs.append(dn.ravel())
+            stable = np.abs(G[n]) > 1e-3 * np.max(np.abs(G[n]))
+            if stable.any():
+                stable_worst = max(stable_worst, float(dn[stable].max()))
+            acc_worst = max(acc_worst, rel_err(acc_e[n], acc[n]))
+        q = float(np.quantile(np.concatenate(diffs), 0.99))
+        report.add("train_step", f"param_delta_q99_step{step}", q, 2e-2)
+        report.add("train_step", f"param_delta_sign_stable_worst_step{step}", stable_worst, 2e-2)
+        report.add("train_step", f"adadelta_accum_worst_step{step}", acc_worst, 1e-3)
+        if q > 2e-2 or stable_worst > 2e-2 or acc_worst > 1e-3:
+            fails.append(("delta", step, q, stable_worst, acc_worst))
         mv = max(rel_err(sd[n], Pn[n]) for n in P if n.endswith("moving_variance") or n.endswith("moving_mean"))
-        report.add("train_step", f"moving_stats_step{step}", mv, 5e-3)
-        if mv > 5e-3:
+        report.add("train_step", f"moving_stats_step{step}", mv, 1e-3)
+        if mv > 1e-3:
             fails.append(("moving", step, mv))
     assert not fails, fails

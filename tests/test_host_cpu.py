@@ -1,0 +1,209 @@
+"""Host-side logic that runs without a GPU: the C-ABI library loads and exports every symbol of
+include/wap_abi.h, parameter layout vs the reference variable set, geometry, loader parity,
+fail-loud behaviour, and the N>1 data-parallel plumbing over gloo (world_size 2)."""
+import os
+import pickle
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, ROOT
+
+import wap_b200  # noqa: E402
+from wap_b200 import _lib  # noqa: E402
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "wap_abi.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(wap_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    fns = _header_functions()
+    assert len(fns) >= 25
+    L = _lib.lib()
+    for f in fns:
+        assert hasattr(L, f), f"libwap_b200.so does not export {f}"
+        assert f in _lib.SIGNATURES, f"_lib.SIGNATURES lacks {f}"
+    assert sorted(_lib.SIGNATURES) == fns
+    assert L.wap_abi_version() == 1
+
+
+def test_param_layout_matches_reference_variable_set():
+    table = _lib.param_table()
+    P = O.init_params(0)
+    assert {n for n, _, _, _ in table} == set(P)
+    flat_end = 0
+    for name, off, shape, flags in table:
+        assert tuple(P[name].shape) == tuple(shape), name
+        assert off % 4 == 0, name
+        if not flags & 2:
+            flat_end = max(flat_end, off + int(np.prod(shape)))
+    n, nd = _lib.lib().wap_param_floats(), _lib.lib().wap_decay_floats()
+    assert n >= flat_end and n - 5428520 < 16 and n % 4 == 0
+    l2 = set(O.l2_names(P))
+    for name, off, shape, flags in table:
+        if flags & 2:
+            assert name.endswith(("moving_mean", "moving_variance"))
+            continue
+        assert bool(flags & 1) == (name in l2), name
+        assert (off < nd) == (name in l2), name          # decayed tensors first, BN gamma/beta after
+    # TF creation order of the conv kernels (checkpoint-compatible names)
+    convs = [n for n, _, _, _ in table if n.endswith("/kernel")]
+    assert convs == [O.conv_name(k) for k in range(99)]
+
+
+@pytest.mark.parametrize("H,W", [(64, 256), (128, 512), (37, 75), (1, 1), (17, 16), (320, 1250)])
+def test_annotation_geometry(H, W):
+    import ctypes as C
+    h, w = C.c_int(), C.c_int()
+    assert _lib.lib().wap_annotation_hw(H, W, C.byref(h), C.byref(w)) == 0
+    c = lambda v: -(-v // 2)  # noqa: E731
+    assert (h.value, w.value) == (c(c(c(c(H)))), c(c(c(c(W)))))
+    assert _lib.lib().wap_encoder_workspace_floats(2, H, W, 1) > _lib.lib().wap_encoder_workspace_floats(2, H, W, 0) > 0
+    assert _lib.lib().wap_decoder_train_workspace_floats(2, h.value, w.value, 5) > 0
+    assert _lib.lib().wap_greedy_workspace_floats(2, h.value, w.value) > _lib.lib().wap_decoder_step_workspace_floats(2, h.value, w.value) > 0
+
+
+def test_bad_arguments_report_errors():
+    L = _lib.lib()
+    assert L.wap_annotation_hw(0, 5, None, None) != 0
+    assert b"bad size" in L.wap_last_error()
+    assert L.wap_param_info(10 ** 6, None, 0, None, None, None, None) != 0
+    with pytest.raises(_lib.WapError):
+        _lib.check(L.wap_encoder_forward(None, None, None, None, 1, 8, 8, 0, 0, 0, None, None), "wap_encoder_forward")
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful without a GPU")
+def test_engine_fails_loudly_without_gpu():
+    with pytest.raises(_lib.WapError):
+        wap_b200.WAPEngine()
+
+
+def test_missing_library_fails_loudly(tmp_path, monkeypatch):
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "nope.so"))
+    monkeypatch.setattr(_lib, "_lib", None)
+    with pytest.raises(_lib.WapError, match="no CPU fallback"):
+        _lib.lib()
+
+
+# ------------------------------------------------------------------ loader (data.py)
+def _fake_corpus(tmp_path, n=23, seed=0):
+    rs = np.random.RandomState(seed)
+    vocab = {f"t{i}": i for i in range(1, 12)}; vocab["<eol>"] = 0
+    feats, lines = {}, []
+    for i in range(n):
+        H, W = int(rs.randint(8, 40)), int(rs.randint(8, 90))
+        feats[f"u{i}"] = rs.randint(0, 256, size=(1, H, W)).astype(np.uint8)
+        L = int(rs.randint(1, 9)) if i != 5 else 30           # one over-long caption
+        lines.append(f"u{i}\t" + " ".join(f"t{int(t)}" for t in rs.randint(1, 12, size=L)))
+    feats["big"] = np.zeros((1, 80, 80), np.uint8); lines.append("big\tt1 t2")    # one over-large image
+    (tmp_path / "f.pkl").write_bytes(pickle.dumps(feats))
+    (tmp_path / "c.txt").write_text("\n".join(lines) + "\n")
+    (tmp_path / "d.txt").write_text("\n".join(f"{k}\t{v}" for k, v in vocab.items()) + "\n")
+    return tmp_path
+
+
+def test_prepare_data_matches_oracle():
+    imgs, caps = O.synth_batch(3, 4, 30, 50, 6, ragged=True)
+    a = wap_b200.prepare_data(imgs, caps); b = O.prepare_data(imgs, caps)
+    for u, v in zip(a, b):
+        assert u.dtype == v.dtype and np.array_equal(u, v)
+    assert a[2].dtype == np.int64 and a[2].shape == (7, 4) and a[3][:, 0].sum() == 7
+
+
+def test_data_iterator_bucketing_invariants(tmp_path, capsys):
+    d = _fake_corpus(tmp_path)
+    lex = wap_b200.load_dict(str(d / "d.txt"))
+    assert lex["<eol>"] == 0 and len(lex) == 12
+    batches, uids = wap_b200.dataIterator(str(d / "f.pkl"), str(d / "c.txt"), lex, batch_size=4, batch_Imagesize=6000, maxlen=10, maxImagesize=5000)
+    assert "u5" not in uids and "big" not in uids and len(uids) == 22
+    areas = []
+    for xs, ys in batches:
+        assert len(xs) == len(ys) <= 4
+        if xs:
+            assert max(a.shape[1] * a.shape[2] for a in xs) * len(xs) <= 6000
+            areas += [a.shape[1] * a.shape[2] for a in xs]
+    assert areas == sorted(areas) and len(areas) == 22
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data.py"), reason="reference checkout not present")
+def test_data_iterator_matches_reference_implementation(tmp_path):
+    """Runs the reference's own data.py (imported from /root/reference, read-only) on a synthetic
+    corpus and compares batch composition, uid order and prepare_data output."""
+    d = _fake_corpus(tmp_path, n=41, seed=3)
+    code = (
+        "import sys, pickle; sys.path.insert(0, '/root/reference'); import data as R\n"
+        f"lex = R.load_dict('{d}/d.txt')\n"
+        f"b, u = R.dataIterator('{d}/f.pkl', '{d}/c.txt', lex, 4, 6000, 10, 5000)\n"
+        "out = [(len(x), [a.shape for a in x], y) for x, y in b]\n"
+        "pd = R.prepare_data(b[2][0], b[2][1])\n"
+        f"pickle.dump((out, u, pd), open('{d}/ref.pkl', 'wb'))\n")
+    subprocess.run([sys.executable, "-c", code], check=True, capture_output=True)
+    ref_out, ref_u, ref_pd = pickle.load(open(d / "ref.pkl", "rb"))
+    lex = wap_b200.load_dict(str(d / "d.txt"))
+    b, u = wap_b200.dataIterator(str(d / "f.pkl"), str(d / "c.txt"), lex, 4, 6000, 10, 5000)
+    assert u == ref_u
+    assert [(len(x), [a.shape for a in x], y) for x, y in b] == ref_out
+    for got, ref in zip(wap_b200.prepare_data(b[2][0], b[2][1]), ref_pd):
+        assert got.dtype == ref.dtype and np.array_equal(got, ref)
+
+
+def test_synthetic_generators_agree():
+    from wap_b200 import synth
+    for rag in (False, True):
+        a = synth.synth_batch(5, 3, 40, 72, 6, rag); b = O.synth_batch(5, 3, 40, 72, 6, rag)
+        assert all(np.array_equal(x, y) for x, y in zip(a[0], b[0])) and a[1] == b[1]
+
+
+# ------------------------------------------------------------------ data-parallel plumbing over gloo
+_DP_WORKER = r'''
+import os, sys, numpy as np, torch
+sys.path.insert(0, os.environ["WAP_ROOT"])
+import wap_b200
+from wap_b200 import dp
+rank, world, local = dp.init_distributed("gloo")
+assert world == 2
+n = wap_b200._lib.lib().wap_param_floats()
+rs = np.random.RandomState(100 + rank)
+g = torch.as_tensor(rs.randn(n).astype(np.float32))            # this replica's flat gradient
+mine = g.clone()
+dp.allreduce_sum_(g)                                             # what WAPEngine.train_step does for N > 1
+other = torch.as_tensor(np.random.RandomState(100 + (1 - rank)).randn(n).astype(np.float32))
+assert torch.allclose(g, mine + other, atol=1e-6)
+mean = g * (1.0 / world)                                         # grad_scale folded into wap_adadelta_l2_step
+assert torch.allclose(mean, (mine + other) / 2, atol=1e-6)
+p = torch.full((8,), float(rank)); dp.broadcast_params(p, 0); assert float(p.sum()) == 0.0
+m = torch.full((4,), float(rank + 1)); dp.sync_moving_stats(m); assert torch.allclose(m, torch.full((4,), 1.5))
+shards = dp.shard_batches(list(range(11)), rank, world)
+assert len(shards) == 5 and all(s % world == rank for s in shards)
+print(f"DP_OK {rank}\n", end="", flush=True)
+'''
+
+
+def test_dp_plumbing_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"; script.write_text(_DP_WORKER)
+    env = dict(os.environ, WAP_ROOT=ROOT, OMP_NUM_THREADS="1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29611", str(script)], env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("DP_OK") == 2
+
+
+def test_dp_mean_of_replica_gradients_equals_oracle_semantics():
+    """SyncReplicasOptimizer semantics (model-distributed.py:704-717): one update with the MEAN of the
+    replica gradients == the oracle's train_step fed the other replica's gradient with inv_world = 1/2."""
+    P = O.lively_params(1)
+    names = O.trainable_names(P)
+    z = {n: np.zeros(P[n].shape) for n in names}
+    xa = O.prepare_data(*O.synth_batch(1, 1, 20, 28, 2)); xb = O.prepare_data(*O.synth_batch(2, 1, 20, 28, 2))
+    _, Ga, _, _, _ = O.train_step(P, z, dict(z), *xa, 1.0)
+    _, Gb, _, _, _ = O.train_step(P, z, dict(z), *xb, 1.0)
+    _, G, P2, _, _ = O.train_step(P, z, dict(z), *xa, 1.0, extra_grads=Gb, inv_world=0.5)
+    for n in names[:40]:
+        np.testing.assert_allclose(G[n], 0.5 * (Ga[n] + Gb[n]), rtol=1e-12, atol=1e-15)

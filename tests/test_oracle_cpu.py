@@ -1,0 +1,201 @@
+"""Pins for the CPU oracle itself (no GPU): brute-force TF 'SAME' op semantics, batch-norm
+semantics, fp64 finite-difference gradient checks, golden vectors, model-size constants, scorer."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, ROOT, t64
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+# ------------------------------------------------------------------ brute-force 'SAME' ops
+def _conv_same_loops(x, w, s):
+    B, H, W, Ci = x.shape; kh, kw, _, Co = w.shape
+    Ho, pt, _ = O.same_pad(H, kh, s); Wo, pl, _ = O.same_pad(W, kw, s)
+    y = np.zeros((B, Ho, Wo, Co))
+    for b in range(B):
+        for i in range(Ho):
+            for j in range(Wo):
+                for u in range(kh):
+                    for v in range(kw):
+                        yy, xx = i * s - pt + u, j * s - pl + v
+                        if 0 <= yy < H and 0 <= xx < W:
+                            y[b, i, j] += x[b, yy, xx] @ w[u, v]
+    return y
+
+
+@pytest.mark.parametrize("H,W,k,s", [(6, 7, 7, 2), (7, 6, 7, 2), (5, 4, 3, 1), (4, 5, 11, 1), (3, 3, 1, 1), (9, 8, 7, 2)])
+def test_conv_same_matches_loops(H, W, k, s):
+    rs = np.random.RandomState(H * 10 + W)
+    x = rs.randn(2, H, W, 2); w = rs.randn(k, k, 2, 3)
+    got = O.conv2d_same(t64(x), t64(w), s).numpy()
+    assert got.shape == (2, -(-H // s), -(-W // s), 3)
+    np.testing.assert_allclose(got, _conv_same_loops(x, w, s), atol=1e-10)
+
+
+def test_stem_padding_is_asymmetric_on_even_sizes():
+    # TF SAME, k=7, s=2, even input: 2 before / 3 after (torch padding=3 would be wrong)
+    assert O.same_pad(128, 7, 2) == (64, 2, 3)
+    assert O.same_pad(127, 7, 2) == (64, 3, 3)
+    assert O.same_pad(9, 3, 1) == (9, 1, 1) and O.same_pad(9, 11, 1) == (9, 5, 5)
+
+
+@pytest.mark.parametrize("H,W", [(4, 4), (5, 3), (1, 7), (6, 5)])
+def test_pools_same_match_loops(H, W):
+    rs = np.random.RandomState(H + 31 * W)
+    x = rs.randn(2, H, W, 3)
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    mx = np.full((2, Ho, Wo, 3), -np.inf); sm = np.zeros((2, Ho, Wo, 3)); cnt = np.zeros((Ho, Wo))
+    for i in range(H):
+        for j in range(W):
+            mx[:, i // 2, j // 2] = np.maximum(mx[:, i // 2, j // 2], x[:, i, j])
+            sm[:, i // 2, j // 2] += x[:, i, j]; cnt[i // 2, j // 2] += 1
+    np.testing.assert_allclose(O.maxpool2_same(t64(x)).numpy(), mx, atol=1e-12)
+    np.testing.assert_allclose(O.avgpool2_same(t64(x)).numpy(), sm / cnt[None, :, :, None], atol=1e-12)
+
+
+def test_batch_norm_semantics():
+    rs = np.random.RandomState(0)
+    x = rs.randn(3, 4, 5, 6) * 2 + 1
+    g, b = rs.randn(6), rs.randn(6); mm, mv = rs.randn(6), rs.rand(6) + 0.5
+    y, (nm, nv) = O.batch_norm(t64(x), t64(g), t64(b), t64(mm), t64(mv), True)
+    mean = x.reshape(-1, 6).mean(0); var = x.reshape(-1, 6).var(0)            # biased
+    np.testing.assert_allclose(y.numpy(), (x - mean) / np.sqrt(var + 1e-4) * g + b, atol=1e-10)
+    n = 3 * 4 * 5
+    np.testing.assert_allclose(nm.numpy(), 0.9 * mm + 0.1 * mean, atol=1e-12)
+    np.testing.assert_allclose(nv.numpy(), 0.9 * mv + 0.1 * var * n / (n - 1), atol=1e-12)   # Bessel-corrected (fused kernel)
+    yi, _ = O.batch_norm(t64(x), t64(g), t64(b), t64(mm), t64(mv), False)
+    np.testing.assert_allclose(yi.numpy(), (x - mm) / np.sqrt(mv + 1e-4) * g + b, atol=1e-10)
+
+
+# ------------------------------------------------------------------ model-size constants
+def test_model_sizes():
+    P = O.init_params(0)
+    tr = O.trainable_names(P)
+    assert len(P) == 527 and len(tr) == 329
+    assert sum(P[n].size for n in tr) == 5428520
+    enc = [n for n in tr if n.startswith(("conv2d", "batch_normalization"))]
+    assert sum(P[n].size for n in enc) == 2979384
+    assert sum(P[n].size for n in O.l2_names(P)) == 5415872
+    plan = O.encoder_plan()
+    assert len(plan) == 99 and plan[33]["kind"] == "tr" and plan[66]["kind"] == "tr" and plan[33]["cin"] == 432 and plan[66]["cout"] == 300
+    imgs, caps = O.synth_batch(1, 1, 64, 256, 10)
+    x, xm, y, ym = O.prepare_data(imgs, caps)
+    assert y.shape == (11, 1) and ym.sum() == 11
+    Pt = O.to_torch(P)
+    ann, am, _ = O.dense_net(Pt, t64(x), t64(xm), False)
+    assert tuple(ann.shape) == (1, 4, 16, 684) and tuple(am.shape) == (1, 4, 16)
+
+
+# ------------------------------------------------------------------ finite differences (fp64)
+def _fd_check(f, tensors, names, n_dirs=3, eps=1e-6, seed=0):
+    cost = f()
+    grads = torch.autograd.grad(cost, [tensors[n] for n in names])
+    rs = np.random.RandomState(seed)
+    for _ in range(n_dirs):
+        dirs = [torch.as_tensor(rs.randn(*tensors[n].shape)) for n in names]
+        ana = sum(float((g * d).sum()) for g, d in zip(grads, dirs))
+        with torch.no_grad():
+            for n, d in zip(names, dirs): tensors[n].add_(eps * d)
+            cp = float(f())
+            for n, d in zip(names, dirs): tensors[n].sub_(2 * eps * d)
+            cm = float(f())
+            for n, d in zip(names, dirs): tensors[n].add_(eps * d)
+        num = (cp - cm) / (2 * eps)
+        assert abs(num - ana) <= 1e-5 * max(1.0, abs(ana)), (num, ana)
+
+
+def test_fd_gradient_decoder():
+    P = O.to_torch(O.lively_params(1), torch.float64, requires_grad=True)
+    rs = np.random.RandomState(2)
+    ann = t64(np.maximum(rs.randn(2, 3, 4, O.ANNOT_C), 0)).requires_grad_(True)
+    am = torch.ones(2, 3, 4, dtype=torch.float64); am[1, :, 3] = 0
+    y = torch.as_tensor(rs.randint(1, 111, size=(4, 2))); y[3, :] = 0; y[2, 1] = 0
+    ym = torch.ones(4, 2, dtype=torch.float64); ym[3, 1] = 0
+    tensors = dict(P); tensors["__ann"] = ann
+    names = [n for n in O.trainable_names(P) if not n.startswith(("conv2d", "batch_normalization"))] + ["__ann"]
+    _fd_check(lambda: O.get_cost(P, ann, y, am, ym), tensors, names)
+
+
+def test_fd_gradient_encoder_training_mode():
+    P = O.to_torch(O.lively_params(2), torch.float64, requires_grad=True)
+    imgs, caps = O.synth_batch(3, 2, 20, 36, 2, ragged=True)
+    x, xm, _, _ = O.prepare_data(imgs, caps)
+    rs = np.random.RandomState(4)
+    proj = None
+
+    def f():
+        nonlocal proj
+        ann, _, _ = O.dense_net(P, t64(x), t64(xm), True, O.hash_drop_fn(5))
+        if proj is None:
+            proj = t64(rs.randn(*ann.shape))
+        return (ann * proj).sum()
+    names = [n for n in O.trainable_names(P) if n.startswith(("conv2d", "batch_normalization"))]
+    _fd_check(f, P, names, n_dirs=2, eps=1e-6)
+
+
+# ------------------------------------------------------------------ golden vectors
+def test_golden_cfg1_forward():
+    g = np.load(os.path.join(GOLDEN, "cfg1_forward.npz"))
+    imgs, caps = O.synth_batch(int(g["data_seed"]), 1, 64, 256, 10)
+    x, xm, y, ym = O.prepare_data(imgs, caps)
+    P = O.calibrate_moving(O.lively_params(int(g["param_seed"])), x, xm)
+    Pt = O.to_torch(P)
+    ann, am, _ = O.dense_net(Pt, t64(x), t64(xm), False)
+    np.testing.assert_allclose(ann.numpy(), g["annotation"], rtol=0, atol=2e-6 * np.abs(g["annotation"]).max())
+    cost = O.get_cost(Pt, ann, torch.as_tensor(y), am, t64(ym))
+    assert abs(float(cost) - float(g["cost"])) < 1e-8 * abs(float(g["cost"]))
+    assert O.greedy_decode(Pt, ann, 30) == g["greedy"].tolist()
+    assert list(O.beam_decode(Pt, ann, 10, 30)[0]) == g["beam"].tolist()
+
+
+def test_golden_small_train():
+    g = np.load(os.path.join(GOLDEN, "small_train.npz"))
+    imgs, caps = O.synth_batch(int(g["data_seed"]), 2, 32, 48, 3, ragged=True)
+    x, xm, y, ym = O.prepare_data(imgs, caps)
+    P = O.to_torch(O.lively_params(int(g["param_seed"])), torch.float64, requires_grad=True)
+    dfn = O.hash_drop_fn(int(g["drop_seed"]))
+    ann, am, nm = O.dense_net(P, t64(x), t64(xm), True, dfn)
+    cost = O.get_cost(P, ann, torch.as_tensor(y), am, t64(ym), dfn)
+    assert abs(float(cost) - float(g["cost"])) < 1e-9 * abs(float(g["cost"]))
+    names = [k[6:] for k in g.files if k.startswith("grad::")]
+    grads = torch.autograd.grad(cost, [P[n] for n in names])
+    for n, gr in zip(names, grads):
+        ref = g["grad::" + n]
+        np.testing.assert_allclose(gr.numpy(), ref, rtol=0, atol=2e-6 * max(np.abs(ref).max(), 1e-12))
+    np.testing.assert_allclose(nm["batch_normalization_98/moving_variance"].numpy(), g["moving_variance_98"], rtol=1e-6)
+
+
+# ------------------------------------------------------------------ misc semantics
+def test_dropout_hash_statistics_and_determinism():
+    a = O.drop_hash_keep(1234, 5, 200000); b = O.drop_hash_keep(1234, 5, 200000)
+    assert np.array_equal(a, b) and abs(a.mean() - 0.8) < 5e-3
+    assert not np.array_equal(a, O.drop_hash_keep(1234, 6, 200000))
+    assert not np.array_equal(a, O.drop_hash_keep(1235, 5, 200000))
+
+
+def test_get_word_first_step_uses_zero_embedding_and_gate_order():
+    P = O.to_torch(O.lively_params(3))
+    rs = np.random.RandomState(1)
+    ann = t64(np.maximum(rs.randn(1, 2, 3, O.ANNOT_C), 0))
+    h = O.hidden_state_0(P, ann); ap = torch.zeros(1, 2, 3, dtype=torch.float64)
+    p, h1, ap1, _ = O.get_word(P, torch.tensor([-1]), h, ap, ann)
+    assert abs(float(p.sum()) - 1) < 1e-12 and abs(float(ap1.sum()) - 1) < 1e-12
+    # r is the FIRST half of the gate vector (model-single-GPU.py:276-277)
+    g = torch.sigmoid(P["b_yz_yr"] + h @ P["U_hz_hr"])
+    r1, z1 = g[:, :256], g[:, 256:]
+    prop = torch.tanh((h @ P["U_rh"]) * r1 + P["b_yh"])
+    pre_h = z1 * h + (1 - z1) * prop
+    ctx, _, _ = O.get_context(P, ann, pre_h, ap, None)
+    assert ctx.shape == (1, O.ANNOT_C)
+
+
+def test_wer_exprate_scorer():
+    rec = {"a": ["x", "y", "z"], "b": ["1", "2"], "c": []}
+    lab = {"a": ["x", "z"], "b": ["1", "2"], "c": ["q"]}
+    wer, exp = O.wer_exprate(rec, lab)
+    assert abs(wer - (1 + 0 + 1) / 5) < 1e-12 and abs(exp - 1 / 3) < 1e-12
+    assert O.edit_distance([1, 2, 3], [1, 3]) == 1 and O.edit_distance([], [1, 2]) == 2

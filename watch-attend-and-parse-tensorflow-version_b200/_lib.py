@@ -40,6 +40,10 @@ SIGNATURES = {
     "wap_decoder_train_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
     "wap_decoder_train_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
     "wap_adadelta_l2_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _f, _vp]),
+    "wap_launch_count": (C.c_uint64, []),
+    "wap_profile_enable": (_i, [_i]),
+    "wap_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)]),
+    "wap_profile_reset": (_i, []),
     "wap_gemm_nn": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
     "wap_gemm_nt": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
     "wap_gemm_tn_atomic": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i]),

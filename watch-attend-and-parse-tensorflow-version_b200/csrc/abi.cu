@@ -1,6 +1,8 @@
 // extern "C" surface of libwap_b200.so (declared in include/wap_abi.h).
 #include <stdarg.h>
 
+#include <vector>
+
 #include "../../include/wap_abi.h"
 #include "gemm.cuh"
 #include "model.h"
@@ -8,6 +10,27 @@
 namespace wap {
 
 static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+
+// ---- per-class device timing
+struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+static std::vector<cudaEvent_t> g_ev_pool;
+static cudaEvent_t ev_get() {
+  if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
+  cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+void prof_begin(cudaStream_t st, int cls, double flops) {
+  if (!g_prof_on) return;
+  ProfRec r; r.a = ev_get(); r.b = ev_get(); r.cls = cls; r.flops = flops;
+  cudaEventRecord(r.a, st);
+  g_prof.push_back(r);
+}
+void prof_end(cudaStream_t st, int cls) {
+  if (!g_prof_on || g_prof.empty()) return;
+  cudaEventRecord(g_prof.back().b, st);
+}
 void set_error(const char* fmt, ...) {
   va_list ap; va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
@@ -47,6 +70,26 @@ using namespace wap;
 extern "C" {
 
 int wap_abi_version(void) { return WAP_ABI_VERSION; }
+uint64_t wap_launch_count(void) { return g_launches; }
+int wap_profile_enable(int on) { g_prof_on = on != 0; return 0; }
+int wap_profile_read(int cls, double* ms, int64_t* launches, double* flops) {
+  double t = 0.0, f = 0.0; int64_t n = 0;
+  for (const ProfRec& r : g_prof) {
+    if (r.cls != cls) continue;
+    float e = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&e, r.a, r.b) != cudaSuccess) {
+      set_error("wap_profile_read: event query failed"); return -2;
+    }
+    t += e; f += r.flops; ++n;
+  }
+  if (ms) *ms = t; if (launches) *launches = n; if (flops) *flops = f;
+  return 0;
+}
+int wap_profile_reset(void) {
+  for (const ProfRec& r : g_prof) { g_ev_pool.push_back(r.a); g_ev_pool.push_back(r.b); }
+  g_prof.clear();
+  return 0;
+}
 const char* wap_last_error(void) { return g_err; }
 
 int wap_param_count(void) { return (int)layout().tensors.size(); }

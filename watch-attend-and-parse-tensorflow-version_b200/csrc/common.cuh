@@ -17,7 +17,17 @@ void set_error(const char* fmt, ...);          // abi.cu (thread-local message)
       return -2;                                                                     \
     }                                                                                \
   } while (0)
-#define WAP_LAUNCH_CHECK() WAP_CHECK(cudaGetLastError())
+extern unsigned long long g_launches;          // abi.cu: kernels launched by this library (cumulative)
+#define WAP_LAUNCH_CHECK()                                                           \
+  do { ++::wap::g_launches; WAP_CHECK(cudaGetLastError()); } while (0)
+
+// optional per-launch-class device timing (cudaEvents on the launching stream); see wap_profile_*()
+enum ProfClass {
+  kProfConv1Fwd = 0, kProfConv3Fwd, kProfTransFwd, kProfConv3Wgrad, kProfConv3Dgrad, kProfConv1Wgrad, kProfConv1Dgrad,
+  kProfTransBwd, kProfCovGemm, kProfOtherGemm, kProfNumClasses
+};
+void prof_begin(cudaStream_t st, int cls, double flops);
+void prof_end(cudaStream_t st, int cls);
 #define WAP_REQUIRE(cond, ...)                                                       \
   do {                                                                               \
     if (!(cond)) { ::wap::set_error(__VA_ARGS__); return -1; }                       \

@@ -11,7 +11,7 @@ namespace wap {
 __global__ void __launch_bounds__(256)
 ann_mean_kernel(const float* __restrict__ ann, const float* __restrict__ a_mask, float* __restrict__ mean, int L) {
   extern __shared__ float sm[];          // w[L] | red[64] | part[16][64]
-  float* s_w = sm; float* red = sm + L; float* part = red + 64;
+  float* s_w = sm; float* red = sm + ((L + 3) & ~3); float* part = red + 64;
   const int b = blockIdx.y, tid = threadIdx.x;
   float sum = 0.f;
   for (int l = tid; l < L; l += 256) { const float m = a_mask != nullptr ? a_mask[(size_t)b * L + l] : 1.f; s_w[l] = m; sum += m; }
@@ -51,7 +51,7 @@ int attn_precompute(cudaStream_t st, const float* params, const float* ann, cons
   if (qf != nullptr)
     WAP_TRY(gemm_nn(st, params + P.Q, kNA, params + P.U_f, kNA, qf, kNA, kCovTaps, kNA, kNA, nullptr, false));
   if (h0 != nullptr) {
-    const size_t smem = sizeof(float) * (L + 64 + 16 * 64);
+    const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
     WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large: L=%d", L);
     ann_mean_kernel<<<dim3(cdiv(kD, 64), B), 256, smem, st>>>(ann, a_mask, mean_scratch, L);
     WAP_LAUNCH_CHECK();

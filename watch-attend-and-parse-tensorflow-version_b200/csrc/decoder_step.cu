@@ -175,7 +175,7 @@ softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask
                    float* __restrict__ ctx, int L, int shared) {
   extern __shared__ float sm[];          // alpha[L] | red[64] | part[16][64]
   float* s_alpha = sm;
-  float* red = sm + L;
+  float* red = sm + ((L + 3) & ~3);      // keep `part` 16-byte aligned for the float4 stores
   float* part = red + 64;
   const int b = blockIdx.y, tid = threadIdx.x;
   const float* e = E + (size_t)b * L;
@@ -255,12 +255,12 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     ACovPatch A{c.ap_in, Bn, c.h, c.w};
     BRowMajor Bq{c.qf, kNA, kCovTaps, kNA};
     EpiStore e{c.COV, kNA, p + P.U_f_b, false, nullptr};
-    WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bq, e, Bn * L, kNA, 124)));
+    WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bq, e, Bn * L, kNA, 124, 1, kProfCovGemm)));
   }
   energy_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(c.COV, c.watch, c.SP, p + P.V_a, p + P.V_a_b, c.TANH, c.E, Bn, L, c.shared);
   WAP_LAUNCH_CHECK();
   {
-    const size_t smem = sizeof(float) * (L + 64 + 16 * 64);
+    const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
     WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large for softmax_ctx_kernel: L=%d", L);
     dim3 grid(cdiv(kD, kCtxChunk), Bn);
     softmax_ctx_kernel<<<grid, 256, smem, st>>>(c.E, c.a_mask, c.ap_in, c.ann, c.alpha, c.ap_out, c.ctx, L, c.shared);

@@ -424,14 +424,14 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
         ARowMajor A{buf[b], ld, M, C};
         BRowMajor Bw{params + c1.w, kBottle, C, kBottle};
         EpiStore e{y1, kBottle, nullptr, false, training ? stats + (size_t)k * 2 * kMaxBnC : nullptr};
-        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, C)));
+        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, C, 1, kProfConv1Fwd)));
         WAP_TRY(run_bn_act(st, 0, bn_args(k, y1, h, w, a1, h, w, kBottle, true)));
       }
       {   // 3x3 growth  96 -> 24, written in place at channel offset C
         AIm2col3 A{a1, kBottle, B, h, w, kBottle, false};
         BRowMajor Bw{params + c3.w, kGrowth, 9 * kBottle, kGrowth};
         EpiStore e{y2, kGrowth, nullptr, false, training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr};
-        WAP_TRY((launch_gemm<Cfg256x24>(st, A, Bw, e, M, kGrowth, 9 * kBottle)));
+        WAP_TRY((launch_gemm<Cfg256x24>(st, A, Bw, e, M, kGrowth, 9 * kBottle, 1, kProfConv3Fwd)));
         WAP_TRY(run_bn_act(st, 0, bn_args(k + 1, y2, h, w, buf[b] + C, h, w, ld, true)));
       }
       C += kGrowth;
@@ -442,7 +442,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       ARowMajor A{buf[b], ld, M, C};
       BRowMajor Bw{params + ct.w, ct.cout, C, ct.cout};
       EpiStore e{yt, ct.cout, nullptr, false, training ? stats + (size_t)k * 2 * kMaxBnC : nullptr};
-      WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, ct.cout, C)));
+      WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, ct.cout, C, 1, kProfTransFwd)));
       WAP_TRY(run_bn_act(st, 2, bn_args(k, yt, h, w, buf[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], true)));
       ++k;
     }
@@ -484,13 +484,13 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         BRowMajor Bd{dytr, ct.cout, M, ct.cout};
         EpiAtomic e{grads + ct.w, ct.cout};
         const int tiles = cdiv(C, 128) * cdiv(ct.cout, 128);
-        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))))));
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfTransBwd)));
       }
       {   // dgrad  G[b] = dy * W^T   (initialises the whole gradient buffer of block b)
         ARowMajor A{dytr, ct.cout, M, ct.cout};
         BColMajor Bw{params + ct.w, ct.cout, ct.cout, C};
         EpiStore e{G[b], ld, nullptr, false, nullptr};
-        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, ct.cout)));
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, ct.cout, 1, kProfTransBwd)));
       }
       --k;
     }
@@ -507,13 +507,13 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         BRowMajor Bd{dy2, kGrowth, M, kGrowth};
         EpiAtomic e{grads + c3.w, kGrowth};
         const int tiles = cdiv(9 * kBottle, 128);
-        WAP_TRY((launch_gemm<Cfg128x32>(st, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))))));
+        WAP_TRY((launch_gemm<Cfg128x32>(st, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv3Wgrad)));
       }
       {   // dgrad 3x3: d a1[M,96]
         AIm2col3 A{dy2, kGrowth, B, h, w, kGrowth, false};
         BDgrad3 Bw{params + c3.w, kBottle, kGrowth};
         EpiStore e{da1, kBottle, nullptr, false, nullptr};
-        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, 9 * kGrowth)));
+        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, 9 * kGrowth, 1, kProfConv3Dgrad)));
       }
       WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, true)));
       {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
@@ -521,13 +521,13 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         BRowMajor Bd{dy1, kBottle, M, kBottle};
         EpiAtomic e{grads + c1.w, kBottle};
         const int tiles = cdiv(C, 128);
-        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))))));
+        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv1Wgrad)));
       }
       {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
         ARowMajor A{dy1, kBottle, M, kBottle};
         BColMajor Bw{params + c1.w, kBottle, kBottle, C};
         EpiStore e{G[b], ld, nullptr, true, nullptr};
-        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, kBottle)));
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, kBottle, 1, kProfConv1Dgrad)));
       }
     }
   }

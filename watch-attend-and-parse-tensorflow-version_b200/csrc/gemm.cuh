@@ -342,12 +342,15 @@ gemm_kernel(const AL A, const BL Bm, const Epi epi, const int M, const int N, co
 
 // ----------------------------------------------------------------------------- launcher
 template <class Cfg, class AL, class BL, class Epi>
-inline int launch_gemm(cudaStream_t st, const AL& A, const BL& Bm, const Epi& epi, int M, int N, int K, int splits = 1) {
+inline int launch_gemm(cudaStream_t st, const AL& A, const BL& Bm, const Epi& epi, int M, int N, int K, int splits = 1,
+                       int prof_cls = kProfOtherGemm) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  prof_begin(st, prof_cls, 2.0 * M * N * K);
   int kps = cdiv(cdiv(K, splits), BK) * BK;
   splits = cdiv(K, kps);
   dim3 grid(cdiv(M, Cfg::BM), cdiv(N, Cfg::BN), splits);
   gemm_kernel<Cfg, AL, BL, Epi><<<grid, Cfg::NT, 0, st>>>(A, Bm, epi, M, N, K, kps);
+  prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
 }

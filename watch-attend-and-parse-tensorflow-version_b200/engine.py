@@ -64,6 +64,20 @@ class ParamStore:
             v = torch.as_tensor(np.asarray(values[name], dtype=np.float32))
             self.views[name].copy_(v.reshape(self.views[name].shape))
 
+    def pack_into(self, flat: torch.Tensor, values: Dict[str, np.ndarray]) -> None:
+        """Write per-variable arrays (trainable variables only) into a flat buffer with this layout
+        (used for optimiser state: accum / accum_update)."""
+        for name, off, shape, flags in self.table:
+            if flags & 2 or name not in values:
+                continue
+            v = torch.as_tensor(np.asarray(values[name], dtype=np.float32)).reshape(-1)
+            flat[off: off + v.numel()].copy_(v)
+
+    def unpack(self, flat: torch.Tensor) -> Dict[str, np.ndarray]:
+        host = flat.detach().cpu().numpy()
+        return {name: host[off: off + int(np.prod(shape))].reshape(shape).copy()
+                for name, off, shape, flags in self.table if not flags & 2}
+
     def state_dict(self) -> Dict[str, np.ndarray]:
         return {n: self.views[n].detach().cpu().numpy().copy() for n in self.names()}
 
