@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Drop-in entry point with the reference's command line (model-single-GPU.py:736-741):
+
+    python model-single-GPU.py --path . --batch_size 6
+
+Same inputs (<path>/data/{dictionary.txt, offline-train.pkl, train_caption.txt, offline-test.pkl,
+test_caption.txt}), same outputs (<path>/log-bs-6.txt, <path>/result/valid_decode_result-bs-6.txt,
+<path>/result/valid-bs-6.wer), same schedule (Adadelta lr 1.0, validation every epoch with beam 10 /
+maxlen 100, patience 15, lr/10 twice, then early stop; S:609-734) — but every FLOP runs in
+libwap_b200.so on the B200.  Under torchrun (WORLD_SIZE > 1) it trains data-parallel with a NCCL
+gradient all-reduce (semantics of model-distributed.py:704-717); rank 0 validates.
+Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid.
+"""
+import argparse
+import os
+import random
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def main(args):
+    import torch
+    import wap_b200
+    from wap_b200 import dp, scorer
+    rank, world, local = dp.init_distributed()
+    torch.cuda.set_device(local)
+    worddicts = wap_b200.load_dict(args.path + '/data/dictionary.txt')
+    worddicts_r = [None] * len(worddicts)
+    for kk, vv in worddicts.items():
+        worddicts_r[vv] = kk
+    train, train_uid_list = wap_b200.dataIterator(args.path + '/data/offline-train.pkl', args.path + '/data/train_caption.txt', worddicts,
+                                                  batch_size=args.batch_size, batch_Imagesize=400000, maxlen=100, maxImagesize=400000)
+    valid, valid_uid_list = wap_b200.dataIterator(args.path + '/data/offline-test.pkl', args.path + '/data/test_caption.txt', worddicts,
+                                                  batch_size=args.batch_size, batch_Imagesize=400000, maxlen=100, maxImagesize=400000)
+    print('train lenght is ', len(train))
+    eng = wap_b200.WAPEngine(seed=args.seed)
+    eng.world_size = world
+    dp.broadcast_params(eng.P.flat); dp.broadcast_params(eng.P.moving)
+
+    uidx, cost_s, dispFreq = 0, 0.0, 100
+    validFreq = sampleFreq = max(len(train) // world, 1)
+    history_errs, estop, halfLrFlag, patience, lrate, bad_counter = [], False, 0, 15, 1.0, 0
+    log = open(args.path + '/log-bs-6.txt', 'w') if rank == 0 else None
+    os.makedirs(args.path + '/result', exist_ok=True)
+    rng = random.Random(args.seed)
+
+    def say(msg):
+        if rank == 0:
+            print(msg); log.write(msg + '\n'); log.flush()
+
+    for epoch in range(args.max_epoch):
+        rng.shuffle(train)                                   # same permutation on every rank; shards are disjoint
+        for batch_x, batch_y in dp.shard_batches(train, rank, world):
+            if not batch_x:
+                continue
+            x, x_m, y, y_m = wap_b200.prepare_data(batch_x, batch_y, pinned=True)
+            uidx += 1
+            cost_i = float(eng.train_step(x, y, x_m, y_m, lr=lrate))
+            cost_s += cost_i
+            if np.isnan(cost_i) or np.isinf(cost_i):
+                print('invalid cost value detected')
+                sys.exit(0)
+            if uidx % dispFreq == 0:
+                cost_s /= dispFreq
+                say('Epoch ' + str(epoch) + ' Update ' + str(uidx) + ' Cost ' + str(cost_s) + ' Lr ' + str(lrate))
+                cost_s = 0.0
+            if uidx % sampleFreq == 0:
+                dp.sync_moving_stats(eng.P.moving)
+            if uidx % sampleFreq == 0 and rank == 0:
+                with open(args.path + '/result/valid_decode_result-bs-6.txt', 'w') as fpp:
+                    idx = 0
+                    for vx, _ in valid:
+                        for xx in vx:
+                            xx_pad = (np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]
+                            annot, _ = eng.dense_net(xx_pad, None, training=False)
+                            if args.greedy_valid:
+                                toks, lens, _ = eng.greedy_decode(annot, 100)
+                                ss = toks[0, :int(lens[0])].tolist()
+                            else:
+                                ss, _, _ = eng.get_sample(annot, 10, 100)
+                            fpp.write(valid_uid_list[idx]); idx += 1
+                            if idx % 100 == 0:
+                                say('gen %d samples' % idx)
+                            for vv in ss:
+                                if vv == 0:
+                                    break
+                                fpp.write(' ' + worddicts_r[vv])
+                            fpp.write('\n')
+                say('valid set decode done')
+            if uidx % validFreq == 0 and rank == 0:
+                probs = []
+                for vx, vy in valid:
+                    if not vx:
+                        continue
+                    x, x_m, y, y_m = wap_b200.prepare_data(vx, vy)
+                    ann, a_m = eng.dense_net(x, x_m, training=False)
+                    l2 = 1e-4 * float((eng.P.flat[:eng.P.n_decay].double() ** 2).sum())     # the reference's cost includes L2 (S:592-598)
+                    probs.append(float(eng.get_cost(ann, y, a_m, y_m, dropout=False)) + l2)
+                valid_err_cost = float(np.mean(probs))
+                wer, sacc = scorer.process(args.path + '/result/valid_decode_result-bs-6.txt', args.path + '/data/test_caption.txt',
+                                           args.path + '/result/valid-bs-6.wer')
+                valid_per, valid_sacc = 100. * wer, 100. * sacc
+                history_errs.append(valid_per)
+                if valid_per <= np.array(history_errs).min():
+                    bad_counter = 0
+                else:
+                    bad_counter += 1
+                    if bad_counter > patience:
+                        if halfLrFlag == 2:
+                            say('Early Stop!'); estop = True
+                        else:
+                            say('Lr decay and retrain!'); bad_counter = 0; lrate = lrate / 10; halfLrFlag += 1
+                say('Valid WER: %.2f%%, ExpRate: %.2f%%, Cost: %f' % (valid_per, valid_sacc, valid_err_cost))
+            if world > 1 and uidx % validFreq == 0:          # schedule decisions are taken on rank 0
+                flags = torch.tensor([lrate, float(estop)], device=eng.device, dtype=torch.float64)
+                torch.distributed.broadcast(flags, 0)
+                lrate, estop = float(flags[0]), bool(flags[1] > 0)
+            if estop:
+                break
+        if estop:
+            break
+
+
+if __name__ == "__main__":
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--path", default=".")
+    parser.add_argument("--batch_size", type=int, default=6)
+    parser.add_argument("--max_epoch", type=int, default=200)
+    parser.add_argument("--seed", type=int, default=0)
+    parser.add_argument("--greedy_valid", action="store_true")
+    (args, unknown) = parser.parse_known_args()
+    main(args)

@@ -207,3 +207,18 @@ def test_dp_mean_of_replica_gradients_equals_oracle_semantics():
     _, G, P2, _, _ = O.train_step(P, z, dict(z), *xa, 1.0, extra_grads=Gb, inv_world=0.5)
     for n in names[:40]:
         np.testing.assert_allclose(G[n], 0.5 * (Ga[n] + Gb[n]), rtol=1e-12, atol=1e-15)
+
+
+def test_scorer_matches_reference_definition(tmp_path):
+    from wap_b200 import scorer
+    rs = np.random.RandomState(0)
+    rec, lab = {}, {}
+    for i in range(30):
+        lab[f"k{i}"] = [str(t) for t in rs.randint(0, 6, size=rs.randint(1, 9))]
+        rec[f"k{i}"] = lab[f"k{i}"] if i % 3 == 0 else [str(t) for t in rs.randint(0, 6, size=rs.randint(0, 9))]
+    assert scorer.score(rec, lab) == pytest.approx(O.wer_exprate(rec, lab))
+    (tmp_path / "r.txt").write_text("".join(k + " " + " ".join(v) + "\n" for k, v in rec.items()))
+    (tmp_path / "l.txt").write_text("".join(k + "\t" + " ".join(v) + "\n" for k, v in lab.items()))
+    wer, sacc = scorer.process(str(tmp_path / "r.txt"), str(tmp_path / "l.txt"), str(tmp_path / "o.wer"))
+    lines = (tmp_path / "o.wer").read_text().splitlines()
+    assert lines[0] == f"WER {wer}" and lines[1] == f"ExpRate {sacc}"     # format parsed at model-single-GPU.py:702-705
