@@ -117,6 +117,15 @@ int wap_gemm_nn(void* stream, const float* A, int lda, const float* B, int ldb, 
 int wap_gemm_nt(void* stream, const float* A, int lda, const float* W, int ldw, float* C, int ldc, int M, int N, int K,
                 const float* bias, int accumulate);
 int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K);
+/* ---- tcgen05 TF32 tensor-core primitives (exported for the kernel-level parity tests)
+ * D[M,N] (=|+=) A[M,K](lda) * Bt[N,K](ldb)^T ; optional fp64 column sum / sum-of-squares [2][N] */
+int wap_tc_available(void);
+int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+                int accumulate, double* stats);
+/* 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) with Wt[Nrows, 9*C] (K-major, row n = output channel,
+ * k = tap*C + ci; rows >= N zero) -> D[B*H*W, N] */
+int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N,
+                   float* D, int ldd, double* stats);
 /* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);
 /* byte offsets (in floats) of selected encoder-workspace regions, for tests: what = 0 stem_raw,

@@ -6,6 +6,7 @@
 #include "../../include/wap_abi.h"
 #include "gemm.cuh"
 #include "model.h"
+#include "tc_gemm.cuh"
 
 namespace wap {
 
@@ -189,6 +190,17 @@ int wap_gemm_nt(void* stream, const float* A, int lda, const float* W, int ldw, 
 }
 int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K) {
   return gemm_tn_atomic(ST(stream), A, lda, B, ldb, C, ldc, M, N, K);
+}
+int wap_tc_available(void) { return tc_available() ? 1 : 0; }
+int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+                int accumulate, double* stats) {
+  TcEpi e{D, ldd, accumulate, stats};
+  return tc_gemm(ST(stream), A, lda, Bt, ldb, M, N, K, e, kProfOtherGemm);
+}
+int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N,
+                   float* D, int ldd, double* stats) {
+  TcEpi e{D, ldd, 0, stats};
+  return tc_conv3x3(ST(stream), x, ldx, B, H, W, C, Wt, Nrows, N, e, kProfOtherGemm);
 }
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
   return dropout_mask(ST(stream), seed, site, (size_t)n, mask);

@@ -1,0 +1,369 @@
+// tcgen05 TF32 GEMM / 3x3 implicit-GEMM kernels (see tc_gemm.cuh for the design).
+#include "tc_gemm.cuh"
+
+#include <cudaTypedefs.h>
+
+namespace wap {
+
+constexpr int kTcBM = 128;          // UMMA M (cta_group::1)
+constexpr int kTcBK = 32;           // floats per stage row = 128 B = one swizzle span
+constexpr int kTcThreads = 192;
+constexpr uint32_t kSpinLimit = 1u << 24;
+
+// ------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// bounded wait: a pipeline bug traps (launch failure) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > kSpinLimit) __trap();
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::tf32, issued by ONE thread)
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrives on the mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns -> 32 registers per thread (thread i = TMEM lane base+i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address        bits [0,14)
+  d |= (uint64_t)0 << 16;                            // leading byte offset  (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   bits [32,46)
+  d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                            // layout: SWIZZLE_128B
+  return d;
+}
+// instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+
+// ------------------------------------------------------------------------------------ kernel
+struct TcShape {
+  int M, N, K;            // logical GEMM (K = total reduction length; for conv: 9*C)
+  int nkb;                // number of 32-wide K blocks
+  // im2col mode
+  int B, H, W, kb_per_tap, TW, TH, tiles_x, tiles_y;
+};
+
+template <int BN> struct TcSmem {
+  static constexpr int kStages = BN <= 32 ? 4 : 3;                  // 2 CTAs/SM must fit in 227 KB
+  static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
+  static constexpr int kBBytes = BN * kTcBK * 4;
+  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kBarOff = kStages * kStage;
+  static constexpr int kStatOff = kBarOff + 128;                    // barriers + tmem slot
+  static constexpr int kTotal = kStatOff + 2 * BN * 4 + 1024;       // + alignment slack
+};
+
+template <int BN, bool IM2COL>
+__global__ void __launch_bounds__(kTcThreads, 2)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpi epi, const TcShape sh) {
+  using S = TcSmem<BN>;
+  constexpr int kTcStages = S::kStages;
+  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty_bar = full_bar + kTcStages;
+  uint64_t* tmem_full = empty_bar + kTcStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_stat = reinterpret_cast<float*>(smem + S::kStatOff);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // tile coordinates
+  int m0 = 0, bimg = 0, x0 = 0, y0 = 0;
+  if (IM2COL) {
+    int t = blockIdx.x;
+    const int tx = t % sh.tiles_x; t /= sh.tiles_x;
+    const int ty = t % sh.tiles_y; bimg = t / sh.tiles_y;
+    x0 = tx * sh.TW; y0 = ty * sh.TH;
+  } else {
+    m0 = blockIdx.x * kTcBM;
+  }
+  const int n0 = blockIdx.y * BN;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (epi.stats != nullptr)
+    for (int i = threadIdx.x; i < 2 * BN; i += kTcThreads) s_stat[i] = 0.f;
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================================================= TMA producer
+    if (lane == 0) {
+      for (int kb = 0; kb < sh.nkb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStage;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kABytes + S::kBBytes);
+        if (IM2COL) {
+          const int tap = kb / sh.kb_per_tap, cb = kb - tap * sh.kb_per_tap;
+          tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
+        } else {
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * kTcBK, m0);
+        }
+        tma_load_2d(sb, &tmB, &full_bar[s], kb * kTcBK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================================= MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BN);
+      for (int kb = 0; kb < sh.nkb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStage);
+        const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kTcBK / 8; ++k) {
+          const uint64_t ad = make_kmajor_sw128_desc(sa + k * 32);
+          const uint64_t bd = make_kmajor_sw128_desc(sb + k * 32);
+          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
+      }
+      umma_commit(tmem_full);                // accumulator complete
+    }
+  } else {
+    // ================================================= epilogue (warps 2..5)
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;             // output row within the tile
+    bool valid; size_t mrow;
+    if (IM2COL) {
+      const int tw = r % sh.TW, th = r / sh.TW;
+      const int x = x0 + tw, y = y0 + th;
+      valid = (x < sh.W) && (y < sh.H);
+      mrow = ((size_t)bimg * sh.H + y) * sh.W + x;
+    } else {
+      valid = (m0 + r) < sh.M;
+      mrow = (size_t)(m0 + r);
+    }
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (valid) {
+        float* dst = epi.out + mrow * epi.ld + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          if (n0 + c + j + 3 < sh.N) {
+            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            if (epi.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            *reinterpret_cast<float4*>(dst + j) = o;
+          } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (n0 + c + j + jj < sh.N) dst[j + jj] = epi.accumulate ? dst[j + jj] + v[j + jj] : v[j + jj];
+          }
+        }
+      }
+      if (epi.stats != nullptr) {
+        float a[32], b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { a[i] = valid ? v[i] : 0.f; b[i] = a[i] * a[i]; }
+        // transposing butterfly: after the 5 rounds lane L holds the sum over the 32 rows of column L
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float sa_ = upper ? a[i] : a[i + off], ka = upper ? a[i + off] : a[i];
+            const float sb_ = upper ? b[i] : b[i + off], kb_ = upper ? b[i + off] : b[i];
+            a[i] = ka + __shfl_xor_sync(0xffffffffu, sa_, off);
+            b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, off);
+          }
+        }
+        atomicAdd(&s_stat[c + lane], a[0]);
+        atomicAdd(&s_stat[BN + c + lane], b[0]);
+      }
+    }
+    if (epi.stats != nullptr) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
+      const int t = threadIdx.x - 64;
+      for (int i = t; i < BN; i += 128) {
+        const int n = n0 + i;
+        if (n < sh.N) {
+          atomicAdd(epi.stats + n, (double)s_stat[i]);
+          atomicAdd(epi.stats + sh.N + n, (double)s_stat[BN + i]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ------------------------------------------------------------------------------------ host side
+static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
+static bool g_encode_tried = false;
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+  if (!g_encode_tried) {
+    g_encode_tried = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+  }
+  return g_encode;
+}
+bool tc_available() { return get_encode() != nullptr; }
+
+static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
+  WAP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
+  for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bdim, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  WAP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank=%d dims=%llu,%llu stride0=%llu box=%u,%u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0], box[0], box[1]);
+  return 0;
+}
+
+template <int BN, bool IM2COL>
+static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const TcEpi& epi, const TcShape& sh, dim3 grid,
+                     int prof_cls, double flops) {
+  static bool configured = false;
+  if (!configured) {
+    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
+    configured = true;
+  }
+  prof_begin(st, prof_cls, flops);
+  tc_gemm_kernel<BN, IM2COL><<<grid, kTcThreads, TcSmem<BN>::kTotal, st>>>(ta, tb, epi, sh);
+  prof_end(st, prof_cls);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
+  WAP_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (epi.ld & 3) == 0, "tc_gemm: strides must be multiples of 4 floats");
+  WAP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)epi.out & 15) == 0, "tc_gemm: pointers must be 16-byte aligned");
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)lda * 4}; const uint32_t box[2] = {kTcBK, kTcBM};
+    WAP_TRY(make_map(&ta, A, 2, dims, str, box));
+  }
+  const int BN = N <= 32 ? 32 : N <= 96 ? 96 : 128;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; const uint64_t str[1] = {(uint64_t)ldb * 4}; const uint32_t box[2] = {kTcBK, (uint32_t)BN};
+    WAP_TRY(make_map(&tb, Bt, 2, dims, str, box));
+  }
+  TcShape sh{}; sh.M = M; sh.N = N; sh.K = K; sh.nkb = cdiv(K, kTcBK);
+  dim3 grid(cdiv(M, kTcBM), cdiv(N, BN));
+  const double flops = 2.0 * M * N * K;
+  if (BN == 32) return launch_tc<32, false>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+  if (BN == 96) return launch_tc<96, false>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+  return launch_tc<128, false>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+}
+
+int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N, const TcEpi& epi, int prof_cls) {
+  WAP_REQUIRE(C % kTcBK == 0 && (ldx & 3) == 0 && (epi.ld & 3) == 0, "tc_conv3x3: C=%d must be a multiple of 32", C);
+  int TW = 1; while (TW < W && TW < kTcBM) TW <<= 1;     // power of two >= W, at most 128
+  const int TH = kTcBM / TW;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldx * 4, (uint64_t)W * ldx * 4, (uint64_t)H * W * ldx * 4};
+    const uint32_t box[4] = {kTcBK, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&ta, x, 4, dims, str, box));
+  }
+  const int BN = N <= 32 ? 32 : N <= 96 ? 96 : 128;
+  const int K = 9 * C;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)Nrows}; const uint64_t str[1] = {(uint64_t)K * 4}; const uint32_t box[2] = {kTcBK, (uint32_t)BN};
+    WAP_TRY(make_map(&tb, Wt, 2, dims, str, box));
+  }
+  TcShape sh{}; sh.M = B * H * W; sh.N = N; sh.K = K; sh.nkb = K / kTcBK;
+  sh.B = B; sh.H = H; sh.W = W; sh.kb_per_tap = C / kTcBK; sh.TW = TW; sh.TH = TH; sh.tiles_x = cdiv(W, TW); sh.tiles_y = cdiv(H, TH);
+  dim3 grid(sh.tiles_x * sh.tiles_y * B, cdiv(N, BN));
+  const double flops = 2.0 * sh.M * N * K;
+  if (BN == 32) return launch_tc<32, true>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+  if (BN == 96) return launch_tc<96, true>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+  return launch_tc<128, true>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+}
+
+}  // namespace wap

@@ -1,0 +1,38 @@
+// tcgen05 (5th-gen tensor core) TF32 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   D[M,N] = A[M,K] * Bt[N,K]^T       fp32 storage, TF32 multiply, fp32 accumulate in TMEM
+//
+// Both operands are K-major in shared memory with the 128-byte swizzle: one pipeline stage is a
+// [128 rows x 32 floats] A tile and a [BN rows x 32 floats] B tile, each row exactly one 128 B
+// swizzle span, written by TMA (cp.async.bulk.tensor, SWIZZLE_128B) and consumed by
+// tcgen05.mma.kind::tf32 (M=128, N=BN, K=8: four instructions per stage).  The A operand is either
+// a plain 2-D row-major matrix (row stride lda: 1x1 convolutions read a channel slice of the
+// dense-block buffer in place) or a 3x3 SAME im2col view of an NHWC tensor fetched as 4-D TMA
+// boxes [32 ch, TW, TH, 1] whose out-of-bounds halo is zero-filled by the TMA unit itself.
+// K tails (C not a multiple of 32) are zero-filled the same way, so no padded copies exist.
+//
+// Warp roles (192 threads): warp 0 = TMA producer (one elected lane), warp 1 = TMEM allocator +
+// MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32x32b, one TMEM lane = one
+// output row per thread): store / accumulate, and optional per-column sum and sum of squares
+// (batch-norm statistics) via a 31-shuffle transposing reduction per 32 columns.
+// Two CTAs are resident per SM so one tile's epilogue overlaps the other's main loop.
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace wap {
+
+struct TcEpi {
+  float* out; int ld;        // D[m*ld + n]
+  int accumulate;            // D += acc
+  double* stats;             // [2][N] column sum / sum of squares of the raw accumulators, or null
+};
+
+// D[M,N] = A[M,K](lda) * Bt[N,K](ldb)^T ; N <= 256 per launch column tile (grid.y tiles of BN)
+int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls);
+// 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) * Wt[Nrows, 9*C]^T -> D[B*H*W, N]  (Nrows >= N rows allocated, extra rows zero)
+int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N, const TcEpi& epi, int prof_cls);
+bool tc_available();
+
+}  // namespace wap
