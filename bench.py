@@ -165,6 +165,7 @@ def run_ours(args):
     L = wap_b200._lib.lib()
     eng = wap_b200.WAPEngine(device=dev, seed=0, init=True)    # same seed on every rank: replicated weights
     eng.world_size = world
+    eng.set_conv_precision(args.precision)
     B = B_PER_GPU
     x, xm, y, ym = make_workload(4 + rank, B)                   # per-rank shard of the global batch
     xd = torch.as_tensor(x).to(dev); xmd = torch.as_tensor(xm).to(dev)
@@ -235,23 +236,27 @@ def run_ours(args):
     pk = peaks()
     top = max((k for k in prof if k != "other_gemm"), key=lambda k: prof[k]["ms_per_step"])
     gemm_ms = sum(v["ms_per_step"] for v in prof.values())
-    roof = {"bound": "tensor", "kernel": f"gemm_kernel<{top}> (fp32 FFMA implicit GEMM)", "achieved": prof[top]["tflops"], "peak": pk["tf"],
+    kname = "gemm_kernel (fp32 FFMA implicit GEMM)" if args.precision == "fp32" or "wgrad" in top or top in ("coverage_gemm",) \
+        else "tc_gemm_kernel (tcgen05 TF32 implicit GEMM, TMA + TMEM)"
+    roof = {"bound": "tensor", "kernel": f"{kname} [{top}]", "achieved": prof[top]["tflops"], "peak": pk["tf"],
             "unit": "TFLOP/s", "frac": prof[top]["tflops"] / pk["tf"], "traffic": None, "peak_source": pk["src"],
             "share_of_step": prof[top]["ms_per_step"] / (ms / args.steps),
             "all_gemm_share_of_step": gemm_ms / (ms / args.steps), "classes": prof,
-            "note": "fp32 CUDA-core path measured against the bf16 tensor-core peak; per-launch CUDA events over a second pass of the same steps"}
+            "note": "algorithmic FLOPs (2MNK, one pass) per launch / CUDA-event time, against the measured bf16 peak; "
+                    "per-launch events recorded over a second pass of the same steps"}
     log("gpu legs done; cpu baseline ...")
     cpu_v, cores, cpu_sps, cpu_n = cpu_oracle_images_per_s(B, 2, 1, 60.0) if (world == 1 and not args.no_cpu_baseline) else (None, None, None, 0)
     h2d = sum(t_.numel() * t_.element_size() for t_ in (xp, xmp, yp, ymp))
     line = {
         "metric": METRIC, "value": world * B * args.steps / (ms * 1e-3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
         "warmup": nwarm, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
+        "dtype": {"fp32": "f32", "tf32": "tf32 (fp32 storage/accumulate)", "tf32x3": "f32 (3xTF32 tensor-core products, fp32 accumulate)"}[args.precision],
+        "data": "synthetic",
         "config": {"workload": f"WAP train step (fwd+bwd+L2/Adadelta), {B}x{IMG_H}x{IMG_W} images/GPU, {CAP_LEN}-token captions "
                                f"(BASELINE configs[1]; configs[3] at 8 GPUs)", "global_batch": world * B,
                    "parallelism": f"dp{world}" + (" (NCCL all-reduce of 5.4M fp32 grads)" if world > 1 else ""),
                    "l2_flush": "none needed: per-step working set (~1.3 GB of saved activations) exceeds the 126 MB L2",
-                   "dropout": 0.2, "final_cost": cost},
+                   "dropout": 0.2, "final_cost": cost, "conv_precision": args.precision},
         "clocks": clocks,
         "e2e": {"value": world * B * args.steps / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps},
@@ -273,6 +278,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"],
+                    help="dense-block conv arithmetic: fp32 FFMA | tf32 tcgen05 (single pass) | tf32x3 tcgen05 (error-compensated, fp32-grade; default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="under ncu: honour --warmup exactly, skip e2e/roofline/cpu legs")
     args = ap.parse_args()

@@ -118,13 +118,24 @@ int wap_gemm_nt(void* stream, const float* A, int lda, const float* W, int ldw, 
                 const float* bias, int accumulate);
 int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, int ldb, float* C, int ldc, int M, int N, int K);
 /* ---- tcgen05 TF32 tensor-core primitives (exported for the kernel-level parity tests)
- * D[M,N] (=|+=) A[M,K](lda) * Bt[N,K](ldb)^T ; optional fp64 column sum / sum-of-squares [2][N] */
+ * D[M,N] (=|+=) A[M,K](lda) * Bt[N,K](ldb)^T ; optional fp64 column sum / sum-of-squares [2][N].
+ * Bt_lo != NULL selects 3xTF32: Bt = rna_tf32(W), Bt_lo = rna_tf32(W - Bt); A is split inside the kernel. */
 int wap_tc_available(void);
-int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+/* precision of the dense-block / transition convolutions (forward and dgrad) of wap_encoder_*:
+ * 0 = fp32 FFMA (CUDA cores), 1 = TF32 tcgen05 tensor cores, single pass with RNA-rounded operands
+ * (10-bit mantissa products), 2 = error-compensated 3xTF32 tcgen05 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,
+ * fp32-grade accuracy: the tensor-core parity mode) */
+int wap_set_conv_precision(int mode);
+int wap_get_conv_precision(void);
+/* debugging aid: bit mask of the conv classes allowed on the tensor-core path (default all) */
+int wap_debug_set_tc_mask(int mask);
+/* debugging aid: during wap_encoder_backward copy [d a1 | d y2 (ld 32) | d y1] of the dense level whose 1x1 conv index is `layer` into buf */
+int wap_debug_capture(int layer, float* buf);
+int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
                 int accumulate, double* stats);
 /* 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) with Wt[Nrows, 9*C] (K-major, row n = output channel,
  * k = tap*C + ci; rows >= N zero) -> D[B*H*W, N] */
-int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N,
+int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
                    float* D, int ldd, double* stats);
 /* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);

@@ -246,6 +246,8 @@ def dense_net(P, x, mask_x, training: bool, drop: DropFn = None, taps: Optional[
                                  P[bn_name(k, "moving_mean")], P[bn_name(k, "moving_variance")], training)
         new_moving[bn_name(k, "moving_mean")] = nm
         new_moving[bn_name(k, "moving_variance")] = nv
+        if taps is not None:
+            taps[f"minpre{k}"] = float(y.detach().abs().min())     # distance of the closest element to the ReLU kink
         y = torch.relu(y)
         if do_drop and training:
             y = _dropout(y, f"drop{k}", drop)
@@ -571,3 +573,14 @@ def hash_drop_fn(seed: int) -> Callable:
         n = int(np.prod(shape))
         return torch.as_tensor(drop_hash_keep(seed & 0xFFFFFFFF, site, n).reshape(shape))
     return fn
+
+
+def relu_kink_margin(P_np, x, x_mask, drop: DropFn = None) -> float:
+    """Smallest |pre-activation| over every BN->ReLU site of a training-mode forward.  A gradient
+    comparison across precisions is only well posed when no element sits on a ReLU kink (with ~2e6
+    activations and values O(1) an element within 1e-6 of zero shows up in about every other
+    random batch; fp32 then legitimately gates it differently from fp64)."""
+    P = to_torch(P_np, torch.float64)
+    taps: dict = {}
+    dense_net(P, torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(x_mask, dtype=torch.float64), True, drop, taps=taps)
+    return min(v for k, v in taps.items() if k.startswith("minpre"))

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import O, REL_TOL, engine_with, make_batch, rel_err, rel_l2, t64
+from helpers import O, REL_TOL, engine_with, make_batch, rel_err, rel_l2, t64, well_posed_batch
 
 pytestmark = pytest.mark.gpu
 
@@ -220,10 +220,10 @@ def test_get_cost_forward(report, B, h, w, T, drop):
 @pytest.mark.parametrize("B,H,W,cap,drop", [(2, 32, 48, 3, False), (2, 40, 72, 5, True)])
 def test_full_gradients(report, B, H, W, cap, drop):
     """Every one of the 329 parameter gradients of cost (no L2) vs fp64 autograd of the oracle."""
-    x, xm, y, ym = make_batch(50 + B, B, H, W, cap, True)
     P = O.lively_params(8)
-    eng = engine_with(P)
     seed = 777
+    x, xm, y, ym = well_posed_batch(P, 50 + B, B, H, W, cap, True, seed if drop else None)
+    eng = engine_with(P)
     cost = eng.forward_backward(x, y, xm, ym, dropout=drop, seed=seed)
     Pt = O.to_torch(P, torch.float64, requires_grad=True)
     dfn = O.hash_drop_fn(seed) if drop else None
@@ -278,46 +278,51 @@ def test_adadelta_l2_step(report):
 
 
 def test_train_steps_match_oracle(report):
-    """Two full optimiser steps (cost incl. L2, updated weights, Adadelta state, moving statistics).
-    Before each step the engine is synchronised to the oracle's state, so each step is compared from
-    identical inputs (Adadelta's early updates are ~sqrt(eps)*sign(g): elements whose gradient is
-    rounding noise may legitimately flip sign, hence the sign-stable subset + quantile criteria)."""
-    B, H, W, cap = 2, 32, 48, 3
+    """Two full optimiser steps from oracle-synchronised state: cost incl. L2, moving statistics and the
+    gradient against the fp64 oracle; Adadelta state and parameters against the TF update formula applied
+    (in fp64) to the engine's OWN gradient.  (Comparing parameter deltas against the oracle's directly is
+    ill-posed: with eps = 1e-8 the first Adadelta updates are ~ g * 1e-4 / sqrt(0.05 g^2 + 1e-8), i.e.
+    fp32-vs-fp64 gradient noise of 1e-5 is amplified to O(0.1) of the update for small |g|.)"""
+    B, H, W, cap = 2, 48, 80, 3
     P = O.lively_params(9)
     eng = engine_with(P)
     names = O.trainable_names(P)
     acc = {n: np.zeros(P[n].shape, np.float64) for n in names}
     accd = {n: np.zeros(P[n].shape, np.float64) for n in names}
     Pn = dict(P)
+    l2set = set(O.l2_names(P))
     fails = []
     for step in range(2):
-        x, xm, y, ym = make_batch(60 + step, B, H, W, cap, True)
         seed = 500 + step
+        x, xm, y, ym = well_posed_batch(Pn, 60 + step, B, H, W, cap, True, seed)
         eng.P.load(Pn); eng.P.pack_into(eng.accum, acc); eng.P.pack_into(eng.accum_update, accd)
-        Pprev = Pn
+        Pprev, acc_prev, accd_prev = Pn, acc, accd
         cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
-        ref_cost, G, Pn, acc, accd = O.train_step(Pprev, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
+        ref_cost, G, Pn, acc, accd = O.train_step(Pprev, acc_prev, accd_prev, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
         e = abs(cost - ref_cost) / abs(ref_cost)
         report.add("train_step", f"cost_step{step}", e, REL_TOL, extra=dict(got=cost, ref=ref_cost))
         if e > REL_TOL:
             fails.append(("cost", step, cost, ref_cost))
         sd = eng.P.state_dict()
-        acc_e = eng.P.unpack(eng.accum)
-        diffs, stable_worst, acc_worst = [], 0.0, 0.0
+        g_eng = eng.P.unpack(eng.grads); acc_e = eng.P.unpack(eng.accum); accd_e = eng.P.unpack(eng.accum_update)
+        gmax = max(float(np.max(np.abs(G[n]))) for n in names)
+        worst_g = worst_p = worst_a = 0.0; worst_name = None
         for n in names:
-            d_got = sd[n].astype(np.float64) - Pprev[n]; d_ref = Pn[n].astype(np.float64) - Pprev[n]
-            dn = np.abs(d_got - d_ref) / max(float(np.max(np.abs(d_ref))), 1e-12)
-            diffs.append(dn.ravel())
-            stable = np.abs(G[n]) > 1e-3 * np.max(np.abs(G[n]))
-            if stable.any():
-                stable_worst = max(stable_worst, float(dn[stable].max()))
-            acc_worst = max(acc_worst, rel_err(acc_e[n], acc[n]))
-        q = float(np.quantile(np.concatenate(diffs), 0.99))
-        report.add("train_step", f"param_delta_q99_step{step}", q, 2e-2)
-        report.add("train_step", f"param_delta_sign_stable_worst_step{step}", stable_worst, 2e-2)
-        report.add("train_step", f"adadelta_accum_worst_step{step}", acc_worst, 1e-3)
-        if q > 2e-2 or stable_worst > 2e-2 or acc_worst > 1e-3:
-            fails.append(("delta", step, q, stable_worst, acc_worst))
+            g = g_eng[n].astype(np.float64) + (2 * O.L2_COEF * Pprev[n].astype(np.float64) if n in l2set else 0.0)
+            eg = float(np.max(np.abs(g - G[n]))) / max(float(np.max(np.abs(G[n]))), 1e-4 * gmax)
+            if eg > worst_g:
+                worst_g, worst_name = eg, n
+            a = O.ADADELTA_RHO * acc_prev[n] + (1 - O.ADADELTA_RHO) * g * g
+            d = np.sqrt(accd_prev[n] + O.ADADELTA_EPS) / np.sqrt(a + O.ADADELTA_EPS) * g
+            u = O.ADADELTA_RHO * accd_prev[n] + (1 - O.ADADELTA_RHO) * d * d
+            pnew = Pprev[n].astype(np.float64) - d
+            worst_a = max(worst_a, rel_err(acc_e[n], a), rel_err(accd_e[n], u))
+            worst_p = max(worst_p, float(np.max(np.abs(sd[n] - pnew))) / max(float(np.max(np.abs(d))), 1e-12))
+        report.add("train_step", f"gradient_incl_l2_vs_oracle_step{step}", worst_g, 2e-3, extra=dict(name=worst_name))
+        report.add("train_step", f"adadelta_state_vs_formula_step{step}", worst_a, 1e-4)
+        report.add("train_step", f"param_update_vs_formula_step{step}", worst_p, 1e-3)
+        if worst_g > 2e-3 or worst_a > 1e-4 or worst_p > 1e-3:
+            fails.append(("update", step, worst_g, worst_a, worst_p))
         mv = max(rel_err(sd[n], Pn[n]) for n in P if n.endswith("moving_variance") or n.endswith("moving_mean"))
         report.add("train_step", f"moving_stats_step{step}", mv, 1e-3)
         if mv > 1e-3:

@@ -19,6 +19,11 @@ def _trunc_tf32(t):
     return (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32)
 
 
+def _rna_tf32(t):
+    """cvt.rna.tf32.f32: round to nearest, ties away from zero, 10 explicit mantissa bits."""
+    return ((t.contiguous().view(torch.int32) + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
 def _L():
     import wap_b200
     return wap_b200._lib, wap_b200._lib.lib()
@@ -31,10 +36,11 @@ def _st():
 p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
 
 
+@pytest.mark.parametrize("x3", [0, 1])
 @pytest.mark.parametrize("M,N,K,lda_pad,acc,stats", [
     (128, 96, 32, 0, 0, 0), (128, 96, 64, 0, 0, 1), (300, 96, 72, 360, 0, 1), (1000, 24, 864, 0, 0, 1),
     (257, 128, 660, 24, 1, 0), (5000, 216, 432, 0, 0, 1), (131, 300, 600, 84, 0, 1), (64, 32, 8, 0, 0, 0)])
-def test_tc_gemm(report, M, N, K, lda_pad, acc, stats):
+def test_tc_gemm(report, M, N, K, lda_pad, acc, stats, x3):
     lib, L = _L()
     assert L.wap_tc_available() == 1
     g = torch.Generator().manual_seed(M * 7 + N)
@@ -44,15 +50,23 @@ def test_tc_gemm(report, M, N, K, lda_pad, acc, stats):
     D0 = torch.randn(M, N, generator=g).cuda()
     D = D0.clone() if acc else torch.full((M, N), float("nan"), device="cuda")
     st = torch.zeros(2, N, dtype=torch.float64, device="cuda") if stats else None
-    lib.check(L.wap_tc_gemm(_st(), p(Afull), lda, p(Bt), K, p(D), N, M, N, K, acc, p(st)), "wap_tc_gemm")
-    torch.cuda.synchronize()
     A = Afull[:, :K]
-    ref_t = _trunc_tf32(A).double() @ _trunc_tf32(Bt).double().t() + (D0.double() if acc else 0)
     ref_x = A.double() @ Bt.double().t() + (D0.double() if acc else 0)
-    e_t = rel_err(D.cpu().numpy(), ref_t.cpu().numpy()); e_x = rel_err(D.cpu().numpy(), ref_x.cpu().numpy())
-    tag = f"tc_gemm_{M}x{N}x{K}_acc{acc}"
-    report.add("tc", tag + "_vs_truncated_inputs", e_t, 2e-5); report.add("tc", tag + "_vs_exact(tf32 error)", e_x, 5e-3)
-    assert e_t <= 2e-5, (e_t, e_x)
+    tag = f"tc_gemm_{M}x{N}x{K}_acc{acc}_x3{x3}"
+    if x3:      # error-compensated 3xTF32: hi/lo weight parts supplied, A split inside the kernel -> fp32-grade result
+        hi = _rna_tf32(Bt); lo = _rna_tf32(Bt - hi)
+        lib.check(L.wap_tc_gemm(_st(), p(Afull), lda, p(hi), p(lo), K, p(D), N, M, N, K, acc, p(st)), "wap_tc_gemm")
+        torch.cuda.synchronize()
+        e_x = rel_err(D.cpu().numpy(), ref_x.cpu().numpy())
+        report.add("tc", tag + "_vs_exact", e_x, 3e-6)
+        assert e_x <= 3e-6, e_x
+    else:
+        lib.check(L.wap_tc_gemm(_st(), p(Afull), lda, p(Bt), None, K, p(D), N, M, N, K, acc, p(st)), "wap_tc_gemm")
+        torch.cuda.synchronize()
+        ref_t = _trunc_tf32(A).double() @ _trunc_tf32(Bt).double().t() + (D0.double() if acc else 0)
+        e_t = rel_err(D.cpu().numpy(), ref_t.cpu().numpy()); e_x = rel_err(D.cpu().numpy(), ref_x.cpu().numpy())
+        report.add("tc", tag + "_vs_truncated_inputs", e_t, 2e-5); report.add("tc", tag + "_vs_exact(tf32 error)", e_x, 5e-3)
+        assert e_t <= 2e-5, (e_t, e_x)
     if stats:
         acc_only = (D.double() - (D0.double() if acc else 0))
         es = rel_err(st[0].cpu().numpy(), acc_only.sum(0).cpu().numpy()); eq = rel_err(st[1].cpu().numpy(), (acc_only ** 2).sum(0).cpu().numpy())
@@ -60,8 +74,9 @@ def test_tc_gemm(report, M, N, K, lda_pad, acc, stats):
         assert es <= 1e-5 and eq <= 1e-5, (es, eq)
 
 
+@pytest.mark.parametrize("x3", [0, 1])
 @pytest.mark.parametrize("B,H,W,C,N", [(2, 8, 16, 96, 24), (1, 5, 9, 96, 24), (3, 4, 32, 96, 24), (1, 32, 128, 96, 24), (2, 7, 20, 32, 96)])
-def test_tc_conv3x3(report, B, H, W, C, N):
+def test_tc_conv3x3(report, B, H, W, C, N, x3):
     lib, L = _L()
     g = torch.Generator().manual_seed(B * 100 + H)
     ldx = C + 8
@@ -72,14 +87,110 @@ def test_tc_conv3x3(report, B, H, W, C, N):
     Wt[:N] = w.reshape(9 * C, N).t()
     D = torch.full((B * H * W, N), float("nan"), device="cuda")
     st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
-    lib.check(L.wap_tc_conv3x3(_st(), p(xfull), ldx, B, H, W, C, p(Wt), Nrows, N, p(D), N, p(st)), "wap_tc_conv3x3")
-    torch.cuda.synchronize()
     x = xfull[..., :C]
-    ref = torch.nn.functional.conv2d(_trunc_tf32(x).double().permute(0, 3, 1, 2), _trunc_tf32(w).double().permute(3, 2, 0, 1), padding=1)
+    tol = 3e-6 if x3 else 2e-5
+    if x3:
+        hi = _rna_tf32(Wt); lo = _rna_tf32(Wt - hi)
+        lib.check(L.wap_tc_conv3x3(_st(), p(xfull), ldx, B, H, W, C, p(hi), p(lo), Nrows, N, p(D), N, p(st)), "wap_tc_conv3x3")
+        ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=1)
+    else:
+        lib.check(L.wap_tc_conv3x3(_st(), p(xfull), ldx, B, H, W, C, p(Wt), None, Nrows, N, p(D), N, p(st)), "wap_tc_conv3x3")
+        ref = torch.nn.functional.conv2d(_trunc_tf32(x).double().permute(0, 3, 1, 2), _trunc_tf32(w).double().permute(3, 2, 0, 1), padding=1)
+    torch.cuda.synchronize()
     ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, N)
     e = rel_err(D.cpu().numpy(), ref.cpu().numpy())
-    tag = f"tc_conv3x3_B{B}_{H}x{W}_C{C}_N{N}"
-    report.add("tc", tag, e, 2e-5)
+    tag = f"tc_conv3x3_B{B}_{H}x{W}_C{C}_N{N}_x3{x3}"
+    report.add("tc", tag, e, tol)
     es = rel_err(st[0].cpu().numpy(), D.double().sum(0).cpu().numpy()); eq = rel_err(st[1].cpu().numpy(), (D.double() ** 2).sum(0).cpu().numpy())
     report.add("tc", tag + "_stats", max(es, eq), 1e-5)
-    assert e <= 2e-5 and es <= 1e-5 and eq <= 1e-5, (e, es, eq)
+    assert e <= tol and es <= 1e-5 and eq <= 1e-5, (e, es, eq)
+
+
+# --------------------------------------------------------------------------------------
+# whole-encoder / whole-step parity of the tensor-core modes.
+#   'tf32x3' (error-compensated 3xTF32): the tensor-core PARITY mode, held to the same 1e-3 as the FFMA path;
+#   'tf32'   (single pass, 10-bit mantissa products): deviation measured and recorded (this 99-layer
+#            network amplifies rounding ~300x: fp32 itself lands at 2e-5), loose bound only.
+TOL = {"tf32x3": 1e-3, "tf32": 8e-2}
+
+
+@pytest.fixture()
+def tf32_engine_factory():
+    import wap_b200
+    from helpers import engine_with
+    made = []
+
+    def make(P, mode):
+        eng = engine_with(P)
+        eng.set_conv_precision(mode)
+        made.append(eng)
+        return eng
+    yield make
+    wap_b200._lib.lib().wap_set_conv_precision(0)
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("B,H,W,training", [(1, 64, 256, False), (2, 37, 75, False), (2, 40, 72, True), (8, 128, 512, True)])
+def test_tf32_encoder_forward(report, tf32_engine_factory, B, H, W, training, mode):
+    from helpers import O, make_batch, t64
+    x, xm, _, _ = make_batch(11 + B, B, H, W, 4, B < 8)
+    P = O.lively_params(3)
+    if not training:
+        P = O.calibrate_moving(P, x, xm)
+    eng = tf32_engine_factory(P, mode)
+    seed = 4242
+    ann, _ = eng.dense_net(x, xm, training=training, dropout=training, seed=seed)
+    if B >= 8:          # fp64 oracle of the full cfg2 batch is slow: use the fp32 FFMA engine path (itself 1e-5 vs oracle) as reference
+        eng.set_conv_precision("fp32")
+        ref, _ = eng.dense_net(x, xm, training=training, dropout=training, seed=seed)
+        ref = ref.cpu().numpy()
+    else:
+        ref, _, _ = O.dense_net(O.to_torch(P), t64(x), t64(xm), training, O.hash_drop_fn(seed) if training else None)
+        ref = ref.numpy()
+    e = rel_err(ann.cpu().numpy(), ref)
+    report.add(mode, f"encoder_B{B}_{H}x{W}_train{int(training)}", e, TOL[mode])
+    assert e <= TOL[mode], e
+
+
+def test_tf32x3_full_gradients_and_greedy(report, tf32_engine_factory):
+    from helpers import O, make_batch, t64
+    B, H, W, cap = 2, 48, 80, 5
+    from helpers import well_posed_batch
+    P = O.lively_params(8)
+    seed = 777
+    x, xm, y, ym = well_posed_batch(P, 52, B, H, W, cap, False, seed)
+    eng = tf32_engine_factory(P, "tf32x3")
+    cost = eng.forward_backward(x, y, xm, ym, dropout=True, seed=seed)
+    Pt = O.to_torch(P, torch.float64, requires_grad=True)
+    dfn = O.hash_drop_fn(seed)
+    ann, am, _ = O.dense_net(Pt, t64(x), t64(xm), True, dfn)
+    ref_cost = O.get_cost(Pt, ann, torch.as_tensor(y), am, t64(ym), dfn)
+    names = O.trainable_names(Pt)
+    grads = torch.autograd.grad(ref_cost, [Pt[n] for n in names])
+    e = abs(float(cost) - float(ref_cost.detach())) / abs(float(ref_cost.detach()))
+    report.add("tf32x3", "cost", e, 1e-3)
+    table = {n: (off, shape) for n, off, shape, fl in eng.P.table if not fl & 2}
+    gflat = eng.grads.cpu().numpy()
+    gmax = max(float(g.abs().max()) for g in grads)
+    worst, worst_name, l2s = 0.0, None, []
+    for n, g in zip(names, grads):
+        off, shape = table[n]
+        got = gflat[off: off + int(np.prod(shape))].reshape(shape); ref = g.numpy()
+        err = float(np.max(np.abs(got - ref))) / max(float(np.max(np.abs(ref))), 1e-4 * gmax)
+        l2s.append(float(np.linalg.norm(got - ref) / max(np.linalg.norm(ref), 1e-30)))
+        if err > worst:
+            worst, worst_name = err, n
+    report.add("tf32x3", "grad_worst_maxnorm", worst, 2e-3, extra=dict(name=worst_name))
+    report.add("tf32x3", "grad_median_rel_l2", float(np.median(l2s)), 1e-3)
+    assert e <= 1e-3 and worst <= 2e-3 and np.median(l2s) <= 1e-3, (e, worst, worst_name, np.median(l2s))
+    # greedy decode on a calibrated model: identical token sequence
+    x1, xm1, _, _ = make_batch(71, 1, 64, 256, 4)
+    P2 = O.calibrate_moving(O.lively_params(6), x1, xm1)
+    eng.P.load(P2)
+    ann1, _ = eng.dense_net(x1, None, training=False)
+    toks, lens, _ = eng.greedy_decode(ann1, 25, check_every=0)
+    ref_ann, _, _ = O.dense_net(O.to_torch(P2), t64(x1), t64(xm1), False)
+    ref_toks = O.greedy_decode(O.to_torch(P2), ref_ann, 25)
+    got = toks[0, : int(lens[0])].cpu().tolist()
+    report.add("tf32x3", "greedy_identical", 0.0 if got == ref_toks else 1.0, 0.0, extra=dict(got=got, ref=ref_toks))
+    assert got == ref_toks

@@ -60,6 +60,10 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
                            float* d_ann, float* wsp);
 int adadelta_l2_step(cudaStream_t st, float* p, const float* g, float* acc, float* accu, size_t n, size_t n_decay,
                      float lr, float rho, float eps, float l2, float gscale, double* l2_cost);
+void set_conv_precision(int mode);
+int get_conv_precision();
+extern int g_tc_debug_mask;
+extern int g_dbg_layer; extern float* g_dbg_buf;
 int mask_subsample(cudaStream_t st, const float* xm, int B, int H, int W, int h, int w, float* am);
 int dropout_mask(cudaStream_t st, uint32_t seed, uint32_t site, size_t n, float* mask);
 
@@ -192,15 +196,24 @@ int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, in
   return gemm_tn_atomic(ST(stream), A, lda, B, ldb, C, ldc, M, N, K);
 }
 int wap_tc_available(void) { return tc_available() ? 1 : 0; }
-int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, int ldb, float* D, int ldd, int M, int N, int K,
+int wap_set_conv_precision(int mode) {
+  WAP_REQUIRE(mode >= 0 && mode <= 2, "wap_set_conv_precision: mode must be 0 (fp32), 1 (tf32) or 2 (3xtf32)");
+  WAP_REQUIRE(mode == 0 || tc_available(), "TF32 tensor-core mode needs cuTensorMapEncodeTiled from the driver");
+  set_conv_precision(mode);
+  return 0;
+}
+int wap_get_conv_precision(void) { return get_conv_precision(); }
+int wap_debug_set_tc_mask(int mask) { g_tc_debug_mask = mask; return 0; }
+int wap_debug_capture(int layer, float* buf) { g_dbg_layer = layer; g_dbg_buf = buf; return 0; }
+int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
                 int accumulate, double* stats) {
   TcEpi e{D, ldd, accumulate, stats};
-  return tc_gemm(ST(stream), A, lda, Bt, ldb, M, N, K, e, kProfOtherGemm);
+  return tc_gemm(ST(stream), A, lda, Bt, Bt_lo, ldb, M, N, K, e, kProfOtherGemm);
 }
-int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N,
+int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
                    float* D, int ldd, double* stats) {
   TcEpi e{D, ldd, 0, stats};
-  return tc_conv3x3(ST(stream), x, ldx, B, H, W, C, Wt, Nrows, N, e, kProfOtherGemm);
+  return tc_conv3x3(ST(stream), x, ldx, B, H, W, C, Wt, Wt_lo, Nrows, N, e, kProfOtherGemm);
 }
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
   return dropout_mask(ST(stream), seed, site, (size_t)n, mask);
@@ -214,6 +227,11 @@ int64_t wap_encoder_workspace_offset(int B, int H, int W, int training, int what
     case 3: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.a1[arg] : -1;
     case 4: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.y2[arg] : -1;
     case 5: return (arg >= 0 && arg < kBlocks - 1) ? (int64_t)ws.ytr[arg] : -1;
+    case 6: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.wt_fwd[arg] : -1;
+    case 7: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.wt_bwd[arg] : -1;
+    case 8: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.wt_fwd_lo[arg] : -1;
+    case 9: return (arg >= 0 && arg < kNumConv) ? (int64_t)ws.wt_bwd_lo[arg] : -1;
+    case 10: return (int64_t)ws.total;
   }
   return -1;
 }

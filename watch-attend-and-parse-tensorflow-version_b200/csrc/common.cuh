@@ -46,6 +46,7 @@ constexpr int kVocab = 111;
 constexpr int kCovK = 11, kCovTaps = 121;
 constexpr int kNumConv = 99;
 constexpr int kMaxBnC = 304;   // >= max conv Cout (300), padded
+constexpr int kDy2Ld = 32;     // row stride of the 3x3-conv output gradient (24 channels zero-padded to one 128 B TMA row)
 constexpr float kBnEps = 1e-4f, kBnMomentum = 0.9f;
 constexpr float kDropRate = 0.2f;
 constexpr uint32_t kDropThresh = 13421772u;   // floor(0.8 * 2^24): keep iff (hash>>8) < thresh

@@ -10,6 +10,7 @@
 
 #include "gemm.cuh"
 #include "model.h"
+#include "tc_gemm.cuh"
 
 namespace wap {
 
@@ -138,7 +139,14 @@ struct BnActArgs {
   const float* gamma; const float* beta;
   float* saved;                              // [2][kMaxBnC]: mean, invstd (training) or null
   int training, dropout; uint32_t seed, site;
+  int round_tf32;                            // round the stored activation to TF32 (RNA): operand of a tcgen05 conv
 };
+
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
 __device__ __forceinline__ void bn_prologue(const BnActArgs& a, float* s_scale, float* s_shift) {
   const double cnt = (double)a.B * a.Hi * a.Wi;
@@ -216,6 +224,10 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
         for (int j = 0; j < 4; ++j) r[j] *= inv;
       }
     }
+    if (a.round_tf32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) r[j] = tf32_rna(r[j]);
+    }
     *reinterpret_cast<float4*>(a.out + po * a.ld_out + c) = make_float4(r[0], r[1], r[2], r[3]);
   }
 }
@@ -228,10 +240,11 @@ struct BnBwdArgs {
   const float* raw; int B, Hi, Wi, C;
   const float* dout; int Ho, Wo, ld_dout;    // gradient wrt the (pooled) activated output, channel slice
   const float* saved; const float* gamma; const float* beta;
-  float* g;                                  // [B*Hi*Wi, C]
+  float* g; int ld_g;                        // [B*Hi*Wi, ld_g]
   double* red;                               // [2][C]: sum g, sum g*xhat
   float* dgamma; float* dbeta;               // += (pass 2)
   int dropout; uint32_t seed, site;
+  int round_tf32;                            // round d raw to TF32 (operand of the tcgen05 dgrad)
 };
 
 template <int POOL>
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, c
         sg[j] += gj;
         sgx[j] = fmaf(gj, (vv[j] - s_mean[c + j]) * s_inv[c + j], sgx[j]);
       }
-      *reinterpret_cast<float4*>(a.g + p * a.C + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+      *reinterpret_cast<float4*>(a.g + p * a.ld_g + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) { atomicAdd(&s_sg[c + j], sg[j]); atomicAdd(&s_sgx[c + j], sgx[j]); }
@@ -333,16 +346,81 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
     const int c = (int)(i % C4) * 4;
     const size_t p = i / C4;
     const float4 v = ldg4(a.raw + p * a.C + c);
-    float4 g = *reinterpret_cast<const float4*>(a.g + p * a.C + c);
+    float4 g = *reinterpret_cast<const float4*>(a.g + p * a.ld_g + c);
     const float vv[4] = {v.x, v.y, v.z, v.w};
     float gg[4] = {g.x, g.y, g.z, g.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float xh = (vv[j] - s_mean[c + j]) * s_inv[c + j];
       gg[j] = s_k[c + j] * (gg[j] - s_mg[c + j] - xh * s_mgx[c + j]);
+      if (a.round_tf32) gg[j] = tf32_rna(gg[j]);
     }
-    *reinterpret_cast<float4*>(a.g + p * a.C + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    *reinterpret_cast<float4*>(a.g + p * a.ld_g + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
   }
+}
+
+// =====================================================================================
+// tcgen05 path: TF32-rounded (RNA), K-major copies of the conv weights, rebuilt from the live fp32
+// weights at every call (one launch for all 98 layers).
+//   fwd copy : [Cout(pad 32)][K]   with k = (tap*Cin + ci)          (B operand of the forward GEMM)
+//   bwd copy : 1x1 / transition: the HWIO matrix itself [Cin][Cout] (B operand of dgrad, K = Cout)
+//              3x3: [Cin=96][tap'*32 + co], tap' mirrored, co >= 24 zero  (dy2 rows are 32 floats)
+// =====================================================================================
+struct WPrepLayer { int kind, cin, cout; long long w, f, b, fl, bl; };
+__constant__ WPrepLayer c_wprep[kNumConv];
+
+__global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __restrict__ params, float* __restrict__ wsp, int with_bwd) {
+  const WPrepLayer L = c_wprep[blockIdx.y];
+  if (L.kind == kStem) return;
+  const float* w = params + L.w;
+  float* f = wsp + L.f; float* fl = wsp + L.fl;
+  float* b = wsp + L.b; float* bl = wsp + L.bl;
+  const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  auto split = [](float v, float* hi, float* lo) { const float h = tf32_rna(v); *hi = h; *lo = tf32_rna(v - h); };
+  if (L.kind == kC3) {
+    const int K = 9 * L.cin;                                  // 864
+    for (int i = t0; i < 32 * K; i += stride) {
+      const int n = i / K, k = i - n * K;
+      split(n < L.cout ? __ldg(w + (size_t)k * L.cout + n) : 0.f, f + i, fl + i);
+    }
+    if (with_bwd) {
+      const int Kb = 9 * kDy2Ld;                              // 288
+      for (int i = t0; i < L.cin * Kb; i += stride) {
+        const int ci = i / Kb, k = i - ci * Kb, tap = k / kDy2Ld, co = k - tap * kDy2Ld;
+        split(co < L.cout ? __ldg(w + ((size_t)(8 - tap) * L.cin + ci) * L.cout + co) : 0.f, b + i, bl + i);
+      }
+    }
+  } else {                                                    // 1x1: w[cin][cout]
+    const int n_el = L.cin * L.cout;
+    for (int i = t0; i < n_el; i += stride) {
+      const int n = i / L.cin, k = i - n * L.cin;
+      split(__ldg(w + (size_t)k * L.cout + n), f + i, fl + i);
+      if (with_bwd) split(__ldg(w + i), b + i, bl + i);
+    }
+  }
+}
+
+static int g_conv_precision = 0;          // 0: fp32 FFMA   1: TF32 tcgen05 (single pass, RNA-rounded operands)   2: 3xTF32 tcgen05 (fp32-grade)
+int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
+int g_tc_debug_mask = 0xFF;               // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd
+void set_conv_precision(int mode) { g_conv_precision = mode; }
+int get_conv_precision() { return g_conv_precision; }
+
+static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, const EncWorkspace& ws, bool with_bwd) {
+  static bool uploaded = false;
+  const ParamLayout& L = layout();
+  WPrepLayer h[kNumConv];
+  for (int i = 0; i < kNumConv; ++i) {
+    h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout;
+    h[i].w = (long long)L.conv[i].w; h[i].f = (long long)ws.wt_fwd[i]; h[i].b = (long long)ws.wt_bwd[i];
+    h[i].fl = (long long)ws.wt_fwd_lo[i]; h[i].bl = (long long)ws.wt_bwd_lo[i];
+  }
+  // offsets depend on the geometry (workspace layout): refresh the table on every call (cheap, 4 KB)
+  (void)uploaded;
+  WAP_CHECK(cudaMemcpyToSymbolAsync(c_wprep, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
+  prep_conv_weights_kernel<<<dim3(24, kNumConv), 256, 0, st>>>(params, wsp, with_bwd ? 1 : 0);
+  WAP_LAUNCH_CHECK();
+  return 0;
 }
 
 // =====================================================================================
@@ -389,6 +467,12 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
   double* stats = reinterpret_cast<double*>(wsp + ws.stats);
   float* saved = wsp + ws.saved;
   if (training) WAP_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * kNumConv * 2 * kMaxBnC, st));
+  const bool tc = g_conv_precision != 0, x3 = g_conv_precision == 2;
+  if (tc) {
+    WAP_REQUIRE(tc_available(), "TF32 tensor-core mode requested but cuTensorMapEncodeTiled is unavailable");
+    WAP_TRY(prep_conv_weights(st, params, wsp, ws, training != 0));
+  }
+  auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
   float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
   auto bn_args = [&](int k, const float* raw, int Hi, int Wi, float* out, int Ho, int Wo, int ld_out, bool drop) {
     const ConvLayer& c = L.conv[k];
@@ -400,6 +484,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
     a.gamma = params + c.gamma; a.beta = params + c.beta;
     a.saved = training ? saved + (size_t)k * 2 * kMaxBnC : nullptr;
     a.training = training; a.dropout = (training && dropout && drop) ? 1 : 0; a.seed = seed; a.site = (uint32_t)k;
+    a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;
   };
   // ---- stem (S:76-88)
@@ -421,17 +506,27 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       const ConvLayer& c3 = L.conv[k + 1];
       float* y1 = wsp + ws.y1[k]; float* a1 = wsp + ws.a1[k]; float* y2 = wsp + ws.y2[k + 1];
       {   // 1x1 bottleneck  C -> 96
-        ARowMajor A{buf[b], ld, M, C};
-        BRowMajor Bw{params + c1.w, kBottle, C, kBottle};
-        EpiStore e{y1, kBottle, nullptr, false, training ? stats + (size_t)k * 2 * kMaxBnC : nullptr};
-        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, C, 1, kProfConv1Fwd)));
+        double* sk = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
+        if (tc) {
+          WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, kBottle, C, TcEpi{y1, kBottle, 0, sk}, kProfConv1Fwd));
+        } else {
+          ARowMajor A{buf[b], ld, M, C};
+          BRowMajor Bw{params + c1.w, kBottle, C, kBottle};
+          EpiStore e{y1, kBottle, nullptr, false, sk};
+          WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, C, 1, kProfConv1Fwd)));
+        }
         WAP_TRY(run_bn_act(st, 0, bn_args(k, y1, h, w, a1, h, w, kBottle, true)));
       }
       {   // 3x3 growth  96 -> 24, written in place at channel offset C
-        AIm2col3 A{a1, kBottle, B, h, w, kBottle, false};
-        BRowMajor Bw{params + c3.w, kGrowth, 9 * kBottle, kGrowth};
-        EpiStore e{y2, kGrowth, nullptr, false, training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr};
-        WAP_TRY((launch_gemm<Cfg256x24>(st, A, Bw, e, M, kGrowth, 9 * kBottle, 1, kProfConv3Fwd)));
+        double* sk = training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr;
+        if (tc) {
+          WAP_TRY(tc_conv3x3(st, a1, kBottle, B, h, w, kBottle, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), 32, kGrowth, TcEpi{y2, kGrowth, 0, sk}, kProfConv3Fwd));
+        } else {
+          AIm2col3 A{a1, kBottle, B, h, w, kBottle, false};
+          BRowMajor Bw{params + c3.w, kGrowth, 9 * kBottle, kGrowth};
+          EpiStore e{y2, kGrowth, nullptr, false, sk};
+          WAP_TRY((launch_gemm<Cfg256x24>(st, A, Bw, e, M, kGrowth, 9 * kBottle, 1, kProfConv3Fwd)));
+        }
         WAP_TRY(run_bn_act(st, 0, bn_args(k + 1, y2, h, w, buf[b] + C, h, w, ld, true)));
       }
       C += kGrowth;
@@ -439,10 +534,15 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
     if (b < kBlocks - 1) {   // transition: 1x1 C -> C/2, BN, ReLU, dropout, avgpool (S:116-130)
       const ConvLayer& ct = L.conv[k];
       float* yt = wsp + ws.ytr[b];
-      ARowMajor A{buf[b], ld, M, C};
-      BRowMajor Bw{params + ct.w, ct.cout, C, ct.cout};
-      EpiStore e{yt, ct.cout, nullptr, false, training ? stats + (size_t)k * 2 * kMaxBnC : nullptr};
-      WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, ct.cout, C, 1, kProfTransFwd)));
+      double* sk = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
+      if (tc) {
+        WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, ct.cout, C, TcEpi{yt, ct.cout, 0, sk}, kProfTransFwd));
+      } else {
+        ARowMajor A{buf[b], ld, M, C};
+        BRowMajor Bw{params + ct.w, ct.cout, C, ct.cout};
+        EpiStore e{yt, ct.cout, nullptr, false, sk};
+        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, ct.cout, C, 1, kProfTransFwd)));
+      }
       WAP_TRY(run_bn_act(st, 2, bn_args(k, yt, h, w, buf[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], true)));
       ++k;
     }
@@ -462,14 +562,19 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   const float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
   float* G[kBlocks] = {wsp + ws.gbuf[0], wsp + ws.gbuf[1], d_annotation};
   float* dy1 = wsp + ws.dy1; float* da1 = wsp + ws.da1; float* dy2 = wsp + ws.dy2; float* dytr = wsp + ws.dytr;
-  auto bwd_args = [&](int k, const float* raw, int Hi, int Wi, const float* dout, int Ho, int Wo, int ld_dout, float* gbuf, bool drop) {
+  const bool tc = g_conv_precision != 0, x3 = g_conv_precision == 2;
+  auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
+  // dy2 rows are 32 floats (24 channels + zero pad) so that one row is one 128-byte TMA/UMMA row
+  WAP_CHECK(cudaMemsetAsync(dy2, 0, sizeof(float) * (size_t)g.M[0] * kDy2Ld, st));
+  auto bwd_args = [&](int k, const float* raw, int Hi, int Wi, const float* dout, int Ho, int Wo, int ld_dout, float* gbuf, int ld_g, bool drop) {
     const ConvLayer& c = L.conv[k];
     BnBwdArgs a;
     a.raw = raw; a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = c.cout;
     a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
     a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
-    a.g = gbuf; a.red = red; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
+    a.g = gbuf; a.ld_g = ld_g; a.red = red; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
     a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.site = (uint32_t)k;
+    a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;
   };
   int k = kNumConv - 1;     // 98: last 3x3
@@ -478,7 +583,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     if (b < kBlocks - 1) {   // transition b -> b+1 (conv index k)
       const ConvLayer& ct = L.conv[k];
       const int C = ld;
-      WAP_TRY(run_bn_bwd(st, 2, bwd_args(k, wsp + ws.ytr[b], h, w, G[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], dytr, true)));
+      WAP_TRY(run_bn_bwd(st, 2, bwd_args(k, wsp + ws.ytr[b], h, w, G[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], dytr, ct.cout, true)));
       {   // wgrad  dW[C, C/2] += buf^T * dy
         AColMajor A{buf[b], ld, C, M};
         BRowMajor Bd{dytr, ct.cout, M, ct.cout};
@@ -486,7 +591,9 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         const int tiles = cdiv(C, 128) * cdiv(ct.cout, 128);
         WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfTransBwd)));
       }
-      {   // dgrad  G[b] = dy * W^T   (initialises the whole gradient buffer of block b)
+      if (tc && (g_tc_debug_mask & 1)) {   // dgrad  G[b] = dy * W^T   (initialises the whole gradient buffer of block b)
+        WAP_TRY(tc_gemm(st, dytr, ct.cout, wsp + ws.wt_bwd[k], lo(ws.wt_bwd_lo[k]), ct.cout, M, C, ct.cout, TcEpi{G[b], ld, 0, nullptr}, kProfTransBwd));
+      } else {
         ARowMajor A{dytr, ct.cout, M, ct.cout};
         BColMajor Bw{params + ct.w, ct.cout, ct.cout, C};
         EpiStore e{G[b], ld, nullptr, false, nullptr};
@@ -501,21 +608,29 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
       const ConvLayer& c1 = L.conv[k1];
       const float* y1 = wsp + ws.y1[k1]; const float* a1 = wsp + ws.a1[k1]; const float* y2 = wsp + ws.y2[k3];
       // BN/ReLU/dropout backward of the 3x3 output
-      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k3, y2, h, w, G[b] + C, h, w, ld, dy2, true)));
+      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k3, y2, h, w, G[b] + C, h, w, ld, dy2, kDy2Ld, true)));
       {   // wgrad 3x3: dW[864,24] += im2col(a1)^T * dy2
         AIm2col3T A{a1, kBottle, B, h, w, kBottle};
-        BRowMajor Bd{dy2, kGrowth, M, kGrowth};
+        BRowMajor Bd{dy2, kDy2Ld, M, kGrowth};
         EpiAtomic e{grads + c3.w, kGrowth};
         const int tiles = cdiv(9 * kBottle, 128);
         WAP_TRY((launch_gemm<Cfg128x32>(st, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv3Wgrad)));
       }
-      {   // dgrad 3x3: d a1[M,96]
-        AIm2col3 A{dy2, kGrowth, B, h, w, kGrowth, false};
+      if (tc && (g_tc_debug_mask & 2)) {   // dgrad 3x3: d a1[M,96]
+        WAP_TRY(tc_conv3x3(st, dy2, kDy2Ld, B, h, w, kDy2Ld, wsp + ws.wt_bwd[k3], lo(ws.wt_bwd_lo[k3]), kBottle, kBottle, TcEpi{da1, kBottle, 0, nullptr}, kProfConv3Dgrad));
+      } else {
+        AIm2col3 A{dy2, kDy2Ld, B, h, w, kGrowth, false};
         BDgrad3 Bw{params + c3.w, kBottle, kGrowth};
         EpiStore e{da1, kBottle, nullptr, false, nullptr};
         WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, 9 * kGrowth, 1, kProfConv3Dgrad)));
       }
-      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, true)));
+      if (k1 == g_dbg_layer && g_dbg_buf != nullptr) {   // [da1 (M*96) | dy2 (M*32)]
+        WAP_CHECK(cudaMemcpyAsync(g_dbg_buf, da1, sizeof(float) * (size_t)M * kBottle, cudaMemcpyDeviceToDevice, st));
+        WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * kBottle, dy2, sizeof(float) * (size_t)M * kDy2Ld, cudaMemcpyDeviceToDevice, st));
+      }
+      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, kBottle, true)));
+      if (k1 == g_dbg_layer && g_dbg_buf != nullptr)     // [.. | dy1 (M*96)]
+        WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * (kBottle + kDy2Ld), dy1, sizeof(float) * (size_t)M * kBottle, cudaMemcpyDeviceToDevice, st));
       {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
         AColMajor A{buf[b], ld, C, M};
         BRowMajor Bd{dy1, kBottle, M, kBottle};
@@ -523,7 +638,9 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         const int tiles = cdiv(C, 128);
         WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv1Wgrad)));
       }
-      {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
+      if (tc && (g_tc_debug_mask & 4)) {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
+        WAP_TRY(tc_gemm(st, dy1, kBottle, wsp + ws.wt_bwd[k1], lo(ws.wt_bwd_lo[k1]), kBottle, M, C, kBottle, TcEpi{G[b], ld, 1, nullptr}, kProfConv1Dgrad));
+      } else {
         ARowMajor A{dy1, kBottle, M, kBottle};
         BColMajor Bw{params + c1.w, kBottle, kBottle, C};
         EpiStore e{G[b], ld, nullptr, true, nullptr};
@@ -534,7 +651,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   // ---- stem: maxpool + ReLU + BN backward, then the 7x7 weight gradient (no dgrad: input is the image)
   {
     float* gstem = wsp + ws.gstem;
-    WAP_TRY(run_bn_bwd(st, 1, bwd_args(0, wsp + ws.stem_raw, g.Hs, g.Ws, G[0], g.h[0], g.w[0], g.Ctot[0], gstem, false)));
+    WAP_TRY(run_bn_bwd(st, 1, bwd_args(0, wsp + ws.stem_raw, g.Hs, g.Ws, G[0], g.h[0], g.w[0], g.Ctot[0], gstem, kStemC, false)));
     int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
     dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
     stem_wgrad_kernel<<<grid, 256, 0, st>>>(x, gstem, grads + L.conv[0].w, H, W, g.Hs, g.Ws, pt, pl);

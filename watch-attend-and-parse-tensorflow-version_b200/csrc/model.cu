@@ -126,11 +126,21 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
     for (int b = 0; b < kBlocks - 1; ++b) ws.gbuf[b] = take((size_t)g.M[b] * g.Ctot[b]);
     ws.dy1 = take((size_t)g.M[0] * kBottle);
     ws.da1 = take((size_t)g.M[0] * kBottle);
-    ws.dy2 = take((size_t)g.M[0] * kGrowth);
+    ws.dy2 = take((size_t)g.M[0] * kDy2Ld);
     size_t tr = 0;
     for (int b = 0; b < kBlocks - 1; ++b) tr = std::max(tr, (size_t)g.M[b] * (g.Ctot[b] / 2));
     ws.dytr = take(tr);
     ws.gstem = take((size_t)g.B * g.Hs * g.Ws * kStemC);
+  }
+  for (int i = 0; i < kNumConv; ++i) {       // tcgen05 weight copies: fwd [N(pad)][K], bwd (dgrad) [Cin][K']
+    const ConvLayer& c = L.conv[i];
+    if (c.kind == kC1 || c.kind == kTr) {
+      ws.wt_fwd[i] = take((size_t)c.cout * c.cin); ws.wt_fwd_lo[i] = take((size_t)c.cout * c.cin);
+      if (training) { ws.wt_bwd[i] = take((size_t)c.cin * c.cout); ws.wt_bwd_lo[i] = take((size_t)c.cin * c.cout); }
+    } else if (c.kind == kC3) {
+      ws.wt_fwd[i] = take((size_t)32 * 9 * kBottle); ws.wt_fwd_lo[i] = take((size_t)32 * 9 * kBottle);
+      if (training) { ws.wt_bwd[i] = take((size_t)kBottle * 9 * kDy2Ld); ws.wt_bwd_lo[i] = take((size_t)kBottle * 9 * kDy2Ld); }
+    }
   }
   ws.total = off;
   return ws;

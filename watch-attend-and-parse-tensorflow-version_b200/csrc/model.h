@@ -65,7 +65,9 @@ struct EncWorkspace {
   size_t saved;                          // floats:  [99][2][kMaxBnC]   mean, invstd
   // backward scratch
   size_t gbuf[kBlocks - 1];              // d block buffer 0,1
-  size_t dy1, da1, dy2, dytr, gstem;     // largest-block sized scratch
+  size_t dy1, da1, dy2, dytr, gstem;     // largest-block sized scratch (dy2 has row stride kDy2Ld = 32)
+  size_t wt_fwd[kNumConv], wt_bwd[kNumConv];   // TF32-rounded K-major weight copies for the tcgen05 path (hi parts)
+  size_t wt_fwd_lo[kNumConv], wt_bwd_lo[kNumConv];   // residuals rna(w - hi) for the 3xTF32 mode
   size_t red;                            // doubles [2][kMaxBnC]
   size_t total;                          // floats
 };

@@ -111,27 +111,42 @@ struct TcShape {
   int B, H, W, kb_per_tap, TW, TH, tiles_x, tiles_y;
 };
 
-template <int BN> struct TcSmem {
-  static constexpr int kStages = BN <= 32 ? 4 : 3;                  // 2 CTAs/SM must fit in 227 KB
+// X3 = error-compensated "3xTF32": D = a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32-grade accuracy).
+// Stage layout: [A (hi)] [A lo] [B hi] [B lo]; the lo tiles exist only when X3.
+template <int BN, bool X3> struct TcSmem {
+  static constexpr int kStages = X3 ? 3 : (BN <= 32 ? 4 : 3);       // X3: 1 CTA/SM (<= 192 KB); else 2 CTAs/SM
   static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
   static constexpr int kBBytes = BN * kTcBK * 4;
-  static constexpr int kStage = kABytes + kBBytes;
+  static constexpr int kStage = (X3 ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kBarOff = kStages * kStage;
   static constexpr int kStatOff = kBarOff + 128;                    // barriers + tmem slot
   static constexpr int kTotal = kStatOff + 2 * BN * 4 + 1024;       // + alignment slack
 };
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_rna_dev(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
 
-template <int BN, bool IM2COL>
-__global__ void __launch_bounds__(kTcThreads, 2)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcEpi epi, const TcShape sh) {
-  using S = TcSmem<BN>;
+template <int BN, bool IM2COL, bool X3>
+__global__ void __launch_bounds__(kTcThreads, X3 ? 1 : 2)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const TcEpi epi, const TcShape sh) {
+  using S = TcSmem<BN, X3>;
   constexpr int kTcStages = S::kStages;
-  constexpr uint32_t kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  // X3 keeps the two small correction products in a SECOND accumulator (columns [kAcc2, kAcc2+BN)) so that their
+  // fp32 accumulation error is relative to their own 2^-11-times smaller magnitude; the epilogue adds the two.
+  constexpr uint32_t kAcc2 = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;
+  constexpr uint32_t kTmemCols = (X3 ? 2 : 1) * (BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
   uint64_t* empty_bar = full_bar + kTcStages;
-  uint64_t* tmem_full = empty_bar + kTcStages;
+  uint64_t* split_bar = empty_bar + kTcStages;
+  uint64_t* tmem_full = split_bar + kTcStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
   float* s_stat = reinterpret_cast<float*>(smem + S::kStatOff);
 
@@ -150,7 +165,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
-    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    if (X3) prefetch_tmap(&tmBlo);
+    for (int s = 0; s < kTcStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
@@ -170,8 +186,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / kTcStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
         uint8_t* sa = smem + s * S::kStage;
-        uint8_t* sb = sa + S::kABytes;
-        mbar_expect_tx(&full_bar[s], S::kABytes + S::kBBytes);
+        uint8_t* sb = sa + (X3 ? 2 : 1) * S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kABytes + (X3 ? 2 : 1) * S::kBBytes);
         if (IM2COL) {
           const int tap = kb / sh.kb_per_tap, cb = kb - tap * sh.kb_per_tap;
           tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
@@ -179,6 +195,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(sa, &tmA, &full_bar[s], kb * kTcBK, m0);
         }
         tma_load_2d(sb, &tmB, &full_bar[s], kb * kTcBK, n0);
+        if (X3) tma_load_2d(sb + S::kBBytes, &tmBlo, &full_bar[s], kb * kTcBK, n0);
       }
     }
   } else if (warp == 1) {
@@ -188,15 +205,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < sh.nkb; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * S::kStage);
-        const uint32_t sb = sa + S::kABytes;
+        const uint32_t sb = sa + (X3 ? 2 : 1) * S::kABytes;
 #pragma unroll
         for (int k = 0; k < kTcBK / 8; ++k) {
           const uint64_t ad = make_kmajor_sw128_desc(sa + k * 32);
           const uint64_t bd = make_kmajor_sw128_desc(sb + k * 32);
           umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+          if (X3) {
+            const uint64_t ald = make_kmajor_sw128_desc(sa + S::kABytes + k * 32);
+            const uint64_t bld = make_kmajor_sw128_desc(sb + S::kBBytes + k * 32);
+            umma_tf32(tmem_base + kAcc2, ald, bd, idesc, (kb | k) != 0 ? 1u : 0u);     // a_lo * b_hi
+            umma_tf32(tmem_base + kAcc2, ad, bld, idesc, 1u);                          // a_hi * b_lo
+          }
         }
         umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
       }
@@ -204,6 +227,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else {
     // ================================================= epilogue (warps 2..5)
+    if (X3) {
+      // ---- operand splitter (main loop): A tile (raw fp32 from TMA) -> hi = rna_tf32(a) in place, lo = a - hi.
+      // Element-wise at identical offsets, so the 128B swizzle pattern is preserved without any index math.
+      const int t = threadIdx.x - 64;
+      for (int kb = 0; kb < sh.nkb; ++kb) {
+        const int s = kb % kTcStages;
+        const uint32_t ph = (kb / kTcStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        float4* hi = reinterpret_cast<float4*>(smem + s * S::kStage);
+        float4* lo = reinterpret_cast<float4*>(smem + s * S::kStage + S::kABytes);
+#pragma unroll
+        for (int i = 0; i < S::kABytes / 16 / 128; ++i) {
+          const float4 v = hi[t + i * 128];
+          float4 h, l;
+          h.x = tf32_rna_dev(v.x); h.y = tf32_rna_dev(v.y); h.z = tf32_rna_dev(v.z); h.w = tf32_rna_dev(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          hi[t + i * 128] = h; lo[t + i * 128] = l;
+        }
+        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
+    }
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;             // output row within the tile
     bool valid; size_t mrow;
@@ -222,6 +268,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int c = 0; c < BN; c += 32) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (X3) {
+        float v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2 + (uint32_t)c, v2);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += v2[i];
+      }
       if (valid) {
         float* dst = epi.out + mrow * epi.ld + n0 + c;
 #pragma unroll
@@ -304,25 +356,31 @@ static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_
   return 0;
 }
 
-template <int BN, bool IM2COL>
-static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const TcEpi& epi, const TcShape& sh, dim3 grid,
-                     int prof_cls, double flops) {
+template <int BN, bool IM2COL, bool X3>
+static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
+                      const TcShape& sh, dim3 grid, int prof_cls, double flops) {
   static bool configured = false;
   if (!configured) {
-    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN>::kTotal));
+    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3>::kTotal));
     configured = true;
   }
   prof_begin(st, prof_cls, flops);
-  tc_gemm_kernel<BN, IM2COL><<<grid, kTcThreads, TcSmem<BN>::kTotal, st>>>(ta, tb, epi, sh);
+  tc_gemm_kernel<BN, IM2COL, X3><<<grid, kTcThreads, TcSmem<BN, X3>::kTotal, st>>>(ta, tb, tblo, epi, sh);
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
 }
+template <int BN, bool IM2COL>
+static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tblo, const TcEpi& epi,
+                     const TcShape& sh, dim3 grid, int prof_cls, double flops) {
+  if (tblo != nullptr) return launch_tc1<BN, IM2COL, true>(st, ta, tb, *tblo, epi, sh, grid, prof_cls, flops);
+  return launch_tc1<BN, IM2COL, false>(st, ta, tb, tb, epi, sh, grid, prof_cls, flops);
+}
 
-int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
+int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
   WAP_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (epi.ld & 3) == 0, "tc_gemm: strides must be multiples of 4 floats");
   WAP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)epi.out & 15) == 0, "tc_gemm: pointers must be 16-byte aligned");
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbl;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)lda * 4}; const uint32_t box[2] = {kTcBK, kTcBM};
     WAP_TRY(make_map(&ta, A, 2, dims, str, box));
@@ -331,20 +389,22 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, int ldb, 
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; const uint64_t str[1] = {(uint64_t)ldb * 4}; const uint32_t box[2] = {kTcBK, (uint32_t)BN};
     WAP_TRY(make_map(&tb, Bt, 2, dims, str, box));
+    if (Bt_lo != nullptr) WAP_TRY(make_map(&tbl, Bt_lo, 2, dims, str, box));
   }
   TcShape sh{}; sh.M = M; sh.N = N; sh.K = K; sh.nkb = cdiv(K, kTcBK);
   dim3 grid(cdiv(M, kTcBM), cdiv(N, BN));
   const double flops = 2.0 * M * N * K;
-  if (BN == 32) return launch_tc<32, false>(st, ta, tb, epi, sh, grid, prof_cls, flops);
-  if (BN == 96) return launch_tc<96, false>(st, ta, tb, epi, sh, grid, prof_cls, flops);
-  return launch_tc<128, false>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+  const CUtensorMap* pl = Bt_lo != nullptr ? &tbl : nullptr;
+  if (BN == 32) return launch_tc<32, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 96) return launch_tc<96, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  return launch_tc<128, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
 }
 
-int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, int Nrows, int N, const TcEpi& epi, int prof_cls) {
+int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N, const TcEpi& epi, int prof_cls) {
   WAP_REQUIRE(C % kTcBK == 0 && (ldx & 3) == 0 && (epi.ld & 3) == 0, "tc_conv3x3: C=%d must be a multiple of 32", C);
   int TW = 1; while (TW < W && TW < kTcBM) TW <<= 1;     // power of two >= W, at most 128
   const int TH = kTcBM / TW;
-  CUtensorMap ta, tb;
+  CUtensorMap ta, tb, tbl;
   {
     const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
     const uint64_t str[3] = {(uint64_t)ldx * 4, (uint64_t)W * ldx * 4, (uint64_t)H * W * ldx * 4};
@@ -356,14 +416,16 @@ int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, in
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)Nrows}; const uint64_t str[1] = {(uint64_t)K * 4}; const uint32_t box[2] = {kTcBK, (uint32_t)BN};
     WAP_TRY(make_map(&tb, Wt, 2, dims, str, box));
+    if (Wt_lo != nullptr) WAP_TRY(make_map(&tbl, Wt_lo, 2, dims, str, box));
   }
+  const CUtensorMap* pl = Wt_lo != nullptr ? &tbl : nullptr;
   TcShape sh{}; sh.M = B * H * W; sh.N = N; sh.K = K; sh.nkb = K / kTcBK;
   sh.B = B; sh.H = H; sh.W = W; sh.kb_per_tap = C / kTcBK; sh.TW = TW; sh.TH = TH; sh.tiles_x = cdiv(W, TW); sh.tiles_y = cdiv(H, TH);
   dim3 grid(sh.tiles_x * sh.tiles_y * B, cdiv(N, BN));
   const double flops = 2.0 * sh.M * N * K;
-  if (BN == 32) return launch_tc<32, true>(st, ta, tb, epi, sh, grid, prof_cls, flops);
-  if (BN == 96) return launch_tc<96, true>(st, ta, tb, epi, sh, grid, prof_cls, flops);
-  return launch_tc<128, true>(st, ta, tb, epi, sh, grid, prof_cls, flops);
+  if (BN == 32) return launch_tc<32, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 96) return launch_tc<96, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  return launch_tc<128, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
 }
 
 }  // namespace wap

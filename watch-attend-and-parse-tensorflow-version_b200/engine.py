@@ -136,6 +136,16 @@ class WAPEngine:
         self.world_size = 1
         self.launches_last_step = 0
 
+    # ------------------------------------------------------------------ precision
+    def set_conv_precision(self, mode: str) -> None:
+        """'fp32' (FFMA), 'tf32' (tcgen05 single pass, 10-bit mantissa products) or 'tf32x3'
+        (error-compensated 3xTF32 on tcgen05: fp32-grade accuracy) for the dense-block / transition
+        convolutions (forward and data gradients).  Library-global."""
+        _lib.check(self.L.wap_set_conv_precision({"fp32": 0, "tf32": 1, "tf32x3": 2}[mode]), "wap_set_conv_precision")
+
+    def conv_precision(self) -> str:
+        return ["fp32", "tf32", "tf32x3"][self.L.wap_get_conv_precision()]
+
     # ------------------------------------------------------------------ helpers
     def _buf(self, key: tuple, n: int, dtype=torch.float32) -> torch.Tensor:
         t = self._ws.get(key)
