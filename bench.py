@@ -147,7 +147,7 @@ def run_reference(args):
                                    f"torch-CPU fp32; TensorFlow 1.6 is not installable here)"},
         "e2e": {"value": v, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
 
 
 def run_ours(args):
@@ -207,7 +207,7 @@ def run_ours(args):
     launches = int(L.wap_launch_count() - n0)
     clocks = sampler.stop() if rank == 0 else None
     if args.profile_run:
-        print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms / args.steps, "gpu_launches": launches}))
+        print(json.dumps({"profile_run": True, "ms_per_step_under_profiler": ms / args.steps, "gpu_launches": launches}), flush=True)
         return
     for _ in range(2):
         step_e2e()
@@ -229,9 +229,35 @@ def run_ours(args):
             prof[name] = dict(ms_per_step=t.value / psteps, launches_per_step=n.value // psteps, gflop_per_step=f.value / psteps / 1e9,
                               tflops=f.value / (t.value * 1e-3) / 1e12 if t.value > 0 else 0.0)
     L.wap_profile_reset()
+    # ---- decoder-step leg (BASELINE metric part 2: "decoder-step us/token"): greedy decode of this rank's
+    # B annotations, whole loop on the device (wap_greedy_decode), fixed 40 steps, CUDA-event timed.
+    decode = None
+    if not args.no_decode:       # every rank runs it (keeps the ranks in lock-step); rank 0 reports
+        ann, _ = eng.dense_net(xd, None, training=False)
+        h, w = ann.shape[1], ann.shape[2]
+        nsteps = 40
+        for _ in range(2):
+            eng.greedy_decode(ann, nsteps, check_every=0)
+        torch.cuda.synchronize()
+        n1 = L.wap_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        e0.record()
+        for _ in range(reps):
+            eng.greedy_decode(ann, nsteps, check_every=0)
+        e1.record(); torch.cuda.synchronize()
+        us_step = e0.elapsed_time(e1) * 1e3 / (reps * nsteps)
+        Ld = h * w
+        bytes_step = 4 * B * Ld * 684 + 4 * B * Ld * 512 + 12 * B * Ld + 4 * 1632496 + 4 * B * 879
+        pkd = peaks()
+        decode = {"us_per_step": us_step, "us_per_token": us_step / B, "tokens_per_s": B / (us_step * 1e-6), "batch": B, "L": Ld,
+                  "launches_per_step": (L.wap_launch_count() - n1) / (reps * nsteps),
+                  "roofline": {"bound": "hbm", "achieved": bytes_step / (us_step * 1e-6) / 1e9, "peak": pkd["hbm_gbs"], "unit": "GB/s",
+                               "frac": bytes_step / (us_step * 1e-6) / 1e9 / pkd["hbm_gbs"], "algorithmic_bytes_per_step": bytes_step,
+                               "note": "includes the one-off precompute (watch GEMM, h0) amortised over 40 steps"}}
+        log(f"decode leg: {us_step:.1f} us/step at B={B}, L={Ld}")
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        finish(dist)
         return
     pk = peaks()
     top = max((k for k in prof if k != "other_gemm"), key=lambda k: prof[k]["ms_per_step"])
@@ -262,14 +288,26 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches,
         "roofline": roof,
+        "decode": decode,
     }
     if cpu_v is not None:
         line["cpu_baseline"] = {"value": cpu_v, "unit": "images/s", "cores": cores, "kind": "port",
                                 "sample": f"{cpu_n} training step(s) (after 1 warm-up) of the full {B}x{IMG_H}x{IMG_W}, T={CAP_LEN + 1} batch; "
                                           f"oracle port of the TF-1.6 graph in torch-CPU fp32 ({cpu_sps:.2f} s/step)"}
-    print(json.dumps(line))
+    log("printing result line")
+    out = json.dumps(line)
+    print(out, flush=True)
+    log("result line printed (%d bytes)" % len(out))
+    finish(dist)
+
+
+def finish(dist):
     if dist is not None:
-        dist.destroy_process_group()
+        try:
+            dist.barrier()
+            dist.destroy_process_group()
+        except Exception as e:      # teardown problems must not lose the result line
+            log("process-group teardown:", e)
 
 
 def main():
@@ -281,6 +319,7 @@ def main():
     ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3"],
                     help="dense-block conv arithmetic: fp32 FFMA | tf32 tcgen05 (single pass) | tf32x3 tcgen05 (error-compensated, fp32-grade; default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--profile-run", action="store_true", help="under ncu: honour --warmup exactly, skip e2e/roofline/cpu legs")
     args = ap.parse_args()
     if args.impl == "reference":
