@@ -80,6 +80,15 @@ int wap_greedy_decode(void* stream, const float* params, const float* annotation
                       int maxlen, int check_every, int32_t* tokens, int32_t* lengths, float* workspace,
                       int* steps_run);
 
+/* ---- the same greedy decode as ONE persistent cooperative kernel (all decoder weights resident in shared
+ * memory, grid-wide barriers between the phases of a step, termination decided on the device).
+ * Bn <= 16, h*w <= 2048.  Never synchronises the host; steps_run_dev (device int, may be NULL) receives
+ * the number of steps executed.  ignore_eol != 0 (benchmarking): never stop early, always run maxlen steps. */
+int64_t wap_greedy_persistent_workspace_floats(int Bn, int h, int w);
+int wap_greedy_decode_persistent(void* stream, const float* params, const float* annotation, int Bn, int h, int w,
+                                 int maxlen, int ignore_eol, int32_t* tokens, int32_t* lengths, float* workspace,
+                                 int32_t* steps_run_dev);
+
 /* ---- WAP.get_cost (S:337-375) forward over the whole caption (tf.scan of Parser.one_time_step,
  *      S:246-308) and its gradient.  y int32 [T,B], y_mask [T,B], a_mask [B,h,w].
  *      cost (device double) = mean_B sum_T mask*CE  (no L2 term; see wap_adadelta_l2_step).

@@ -328,3 +328,21 @@ def test_train_steps_match_oracle(report):
         if mv > 1e-3:
             fails.append(("moving", step, mv))
     assert not fails, fails
+
+
+@pytest.mark.parametrize("B,h,w", [(8, 8, 32), (16, 5, 9), (1, 4, 16), (3, 20, 50)])
+def test_greedy_persistent_matches_stepwise(report, B, h, w):
+    """The single-launch persistent decoder emits exactly the token sequences of the step-by-step kernels
+    (which test_greedy_and_beam_sequences_identical ties to the oracle), incl. lengths and early stop."""
+    P = O.lively_params(6)
+    eng = engine_with(P)
+    anns = torch.as_tensor(np.concatenate([_rand_annotation(70 + i, 1, h, w) for i in range(B)], 0)).cuda()
+    t1, l1, _ = eng.greedy_decode(anns, 30, check_every=0, persistent=False)
+    t2, l2, _ = eng.greedy_decode(anns, 30, persistent=True)
+    torch.cuda.synchronize()
+    ok = bool((l1 == l2).all()) and all(t1[b, : int(l1[b])].tolist() == t2[b, : int(l2[b])].tolist() for b in range(B))
+    report.add("greedy_persistent", f"B{B}_{h}x{w}", 0.0 if ok else 1.0, 0.0, extra=dict(l1=l1.tolist(), l2=l2.tolist(), t1=t1[0].tolist(), t2=t2[0].tolist()))
+    assert ok, (l1.tolist(), l2.tolist(), t1[0].tolist(), t2[0].tolist())
+    if B <= 3:
+        ref = O.greedy_decode(O.to_torch(P), t64(anns[:1].cpu().numpy()), 30)
+        assert t2[0, : int(l2[0])].tolist() == ref

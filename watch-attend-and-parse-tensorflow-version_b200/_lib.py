@@ -36,6 +36,8 @@ SIGNATURES = {
     "wap_decoder_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wap_greedy_workspace_floats": (_i64, [_i, _i, _i]),
     "wap_greedy_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ip]),
+    "wap_greedy_persistent_workspace_floats": (_i64, [_i, _i, _i]),
+    "wap_greedy_decode_persistent": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "wap_decoder_train_workspace_floats": (_i64, [_i, _i, _i, _i]),
     "wap_decoder_train_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
     "wap_decoder_train_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),

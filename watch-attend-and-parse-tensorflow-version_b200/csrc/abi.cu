@@ -58,6 +58,9 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
 int decoder_train_backward(cudaStream_t st, const float* params, float* grads, const float* ann, const float* a_mask,
                            const int* y, const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
                            float* d_ann, float* wsp);
+size_t greedy_persist_ws_floats(int Bn, int L);
+int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
+                             int* tokens, int* lengths, float* wsp, int* steps_run_dev);
 int adadelta_l2_step(cudaStream_t st, float* p, const float* g, float* acc, float* accu, size_t n, size_t n_decay,
                      float lr, float rho, float eps, float l2, float gscale, double* l2_cost);
 void set_conv_precision(int mode);
@@ -161,6 +164,13 @@ int wap_greedy_decode(void* stream, const float* params, const float* annotation
                       int maxlen, int check_every, int32_t* tokens, int32_t* lengths, float* workspace, int* steps_run) {
   WAP_REQUIRE(params && annotation && tokens && lengths && workspace && maxlen > 0, "wap_greedy_decode: bad arguments");
   return greedy_decode(ST(stream), params, annotation, Bn, h, w, maxlen, check_every, tokens, lengths, workspace, steps_run);
+}
+
+int64_t wap_greedy_persistent_workspace_floats(int Bn, int h, int w) { return (int64_t)greedy_persist_ws_floats(Bn, h * w); }
+int wap_greedy_decode_persistent(void* stream, const float* params, const float* annotation, int Bn, int h, int w, int maxlen,
+                                 int ignore_eol, int32_t* tokens, int32_t* lengths, float* workspace, int32_t* steps_run_dev) {
+  WAP_REQUIRE(params && annotation && tokens && lengths && workspace && maxlen > 0, "wap_greedy_decode_persistent: bad arguments");
+  return greedy_decode_persistent(ST(stream), params, annotation, Bn, h, w, maxlen, ignore_eol, tokens, lengths, workspace, steps_run_dev);
 }
 
 int64_t wap_decoder_train_workspace_floats(int B, int h, int w, int T) { return (int64_t)decoder_train_ws_floats(B, h * w, T); }

@@ -1,0 +1,487 @@
+// Persistent greedy decoder: the WHOLE token loop of WAP.get_word / get_sample(argmax)
+// (model-single-GPU.py:379-439, :461-483) in ONE cooperative kernel launch.
+//
+// One CTA per SM.  Every decoder weight (6.5 MB fp32) is sliced across the CTAs and stays RESIDENT in
+// shared memory for the whole sequence: each CTA owns <= 2 GRU hidden units (their r/z/candidate
+// columns of all six GRU matrices), <= 4 speller columns of W_a, one maxout pair of the logit layer,
+// and a [121 taps x 128 channels] slice of the fused coverage filter Q' = Q*U_f.  A time step is six
+// phases separated by a grid-wide barrier (atomic counter + acquire spin; co-residency is guaranteed
+// by the cooperative launch):
+//   A  GRU-1 gates for the owned units              (needs y_{t-1}, h_{t-1})      -> pre_h
+//   B  speller columns, GRU-2 pre_h-side products   (needs pre_h)                 -> SP (global), smem
+//   C  coverage stencil + tanh + V_a dot            (CTA = position group x 128-channel group) -> e += partial
+//   D  masked softmax, alpha_past update, context   (CTA = image x channel chunk) -> ctx
+//   E  GRU-2 for the owned units; emb/ctx part of the owned logit pair           -> h_t
+//   F  h part of the logit pair, maxout                                          -> MO
+//   G  (no barrier) every CTA redundantly evaluates Wo, argmax and the stop rule, so the next token and
+//      the termination decision are known CTA-locally: no host round trip, no extra barrier.
+// Per step the only HBM/L2 traffic is the annotation (context), the hoisted watch tensor, alpha_past and
+// a few KB of vectors: the algorithmic bytes of SURVEY 8d minus the (now on-chip) weights.
+#include <algorithm>
+
+#include "decoder.cuh"
+
+namespace wap {
+
+int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
+                    float* watch, float* h0, float* qf, float* mean_scratch);
+
+namespace {
+
+constexpr int kPT = 256;                  // threads per CTA
+constexpr int kMaxB = 16;                 // sequences per launch
+constexpr int kMaxL = 2048;               // annotation positions per image supported by the smem carve-up
+constexpr int kPadMax = 6144;             // floats of the zero-bordered alpha_past image (H+10)*(W+10) staged in smem
+constexpr int kCG = 4, kCGW = kNA / kCG;  // coverage channel groups: 4 x 128
+constexpr int kMinCtas = 128;             // ownership scheme needs >= 128 CTAs (<= 2 hidden units per CTA)
+
+struct DecOff {   // offsets (floats) into the flat parameter buffer
+  int U_f_b, W_a, W_a_b, V_a, V_a_b, W_yz_yr, b_yz_yr, U_hz_hr, W_yh, b_yh, U_rh, U_hz_hr_nl, b_hz_hr_nl, W_c_z_r, U_rh_nl,
+      b_rh_nl, W_c_h_nl, embed, Wc, bc, Wh, bh, Wy, by, Wo, bo;
+};
+
+struct PersistArgs {
+  const float* params; const float* ann; const float* watch; const float* qf; const float* h0;
+  DecOff o;
+  int Bn, H, W, L, maxlen, ignore_eol;
+  // global scratch (cross-CTA); read with ld.global.cg after a barrier
+  float* hbuf;      // [2][Bn][256]  ping-pong hidden state
+  float* pre_h;     // [Bn][256]
+  float* SP;        // [Bn][512]
+  float* E;         // [2][Bn][L]    energies (ping-pong: the buffer of step t+1 is zeroed during step t)
+  float* ap;        // [Bn][L]       alpha_past
+  float* ctx;       // [Bn][684]
+  float* MO;        // [Bn][128]
+  float* LOg;       // [2][Bn][112]  output logits accumulated by the pair owners (ping-pong, pre-set to bo)
+  unsigned* barrier;
+  int* tokens; int* lengths;   // [Bn][maxlen], [Bn]
+  int* steps_run;
+  long long* prof;   // optional [8]: accumulated SM cycles of CTA 0 per phase (A,B,C,D,E,F,G) + setup
+};
+
+// Grid-wide barrier: one monotonically increasing counter (RED.ADD by thread 0 of every CTA, acquire spin).
+// Co-residency of all CTAs is guaranteed by the cooperative launch.  (A flag-per-CTA variant polled by a
+// warp measured ~2 us SLOWER per barrier on B200: 148 acquire loads per waiter.)
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned nblocks, unsigned& epoch) {
+  __syncthreads();
+  ++epoch;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned target = epoch * nblocks;
+    atomicAdd(counter, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    } while (v < target);
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ float warp_dot(const float* x, const float* w, int n, int lane) {
+  float s = 0.f;
+  for (int k = lane; k < n; k += 32) s = fmaf(x[k], w[k], s);
+  return warp_sum(s);
+}
+// column `col` of a row-major [K][N] matrix -> contiguous smem
+__device__ __forceinline__ void load_col(float* dst, const float* W, int K, int N, int col) {
+  for (int k = threadIdx.x; k < K; k += kPT) dst[k] = __ldg(W + (size_t)k * N + col);
+}
+
+// cross-CTA vector -> smem with independent 128-bit L2 loads (n4 float4's, both pointers 16-byte aligned)
+__device__ __forceinline__ void stage_cg(float* dst, const float* src, int n4) {
+  const float4* s4 = reinterpret_cast<const float4*>(src);
+  float4* d4 = reinterpret_cast<float4*>(dst);
+#pragma unroll 4
+  for (int i = threadIdx.x; i < n4; i += kPT) d4[i] = __ldcg(s4 + i);
+}
+
+constexpr int kSmemFloats = kCovTaps * kCGW + 2 * 6 * kN + 2 * 3 * kN + 2 * 3 * kD + 4 * kN + 2 * kMw + 2 * kD + 2 * kN +
+                            kMaxB * kD + 2 * kMaxB * 8 + kPadMax + 64 + 16 * 64 + kMaxB * 112 + 2 * kMaxB + 2 * 112;
+
+__global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const PersistArgs a) {
+  extern __shared__ __align__(16) float sm[];
+  const int cta = blockIdx.x, nC = gridDim.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int Bn = a.Bn, L = a.L;
+  const float* P = a.params; const DecOff& o = a.o;
+  // ---- shared memory carve-up
+  float* Qs = sm;                                   // [121][128]   coverage filter slice
+  float* WA = Qs + kCovTaps * kCGW;                 // [2][6][256]  GRU-1 columns of the owned units
+  float* WB = WA + 2 * 6 * kN;                      // [2][3][256]  GRU-2 pre_h-side columns
+  float* WE = WB + 2 * 3 * kN;                      // [2][3][684]  GRU-2 context-side columns
+  float* WS = WE + 2 * 3 * kD;                      // [4][256]     speller columns
+  float* WPy = WS + 4 * kN;                         // [2][256]     logit pair: Wy
+  float* WPc = WPy + 2 * kMw;                       // [2][684]                 Wc
+  float* WPh = WPc + 2 * kD;                        // [2][256]                 Wh
+  float* X = WPh + 2 * kN;                          // [kMaxB][684] staging of the phase input vectors
+  float* own = X + kMaxB * kD;                      // [2][kMaxB][8]: pre_h, g2r, g2z, ph2   (per owned unit)
+  float* sal = own + 2 * kMaxB * 8;                 // [kPadMax] zero-bordered alpha_past image (phase C) / alpha row (phase D)
+  float* red = sal + kPadMax;                       // [64]
+  float* part = red + 64;                           // [16][64]
+  float* LO = part + 16 * 64;                       // [kMaxB][112]
+  int* sy = reinterpret_cast<int*>(LO + kMaxB * 112);   // [kMaxB] current token
+  int* sfin = sy + kMaxB;                           // [kMaxB] finished flag
+  float* WoR = reinterpret_cast<float*>(sfin + kMaxB);  // [112] row `cta` of Wo (the maxout unit this CTA owns)
+
+  // ---- ownership
+  const int nu = (cta < kN) ? 1 + ((cta + nC) < kN ? 1 : 0) : 0;       // hidden units cta, cta+nC
+  const int unit[2] = {cta, cta + nC};
+  int nsp = 0; for (int c = cta; c < kNA; c += nC) ++nsp;               // speller columns cta + i*nC
+  const bool has_pair = cta < kMw / 2;                                  // logit columns 2*cta, 2*cta+1
+  const int cg = cta % kCG, pg = cta / kCG, npg = nC / kCG;             // coverage: channel group, position group
+  const int npos = Bn * L;
+  // position groups never span two images: gpi groups per image (one alpha_past staging, one im2col pass per <= 64 positions)
+  const int gpi = max(1, npg / Bn), cimg = pg / gpi, cgrp = pg % gpi;
+  const bool c_active = cimg < Bn;
+  const int pos0 = c_active ? cimg * L + (int)((long long)L * cgrp / gpi) : 0;
+  const int pos1 = c_active ? cimg * L + (int)((long long)L * (cgrp + 1) / gpi) : 0;
+  const int cpb = max(1, nC / Bn);                                      // context: CTAs per image
+  const int db = cta / cpb, dchunk = cta % cpb;                         // image / chunk (only if db < Bn)
+  const int c4_per = (kD / 4 + cpb - 1) / cpb;                          // float4 columns per chunk
+
+  // ---- one-off: slice the weights into shared memory
+  for (int i = tid; i < kCovTaps * kCGW; i += kPT) Qs[i] = __ldg(a.qf + (size_t)(i / kCGW) * kNA + cg * kCGW + (i % kCGW));
+  for (int s = 0; s < nu; ++s) {
+    const int j = unit[s];
+    load_col(WA + (s * 6 + 0) * kN, P + o.W_yz_yr, kMw, 2 * kN, j);
+    load_col(WA + (s * 6 + 1) * kN, P + o.W_yz_yr, kMw, 2 * kN, kN + j);
+    load_col(WA + (s * 6 + 2) * kN, P + o.W_yh, kMw, kN, j);
+    load_col(WA + (s * 6 + 3) * kN, P + o.U_hz_hr, kN, 2 * kN, j);
+    load_col(WA + (s * 6 + 4) * kN, P + o.U_hz_hr, kN, 2 * kN, kN + j);
+    load_col(WA + (s * 6 + 5) * kN, P + o.U_rh, kN, kN, j);
+    load_col(WB + (s * 3 + 0) * kN, P + o.U_hz_hr_nl, kN, 2 * kN, j);
+    load_col(WB + (s * 3 + 1) * kN, P + o.U_hz_hr_nl, kN, 2 * kN, kN + j);
+    load_col(WB + (s * 3 + 2) * kN, P + o.U_rh_nl, kN, kN, j);
+    load_col(WE + (s * 3 + 0) * kD, P + o.W_c_z_r, kD, 2 * kN, j);
+    load_col(WE + (s * 3 + 1) * kD, P + o.W_c_z_r, kD, 2 * kN, kN + j);
+    load_col(WE + (s * 3 + 2) * kD, P + o.W_c_h_nl, kD, kN, j);
+  }
+  for (int i = 0; i < nsp; ++i) load_col(WS + i * kN, P + o.W_a, kN, kNA, cta + i * nC);
+  if (has_pair)
+    for (int c = 0; c < 2; ++c) {
+      load_col(WPy + c * kMw, P + o.Wy, kMw, kMw, 2 * cta + c);
+      load_col(WPc + c * kD, P + o.Wc, kD, kMw, 2 * cta + c);
+      load_col(WPh + c * kN, P + o.Wh, kN, kMw, 2 * cta + c);
+    }
+  if (has_pair) for (int j = tid; j < kVocab; j += kPT) WoR[j] = __ldg(P + o.Wo + (size_t)cta * kVocab + j);
+  if (tid < kMaxB) { sy[tid] = -1; sfin[tid] = 0; }
+  // zero the step-0 energy buffer and alpha_past (ownerless: strided over the grid)
+  for (int i = cta * kPT + tid; i < npos; i += nC * kPT) { a.E[i] = 0.f; a.ap[i] = 0.f; }
+  for (int i = cta * kPT + tid; i < Bn * 112; i += nC * kPT) a.LOg[i] = (i % 112) < kVocab ? __ldg(P + o.bo + (i % 112)) : 0.f;
+  unsigned epoch = 0;
+  long long tprev = clock64();
+  long long pacc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto mark = [&](int ph) { const long long now = clock64(); pacc[ph] += now - tprev; tprev = now; };
+  grid_barrier(a.barrier, nC, epoch);
+  mark(7);
+
+  int t = 0;
+  for (; t < a.maxlen; ++t) {
+    const float* hprev = (t == 0) ? a.h0 : a.hbuf + (size_t)((t - 1) & 1) * Bn * kN;
+    float* hnew = a.hbuf + (size_t)(t & 1) * Bn * kN;
+    float* Ecur = a.E + (size_t)(t & 1) * npos;
+    float* Enext = a.E + (size_t)((t + 1) & 1) * npos;
+    float* LOcur = a.LOg + (size_t)(t & 1) * Bn * 112;
+    float* LOnext = a.LOg + (size_t)((t + 1) & 1) * Bn * 112;
+    // ====================================================== A: GRU-1 for the owned units
+    {   // X[b] = [emb(y_b) | h_prev[b]]   (independent 128-bit loads)
+      float4* X4 = reinterpret_cast<float4*>(X);
+#pragma unroll 4
+      for (int i = tid; i < Bn * (2 * kN / 4); i += kPT) {
+        const int b = i / (2 * kN / 4), k4 = i - b * (2 * kN / 4);
+        float4 v = make4(0.f);
+        if (k4 < kMw / 4) { const int y = sy[b]; if (y >= 0) v = ldg4(P + o.embed + (size_t)y * kMw + k4 * 4); }
+        else v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)b * kN) + (k4 - kMw / 4));
+        X4[i] = v;
+      }
+    }
+    __syncthreads();
+    for (int p = warp; p < nu * Bn; p += kPT / 32) {
+      const int s = p / Bn, b = p - s * Bn, j = unit[s];
+      const float* xe = X + b * 2 * kN; const float* xh = xe + kMw;
+      const float* w = WA + s * 6 * kN;
+      const float er = warp_dot(xe, w, kMw, lane), ez = warp_dot(xe, w + kN, kMw, lane), eh = warp_dot(xe, w + 2 * kN, kMw, lane);
+      const float hr = warp_dot(xh, w + 3 * kN, kN, lane), hz = warp_dot(xh, w + 4 * kN, kN, lane), hu = warp_dot(xh, w + 5 * kN, kN, lane);
+      if (lane == 0) {
+        const float r = sigmoidf_(er + hr + __ldg(P + o.b_yz_yr + j)), z = sigmoidf_(ez + hz + __ldg(P + o.b_yz_yr + kN + j));
+        const float prop = tanhf(fmaf(hu, r, eh + __ldg(P + o.b_yh + j)));
+        const float hp = xh[j];
+        const float ph = z * hp + (1.f - z) * prop;
+        own[(s * kMaxB + b) * 8 + 0] = ph;
+        a.pre_h[(size_t)b * kN + j] = ph;
+      }
+    }
+    for (int i = cta * kPT + tid; i < npos; i += nC * kPT) Enext[i] = 0.f;     // energies of the NEXT step
+    for (int i = cta * kPT + tid; i < Bn * 112; i += nC * kPT) LOnext[i] = (i % 112) < kVocab ? __ldg(P + o.bo + (i % 112)) : 0.f;
+    grid_barrier(a.barrier, nC, epoch);
+    mark(0);
+    // ====================================================== B: pre_h-side products
+    stage_cg(X, a.pre_h, Bn * kN / 4);
+    __syncthreads();
+    for (int p = warp; p < (nu * 3 + nsp) * Bn; p += kPT / 32) {
+      const int q = p / Bn, b = p - q * Bn;
+      const float* x = X + b * kN;
+      if (q < nu * 3) {
+        const int s = q / 3, c = q - s * 3, j = unit[s];
+        const float v = warp_dot(x, WB + (s * 3 + c) * kN, kN, lane);
+        if (lane == 0) {
+          const float bias = c == 0 ? __ldg(P + o.b_hz_hr_nl + j) : c == 1 ? __ldg(P + o.b_hz_hr_nl + kN + j) : __ldg(P + o.b_rh_nl + j);
+          own[(s * kMaxB + b) * 8 + 1 + c] = v + bias;
+        }
+      } else {
+        const int i = q - nu * 3, col = cta + i * nC;
+        const float v = warp_dot(x, WS + i * kN, kN, lane);
+        if (lane == 0) a.SP[(size_t)b * kNA + col] = v + __ldg(P + o.W_a_b + col);
+      }
+    }
+    grid_barrier(a.barrier, nC, epoch);
+    mark(1);
+    // ====================================================== C: coverage stencil + tanh + V_a dot (partial over 128 channels)
+    // im2col GEMM [<=64 positions x 121 taps] x [121 x 128]: warp = 8 positions, lane = 4 channels; per tap two
+    // broadcast 128-bit loads of patch values and one 128-bit load of Q' feed 32 FMAs.
+    {
+      const int PW = a.W + 2 * (kCovK / 2), PH = a.H + 2 * (kCovK / 2);
+      float* Apat = X;                                  // [121][64] im2col tile (X is free between phases B and E)
+      const int c0 = cg * kCGW + lane * 4;
+      const float4 ub4 = ldg4(P + o.U_f_b + c0), va4 = ldg4(P + o.V_a + c0);
+      int bcur = -1;
+      for (int pbase = pos0; pbase < pos1;) {
+        const int b = pbase / L;
+        const int pend = min(min(pos1, (b + 1) * L), pbase + 64);
+        __syncthreads();
+        if (b != bcur) {                               // stage alpha_past of image b with a zero border of 5
+          for (int i = tid; i < PH * PW; i += kPT) {
+            const int yy = i / PW - kCovK / 2, xx = i % PW - kCovK / 2;
+            sal[i] = ((unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W) ? __ldcg(a.ap + (size_t)b * L + yy * a.W + xx) : 0.f;
+          }
+          __syncthreads();
+          bcur = b;
+        }
+        for (int i = tid; i < kCovTaps * 64; i += kPT) {       // im2col: Apat[tap][p]
+          const int tap = i >> 6, pp = i & 63, pos = pbase + pp;
+          float v = 0.f;
+          if (pos < pend) { const int l = pos - b * L, y = l / a.W, x = l - y * a.W; v = sal[(y + tap / kCovK) * PW + x + tap % kCovK]; }
+          Apat[i] = v;
+        }
+        __syncthreads();
+        const float4 sp4 = __ldcg(reinterpret_cast<const float4*>(a.SP + (size_t)b * kNA + c0));
+        float acc[8][4];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+        if (pbase + warp * 8 < pend) {
+#pragma unroll 2
+          for (int tap = 0; tap < kCovTaps; ++tap) {
+            const float4 q = *reinterpret_cast<const float4*>(Qs + tap * kCGW + lane * 4);
+            const float4 p0 = *reinterpret_cast<const float4*>(Apat + tap * 64 + warp * 8);
+            const float4 p1 = *reinterpret_cast<const float4*>(Apat + tap * 64 + warp * 8 + 4);
+            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              acc[i][0] = fmaf(pv[i], q.x, acc[i][0]); acc[i][1] = fmaf(pv[i], q.y, acc[i][1]);
+              acc[i][2] = fmaf(pv[i], q.z, acc[i][2]); acc[i][3] = fmaf(pv[i], q.w, acc[i][3]);
+            }
+          }
+          float4 w4[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {                // all watch rows in flight before any of them is used
+            const int pos = min(pbase + warp * 8 + i, pend - 1);
+            w4[i] = ldg4(a.watch + (size_t)pos * kNA + c0);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int pos = pbase + warp * 8 + i;
+            float e = va4.x * tanhf(acc[i][0] + ub4.x + w4[i].x + sp4.x) + va4.y * tanhf(acc[i][1] + ub4.y + w4[i].y + sp4.y) +
+                      va4.z * tanhf(acc[i][2] + ub4.z + w4[i].z + sp4.z) + va4.w * tanhf(acc[i][3] + ub4.w + w4[i].w + sp4.w);
+            e = warp_sum(e);
+            if (lane == 0 && pos < pend) atomicAdd(Ecur + pos, e);
+          }
+        }
+        pbase = pend;
+      }
+      __syncthreads();
+    }
+    grid_barrier(a.barrier, nC, epoch);
+    mark(2);
+    // ====================================================== D: softmax over L, alpha_past update, context chunk
+    if (db < Bn) {
+      const float vab = __ldg(P + o.V_a_b);
+      float mx = -INFINITY;
+      for (int l = tid; l < L; l += kPT) { const float e = __ldcg(Ecur + (size_t)db * L + l) + vab; sal[l] = e; mx = fmaxf(mx, e); }
+      mx = block_max(mx, red);
+      float sum = 0.f;
+      for (int l = tid; l < L; l += kPT) { const float u = expf(sal[l] - mx); sal[l] = u; sum += u; }
+      sum = block_sum(sum, red);
+      const float inv = 1.f / sum;
+      for (int l = tid; l < L; l += kPT) {
+        const float al = sal[l] * inv;
+        sal[l] = al;
+        if (dchunk == 0) a.ap[(size_t)db * L + l] += al;       // next read is phase C of step t+1 (4 barriers away)
+      }
+      __syncthreads();
+      const int cq = tid & 15, lg = tid >> 4;                  // 16 float4 columns x 16 position groups
+      for (int q0 = 0; q0 < c4_per; q0 += 16) {
+        const int c4 = dchunk * c4_per + q0 + cq;
+        float4 acc = make4(0.f);
+        if (q0 + cq < c4_per && c4 < kD / 4) {
+          const float* base = a.ann + (size_t)db * L * kD + c4 * 4;
+          for (int l = lg; l < L; l += 16) {
+            const float4 v = ldg4(base + (size_t)l * kD);
+            const float al = sal[l];
+            acc.x = fmaf(al, v.x, acc.x); acc.y = fmaf(al, v.y, acc.y); acc.z = fmaf(al, v.z, acc.z); acc.w = fmaf(al, v.w, acc.w);
+          }
+        }
+        __syncthreads();
+        *reinterpret_cast<float4*>(&part[lg * 64 + cq * 4]) = acc;
+        __syncthreads();
+        if (tid < 64) {
+          const int cc = (dchunk * c4_per + q0) * 4 + tid;
+          if (q0 * 4 + tid < c4_per * 4 && cc < kD) {
+            float s = 0.f;
+#pragma unroll
+            for (int g = 0; g < 16; ++g) s += part[g * 64 + tid];
+            a.ctx[(size_t)db * kD + cc] = s;
+          }
+        }
+      }
+    }
+    grid_barrier(a.barrier, nC, epoch);
+    mark(3);
+    // ====================================================== E: GRU-2 for the owned units + emb/ctx part of the logit pair
+    stage_cg(X, a.ctx, Bn * kD / 4);
+    __syncthreads();
+    for (int p = warp; p < (nu + (has_pair ? 2 : 0)) * Bn; p += kPT / 32) {
+      const int q = p / Bn, b = p - q * Bn;
+      const float* xc = X + b * kD;
+      if (q < nu) {
+        const int s = q, j = unit[s];
+        const float cr = warp_dot(xc, WE + (s * 3 + 0) * kD, kD, lane), cz = warp_dot(xc, WE + (s * 3 + 1) * kD, kD, lane);
+        const float ch = warp_dot(xc, WE + (s * 3 + 2) * kD, kD, lane);
+        if (lane == 0) {
+          const float* ow = own + (s * kMaxB + b) * 8;
+          const float r = sigmoidf_(ow[1] + cr), z = sigmoidf_(ow[2] + cz);
+          const float prop = tanhf(fmaf(ow[3], r, ch));
+          hnew[(size_t)b * kN + j] = z * ow[0] + (1.f - z) * prop;
+        }
+      } else {
+        const int c = q - nu, n = 2 * cta + c;
+        float v = warp_dot(xc, WPc + c * kD, kD, lane);
+        // embedding part: gather directly (256 floats)
+        const int y = sy[b];
+        float e = 0.f;
+        if (y >= 0) for (int k = lane; k < kMw; k += 32) e = fmaf(__ldg(P + o.embed + (size_t)y * kMw + k), WPy[c * kMw + k], e);
+        e = warp_sum(e);
+        if (lane == 0) own[(c * kMaxB + b) * 8 + 4] = v + e + __ldg(P + o.by + n) + __ldg(P + o.bc + n) + __ldg(P + o.bh + n);
+      }
+    }
+    grid_barrier(a.barrier, nC, epoch);
+    mark(4);
+    // ====================================================== F: h part of the logit pair, maxout
+    if (has_pair) {
+      stage_cg(X, hnew, Bn * kN / 4);
+      __syncthreads();
+      for (int p = warp; p < 2 * Bn; p += kPT / 32) {
+        const int c = p / Bn, b = p - c * Bn;
+        const float v = warp_dot(X + b * kN, WPh + c * kN, kN, lane);
+        if (lane == 0) own[(c * kMaxB + b) * 8 + 5] = v + own[(c * kMaxB + b) * 8 + 4];
+      }
+      __syncthreads();
+      // maxout of the owned pair, then its rank-1 contribution MO[b,cta] * Wo[cta,:] to the output logits (RED.ADD)
+      for (int i = tid; i < Bn * kVocab; i += kPT) {
+        const int b = i / kVocab, j = i - b * kVocab;
+        const float m = fmaxf(own[(0 * kMaxB + b) * 8 + 5], own[(1 * kMaxB + b) * 8 + 5]);
+        atomicAdd(LOcur + b * 112 + j, m * WoR[j]);
+      }
+    }
+    grid_barrier(a.barrier, nC, epoch);
+    mark(5);
+    // ====================================================== G: argmax + stop rule (redundant in every CTA; logits were accumulated in F)
+    stage_cg(LO, LOcur, Bn * 112 / 4);
+    __syncthreads();
+    for (int b = warp; b < Bn; b += kPT / 32) {
+      float mx = -INFINITY; int am = 0x7fffffff;
+      for (int j = lane; j < kVocab; j += 32) { const float v = LO[b * 112 + j]; if (v > mx) { mx = v; am = j; } }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) {
+        const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+        const int oa = __shfl_xor_sync(0xffffffffu, am, off);
+        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
+      }
+      if (lane == 0) {
+        if (!sfin[b]) {
+          if (cta == 0) a.tokens[(size_t)b * a.maxlen + t] = am;
+          if ((am == 0 && !a.ignore_eol) || t == a.maxlen - 1) { sfin[b] = 1; if (cta == 0) a.lengths[b] = t + 1; }
+        }
+        sy[b] = am;
+      }
+    }
+    __syncthreads();
+    mark(6);
+    int alive = 0;
+    for (int b = 0; b < Bn; ++b) alive += sfin[b] ? 0 : 1;
+    if (alive == 0) { ++t; break; }
+  }
+  if (cta == 0 && tid == 0 && a.steps_run != nullptr) *a.steps_run = t;
+  if (cta == 0 && tid == 0 && a.prof != nullptr)
+    for (int i = 0; i < 8; ++i) a.prof[i] = pacc[i];
+}
+
+}  // namespace
+
+size_t greedy_persist_ws_floats(int Bn, int L) {
+  size_t o = 0;
+  auto take = [&](size_t n) { o += (n + 3) & ~(size_t)3; };
+  take((size_t)2 * Bn * kN); take((size_t)Bn * kN); take((size_t)Bn * kNA); take((size_t)2 * Bn * L); take((size_t)Bn * L);
+  take((size_t)Bn * kD); take((size_t)Bn * (kMw / 2)); take(8 * 160 + 24); take((size_t)2 * Bn * 112);
+  take((size_t)Bn * L * kNA); take((size_t)kCovTaps * kNA); take((size_t)Bn * kN); take((size_t)Bn * kD); take(4);
+  return o;
+}
+
+// Greedy decode of Bn <= 16 images in one persistent cooperative kernel (plus the hoisted precompute).
+// steps_run_dev: optional device int.  Never synchronises the host.
+int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
+                             int* tokens, int* lengths, float* wsp, int* steps_run_dev) {
+  const int L = h * w;
+  WAP_REQUIRE(Bn >= 1 && Bn <= kMaxB && L <= kMaxL && (h + 10) * (w + 10) <= kPadMax,
+              "greedy_decode_persistent: Bn=%d (<=%d), L=%d (<=%d), padded grid %d (<=%d)", Bn, kMaxB, L, kMaxL, (h + 10) * (w + 10), kPadMax);
+  static int num_ctas = 0;
+  const size_t smem = sizeof(float) * kSmemFloats;
+  if (num_ctas == 0) {
+    int dev = 0, sms = 0, coop = 0, per_sm = 0;
+    WAP_CHECK(cudaGetDevice(&dev));
+    WAP_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    WAP_CHECK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    WAP_REQUIRE(coop != 0, "device does not support cooperative launch");
+    WAP_CHECK(cudaFuncSetAttribute(greedy_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    WAP_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, greedy_persistent_kernel, kPT, smem));
+    WAP_REQUIRE(per_sm >= 1, "persistent decoder does not fit on an SM (smem %zu B)", smem);
+    num_ctas = std::min(160, (sms / kCG) * kCG);
+    WAP_REQUIRE(num_ctas >= kMinCtas, "persistent decoder needs >= %d SMs (have %d)", kMinCtas, sms);
+  }
+  size_t o = 0;
+  auto take = [&](size_t n) { float* p = wsp + o; o += (n + 3) & ~(size_t)3; return p; };
+  PersistArgs a;
+  a.params = params; a.ann = ann; a.Bn = Bn; a.H = h; a.W = w; a.L = L; a.maxlen = maxlen; a.ignore_eol = ignore_eol;
+  a.hbuf = take((size_t)2 * Bn * kN); a.pre_h = take((size_t)Bn * kN); a.SP = take((size_t)Bn * kNA);
+  a.E = take((size_t)2 * Bn * L); a.ap = take((size_t)Bn * L); a.ctx = take((size_t)Bn * kD); a.MO = take((size_t)Bn * (kMw / 2));
+  a.barrier = reinterpret_cast<unsigned*>(take(8 * 160 + 24));   // barrier counter (+ padding), then the profile words
+  a.LOg = take((size_t)2 * Bn * 112);
+  float* watch = take((size_t)Bn * L * kNA); float* qf = take((size_t)kCovTaps * kNA); float* h0 = take((size_t)Bn * kN);
+  float* mean = take((size_t)Bn * kD);
+  a.watch = watch; a.qf = qf; a.h0 = h0; a.tokens = tokens; a.lengths = lengths; a.steps_run = steps_run_dev;
+  a.prof = reinterpret_cast<long long*>(a.barrier + 8 * 160);   // 8 x int64 after the barrier slots
+  const ParamLayout& P = layout();
+  DecOff& d = a.o;
+  d.U_f_b = (int)P.U_f_b; d.W_a = (int)P.W_a; d.W_a_b = (int)P.W_a_b; d.V_a = (int)P.V_a; d.V_a_b = (int)P.V_a_b;
+  d.W_yz_yr = (int)P.W_yz_yr; d.b_yz_yr = (int)P.b_yz_yr; d.U_hz_hr = (int)P.U_hz_hr; d.W_yh = (int)P.W_yh; d.b_yh = (int)P.b_yh;
+  d.U_rh = (int)P.U_rh; d.U_hz_hr_nl = (int)P.U_hz_hr_nl; d.b_hz_hr_nl = (int)P.b_hz_hr_nl; d.W_c_z_r = (int)P.W_c_z_r;
+  d.U_rh_nl = (int)P.U_rh_nl; d.b_rh_nl = (int)P.b_rh_nl; d.W_c_h_nl = (int)P.W_c_h_nl; d.embed = (int)P.embed; d.Wc = (int)P.Wc;
+  d.bc = (int)P.bc; d.Wh = (int)P.Wh; d.bh = (int)P.bh; d.Wy = (int)P.Wy; d.by = (int)P.by; d.Wo = (int)P.Wo; d.bo = (int)P.bo;
+  WAP_TRY(attn_precompute(st, params, ann, nullptr, Bn, h, w, watch, h0, qf, mean));     // hidden_state_0 is unmasked (S:590)
+  WAP_CHECK(cudaMemsetAsync(a.barrier, 0, (8 * 160 + 24) * sizeof(unsigned), st));
+  WAP_CHECK(cudaMemsetAsync(lengths, 0, sizeof(int) * Bn, st));
+  void* args[] = {(void*)&a};
+  WAP_CHECK(cudaLaunchCooperativeKernel((const void*)greedy_persistent_kernel, dim3(num_ctas), dim3(kPT), args, smem, st));
+  ++g_launches;
+  return 0;
+}
+
+}  // namespace wap

@@ -227,11 +227,25 @@ class WAPEngine:
                    "wap_decoder_step")
         return probs, word, h_new, ap_new
 
-    def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8):
-        """Greedy decode of every image in the batch; returns (tokens [B,maxlen] int32, lengths [B] int32, steps)."""
+    def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8, persistent: Optional[bool] = None,
+                      ignore_eol: bool = False):
+        """Greedy decode of every image in the batch; returns (tokens [B,maxlen] int32, lengths [B] int32, steps).
+        persistent (default: whenever the shape allows): one cooperative kernel per <= 16 images runs the whole
+        token loop on the device; otherwise the step-by-step kernels with `check_every` host syncs."""
         B, h, w, _ = annotation.shape
         tokens = torch.zeros((B, maxlen), dtype=torch.int32, device=self.device)
         lengths = torch.zeros((B,), dtype=torch.int32, device=self.device)
+        if persistent is None:
+            persistent = h * w <= 2048 and (h + 10) * (w + 10) <= 6144
+        if persistent:
+            steps_dev = torch.zeros((1,), dtype=torch.int32, device=self.device)
+            for b0 in range(0, B, 16):
+                nb = min(16, B - b0)
+                ws = self._buf(("greedy_p", nb, h, w), self.L.wap_greedy_persistent_workspace_floats(nb, h, w))
+                _lib.check(self.L.wap_greedy_decode_persistent(_stream(), _p(self.P.flat), _p(annotation[b0:b0 + nb]), nb, h, w, maxlen,
+                                                               int(ignore_eol), _p(tokens[b0:b0 + nb]), _p(lengths[b0:b0 + nb]), _p(ws), _p(steps_dev)),
+                           "wap_greedy_decode_persistent")
+            return tokens, lengths, steps_dev
         ws = self._buf(("greedy", B, h, w), self.L.wap_greedy_workspace_floats(B, h, w))
         steps = C.c_int(0)
         _lib.check(self.L.wap_greedy_decode(_stream(), _p(self.P.flat), _p(annotation), B, h, w, maxlen, check_every, _p(tokens),
