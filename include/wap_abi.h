@@ -140,12 +140,20 @@ int wap_get_conv_precision(void);
 int wap_debug_set_tc_mask(int mask);
 /* debugging aid: during wap_encoder_backward copy [d a1 | d y2 (ld 32) | d y1] of the dense level whose 1x1 conv index is `layer` into buf */
 int wap_debug_capture(int layer, float* buf);
+/* debugging aid for the tensor-core wgrad kernel: dump stage-0 shared memory of CTA 0 to buf; xor into the instruction descriptor */
+int wap_debug_wgrad(float* buf, int idesc_xor);
 int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
                 int accumulate, double* stats);
 /* 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) with Wt[Nrows, 9*C] (K-major, row n = output channel,
  * k = tap*C + ci; rows >= N zero) -> D[B*H*W, N] */
 int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
                    float* D, int ldd, double* stats);
+/* weight gradients on tensor cores (MN-major operands, split over pixels, RED.ADD into dW):
+ * 1x1: dW[C,N] (ldo) += X[Mpix,C](ldx)^T dY[Mpix,N](ldy), N <= 96;
+ * 3x3: dW[9*C,N] += im2col3x3(X[B,H,W,C])^T dY[B,H,W,32-padded], N <= 32, ldy = 32.  x3 != 0: 3xTF32. */
+int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int x3);
+int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo,
+                     int x3);
 /* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);
 /* byte offsets (in floats) of selected encoder-workspace regions, for tests: what = 0 stem_raw,

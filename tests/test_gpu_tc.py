@@ -194,3 +194,46 @@ def test_tf32x3_full_gradients_and_greedy(report, tf32_engine_factory):
     got = toks[0, : int(lens[0])].cpu().tolist()
     report.add("tf32x3", "greedy_identical", 0.0 if got == ref_toks else 1.0, 0.0, extra=dict(got=got, ref=ref_toks))
     assert got == ref_toks
+
+
+# --------------------------------------------------------------------------------------
+# tensor-core weight gradients (MN-major operands)
+@pytest.mark.parametrize("x3", [0, 1])
+@pytest.mark.parametrize("Mpix,C,N,ldx", [(64, 48, 96, 432), (1000, 432, 96, 432), (4100, 660, 96, 684), (30, 516, 96, 684), (32768, 120, 96, 432)])
+def test_tc_wgrad_1x1(report, Mpix, C, N, ldx, x3):
+    lib, L = _L()
+    g = torch.Generator().manual_seed(Mpix + C)
+    X = torch.randn(Mpix, ldx, generator=g).cuda(); dY = torch.randn(Mpix, N, generator=g).cuda()
+    dW0 = torch.randn(C, N, generator=g).cuda(); dW = dW0.clone()
+    lib.check(L.wap_tc_wgrad_1x1(_st(), p(X), ldx, p(dY), N, Mpix, C, N, p(dW), N, x3), "wap_tc_wgrad_1x1")
+    torch.cuda.synchronize()
+    Xc = X[:, :C]
+    if x3:
+        ref = dW0.double() + Xc.double().t() @ dY.double(); tol = 4e-6
+    else:
+        ref = dW0.double() + _trunc_tf32(Xc).double().t() @ _trunc_tf32(dY).double(); tol = 3e-5
+    e = rel_err(dW.cpu().numpy(), ref.cpu().numpy())
+    report.add("tc", f"tc_wgrad1x1_M{Mpix}_C{C}_x3{x3}", e, tol)
+    assert e <= tol, e
+
+
+@pytest.mark.parametrize("x3", [0, 1])
+@pytest.mark.parametrize("B,H,W", [(2, 8, 16), (1, 5, 9), (2, 4, 32), (1, 32, 128), (3, 7, 20)])
+def test_tc_wgrad_3x3(report, B, H, W, x3):
+    lib, L = _L()
+    C, N = 96, 24
+    g = torch.Generator().manual_seed(B * 10 + H)
+    X = torch.randn(B, H, W, C, generator=g).cuda()
+    dYp = torch.zeros(B, H, W, 32, device="cuda"); dYp[..., :N] = torch.randn(B, H, W, N, generator=g).cuda()
+    dW0 = torch.randn(9 * C, N, generator=g).cuda(); dW = dW0.clone()
+    lib.check(L.wap_tc_wgrad_3x3(_st(), p(X), C, p(dYp), 32, B, H, W, C, N, p(dW), N, x3), "wap_tc_wgrad_3x3")
+    torch.cuda.synchronize()
+    Xr = X if x3 else _trunc_tf32(X); Yr = dYp[..., :N] if x3 else _trunc_tf32(dYp[..., :N].contiguous())
+    w = torch.zeros(N, C, 3, 3, dtype=torch.float64, device="cuda", requires_grad=True)
+    y = torch.nn.functional.conv2d(Xr.double().permute(0, 3, 1, 2), w, padding=1)
+    (y * Yr.double().permute(0, 3, 1, 2)).sum().backward()
+    ref = dW0.double() + w.grad.permute(2, 3, 1, 0).reshape(9 * C, N)
+    tol = 4e-6 if x3 else 3e-5
+    e = rel_err(dW.cpu().numpy(), ref.cpu().numpy())
+    report.add("tc", f"tc_wgrad3x3_B{B}_{H}x{W}_x3{x3}", e, tol)
+    assert e <= tol, e

@@ -54,8 +54,11 @@ SIGNATURES = {
     "wap_get_conv_precision": (_i, []),
     "wap_debug_set_tc_mask": (_i, [_i]),
     "wap_debug_capture": (_i, [_i, _vp]),
+    "wap_debug_wgrad": (_i, [_vp, _i]),
     "wap_tc_gemm": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
     "wap_tc_conv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
+    "wap_tc_wgrad_1x1": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i]),
+    "wap_tc_wgrad_3x3": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i]),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),
     "wap_encoder_workspace_offset": (_i64, [_i, _i, _i, _i, _i, _i]),
 }

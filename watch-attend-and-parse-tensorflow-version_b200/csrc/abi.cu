@@ -72,6 +72,7 @@ int dropout_mask(cudaStream_t st, uint32_t seed, uint32_t site, size_t n, float*
 
 }  // namespace wap
 
+namespace wap { float* g_wg_dbg = nullptr; int g_wg_xor = 0; }
 using namespace wap;
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
 
@@ -224,6 +225,13 @@ int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, i
                    float* D, int ldd, double* stats) {
   TcEpi e{D, ldd, 0, stats};
   return tc_conv3x3(ST(stream), x, ldx, B, H, W, C, Wt, Wt_lo, Nrows, N, e, kProfOtherGemm);
+}
+int wap_debug_wgrad(float* buf, int idesc_xor) { g_wg_dbg = buf; g_wg_xor = idesc_xor; return 0; }
+int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int x3) {
+  return tc_wgrad_1x1(ST(stream), X, ldx, dY, ldy, Mpix, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
+}
+int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
+  return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
   return dropout_mask(ST(stream), seed, site, (size_t)n, mask);

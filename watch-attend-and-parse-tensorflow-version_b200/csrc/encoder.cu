@@ -584,7 +584,10 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
       const ConvLayer& ct = L.conv[k];
       const int C = ld;
       WAP_TRY(run_bn_bwd(st, 2, bwd_args(k, wsp + ws.ytr[b], h, w, G[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], dytr, ct.cout, true)));
-      {   // wgrad  dW[C, C/2] += buf^T * dy
+      if (tc && (g_tc_debug_mask & 64)) {   // wgrad  dW[C, C/2] += buf^T * dy   (column chunks of <= 96)
+        for (int n0 = 0; n0 < ct.cout; n0 += 96)
+          WAP_TRY(tc_wgrad_1x1(st, buf[b], ld, dytr + n0, ct.cout, M, C, std::min(96, ct.cout - n0), grads + ct.w + n0, ct.cout, x3, kProfTransBwd));
+      } else {
         AColMajor A{buf[b], ld, C, M};
         BRowMajor Bd{dytr, ct.cout, M, ct.cout};
         EpiAtomic e{grads + ct.w, ct.cout};
@@ -609,7 +612,9 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
       const float* y1 = wsp + ws.y1[k1]; const float* a1 = wsp + ws.a1[k1]; const float* y2 = wsp + ws.y2[k3];
       // BN/ReLU/dropout backward of the 3x3 output
       WAP_TRY(run_bn_bwd(st, 0, bwd_args(k3, y2, h, w, G[b] + C, h, w, ld, dy2, kDy2Ld, true)));
-      {   // wgrad 3x3: dW[864,24] += im2col(a1)^T * dy2
+      if (tc && (g_tc_debug_mask & 64)) {   // wgrad 3x3: dW[864,24] += im2col(a1)^T * dy2
+        WAP_TRY(tc_wgrad_3x3(st, a1, kBottle, dy2, kDy2Ld, B, h, w, kBottle, kGrowth, grads + c3.w, kGrowth, x3, kProfConv3Wgrad));
+      } else {
         AIm2col3T A{a1, kBottle, B, h, w, kBottle};
         BRowMajor Bd{dy2, kDy2Ld, M, kGrowth};
         EpiAtomic e{grads + c3.w, kGrowth};
@@ -631,7 +636,9 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
       WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, kBottle, true)));
       if (k1 == g_dbg_layer && g_dbg_buf != nullptr)     // [.. | dy1 (M*96)]
         WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * (kBottle + kDy2Ld), dy1, sizeof(float) * (size_t)M * kBottle, cudaMemcpyDeviceToDevice, st));
-      {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
+      if (tc && (g_tc_debug_mask & 64)) {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
+        WAP_TRY(tc_wgrad_1x1(st, buf[b], ld, dy1, kBottle, M, C, kBottle, grads + c1.w, kBottle, x3, kProfConv1Wgrad));
+      } else {
         AColMajor A{buf[b], ld, C, M};
         BRowMajor Bd{dy1, kBottle, M, kBottle};
         EpiAtomic e{grads + c1.w, kBottle};

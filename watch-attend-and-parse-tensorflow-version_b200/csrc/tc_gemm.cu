@@ -3,6 +3,8 @@
 
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+
 namespace wap {
 
 constexpr int kTcBM = 128;          // UMMA M (cta_group::1)
@@ -326,6 +328,203 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
+
+// =====================================================================================
+// Weight-gradient GEMM on tensor cores:  dW[M, N] += sum over pixels p of  X[p, m] * dY[p, n]
+// Both operands have the reduction index (pixels) as their SLOW memory dimension, i.e. they are
+// "MN-major" for the tensor core.  Canonical MN-major SWIZZLE_128B layout (tf32): one 1024-byte atom =
+// 8 pixel rows x 32 channels (128 B); atoms of consecutive 8-row groups are SBO = 1024 B apart, the next
+// block of 32 channels is LBO apart.  A stage holds kWgRows = 32 pixel rows of NBA + NBB channel blocks,
+// each block written by one TMA box {32 channels, 32 pixels}.  For the 3x3 conv the pixel rows of a stage
+// are a TW x TH rectangle fetched as a 4-D box, shifted by the tap of the channel block (zero-filled halo).
+// 3xTF32: BOTH operands are activations, so the splitter warps produce hi/lo tiles of both.
+// The K (pixel) range is split across grid.z; partial tiles are accumulated with RED.ADD.F32.
+// =====================================================================================
+constexpr int kWgRows = 32;                       // pixel rows per stage
+constexpr int kWgBlk = kWgRows * 128;             // bytes of one 32-channel block of a stage (4096)
+
+struct WgShape {
+  int M, N;                 // output rows (channels of X / taps*channels) and columns
+  int nstages;              // total pixel stages (all of K)
+  int stages_per_split;
+  int ldo;                  // output row stride
+  // im2col mode
+  int C, H, W, TW, TH, tiles_x, tiles_y;
+  float* dbg; int dbg_idesc_xor;   // debugging aids
+};
+
+template <int NBB, bool X3> struct WgSmem {
+  static constexpr int kNBA = 4;
+  static constexpr int kStages = 3;
+  static constexpr int kABytes = kNBA * kWgBlk;                    // 16384
+  static constexpr int kBBytes = NBB * kWgBlk;
+  static constexpr int kStage = (X3 ? 2 : 1) * (kABytes + kBBytes);
+  static constexpr int kBarOff = kStages * kStage;
+  static constexpr int kTotal = kBarOff + 128 + 1024;
+};
+
+// MN-major 32-bit operands must use the "128-byte swizzle with 32-byte atoms" layout (UMMA layout type 1,
+// TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): an atom is 4 K-rows x 128 B (32 channels); 32-byte chunk c of
+// row r is stored at chunk c ^ (r & 3).  SBO = next 4-row group (512 B), LBO = next 32-channel block.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;             // leading byte offset: next 32-channel block
+  d |= (uint64_t)(512 >> 4) << 32;                   // stride byte offset: next 4-row (K) group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                            // SWIZZLE_128B_BASE32B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int n) {   // both operands MN-major
+  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+
+template <int NBB, bool IM2COL, bool X3>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, float* __restrict__ out, const WgShape sh) {
+  using S = WgSmem<NBB, X3>;
+  constexpr int BN = NBB * 32;
+  constexpr uint32_t kAcc2 = BN <= 32 ? 32 : 128;
+  constexpr uint32_t kTmemCols = (X3 ? 2 : 1) * (BN <= 32 ? 32 : 128);
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty_bar = full_bar + S::kStages;
+  uint64_t* split_bar = empty_bar + S::kStages;
+  uint64_t* tmem_full = split_bar + S::kStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTcBM;
+  const int s_beg = blockIdx.z * sh.stages_per_split;
+  const int s_end = min(sh.nstages, s_beg + sh.stages_per_split);
+  const int ns = s_end - s_beg;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmY);
+    for (int s = 0; s < S::kStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); mbar_init(&split_bar[s], 4); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (ns <= 0) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem_base, kTmemCols); return; }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < ns; ++i) {
+        const int st = s_beg + i, s = i % S::kStages;
+        const uint32_t ph = (i / S::kStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1);
+        uint8_t* sa = smem + s * S::kStage;
+        uint8_t* sb = sa + (X3 ? 2 : 1) * S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kABytes + S::kBBytes);
+        if (IM2COL) {
+          int t = st;
+          const int tx = t % sh.tiles_x; t /= sh.tiles_x;
+          const int ty = t % sh.tiles_y; const int bimg = t / sh.tiles_y;
+          const int x0 = tx * sh.TW, y0 = ty * sh.TH;
+          const int cpb = sh.C / 32;                          // channel blocks per tap
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) {
+            const int gb = m0 / 32 + blk, tap = gb / cpb, cb = gb - tap * cpb;
+            if (tap < 9) tma_load_4d(sa + blk * kWgBlk, &tmX, &full_bar[s], cb * 32, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
+            else tma_load_4d(sa + blk * kWgBlk, &tmX, &full_bar[s], sh.C, x0, y0, bimg);       // fully out of bounds: zeros
+          }
+#pragma unroll
+          for (int blk = 0; blk < NBB; ++blk) tma_load_4d(sb + blk * kWgBlk, &tmY, &full_bar[s], blk * 32, x0, y0, bimg);
+        } else {
+#pragma unroll
+          for (int blk = 0; blk < 4; ++blk) tma_load_2d(sa + blk * kWgBlk, &tmX, &full_bar[s], m0 + blk * 32, st * kWgRows);
+#pragma unroll
+          for (int blk = 0; blk < NBB; ++blk) tma_load_2d(sb + blk * kWgBlk, &tmY, &full_bar[s], blk * 32, st * kWgRows);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_mn(BN) ^ (uint32_t)sh.dbg_idesc_xor;
+      for (int i = 0; i < ns; ++i) {
+        const int s = i % S::kStages;
+        const uint32_t ph = (i / S::kStages) & 1;
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStage);
+        const uint32_t sb = sa + (X3 ? 2 : 1) * S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kWgRows / 8; ++k) {
+          const uint64_t ad = make_mnmajor_sw128_desc(sa + k * 1024, kWgBlk);
+          const uint64_t bd = make_mnmajor_sw128_desc(sb + k * 1024, kWgBlk);
+          umma_tf32(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+          if (X3) {
+            const uint64_t ald = make_mnmajor_sw128_desc(sa + S::kABytes + k * 1024, kWgBlk);
+            const uint64_t bld = make_mnmajor_sw128_desc(sb + S::kBBytes + k * 1024, kWgBlk);
+            umma_tf32(tmem_base + kAcc2, ald, bd, idesc, (i | k) != 0 ? 1u : 0u);
+            umma_tf32(tmem_base + kAcc2, ad, bld, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    if (X3) {      // split BOTH operand tiles: hi = rna_tf32(v) in place, lo = v - hi
+      const int t = threadIdx.x - 64;
+      for (int i = 0; i < ns; ++i) {
+        const int s = i % S::kStages;
+        const uint32_t ph = (i / S::kStages) & 1;
+        mbar_wait(&full_bar[s], ph);
+        uint8_t* base = smem + s * S::kStage;
+        float4* ahi = reinterpret_cast<float4*>(base);
+        float4* alo = reinterpret_cast<float4*>(base + S::kABytes);
+        float4* bhi = reinterpret_cast<float4*>(base + 2 * S::kABytes);
+        float4* blo = reinterpret_cast<float4*>(base + 2 * S::kABytes + S::kBBytes);
+        auto split4 = [](float4* hi, float4* lo, int idx) {
+          const float4 v = hi[idx];
+          float4 h, l;
+          h.x = tf32_rna_dev(v.x); h.y = tf32_rna_dev(v.y); h.z = tf32_rna_dev(v.z); h.w = tf32_rna_dev(v.w);
+          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
+          hi[idx] = h; lo[idx] = l;
+        };
+#pragma unroll
+        for (int j = 0; j < S::kABytes / 16 / 128; ++j) split4(ahi, alo, t + j * 128);
+#pragma unroll
+        for (int j = 0; j < S::kBBytes / 16 / 128; ++j) split4(bhi, blo, t + j * 128);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&split_bar[s]);
+      }
+    }
+    const int q = warp & 3, r = q * 32 + lane, m = m0 + r;
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    if (sh.dbg != nullptr && blockIdx.x == 0 && blockIdx.z == 0)
+      for (int i = threadIdx.x - 64; i < S::kStage / 4; i += 128) sh.dbg[i] = reinterpret_cast<const float*>(smem)[i];
+#pragma unroll 1
+    for (int c = 0; c < BN; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (X3) {
+        float v2[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2 + (uint32_t)c, v2);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] += v2[i];
+      }
+      if (m < sh.M) {
+        float* dst = out + (size_t)m * sh.ldo + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < sh.N) atomicAdd(dst + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
 // ------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static bool g_encode_tried = false;
@@ -342,14 +541,15 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 bool tc_available() { return get_encode() != nullptr; }
 
-static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   WAP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bdim, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WAP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank=%d dims=%llu,%llu stride0=%llu box=%u,%u", (int)r, rank,
               (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)strides_bytes[0], box[0], box[1]);
@@ -426,6 +626,77 @@ int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, in
   if (BN == 32) return launch_tc<32, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   if (BN == 96) return launch_tc<96, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   return launch_tc<128, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+}
+
+
+extern float* g_wg_dbg; extern int g_wg_xor;
+template <int NBB, bool IM2COL>
+static int launch_wg(cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& ty, float* out, const WgShape& sh, dim3 grid, bool x3,
+                     int prof_cls, double flops) {
+  static bool configured = false;
+  if (!configured) {
+    WAP_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<NBB, IM2COL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<NBB, true>::kTotal));
+    WAP_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<NBB, IM2COL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WgSmem<NBB, false>::kTotal));
+    configured = true;
+  }
+  WgShape sh2 = sh; sh2.dbg = g_wg_dbg; sh2.dbg_idesc_xor = g_wg_xor;
+  prof_begin(st, prof_cls, flops);
+  if (x3) tc_wgrad_kernel<NBB, IM2COL, true><<<grid, kTcThreads, WgSmem<NBB, true>::kTotal, st>>>(tx, ty, out, sh2);
+  else tc_wgrad_kernel<NBB, IM2COL, false><<<grid, kTcThreads, WgSmem<NBB, false>::kTotal, st>>>(tx, ty, out, sh2);
+  prof_end(st, prof_cls);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+static int pick_splits(int nstages, int mtiles) {
+  int splits = std::max(1, std::min(nstages / 6, 148 / std::max(mtiles, 1)));
+  return std::max(1, splits);
+}
+
+// dW[C, N] (ldo) += X[Mpix, C](ldx)^T * dY[Mpix, N](ldy)      N in {96 (NBB=3)}: 1x1 conv weight gradient
+int tc_wgrad_1x1(cudaStream_t st, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, bool x3, int prof_cls) {
+  WAP_REQUIRE(N <= 96 && (ldx & 3) == 0 && (ldy & 3) == 0, "tc_wgrad_1x1: N=%d must be <= 96", N);
+  CUtensorMap tx, ty;
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)Mpix}; const uint64_t str[1] = {(uint64_t)ldx * 4}; const uint32_t box[2] = {32, kWgRows};
+    WAP_TRY(make_map(&tx, X, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)Mpix}; const uint64_t str[1] = {(uint64_t)ldy * 4}; const uint32_t box[2] = {32, kWgRows};
+    WAP_TRY(make_map(&ty, dY, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  }
+  WgShape sh{}; sh.M = C; sh.N = N; sh.nstages = cdiv(Mpix, kWgRows); sh.ldo = ldo;
+  const int mt = cdiv(C, kTcBM), splits = pick_splits(sh.nstages, mt);
+  sh.stages_per_split = cdiv(sh.nstages, splits);
+  dim3 grid(mt, 1, cdiv(sh.nstages, sh.stages_per_split));
+  return launch_wg<3, false>(st, tx, ty, dW, sh, grid, x3, prof_cls, 2.0 * Mpix * C * N);
+}
+
+// dW[9*C, N] (ldo) += im2col3x3(X[B,H,W,C] (ldx))^T * dY[B,H,W,32-padded] (ldy = 32)   N <= 32: 3x3 conv weight gradient
+int tc_wgrad_3x3(cudaStream_t st, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, bool x3,
+                 int prof_cls) {
+  WAP_REQUIRE(C % 32 == 0 && N <= 32 && ldy == 32, "tc_wgrad_3x3: C=%d N=%d ldy=%d", C, N, ldy);
+  int TW = 1; while (TW < W && TW < kWgRows) TW <<= 1;
+  const int TH = kWgRows / TW;
+  CUtensorMap tx, ty;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldx * 4, (uint64_t)W * ldx * 4, (uint64_t)H * W * ldx * 4};
+    const uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&tx, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)ldy, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldy * 4, (uint64_t)W * ldy * 4, (uint64_t)H * W * ldy * 4};
+    const uint32_t box[4] = {32, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&ty, dY, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
+  }
+  WgShape sh{}; sh.M = 9 * C; sh.N = N; sh.ldo = ldo; sh.C = C; sh.H = H; sh.W = W; sh.TW = TW; sh.TH = TH;
+  sh.tiles_x = cdiv(W, TW); sh.tiles_y = cdiv(H, TH); sh.nstages = sh.tiles_x * sh.tiles_y * B;
+  const int mt = cdiv(9 * C, kTcBM), splits = pick_splits(sh.nstages, mt);
+  sh.stages_per_split = cdiv(sh.nstages, splits);
+  dim3 grid(mt, 1, cdiv(sh.nstages, sh.stages_per_split));
+  return launch_wg<1, true>(st, tx, ty, dW, sh, grid, x3, prof_cls, 2.0 * B * H * W * 9 * C * N);
 }
 
 }  // namespace wap
