@@ -12,9 +12,11 @@
 #include <algorithm>
 
 #include "decoder.cuh"
+#include "tc_gemm.cuh"
 
 namespace wap {
 
+int get_conv_precision();
 size_t step_ws_floats(int Bn, int L);
 int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
                     float* watch, float* h0, float* qf, float* mean_scratch);
@@ -29,6 +31,7 @@ struct DecTrainWs {
   float *dLG, *dMO, *dHlog, *dCTX, *dEMB, *dG1, *dEh, *dUH, *dSP, *dG2, *dCH, *dPH2, *DZ, *dWatch, *DF;
   float *dAP0, *dAP1, *dalpha, *de, *dh0, *dh1, *dpre_h, *dQf, *dmean;
   float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
+  float *qf_hi, *qf_lo, *Ua_hi, *Ua_lo, *UaT_hi, *UaT_lo;    // tensor-core operand copies (3xTF32 hi/lo parts)
 };
 static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   DecTrainWs w; size_t o = 0;
@@ -49,6 +52,8 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.dQf = take((size_t)kCovTaps * kNA); w.dmean = take((size_t)B * kD);
   w.T_Wczr = take((size_t)2 * kN * kD); w.T_Wchnl = take((size_t)kN * kD); w.T_Uhzhrnl = take((size_t)2 * kN * kN);
   w.T_Urhnl = take((size_t)kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
+  w.qf_hi = take((size_t)kCovTaps * kNA); w.qf_lo = take((size_t)kCovTaps * kNA);
+  w.Ua_hi = take((size_t)kD * kNA); w.Ua_lo = take((size_t)kD * kNA); w.UaT_hi = take((size_t)kD * kNA); w.UaT_lo = take((size_t)kD * kNA);
   if (total != nullptr) *total = o;
   return w;
 }
@@ -190,7 +195,15 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   const ParamLayout& P = layout();
   const int L = h * w, TB = T * B;
   DecTrainWs W = carve_train(wsp, B, L, T, nullptr);
-  WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, W.watch, W.H, W.qf, W.mean));   // H[0] = h0 (masked mean, S:345-347)
+  const int prec = get_conv_precision();
+  const bool tc = prec != 0 && tc_available();
+  if (tc) {   // hoisted watch GEMM [B*L,684]x[684,512] on tensor cores; h0 and Q' as usual
+    WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, nullptr, W.H, W.qf, W.mean));
+    WAP_TRY(tc_prep_bt(st, params + P.U_a, kD, kNA, 1, W.UaT_hi, W.UaT_lo));
+    WAP_TRY(tc_gemm(st, ann, kD, W.UaT_hi, prec == 2 ? W.UaT_lo : nullptr, kD, B * L, kNA, kD, TcEpi{W.watch, kNA, 0, nullptr, params + P.U_a_b}, kProfOtherGemm));
+  } else {
+    WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, W.watch, W.H, W.qf, W.mean));   // H[0] = h0 (masked mean, S:345-347)
+  }
   emb_shift_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(params + P.embed, y, W.EMB, T, B);
   WAP_LAUNCH_CHECK();
   // emb-dependent GRU-1 pre-activations for all steps at once
@@ -399,6 +412,12 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_TRY(transpose(st, p + P.W_a, W.T_Wa, kN, kNA));
   WAP_TRY(transpose(st, p + P.U_hz_hr, W.T_Uhzhr, kN, 2 * kN));
   WAP_TRY(transpose(st, p + P.U_rh, W.T_Urh, kN, kN));
+  const int prec = get_conv_precision();
+  const bool tc = prec != 0 && tc_available();
+  if (tc) {
+    WAP_TRY(tc_prep_bt(st, W.qf, kNA, kCovTaps, 0, W.qf_hi, W.qf_lo));
+    WAP_TRY(tc_prep_bt(st, p + P.U_a, kNA, kD, 0, W.Ua_hi, W.Ua_lo));
+  }
   // ---- head (LO holds dLO after the forward CE kernel)
   wo_bwd_data_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LO, p + P.Wo, W.dMO, TB);
   WAP_LAUNCH_CHECK();
@@ -454,7 +473,8 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       WAP_TRY(skinny_gemm(st, a));
     }
     // coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
-    WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
+    if (tc) WAP_TRY(tc_gemm(st, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, 124, 0, nullptr, nullptr}, kProfOtherGemm));
+    else WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
     cov_bwd_gather_kernel<<<cdiv(B * L, 256), 256, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w);
     WAP_LAUNCH_CHECK();
     gru1_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
@@ -506,7 +526,8 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   }
   // watch path: dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
   WAP_TRY(gemm_tn_atomic(st, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));
-  WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
+  if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr}, kProfOtherGemm));
+  else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
   // context path
   dann_ctx_kernel<<<(unsigned)cdivz((size_t)B * L * (kD / 4), 256), 256, 0, st>>>(W.ALPHA, W.dCTX, d_ann, T, B, L);
   WAP_LAUNCH_CHECK();

@@ -276,6 +276,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += v2[i];
       }
+      if (epi.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) v[j] += __ldg(epi.bias + n0 + c + j);
+      }
       if (valid) {
         float* dst = epi.out + mrow * epi.ld + n0 + c;
 #pragma unroll
@@ -577,7 +581,26 @@ static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& 
   return launch_tc1<BN, IM2COL, false>(st, ta, tb, tb, epi, sh, grid, prof_cls, flops);
 }
 
+__global__ void tc_prep_bt_kernel(const float* __restrict__ W, int K, int N, int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int n = i / K, k = i - n * K;
+  const float v = transpose ? __ldg(W + (size_t)k * N + n) : __ldg(W + i);
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  const float h = __uint_as_float(u);
+  hi[i] = h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - h));
+  lo[i] = __uint_as_float(u);
+}
+int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, float* hi, float* lo) {
+  tc_prep_bt_kernel<<<cdiv(N * K, 256), 256, 0, st>>>(W, K, N, transpose, hi, lo);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
 int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
+  WAP_REQUIRE(epi.bias == nullptr || epi.stats == nullptr, "tc_gemm: bias and statistics cannot be combined");
   WAP_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (epi.ld & 3) == 0, "tc_gemm: strides must be multiples of 4 floats");
   WAP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)epi.out & 15) == 0, "tc_gemm: pointers must be 16-byte aligned");
   CUtensorMap ta, tb, tbl;

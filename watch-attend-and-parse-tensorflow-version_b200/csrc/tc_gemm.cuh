@@ -27,7 +27,11 @@ struct TcEpi {
   float* out; int ld;        // D[m*ld + n]
   int accumulate;            // D += acc
   double* stats;             // [2][N] column sum / sum of squares of the raw accumulators, or null
+  const float* bias;         // optional [N] added to the stored value (not to the statistics)
 };
+
+// Bt_hi/lo[N][K] = split(transpose(W[K][N])) (transpose != 0) or split(W[N][K]) : operand preparation for tc_gemm's 3xTF32 mode
+int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, float* hi, float* lo);
 
 // D[M,N] = A[M,K](lda) * Bt[N,K](ldb)^T ; N <= 256 per launch column tile (grid.y tiles of BN)
 // Bt_lo != null selects the error-compensated 3xTF32 variant: Bt = rna_tf32(W), Bt_lo = rna_tf32(W - Bt); A is split on the fly.
