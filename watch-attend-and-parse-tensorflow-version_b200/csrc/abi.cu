@@ -218,12 +218,12 @@ int wap_debug_set_tc_mask(int mask) { g_tc_debug_mask = mask; return 0; }
 int wap_debug_capture(int layer, float* buf) { g_dbg_layer = layer; g_dbg_buf = buf; return 0; }
 int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
                 int accumulate, double* stats) {
-  TcEpi e{D, ldd, accumulate, stats, nullptr};
+  TcEpi e{D, ldd, accumulate, stats, nullptr, 0};
   return tc_gemm(ST(stream), A, lda, Bt, Bt_lo, ldb, M, N, K, e, kProfOtherGemm);
 }
 int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
                    float* D, int ldd, double* stats) {
-  TcEpi e{D, ldd, 0, stats, nullptr};
+  TcEpi e{D, ldd, 0, stats, nullptr, 0};
   return tc_conv3x3(ST(stream), x, ldx, B, H, W, C, Wt, Wt_lo, Nrows, N, e, kProfOtherGemm);
 }
 int wap_debug_wgrad(float* buf, int idesc_xor) { g_wg_dbg = buf; g_wg_xor = idesc_xor; return 0; }

@@ -54,6 +54,8 @@ struct StepCtx {
   float* h_new;         // [Bn,256]
   // optional extra segment on the ctx GEMM (inference logits: ctx*Wc -> LG)
   SkinnySeg extra_ctx; int has_extra_ctx;
+  // tensor-core coverage GEMM (training scan): patches materialised in Ppat [Bn*L,128], Q'^T hi/lo [512][128]; tc_mode 0 = FFMA
+  int tc_mode; float* Ppat; const float* qfT_hi; const float* qfT_lo;
 };
 int decoder_step(cudaStream_t st, const StepCtx& c);
 

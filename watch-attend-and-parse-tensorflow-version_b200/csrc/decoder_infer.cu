@@ -152,6 +152,7 @@ int decoder_word_step(cudaStream_t st, const float* params, const float* ann, co
   c.G1 = s.G1; c.UH = s.UH; c.prop1 = s.prop1; c.pre_h = s.pre_h; c.SP = s.SP; c.G2 = s.G2; c.PH2 = s.PH2; c.CH = s.CH;
   c.prop2 = s.prop2; c.COV = s.COV; c.TANH = s.COV; c.E = s.E; c.alpha = s.alpha; c.ap_out = ap_out; c.ctx = s.ctx; c.h_new = h_new;
   c.extra_ctx = {params + P.Wc, kMw, kMw, s.LG, kMw}; c.has_extra_ctx = 1;
+  c.tc_mode = 0; c.Ppat = nullptr; c.qfT_hi = nullptr; c.qfT_lo = nullptr;
   WAP_TRY(decoder_step(st, c));
   {   // logits: + h*Wh ; maxout ; Wo ; softmax (dropout is off at decode time, S:433 with training=False)
     SkinnyArgs a; a.X = h_new; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 1;

@@ -1,5 +1,6 @@
 // Decoder time-step kernels (forward).  See decoder.cuh for the data flow.
 #include "decoder.cuh"
+#include "tc_gemm.cuh"
 
 namespace wap {
 
@@ -220,6 +221,39 @@ softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask
   }
 }
 
+// Ppat[pos][tap (128, taps >= 121 zero)] = alpha_past[b, y + dy, x + dx]   (11x11 SAME patches, float4 per thread)
+__global__ void __launch_bounds__(256) cov_im2col_kernel(const float* __restrict__ ap, float* __restrict__ Ppat, int Bn, int H, int W) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Bn * H * W * 32) return;
+  const int pos = i >> 5, t4 = (i & 31) * 4;
+  const int x = pos % W, t = pos / W, y = t % H;
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int tap = t4 + j, dy = tap / kCovK - kCovK / 2, dx = tap % kCovK - kCovK / 2;
+    v[j] = (tap < kCovTaps && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W) ? __ldg(ap + pos + dy * W + dx) : 0.f;
+  }
+  *reinterpret_cast<float4*>(Ppat + (size_t)pos * 128 + t4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+// Q'^T hi/lo [512][128] (taps >= 121 zero) for the tensor-core coverage GEMM
+__global__ void prep_qfT_kernel(const float* __restrict__ qf, float* __restrict__ hi, float* __restrict__ lo) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= kNA * 128) return;
+  const int c = i >> 7, tap = i & 127;
+  const float v = tap < kCovTaps ? __ldg(qf + (size_t)tap * kNA + c) : 0.f;
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  const float h = __uint_as_float(u);
+  hi[i] = h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - h));
+  lo[i] = __uint_as_float(u);
+}
+int prep_qfT(cudaStream_t st, const float* qf, float* hi, float* lo) {
+  prep_qfT_kernel<<<cdiv(kNA * 128, 256), 256, 0, st>>>(qf, hi, lo);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
 // =====================================================================================
 // one full decoder step
 // =====================================================================================
@@ -251,7 +285,12 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     a.seg[2] = {p + P.U_rh_nl, kN, kN, c.PH2, kN};
     WAP_TRY(skinny_gemm(st, a));
   }
-  {   // coverage: COV[Bn*L,512] = patches(alpha_past)[Bn*L,121] * Q'[121,512]   (+ U_f_b)
+  if (c.tc_mode != 0) {   // coverage on tensor cores: im2col patches [Bn*L,128] x Q'^T[512][128]  (+ U_f_b)
+    cov_im2col_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(c.ap_in, c.Ppat, Bn, c.h, c.w);
+    WAP_LAUNCH_CHECK();
+    WAP_TRY(tc_gemm(st, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
+                    TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
+  } else {   // coverage: COV[Bn*L,512] = patches(alpha_past)[Bn*L,121] * Q'[121,512]   (+ U_f_b)
     ACovPatch A{c.ap_in, Bn, c.h, c.w};
     BRowMajor Bq{c.qf, kNA, kCovTaps, kNA};
     EpiStore e{c.COV, kNA, p + P.U_f_b, false, nullptr};

@@ -17,6 +17,7 @@
 namespace wap {
 
 int get_conv_precision();
+int prep_qfT(cudaStream_t st, const float* qf, float* hi, float* lo);
 size_t step_ws_floats(int Bn, int L);
 int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
                     float* watch, float* h0, float* qf, float* mean_scratch);
@@ -32,6 +33,7 @@ struct DecTrainWs {
   float *dAP0, *dAP1, *dalpha, *de, *dh0, *dh1, *dpre_h, *dQf, *dmean;
   float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
   float *qf_hi, *qf_lo, *Ua_hi, *Ua_lo, *UaT_hi, *UaT_lo;    // tensor-core operand copies (3xTF32 hi/lo parts)
+  float *Ppat, *qfT_hi, *qfT_lo;                              // coverage im2col patches [B*L,128], Q'^T [512][128]
 };
 static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   DecTrainWs w; size_t o = 0;
@@ -54,6 +56,7 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.T_Urhnl = take((size_t)kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
   w.qf_hi = take((size_t)kCovTaps * kNA); w.qf_lo = take((size_t)kCovTaps * kNA);
   w.Ua_hi = take((size_t)kD * kNA); w.Ua_lo = take((size_t)kD * kNA); w.UaT_hi = take((size_t)kD * kNA); w.UaT_lo = take((size_t)kD * kNA);
+  w.Ppat = take(BL * 128); w.qfT_hi = take((size_t)kNA * 128); w.qfT_lo = take((size_t)kNA * 128);
   if (total != nullptr) *total = o;
   return w;
 }
@@ -200,7 +203,8 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   if (tc) {   // hoisted watch GEMM [B*L,684]x[684,512] on tensor cores; h0 and Q' as usual
     WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, nullptr, W.H, W.qf, W.mean));
     WAP_TRY(tc_prep_bt(st, params + P.U_a, kD, kNA, 1, W.UaT_hi, W.UaT_lo));
-    WAP_TRY(tc_gemm(st, ann, kD, W.UaT_hi, prec == 2 ? W.UaT_lo : nullptr, kD, B * L, kNA, kD, TcEpi{W.watch, kNA, 0, nullptr, params + P.U_a_b}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, ann, kD, W.UaT_hi, prec == 2 ? W.UaT_lo : nullptr, kD, B * L, kNA, kD, TcEpi{W.watch, kNA, 0, nullptr, params + P.U_a_b, 0}, kProfOtherGemm));
+    WAP_TRY(prep_qfT(st, W.qf, W.qfT_hi, W.qfT_lo));
   } else {
     WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, W.watch, W.H, W.qf, W.mean));   // H[0] = h0 (masked mean, S:345-347)
   }
@@ -219,6 +223,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
     c.SP = W.SP + r * kNA; c.G2 = W.G2 + r * 2 * kN; c.PH2 = W.PH2 + r * kN; c.CH = W.CH + r * kN; c.prop2 = W.PROP2 + r * kN;
     c.COV = W.COV; c.TANH = W.TANH + r * L * kNA; c.E = W.E; c.alpha = W.ALPHA + r * L; c.ap_out = W.AP + (r + B) * L;
     c.ctx = W.CTX + r * kD; c.h_new = W.H + (r + B) * kN; c.has_extra_ctx = 0;
+    c.tc_mode = tc ? prec : 0; c.Ppat = W.Ppat; c.qfT_hi = W.qfT_hi; c.qfT_lo = W.qfT_lo;
     WAP_TRY(decoder_step(st, c));
   }
   // logits for all steps (S:354-364)
@@ -343,7 +348,7 @@ dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const fl
 // dAP_out[b,l'] = dalpha_total... transposed 11x11 stencil:  dAP_out = dAP_in + sum_tap DF[b, l'-off(tap), tap]
 __global__ void __launch_bounds__(256)
 cov_bwd_gather_kernel(const float* __restrict__ DF, const float* __restrict__ dAP_in, float* __restrict__ dAP_out,
-                      int Bn, int H, int W) {
+                      int Bn, int H, int W, int tap_major) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * H * W) return;
   const int x = i % W, t = i / W, y = t % H, b = t / H;
@@ -351,8 +356,10 @@ cov_bwd_gather_kernel(const float* __restrict__ DF, const float* __restrict__ dA
   for (int tap = 0; tap < kCovTaps; ++tap) {
     const int dy = tap / kCovK - kCovK / 2, dx = tap % kCovK - kCovK / 2;
     const int ys = y - dy, xs = x - dx;     // source position l with l + off(tap) = l'
-    if ((unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W)
-      s += DF[((size_t)(b * H + ys) * W + xs) * 124 + tap];
+    if ((unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W) {
+      const size_t src = (size_t)(b * H + ys) * W + xs;
+      s += tap_major ? DF[(size_t)tap * Bn * H * W + src] : DF[src * 124 + tap];   // tap-major: coalesced across x
+    }
   }
   dAP_out[i] = s;
 }
@@ -473,9 +480,9 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       WAP_TRY(skinny_gemm(st, a));
     }
     // coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
-    if (tc) WAP_TRY(tc_gemm(st, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, 124, 0, nullptr, nullptr}, kProfOtherGemm));
+    if (tc) WAP_TRY(tc_gemm(st, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
     else WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
-    cov_bwd_gather_kernel<<<cdiv(B * L, 256), 256, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w);
+    cov_bwd_gather_kernel<<<cdiv(B * L, 256), 256, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0);
     WAP_LAUNCH_CHECK();
     gru1_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
                                                         W.dG1 + r * 2 * kN, W.dEh + r * kN, W.dUH + r * kN, dh_out, B);
@@ -526,7 +533,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   }
   // watch path: dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
   WAP_TRY(gemm_tn_atomic(st, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));
-  if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr}, kProfOtherGemm));
+  if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
   // context path
   dann_ctx_kernel<<<(unsigned)cdivz((size_t)B * L * (kD / 4), 256), 256, 0, st>>>(W.ALPHA, W.dCTX, d_ann, T, B, L);

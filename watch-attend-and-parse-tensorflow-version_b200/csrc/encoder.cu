@@ -508,7 +508,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       {   // 1x1 bottleneck  C -> 96
         double* sk = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
         if (tc) {
-          WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, kBottle, C, TcEpi{y1, kBottle, 0, sk, nullptr}, kProfConv1Fwd));
+          WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, kBottle, C, TcEpi{y1, kBottle, 0, sk, nullptr, 0}, kProfConv1Fwd));
         } else {
           ARowMajor A{buf[b], ld, M, C};
           BRowMajor Bw{params + c1.w, kBottle, C, kBottle};
@@ -520,7 +520,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       {   // 3x3 growth  96 -> 24, written in place at channel offset C
         double* sk = training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr;
         if (tc) {
-          WAP_TRY(tc_conv3x3(st, a1, kBottle, B, h, w, kBottle, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), 32, kGrowth, TcEpi{y2, kGrowth, 0, sk, nullptr}, kProfConv3Fwd));
+          WAP_TRY(tc_conv3x3(st, a1, kBottle, B, h, w, kBottle, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), 32, kGrowth, TcEpi{y2, kGrowth, 0, sk, nullptr, 0}, kProfConv3Fwd));
         } else {
           AIm2col3 A{a1, kBottle, B, h, w, kBottle, false};
           BRowMajor Bw{params + c3.w, kGrowth, 9 * kBottle, kGrowth};
@@ -536,7 +536,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       float* yt = wsp + ws.ytr[b];
       double* sk = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
       if (tc) {
-        WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, ct.cout, C, TcEpi{yt, ct.cout, 0, sk, nullptr}, kProfTransFwd));
+        WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, ct.cout, C, TcEpi{yt, ct.cout, 0, sk, nullptr, 0}, kProfTransFwd));
       } else {
         ARowMajor A{buf[b], ld, M, C};
         BRowMajor Bw{params + ct.w, ct.cout, C, ct.cout};
@@ -595,7 +595,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfTransBwd)));
       }
       if (tc && (g_tc_debug_mask & 1)) {   // dgrad  G[b] = dy * W^T   (initialises the whole gradient buffer of block b)
-        WAP_TRY(tc_gemm(st, dytr, ct.cout, wsp + ws.wt_bwd[k], lo(ws.wt_bwd_lo[k]), ct.cout, M, C, ct.cout, TcEpi{G[b], ld, 0, nullptr, nullptr}, kProfTransBwd));
+        WAP_TRY(tc_gemm(st, dytr, ct.cout, wsp + ws.wt_bwd[k], lo(ws.wt_bwd_lo[k]), ct.cout, M, C, ct.cout, TcEpi{G[b], ld, 0, nullptr, nullptr, 0}, kProfTransBwd));
       } else {
         ARowMajor A{dytr, ct.cout, M, ct.cout};
         BColMajor Bw{params + ct.w, ct.cout, ct.cout, C};
@@ -622,7 +622,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         WAP_TRY((launch_gemm<Cfg128x32>(st, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv3Wgrad)));
       }
       if (tc && (g_tc_debug_mask & 2)) {   // dgrad 3x3: d a1[M,96]
-        WAP_TRY(tc_conv3x3(st, dy2, kDy2Ld, B, h, w, kDy2Ld, wsp + ws.wt_bwd[k3], lo(ws.wt_bwd_lo[k3]), kBottle, kBottle, TcEpi{da1, kBottle, 0, nullptr, nullptr}, kProfConv3Dgrad));
+        WAP_TRY(tc_conv3x3(st, dy2, kDy2Ld, B, h, w, kDy2Ld, wsp + ws.wt_bwd[k3], lo(ws.wt_bwd_lo[k3]), kBottle, kBottle, TcEpi{da1, kBottle, 0, nullptr, nullptr, 0}, kProfConv3Dgrad));
       } else {
         AIm2col3 A{dy2, kDy2Ld, B, h, w, kGrowth, false};
         BDgrad3 Bw{params + c3.w, kBottle, kGrowth};
@@ -646,7 +646,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv1Wgrad)));
       }
       if (tc && (g_tc_debug_mask & 4)) {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
-        WAP_TRY(tc_gemm(st, dy1, kBottle, wsp + ws.wt_bwd[k1], lo(ws.wt_bwd_lo[k1]), kBottle, M, C, kBottle, TcEpi{G[b], ld, 1, nullptr, nullptr}, kProfConv1Dgrad));
+        WAP_TRY(tc_gemm(st, dy1, kBottle, wsp + ws.wt_bwd[k1], lo(ws.wt_bwd_lo[k1]), kBottle, M, C, kBottle, TcEpi{G[b], ld, 1, nullptr, nullptr, 0}, kProfConv1Dgrad));
       } else {
         ARowMajor A{dy1, kBottle, M, kBottle};
         BColMajor Bw{params + c1.w, kBottle, kBottle, C};

@@ -8,7 +8,13 @@
 namespace wap {
 
 constexpr int kTcBM = 128;          // UMMA M (cta_group::1)
-constexpr int kTcBK = 32;           // floats per stage row = 128 B = one swizzle span
+#ifndef WAP_TC_BK
+#define WAP_TC_BK 32
+#endif
+constexpr int kTcBK = WAP_TC_BK;    // floats per stage row: 32 (128 B rows, SWIZZLE_128B, 1 CTA/SM in 3xTF32 mode) or
+                                    // 16 (64 B rows, SWIZZLE_64B: half-size stages so that TWO CTAs stay resident per SM)
+constexpr int kTcRowB = kTcBK * 4;
+static_assert(kTcBK == 32 || kTcBK == 16, "WAP_TC_BK must be 16 or 32");
 constexpr int kTcThreads = 192;
 constexpr uint32_t kSpinLimit = 1u << 24;
 
@@ -90,14 +96,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// shared-memory matrix descriptor: K-major, SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart
+// shared-memory matrix descriptor: K-major, rows of kTcRowB bytes = one swizzle span (SWIZZLE_128B or SWIZZLE_64B),
+// 8-row groups 8*kTcRowB bytes apart
 __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);       // start address        bits [0,14)
   d |= (uint64_t)0 << 16;                            // leading byte offset  (unused for swizzled K-major)
-  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset   bits [32,46)
+  d |= (uint64_t)((8 * kTcRowB) >> 4) << 32;         // stride byte offset   bits [32,46)
   d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                            // layout: SWIZZLE_128B
+  d |= (uint64_t)(kTcRowB == 128 ? 2 : 4) << 61;     // layout: SWIZZLE_128B / SWIZZLE_64B
   return d;
 }
 // instruction descriptor: D=f32, A=B=tf32, both K-major, M=128, N=BN
@@ -116,7 +123,7 @@ struct TcShape {
 // X3 = error-compensated "3xTF32": D = a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32-grade accuracy).
 // Stage layout: [A (hi)] [A lo] [B hi] [B lo]; the lo tiles exist only when X3.
 template <int BN, bool X3> struct TcSmem {
-  static constexpr int kStages = X3 ? 3 : (BN <= 32 ? 4 : 3);       // X3: 1 CTA/SM (<= 192 KB); else 2 CTAs/SM
+  static constexpr int kStages = kTcBK == 16 ? (X3 ? 3 : 4) : (X3 ? 3 : (BN <= 32 ? 4 : 3));   // sized for 2 CTAs/SM when possible
   static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
   static constexpr int kBBytes = BN * kTcBK * 4;
   static constexpr int kStage = (X3 ? 2 : 1) * (kABytes + kBBytes);
@@ -134,7 +141,7 @@ __device__ __forceinline__ float tf32_rna_dev(float x) {
 }
 
 template <int BN, bool IM2COL, bool X3>
-__global__ void __launch_bounds__(kTcThreads, X3 ? 1 : 2)
+__global__ void __launch_bounds__(kTcThreads, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
   using S = TcSmem<BN, X3>;
@@ -280,7 +287,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) v[j] += __ldg(epi.bias + n0 + c + j);
       }
-      if (valid) {
+      if (valid && epi.transpose_out) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < sh.N) epi.out[(size_t)(n0 + c + j) * epi.ld + mrow] = v[j];
+      } else if (valid) {
         float* dst = epi.out + mrow * epi.ld + n0 + c;
 #pragma unroll
         for (int j = 0; j < 32; j += 4) {
@@ -546,7 +557,7 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 bool tc_available() { return get_encode() != nullptr; }
 
 static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                    CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    CUtensorMapSwizzle swz = (kTcRowB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   WAP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
@@ -601,7 +612,8 @@ int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, flo
 
 int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
   WAP_REQUIRE(epi.bias == nullptr || epi.stats == nullptr, "tc_gemm: bias and statistics cannot be combined");
-  WAP_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && (epi.ld & 3) == 0, "tc_gemm: strides must be multiples of 4 floats");
+  WAP_REQUIRE(!epi.transpose_out || !epi.accumulate, "tc_gemm: transposed store cannot accumulate");
+  WAP_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && ((epi.ld & 3) == 0 || epi.transpose_out), "tc_gemm: strides must be multiples of 4 floats");
   WAP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)epi.out & 15) == 0, "tc_gemm: pointers must be 16-byte aligned");
   CUtensorMap ta, tb, tbl;
   {
@@ -624,7 +636,7 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
 }
 
 int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N, const TcEpi& epi, int prof_cls) {
-  WAP_REQUIRE(C % kTcBK == 0 && (ldx & 3) == 0 && (epi.ld & 3) == 0, "tc_conv3x3: C=%d must be a multiple of 32", C);
+  WAP_REQUIRE(C % kTcBK == 0 && (ldx & 3) == 0 && (epi.ld & 3) == 0, "tc_conv3x3: C=%d must be a multiple of %d", C, kTcBK);
   int TW = 1; while (TW < W && TW < kTcBM) TW <<= 1;     // power of two >= W, at most 128
   const int TH = kTcBM / TW;
   CUtensorMap ta, tb, tbl;

@@ -28,6 +28,7 @@ struct TcEpi {
   int accumulate;            // D += acc
   double* stats;             // [2][N] column sum / sum of squares of the raw accumulators, or null
   const float* bias;         // optional [N] added to the stored value (not to the statistics)
+  int transpose_out;         // store D[m,n] at out[n*ld + m] (coalesced: one TMEM lane = one row m per thread)
 };
 
 // Bt_hi/lo[N][K] = split(transpose(W[K][N])) (transpose != 0) or split(W[N][K]) : operand preparation for tc_gemm's 3xTF32 mode
