@@ -72,6 +72,17 @@ int wap_decoder_step(void* stream, const float* params, const float* annotation,
                      const float* h_prev, const float* alpha_past, float* probs, int32_t* word,
                      float* h_new, float* alpha_past_new, float* workspace);
 
+/* ---- Parser.one_time_step (S:260-308), the body of the tf.scan in get_ht_ctx (S:246-255), for a GIVEN embedding
+ * emb_y [Bn,256]: carry (h, alpha_past) + masks -> h_new [Bn,256], context [Bn,684], alpha [Bn,h,w], alpha_past'.
+ * a_mask [Bn,h,w] / y_mask [Bn] may be NULL.  workspace: wap_decoder_step_workspace_floats(). */
+int wap_one_time_step(void* stream, const float* params, const float* annotation, const float* watch, const float* qfused,
+                      const float* a_mask, const float* y_mask, int Bn, int h, int w, const float* emb_y, const float* h_prev,
+                      const float* alpha_past, float* h_new, float* context, float* alpha, float* alpha_past_new, float* workspace);
+/* ---- Attender.get_context (S:166-206): annotation, h_{t-1}, alpha_past, a_mask -> context, alpha, alpha_past' */
+int wap_get_context(void* stream, const float* params, const float* annotation, const float* watch, const float* qfused,
+                    const float* a_mask, int Bn, int h, int w, const float* h_t_1, const float* alpha_past, float* context,
+                    float* alpha, float* alpha_past_new, float* workspace);
+
 /* ---- greedy decode (intended semantics of the dead branch S:475-483) of Bn images at once.
  * tokens [Bn,maxlen] int32, lengths [Bn] int32 (tokens written incl. the final <eol>=0 if emitted).
  * check_every > 0: synchronises the host every that many steps to stop early. */
@@ -154,6 +165,12 @@ int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, i
 int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int x3);
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo,
                      int x3);
+/* ---- dropout seed from device memory: when seed_dev != NULL every dropout site (S:89-93, S:361) reads its seed from
+ * *seed_dev at kernel run time instead of the by-value `seed` argument, so that a training step captured once in a CUDA
+ * graph can be replayed with a fresh seed per step (tf.layers.dropout draws new masks on every sess.run).  NULL restores
+ * the by-value behaviour.  Library-global. */
+int wap_set_dropout_seed_source(const uint32_t* seed_dev);
+
 /* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);
 /* byte offsets (in floats) of selected encoder-workspace regions, for tests: what = 0 stem_raw,

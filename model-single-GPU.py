@@ -9,7 +9,8 @@ test_caption.txt}), same outputs (<path>/log-bs-6.txt, <path>/result/valid_decod
 maxlen 100, patience 15, lr/10 twice, then early stop; S:609-734) — but every FLOP runs in
 libwap_b200.so on the B200.  Under torchrun (WORLD_SIZE > 1) it trains data-parallel with a NCCL
 gradient all-reduce (semantics of model-distributed.py:704-717); rank 0 validates.
-Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid.
+Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --save CKPT.npz (written by rank 0 whenever the
+validation WER improves - the reference's tf.train.Saver is constructed but never called), --resume CKPT.npz.
 """
 import argparse
 import os
@@ -40,7 +41,11 @@ def main(args):
     print('train lenght is ', len(train))
     eng = wap_b200.WAPEngine(seed=args.seed)
     eng.world_size = world
+    if args.resume:
+        eng.load(args.resume)
     dp.broadcast_params(eng.P.flat); dp.broadcast_params(eng.P.moving)
+    if args.resume and world > 1:
+        dp.broadcast_params(eng.accum); dp.broadcast_params(eng.accum_update)
 
     uidx, cost_s, dispFreq = 0, 0.0, 100
     validFreq = sampleFreq = max(len(train) // world, 1)
@@ -108,6 +113,8 @@ def main(args):
                 history_errs.append(valid_per)
                 if valid_per <= np.array(history_errs).min():
                     bad_counter = 0
+                    if args.save:
+                        eng.save(args.save)
                 else:
                     bad_counter += 1
                     if bad_counter > patience:
@@ -133,5 +140,7 @@ if __name__ == "__main__":
     parser.add_argument("--max_epoch", type=int, default=200)
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--greedy_valid", action="store_true")
+    parser.add_argument("--save", default="")
+    parser.add_argument("--resume", default="")
     (args, unknown) = parser.parse_known_args()
     main(args)

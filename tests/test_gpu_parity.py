@@ -346,3 +346,77 @@ def test_greedy_persistent_matches_stepwise(report, B, h, w):
     if B <= 3:
         ref = O.greedy_decode(O.to_torch(P), t64(anns[:1].cpu().numpy()), 30)
         assert t2[0, : int(l2[0])].tolist() == ref
+
+
+def test_get_context_and_one_time_step_with_masks(report):
+    """Attender.get_context (S:166-206) and Parser.one_time_step / get_ht_ctx (S:246-308) incl. a_mask / y_mask."""
+    import wap_b200
+    P = O.lively_params(5)
+    eng = engine_with(P)
+    Pt = O.to_torch(P)
+    B, h, w, T = 3, 4, 7, 4
+    rs = np.random.RandomState(3)
+    ann = _rand_annotation(21, B, h, w)
+    am = np.ones((B, h, w), np.float32); am[1, 2:, :] = 0; am[2, :, 5:] = 0
+    hp = np.tanh(rs.randn(B, 256)).astype(np.float32); ap = (rs.rand(B, h, w) * 0.2).astype(np.float32)
+    ann_d = torch.as_tensor(ann).cuda()
+    fails = []
+    for mask in (None, am):
+        ctx, al, apn = eng.get_context(ann_d, hp, ap, mask)
+        rc, ra, rap = O.get_context(Pt, t64(ann), t64(hp), t64(ap), t64(mask) if mask is not None else None)
+        tag = "masked" if mask is not None else "unmasked"
+        _check(report, "get_context", "context_" + tag, ctx.cpu().numpy(), rc.numpy(), REL_TOL, fails)
+        _check(report, "get_context", "alpha_" + tag, al.cpu().numpy(), ra.numpy(), REL_TOL, fails)
+        _check(report, "get_context", "alpha_past_" + tag, apn.cpu().numpy(), rap.numpy(), REL_TOL, fails)
+    emb = rs.randn(T, B, 256).astype(np.float32) * 0.3
+    ym = np.ones((T, B), np.float32); ym[2:, 1] = 0; ym[3, 2] = 0
+    att = wap_b200.Attender(684, 256, 512, engine=eng); par = wap_b200.Parser(256, 256, att, 684)
+    hs, cs, als, aps, _, _ = par.get_ht_ctx(torch.as_tensor(emb).cuda(), torch.as_tensor(hp).cuda(), ann_d, torch.as_tensor(am).cuda(),
+                                            torch.as_tensor(ym).cuda())
+    hh, app = t64(hp), torch.zeros(B, h, w, dtype=torch.float64)
+    for t in range(T):
+        hh, cc, aa, app = O.one_time_step(Pt, hh, app, t64(ann), t64(am), t64(emb[t]), t64(ym[t]))
+        _check(report, "one_time_step", f"h_t{t}", hs[t].cpu().numpy(), hh.numpy(), REL_TOL, fails)
+        _check(report, "one_time_step", f"ctx_t{t}", cs[t].cpu().numpy(), cc.numpy(), REL_TOL, fails)
+        _check(report, "one_time_step", f"alpha_past_t{t}", aps[t].cpu().numpy(), app.numpy(), REL_TOL, fails)
+    assert not fails, fails
+
+
+def test_checkpoint_roundtrip(tmp_path):
+    P = O.lively_params(2)
+    eng = engine_with(P)
+    x, xm, y, ym = make_batch(5, 2, 32, 48, 3, True)
+    eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=3)
+    path = str(tmp_path / "ckpt.npz")
+    eng.save(path)
+    c1 = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=4))
+    eng2 = engine_with(O.lively_params(7))
+    eng2.load(path)
+    assert eng2.step_count == 1
+    c2 = float(eng2.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=4))
+    assert abs(c1 - c2) <= 1e-6 * abs(c1), (c1, c2)
+    z = np.load(path)
+    assert "conv2d_98/kernel" in z.files and "batch_normalization_50/moving_variance" in z.files and "__opt__/accum/embed" in z.files
+
+
+def test_cuda_graph_replay_matches_stream_launches():
+    """use_graphs: captured forward+backward replayed with a fresh device-side dropout seed == eager launches, bit for bit
+    in everything that is not an atomics-ordered sum (cost / gradients compared to 1e-5)."""
+    P = O.lively_params(3)
+    a, b = engine_with(P), engine_with(P)
+    b.use_graphs = True
+    x, xm, y, ym = make_batch(11, 3, 32, 64, 4, True)
+    for step in range(4):                     # step 0 captures, 1-3 replay; seeds differ per step
+        ca = float(a.train_step(x, y, xm, ym, lr=1.0, dropout=True))
+        ga = a.grads.clone()
+        cb = float(b.train_step(x, y, xm, ym, lr=1.0, dropout=True))
+        assert abs(ca - cb) <= 1e-5 * abs(ca), (step, ca, cb)
+        assert rel_l2(b.grads.cpu().numpy(), ga.cpu().numpy()) < 1e-4, step
+    assert b.replayed_launches > 0 and len(b._graphs) == 1
+    assert rel_l2(b.P.flat.cpu().numpy(), a.P.flat.cpu().numpy()) < 1e-4
+    # a different shape gets its own graph; the first keeps working
+    x2, xm2, y2, ym2 = make_batch(12, 2, 32, 48, 3, True)
+    ca = float(a.train_step(x2, y2, xm2, ym2)); cb = float(b.train_step(x2, y2, xm2, ym2))
+    assert abs(ca - cb) <= 1e-5 * abs(ca)
+    ca = float(a.train_step(x, y, xm, ym)); cb = float(b.train_step(x, y, xm, ym))
+    assert abs(ca - cb) <= 1e-5 * abs(ca) and len(b._graphs) == 2

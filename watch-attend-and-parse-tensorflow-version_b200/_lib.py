@@ -34,6 +34,8 @@ SIGNATURES = {
     "wap_attn_precompute": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "wap_decoder_step_workspace_floats": (_i64, [_i, _i, _i]),
     "wap_decoder_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wap_one_time_step": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "wap_get_context": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
     "wap_greedy_workspace_floats": (_i64, [_i, _i, _i]),
     "wap_greedy_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ip]),
     "wap_greedy_persistent_workspace_floats": (_i64, [_i, _i, _i]),
@@ -59,6 +61,7 @@ SIGNATURES = {
     "wap_tc_conv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "wap_tc_wgrad_1x1": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i]),
     "wap_tc_wgrad_3x3": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i]),
+    "wap_set_dropout_seed_source": (_i, [_vp]),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),
     "wap_encoder_workspace_offset": (_i64, [_i, _i, _i, _i, _i, _i]),
 }

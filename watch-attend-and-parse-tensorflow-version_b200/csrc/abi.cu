@@ -50,6 +50,12 @@ size_t decoder_train_ws_floats(int B, int L, int T);
 int decoder_word_step(cudaStream_t st, const float* params, const float* ann, const float* watch, const float* qf,
                       const float* a_mask, int shared, int Bn, int h, int w, const int* y, const float* h_prev,
                       const float* ap_in, float* probs, int* word, float* h_new, float* ap_out, float* wsp);
+int decoder_one_time_step(cudaStream_t st, const float* params, const float* ann, const float* watch, const float* qf,
+                          const float* a_mask, const float* y_mask, int Bn, int h, int w, const float* emb_y, const float* h_prev,
+                          const float* ap_in, float* h_new, float* ctx, float* alpha, float* ap_out, float* wsp);
+int attender_get_context(cudaStream_t st, const float* params, const float* ann, const float* watch, const float* qf,
+                         const float* a_mask, int Bn, int h, int w, const float* h_t_1, const float* ap_in,
+                         float* ctx, float* alpha, float* ap_out, float* wsp);
 int greedy_decode(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen,
                   int check_every, int* tokens, int* lengths, float* wsp, int* steps_run);
 int decoder_train_forward(cudaStream_t st, const float* params, const float* ann, const float* a_mask, const int* y,
@@ -160,6 +166,23 @@ int wap_decoder_step(void* stream, const float* params, const float* annotation,
                            probs, word, h_new, alpha_past_new, workspace);
 }
 
+int wap_one_time_step(void* stream, const float* params, const float* annotation, const float* watch, const float* qfused,
+                      const float* a_mask, const float* y_mask, int Bn, int h, int w, const float* emb_y, const float* h_prev,
+                      const float* alpha_past, float* h_new, float* context, float* alpha, float* alpha_past_new, float* workspace) {
+  WAP_REQUIRE(params && annotation && watch && qfused && emb_y && h_prev && alpha_past && h_new && context && alpha && alpha_past_new && workspace,
+              "wap_one_time_step: bad arguments");
+  return decoder_one_time_step(ST(stream), params, annotation, watch, qfused, a_mask, y_mask, Bn, h, w, emb_y, h_prev, alpha_past, h_new,
+                               context, alpha, alpha_past_new, workspace);
+}
+int wap_get_context(void* stream, const float* params, const float* annotation, const float* watch, const float* qfused,
+                    const float* a_mask, int Bn, int h, int w, const float* h_t_1, const float* alpha_past, float* context,
+                    float* alpha, float* alpha_past_new, float* workspace) {
+  WAP_REQUIRE(params && annotation && watch && qfused && h_t_1 && alpha_past && context && alpha && alpha_past_new && workspace,
+              "wap_get_context: bad arguments");
+  return attender_get_context(ST(stream), params, annotation, watch, qfused, a_mask, Bn, h, w, h_t_1, alpha_past, context, alpha,
+                              alpha_past_new, workspace);
+}
+
 int64_t wap_greedy_workspace_floats(int Bn, int h, int w) { return (int64_t)greedy_ws_floats(Bn, h * w); }
 int wap_greedy_decode(void* stream, const float* params, const float* annotation, int Bn, int h, int w,
                       int maxlen, int check_every, int32_t* tokens, int32_t* lengths, float* workspace, int* steps_run) {
@@ -233,6 +256,7 @@ int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }
+int wap_set_dropout_seed_source(const uint32_t* seed_dev) { wap::g_seed_src = seed_dev; return 0; }
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
   return dropout_mask(ST(stream), seed, site, (size_t)n, mask);
 }

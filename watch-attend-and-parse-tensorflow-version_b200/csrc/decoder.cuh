@@ -58,6 +58,11 @@ struct StepCtx {
   int tc_mode; float* Ppat; const float* qfT_hi; const float* qfT_lo;
 };
 int decoder_step(cudaStream_t st, const StepCtx& c);
+int attention_tail(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* a_mask, int shared, int Bn, int L,
+                   const float* SP, const float* ap_in, float* COV, float* TANH, float* E, float* alpha, float* ap_out, float* ctx);
+int attention_core(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* qf, const float* a_mask, int shared,
+                   int Bn, int h, int w, const float* SP, const float* ap_in, float* COV, float* TANH, float* E, float* alpha,
+                   float* ap_out, float* ctx);
 
 // fills up to 8 row-broadcast segments: dst[b*ld + j] = bias ? bias[j] : 0
 struct FillSeg { float* dst; int ld, n; const float* bias; };

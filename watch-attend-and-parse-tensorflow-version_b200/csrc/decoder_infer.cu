@@ -169,6 +169,50 @@ int decoder_word_step(cudaStream_t st, const float* params, const float* ann, co
   return 0;
 }
 
+
+// Parser.one_time_step (model-single-GPU.py:260-308) for a GIVEN embedding emb_y[Bn,256] (the scan body of get_ht_ctx):
+// -> h_new, context, alpha, alpha_past'.  a_mask [Bn,L] / y_mask [Bn] may be null.
+int decoder_one_time_step(cudaStream_t st, const float* params, const float* ann, const float* watch, const float* qf,
+                          const float* a_mask, const float* y_mask, int Bn, int h, int w, const float* emb_y, const float* h_prev,
+                          const float* ap_in, float* h_new, float* ctx, float* alpha, float* ap_out, float* wsp) {
+  const ParamLayout& P = layout();
+  const int L = h * w;
+  StepWs s = carve_step(wsp, Bn, L, nullptr);
+  {
+    FillArgs f; f.rows = Bn; f.nseg = 2;
+    f.seg[0] = {s.G1, 3 * kN, 2 * kN, params + P.b_yz_yr};
+    f.seg[1] = {s.G1 + 2 * kN, 3 * kN, kN, params + P.b_yh};
+    WAP_TRY(fill_rows(st, f));
+    SkinnyArgs a; a.X = emb_y; a.ldx = kMw; a.ids = nullptr; a.Bn = Bn; a.K = kMw; a.nseg = 2;
+    a.seg[0] = {params + P.W_yz_yr, 2 * kN, 2 * kN, s.G1, 3 * kN};
+    a.seg[1] = {params + P.W_yh, kN, kN, s.G1 + 2 * kN, 3 * kN};
+    WAP_TRY(skinny_gemm(st, a));
+  }
+  StepCtx c;
+  c.Bn = Bn; c.h = h; c.w = w; c.L = L; c.params = params; c.ann = ann; c.watch = watch; c.shared = 0; c.qf = qf;
+  c.a_mask = a_mask; c.y_mask = y_mask; c.h_prev = h_prev; c.ap_in = ap_in;
+  c.G1 = s.G1; c.UH = s.UH; c.prop1 = s.prop1; c.pre_h = s.pre_h; c.SP = s.SP; c.G2 = s.G2; c.PH2 = s.PH2; c.CH = s.CH;
+  c.prop2 = s.prop2; c.COV = s.COV; c.TANH = s.COV; c.E = s.E; c.alpha = alpha; c.ap_out = ap_out; c.ctx = ctx; c.h_new = h_new;
+  c.has_extra_ctx = 0; c.tc_mode = 0; c.Ppat = nullptr; c.qfT_hi = nullptr; c.qfT_lo = nullptr;
+  return decoder_step(st, c);
+}
+
+// Attender.get_context (model-single-GPU.py:166-206): annotation, h_{t-1}, alpha_past, a_mask -> context, alpha, alpha_past'
+int attender_get_context(cudaStream_t st, const float* params, const float* ann, const float* watch, const float* qf,
+                         const float* a_mask, int Bn, int h, int w, const float* h_t_1, const float* ap_in,
+                         float* ctx, float* alpha, float* ap_out, float* wsp) {
+  const ParamLayout& P = layout();
+  const int L = h * w;
+  StepWs s = carve_step(wsp, Bn, L, nullptr);
+  FillArgs f; f.rows = Bn; f.nseg = 1; f.seg[0] = {s.SP, kNA, kNA, params + P.W_a_b};
+  WAP_TRY(fill_rows(st, f));
+  SkinnyArgs a; a.X = h_t_1; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 1;
+  a.seg[0] = {params + P.W_a, kNA, kNA, s.SP, kNA};
+  WAP_TRY(skinny_gemm(st, a));
+  WAP_TRY(attention_core(st, params, ann, watch, qf, a_mask, 0, Bn, h, w, s.SP, ap_in, s.COV, s.COV, s.E, alpha, ap_out, ctx));
+  return 0;
+}
+
 // ------------------------------------------------------------------------------------ greedy loop
 // tokens[b, t] receives the argmax word while sequence b is alive; lengths[b] = number of tokens
 // written (including the terminating <eol>=0 if it was emitted).  state: y (next input id).

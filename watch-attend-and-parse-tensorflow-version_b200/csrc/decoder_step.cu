@@ -254,6 +254,31 @@ int prep_qfT(cudaStream_t st, const float* qf, float* hi, float* lo) {
   return 0;
 }
 
+// energies -> masked softmax -> alpha_past update -> context, given the coverage tensor COV (S:185-203)
+int attention_tail(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* a_mask, int shared, int Bn, int L,
+                   const float* SP, const float* ap_in, float* COV, float* TANH, float* E, float* alpha, float* ap_out, float* ctx) {
+  const ParamLayout& P = layout();
+  energy_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(COV, watch, SP, p + P.V_a, p + P.V_a_b, TANH, E, Bn, L, shared);
+  WAP_LAUNCH_CHECK();
+  const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
+  WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large for softmax_ctx_kernel: L=%d", L);
+  dim3 grid(cdiv(kD, kCtxChunk), Bn);
+  softmax_ctx_kernel<<<grid, 256, smem, st>>>(E, a_mask, ap_in, ann, alpha, ap_out, ctx, L, shared);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+// Attender.get_context after the speller projection: coverage GEMM (fp32 FFMA) + attention_tail
+int attention_core(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* qf, const float* a_mask, int shared,
+                   int Bn, int h, int w, const float* SP, const float* ap_in, float* COV, float* TANH, float* E, float* alpha,
+                   float* ap_out, float* ctx) {
+  const ParamLayout& P = layout();
+  ACovPatch A{ap_in, Bn, h, w};
+  BRowMajor Bq{qf, kNA, kCovTaps, kNA};
+  EpiStore e{COV, kNA, p + P.U_f_b, false, nullptr};
+  WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bq, e, Bn * h * w, kNA, 124, 1, kProfCovGemm)));
+  return attention_tail(st, p, ann, watch, a_mask, shared, Bn, h * w, SP, ap_in, COV, TANH, E, alpha, ap_out, ctx);
+}
+
 // =====================================================================================
 // one full decoder step
 // =====================================================================================
@@ -290,20 +315,9 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     WAP_LAUNCH_CHECK();
     WAP_TRY(tc_gemm(st, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
                     TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
-  } else {   // coverage: COV[Bn*L,512] = patches(alpha_past)[Bn*L,121] * Q'[121,512]   (+ U_f_b)
-    ACovPatch A{c.ap_in, Bn, c.h, c.w};
-    BRowMajor Bq{c.qf, kNA, kCovTaps, kNA};
-    EpiStore e{c.COV, kNA, p + P.U_f_b, false, nullptr};
-    WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bq, e, Bn * L, kNA, 124, 1, kProfCovGemm)));
-  }
-  energy_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(c.COV, c.watch, c.SP, p + P.V_a, p + P.V_a_b, c.TANH, c.E, Bn, L, c.shared);
-  WAP_LAUNCH_CHECK();
-  {
-    const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
-    WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large for softmax_ctx_kernel: L=%d", L);
-    dim3 grid(cdiv(kD, kCtxChunk), Bn);
-    softmax_ctx_kernel<<<grid, 256, smem, st>>>(c.E, c.a_mask, c.ap_in, c.ann, c.alpha, c.ap_out, c.ctx, L, c.shared);
-    WAP_LAUNCH_CHECK();
+    WAP_TRY(attention_tail(st, p, c.ann, c.watch, c.a_mask, c.shared, Bn, L, c.SP, c.ap_in, c.COV, c.TANH, c.E, c.alpha, c.ap_out, c.ctx));
+  } else {
+    WAP_TRY(attention_core(st, p, c.ann, c.watch, c.qf, c.a_mask, c.shared, Bn, c.h, c.w, c.SP, c.ap_in, c.COV, c.TANH, c.E, c.alpha, c.ap_out, c.ctx));
   }
   {   // ctx * [W_c_z_r | W_c_h_nl (| Wc)]
     SkinnyArgs a; a.X = c.ctx; a.ldx = kD; a.ids = nullptr; a.Bn = Bn; a.K = kD; a.nseg = 2;

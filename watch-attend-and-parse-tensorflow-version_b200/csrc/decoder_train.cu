@@ -81,18 +81,22 @@ __global__ void bias3_rows_kernel(float* LG, int rows, const float* by, const fl
   if (i < rows * kMw) { const int j = i % kMw; LG[i] = by[j] + bc[j] + bh[j]; }
 }
 // maxout over adjacent pairs + dropout (site kNumConv) (S:359-362)
-__global__ void maxout_drop_kernel(const float* __restrict__ LG, float* __restrict__ MO, int rows, int dropout, uint32_t seed) {
+__global__ void maxout_drop_kernel(const float* __restrict__ LG, float* __restrict__ MO, int rows, int dropout, uint32_t seed,
+                                   const uint32_t* __restrict__ seed_src) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * (kMw / 2)) return;
+  if (dropout && seed_src != nullptr) seed = __ldg(seed_src);
   const float2 v = *reinterpret_cast<const float2*>(LG + 2 * (size_t)i);
   float m = fmaxf(v.x, v.y);
   if (dropout) m = drop_keep(seed, kNumConv, (uint32_t)i) ? m * (1.f / (1.f - kDropRate)) : 0.f;
   MO[i] = m;
 }
 __global__ void maxout_drop_bwd_kernel(const float* __restrict__ LG, const float* __restrict__ dMO, float* __restrict__ dLG,
-                                       int rows, int dropout, uint32_t seed) {
+                                       int rows, int dropout, uint32_t seed,
+                                   const uint32_t* __restrict__ seed_src) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * (kMw / 2)) return;
+  if (dropout && seed_src != nullptr) seed = __ldg(seed_src);
   const float2 v = *reinterpret_cast<const float2*>(LG + 2 * (size_t)i);
   float g = dMO[i];
   if (dropout) g = drop_keep(seed, kNumConv, (uint32_t)i) ? g * (1.f / (1.f - kDropRate)) : 0.f;
@@ -232,7 +236,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
   WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
   WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.Wy, kMw, W.LG, kMw, TB, kMw, kMw, nullptr, true));
-  maxout_drop_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.MO, TB, dropout, seed);
+  maxout_drop_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.MO, TB, dropout, seed, g_seed_src);
   WAP_LAUNCH_CHECK();
   wo_fwd_kernel<<<cdiv(TB * kVocab, 256), 256, 0, st>>>(W.MO, params + P.Wo, params + P.bo, W.LO, TB);
   WAP_LAUNCH_CHECK();
@@ -319,49 +323,88 @@ softmax_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ da
 constexpr int kDzPix = 8;
 __global__ void __launch_bounds__(128)
 dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const float* __restrict__ Va,
-          float* __restrict__ DZ, float* __restrict__ dWatch, float* __restrict__ dSP, float* __restrict__ dVa,
-          float* __restrict__ dVab, int L) {
+          float* __restrict__ DZ, float* __restrict__ dSP, float* __restrict__ dVa, float* __restrict__ dVab, int L) {
   const int b = blockIdx.y, l0 = blockIdx.x * kDzPix, c = threadIdx.x * 4;
   const float4 va = ldg4(Va + c);
   float4 sp = make4(0.f), dv = make4(0.f);
   float sde = 0.f;
-  for (int l = l0; l < min(L, l0 + kDzPix); ++l) {
-    const size_t row = (size_t)b * L + l;
-    const float d = de[row];
-    const float4 t = ldg4(TANH + row * kNA + c);
+  float4 t[kDzPix]; float d[kDzPix];
+#pragma unroll
+  for (int j = 0; j < kDzPix; ++j) {          // all loads in flight before the first use
+    const bool ok = l0 + j < L;
+    const size_t row = (size_t)b * L + (ok ? l0 + j : l0);
+    d[j] = ok ? de[row] : 0.f;
+    t[j] = ldg4(TANH + row * kNA + c);
+  }
+#pragma unroll
+  for (int j = 0; j < kDzPix; ++j) {
+    if (l0 + j >= L) break;
+    const size_t row = (size_t)b * L + l0 + j;
     float4 z;
-    z.x = d * va.x * (1.f - t.x * t.x); z.y = d * va.y * (1.f - t.y * t.y);
-    z.z = d * va.z * (1.f - t.z * t.z); z.w = d * va.w * (1.f - t.w * t.w);
+    z.x = d[j] * va.x * (1.f - t[j].x * t[j].x); z.y = d[j] * va.y * (1.f - t[j].y * t[j].y);
+    z.z = d[j] * va.z * (1.f - t[j].z * t[j].z); z.w = d[j] * va.w * (1.f - t[j].w * t[j].w);
     *reinterpret_cast<float4*>(DZ + row * kNA + c) = z;
-    float4 wv = *reinterpret_cast<float4*>(dWatch + row * kNA + c);
-    wv.x += z.x; wv.y += z.y; wv.z += z.z; wv.w += z.w;
-    *reinterpret_cast<float4*>(dWatch + row * kNA + c) = wv;
     sp.x += z.x; sp.y += z.y; sp.z += z.z; sp.w += z.w;
-    dv.x = fmaf(d, t.x, dv.x); dv.y = fmaf(d, t.y, dv.y); dv.z = fmaf(d, t.z, dv.z); dv.w = fmaf(d, t.w, dv.w);
-    sde += d;
+    dv.x = fmaf(d[j], t[j].x, dv.x); dv.y = fmaf(d[j], t[j].y, dv.y); dv.z = fmaf(d[j], t[j].z, dv.z); dv.w = fmaf(d[j], t[j].w, dv.w);
+    sde += d[j];
   }
   float* s = dSP + (size_t)b * kNA + c;
   atomicAdd(s, sp.x); atomicAdd(s + 1, sp.y); atomicAdd(s + 2, sp.z); atomicAdd(s + 3, sp.w);
   atomicAdd(dVa + c, dv.x); atomicAdd(dVa + c + 1, dv.y); atomicAdd(dVa + c + 2, dv.z); atomicAdd(dVa + c + 3, dv.w);
   if (threadIdx.x == 0) atomicAdd(dVab, sde);
 }
-// dAP_out[b,l'] = dalpha_total... transposed 11x11 stencil:  dAP_out = dAP_in + sum_tap DF[b, l'-off(tap), tap]
+// dWatch[i] = sum_t DZ[t][i]   (one pass after the scan instead of a read-modify-write of dWatch every step)
 __global__ void __launch_bounds__(256)
+sum_steps_kernel(const float* __restrict__ DZ, float* __restrict__ out, int T, size_t n4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 acc = make4(0.f);
+  int t = 0;
+  for (; t + 8 <= T; t += 8) {
+    float4 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = ldg4(DZ + ((size_t)(t + j) * n4 + i) * 4);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc.x += v[j].x; acc.y += v[j].y; acc.z += v[j].z; acc.w += v[j].w; }
+  }
+  for (; t < T; ++t) { const float4 v = ldg4(DZ + ((size_t)t * n4 + i) * 4); acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w; }
+  *reinterpret_cast<float4*>(out + i * 4) = acc;
+}
+// dAP_out[b,l'] = dAP_in[b,l'] + sum_tap DF[b, l'-off(tap), tap]   (transposed 11x11 stencil).  One CTA = 32 consecutive
+// positions x 16 warps; warp w sums taps w, w+16, ... (8 independent loads per thread), then a 16-way smem reduction.
+constexpr int kGatherWarps = 16;
+__global__ void __launch_bounds__(32 * kGatherWarps)
 cov_bwd_gather_kernel(const float* __restrict__ DF, const float* __restrict__ dAP_in, float* __restrict__ dAP_out,
                       int Bn, int H, int W, int tap_major) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Bn * H * W) return;
-  const int x = i % W, t = i / W, y = t % H, b = t / H;
-  float s = dAP_in[i];
-  for (int tap = 0; tap < kCovTaps; ++tap) {
-    const int dy = tap / kCovK - kCovK / 2, dx = tap % kCovK - kCovK / 2;
-    const int ys = y - dy, xs = x - dx;     // source position l with l + off(tap) = l'
-    if ((unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W) {
-      const size_t src = (size_t)(b * H + ys) * W + xs;
-      s += tap_major ? DF[(size_t)tap * Bn * H * W + src] : DF[src * 124 + tap];   // tap-major: coalesced across x
+  __shared__ float part[kGatherWarps][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + lane, n = Bn * H * W;
+  float s = 0.f;
+  if (i < n) {
+    const int x = i % W, t = i / W, y = t % H, b = t / H;
+    constexpr int kIt = (kCovTaps + kGatherWarps - 1) / kGatherWarps;
+    float v[kIt];
+#pragma unroll
+    for (int j = 0; j < kIt; ++j) {
+      const int tap = warp + j * kGatherWarps;
+      const int dy = tap / kCovK - kCovK / 2, dx = tap % kCovK - kCovK / 2;
+      const int ys = y - dy, xs = x - dx;     // source position l with l + off(tap) = l'
+      const bool ok = tap < kCovTaps && (unsigned)ys < (unsigned)H && (unsigned)xs < (unsigned)W;
+      const size_t src = (size_t)(b * H + (ok ? ys : 0)) * W + (ok ? xs : 0);
+      const float val = tap_major ? DF[(size_t)(ok ? tap : 0) * n + src] : DF[src * 124 + (ok ? tap : 0)];   // tap-major: coalesced across x
+      v[j] = ok ? val : 0.f;
     }
+#pragma unroll
+    for (int j = 0; j < kIt; ++j) s += v[j];
   }
-  dAP_out[i] = s;
+  part[warp][lane] = s;
+  __syncthreads();
+  if (warp == 0 && i < n) {
+    float a = dAP_in[i];
+#pragma unroll
+    for (int k = 0; k < kGatherWarps; ++k) a += part[k][lane];
+    dAP_out[i] = a;
+  }
 }
 // d ann[b,l,c] += sum_t alpha[t,b,l] * dctx[t,b,c]
 __global__ void __launch_bounds__(256)
@@ -430,7 +473,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_LAUNCH_CHECK();
   wo_bwd_weight_kernel<<<cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, st>>>(W.MO, W.LO, g + P.Wo, g + P.bo, TB);
   WAP_LAUNCH_CHECK();
-  maxout_drop_bwd_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.dMO, W.dLG, TB, dropout, seed);
+  maxout_drop_bwd_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.dMO, W.dLG, TB, dropout, seed, g_seed_src);
   WAP_LAUNCH_CHECK();
   WAP_TRY(gemm_tn_atomic(st, W.H + (size_t)B * kN, kN, W.dLG, kMw, g + P.Wh, kMw, kN, kMw, TB));
   WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dLG, kMw, g + P.Wc, kMw, kD, kMw, TB));
@@ -444,7 +487,6 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   // ---- BPTT
   WAP_CHECK(cudaMemsetAsync(W.dh0, 0, sizeof(float) * B * kN, st));
   WAP_CHECK(cudaMemsetAsync(W.dAP0, 0, sizeof(float) * B * L, st));
-  WAP_CHECK(cudaMemsetAsync(W.dWatch, 0, sizeof(float) * B * L * kNA, st));
   WAP_CHECK(cudaMemsetAsync(W.dSP, 0, sizeof(float) * TB * kNA, st));
   float* dh_in = W.dh0; float* dh_out = W.dh1; float* dAP_in = W.dAP0; float* dAP_out = W.dAP1;
   for (int t = T - 1; t >= 0; --t) {
@@ -471,7 +513,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     softmax_bwd_kernel<<<B, 256, 0, st>>>(W.ALPHA + r * L, W.dalpha, W.de, L);
     WAP_LAUNCH_CHECK();
     float* DZt = W.DZ + r * L * kNA;
-    dz_kernel<<<dim3(cdiv(L, kDzPix), B), 128, 0, st>>>(W.TANH + r * L * kNA, W.de, p + P.V_a, DZt, W.dWatch, W.dSP + r * kNA,
+    dz_kernel<<<dim3(cdiv(L, kDzPix), B), 128, 0, st>>>(W.TANH + r * L * kNA, W.de, p + P.V_a, DZt, W.dSP + r * kNA,
                                                          g + P.V_a, g + P.V_a_b, L);
     WAP_LAUNCH_CHECK();
     {   // dpre_h += dSP*W_a^T
@@ -482,7 +524,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     // coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
     if (tc) WAP_TRY(tc_gemm(st, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
     else WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
-    cov_bwd_gather_kernel<<<cdiv(B * L, 256), 256, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0);
+    cov_bwd_gather_kernel<<<cdiv(B * L, 32), 32 * kGatherWarps, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0);
     WAP_LAUNCH_CHECK();
     gru1_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
                                                         W.dG1 + r * 2 * kN, W.dEh + r * kN, W.dUH + r * kN, dh_out, B);
@@ -531,7 +573,9 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     WAP_TRY(gemm_nt(st, W.dQf, kNA, p + P.U_f, kNA, g + P.Q, kNA, kCovTaps, kNA, kNA, nullptr, true));
     WAP_TRY(gemm_tn_atomic(st, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
   }
-  // watch path: dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
+  // watch path: dWatch = sum_t DZ_t ; dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
+  sum_steps_kernel<<<cdiv((size_t)B * L * kNA / 4, 256), 256, 0, st>>>(W.DZ, W.dWatch, T, (size_t)B * L * kNA / 4);
+  WAP_LAUNCH_CHECK();
   WAP_TRY(gemm_tn_atomic(st, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));
   if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));

@@ -139,6 +139,7 @@ struct BnActArgs {
   const float* gamma; const float* beta;
   float* saved;                              // [2][kMaxBnC]: mean, invstd (training) or null
   int training, dropout; uint32_t seed, site;
+  const uint32_t* seed_src;                  // non-null: the seed is read from device memory (CUDA-graph replay with a fresh seed)
   int round_tf32;                            // round the stored activation to TF32 (RNA): operand of a tcgen05 conv
 };
 
@@ -181,6 +182,7 @@ __device__ __forceinline__ float bn_relu_drop(float v, float sc, float sh, bool 
 // POOL: 0 none, 1 max 2x2 SAME, 2 avg 2x2 SAME (valid-count divisor)
 template <int POOL>
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
+  const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
   __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
   bn_prologue(a, s_scale, s_shift);
   __syncthreads();
@@ -195,7 +197,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
       const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
       for (int j = 0; j < 4; ++j)
-        r[j] = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, a.seed, a.site, (uint32_t)(po * a.C + c + j));
+        r[j] = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, seed, a.site, (uint32_t)(po * a.C + c + j));
     } else {
       const int xo = (int)(po % a.Wo); const size_t t = po / a.Wo; const int yo = (int)(t % a.Ho); const int b = (int)(t / a.Ho);
 #pragma unroll
@@ -212,7 +214,7 @@ __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
             const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float y = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, a.seed, a.site, (uint32_t)(pi * a.C + c + j));
+              const float y = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, seed, a.site, (uint32_t)(pi * a.C + c + j));
               r[j] = (POOL == 1) ? fmaxf(r[j], y) : r[j] + y;
             }
             ++cnt;
@@ -244,11 +246,13 @@ struct BnBwdArgs {
   double* red;                               // [2][C]: sum g, sum g*xhat
   float* dgamma; float* dbeta;               // += (pass 2)
   int dropout; uint32_t seed, site;
+  const uint32_t* seed_src;
   int round_tf32;                            // round d raw to TF32 (operand of the tcgen05 dgrad)
 };
 
 template <int POOL>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, const int pix_per_cta) {
+  const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
   __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC];
   __shared__ float s_sg[kMaxBnC], s_sgx[kMaxBnC];
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
@@ -313,7 +317,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, c
       for (int j = 0; j < 4; ++j) {
         const float pre = fmaf(vv[j], s_scale[c + j], s_shift[c + j]);
         float gj = (pre > 0.f) ? up[j] : 0.f;
-        if (a.dropout) gj = drop_keep(a.seed, a.site, (uint32_t)(p * a.C + c + j)) ? gj * (1.f / (1.f - kDropRate)) : 0.f;
+        if (a.dropout) gj = drop_keep(seed, a.site, (uint32_t)(p * a.C + c + j)) ? gj * (1.f / (1.f - kDropRate)) : 0.f;
         gg[j] = gj;
         sg[j] += gj;
         sgx[j] = fmaf(gj, (vv[j] - s_mean[c + j]) * s_inv[c + j], sgx[j]);
@@ -403,13 +407,14 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
 static int g_conv_precision = 0;          // 0: fp32 FFMA   1: TF32 tcgen05 (single pass, RNA-rounded operands)   2: 3xTF32 tcgen05 (fp32-grade)
 int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
 int g_tc_debug_mask = 0xFF;               // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd
+const uint32_t* g_seed_src = nullptr;     // wap_set_dropout_seed_source(): device word holding the dropout seed (overrides the by-value seed)
 void set_conv_precision(int mode) { g_conv_precision = mode; }
 int get_conv_precision() { return g_conv_precision; }
 
 static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, const EncWorkspace& ws, bool with_bwd) {
   static bool uploaded = false;
   const ParamLayout& L = layout();
-  WPrepLayer h[kNumConv];
+  static WPrepLayer h[kNumConv];   // static: a captured CUDA graph re-reads this host table at every replay
   for (int i = 0; i < kNumConv; ++i) {
     h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout;
     h[i].w = (long long)L.conv[i].w; h[i].f = (long long)ws.wt_fwd[i]; h[i].b = (long long)ws.wt_bwd[i];
@@ -483,7 +488,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
     a.mmean = moving + c.mmean; a.mvar = moving + c.mvar;
     a.gamma = params + c.gamma; a.beta = params + c.beta;
     a.saved = training ? saved + (size_t)k * 2 * kMaxBnC : nullptr;
-    a.training = training; a.dropout = (training && dropout && drop) ? 1 : 0; a.seed = seed; a.site = (uint32_t)k;
+    a.training = training; a.dropout = (training && dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = g_seed_src; a.site = (uint32_t)k;
     a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;
   };
@@ -573,7 +578,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
     a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
     a.g = gbuf; a.ld_g = ld_g; a.red = red; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
-    a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.site = (uint32_t)k;
+    a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = g_seed_src; a.site = (uint32_t)k;
     a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;
   };

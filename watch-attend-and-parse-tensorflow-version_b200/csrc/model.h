@@ -73,4 +73,5 @@ struct EncWorkspace {
 };
 EncWorkspace make_enc_workspace(const EncGeom& g, bool training);
 
+extern const uint32_t* g_seed_src;   // device word overriding the by-value dropout seed (null: by-value)
 }  // namespace wap

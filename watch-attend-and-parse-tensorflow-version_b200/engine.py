@@ -133,6 +133,12 @@ class WAPEngine:
         self._cost = torch.zeros(2, dtype=torch.float64, device=self.device)   # [CE cost, L2 cost]
         self.step_count = 0
         self.dropout_seed = 1234
+        # CUDA-graph replay of forward+backward per (shapes, dropout, precision): removes the launch gaps between the ~1700 kernels of a step
+        self.use_graphs = False
+        self.max_graphs = 16
+        self._graphs: Dict[tuple, tuple] = {}
+        self._seed_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.replayed_launches = 0
         self.world_size = 1
         self.launches_last_step = 0
 
@@ -180,6 +186,7 @@ class WAPEngine:
         ws = self._buf(("enc", B, H, W, bool(training)), self.L.wap_encoder_workspace_floats(B, H, W, int(training)))
         ann = torch.empty((B, h, w, ANNOT_C), dtype=torch.float32, device=self.device)
         sd = self.dropout_seed if seed is None else seed
+        self.L.wap_set_dropout_seed_source(None)
         _lib.check(self.L.wap_encoder_forward(_stream(), _p(self.P.flat), _p(self.P.moving), _p(x), B, H, W, int(training),
                                               int(bool(dropout) and bool(training)), C.c_uint32(sd & 0xFFFFFFFF), _p(ann), _p(ws)),
                    "wap_encoder_forward")
@@ -226,6 +233,60 @@ class WAPEngine:
                                            _p(h_pre), _p(alpha_past_pre), _p(probs), _p(word), _p(h_new), _p(ap_new), _p(ws)),
                    "wap_decoder_step")
         return probs, word, h_new, ap_new
+
+    def get_context(self, annotation4ctx, h_t_1, alpha_past4ctx, a_mask=None, watch=None, qf=None):
+        """Attender.get_context (S:166-206) -> (context [B,684], alpha [B,h,w], alpha_past' [B,h,w])."""
+        B, h, w, _ = annotation4ctx.shape
+        if watch is None or qf is None:
+            watch, _, qf = self.precompute(annotation4ctx)
+        h_t_1 = self._dev(h_t_1, torch.float32); ap = self._dev(alpha_past4ctx, torch.float32)
+        am = self._dev(a_mask, torch.float32) if a_mask is not None else None
+        ctx = torch.empty((B, ANNOT_C), dtype=torch.float32, device=self.device)
+        alpha = torch.empty((B, h, w), dtype=torch.float32, device=self.device); ap_new = torch.empty_like(alpha)
+        ws = self._buf(("step", B, h, w), self.L.wap_decoder_step_workspace_floats(B, h, w))
+        _lib.check(self.L.wap_get_context(_stream(), _p(self.P.flat), _p(annotation4ctx), _p(watch), _p(qf), _p(am), B, h, w, _p(h_t_1), _p(ap),
+                                          _p(ctx), _p(alpha), _p(ap_new), _p(ws)), "wap_get_context")
+        return ctx, alpha, ap_new
+
+    def one_time_step(self, carry, emb_mask, watch=None, qf=None):
+        """Parser.one_time_step (S:260-308): carry = (h, ctx, alpha, alpha_past, annotation, a_mask), emb_mask = (emb_y, y_mask)
+        -> the same 6-tuple for the next step (tf.scan body of get_ht_ctx, S:246-255)."""
+        h_prev, _, _, ap, ann, a_mask = carry
+        emb_y, y_mask = emb_mask
+        B, h, w, _ = ann.shape
+        if watch is None or qf is None:
+            watch, _, qf = self.precompute(ann)
+        emb_y = self._dev(emb_y, torch.float32); h_prev = self._dev(h_prev, torch.float32); ap = self._dev(ap, torch.float32)
+        am = self._dev(a_mask, torch.float32) if a_mask is not None else None
+        ym = self._dev(y_mask, torch.float32) if y_mask is not None else None
+        h_new = torch.empty((B, DIM_DEC), dtype=torch.float32, device=self.device)
+        ctx = torch.empty((B, ANNOT_C), dtype=torch.float32, device=self.device)
+        alpha = torch.empty((B, h, w), dtype=torch.float32, device=self.device); ap_new = torch.empty_like(alpha)
+        ws = self._buf(("step", B, h, w), self.L.wap_decoder_step_workspace_floats(B, h, w))
+        _lib.check(self.L.wap_one_time_step(_stream(), _p(self.P.flat), _p(ann), _p(watch), _p(qf), _p(am), _p(ym), B, h, w, _p(emb_y), _p(h_prev),
+                                            _p(ap), _p(h_new), _p(ctx), _p(alpha), _p(ap_new), _p(ws)), "wap_one_time_step")
+        return h_new, ctx, alpha, ap_new, ann, a_mask
+
+    # ------------------------------------------------------------------ checkpoint (the reference has none that fires: SURVEY 5)
+    def save(self, path: str) -> None:
+        """.npz keyed by the TF variable names (+ '__opt__/accum/<name>', '__opt__/accum_update/<name>', '__step__')."""
+        out = dict(self.P.state_dict())
+        for k, v in self.P.unpack(self.accum).items():
+            out["__opt__/accum/" + k] = v
+        for k, v in self.P.unpack(self.accum_update).items():
+            out["__opt__/accum_update/" + k] = v
+        out["__step__"] = np.array(self.step_count)
+        np.savez(path, **out)
+
+    def load(self, path: str) -> None:
+        z = np.load(path)
+        self.P.load({k: z[k] for k in self.P.names()})
+        acc = {k[len("__opt__/accum/"):]: z[k] for k in z.files if k.startswith("__opt__/accum/")}
+        accu = {k[len("__opt__/accum_update/"):]: z[k] for k in z.files if k.startswith("__opt__/accum_update/")}
+        if acc:
+            self.P.pack_into(self.accum, acc); self.P.pack_into(self.accum_update, accu)
+        if "__step__" in z.files:
+            self.step_count = int(z["__step__"])
 
     def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8, persistent: Optional[bool] = None,
                       ignore_eol: bool = False):
@@ -303,18 +364,51 @@ class WAPEngine:
         T = y.shape[0]
         ws = self._buf(("dec", B, h, w, T), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
         sd = self.dropout_seed if seed is None else seed
+        self.L.wap_set_dropout_seed_source(None)
         _lib.check(self.L.wap_decoder_train_forward(_stream(), _p(self.P.flat), _p(annotation), _p(a_mask), _p(y), _p(y_mask), B, h, w, T,
                                                     int(dropout), C.c_uint32(sd & 0xFFFFFFFF), _p(self._cost), _p(ws)),
                    "wap_decoder_train_forward")
         return self._cost[0]
 
     def forward_backward(self, x, y, x_mask, y_mask, dropout: bool = True, seed: Optional[int] = None):
-        """Forward + backward of cost (no L2 term, no update): fills self.grads; returns device cost."""
-        x = self._dev(x, torch.float32); x_mask = self._dev(x_mask, torch.float32)
-        y = self._dev(y, torch.int32); y_mask = self._dev(y_mask, torch.float32)
+        """Forward + backward of cost (no L2 term, no update): fills self.grads; returns device cost.
+        With self.use_graphs the launch sequence is captured once per (shapes, dropout, precision) into a CUDA graph and
+        replayed afterwards; the dropout seed then travels through device memory (wap_set_dropout_seed_source)."""
+        sd = (self.dropout_seed + 7919 * self.step_count) if seed is None else seed
+        if not self.use_graphs:
+            self.L.wap_set_dropout_seed_source(None)
+            return self._forward_backward(self._dev(x, torch.float32), self._dev(y, torch.int32), self._dev(x_mask, torch.float32),
+                                          self._dev(y_mask, torch.float32), dropout, sd)
+        key = (tuple(x.shape), tuple(y.shape), bool(dropout), self.L.wap_get_conv_precision())
+        ent = self._graphs.get(key)
+        fresh = ent is None
+        if fresh:
+            mk = lambda a, dt: torch.empty(tuple(a.shape), dtype=dt, device=self.device)     # noqa: E731
+            ent = [None, mk(x, torch.float32), mk(y, torch.int32), mk(x_mask, torch.float32), mk(y_mask, torch.float32), 0]
+        _, sx, sy, sxm, sym, _ = ent
+        for dst, src in ((sx, x), (sy, y), (sxm, x_mask), (sym, y_mask)):
+            dst.copy_(src if isinstance(src, torch.Tensor) else torch.as_tensor(np.ascontiguousarray(src)), non_blocking=True)
+        self._seed_dev.fill_(int(np.array(sd & 0xFFFFFFFF, dtype=np.uint32).astype(np.int32)))
+        self.L.wap_set_dropout_seed_source(_p(self._seed_dev))
+        if not fresh:
+            ent[0].replay()
+            self.replayed_launches += ent[5]
+            return self._cost[0]
+        self._forward_backward(sx, sy, sxm, sym, dropout, sd)          # this step, eagerly (also sizes every workspace)
+        torch.cuda.current_stream().synchronize()
+        n0 = self.L.wap_launch_count()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):                                       # capture only: nothing runs, self.grads/_cost keep this step's values
+            self._forward_backward(sx, sy, sxm, sym, dropout, sd)
+        ent[0], ent[5] = g, int(self.L.wap_launch_count() - n0)
+        if len(self._graphs) >= self.max_graphs:
+            self._graphs.pop(next(iter(self._graphs)))
+        self._graphs[key] = ent
+        return self._cost[0]
+
+    def _forward_backward(self, x, y, x_mask, y_mask, dropout, sd):
         B, H, W = x.shape[0], x.shape[1], x.shape[2]
         T = y.shape[0]
-        sd = (self.dropout_seed + 7919 * self.step_count) if seed is None else seed
         sd_c = C.c_uint32(sd & 0xFFFFFFFF)
         h, w = self.annotation_hw(H, W)
         st = _stream()
@@ -333,6 +427,10 @@ class WAPEngine:
         _lib.check(self.L.wap_encoder_backward(st, _p(self.P.flat), _p(self.grads), _p(x), B, H, W, int(dropout), sd_c, _p(ann), _p(d_ann), _p(ews)),
                    "wap_encoder_backward")
         return self._cost[0]
+
+    def launch_count(self) -> int:
+        """Kernels launched by the library so far, including those replayed from captured graphs."""
+        return int(self.L.wap_launch_count()) + self.replayed_launches
 
     def apply_update(self, lr: float) -> torch.Tensor:
         """L2 (S:594-598) + Adadelta (S:602-607) on the flat buffers; returns device L2 cost."""
@@ -380,6 +478,9 @@ class Attender:
         self.coverage_kernel = [11, 11]
         self.engine = engine
 
+    def get_context(self, annotation4ctx, h_t_1, alpha_past4ctx, a_mask):
+        return self.engine.get_context(annotation4ctx, h_t_1, alpha_past4ctx, a_mask)
+
 
 class Parser:
     def __init__(self, hidden_dim, word_dim, attender, context_dim, engine: Optional[WAPEngine] = None):
@@ -387,6 +488,21 @@ class Parser:
             raise ValueError("Parser is specialised for (256, 256, 684) (S:586)")
         self.attender, self.hidden_dim, self.word_dim, self.context_dim = attender, hidden_dim, word_dim, context_dim
         self.engine = engine or attender.engine
+
+    def one_time_step(self, tuple_h0_ctx_alpha_alpha_past_annotation, tuple_emb_mask):
+        return self.engine.one_time_step(tuple_h0_ctx_alpha_alpha_past_annotation, tuple_emb_mask)
+
+    def get_ht_ctx(self, emb_y, target_hidden_state_0, annotations, a_m, y_m):
+        """tf.scan over one_time_step (S:246-255): returns the stacked (h, ctx, alpha, alpha_past) of every step."""
+        B, h, w, _ = annotations.shape
+        watch, _, qf = self.engine.precompute(annotations)
+        dev = self.engine.device
+        carry = (target_hidden_state_0, None, None, torch.zeros((B, h, w), device=dev), annotations, a_m)
+        hs, cs, als, aps = [], [], [], []
+        for t in range(emb_y.shape[0]):
+            carry = self.engine.one_time_step(carry, (emb_y[t], y_m[t] if y_m is not None else None), watch, qf)
+            hs.append(carry[0]); cs.append(carry[1]); als.append(carry[2]); aps.append(carry[3])
+        return torch.stack(hs), torch.stack(cs), torch.stack(als), torch.stack(aps), annotations, a_m
 
 
 class WAP:
