@@ -171,6 +171,11 @@ int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int
  * the by-value behaviour.  Library-global. */
 int wap_set_dropout_seed_source(const uint32_t* seed_dev);
 
+/* ---- programmatic dependent launch (default on): kernels are launched with the programmatic-stream-serialization
+ * attribute so that launch latency overlaps the predecessor's execution; 0 restores plain stream ordering. */
+int wap_set_pdl(int on);
+int wap_get_pdl(void);
+
 /* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);
 /* byte offsets (in floats) of selected encoder-workspace regions, for tests: what = 0 stem_raw,

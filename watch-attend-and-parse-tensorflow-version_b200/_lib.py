@@ -62,6 +62,8 @@ SIGNATURES = {
     "wap_tc_wgrad_1x1": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i]),
     "wap_tc_wgrad_3x3": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i]),
     "wap_set_dropout_seed_source": (_i, [_vp]),
+    "wap_set_pdl": (_i, [_i]),
+    "wap_get_pdl": (_i, []),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),
     "wap_encoder_workspace_offset": (_i64, [_i, _i, _i, _i, _i, _i]),
 }

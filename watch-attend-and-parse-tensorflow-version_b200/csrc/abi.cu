@@ -12,6 +12,7 @@ namespace wap {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
+int g_pdl = 1;
 
 // ---- per-class device timing
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
@@ -256,6 +257,8 @@ int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }
+int wap_set_pdl(int on) { wap::g_pdl = on ? 1 : 0; return 0; }
+int wap_get_pdl(void) { return wap::g_pdl; }
 int wap_set_dropout_seed_source(const uint32_t* seed_dev) { wap::g_seed_src = seed_dev; return 0; }
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
   return dropout_mask(ST(stream), seed, site, (size_t)n, mask);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <utility>
 
 namespace wap {
 
@@ -20,6 +21,28 @@ void set_error(const char* fmt, ...);          // abi.cu (thread-local message)
 extern unsigned long long g_launches;          // abi.cu: kernels launched by this library (cumulative)
 #define WAP_LAUNCH_CHECK()                                                           \
   do { ++::wap::g_launches; WAP_CHECK(cudaGetLastError()); } while (0)
+
+// ---------------------------------------------------------------- programmatic dependent launch (PDL)
+// A training step is ~1700 short dependent kernels; with the programmatic-stream-serialization attribute the next kernel's
+// grid is scheduled as soon as every CTA of the current one has executed pdl_sync(), so its launch latency and CTA
+// start-up overlap the current kernel's execution.  Every kernel of this library calls pdl_sync() first:
+// griddepcontrol.wait returns when the preceding grids have completed and their writes are visible (immediately when the
+// kernel was launched without the attribute), and launch_dependents then lets the successor start queueing.
+extern int g_pdl;                              // abi.cu: wap_set_pdl()
+__device__ __forceinline__ void pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 // optional per-launch-class device timing (cudaEvents on the launching stream); see wap_profile_*()
 enum ProfClass {

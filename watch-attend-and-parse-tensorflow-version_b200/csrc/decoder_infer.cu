@@ -10,6 +10,7 @@ namespace wap {
 // mean over positions (masked, S:345; unmasked, S:590)
 __global__ void __launch_bounds__(256)
 ann_mean_kernel(const float* __restrict__ ann, const float* __restrict__ a_mask, float* __restrict__ mean, int L) {
+  pdl_sync();
   extern __shared__ float sm[];          // w[L] | red[64] | part[16][64]
   float* s_w = sm; float* red = sm + ((L + 3) & ~3); float* part = red + 64;
   const int b = blockIdx.y, tid = threadIdx.x;
@@ -37,6 +38,7 @@ ann_mean_kernel(const float* __restrict__ ann, const float* __restrict__ a_mask,
 }
 
 __global__ void tanh_inplace_kernel(float* x, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) x[i] = tanhf(x[i]);
 }
@@ -53,14 +55,14 @@ int attn_precompute(cudaStream_t st, const float* params, const float* ann, cons
   if (h0 != nullptr) {
     const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
     WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large: L=%d", L);
-    ann_mean_kernel<<<dim3(cdiv(kD, 64), B), 256, smem, st>>>(ann, a_mask, mean_scratch, L);
+    WAP_CHECK(launch_pdl(ann_mean_kernel, dim3(cdiv(kD, 64), B), 256, smem, st, ann, a_mask, mean_scratch, L));
     WAP_LAUNCH_CHECK();
     FillArgs f; f.rows = B; f.nseg = 1; f.seg[0] = {h0, kN, kN, params + P.ba2h};
     WAP_TRY(fill_rows(st, f));
     SkinnyArgs a; a.X = mean_scratch; a.ldx = kD; a.ids = nullptr; a.Bn = B; a.K = kD; a.nseg = 1;
     a.seg[0] = {params + P.Wa2h, kN, kN, h0, kN};
     WAP_TRY(skinny_gemm(st, a));
-    tanh_inplace_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(h0, B * kN);
+    WAP_CHECK(launch_pdl(tanh_inplace_kernel, cdiv(B * kN, 256), 256, 0, st, h0, B * kN));
     WAP_LAUNCH_CHECK();
   }
   return 0;
@@ -68,10 +70,12 @@ int attn_precompute(cudaStream_t st, const float* params, const float* ann, cons
 
 // ------------------------------------------------------------------------------------ head
 __global__ void lg_init_kernel(float* LG, int Bn, const float* by, const float* bc, const float* bh) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Bn * kMw) { const int j = i % kMw; LG[i] = by[j] + bc[j] + bh[j]; }
 }
 __global__ void maxout_kernel(const float* __restrict__ LG, float* __restrict__ MO, int rows) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * (kMw / 2)) {
     const float2 v = *reinterpret_cast<const float2*>(LG + 2 * (size_t)i);
@@ -81,6 +85,7 @@ __global__ void maxout_kernel(const float* __restrict__ LG, float* __restrict__ 
 // softmax over 111 logits (one warp per row) + first-index argmax
 __global__ void __launch_bounds__(256)
 softmax_argmax_kernel(const float* __restrict__ LO, float* __restrict__ probs, int* __restrict__ word, int rows) {
+  pdl_sync();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   const float* lo = LO + (size_t)r * kVocab;
@@ -138,7 +143,7 @@ int decoder_word_step(cudaStream_t st, const float* params, const float* ann, co
     f.seg[1] = {s.G1 + 2 * kN, 3 * kN, kN, params + P.b_yh};
     f.seg[2] = {s.LO, kVocab, kVocab, params + P.bo};
     WAP_TRY(fill_rows(st, f));
-    lg_init_kernel<<<cdiv(Bn * kMw, 256), 256, 0, st>>>(s.LG, Bn, params + P.by, params + P.bc, params + P.bh);
+    WAP_CHECK(launch_pdl(lg_init_kernel, cdiv(Bn * kMw, 256), 256, 0, st, s.LG, Bn, params + P.by, params + P.bc, params + P.bh));
     WAP_LAUNCH_CHECK();
     SkinnyArgs a; a.X = params + P.embed; a.ldx = kMw; a.ids = y; a.Bn = Bn; a.K = kMw; a.nseg = 3;
     a.seg[0] = {params + P.W_yz_yr, 2 * kN, 2 * kN, s.G1, 3 * kN};
@@ -158,12 +163,12 @@ int decoder_word_step(cudaStream_t st, const float* params, const float* ann, co
     SkinnyArgs a; a.X = h_new; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 1;
     a.seg[0] = {params + P.Wh, kMw, kMw, s.LG, kMw};
     WAP_TRY(skinny_gemm(st, a));
-    maxout_kernel<<<cdiv(Bn * kMw / 2, 256), 256, 0, st>>>(s.LG, s.MO, Bn);
+    WAP_CHECK(launch_pdl(maxout_kernel, cdiv(Bn * kMw / 2, 256), 256, 0, st, s.LG, s.MO, Bn));
     WAP_LAUNCH_CHECK();
     SkinnyArgs o; o.X = s.MO; o.ldx = kMw / 2; o.ids = nullptr; o.Bn = Bn; o.K = kMw / 2; o.nseg = 1;
     o.seg[0] = {params + P.Wo, kVocab, kVocab, s.LO, kVocab};
     WAP_TRY(skinny_gemm(st, o));
-    softmax_argmax_kernel<<<cdiv(Bn * 32, 256), 256, 0, st>>>(s.LO, probs, word, Bn);
+    WAP_CHECK(launch_pdl(softmax_argmax_kernel, cdiv(Bn * 32, 256), 256, 0, st, s.LO, probs, word, Bn));
     WAP_LAUNCH_CHECK();
   }
   return 0;
@@ -218,6 +223,7 @@ int attender_get_context(cudaStream_t st, const float* params, const float* ann,
 // written (including the terminating <eol>=0 if it was emitted).  state: y (next input id).
 __global__ void greedy_update_kernel(const int* __restrict__ word, int* __restrict__ y, int* __restrict__ tokens,
                                      int* __restrict__ lengths, int* __restrict__ alive, int Bn, int t, int maxlen) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= Bn) return;
   if (lengths[b] >= 0) return;                  // finished earlier (length fixed)
@@ -227,6 +233,7 @@ __global__ void greedy_update_kernel(const int* __restrict__ word, int* __restri
   if (wd == 0 || t == maxlen - 1) { lengths[b] = t + 1; atomicSub(alive, 1); }
 }
 __global__ void greedy_init_kernel(int* y, int* lengths, int* alive, int Bn) {
+  pdl_sync();
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < Bn) { y[b] = -1; lengths[b] = -1; }
   if (b == 0) *alive = Bn;
@@ -258,12 +265,12 @@ int greedy_decode(cudaStream_t st, const float* params, const float* ann, int Bn
   int *y = g.y, *word = g.word, *alive = g.alive;
   WAP_TRY(attn_precompute(st, params, ann, nullptr, Bn, h, w, watch, hA, qf, mean));   // hidden_state_0: unmasked (S:590)
   WAP_CHECK(cudaMemsetAsync(apA, 0, sizeof(float) * Bn * L, st));
-  greedy_init_kernel<<<cdiv(Bn, 128), 128, 0, st>>>(y, lengths, alive, Bn);
+  WAP_CHECK(launch_pdl(greedy_init_kernel, cdiv(Bn, 128), 128, 0, st, y, lengths, alive, Bn));
   WAP_LAUNCH_CHECK();
   int t = 0;
   for (; t < maxlen; ++t) {
     WAP_TRY(decoder_word_step(st, params, ann, watch, qf, nullptr, 0, Bn, h, w, y, hA, apA, nullptr, word, hB, apB, stepws));
-    greedy_update_kernel<<<cdiv(Bn, 128), 128, 0, st>>>(word, y, tokens, lengths, alive, Bn, t, maxlen);
+    WAP_CHECK(launch_pdl(greedy_update_kernel, cdiv(Bn, 128), 128, 0, st, word, y, tokens, lengths, alive, Bn, t, maxlen));
     WAP_LAUNCH_CHECK();
     std::swap(hA, hB); std::swap(apA, apB);
     if (check_every > 0 && ((t + 1) % check_every == 0)) {

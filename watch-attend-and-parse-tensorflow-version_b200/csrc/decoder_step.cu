@@ -8,6 +8,7 @@ namespace wap {
 // skinny GEMM
 // =====================================================================================
 __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
+  pdl_sync();
   __shared__ float xs[kSkRows][kSkKC];
   int s = 0;
   while (s + 1 < a.nseg && (int)blockIdx.x >= a.tile0[s + 1]) ++s;
@@ -71,7 +72,7 @@ int skinny_gemm(cudaStream_t st, SkinnyArgs a) {
   a.tile0[0] = 0;
   for (int s = 0; s < a.nseg; ++s) a.tile0[s + 1] = a.tile0[s] + cdiv(a.seg[s].N, kSkCols);
   dim3 grid(a.tile0[a.nseg], cdiv(a.K, kSkKC));
-  skinny_gemm_kernel<<<grid, 64, 0, st>>>(a);
+  WAP_CHECK(launch_pdl(skinny_gemm_kernel, grid, 64, 0, st, a));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -80,6 +81,7 @@ int skinny_gemm(cudaStream_t st, SkinnyArgs a) {
 // row-broadcast fill (bias initialisation of the atomically-accumulated outputs)
 // =====================================================================================
 __global__ void __launch_bounds__(256) fill_rows_kernel(const FillArgs a) {
+  pdl_sync();
   const FillSeg sg = a.seg[blockIdx.y];
   const int total = a.rows * sg.n;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -91,7 +93,7 @@ int fill_rows(cudaStream_t st, const FillArgs& a) {
   int mx = 1;
   for (int s = 0; s < a.nseg; ++s) mx = max(mx, a.rows * a.seg[s].n);
   dim3 grid(min(cdiv(mx, 256), 64), a.nseg);
-  fill_rows_kernel<<<grid, 256, 0, st>>>(a);
+  WAP_CHECK(launch_pdl(fill_rows_kernel, grid, 256, 0, st, a));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -103,6 +105,7 @@ int fill_rows(cudaStream_t st, const FillArgs& a) {
 __global__ void __launch_bounds__(256)
 gru1_gate_kernel(float* __restrict__ G1, const float* __restrict__ UH, const float* __restrict__ h_prev,
                  const float* __restrict__ y_mask, float* __restrict__ prop1, float* __restrict__ pre_h, int Bn) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * kN) return;
   const int b = i / kN, j = i - b * kN;
@@ -121,6 +124,7 @@ __global__ void __launch_bounds__(256)
 gru2_gate_kernel(float* __restrict__ G2, const float* __restrict__ PH2, const float* __restrict__ CH,
                  const float* __restrict__ pre_h, const float* __restrict__ y_mask,
                  float* __restrict__ prop2, float* __restrict__ h_new, int Bn) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * kN) return;
   const int b = i / kN, j = i - b * kN;
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(256)
 energy_kernel(const float* COV, const float* __restrict__ watch, const float* __restrict__ SP,
               const float* __restrict__ Va, const float* __restrict__ Vab, float* TANH,
               float* __restrict__ E, int Bn, int L, int shared) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= Bn * L) return;
   const int b = warp / L, l = warp - b * L;
@@ -174,6 +179,7 @@ __global__ void __launch_bounds__(256)
 softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask, const float* __restrict__ ap_in,
                    const float* __restrict__ ann, float* __restrict__ alpha, float* __restrict__ ap_out,
                    float* __restrict__ ctx, int L, int shared) {
+  pdl_sync();
   extern __shared__ float sm[];          // alpha[L] | red[64] | part[16][64]
   float* s_alpha = sm;
   float* red = sm + ((L + 3) & ~3);      // keep `part` 16-byte aligned for the float4 stores
@@ -223,6 +229,7 @@ softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask
 
 // Ppat[pos][tap (128, taps >= 121 zero)] = alpha_past[b, y + dy, x + dx]   (11x11 SAME patches, float4 per thread)
 __global__ void __launch_bounds__(256) cov_im2col_kernel(const float* __restrict__ ap, float* __restrict__ Ppat, int Bn, int H, int W) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * H * W * 32) return;
   const int pos = i >> 5, t4 = (i & 31) * 4;
@@ -237,6 +244,7 @@ __global__ void __launch_bounds__(256) cov_im2col_kernel(const float* __restrict
 }
 // Q'^T hi/lo [512][128] (taps >= 121 zero) for the tensor-core coverage GEMM
 __global__ void prep_qfT_kernel(const float* __restrict__ qf, float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= kNA * 128) return;
   const int c = i >> 7, tap = i & 127;
@@ -249,7 +257,7 @@ __global__ void prep_qfT_kernel(const float* __restrict__ qf, float* __restrict_
   lo[i] = __uint_as_float(u);
 }
 int prep_qfT(cudaStream_t st, const float* qf, float* hi, float* lo) {
-  prep_qfT_kernel<<<cdiv(kNA * 128, 256), 256, 0, st>>>(qf, hi, lo);
+  WAP_CHECK(launch_pdl(prep_qfT_kernel, cdiv(kNA * 128, 256), 256, 0, st, qf, hi, lo));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -258,12 +266,12 @@ int prep_qfT(cudaStream_t st, const float* qf, float* hi, float* lo) {
 int attention_tail(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* a_mask, int shared, int Bn, int L,
                    const float* SP, const float* ap_in, float* COV, float* TANH, float* E, float* alpha, float* ap_out, float* ctx) {
   const ParamLayout& P = layout();
-  energy_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(COV, watch, SP, p + P.V_a, p + P.V_a_b, TANH, E, Bn, L, shared);
+  WAP_CHECK(launch_pdl(energy_kernel, cdiv(Bn * L * 32, 256), 256, 0, st, COV, watch, SP, p + P.V_a, p + P.V_a_b, TANH, E, Bn, L, shared));
   WAP_LAUNCH_CHECK();
   const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
   WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large for softmax_ctx_kernel: L=%d", L);
   dim3 grid(cdiv(kD, kCtxChunk), Bn);
-  softmax_ctx_kernel<<<grid, 256, smem, st>>>(E, a_mask, ap_in, ann, alpha, ap_out, ctx, L, shared);
+  WAP_CHECK(launch_pdl(softmax_ctx_kernel, grid, 256, smem, st, E, a_mask, ap_in, ann, alpha, ap_out, ctx, L, shared));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -301,7 +309,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     a.seg[1] = {p + P.U_rh, kN, kN, c.UH, kN};
     WAP_TRY(skinny_gemm(st, a));
   }
-  gru1_gate_kernel<<<cdiv(Bn * kN, 256), 256, 0, st>>>(c.G1, c.UH, c.h_prev, c.y_mask, c.prop1, c.pre_h, Bn);
+  WAP_CHECK(launch_pdl(gru1_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, c.G1, c.UH, c.h_prev, c.y_mask, c.prop1, c.pre_h, Bn));
   WAP_LAUNCH_CHECK();
   {   // pre_h * [W_a | U_hz_hr_nl | U_rh_nl]
     SkinnyArgs a; a.X = c.pre_h; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 3;
@@ -311,7 +319,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     WAP_TRY(skinny_gemm(st, a));
   }
   if (c.tc_mode != 0) {   // coverage on tensor cores: im2col patches [Bn*L,128] x Q'^T[512][128]  (+ U_f_b)
-    cov_im2col_kernel<<<cdiv(Bn * L * 32, 256), 256, 0, st>>>(c.ap_in, c.Ppat, Bn, c.h, c.w);
+    WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, st, c.ap_in, c.Ppat, Bn, c.h, c.w));
     WAP_LAUNCH_CHECK();
     WAP_TRY(tc_gemm(st, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
                     TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
@@ -326,7 +334,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     if (c.has_extra_ctx) { a.seg[2] = c.extra_ctx; a.nseg = 3; }
     WAP_TRY(skinny_gemm(st, a));
   }
-  gru2_gate_kernel<<<cdiv(Bn * kN, 256), 256, 0, st>>>(c.G2, c.PH2, c.CH, c.pre_h, c.y_mask, c.prop2, c.h_new, Bn);
+  WAP_CHECK(launch_pdl(gru2_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, c.G2, c.PH2, c.CH, c.pre_h, c.y_mask, c.prop2, c.h_new, Bn));
   WAP_LAUNCH_CHECK();
   return 0;
 }

@@ -65,24 +65,28 @@ size_t decoder_train_ws_floats(int B, int L, int T) { size_t t; carve_train(null
 // ------------------------------------------------------------------------------------ small kernels
 // EMB[t,b,:] = t == 0 ? 0 : embed[y[t-1,b]]   (S:340-343)
 __global__ void emb_shift_kernel(const float* __restrict__ embed, const int* __restrict__ y, float* __restrict__ EMB, int T, int B) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * B * kMw) return;
   const int j = i % kMw, r = i / kMw, t = r / B;
   EMB[i] = (t == 0) ? 0.f : __ldg(embed + (size_t)y[r - B] * kMw + j);
 }
 __global__ void emb_scatter_kernel(const float* __restrict__ dEMB, const int* __restrict__ y, float* __restrict__ dembed, int T, int B) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= T * B * kMw) return;
   const int j = i % kMw, r = i / kMw, t = r / B;
   if (t > 0) atomicAdd(dembed + (size_t)y[r - B] * kMw + j, dEMB[i]);
 }
 __global__ void bias3_rows_kernel(float* LG, int rows, const float* by, const float* bc, const float* bh) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < rows * kMw) { const int j = i % kMw; LG[i] = by[j] + bc[j] + bh[j]; }
 }
 // maxout over adjacent pairs + dropout (site kNumConv) (S:359-362)
 __global__ void maxout_drop_kernel(const float* __restrict__ LG, float* __restrict__ MO, int rows, int dropout, uint32_t seed,
                                    const uint32_t* __restrict__ seed_src) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * (kMw / 2)) return;
   if (dropout && seed_src != nullptr) seed = __ldg(seed_src);
@@ -94,6 +98,7 @@ __global__ void maxout_drop_kernel(const float* __restrict__ LG, float* __restri
 __global__ void maxout_drop_bwd_kernel(const float* __restrict__ LG, const float* __restrict__ dMO, float* __restrict__ dLG,
                                        int rows, int dropout, uint32_t seed,
                                    const uint32_t* __restrict__ seed_src) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * (kMw / 2)) return;
   if (dropout && seed_src != nullptr) seed = __ldg(seed_src);
@@ -106,6 +111,7 @@ __global__ void maxout_drop_bwd_kernel(const float* __restrict__ LG, const float
 // LO[r,j] = bo[j] + sum_i MO[r,i] Wo[i,j]
 __global__ void wo_fwd_kernel(const float* __restrict__ MO, const float* __restrict__ Wo, const float* __restrict__ bo,
                               float* __restrict__ LO, int rows) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * kVocab) return;
   const int r = i / kVocab, j = i - r * kVocab;
@@ -116,6 +122,7 @@ __global__ void wo_fwd_kernel(const float* __restrict__ MO, const float* __restr
   LO[i] = s;
 }
 __global__ void wo_bwd_data_kernel(const float* __restrict__ dLO, const float* __restrict__ Wo, float* __restrict__ dMO, int rows) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * (kMw / 2)) return;
   const int r = i / (kMw / 2), k = i - r * (kMw / 2);
@@ -126,6 +133,7 @@ __global__ void wo_bwd_data_kernel(const float* __restrict__ dLO, const float* _
 }
 __global__ void wo_bwd_weight_kernel(const float* __restrict__ MO, const float* __restrict__ dLO, float* __restrict__ dWo,
                                      float* __restrict__ dbo, int rows) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (kMw / 2 + 1) * kVocab) return;
   const int k = i / kVocab, j = i - k * kVocab;
@@ -137,6 +145,7 @@ __global__ void wo_bwd_weight_kernel(const float* __restrict__ MO, const float* 
 __global__ void __launch_bounds__(256)
 ce_kernel(float* __restrict__ LO, const int* __restrict__ y, const float* __restrict__ y_mask, double* __restrict__ cost,
           int rows, int B, float grad_scale) {
+  pdl_sync();
   const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (r >= rows) return;
   float* lo = LO + (size_t)r * kVocab;
@@ -161,6 +170,7 @@ ce_kernel(float* __restrict__ LO, const int* __restrict__ y, const float* __rest
 }
 // column sums: out[j] += sum_r X[r*ld + j]
 __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X, int ld, int rows, int n, float* __restrict__ out) {
+  pdl_sync();
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const int r0 = blockIdx.y * 64, r1 = min(rows, r0 + 64);
@@ -169,11 +179,12 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* __restrict__ X
   atomicAdd(out + j, s);
 }
 static int colsum(cudaStream_t st, const float* X, int ld, int rows, int n, float* out) {
-  colsum_kernel<<<dim3(cdiv(n, 256), cdiv(rows, 64)), 256, 0, st>>>(X, ld, rows, n, out);
+  WAP_CHECK(launch_pdl(colsum_kernel, dim3(cdiv(n, 256), cdiv(rows, 64)), 256, 0, st, X, ld, rows, n, out));
   WAP_LAUNCH_CHECK();
   return 0;
 }
 __global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+  pdl_sync();
   __shared__ float t[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) if (r0 + i < R && c < C) t[i][threadIdx.x] = src[(size_t)(r0 + i) * C + c];
@@ -182,15 +193,17 @@ __global__ void transpose_kernel(const float* __restrict__ src, float* __restric
   for (int i = threadIdx.y; i < 32; i += 8) if (c0 + i < C && r < R) dst[(size_t)(c0 + i) * R + r] = t[threadIdx.x][i];
 }
 static int transpose(cudaStream_t st, const float* src, float* dst, int R, int C) {
-  transpose_kernel<<<dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st>>>(src, dst, R, C);
+  WAP_CHECK(launch_pdl(transpose_kernel, dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st, src, dst, R, C));
   WAP_LAUNCH_CHECK();
   return 0;
 }
 __global__ void copy_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] = src[i];
 }
 __global__ void add_kernel(const float* __restrict__ src, float* __restrict__ dst, size_t n) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dst[i] += src[i];
 }
@@ -212,7 +225,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   } else {
     WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, W.watch, W.H, W.qf, W.mean));   // H[0] = h0 (masked mean, S:345-347)
   }
-  emb_shift_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(params + P.embed, y, W.EMB, T, B);
+  WAP_CHECK(launch_pdl(emb_shift_kernel, cdiv(TB * kMw, 256), 256, 0, st, params + P.embed, y, W.EMB, T, B));
   WAP_LAUNCH_CHECK();
   // emb-dependent GRU-1 pre-activations for all steps at once
   WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yz_yr, 2 * kN, W.G1, 3 * kN, TB, 2 * kN, kMw, params + P.b_yz_yr, false));
@@ -231,17 +244,17 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
     WAP_TRY(decoder_step(st, c));
   }
   // logits for all steps (S:354-364)
-  bias3_rows_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(W.LG, TB, params + P.by, params + P.bc, params + P.bh);
+  WAP_CHECK(launch_pdl(bias3_rows_kernel, cdiv(TB * kMw, 256), 256, 0, st, W.LG, TB, params + P.by, params + P.bc, params + P.bh));
   WAP_LAUNCH_CHECK();
   WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
   WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
   WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.Wy, kMw, W.LG, kMw, TB, kMw, kMw, nullptr, true));
-  maxout_drop_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.MO, TB, dropout, seed, g_seed_src);
+  WAP_CHECK(launch_pdl(maxout_drop_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.MO, TB, dropout, seed, g_seed_src));
   WAP_LAUNCH_CHECK();
-  wo_fwd_kernel<<<cdiv(TB * kVocab, 256), 256, 0, st>>>(W.MO, params + P.Wo, params + P.bo, W.LO, TB);
+  WAP_CHECK(launch_pdl(wo_fwd_kernel, cdiv(TB * kVocab, 256), 256, 0, st, W.MO, params + P.Wo, params + P.bo, W.LO, TB));
   WAP_LAUNCH_CHECK();
   WAP_CHECK(cudaMemsetAsync(W.cost, 0, sizeof(double), st));
-  ce_kernel<<<cdiv(TB * 32, 256), 256, 0, st>>>(W.LO, y, y_mask, W.cost, TB, B, 1.f);
+  WAP_CHECK(launch_pdl(ce_kernel, cdiv(TB * 32, 256), 256, 0, st, W.LO, y, y_mask, W.cost, TB, B, 1.f));
   WAP_LAUNCH_CHECK();
   if (cost_out != nullptr) WAP_CHECK(cudaMemcpyAsync(cost_out, W.cost, sizeof(double), cudaMemcpyDeviceToDevice, st));
   return 0;
@@ -254,6 +267,7 @@ gru2_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dHlog
                 const float* __restrict__ prop2, const float* __restrict__ PH2, const float* __restrict__ pre_h,
                 const float* __restrict__ y_mask, float* __restrict__ dG2, float* __restrict__ dCH, float* __restrict__ dPH2,
                 float* __restrict__ dpre_h, int Bn) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * kN) return;
   const int b = i / kN, j = i - b * kN;
@@ -276,6 +290,7 @@ __global__ void __launch_bounds__(256)
 gru1_bwd_kernel(const float* __restrict__ dpre_h, const float* __restrict__ G1, const float* __restrict__ prop1,
                 const float* __restrict__ UH, const float* __restrict__ h_prev, const float* __restrict__ y_mask,
                 float* __restrict__ dG1, float* __restrict__ dEh, float* __restrict__ dUH, float* __restrict__ dh_out, int Bn) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * kN) return;
   const int b = i / kN, j = i - b * kN;
@@ -297,6 +312,7 @@ gru1_bwd_kernel(const float* __restrict__ dpre_h, const float* __restrict__ G1, 
 __global__ void __launch_bounds__(256)
 dalpha_kernel(const float* __restrict__ ann, const float* __restrict__ dctx, const float* __restrict__ dAP,
               float* __restrict__ dalpha, int Bn, int L) {
+  pdl_sync();
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= Bn * L) return;
   const int b = warp / L;
@@ -312,6 +328,7 @@ dalpha_kernel(const float* __restrict__ ann, const float* __restrict__ dctx, con
 // softmax backward per image: de = alpha * (dalpha - sum(alpha*dalpha))
 __global__ void __launch_bounds__(256)
 softmax_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ dalpha, float* __restrict__ de, int L) {
+  pdl_sync();
   __shared__ float red[33];
   const int b = blockIdx.x;
   float s = 0.f;
@@ -324,6 +341,7 @@ constexpr int kDzPix = 8;
 __global__ void __launch_bounds__(128)
 dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const float* __restrict__ Va,
           float* __restrict__ DZ, float* __restrict__ dSP, float* __restrict__ dVa, float* __restrict__ dVab, int L) {
+  pdl_sync();
   const int b = blockIdx.y, l0 = blockIdx.x * kDzPix, c = threadIdx.x * 4;
   const float4 va = ldg4(Va + c);
   float4 sp = make4(0.f), dv = make4(0.f);
@@ -356,6 +374,7 @@ dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const fl
 // dWatch[i] = sum_t DZ[t][i]   (one pass after the scan instead of a read-modify-write of dWatch every step)
 __global__ void __launch_bounds__(256)
 sum_steps_kernel(const float* __restrict__ DZ, float* __restrict__ out, int T, size_t n4) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n4) return;
   float4 acc = make4(0.f);
@@ -376,6 +395,7 @@ constexpr int kGatherWarps = 16;
 __global__ void __launch_bounds__(32 * kGatherWarps)
 cov_bwd_gather_kernel(const float* __restrict__ DF, const float* __restrict__ dAP_in, float* __restrict__ dAP_out,
                       int Bn, int H, int W, int tap_major) {
+  pdl_sync();
   __shared__ float part[kGatherWarps][33];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + lane, n = Bn * H * W;
@@ -409,6 +429,7 @@ cov_bwd_gather_kernel(const float* __restrict__ DF, const float* __restrict__ dA
 // d ann[b,l,c] += sum_t alpha[t,b,l] * dctx[t,b,c]
 __global__ void __launch_bounds__(256)
 dann_ctx_kernel(const float* __restrict__ ALPHA, const float* __restrict__ DCTX, float* __restrict__ dann, int T, int B, int L) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int C4 = kD / 4;
   if (i >= (size_t)B * L * C4) return;
@@ -423,12 +444,14 @@ dann_ctx_kernel(const float* __restrict__ ALPHA, const float* __restrict__ DCTX,
 }
 // h0 = tanh(mean*Wa2h + b): dpre = dh * (1 - h0^2)
 __global__ void tanh_bwd_kernel(const float* __restrict__ dh, const float* __restrict__ h, float* __restrict__ dpre, int n) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) dpre[i] = dh[i] * (1.f - h[i] * h[i]);
 }
 // d ann[b,l,:] += mask[b,l]/sum(mask[b]) * dmean[b,:]
 __global__ void __launch_bounds__(256)
 dann_mean_kernel(const float* __restrict__ dmean, const float* __restrict__ a_mask, float* __restrict__ dann, int B, int L) {
+  pdl_sync();
   __shared__ float red[33];
   const int b = blockIdx.y;
   float s = 0.f;
@@ -469,11 +492,11 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     WAP_TRY(tc_prep_bt(st, p + P.U_a, kNA, kD, 0, W.Ua_hi, W.Ua_lo));
   }
   // ---- head (LO holds dLO after the forward CE kernel)
-  wo_bwd_data_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LO, p + P.Wo, W.dMO, TB);
+  WAP_CHECK(launch_pdl(wo_bwd_data_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LO, p + P.Wo, W.dMO, TB));
   WAP_LAUNCH_CHECK();
-  wo_bwd_weight_kernel<<<cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, st>>>(W.MO, W.LO, g + P.Wo, g + P.bo, TB);
+  WAP_CHECK(launch_pdl(wo_bwd_weight_kernel, cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, st, W.MO, W.LO, g + P.Wo, g + P.bo, TB));
   WAP_LAUNCH_CHECK();
-  maxout_drop_bwd_kernel<<<cdiv(TB * kMw / 2, 256), 256, 0, st>>>(W.LG, W.dMO, W.dLG, TB, dropout, seed, g_seed_src);
+  WAP_CHECK(launch_pdl(maxout_drop_bwd_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.dMO, W.dLG, TB, dropout, seed, g_seed_src));
   WAP_LAUNCH_CHECK();
   WAP_TRY(gemm_tn_atomic(st, W.H + (size_t)B * kN, kN, W.dLG, kMw, g + P.Wh, kMw, kN, kMw, TB));
   WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dLG, kMw, g + P.Wc, kMw, kD, kMw, TB));
@@ -493,8 +516,8 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     const size_t r = (size_t)t * B;
     const float* ym = y_mask + r;
     float* dctx = W.dCTX + r * kD;                 // holds the logit-path part already
-    gru2_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(dh_in, W.dHlog + r * kN, W.G2 + r * 2 * kN, W.PROP2 + r * kN, W.PH2 + r * kN,
-                                                        W.PREH + r * kN, ym, W.dG2 + r * 2 * kN, W.dCH + r * kN, W.dPH2 + r * kN, W.dpre_h, B);
+    WAP_CHECK(launch_pdl(gru2_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, dh_in, W.dHlog + r * kN, W.G2 + r * 2 * kN, W.PROP2 + r * kN, W.PH2 + r * kN,
+                                                        W.PREH + r * kN, ym, W.dG2 + r * 2 * kN, W.dCH + r * kN, W.dPH2 + r * kN, W.dpre_h, B));
     WAP_LAUNCH_CHECK();
     {   // dctx += dG2*W_c_z_r^T + dCH*W_c_h_nl^T ; dpre_h += dG2*U_hz_hr_nl^T + dPH2*U_rh_nl^T
       SkinnyArgs a; a.ids = nullptr; a.Bn = B;
@@ -508,13 +531,13 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       a.X = W.dPH2 + r * kN; a.seg[0] = {W.T_Urhnl, kN, kN, W.dpre_h, kN};
       WAP_TRY(skinny_gemm(st, a));
     }
-    dalpha_kernel<<<cdiv(B * L * 32, 256), 256, 0, st>>>(ann, dctx, dAP_in, W.dalpha, B, L);
+    WAP_CHECK(launch_pdl(dalpha_kernel, cdiv(B * L * 32, 256), 256, 0, st, ann, dctx, dAP_in, W.dalpha, B, L));
     WAP_LAUNCH_CHECK();
-    softmax_bwd_kernel<<<B, 256, 0, st>>>(W.ALPHA + r * L, W.dalpha, W.de, L);
+    WAP_CHECK(launch_pdl(softmax_bwd_kernel, B, 256, 0, st, W.ALPHA + r * L, W.dalpha, W.de, L));
     WAP_LAUNCH_CHECK();
     float* DZt = W.DZ + r * L * kNA;
-    dz_kernel<<<dim3(cdiv(L, kDzPix), B), 128, 0, st>>>(W.TANH + r * L * kNA, W.de, p + P.V_a, DZt, W.dSP + r * kNA,
-                                                         g + P.V_a, g + P.V_a_b, L);
+    WAP_CHECK(launch_pdl(dz_kernel, dim3(cdiv(L, kDzPix), B), 128, 0, st, W.TANH + r * L * kNA, W.de, p + P.V_a, DZt, W.dSP + r * kNA,
+                                                         g + P.V_a, g + P.V_a_b, L));
     WAP_LAUNCH_CHECK();
     {   // dpre_h += dSP*W_a^T
       SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dSP + r * kNA; a.ldx = kNA; a.K = kNA; a.nseg = 1;
@@ -524,10 +547,10 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     // coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
     if (tc) WAP_TRY(tc_gemm(st, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
     else WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
-    cov_bwd_gather_kernel<<<cdiv(B * L, 32), 32 * kGatherWarps, 0, st>>>(W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0);
+    WAP_CHECK(launch_pdl(cov_bwd_gather_kernel, cdiv(B * L, 32), 32 * kGatherWarps, 0, st, W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0));
     WAP_LAUNCH_CHECK();
-    gru1_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
-                                                        W.dG1 + r * 2 * kN, W.dEh + r * kN, W.dUH + r * kN, dh_out, B);
+    WAP_CHECK(launch_pdl(gru1_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
+                                                        W.dG1 + r * 2 * kN, W.dEh + r * kN, W.dUH + r * kN, dh_out, B));
     WAP_LAUNCH_CHECK();
     {   // dh_prev += dG1*U_hz_hr^T + dUH*U_rh^T
       SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dG1 + r * 2 * kN; a.ldx = 2 * kN; a.K = 2 * kN; a.nseg = 1;
@@ -559,7 +582,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   // embedding: dEMB = dLG*Wy^T (already) + dG1*W_yz_yr^T + dEh*W_yh^T ; scatter-add into the table
   WAP_TRY(gemm_nt(st, W.dG1, 2 * kN, p + P.W_yz_yr, 2 * kN, W.dEMB, kMw, TB, kMw, 2 * kN, nullptr, true));
   WAP_TRY(gemm_nt(st, W.dEh, kN, p + P.W_yh, kN, W.dEMB, kMw, TB, kMw, kN, nullptr, true));
-  emb_scatter_kernel<<<cdiv(TB * kMw, 256), 256, 0, st>>>(W.dEMB, y, g + P.embed, T, B);
+  WAP_CHECK(launch_pdl(emb_scatter_kernel, cdiv(TB * kMw, 256), 256, 0, st, W.dEMB, y, g + P.embed, T, B));
   WAP_LAUNCH_CHECK();
   // fused coverage filter: dQ' = sum_t patches(AP_t)^T * DZ_t  (one GEMM over T*B images)
   {
@@ -574,21 +597,21 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     WAP_TRY(gemm_tn_atomic(st, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
   }
   // watch path: dWatch = sum_t DZ_t ; dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
-  sum_steps_kernel<<<cdiv((size_t)B * L * kNA / 4, 256), 256, 0, st>>>(W.DZ, W.dWatch, T, (size_t)B * L * kNA / 4);
+  WAP_CHECK(launch_pdl(sum_steps_kernel, cdiv((size_t)B * L * kNA / 4, 256), 256, 0, st, W.DZ, W.dWatch, T, (size_t)B * L * kNA / 4));
   WAP_LAUNCH_CHECK();
   WAP_TRY(gemm_tn_atomic(st, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));
   if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
   // context path
-  dann_ctx_kernel<<<(unsigned)cdivz((size_t)B * L * (kD / 4), 256), 256, 0, st>>>(W.ALPHA, W.dCTX, d_ann, T, B, L);
+  WAP_CHECK(launch_pdl(dann_ctx_kernel, (unsigned)cdivz((size_t)B * L * (kD / 4), 256), 256, 0, st, W.ALPHA, W.dCTX, d_ann, T, B, L));
   WAP_LAUNCH_CHECK();
   // h0 path: dh_in now holds d h0
-  tanh_bwd_kernel<<<cdiv(B * kN, 256), 256, 0, st>>>(dh_in, W.H, W.dpre_h, B * kN);
+  WAP_CHECK(launch_pdl(tanh_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, dh_in, W.H, W.dpre_h, B * kN));
   WAP_LAUNCH_CHECK();
   WAP_TRY(gemm_tn_atomic(st, W.mean, kD, W.dpre_h, kN, g + P.Wa2h, kN, kD, kN, B));
   WAP_TRY(colsum(st, W.dpre_h, kN, B, kN, g + P.ba2h));
   WAP_TRY(gemm_nt(st, W.dpre_h, kN, p + P.Wa2h, kN, W.dmean, kD, B, kD, kN, nullptr, false));
-  dann_mean_kernel<<<dim3(std::min(cdiv(L * (kD / 4), 256), 64), B), 256, 0, st>>>(W.dmean, a_mask, d_ann, B, L);
+  WAP_CHECK(launch_pdl(dann_mean_kernel, dim3(std::min(cdiv(L * (kD / 4), 256), 64), B), 256, 0, st, W.dmean, a_mask, d_ann, B, L));
   WAP_LAUNCH_CHECK();
   return 0;
 }

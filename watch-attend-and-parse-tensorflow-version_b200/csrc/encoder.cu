@@ -24,6 +24,7 @@ constexpr int kStemTile = 16, kStemPatch = kStemTile * 2 + 5;   // 37
 __global__ void __launch_bounds__(256)
 stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ out,
                  double* __restrict__ stats, int H, int W, int Hs, int Ws, int pt, int pl) {
+  pdl_sync();
   __shared__ float patch[kStemPatch][kStemPatch + 1];
   __shared__ __align__(16) float ws[49 * kStemC];
   __shared__ float s_stat[2 * kStemC];
@@ -79,6 +80,7 @@ stem_conv_kernel(const float* __restrict__ x, const float* __restrict__ w, float
 __global__ void __launch_bounds__(256)
 stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                   int H, int W, int Hs, int Ws, int pt, int pl) {
+  pdl_sync();
   constexpr int kHalf = kStemTile * kStemTile / 2;         // 128 output pixels per pass
   constexpr int kOutPerThread = (49 * kStemC + 255) / 256;  // 10
   __shared__ float patch[kStemPatch][kStemPatch + 1];
@@ -182,6 +184,7 @@ __device__ __forceinline__ float bn_relu_drop(float v, float sc, float sh, bool 
 // POOL: 0 none, 1 max 2x2 SAME, 2 avg 2x2 SAME (valid-count divisor)
 template <int POOL>
 __global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
+  pdl_sync();
   const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
   __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
   bn_prologue(a, s_scale, s_shift);
@@ -252,6 +255,7 @@ struct BnBwdArgs {
 
 template <int POOL>
 __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, const int pix_per_cta) {
+  pdl_sync();
   const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
   __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC];
   __shared__ float s_sg[kMaxBnC], s_sgx[kMaxBnC];
@@ -335,6 +339,7 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, c
 }
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
+  pdl_sync();
   __shared__ float s_k[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC], s_mg[kMaxBnC], s_mgx[kMaxBnC];
   const double cnt = (double)a.B * a.Hi * a.Wi;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
@@ -374,6 +379,7 @@ struct WPrepLayer { int kind, cin, cout; long long w, f, b, fl, bl; };
 __constant__ WPrepLayer c_wprep[kNumConv];
 
 __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __restrict__ params, float* __restrict__ wsp, int with_bwd) {
+  pdl_sync();
   const WPrepLayer L = c_wprep[blockIdx.y];
   if (L.kind == kStem) return;
   const float* w = params + L.w;
@@ -423,7 +429,7 @@ static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, c
   // offsets depend on the geometry (workspace layout): refresh the table on every call (cheap, 4 KB)
   (void)uploaded;
   WAP_CHECK(cudaMemcpyToSymbolAsync(c_wprep, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
-  prep_conv_weights_kernel<<<dim3(24, kNumConv), 256, 0, st>>>(params, wsp, with_bwd ? 1 : 0);
+  WAP_CHECK(launch_pdl(prep_conv_weights_kernel, dim3(24, kNumConv), 256, 0, st, params, wsp, with_bwd ? 1 : 0));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -438,9 +444,9 @@ static inline int ew_grid(size_t total_vec) {
 static int run_bn_act(cudaStream_t st, int pool, const BnActArgs& a) {
   const size_t total = (size_t)a.B * a.Ho * a.Wo * (a.C / 4);
   const int grid = ew_grid(total);
-  if (pool == 0) bn_act_kernel<0><<<grid, 256, 0, st>>>(a);
-  else if (pool == 1) bn_act_kernel<1><<<grid, 256, 0, st>>>(a);
-  else bn_act_kernel<2><<<grid, 256, 0, st>>>(a);
+  if (pool == 0) WAP_CHECK(launch_pdl(bn_act_kernel<0>, grid, 256, 0, st, a));
+  else if (pool == 1) WAP_CHECK(launch_pdl(bn_act_kernel<1>, grid, 256, 0, st, a));
+  else WAP_CHECK(launch_pdl(bn_act_kernel<2>, grid, 256, 0, st, a));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -450,11 +456,11 @@ static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
   const size_t npix = (size_t)a.B * a.Hi * a.Wi;
   int ppc = (int)std::max<size_t>(64, cdivz(npix, 148 * 4));
   const int grid = (int)cdivz(npix, ppc);
-  if (pool == 0) bn_bwd_reduce_kernel<0><<<grid, 256, 0, st>>>(a, ppc);
-  else if (pool == 1) bn_bwd_reduce_kernel<1><<<grid, 256, 0, st>>>(a, ppc);
-  else bn_bwd_reduce_kernel<2><<<grid, 256, 0, st>>>(a, ppc);
+  if (pool == 0) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<0>, grid, 256, 0, st, a, ppc));
+  else if (pool == 1) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<1>, grid, 256, 0, st, a, ppc));
+  else WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<2>, grid, 256, 0, st, a, ppc));
   WAP_LAUNCH_CHECK();
-  bn_bwd_apply_kernel<<<ew_grid(npix * (a.C / 4)), 256, 0, st>>>(a);
+  WAP_CHECK(launch_pdl(bn_bwd_apply_kernel, ew_grid(npix * (a.C / 4)), 256, 0, st, a));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -496,8 +502,8 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
   {
     int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
     dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
-    stem_conv_kernel<<<grid, 256, 0, st>>>(x, params + L.conv[0].w, wsp + ws.stem_raw, training ? stats : nullptr,
-                                           H, W, g.Hs, g.Ws, pt, pl);
+    WAP_CHECK(launch_pdl(stem_conv_kernel, grid, 256, 0, st, x, params + L.conv[0].w, wsp + ws.stem_raw, training ? stats : nullptr,
+                                           H, W, g.Hs, g.Ws, pt, pl));
     WAP_LAUNCH_CHECK();
     WAP_TRY(run_bn_act(st, 1, bn_args(0, wsp + ws.stem_raw, g.Hs, g.Ws, buf[0], g.h[0], g.w[0], g.Ctot[0], false)));
   }
@@ -666,7 +672,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     WAP_TRY(run_bn_bwd(st, 1, bwd_args(0, wsp + ws.stem_raw, g.Hs, g.Ws, G[0], g.h[0], g.w[0], g.Ctot[0], gstem, kStemC, false)));
     int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
     dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
-    stem_wgrad_kernel<<<grid, 256, 0, st>>>(x, gstem, grads + L.conv[0].w, H, W, g.Hs, g.Ws, pt, pl);
+    WAP_CHECK(launch_pdl(stem_wgrad_kernel, grid, 256, 0, st, x, gstem, grads + L.conv[0].w, H, W, g.Hs, g.Ws, pt, pl));
     WAP_LAUNCH_CHECK();
   }
   return 0;

@@ -162,6 +162,7 @@ template <> struct EpiTraits<EpiAtomic> { static constexpr bool kAtomic = true; 
 template <class Cfg, class AL, class BL, class Epi>
 __global__ void __launch_bounds__(Cfg::NT)
 gemm_kernel(const AL A, const BL Bm, const Epi epi, const int M, const int N, const int K, const int k_per_split) {
+  pdl_sync();
   constexpr int BM = Cfg::BM, BN = Cfg::BN, RM = Cfg::RM, RN = Cfg::RN, NT = Cfg::NT;
   constexpr int LDA = BM + 4, LDB = BN + 4;
   constexpr int NA = (BM * BK / 4 + NT - 1) / NT, NB = (BN * BK / 4 + NT - 1) / NT;
@@ -349,7 +350,7 @@ inline int launch_gemm(cudaStream_t st, const AL& A, const BL& Bm, const Epi& ep
   int kps = cdiv(cdiv(K, splits), BK) * BK;
   splits = cdiv(K, kps);
   dim3 grid(cdiv(M, Cfg::BM), cdiv(N, Cfg::BN), splits);
-  gemm_kernel<Cfg, AL, BL, Epi><<<grid, Cfg::NT, 0, st>>>(A, Bm, epi, M, N, K, kps);
+  WAP_CHECK(launch_pdl(gemm_kernel<Cfg, AL, BL, Epi>, grid, Cfg::NT, 0, st, A, Bm, epi, M, N, K, kps));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;

@@ -10,6 +10,7 @@ namespace wap {
 __global__ void __launch_bounds__(256)
 adadelta_l2_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ acc, float* __restrict__ accu,
                    size_t n4, size_t n_decay, float lr, float rho, float eps, float l2, float gscale, double* l2_cost) {
+  pdl_sync();
   __shared__ float red[33];
   float sq = 0.f;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -43,29 +44,31 @@ int adadelta_l2_step(cudaStream_t st, float* p, const float* g, float* acc, floa
                      float lr, float rho, float eps, float l2, float gscale, double* l2_cost) {
   WAP_REQUIRE((n & 3) == 0 && (n_decay & 3) == 0, "adadelta: n=%zu n_decay=%zu must be multiples of 4", n, n_decay);
   if (l2_cost != nullptr) WAP_CHECK(cudaMemsetAsync(l2_cost, 0, sizeof(double), st));
-  adadelta_l2_kernel<<<148 * 4, 256, 0, st>>>(p, g, acc, accu, n / 4, n_decay, lr, rho, eps, l2, gscale, l2_cost);
+  WAP_CHECK(launch_pdl(adadelta_l2_kernel, 148 * 4, 256, 0, st, p, g, acc, accu, n / 4, n_decay, lr, rho, eps, l2, gscale, l2_cost));
   WAP_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void mask_subsample_kernel(const float* __restrict__ xm, float* __restrict__ am, int B, int H, int W, int h, int w) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * h * w) return;
   const int x = i % w, t = i / w, y = t % h, b = t / h;
   am[i] = xm[((size_t)b * H + y * 16) * W + x * 16];
 }
 int mask_subsample(cudaStream_t st, const float* xm, int B, int H, int W, int h, int w, float* am) {
-  mask_subsample_kernel<<<cdiv(B * h * w, 256), 256, 0, st>>>(xm, am, B, H, W, h, w);
+  WAP_CHECK(launch_pdl(mask_subsample_kernel, cdiv(B * h * w, 256), 256, 0, st, xm, am, B, H, W, h, w));
   WAP_LAUNCH_CHECK();
   return 0;
 }
 
 __global__ void dropout_mask_kernel(uint32_t seed, uint32_t site, size_t n, float* mask) {
+  pdl_sync();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) mask[i] = drop_keep(seed, site, (uint32_t)i) ? 1.f : 0.f;
 }
 int dropout_mask(cudaStream_t st, uint32_t seed, uint32_t site, size_t n, float* mask) {
-  dropout_mask_kernel<<<(unsigned)cdivz(n, 256), 256, 0, st>>>(seed, site, n, mask);
+  WAP_CHECK(launch_pdl(dropout_mask_kernel, (unsigned)cdivz(n, 256), 256, 0, st, seed, site, n, mask));
   WAP_LAUNCH_CHECK();
   return 0;
 }

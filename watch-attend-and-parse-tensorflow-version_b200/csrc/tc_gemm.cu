@@ -144,6 +144,7 @@ template <int BN, bool IM2COL, bool X3>
 __global__ void __launch_bounds__(kTcThreads, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
+  pdl_sync();
   using S = TcSmem<BN, X3>;
   constexpr int kTcStages = S::kStages;
   // X3 keeps the two small correction products in a SECOND accumulator (columns [kAcc2, kAcc2+BN)) so that their
@@ -397,6 +398,7 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32_mn(int n) {   // both ope
 template <int NBB, bool IM2COL, bool X3>
 __global__ void __launch_bounds__(kTcThreads, 1)
 tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, float* __restrict__ out, const WgShape sh) {
+  pdl_sync();
   using S = WgSmem<NBB, X3>;
   constexpr int BN = NBB * 32;
   constexpr uint32_t kAcc2 = BN <= 32 ? 32 : 128;
@@ -580,7 +582,7 @@ static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap&
     configured = true;
   }
   prof_begin(st, prof_cls, flops);
-  tc_gemm_kernel<BN, IM2COL, X3><<<grid, kTcThreads, TcSmem<BN, X3>::kTotal, st>>>(ta, tb, tblo, epi, sh);
+  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3>, grid, kTcThreads, TcSmem<BN, X3>::kTotal, st, ta, tb, tblo, epi, sh));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
@@ -593,6 +595,7 @@ static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& 
 }
 
 __global__ void tc_prep_bt_kernel(const float* __restrict__ W, int K, int N, int transpose, float* __restrict__ hi, float* __restrict__ lo) {
+  pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
   const int n = i / K, k = i - n * K;
@@ -605,7 +608,7 @@ __global__ void tc_prep_bt_kernel(const float* __restrict__ W, int K, int N, int
   lo[i] = __uint_as_float(u);
 }
 int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, float* hi, float* lo) {
-  tc_prep_bt_kernel<<<cdiv(N * K, 256), 256, 0, st>>>(W, K, N, transpose, hi, lo);
+  WAP_CHECK(launch_pdl(tc_prep_bt_kernel, cdiv(N * K, 256), 256, 0, st, W, K, N, transpose, hi, lo));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -676,8 +679,8 @@ static int launch_wg(cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& 
   }
   WgShape sh2 = sh; sh2.dbg = g_wg_dbg; sh2.dbg_idesc_xor = g_wg_xor;
   prof_begin(st, prof_cls, flops);
-  if (x3) tc_wgrad_kernel<NBB, IM2COL, true><<<grid, kTcThreads, WgSmem<NBB, true>::kTotal, st>>>(tx, ty, out, sh2);
-  else tc_wgrad_kernel<NBB, IM2COL, false><<<grid, kTcThreads, WgSmem<NBB, false>::kTotal, st>>>(tx, ty, out, sh2);
+  if (x3) WAP_CHECK(launch_pdl(tc_wgrad_kernel<NBB, IM2COL, true>, grid, kTcThreads, WgSmem<NBB, true>::kTotal, st, tx, ty, out, sh2));
+  else WAP_CHECK(launch_pdl(tc_wgrad_kernel<NBB, IM2COL, false>, grid, kTcThreads, WgSmem<NBB, false>::kTotal, st, tx, ty, out, sh2));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
