@@ -112,6 +112,13 @@ int wap_decoder_train_backward(void* stream, const float* params, float* grads, 
                                const float* a_mask, const int32_t* y, const float* y_mask, int B, int h, int w,
                                int T, int dropout, uint32_t seed, float* d_annotation, float* workspace);
 
+/* ---- decoder backward + encoder backward in one call (same arguments and results as wap_decoder_train_backward followed
+ * by wap_encoder_backward).  The decoder's batched weight gradients run on a side stream next to the encoder backward and
+ * rejoin `stream` before the call returns its last launch, so the caller sees ordinary stream semantics. */
+int wap_train_backward(void* stream, const float* params, float* grads, const float* x, int B, int H, int W, const float* annotation,
+                       const float* a_mask, const int* y, const float* y_mask, int T, int dropout, uint32_t seed, float* d_annotation,
+                       float* encoder_workspace, float* decoder_workspace);
+
 /* ---- L2 (S:594-598) + tf.train.AdadeltaOptimizer(lr) (S:602-607; rho .95, eps 1e-8) on the flat
  *      buffers, with the data-parallel 1/world_size mean of the summed replica gradients
  *      (SyncReplicasOptimizer, D:704-717) folded in.  g = grad_scale*grads + 2*l2*p (decayed part).
@@ -175,6 +182,9 @@ int wap_set_dropout_seed_source(const uint32_t* seed_dev);
  * attribute so that launch latency overlaps the predecessor's execution; 0 restores plain stream ordering. */
 int wap_set_pdl(int on);
 int wap_get_pdl(void);
+/* ---- weight-gradient kernels on side streams (forked/joined with events inside one call; default on) */
+int wap_set_overlap(int on);
+int wap_get_overlap(void);
 
 /* keep-mask of the dropout RNG for elements [0,n) of `site` under `seed` (1.0 / 0.0), for tests */
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask);

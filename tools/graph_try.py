@@ -7,7 +7,8 @@ from wap_b200 import synth
 eng = wap_b200.WAPEngine(seed=0)
 eng.set_conv_precision(sys.argv[1] if len(sys.argv) > 1 else "tf32x3")
 eng.L.wap_set_pdl(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-print("pdl", eng.L.wap_get_pdl())
+eng.L.wap_set_overlap(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+print("pdl", eng.L.wap_get_pdl(), "overlap", eng.L.wap_get_overlap())
 B, H, W, T = 8, 128, 512, 40
 imgs, caps = synth.synth_batch(0, B, H, W, T)
 x, xm, y, ym = wap_b200.prepare_data(imgs, caps)

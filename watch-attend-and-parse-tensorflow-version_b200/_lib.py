@@ -43,6 +43,7 @@ SIGNATURES = {
     "wap_decoder_train_workspace_floats": (_i64, [_i, _i, _i, _i]),
     "wap_decoder_train_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
     "wap_decoder_train_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
+    "wap_train_backward": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _i, _i, C.c_uint32, _vp, _vp, _vp]),
     "wap_adadelta_l2_step": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f, _f, _f, _f, _f, _vp]),
     "wap_launch_count": (C.c_uint64, []),
     "wap_profile_enable": (_i, [_i]),
@@ -64,6 +65,8 @@ SIGNATURES = {
     "wap_set_dropout_seed_source": (_i, [_vp]),
     "wap_set_pdl": (_i, [_i]),
     "wap_get_pdl": (_i, []),
+    "wap_set_overlap": (_i, [_i]),
+    "wap_get_overlap": (_i, []),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),
     "wap_encoder_workspace_offset": (_i64, [_i, _i, _i, _i, _i, _i]),
 }

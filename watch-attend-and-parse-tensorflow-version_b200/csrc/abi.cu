@@ -13,6 +13,17 @@ namespace wap {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_pdl = 1;
+static int g_overlap = 1;
+SideStreams* side_streams() {
+  static SideStreams ss; static int state = 0;     // 0: not created, 1: ok, -1: failed
+  if (state == 0) {
+    state = 1;
+    for (int i = 0; i < 2 && state == 1; ++i) if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) state = -1;
+    for (int i = 0; i < 2 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
+    for (int i = 0; i < 8 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.done[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
+  }
+  return state == 1 ? &ss : nullptr;
+}
 
 // ---- per-class device timing
 struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
@@ -23,6 +34,7 @@ static cudaEvent_t ev_get() {
   if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
+bool overlap_enabled() { return g_overlap != 0 && !g_prof_on; }
 void prof_begin(cudaStream_t st, int cls, double flops) {
   if (!g_prof_on) return;
   ProfRec r; r.a = ev_get(); r.b = ev_get(); r.cls = cls; r.flops = flops;
@@ -64,7 +76,8 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
                           double* cost_out, float* wsp);
 int decoder_train_backward(cudaStream_t st, const float* params, float* grads, const float* ann, const float* a_mask,
                            const int* y, const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
-                           float* d_ann, float* wsp);
+                           float* d_ann, float* wsp, bool defer_join);
+int decoder_join(cudaStream_t st);
 size_t greedy_persist_ws_floats(int Bn, int L);
 int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
                              int* tokens, int* lengths, float* wsp, int* steps_run_dev);
@@ -209,7 +222,21 @@ int wap_decoder_train_backward(void* stream, const float* params, float* grads, 
                                const float* a_mask, const int32_t* y, const float* y_mask, int B, int h, int w,
                                int T, int dropout, uint32_t seed, float* d_annotation, float* workspace) {
   WAP_REQUIRE(params && grads && annotation && y && y_mask && d_annotation && workspace, "wap_decoder_train_backward: bad arguments");
-  return decoder_train_backward(ST(stream), params, grads, annotation, a_mask, y, y_mask, B, h, w, T, dropout, seed, d_annotation, workspace);
+  return decoder_train_backward(ST(stream), params, grads, annotation, a_mask, y, y_mask, B, h, w, T, dropout, seed, d_annotation, workspace, false);
+}
+
+int wap_train_backward(void* stream, const float* params, float* grads, const float* x, int B, int H, int W, const float* annotation,
+                       const float* a_mask, const int* y, const float* y_mask, int T, int dropout, uint32_t seed, float* d_annotation,
+                       float* encoder_workspace, float* decoder_workspace) {
+  WAP_REQUIRE(params && grads && x && annotation && y && y_mask && d_annotation && encoder_workspace && decoder_workspace,
+              "wap_train_backward: bad arguments");
+  int h, w;
+  if (wap_annotation_hw(H, W, &h, &w) != 0) return -1;
+  int r = decoder_train_backward(ST(stream), params, grads, annotation, a_mask, y, y_mask, B, h, w, T, dropout, seed, d_annotation,
+                                 decoder_workspace, true);
+  if (r == 0) r = encoder_backward(ST(stream), params, grads, x, B, H, W, dropout, seed, annotation, d_annotation, encoder_workspace);
+  const int rj = decoder_join(ST(stream));     // always rejoin the side stream, also on error
+  return r != 0 ? r : rj;
 }
 
 int wap_adadelta_l2_step(void* stream, float* params, const float* grads, float* accum, float* accum_update,
@@ -257,6 +284,8 @@ int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }
+int wap_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }
+int wap_get_overlap(void) { return g_overlap; }
 int wap_set_pdl(int on) { wap::g_pdl = on ? 1 : 0; return 0; }
 int wap_get_pdl(void) { return wap::g_pdl; }
 int wap_set_dropout_seed_source(const uint32_t* seed_dev) { wap::g_seed_src = seed_dev; return 0; }

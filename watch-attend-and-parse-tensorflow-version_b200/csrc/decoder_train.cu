@@ -470,9 +470,19 @@ dann_mean_kernel(const float* __restrict__ dmean, const float* __restrict__ a_ma
 
 // ------------------------------------------------------------------------------------ backward
 // grads (flat) accumulated (+=); d_ann [B,L,684] is written (=).
+static bool g_dec_join_pending = false;
+// the caller's stream waits for the decoder weight gradients still running on the side stream
+int decoder_join(cudaStream_t st) {
+  if (g_dec_join_pending) {
+    SideStreams* ss = side_streams();
+    if (ss != nullptr) WAP_CHECK(cudaStreamWaitEvent(st, ss->done[5], 0));
+    g_dec_join_pending = false;
+  }
+  return 0;
+}
 int decoder_train_backward(cudaStream_t st, const float* params, float* grads, const float* ann, const float* a_mask,
                            const int* y, const float* y_mask, int B, int h, int w, int T, int dropout, uint32_t seed,
-                           float* d_ann, float* wsp) {
+                           float* d_ann, float* wsp, bool defer_join) {
   const ParamLayout& P = layout();
   const int L = h * w, TB = T * B;
   DecTrainWs W = carve_train(wsp, B, L, T, nullptr);
@@ -561,45 +571,52 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     }
     std::swap(dh_in, dh_out); std::swap(dAP_in, dAP_out);
   }
+  // watch path: dWatch = sum_t DZ_t
+  WAP_CHECK(launch_pdl(sum_steps_kernel, cdiv((size_t)B * L * kNA / 4, 256), 256, 0, st, W.DZ, W.dWatch, T, (size_t)B * L * kNA / 4));
+  WAP_LAUNCH_CHECK();
+  // Everything below that only feeds `grads` (the batched weight gradients) runs on a side stream next to the d_annotation
+  // path and - when the caller defers the join (wap_train_backward) - next to the encoder backward.
+  SideStreams* ss = overlap_enabled() ? side_streams() : nullptr;
+  cudaStream_t sw = ss != nullptr ? ss->s[1] : st;
+  if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->fork[1], st)); WAP_CHECK(cudaStreamWaitEvent(sw, ss->fork[1], 0)); }
   // ---- batched weight gradients over all T*B rows
   const float* Hprev = W.H;   // H[0..T-1]
-  WAP_TRY(gemm_tn_atomic(st, W.EMB, kMw, W.dG1, 2 * kN, g + P.W_yz_yr, 2 * kN, kMw, 2 * kN, TB));
-  WAP_TRY(colsum(st, W.dG1, 2 * kN, TB, 2 * kN, g + P.b_yz_yr));
-  WAP_TRY(gemm_tn_atomic(st, W.EMB, kMw, W.dEh, kN, g + P.W_yh, kN, kMw, kN, TB));
-  WAP_TRY(colsum(st, W.dEh, kN, TB, kN, g + P.b_yh));
-  WAP_TRY(gemm_tn_atomic(st, Hprev, kN, W.dG1, 2 * kN, g + P.U_hz_hr, 2 * kN, kN, 2 * kN, TB));
-  WAP_TRY(gemm_tn_atomic(st, Hprev, kN, W.dUH, kN, g + P.U_rh, kN, kN, kN, TB));
-  WAP_TRY(gemm_tn_atomic(st, W.PREH, kN, W.dSP, kNA, g + P.W_a, kNA, kN, kNA, TB));
-  WAP_TRY(colsum(st, W.dSP, kNA, TB, kNA, g + P.W_a_b));
-  WAP_TRY(colsum(st, W.dSP, kNA, TB, kNA, g + P.U_f_b));
-  WAP_TRY(colsum(st, W.dSP, kNA, TB, kNA, g + P.U_a_b));
-  WAP_TRY(gemm_tn_atomic(st, W.PREH, kN, W.dG2, 2 * kN, g + P.U_hz_hr_nl, 2 * kN, kN, 2 * kN, TB));
-  WAP_TRY(colsum(st, W.dG2, 2 * kN, TB, 2 * kN, g + P.b_hz_hr_nl));
-  WAP_TRY(gemm_tn_atomic(st, W.PREH, kN, W.dPH2, kN, g + P.U_rh_nl, kN, kN, kN, TB));
-  WAP_TRY(colsum(st, W.dPH2, kN, TB, kN, g + P.b_rh_nl));
-  WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dG2, 2 * kN, g + P.W_c_z_r, 2 * kN, kD, 2 * kN, TB));
-  WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dCH, kN, g + P.W_c_h_nl, kN, kD, kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, W.EMB, kMw, W.dG1, 2 * kN, g + P.W_yz_yr, 2 * kN, kMw, 2 * kN, TB));
+  WAP_TRY(colsum(sw, W.dG1, 2 * kN, TB, 2 * kN, g + P.b_yz_yr));
+  WAP_TRY(gemm_tn_atomic(sw, W.EMB, kMw, W.dEh, kN, g + P.W_yh, kN, kMw, kN, TB));
+  WAP_TRY(colsum(sw, W.dEh, kN, TB, kN, g + P.b_yh));
+  WAP_TRY(gemm_tn_atomic(sw, Hprev, kN, W.dG1, 2 * kN, g + P.U_hz_hr, 2 * kN, kN, 2 * kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, Hprev, kN, W.dUH, kN, g + P.U_rh, kN, kN, kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dSP, kNA, g + P.W_a, kNA, kN, kNA, TB));
+  WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.W_a_b));
+  WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.U_f_b));
+  WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.U_a_b));
+  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dG2, 2 * kN, g + P.U_hz_hr_nl, 2 * kN, kN, 2 * kN, TB));
+  WAP_TRY(colsum(sw, W.dG2, 2 * kN, TB, 2 * kN, g + P.b_hz_hr_nl));
+  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dPH2, kN, g + P.U_rh_nl, kN, kN, kN, TB));
+  WAP_TRY(colsum(sw, W.dPH2, kN, TB, kN, g + P.b_rh_nl));
+  WAP_TRY(gemm_tn_atomic(sw, W.CTX, kD, W.dG2, 2 * kN, g + P.W_c_z_r, 2 * kN, kD, 2 * kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, W.CTX, kD, W.dCH, kN, g + P.W_c_h_nl, kN, kD, kN, TB));
   // embedding: dEMB = dLG*Wy^T (already) + dG1*W_yz_yr^T + dEh*W_yh^T ; scatter-add into the table
-  WAP_TRY(gemm_nt(st, W.dG1, 2 * kN, p + P.W_yz_yr, 2 * kN, W.dEMB, kMw, TB, kMw, 2 * kN, nullptr, true));
-  WAP_TRY(gemm_nt(st, W.dEh, kN, p + P.W_yh, kN, W.dEMB, kMw, TB, kMw, kN, nullptr, true));
-  WAP_CHECK(launch_pdl(emb_scatter_kernel, cdiv(TB * kMw, 256), 256, 0, st, W.dEMB, y, g + P.embed, T, B));
+  WAP_TRY(gemm_nt(sw, W.dG1, 2 * kN, p + P.W_yz_yr, 2 * kN, W.dEMB, kMw, TB, kMw, 2 * kN, nullptr, true));
+  WAP_TRY(gemm_nt(sw, W.dEh, kN, p + P.W_yh, kN, W.dEMB, kMw, TB, kMw, kN, nullptr, true));
+  WAP_CHECK(launch_pdl(emb_scatter_kernel, cdiv(TB * kMw, 256), 256, 0, sw, W.dEMB, y, g + P.embed, T, B));
   WAP_LAUNCH_CHECK();
   // fused coverage filter: dQ' = sum_t patches(AP_t)^T * DZ_t  (one GEMM over T*B images)
   {
-    WAP_CHECK(cudaMemsetAsync(W.dQf, 0, sizeof(float) * kCovTaps * kNA, st));
+    WAP_CHECK(cudaMemsetAsync(W.dQf, 0, sizeof(float) * kCovTaps * kNA, sw));
     ACovPatchT A{W.AP, T * B, h, w};
     BRowMajor Bd{W.DZ, kNA, TB * L, kNA};
     EpiAtomic e{W.dQf, kNA};
     const int K = ((TB * L + 3) / 4) * 4;
-    WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, kCovTaps, kNA, K, std::max(1, std::min(cdiv(K, 64), 148)))));
+    WAP_TRY((launch_gemm<Cfg128x128>(sw, A, Bd, e, kCovTaps, kNA, K, std::max(1, std::min(cdiv(K, 64), 148)))));
     // dQ += dQ' * U_f^T ; dU_f += Q^T * dQ'
-    WAP_TRY(gemm_nt(st, W.dQf, kNA, p + P.U_f, kNA, g + P.Q, kNA, kCovTaps, kNA, kNA, nullptr, true));
-    WAP_TRY(gemm_tn_atomic(st, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
+    WAP_TRY(gemm_nt(sw, W.dQf, kNA, p + P.U_f, kNA, g + P.Q, kNA, kCovTaps, kNA, kNA, nullptr, true));
+    WAP_TRY(gemm_tn_atomic(sw, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
   }
-  // watch path: dWatch = sum_t DZ_t ; dU_a += ann^T * dWatch ; d ann = dWatch * U_a^T
-  WAP_CHECK(launch_pdl(sum_steps_kernel, cdiv((size_t)B * L * kNA / 4, 256), 256, 0, st, W.DZ, W.dWatch, T, (size_t)B * L * kNA / 4));
-  WAP_LAUNCH_CHECK();
-  WAP_TRY(gemm_tn_atomic(st, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));
+  WAP_TRY(gemm_tn_atomic(sw, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));     // dU_a += ann^T * dWatch
+  if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->done[5], sw)); g_dec_join_pending = true; }
+  // d ann = dWatch * U_a^T
   if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
   // context path
@@ -613,6 +630,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_TRY(gemm_nt(st, W.dpre_h, kN, p + P.Wa2h, kN, W.dmean, kD, B, kD, kN, nullptr, false));
   WAP_CHECK(launch_pdl(dann_mean_kernel, dim3(std::min(cdiv(L * (kD / 4), 256), 64), B), 256, 0, st, W.dmean, a_mask, d_ann, B, L));
   WAP_LAUNCH_CHECK();
+  if (!defer_join) WAP_TRY(decoder_join(st));
   return 0;
 }
 

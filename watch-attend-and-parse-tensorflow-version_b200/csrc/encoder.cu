@@ -572,11 +572,24 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   double* red = reinterpret_cast<double*>(wsp + ws.red);
   const float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
   float* G[kBlocks] = {wsp + ws.gbuf[0], wsp + ws.gbuf[1], d_annotation};
-  float* dy1 = wsp + ws.dy1; float* da1 = wsp + ws.da1; float* dy2 = wsp + ws.dy2; float* dytr = wsp + ws.dytr;
+  float* dy1v[2] = {wsp + ws.dy1, wsp + ws.dy1b}; float* dy2v[2] = {wsp + ws.dy2, wsp + ws.dy2b};
+  float* da1 = wsp + ws.da1; float* dytr = wsp + ws.dytr;
+  // Weight gradients only feed `grads`, so they run on a side stream next to the dgrad -> BN-backward chain of the
+  // following levels (which leaves most SMs idle in blocks 1 and 2: 64 and 16 row tiles).  dy1 / dy2 ping-pong between two
+  // buffers; the main stream waits for the weight gradient that read a buffer before overwriting it two levels later.
+  SideStreams* ss = overlap_enabled() ? side_streams() : nullptr;
+  cudaStream_t sw = ss != nullptr ? ss->s[0] : st;
+  bool pend[5] = {false, false, false, false, false};     // done[] events outstanding: wgrad3 (parity 0/1), wgrad1 (parity 0/1), transition
+  auto fork = [&]() -> int {
+    if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->fork[0], st)); WAP_CHECK(cudaStreamWaitEvent(sw, ss->fork[0], 0)); }
+    return 0;
+  };
+  auto mark = [&](int e) -> int { if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->done[e], sw)); pend[e] = true; } return 0; };
+  auto join = [&](int e) -> int { if (ss != nullptr && pend[e]) { WAP_CHECK(cudaStreamWaitEvent(st, ss->done[e], 0)); pend[e] = false; } return 0; };
   const bool tc = g_conv_precision != 0, x3 = g_conv_precision == 2;
   auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
   // dy2 rows are 32 floats (24 channels + zero pad) so that one row is one 128-byte TMA/UMMA row
-  WAP_CHECK(cudaMemsetAsync(dy2, 0, sizeof(float) * (size_t)g.M[0] * kDy2Ld, st));
+  for (int i = 0; i < 2; ++i) WAP_CHECK(cudaMemsetAsync(dy2v[i], 0, sizeof(float) * (size_t)g.M[0] * kDy2Ld, st));
   auto bwd_args = [&](int k, const float* raw, int Hi, int Wi, const float* dout, int Ho, int Wo, int ld_dout, float* gbuf, int ld_g, bool drop) {
     const ConvLayer& c = L.conv[k];
     BnBwdArgs a;
@@ -594,17 +607,20 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     if (b < kBlocks - 1) {   // transition b -> b+1 (conv index k)
       const ConvLayer& ct = L.conv[k];
       const int C = ld;
+      WAP_TRY(join(4));
       WAP_TRY(run_bn_bwd(st, 2, bwd_args(k, wsp + ws.ytr[b], h, w, G[b + 1], g.h[b + 1], g.w[b + 1], g.Ctot[b + 1], dytr, ct.cout, true)));
+      WAP_TRY(fork());
       if (tc && (g_tc_debug_mask & 64)) {   // wgrad  dW[C, C/2] += buf^T * dy   (column chunks of <= 96)
         for (int n0 = 0; n0 < ct.cout; n0 += 96)
-          WAP_TRY(tc_wgrad_1x1(st, buf[b], ld, dytr + n0, ct.cout, M, C, std::min(96, ct.cout - n0), grads + ct.w + n0, ct.cout, x3, kProfTransBwd));
+          WAP_TRY(tc_wgrad_1x1(sw, buf[b], ld, dytr + n0, ct.cout, M, C, std::min(96, ct.cout - n0), grads + ct.w + n0, ct.cout, x3, kProfTransBwd));
       } else {
         AColMajor A{buf[b], ld, C, M};
         BRowMajor Bd{dytr, ct.cout, M, ct.cout};
         EpiAtomic e{grads + ct.w, ct.cout};
         const int tiles = cdiv(C, 128) * cdiv(ct.cout, 128);
-        WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfTransBwd)));
+        WAP_TRY((launch_gemm<Cfg128x128>(sw, A, Bd, e, C, ct.cout, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfTransBwd)));
       }
+      WAP_TRY(mark(4));
       if (tc && (g_tc_debug_mask & 1)) {   // dgrad  G[b] = dy * W^T   (initialises the whole gradient buffer of block b)
         WAP_TRY(tc_gemm(st, dytr, ct.cout, wsp + ws.wt_bwd[k], lo(ws.wt_bwd_lo[k]), ct.cout, M, C, ct.cout, TcEpi{G[b], ld, 0, nullptr, nullptr, 0}, kProfTransBwd));
       } else {
@@ -621,17 +637,22 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
       const ConvLayer& c3 = L.conv[k3];
       const ConvLayer& c1 = L.conv[k1];
       const float* y1 = wsp + ws.y1[k1]; const float* a1 = wsp + ws.a1[k1]; const float* y2 = wsp + ws.y2[k3];
+      const int par = j & 1;
+      float* dy1 = dy1v[par]; float* dy2 = dy2v[par];
       // BN/ReLU/dropout backward of the 3x3 output
+      WAP_TRY(join(par));
       WAP_TRY(run_bn_bwd(st, 0, bwd_args(k3, y2, h, w, G[b] + C, h, w, ld, dy2, kDy2Ld, true)));
+      WAP_TRY(fork());
       if (tc && (g_tc_debug_mask & 64)) {   // wgrad 3x3: dW[864,24] += im2col(a1)^T * dy2
-        WAP_TRY(tc_wgrad_3x3(st, a1, kBottle, dy2, kDy2Ld, B, h, w, kBottle, kGrowth, grads + c3.w, kGrowth, x3, kProfConv3Wgrad));
+        WAP_TRY(tc_wgrad_3x3(sw, a1, kBottle, dy2, kDy2Ld, B, h, w, kBottle, kGrowth, grads + c3.w, kGrowth, x3, kProfConv3Wgrad));
       } else {
         AIm2col3T A{a1, kBottle, B, h, w, kBottle};
         BRowMajor Bd{dy2, kDy2Ld, M, kGrowth};
         EpiAtomic e{grads + c3.w, kGrowth};
         const int tiles = cdiv(9 * kBottle, 128);
-        WAP_TRY((launch_gemm<Cfg128x32>(st, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv3Wgrad)));
+        WAP_TRY((launch_gemm<Cfg128x32>(sw, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv3Wgrad)));
       }
+      WAP_TRY(mark(par));
       if (tc && (g_tc_debug_mask & 2)) {   // dgrad 3x3: d a1[M,96]
         WAP_TRY(tc_conv3x3(st, dy2, kDy2Ld, B, h, w, kDy2Ld, wsp + ws.wt_bwd[k3], lo(ws.wt_bwd_lo[k3]), kBottle, kBottle, TcEpi{da1, kBottle, 0, nullptr, nullptr, 0}, kProfConv3Dgrad));
       } else {
@@ -644,18 +665,21 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         WAP_CHECK(cudaMemcpyAsync(g_dbg_buf, da1, sizeof(float) * (size_t)M * kBottle, cudaMemcpyDeviceToDevice, st));
         WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * kBottle, dy2, sizeof(float) * (size_t)M * kDy2Ld, cudaMemcpyDeviceToDevice, st));
       }
+      WAP_TRY(join(2 + par));
       WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, kBottle, true)));
+      WAP_TRY(fork());
       if (k1 == g_dbg_layer && g_dbg_buf != nullptr)     // [.. | dy1 (M*96)]
         WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * (kBottle + kDy2Ld), dy1, sizeof(float) * (size_t)M * kBottle, cudaMemcpyDeviceToDevice, st));
       if (tc && (g_tc_debug_mask & 64)) {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
-        WAP_TRY(tc_wgrad_1x1(st, buf[b], ld, dy1, kBottle, M, C, kBottle, grads + c1.w, kBottle, x3, kProfConv1Wgrad));
+        WAP_TRY(tc_wgrad_1x1(sw, buf[b], ld, dy1, kBottle, M, C, kBottle, grads + c1.w, kBottle, x3, kProfConv1Wgrad));
       } else {
         AColMajor A{buf[b], ld, C, M};
         BRowMajor Bd{dy1, kBottle, M, kBottle};
         EpiAtomic e{grads + c1.w, kBottle};
         const int tiles = cdiv(C, 128);
-        WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv1Wgrad)));
+        WAP_TRY((launch_gemm<Cfg128x96>(sw, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv1Wgrad)));
       }
+      WAP_TRY(mark(2 + par));
       if (tc && (g_tc_debug_mask & 4)) {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
         WAP_TRY(tc_gemm(st, dy1, kBottle, wsp + ws.wt_bwd[k1], lo(ws.wt_bwd_lo[k1]), kBottle, M, C, kBottle, TcEpi{G[b], ld, 1, nullptr, nullptr, 0}, kProfConv1Dgrad));
       } else {
@@ -675,6 +699,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     WAP_CHECK(launch_pdl(stem_wgrad_kernel, grid, 256, 0, st, x, gstem, grads + L.conv[0].w, H, W, g.Hs, g.Ws, pt, pl));
     WAP_LAUNCH_CHECK();
   }
+  for (int e = 0; e < 5; ++e) WAP_TRY(join(e));      // every side-stream weight gradient rejoins the caller's stream
   return 0;
 }
 

@@ -127,6 +127,8 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
     ws.dy1 = take((size_t)g.M[0] * kBottle);
     ws.da1 = take((size_t)g.M[0] * kBottle);
     ws.dy2 = take((size_t)g.M[0] * kDy2Ld);
+    ws.dy1b = take((size_t)g.M[0] * kBottle);
+    ws.dy2b = take((size_t)g.M[0] * kDy2Ld);
     size_t tr = 0;
     for (int b = 0; b < kBlocks - 1; ++b) tr = std::max(tr, (size_t)g.M[b] * (g.Ctot[b] / 2));
     ws.dytr = take(tr);

@@ -65,7 +65,8 @@ struct EncWorkspace {
   size_t saved;                          // floats:  [99][2][kMaxBnC]   mean, invstd
   // backward scratch
   size_t gbuf[kBlocks - 1];              // d block buffer 0,1
-  size_t dy1, da1, dy2, dytr, gstem;     // largest-block sized scratch (dy2 has row stride kDy2Ld = 32)
+  size_t dy1, da1, dy2, dytr, gstem, dy1b, dy2b;   // dy1b/dy2b: ping-pong partners (weight gradients run on a side stream)
+  //     // largest-block sized scratch (dy2 has row stride kDy2Ld = 32)
   size_t wt_fwd[kNumConv], wt_bwd[kNumConv];   // TF32-rounded K-major weight copies for the tcgen05 path (hi parts)
   size_t wt_fwd_lo[kNumConv], wt_bwd_lo[kNumConv];   // residuals rna(w - hi) for the 3xTF32 mode
   size_t red;                            // doubles [2][kMaxBnC]
@@ -73,5 +74,15 @@ struct EncWorkspace {
 };
 EncWorkspace make_enc_workspace(const EncGeom& g, bool training);
 
+// Side streams for work that is off the critical path of a training step (weight gradients): forked from / joined to
+// the caller's stream with events, so the pattern is capturable into a CUDA graph.  overlap_enabled() is false while
+// per-launch profiling is on (wap_profile_enable) or after wap_set_overlap(0).
+struct SideStreams {
+  cudaStream_t s[2];          // 0: encoder weight gradients   1: decoder weight gradients
+  cudaEvent_t fork[2];        // recorded on the main stream, waited by the side stream
+  cudaEvent_t done[8];        // recorded on a side stream, waited by the main stream
+};
+SideStreams* side_streams();  // lazily created; nullptr on failure
+bool overlap_enabled();
 extern const uint32_t* g_seed_src;   // device word overriding the by-value dropout seed (null: by-value)
 }  // namespace wap

@@ -422,10 +422,8 @@ class WAPEngine:
                    "wap_encoder_forward")
         _lib.check(self.L.wap_decoder_train_forward(st, _p(self.P.flat), _p(ann), _p(a_mask), _p(y), _p(y_mask), B, h, w, T, int(dropout), sd_c,
                                                     _p(self._cost), _p(dws)), "wap_decoder_train_forward")
-        _lib.check(self.L.wap_decoder_train_backward(st, _p(self.P.flat), _p(self.grads), _p(ann), _p(a_mask), _p(y), _p(y_mask), B, h, w, T,
-                                                     int(dropout), sd_c, _p(d_ann), _p(dws)), "wap_decoder_train_backward")
-        _lib.check(self.L.wap_encoder_backward(st, _p(self.P.flat), _p(self.grads), _p(x), B, H, W, int(dropout), sd_c, _p(ann), _p(d_ann), _p(ews)),
-                   "wap_encoder_backward")
+        _lib.check(self.L.wap_train_backward(st, _p(self.P.flat), _p(self.grads), _p(x), B, H, W, _p(ann), _p(a_mask), _p(y), _p(y_mask), T,
+                                             int(dropout), sd_c, _p(d_ann), _p(ews), _p(dws)), "wap_train_backward")
         return self._cost[0]
 
     def launch_count(self) -> int:
