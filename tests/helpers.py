@@ -43,15 +43,45 @@ def t64(a):
     return torch.as_tensor(np.asarray(a), dtype=torch.float64)
 
 
-def well_posed_batch(P, seed, B, H, W, cap_len, ragged, drop_seed=None, margin=1.5e-6, tries=80):
+_WP_CACHE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "well_posed_cache.json")
+
+
+def _wp_key(P, seed, B, H, W, cap_len, ragged, drop_seed, margin):
+    import zlib
+    crc = 0
+    for n in ("conv2d_1/kernel", "conv2d_98/kernel", "batch_normalization_50/gamma", "W_a"):
+        crc = zlib.crc32(np.ascontiguousarray(P[n], dtype=np.float32).tobytes(), crc)
+    return f"{crc:08x}_{seed}_{B}_{H}_{W}_{cap_len}_{int(ragged)}_{drop_seed}_{margin:g}"
+
+
+def well_posed_batch(P, seed, B, H, W, cap_len, ragged, drop_seed=None, margin=4e-6, tries=2000):
     """First batch (seeds seed, seed+1000, ...) none of whose ~1e6 BN outputs lies within `margin`
-    (a few fp32 ulps of an O(1) value) of the ReLU kink (see oracle.relu_kink_margin).  An element
-    on the kink is gated differently by fp32 and fp64 arithmetic - legitimately - and with only a few
-    dozen pixels per channel in block 2 of these small test images one flipped element moves that
-    channel's gradients by ~1e-2, which says nothing about the kernels."""
+    (a few fp32 ulps of an O(1) value; the CUDA forward is within ~2e-6 of fp64) of the ReLU kink (see
+    oracle.relu_kink_margin).  An element on the kink is gated differently by fp32 and fp64 arithmetic -
+    legitimately - and with only a few dozen pixels per channel in block 2 of these small test images one
+    flipped element moves that channel's gradients by ~1e-2, which says nothing about the kernels.
+    The index of the batch found is cached in tests/golden/well_posed_cache.json (the search costs up to
+    ~300 oracle forwards); a cached index is re-verified with one oracle forward."""
+    import json
+    drop = (lambda: O.hash_drop_fn(drop_seed)) if drop_seed is not None else (lambda: None)
+    key = _wp_key(P, seed, B, H, W, cap_len, ragged, drop_seed, margin)
+    try:
+        cache = json.load(open(_WP_CACHE))
+    except (OSError, ValueError):
+        cache = {}
+    if key in cache:
+        x, xm, y, ym = make_batch(seed + 1000 * cache[key], B, H, W, cap_len, ragged)
+        if O.relu_kink_margin(P, x, xm, drop()) > margin:
+            return x, xm, y, ym
     for i in range(tries):
         x, xm, y, ym = make_batch(seed + 1000 * i, B, H, W, cap_len, ragged)
-        m = O.relu_kink_margin(P, x, xm, O.hash_drop_fn(drop_seed) if drop_seed is not None else None)
-        if m > margin:
+        if O.relu_kink_margin(P, x, xm, drop()) > margin:
+            cache[key] = i
+            for path in (_WP_CACHE, os.path.join(os.path.dirname(_WP_CACHE), "..", "..", "gpurun_out", "well_posed_cache.json")):
+                try:
+                    os.makedirs(os.path.dirname(path), exist_ok=True)
+                    json.dump(cache, open(path, "w"), indent=0, sort_keys=True)
+                except OSError:
+                    pass
             return x, xm, y, ym
     raise RuntimeError("no well-posed batch found")

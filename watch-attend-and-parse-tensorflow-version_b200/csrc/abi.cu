@@ -18,8 +18,8 @@ SideStreams* side_streams() {
   static SideStreams ss; static int state = 0;     // 0: not created, 1: ok, -1: failed
   if (state == 0) {
     state = 1;
-    for (int i = 0; i < 2 && state == 1; ++i) if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) state = -1;
-    for (int i = 0; i < 2 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
+    for (int i = 0; i < 3 && state == 1; ++i) if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) state = -1;
+    for (int i = 0; i < 4 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
     for (int i = 0; i < 8 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.done[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
   }
   return state == 1 ? &ss : nullptr;

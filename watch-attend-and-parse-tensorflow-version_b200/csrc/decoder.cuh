@@ -56,6 +56,10 @@ struct StepCtx {
   SkinnySeg extra_ctx; int has_extra_ctx;
   // tensor-core coverage GEMM (training scan): patches materialised in Ppat [Bn*L,128], Q'^T hi/lo [512][128]; tc_mode 0 = FFMA
   int tc_mode; float* Ppat; const float* qfT_hi; const float* qfT_lo;
+  // training scan: the bias rows of all T steps are filled by one launch before the loop
+  int skip_fill = 0;
+  // training scan: coverage chain (im2col + GEMM, depends only on ap_in) on a side stream, next to the GRU-1 half of the step
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 int decoder_step(cudaStream_t st, const StepCtx& c);
 int attention_tail(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* a_mask, int shared, int Bn, int L,

@@ -294,7 +294,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
   const ParamLayout& P = layout();
   const float* p = c.params;
   const int Bn = c.Bn, L = c.L;
-  {   // bias-initialise the atomically accumulated buffers of this step
+  if (!c.skip_fill) {   // bias-initialise the atomically accumulated buffers of this step
     FillArgs f; f.rows = Bn; f.nseg = 5;
     f.seg[0] = {c.UH, kN, kN, nullptr};
     f.seg[1] = {c.SP, kNA, kNA, p + P.W_a_b};
@@ -302,6 +302,15 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     f.seg[3] = {c.PH2, kN, kN, p + P.b_rh_nl};
     f.seg[4] = {c.CH, kN, kN, nullptr};
     WAP_TRY(fill_rows(st, f));
+  }
+  const bool side_cov = c.tc_mode != 0 && c.side != nullptr;
+  if (side_cov) {   // ap_in is final (previous step's softmax): start the coverage chain next to the GRU-1 half
+    WAP_CHECK(cudaEventRecord(c.ev_fork, st)); WAP_CHECK(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
+    WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, c.side, c.ap_in, c.Ppat, Bn, c.h, c.w));
+    WAP_LAUNCH_CHECK();
+    WAP_TRY(tc_gemm(c.side, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
+                    TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
+    WAP_CHECK(cudaEventRecord(c.ev_join, c.side));
   }
   {   // h_prev * [U_hz_hr | U_rh]
     SkinnyArgs a; a.X = c.h_prev; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 2;
@@ -318,7 +327,10 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     a.seg[2] = {p + P.U_rh_nl, kN, kN, c.PH2, kN};
     WAP_TRY(skinny_gemm(st, a));
   }
-  if (c.tc_mode != 0) {   // coverage on tensor cores: im2col patches [Bn*L,128] x Q'^T[512][128]  (+ U_f_b)
+  if (side_cov) {
+    WAP_CHECK(cudaStreamWaitEvent(st, c.ev_join, 0));
+    WAP_TRY(attention_tail(st, p, c.ann, c.watch, c.a_mask, c.shared, Bn, L, c.SP, c.ap_in, c.COV, c.TANH, c.E, c.alpha, c.ap_out, c.ctx));
+  } else if (c.tc_mode != 0) {   // coverage on tensor cores: im2col patches [Bn*L,128] x Q'^T[512][128]  (+ U_f_b)
     WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, st, c.ap_in, c.Ppat, Bn, c.h, c.w));
     WAP_LAUNCH_CHECK();
     WAP_TRY(tc_gemm(st, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,

@@ -23,6 +23,7 @@ int attn_precompute(cudaStream_t st, const float* params, const float* ann, cons
                     float* watch, float* h0, float* qf, float* mean_scratch);
 
 // ------------------------------------------------------------------------------------ workspace
+constexpr int kLdA = 4 * kN, kLdB = 3 * kN;
 struct DecTrainWs {
   // forward (saved)
   float *EMB, *G1, *H, *UH, *PROP1, *PREH, *SP, *G2, *PH2, *CH, *PROP2, *TANH, *ALPHA, *AP, *CTX;
@@ -47,13 +48,17 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.watch = take(BL * kNA); w.qf = take((size_t)kCovTaps * kNA); w.mean = take((size_t)B * kD);
   w.COV = take(BL * kNA); w.E = take(BL); w.LG = take(TB * kMw); w.MO = take(TB * kMw / 2); w.LO = take(TB * kVocab);
   w.dLG = take(TB * kMw); w.dMO = take(TB * kMw / 2); w.dHlog = take(TB * kN); w.dCTX = take(TB * kD); w.dEMB = take(TB * kMw);
-  w.dG1 = take(TB * 2 * kN); w.dEh = take(TB * kN); w.dUH = take(TB * kN); w.dSP = take(TB * kNA); w.dG2 = take(TB * 2 * kN);
-  w.dCH = take(TB * kN); w.dPH2 = take(TB * kN); w.DZ = take(TB * L * kNA); w.dWatch = take(BL * kNA); w.DF = take(BL * 124);
+  // per-step gradient rows laid out so that the BPTT data gradients are single skinny GEMMs over concatenated operands:
+  //   DA row (kLdA = 1024): [dPH2 | dG2 (r|z) | dCH]     DB row (kLdB = 768): [dG1 (r|z) | dUH]
+  w.dPH2 = take(TB * kLdA); w.dG2 = w.dPH2 + kN; w.dCH = w.dPH2 + 3 * kN;
+  w.dG1 = take(TB * kLdB); w.dUH = w.dG1 + 2 * kN;
+  w.dEh = take(TB * kN); w.dSP = take(TB * kNA); w.DZ = take(TB * L * kNA); w.dWatch = take(BL * kNA); w.DF = take(BL * 124);
   w.dAP0 = take(BL); w.dAP1 = take(BL); w.dalpha = take(BL); w.de = take(BL);
   w.dh0 = take((size_t)B * kN); w.dh1 = take((size_t)B * kN); w.dpre_h = take((size_t)B * kN);
   w.dQf = take((size_t)kCovTaps * kNA); w.dmean = take((size_t)B * kD);
-  w.T_Wczr = take((size_t)2 * kN * kD); w.T_Wchnl = take((size_t)kN * kD); w.T_Uhzhrnl = take((size_t)2 * kN * kN);
-  w.T_Urhnl = take((size_t)kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
+  // stacked transposes matching the concatenated operands: [T_Wczr; T_Wchnl] (768x684), [T_Urhnl; T_Uhzhrnl] (768x256), [T_Uhzhr; T_Urh] (768x256)
+  w.T_Wczr = take((size_t)2 * kN * kD); w.T_Wchnl = take((size_t)kN * kD); w.T_Urhnl = take((size_t)kN * kN);
+  w.T_Uhzhrnl = take((size_t)2 * kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
   w.qf_hi = take((size_t)kCovTaps * kNA); w.qf_lo = take((size_t)kCovTaps * kNA);
   w.Ua_hi = take((size_t)kD * kNA); w.Ua_lo = take((size_t)kD * kNA); w.UaT_hi = take((size_t)kD * kNA); w.UaT_lo = take((size_t)kD * kNA);
   w.Ppat = take(BL * 128); w.qfT_hi = take((size_t)kNA * 128); w.qfT_lo = take((size_t)kNA * 128);
@@ -231,6 +236,16 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yz_yr, 2 * kN, W.G1, 3 * kN, TB, 2 * kN, kMw, params + P.b_yz_yr, false));
   WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yh, kN, W.G1 + 2 * kN, 3 * kN, TB, kN, kMw, params + P.b_yh, false));
   WAP_CHECK(cudaMemsetAsync(W.AP, 0, sizeof(float) * B * L, st));
+  {   // bias rows of the atomically accumulated per-step buffers, all T steps at once
+    FillArgs f; f.rows = TB; f.nseg = 5;
+    f.seg[0] = {W.UH, kN, kN, nullptr};
+    f.seg[1] = {W.SP, kNA, kNA, params + P.W_a_b};
+    f.seg[2] = {W.G2, 2 * kN, 2 * kN, params + P.b_hz_hr_nl};
+    f.seg[3] = {W.PH2, kN, kN, params + P.b_rh_nl};
+    f.seg[4] = {W.CH, kN, kN, nullptr};
+    WAP_TRY(fill_rows(st, f));
+  }
+  SideStreams* sl = (tc && overlap_enabled()) ? side_streams() : nullptr;
   for (int t = 0; t < T; ++t) {
     const size_t r = (size_t)t * B;
     StepCtx c;
@@ -241,6 +256,8 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
     c.COV = W.COV; c.TANH = W.TANH + r * L * kNA; c.E = W.E; c.alpha = W.ALPHA + r * L; c.ap_out = W.AP + (r + B) * L;
     c.ctx = W.CTX + r * kD; c.h_new = W.H + (r + B) * kN; c.has_extra_ctx = 0;
     c.tc_mode = tc ? prec : 0; c.Ppat = W.Ppat; c.qfT_hi = W.qfT_hi; c.qfT_lo = W.qfT_lo;
+    c.skip_fill = 1;
+    if (sl != nullptr) { c.side = sl->s[2]; c.ev_fork = sl->fork[2]; c.ev_join = sl->done[6]; }
     WAP_TRY(decoder_step(st, c));
   }
   // logits for all steps (S:354-364)
@@ -278,11 +295,11 @@ gru2_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dHlog
   const float dhn = m * dh;
   const float dz = dhn * (ph - p), dp = dhn * (1.f - z);
   const float dpp = dp * (1.f - p * p);
-  dCH[i] = dpp;
-  dPH2[i] = dpp * r;
+  dCH[(size_t)b * kLdA + j] = dpp;
+  dPH2[(size_t)b * kLdA + j] = dpp * r;
   const float dr = dpp * PH2[i];
-  dG2[(size_t)b * 2 * kN + j] = dr * r * (1.f - r);
-  dG2[(size_t)b * 2 * kN + kN + j] = dz * z * (1.f - z);
+  dG2[(size_t)b * kLdA + j] = dr * r * (1.f - r);
+  dG2[(size_t)b * kLdA + kN + j] = dz * z * (1.f - z);
   dpre_h[i] = (1.f - m) * dh + dhn * z;
 }
 // GRU-1 backward (elementwise)
@@ -302,10 +319,10 @@ gru1_bwd_kernel(const float* __restrict__ dpre_h, const float* __restrict__ G1, 
   const float dz = dp_ * (h - p), dprop = dp_ * (1.f - z);
   const float dpp = dprop * (1.f - p * p);
   dEh[i] = dpp;
-  dUH[i] = dpp * r;
+  dUH[(size_t)b * kLdB + j] = dpp * r;
   const float dr = dpp * UH[i];
-  dG1[(size_t)b * 2 * kN + j] = dr * r * (1.f - r);
-  dG1[(size_t)b * 2 * kN + kN + j] = dz * z * (1.f - z);
+  dG1[(size_t)b * kLdB + j] = dr * r * (1.f - r);
+  dG1[(size_t)b * kLdB + kN + j] = dz * z * (1.f - z);
   dh_out[i] = (1.f - m) * d + dp_ * z;
 }
 // d alpha[b,l] = a[b,l,:] . dctx[b,:] + dAP[b,l]    (warp per position)
@@ -508,12 +525,17 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_LAUNCH_CHECK();
   WAP_CHECK(launch_pdl(maxout_drop_bwd_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.dMO, W.dLG, TB, dropout, seed, g_seed_src));
   WAP_LAUNCH_CHECK();
-  WAP_TRY(gemm_tn_atomic(st, W.H + (size_t)B * kN, kN, W.dLG, kMw, g + P.Wh, kMw, kN, kMw, TB));
-  WAP_TRY(gemm_tn_atomic(st, W.CTX, kD, W.dLG, kMw, g + P.Wc, kMw, kD, kMw, TB));
-  WAP_TRY(gemm_tn_atomic(st, W.EMB, kMw, W.dLG, kMw, g + P.Wy, kMw, kMw, kMw, TB));
-  WAP_TRY(colsum(st, W.dLG, kMw, TB, kMw, g + P.bh));
-  WAP_TRY(colsum(st, W.dLG, kMw, TB, kMw, g + P.bc));
-  WAP_TRY(colsum(st, W.dLG, kMw, TB, kMw, g + P.by));
+  {   // weight gradients of the logit layer: side stream (joined together with the tail, see below)
+    SideStreams* sh = overlap_enabled() ? side_streams() : nullptr;
+    cudaStream_t swh = sh != nullptr ? sh->s[1] : st;
+    if (sh != nullptr) { WAP_CHECK(cudaEventRecord(sh->fork[1], st)); WAP_CHECK(cudaStreamWaitEvent(swh, sh->fork[1], 0)); }
+    WAP_TRY(gemm_tn_atomic(swh, W.H + (size_t)B * kN, kN, W.dLG, kMw, g + P.Wh, kMw, kN, kMw, TB));
+    WAP_TRY(gemm_tn_atomic(swh, W.CTX, kD, W.dLG, kMw, g + P.Wc, kMw, kD, kMw, TB));
+    WAP_TRY(gemm_tn_atomic(swh, W.EMB, kMw, W.dLG, kMw, g + P.Wy, kMw, kMw, kMw, TB));
+    WAP_TRY(colsum(swh, W.dLG, kMw, TB, kMw, g + P.bh));
+    WAP_TRY(colsum(swh, W.dLG, kMw, TB, kMw, g + P.bc));
+    WAP_TRY(colsum(swh, W.dLG, kMw, TB, kMw, g + P.by));
+  }
   WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wh, kMw, W.dHlog, kN, TB, kN, kMw, nullptr, false));
   WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wc, kMw, W.dCTX, kD, TB, kD, kMw, nullptr, false));
   WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wy, kMw, W.dEMB, kMw, TB, kMw, kMw, nullptr, false));
@@ -522,55 +544,68 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_CHECK(cudaMemsetAsync(W.dAP0, 0, sizeof(float) * B * L, st));
   WAP_CHECK(cudaMemsetAsync(W.dSP, 0, sizeof(float) * TB * kNA, st));
   float* dh_in = W.dh0; float* dh_out = W.dh1; float* dAP_in = W.dAP0; float* dAP_out = W.dAP1;
+  // Two chains per step.  Main stream: gru2_bwd -> [dG2|dCH] -> dctx -> dalpha -> softmax_bwd -> dz -> dSP -> dpre_h -> gru1_bwd ->
+  // [dG1|dUH] -> dh.  Side stream: [dPH2|dG2] -> dpre_h (joins before gru1_bwd) and the coverage backward DZ -> DF -> dAP (joins before
+  // the next step's dalpha).
+  SideStreams* sl = overlap_enabled() ? side_streams() : nullptr;
+  cudaStream_t s2 = sl != nullptr ? sl->s[2] : st;
+  auto fork2 = [&](int e) -> int {
+    if (sl != nullptr) { WAP_CHECK(cudaEventRecord(sl->fork[e], st)); WAP_CHECK(cudaStreamWaitEvent(s2, sl->fork[e], 0)); }
+    return 0;
+  };
+  bool pend_ap = false;
   for (int t = T - 1; t >= 0; --t) {
     const size_t r = (size_t)t * B;
     const float* ym = y_mask + r;
     float* dctx = W.dCTX + r * kD;                 // holds the logit-path part already
     WAP_CHECK(launch_pdl(gru2_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, dh_in, W.dHlog + r * kN, W.G2 + r * 2 * kN, W.PROP2 + r * kN, W.PH2 + r * kN,
-                                                        W.PREH + r * kN, ym, W.dG2 + r * 2 * kN, W.dCH + r * kN, W.dPH2 + r * kN, W.dpre_h, B));
+                         W.PREH + r * kN, ym, W.dG2 + r * kLdA, W.dCH + r * kLdA, W.dPH2 + r * kLdA, W.dpre_h, B));
     WAP_LAUNCH_CHECK();
-    {   // dctx += dG2*W_c_z_r^T + dCH*W_c_h_nl^T ; dpre_h += dG2*U_hz_hr_nl^T + dPH2*U_rh_nl^T
-      SkinnyArgs a; a.ids = nullptr; a.Bn = B;
-      a.X = W.dG2 + r * 2 * kN; a.ldx = 2 * kN; a.K = 2 * kN; a.nseg = 2;
+    WAP_TRY(fork2(2));
+    {   // side: dpre_h += [dPH2|dG2] * [U_rh_nl^T; U_hz_hr_nl^T]
+      SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dPH2 + r * kLdA; a.ldx = kLdA; a.K = 3 * kN; a.nseg = 1;
+      a.seg[0] = {W.T_Urhnl, kN, kN, W.dpre_h, kN};
+      WAP_TRY(skinny_gemm(s2, a));
+      if (sl != nullptr) WAP_CHECK(cudaEventRecord(sl->done[6], s2));
+    }
+    {   // dctx += [dG2|dCH] * [W_c_z_r^T; W_c_h_nl^T]
+      SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dG2 + r * kLdA; a.ldx = kLdA; a.K = 3 * kN; a.nseg = 1;
       a.seg[0] = {W.T_Wczr, kD, kD, dctx, kD};
-      a.seg[1] = {W.T_Uhzhrnl, kN, kN, W.dpre_h, kN};
-      WAP_TRY(skinny_gemm(st, a));
-      a.X = W.dCH + r * kN; a.ldx = kN; a.K = kN; a.nseg = 1;
-      a.seg[0] = {W.T_Wchnl, kD, kD, dctx, kD};
-      WAP_TRY(skinny_gemm(st, a));
-      a.X = W.dPH2 + r * kN; a.seg[0] = {W.T_Urhnl, kN, kN, W.dpre_h, kN};
       WAP_TRY(skinny_gemm(st, a));
     }
+    if (sl != nullptr && pend_ap) WAP_CHECK(cudaStreamWaitEvent(st, sl->done[7], 0));     // dAP_in of this step (side-stream gather of step t+1)
     WAP_CHECK(launch_pdl(dalpha_kernel, cdiv(B * L * 32, 256), 256, 0, st, ann, dctx, dAP_in, W.dalpha, B, L));
     WAP_LAUNCH_CHECK();
     WAP_CHECK(launch_pdl(softmax_bwd_kernel, B, 256, 0, st, W.ALPHA + r * L, W.dalpha, W.de, L));
     WAP_LAUNCH_CHECK();
     float* DZt = W.DZ + r * L * kNA;
     WAP_CHECK(launch_pdl(dz_kernel, dim3(cdiv(L, kDzPix), B), 128, 0, st, W.TANH + r * L * kNA, W.de, p + P.V_a, DZt, W.dSP + r * kNA,
-                                                         g + P.V_a, g + P.V_a_b, L));
+                         g + P.V_a, g + P.V_a_b, L));
     WAP_LAUNCH_CHECK();
+    WAP_TRY(fork2(3));
+    // side: coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
+    if (tc) WAP_TRY(tc_gemm(s2, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
+    else WAP_TRY(gemm_nt(s2, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
+    WAP_CHECK(launch_pdl(cov_bwd_gather_kernel, cdiv(B * L, 32), 32 * kGatherWarps, 0, s2, W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0));
+    WAP_LAUNCH_CHECK();
+    if (sl != nullptr) { WAP_CHECK(cudaEventRecord(sl->done[7], s2)); pend_ap = true; }
     {   // dpre_h += dSP*W_a^T
       SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dSP + r * kNA; a.ldx = kNA; a.K = kNA; a.nseg = 1;
       a.seg[0] = {W.T_Wa, kN, kN, W.dpre_h, kN};
       WAP_TRY(skinny_gemm(st, a));
     }
-    // coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
-    if (tc) WAP_TRY(tc_gemm(st, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
-    else WAP_TRY(gemm_nt(st, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
-    WAP_CHECK(launch_pdl(cov_bwd_gather_kernel, cdiv(B * L, 32), 32 * kGatherWarps, 0, st, W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0));
-    WAP_LAUNCH_CHECK();
+    if (sl != nullptr) WAP_CHECK(cudaStreamWaitEvent(st, sl->done[6], 0));
     WAP_CHECK(launch_pdl(gru1_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
-                                                        W.dG1 + r * 2 * kN, W.dEh + r * kN, W.dUH + r * kN, dh_out, B));
+                         W.dG1 + r * kLdB, W.dEh + r * kN, W.dUH + r * kLdB, dh_out, B));
     WAP_LAUNCH_CHECK();
-    {   // dh_prev += dG1*U_hz_hr^T + dUH*U_rh^T
-      SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dG1 + r * 2 * kN; a.ldx = 2 * kN; a.K = 2 * kN; a.nseg = 1;
+    {   // dh_prev += [dG1|dUH] * [U_hz_hr^T; U_rh^T]
+      SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dG1 + r * kLdB; a.ldx = kLdB; a.K = 3 * kN; a.nseg = 1;
       a.seg[0] = {W.T_Uhzhr, kN, kN, dh_out, kN};
-      WAP_TRY(skinny_gemm(st, a));
-      a.X = W.dUH + r * kN; a.ldx = kN; a.K = kN; a.seg[0] = {W.T_Urh, kN, kN, dh_out, kN};
       WAP_TRY(skinny_gemm(st, a));
     }
     std::swap(dh_in, dh_out); std::swap(dAP_in, dAP_out);
   }
+  if (sl != nullptr && pend_ap) WAP_CHECK(cudaStreamWaitEvent(st, sl->done[7], 0));
   // watch path: dWatch = sum_t DZ_t
   WAP_CHECK(launch_pdl(sum_steps_kernel, cdiv((size_t)B * L * kNA / 4, 256), 256, 0, st, W.DZ, W.dWatch, T, (size_t)B * L * kNA / 4));
   WAP_LAUNCH_CHECK();
@@ -581,24 +616,24 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->fork[1], st)); WAP_CHECK(cudaStreamWaitEvent(sw, ss->fork[1], 0)); }
   // ---- batched weight gradients over all T*B rows
   const float* Hprev = W.H;   // H[0..T-1]
-  WAP_TRY(gemm_tn_atomic(sw, W.EMB, kMw, W.dG1, 2 * kN, g + P.W_yz_yr, 2 * kN, kMw, 2 * kN, TB));
-  WAP_TRY(colsum(sw, W.dG1, 2 * kN, TB, 2 * kN, g + P.b_yz_yr));
+  WAP_TRY(gemm_tn_atomic(sw, W.EMB, kMw, W.dG1, kLdB, g + P.W_yz_yr, 2 * kN, kMw, 2 * kN, TB));
+  WAP_TRY(colsum(sw, W.dG1, kLdB, TB, 2 * kN, g + P.b_yz_yr));
   WAP_TRY(gemm_tn_atomic(sw, W.EMB, kMw, W.dEh, kN, g + P.W_yh, kN, kMw, kN, TB));
   WAP_TRY(colsum(sw, W.dEh, kN, TB, kN, g + P.b_yh));
-  WAP_TRY(gemm_tn_atomic(sw, Hprev, kN, W.dG1, 2 * kN, g + P.U_hz_hr, 2 * kN, kN, 2 * kN, TB));
-  WAP_TRY(gemm_tn_atomic(sw, Hprev, kN, W.dUH, kN, g + P.U_rh, kN, kN, kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, Hprev, kN, W.dG1, kLdB, g + P.U_hz_hr, 2 * kN, kN, 2 * kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, Hprev, kN, W.dUH, kLdB, g + P.U_rh, kN, kN, kN, TB));
   WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dSP, kNA, g + P.W_a, kNA, kN, kNA, TB));
   WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.W_a_b));
   WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.U_f_b));
   WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.U_a_b));
-  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dG2, 2 * kN, g + P.U_hz_hr_nl, 2 * kN, kN, 2 * kN, TB));
-  WAP_TRY(colsum(sw, W.dG2, 2 * kN, TB, 2 * kN, g + P.b_hz_hr_nl));
-  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dPH2, kN, g + P.U_rh_nl, kN, kN, kN, TB));
-  WAP_TRY(colsum(sw, W.dPH2, kN, TB, kN, g + P.b_rh_nl));
-  WAP_TRY(gemm_tn_atomic(sw, W.CTX, kD, W.dG2, 2 * kN, g + P.W_c_z_r, 2 * kN, kD, 2 * kN, TB));
-  WAP_TRY(gemm_tn_atomic(sw, W.CTX, kD, W.dCH, kN, g + P.W_c_h_nl, kN, kD, kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dG2, kLdA, g + P.U_hz_hr_nl, 2 * kN, kN, 2 * kN, TB));
+  WAP_TRY(colsum(sw, W.dG2, kLdA, TB, 2 * kN, g + P.b_hz_hr_nl));
+  WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dPH2, kLdA, g + P.U_rh_nl, kN, kN, kN, TB));
+  WAP_TRY(colsum(sw, W.dPH2, kLdA, TB, kN, g + P.b_rh_nl));
+  WAP_TRY(gemm_tn_atomic(sw, W.CTX, kD, W.dG2, kLdA, g + P.W_c_z_r, 2 * kN, kD, 2 * kN, TB));
+  WAP_TRY(gemm_tn_atomic(sw, W.CTX, kD, W.dCH, kLdA, g + P.W_c_h_nl, kN, kD, kN, TB));
   // embedding: dEMB = dLG*Wy^T (already) + dG1*W_yz_yr^T + dEh*W_yh^T ; scatter-add into the table
-  WAP_TRY(gemm_nt(sw, W.dG1, 2 * kN, p + P.W_yz_yr, 2 * kN, W.dEMB, kMw, TB, kMw, 2 * kN, nullptr, true));
+  WAP_TRY(gemm_nt(sw, W.dG1, kLdB, p + P.W_yz_yr, 2 * kN, W.dEMB, kMw, TB, kMw, 2 * kN, nullptr, true));
   WAP_TRY(gemm_nt(sw, W.dEh, kN, p + P.W_yh, kN, W.dEMB, kMw, TB, kMw, kN, nullptr, true));
   WAP_CHECK(launch_pdl(emb_scatter_kernel, cdiv(TB * kMw, 256), 256, 0, sw, W.dEMB, y, g + P.embed, T, B));
   WAP_LAUNCH_CHECK();

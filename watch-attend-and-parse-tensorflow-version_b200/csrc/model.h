@@ -78,8 +78,8 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training);
 // the caller's stream with events, so the pattern is capturable into a CUDA graph.  overlap_enabled() is false while
 // per-launch profiling is on (wap_profile_enable) or after wap_set_overlap(0).
 struct SideStreams {
-  cudaStream_t s[2];          // 0: encoder weight gradients   1: decoder weight gradients
-  cudaEvent_t fork[2];        // recorded on the main stream, waited by the side stream
+  cudaStream_t s[3];          // 0: encoder weight gradients   1: decoder weight gradients   2: second chain of the decoder scans
+  cudaEvent_t fork[4];        // recorded on the main stream, waited by a side stream
   cudaEvent_t done[8];        // recorded on a side stream, waited by the main stream
 };
 SideStreams* side_streams();  // lazily created; nullptr on failure
