@@ -136,6 +136,8 @@ int wap_adadelta_l2_step(void* stream, float* params, const float* grads, float*
 uint64_t wap_launch_count(void);
 int wap_profile_enable(int on);
 int wap_profile_read(int cls, double* ms, int64_t* launches, double* flops);
+/* algorithmic HBM bytes (operands read once + result written/accumulated once) summed over the recorded launches of a class */
+int wap_profile_read_bytes(int cls, double* bytes);
 int wap_profile_reset(void);
 
 /* ---- fp32 GEMM primitives (exported for the kernel-level parity tests) */
@@ -182,6 +184,9 @@ int wap_set_dropout_seed_source(const uint32_t* seed_dev);
  * attribute so that launch latency overlaps the predecessor's execution; 0 restores plain stream ordering. */
 int wap_set_pdl(int on);
 int wap_get_pdl(void);
+/* ---- debug: CTA (0,0) of every following tcgen05 GEMM launch writes clock64() stamps [k-block][TMA issue, data landed, split done,
+ * MMA issued] into trace (device int64, >= 4 * k-blocks); NULL turns it off */
+int wap_debug_tc_trace(long long* trace);
 /* ---- weight-gradient kernels on side streams (forked/joined with events inside one call; default on) */
 int wap_set_overlap(int on);
 int wap_get_overlap(void);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "wap_launch_count": (C.c_uint64, []),
     "wap_profile_enable": (_i, [_i]),
     "wap_profile_read": (_i, [_i, C.POINTER(C.c_double), C.POINTER(_i64), C.POINTER(C.c_double)]),
+    "wap_profile_read_bytes": (_i, [_i, _vp]),
     "wap_profile_reset": (_i, []),
     "wap_gemm_nn": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
     "wap_gemm_nt": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
@@ -65,6 +66,7 @@ SIGNATURES = {
     "wap_set_dropout_seed_source": (_i, [_vp]),
     "wap_set_pdl": (_i, [_i]),
     "wap_get_pdl": (_i, []),
+    "wap_debug_tc_trace": (_i, [_vp]),
     "wap_set_overlap": (_i, [_i]),
     "wap_get_overlap": (_i, []),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),

@@ -13,6 +13,7 @@ namespace wap {
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_pdl = 1;
+extern long long* g_tc_trace;
 static int g_overlap = 1;
 SideStreams* side_streams() {
   static SideStreams ss; static int state = 0;     // 0: not created, 1: ok, -1: failed
@@ -26,7 +27,8 @@ SideStreams* side_streams() {
 }
 
 // ---- per-class device timing
-struct ProfRec { cudaEvent_t a, b; int cls; double flops; };
+struct ProfRec { cudaEvent_t a, b; int cls; double flops, bytes; };
+static double g_prof_next_bytes = 0.0;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 static std::vector<cudaEvent_t> g_ev_pool;
@@ -35,9 +37,10 @@ static cudaEvent_t ev_get() {
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 bool overlap_enabled() { return g_overlap != 0 && !g_prof_on; }
+void prof_set_bytes(double bytes) { g_prof_next_bytes = bytes; }
 void prof_begin(cudaStream_t st, int cls, double flops) {
-  if (!g_prof_on) return;
-  ProfRec r; r.a = ev_get(); r.b = ev_get(); r.cls = cls; r.flops = flops;
+  if (!g_prof_on) { g_prof_next_bytes = 0.0; return; }
+  ProfRec r; r.a = ev_get(); r.b = ev_get(); r.cls = cls; r.flops = flops; r.bytes = g_prof_next_bytes; g_prof_next_bytes = 0.0;
   cudaEventRecord(r.a, st);
   g_prof.push_back(r);
 }
@@ -112,6 +115,12 @@ int wap_profile_read(int cls, double* ms, int64_t* launches, double* flops) {
     t += e; f += r.flops; ++n;
   }
   if (ms) *ms = t; if (launches) *launches = n; if (flops) *flops = f;
+  return 0;
+}
+int wap_profile_read_bytes(int cls, double* bytes) {
+  double b = 0.0;
+  for (const ProfRec& r : g_prof) if (r.cls == cls) b += r.bytes;
+  if (bytes) *bytes = b;
   return 0;
 }
 int wap_profile_reset(void) {
@@ -284,6 +293,7 @@ int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }
+int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
 int wap_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }
 int wap_get_overlap(void) { return g_overlap; }
 int wap_set_pdl(int on) { wap::g_pdl = on ? 1 : 0; return 0; }

@@ -50,6 +50,7 @@ enum ProfClass {
   kProfTransBwd, kProfCovGemm, kProfOtherGemm, kProfNumClasses
 };
 void prof_begin(cudaStream_t st, int cls, double flops);
+void prof_set_bytes(double bytes);             // algorithmic HBM bytes of the NEXT prof_begin (default: 4(MK+KN+MN) unknown -> 0)
 void prof_end(cudaStream_t st, int cls);
 #define WAP_REQUIRE(cond, ...)                                                       \
   do {                                                                               \

@@ -346,6 +346,7 @@ template <class Cfg, class AL, class BL, class Epi>
 inline int launch_gemm(cudaStream_t st, const AL& A, const BL& Bm, const Epi& epi, int M, int N, int K, int splits = 1,
                        int prof_cls = kProfOtherGemm) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
+  prof_set_bytes(4.0 * ((double)M * K + (double)K * N + (double)M * N));
   prof_begin(st, prof_cls, 2.0 * M * N * K);
   int kps = cdiv(cdiv(K, splits), BK) * BK;
   splits = cdiv(K, kps);

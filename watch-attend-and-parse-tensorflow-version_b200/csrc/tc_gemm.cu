@@ -75,6 +75,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[tmem: lane = row, column = k] * B[smem desc]   (A operand staged in tensor memory)
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// 32 registers per thread -> 32 lanes x 32 consecutive fp32 columns (thread i = TMEM lane base+i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr),
+        "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+        "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+        "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+        "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15])),
+        "r"(__float_as_uint(v[16])), "r"(__float_as_uint(v[17])), "r"(__float_as_uint(v[18])), "r"(__float_as_uint(v[19])),
+        "r"(__float_as_uint(v[20])), "r"(__float_as_uint(v[21])), "r"(__float_as_uint(v[22])), "r"(__float_as_uint(v[23])),
+        "r"(__float_as_uint(v[24])), "r"(__float_as_uint(v[25])), "r"(__float_as_uint(v[26])), "r"(__float_as_uint(v[27])),
+        "r"(__float_as_uint(v[28])), "r"(__float_as_uint(v[29])), "r"(__float_as_uint(v[30])), "r"(__float_as_uint(v[31]))
+      : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // arrives on the mbarrier once all previously issued MMAs have completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -118,17 +144,28 @@ struct TcShape {
   int nkb;                // number of 32-wide K blocks
   // im2col mode
   int B, H, W, kb_per_tap, TW, TH, tiles_x, tiles_y;
+  long long* trace;       // debug: CTA 0 records clock64() per k-block: [kb][0 TMA issue, 1 data landed (splitter/MMA saw full), 2 split done, 3 MMA issued]
 };
 
 // X3 = error-compensated "3xTF32": D = a_hi*b_hi + a_lo*b_hi + a_hi*b_lo (fp32-grade accuracy).
-// Stage layout: [A (hi)] [A lo] [B hi] [B lo]; the lo tiles exist only when X3.
+// The three MMAs of a k-block would read A twice and B three times from shared memory, and the hi/lo split of the raw fp32
+// A tile would add a read and two writes: 172 KB of shared-memory traffic per 128x96x32 k-block, which is what bounded the
+// X3 kernels (~1390 cycles per k-block at 128 B/clk).  So the splitter warps write a_hi / a_lo into TENSOR MEMORY (lane =
+// tile row, 32 columns each) and the MMAs take A from TMEM: shared memory then only sees the TMA write, one read of A by the
+// splitter and the B reads.  Stage layout in smem: [A raw] [B hi] [B lo] (B lo only when X3).
 template <int BN, bool X3> struct TcSmem {
-  static constexpr int kStages = kTcBK == 16 ? (X3 ? 3 : 4) : (X3 ? 3 : (BN <= 32 ? 4 : 3));   // sized for 2 CTAs/SM when possible
+  // These kernels are bound by bytes in flight per SM (Little's law over the ~1.5 us L2->smem TMA latency), so the X3 variants
+  // (one CTA per SM) take as many stages as the 227 KB of shared memory hold; single-pass variants are sized for 2 CTAs/SM.
+#ifndef WAP_TC_X3_DEEP
+#define WAP_TC_X3_DEEP 1
+#endif
+  static constexpr int kStages = kTcBK == 16 ? (X3 ? 3 : 4)
+                               : (X3 ? (BN <= 96 ? 4 : 3) : (BN <= 32 ? 4 : 3));     // X3: 4 x 64 TMEM columns of A ring + 2 x 128 accumulator columns = 512
   static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
   static constexpr int kBBytes = BN * kTcBK * 4;
-  static constexpr int kStage = (X3 ? 2 : 1) * (kABytes + kBBytes);
+  static constexpr int kStage = kABytes + (X3 ? 2 : 1) * kBBytes;
   static constexpr int kBarOff = kStages * kStage;
-  static constexpr int kStatOff = kBarOff + 128;                    // barriers + tmem slot
+  static constexpr int kStatOff = kBarOff + 256;                    // barriers + tmem slot
   static constexpr int kTotal = kStatOff + 2 * BN * 4 + 1024;       // + alignment slack
 };
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -140,8 +177,12 @@ __device__ __forceinline__ float tf32_rna_dev(float x) {
   return __uint_as_float(u);
 }
 
+// X3 kernels carry a second group of four splitter warps (warps 6..9): the split of one k-block is a serial chain
+// (shared-memory loads -> cvt -> tcgen05.st -> wait::st -> arrive) of ~1000 cycles, twice the tensor time of the k-block
+// (12 MMAs x 48 cycles), so two groups take alternate k-blocks.
+template <bool X3> struct TcThreads { static constexpr int kN = X3 ? kTcThreads + 128 : kTcThreads; };
 template <int BN, bool IM2COL, bool X3>
-__global__ void __launch_bounds__(kTcThreads, (X3 && kTcBK == 32) ? 1 : 2)
+__global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
   pdl_sync();
@@ -150,7 +191,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // X3 keeps the two small correction products in a SECOND accumulator (columns [kAcc2, kAcc2+BN)) so that their
   // fp32 accumulation error is relative to their own 2^-11-times smaller magnitude; the epilogue adds the two.
   constexpr uint32_t kAcc2 = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;
-  constexpr uint32_t kTmemCols = (X3 ? 2 : 1) * (BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256);
+  constexpr uint32_t kAccCols = (X3 ? 2 : 1) * (BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256);
+  constexpr uint32_t kARing = kAccCols;                           // X3: stage s keeps a_hi at kARing + 64 s, a_lo 32 columns further
+  constexpr uint32_t kNeed = kAccCols + (X3 ? 64u * kTcStages : 0u);
+  constexpr uint32_t kTmemCols = kNeed <= 32 ? 32 : kNeed <= 64 ? 64 : kNeed <= 128 ? 128 : kNeed <= 256 ? 256 : 512;
+  static_assert(kNeed <= 512, "TMEM budget");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
@@ -181,7 +226,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     fence_barrier_init();
   }
   if (epi.stats != nullptr)
-    for (int i = threadIdx.x; i < 2 * BN; i += kTcThreads) s_stat[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -195,8 +240,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1);
+        if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) sh.trace[kb * 4 + 0] = clock64();
         uint8_t* sa = smem + s * S::kStage;
-        uint8_t* sb = sa + (X3 ? 2 : 1) * S::kABytes;
+        uint8_t* sb = sa + S::kABytes;
         mbar_expect_tx(&full_bar[s], S::kABytes + (X3 ? 2 : 1) * S::kBBytes);
         if (IM2COL) {
           const int tap = kb / sh.kb_per_tap, cb = kb - tap * sh.kb_per_tap;
@@ -217,18 +263,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t ph = (kb / kTcStages) & 1;
         mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
         tc_fence_after();
+        if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) sh.trace[kb * 4 + 3] = clock64();
         const uint32_t sa = smem_u32(smem + s * S::kStage);
-        const uint32_t sb = sa + (X3 ? 2 : 1) * S::kABytes;
+        const uint32_t sb = sa + S::kABytes;
 #pragma unroll
         for (int k = 0; k < kTcBK / 8; ++k) {
-          const uint64_t ad = make_kmajor_sw128_desc(sa + k * 32);
           const uint64_t bd = make_kmajor_sw128_desc(sb + k * 32);
-          umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           if (X3) {
-            const uint64_t ald = make_kmajor_sw128_desc(sa + S::kABytes + k * 32);
+            const uint32_t ah = tmem_base + kARing + (uint32_t)s * 64u + (uint32_t)k * 8u, al = ah + 32u;
             const uint64_t bld = make_kmajor_sw128_desc(sb + S::kBBytes + k * 32);
-            umma_tf32(tmem_base + kAcc2, ald, bd, idesc, (kb | k) != 0 ? 1u : 0u);     // a_lo * b_hi
-            umma_tf32(tmem_base + kAcc2, ad, bld, idesc, 1u);                          // a_hi * b_lo
+            umma_tf32_ts(tmem_base, ah, bd, idesc, (kb | k) != 0 ? 1u : 0u);            // a_hi * b_hi
+            umma_tf32_ts(tmem_base + kAcc2, al, bd, idesc, (kb | k) != 0 ? 1u : 0u);    // a_lo * b_hi
+            umma_tf32_ts(tmem_base + kAcc2, ah, bld, idesc, 1u);                        // a_hi * b_lo
+          } else {
+            const uint64_t ad = make_kmajor_sw128_desc(sa + k * 32);
+            umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
@@ -238,28 +287,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else {
     // ================================================= epilogue (warps 2..5)
     if (X3) {
-      // ---- operand splitter (main loop): A tile (raw fp32 from TMA) -> hi = rna_tf32(a) in place, lo = a - hi.
-      // Element-wise at identical offsets, so the 128B swizzle pattern is preserved without any index math.
-      const int t = threadIdx.x - 64;
-      for (int kb = 0; kb < sh.nkb; ++kb) {
+      // ---- operand splitter (main loop): thread = tile row.  Reads its 128-byte row of the raw fp32 A tile (undoing the
+      // 128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), splits it into hi = rna_tf32(a) and lo = a - hi
+      // and stores both into the TMEM ring of this stage; the MMAs take A from there.
+      const int qq = warp & 3, rr = qq * 32 + lane;
+      for (int kb = warp >= 6 ? 1 : 0; kb < sh.nkb; kb += 2) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
         mbar_wait(&full_bar[s], ph);
-        float4* hi = reinterpret_cast<float4*>(smem + s * S::kStage);
-        float4* lo = reinterpret_cast<float4*>(smem + s * S::kStage + S::kABytes);
+        if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 127) == 64) sh.trace[kb * 4 + 1] = clock64();
+        const float4* row = reinterpret_cast<const float4*>(smem + s * S::kStage + rr * 128);
+        float hi[32], lo[32];
 #pragma unroll
-        for (int i = 0; i < S::kABytes / 16 / 128; ++i) {
-          const float4 v = hi[t + i * 128];
-          float4 h, l;
-          h.x = tf32_rna_dev(v.x); h.y = tf32_rna_dev(v.y); h.z = tf32_rna_dev(v.z); h.w = tf32_rna_dev(v.w);
-          l.x = v.x - h.x; l.y = v.y - h.y; l.z = v.z - h.z; l.w = v.w - h.w;
-          hi[t + i * 128] = h; lo[t + i * 128] = l;
+        for (int c = 0; c < 8; ++c) {
+          const float4 v = row[c ^ (rr & 7)];
+          hi[4 * c + 0] = tf32_rna_dev(v.x); hi[4 * c + 1] = tf32_rna_dev(v.y); hi[4 * c + 2] = tf32_rna_dev(v.z); hi[4 * c + 3] = tf32_rna_dev(v.w);
+          lo[4 * c + 0] = v.x - hi[4 * c + 0]; lo[4 * c + 1] = v.y - hi[4 * c + 1]; lo[4 * c + 2] = v.z - hi[4 * c + 2]; lo[4 * c + 3] = v.w - hi[4 * c + 3];
         }
-        fence_proxy_async();                 // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        const uint32_t ta = tmem_base + ((uint32_t)(qq * 32) << 16) + kARing + (uint32_t)s * 64u;
+        tmem_st32(ta, hi);
+        tmem_st32(ta + 32u, lo);
+        tmem_wait_st();
+        tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&split_bar[s]);
+        if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 127) == 64) sh.trace[kb * 4 + 2] = clock64();
       }
     }
+    if (warp >= 6) goto tail;                // second splitter group: no epilogue role
+    {
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;             // output row within the tile
     bool valid; size_t mrow;
@@ -338,7 +394,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
     }
+    }
   }
+tail:
   tc_fence_before();
   __syncthreads();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
@@ -371,12 +429,12 @@ struct WgShape {
 
 template <int NBB, bool X3> struct WgSmem {
   static constexpr int kNBA = 4;
-  static constexpr int kStages = 3;
+  static constexpr int kStages = (X3 && WAP_TC_X3_DEEP) ? (NBB <= 1 ? 5 : 4) : 3;
   static constexpr int kABytes = kNBA * kWgBlk;                    // 16384
   static constexpr int kBBytes = NBB * kWgBlk;
   static constexpr int kStage = (X3 ? 2 : 1) * (kABytes + kBBytes);
   static constexpr int kBarOff = kStages * kStage;
-  static constexpr int kTotal = kBarOff + 128 + 1024;
+  static constexpr int kTotal = kBarOff + 256 + 1024;
 };
 
 // MN-major 32-bit operands must use the "128-byte swizzle with 32-byte atoms" layout (UMMA layout type 1,
@@ -573,6 +631,7 @@ static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_
   return 0;
 }
 
+long long* g_tc_trace = nullptr;
 template <int BN, bool IM2COL, bool X3>
 static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
                       const TcShape& sh, dim3 grid, int prof_cls, double flops) {
@@ -581,8 +640,9 @@ static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap&
     WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3>::kTotal));
     configured = true;
   }
+  TcShape sh2 = sh; sh2.trace = g_tc_trace;
   prof_begin(st, prof_cls, flops);
-  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3>, grid, kTcThreads, TcSmem<BN, X3>::kTotal, st, ta, tb, tblo, epi, sh));
+  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3>, grid, TcThreads<X3>::kN, TcSmem<BN, X3>::kTotal, st, ta, tb, tblo, epi, sh2));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
@@ -633,6 +693,7 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
   dim3 grid(cdiv(M, kTcBM), cdiv(N, BN));
   const double flops = 2.0 * M * N * K;
   const CUtensorMap* pl = Bt_lo != nullptr ? &tbl : nullptr;
+  prof_set_bytes(4.0 * ((double)M * K + (double)N * K * (Bt_lo != nullptr ? 2 : 1) + (double)M * N * (epi.accumulate ? 2 : 1)));
   if (BN == 32) return launch_tc<32, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   if (BN == 96) return launch_tc<96, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   return launch_tc<128, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
@@ -661,6 +722,7 @@ int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, in
   sh.B = B; sh.H = H; sh.W = W; sh.kb_per_tap = C / kTcBK; sh.TW = TW; sh.TH = TH; sh.tiles_x = cdiv(W, TW); sh.tiles_y = cdiv(H, TH);
   dim3 grid(sh.tiles_x * sh.tiles_y * B, cdiv(N, BN));
   const double flops = 2.0 * sh.M * N * K;
+  prof_set_bytes(4.0 * ((double)sh.M * C + (double)Nrows * K * (Wt_lo != nullptr ? 2 : 1) + (double)sh.M * N));   // every input element once
   if (BN == 32) return launch_tc<32, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   if (BN == 96) return launch_tc<96, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   return launch_tc<128, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
@@ -707,6 +769,7 @@ int tc_wgrad_1x1(cudaStream_t st, const float* X, int ldx, const float* dY, int 
   const int mt = cdiv(C, kTcBM), splits = pick_splits(sh.nstages, mt);
   sh.stages_per_split = cdiv(sh.nstages, splits);
   dim3 grid(mt, 1, cdiv(sh.nstages, sh.stages_per_split));
+  prof_set_bytes(4.0 * ((double)Mpix * C + (double)Mpix * N + (double)C * N));
   return launch_wg<3, false>(st, tx, ty, dW, sh, grid, x3, prof_cls, 2.0 * Mpix * C * N);
 }
 
@@ -734,6 +797,7 @@ int tc_wgrad_3x3(cudaStream_t st, const float* X, int ldx, const float* dY, int 
   const int mt = cdiv(9 * C, kTcBM), splits = pick_splits(sh.nstages, mt);
   sh.stages_per_split = cdiv(sh.nstages, splits);
   dim3 grid(mt, 1, cdiv(sh.nstages, sh.stages_per_split));
+  prof_set_bytes(4.0 * ((double)B * H * W * (C + 32) + 9.0 * C * N));
   return launch_wg<1, true>(st, tx, ty, dW, sh, grid, x3, prof_cls, 2.0 * B * H * W * 9 * C * N);
 }
 
