@@ -187,6 +187,10 @@ int wap_get_pdl(void);
 /* ---- debug: CTA (0,0) of every following tcgen05 GEMM launch writes clock64() stamps [k-block][TMA issue, data landed, split done,
  * MMA issued] into trace (device int64, >= 4 * k-blocks); NULL turns it off */
 int wap_debug_tc_trace(long long* trace);
+/* ---- debug: the bounded mbarrier waits of the tcgen05 kernels trap instead of hanging; the first call arms a note in host-mapped
+ * memory, later calls return them: out[1] = count, then notes of 8 ints from out[8]: {site + 100*k-block, blockIdx.x, blockIdx.y, warp,
+ * parity, gridDim.x, gridDim.y, blockDim.x} */
+int wap_debug_trap_info(int* out256);
 /* ---- weight-gradient kernels on side streams (forked/joined with events inside one call; default on) */
 int wap_set_overlap(int on);
 int wap_get_overlap(void);

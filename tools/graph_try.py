@@ -14,8 +14,13 @@ imgs, caps = synth.synth_batch(0, B, H, W, T)
 x, xm, y, ym = wap_b200.prepare_data(imgs, caps)
 xd, xmd = torch.as_tensor(x).cuda(), torch.as_tensor(xm).cuda()
 yd, ymd = torch.as_tensor(y).cuda().int(), torch.as_tensor(ym).cuda()
+import ctypes as C
+trap = (C.c_int * 256)(); eng.L.wap_debug_trap_info(trap)
 def step():
-    eng.forward_backward(xd, yd, xmd, ymd, True, 5); eng.apply_update(1.0)
+    try:
+        eng.forward_backward(xd, yd, xmd, ymd, True, 5); eng.apply_update(1.0)
+    except Exception as e:
+        eng.L.wap_debug_trap_info(trap); print("TRAP NOTES", trap[1], [list(trap[8 + 8 * i: 16 + 8 * i]) for i in range(min(trap[1], 30))]); raise
 def timeit(f, n=20):
     for _ in range(3): f()
     torch.cuda.synchronize(); a = torch.cuda.Event(True); b = torch.cuda.Event(True)

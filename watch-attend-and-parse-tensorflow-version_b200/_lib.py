@@ -11,7 +11,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libwap_b200.so")
+LIB_PATH = os.environ.get("WAP_B200_LIB") or os.path.join(_HERE, "libwap_b200.so")     # env override: debugging aid (A/B builds)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "wap_abi.h")
 
 _vp, _i, _i64, _u32, _f = C.c_void_p, C.c_int, C.c_int64, C.c_uint32, C.c_float
@@ -67,6 +67,7 @@ SIGNATURES = {
     "wap_set_pdl": (_i, [_i]),
     "wap_get_pdl": (_i, []),
     "wap_debug_tc_trace": (_i, [_vp]),
+    "wap_debug_trap_info": (_i, [_vp]),
     "wap_set_overlap": (_i, [_i]),
     "wap_get_overlap": (_i, []),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),

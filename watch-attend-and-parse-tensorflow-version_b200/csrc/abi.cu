@@ -14,6 +14,7 @@ static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_pdl = 1;
 extern long long* g_tc_trace;
+const int* trap_note_host();
 static int g_overlap = 1;
 SideStreams* side_streams() {
   static SideStreams ss; static int state = 0;     // 0: not created, 1: ok, -1: failed
@@ -292,6 +293,12 @@ int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int
 }
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
+}
+int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies them: [1] = count, notes of 8 ints from [8] */
+  const int* h = wap::trap_note_host();
+  if (h == nullptr) return -1;
+  if (out256) for (int i = 0; i < 256; ++i) out256[i] = h[i];
+  return 0;
 }
 int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
 int wap_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }

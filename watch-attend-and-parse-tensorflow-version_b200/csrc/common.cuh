@@ -29,6 +29,8 @@ extern unsigned long long g_launches;          // abi.cu: kernels launched by th
 // griddepcontrol.wait returns when the preceding grids have completed and their writes are visible (immediately when the
 // kernel was launched without the attribute), and launch_dependents then lets the successor start queueing.
 extern int g_pdl;                              // abi.cu: wap_set_pdl()
+// (Measured and rejected: triggering before the wait - so that barrier/TMEM set-up or weight prefetch overlap the predecessor -
+// gained nothing in the skinny GEMMs, cost 0.2 ms/step in the tcgen05 kernels, and both together ended in launch failures.)
 __device__ __forceinline__ void pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");

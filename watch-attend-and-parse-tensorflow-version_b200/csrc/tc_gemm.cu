@@ -36,11 +36,30 @@ __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
       : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
   return ok != 0;
 }
-// bounded wait: a pipeline bug traps (launch failure) instead of hanging the GPU
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// bounded wait: a pipeline bug traps (launch failure) instead of hanging the GPU.  Before trapping the waiter leaves a note in
+// host-mapped memory (wap_debug_trap_info): {site, blockIdx.x, blockIdx.y, warp, parity, gridDim.x, gridDim.y, blockDim.x}.
+__device__ int* g_trap_note = nullptr;
+__device__ __noinline__ void mbar_timeout(int site, uint32_t parity) {
+  if (g_trap_note != nullptr) {
+    const int slot = atomicAdd_system(g_trap_note + 1, 1);            // [0] unused, [1] count, then 8 ints per note
+    if (slot < 30) {
+      volatile int* n = g_trap_note + 8 + 8 * slot;
+      n[1] = blockIdx.x; n[2] = blockIdx.y; n[3] = threadIdx.x >> 5; n[4] = (int)parity; n[5] = gridDim.x; n[6] = gridDim.y; n[7] = blockDim.x;
+      n[0] = site;
+    }
+    __threadfence_system();
+    for (volatile int d = 0; d < 2000000; ++d) {}                      // let the other stuck waiters leave their notes too
+  }
+  __trap();
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int site = 0) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
+#ifdef WAP_TRAP_NOTES          // debug builds only (build.sh -DWAP_TRAP_NOTES): the note call costs 0.66 ms per training step
+    if (++spins > kSpinLimit) mbar_timeout(site, parity);
+#else
     if (++spins > kSpinLimit) __trap();
+#endif
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -177,10 +196,10 @@ __device__ __forceinline__ float tf32_rna_dev(float x) {
   return __uint_as_float(u);
 }
 
-// X3 kernels carry a second group of four splitter warps (warps 6..9): the split of one k-block is a serial chain
-// (shared-memory loads -> cvt -> tcgen05.st -> wait::st -> arrive) of ~1000 cycles, twice the tensor time of the k-block
-// (12 MMAs x 48 cycles), so two groups take alternate k-blocks.
-template <bool X3> struct TcThreads { static constexpr int kN = X3 ? kTcThreads + 128 : kTcThreads; };
+// (A second group of splitter warps taking alternate k-blocks was measured: no gain - the X3 main loop is bound by the tensor
+// pipe plus the TMEM stores of the split, ~1100 cycles per k-block, see DESIGN 3.2 - and with 3 stages a group that skips
+// k-blocks can alias mbarrier parities.  One group of four warps observes every phase of every stage.)
+template <bool X3> struct TcThreads { static constexpr int kN = kTcThreads; };
 template <int BN, bool IM2COL, bool X3>
 __global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
@@ -239,7 +258,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < sh.nkb; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1, 1 + 100 * kb);
         if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) sh.trace[kb * 4 + 0] = clock64();
         uint8_t* sa = smem + s * S::kStage;
         uint8_t* sb = sa + S::kABytes;
@@ -261,7 +280,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int kb = 0; kb < sh.nkb; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
-        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, 2 + 100 * kb);
         tc_fence_after();
         if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) sh.trace[kb * 4 + 3] = clock64();
         const uint32_t sa = smem_u32(smem + s * S::kStage);
@@ -291,10 +310,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), splits it into hi = rna_tf32(a) and lo = a - hi
       // and stores both into the TMEM ring of this stage; the MMAs take A from there.
       const int qq = warp & 3, rr = qq * 32 + lane;
-      for (int kb = warp >= 6 ? 1 : 0; kb < sh.nkb; kb += 2) {
+      for (int kb = 0; kb < sh.nkb; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&full_bar[s], ph, 3 + 100 * kb);
         if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 127) == 64) sh.trace[kb * 4 + 1] = clock64();
         const float4* row = reinterpret_cast<const float4*>(smem + s * S::kStage + rr * 128);
         float hi[32], lo[32];
@@ -328,7 +347,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       valid = (m0 + r) < sh.M;
       mrow = (size_t)(m0 + r);
     }
-    mbar_wait(tmem_full, 0);
+    mbar_wait(tmem_full, 0, 4);
     tc_fence_after();
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
@@ -492,7 +511,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int i = 0; i < ns; ++i) {
         const int st = s_beg + i, s = i % S::kStages;
         const uint32_t ph = (i / S::kStages) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
+        mbar_wait(&empty_bar[s], ph ^ 1, 11 + 100 * i);
         uint8_t* sa = smem + s * S::kStage;
         uint8_t* sb = sa + (X3 ? 2 : 1) * S::kABytes;
         mbar_expect_tx(&full_bar[s], S::kABytes + S::kBBytes);
@@ -524,7 +543,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int i = 0; i < ns; ++i) {
         const int s = i % S::kStages;
         const uint32_t ph = (i / S::kStages) & 1;
-        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph);
+        mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, 12 + 100 * i);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + s * S::kStage);
         const uint32_t sb = sa + (X3 ? 2 : 1) * S::kABytes;
@@ -550,7 +569,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       for (int i = 0; i < ns; ++i) {
         const int s = i % S::kStages;
         const uint32_t ph = (i / S::kStages) & 1;
-        mbar_wait(&full_bar[s], ph);
+        mbar_wait(&full_bar[s], ph, 13 + 100 * i);
         uint8_t* base = smem + s * S::kStage;
         float4* ahi = reinterpret_cast<float4*>(base);
         float4* alo = reinterpret_cast<float4*>(base + S::kABytes);
@@ -573,7 +592,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       }
     }
     const int q = warp & 3, r = q * 32 + lane, m = m0 + r;
-    mbar_wait(tmem_full, 0);
+    mbar_wait(tmem_full, 0, 14);
     tc_fence_after();
     if (sh.dbg != nullptr && blockIdx.x == 0 && blockIdx.z == 0)
       for (int i = threadIdx.x - 64; i < S::kStage / 4; i += 128) sh.dbg[i] = reinterpret_cast<const float*>(smem)[i];
@@ -632,6 +651,17 @@ static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_
 }
 
 long long* g_tc_trace = nullptr;
+static int* g_trap_host = nullptr;
+const int* trap_note_host() {
+  if (g_trap_host == nullptr) {
+    int* dptr = nullptr;
+    if (cudaHostAlloc(&g_trap_host, 1024, cudaHostAllocMapped) != cudaSuccess) return nullptr;
+    memset(g_trap_host, 0, 1024);
+    if (cudaHostGetDevicePointer(&dptr, g_trap_host, 0) != cudaSuccess) return nullptr;
+    cudaMemcpyToSymbol(g_trap_note, &dptr, sizeof(dptr));
+  }
+  return g_trap_host;
+}
 template <int BN, bool IM2COL, bool X3>
 static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
                       const TcShape& sh, dim3 grid, int prof_cls, double flops) {
