@@ -354,7 +354,7 @@ softmax_bwd_kernel(const float* __restrict__ alpha, const float* __restrict__ da
   for (int l = threadIdx.x; l < L; l += 256) { const float a = alpha[(size_t)b * L + l]; de[(size_t)b * L + l] = a * (dalpha[(size_t)b * L + l] - s); }
 }
 // dz[b,l,c] = de[b,l] * V_a[c] * (1 - tanh^2)  -> DZ, dWatch += dz, dSP[b,c] += sum_l dz, dV_a[c] += sum de*tanh, dV_a_b += sum de
-constexpr int kDzPix = 8;
+constexpr int kDzPix = 16;        // 16 rows per CTA: half the atomics on dSP / dV_a of 8 (the contended part), still 128 CTAs x 16 loads in flight
 __global__ void __launch_bounds__(128)
 dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const float* __restrict__ Va,
           float* __restrict__ DZ, float* __restrict__ dSP, float* __restrict__ dVa, float* __restrict__ dVab, int L) {

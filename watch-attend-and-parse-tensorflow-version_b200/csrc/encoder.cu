@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
 //   bwd copy : 1x1 / transition: the HWIO matrix itself [Cin][Cout] (B operand of dgrad, K = Cout)
 //              3x3: [Cin=96][tap'*32 + co], tap' mirrored, co >= 24 zero  (dy2 rows are 32 floats)
 // =====================================================================================
-struct WPrepLayer { int kind, cin, cout; long long w, f, b, fl, bl; };
+struct WPrepLayer { int kind, cin, cout, bld; long long w, f, b, fl, bl; };
 __constant__ WPrepLayer c_wprep[kNumConv];
 
 __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __restrict__ params, float* __restrict__ wsp, int with_bwd) {
@@ -405,7 +405,7 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
     for (int i = t0; i < n_el; i += stride) {
       const int n = i / L.cin, k = i - n * L.cin;
       split(__ldg(w + (size_t)k * L.cout + n), f + i, fl + i);
-      if (with_bwd) split(__ldg(w + i), b + i, bl + i);
+      if (with_bwd) { const int r = i / L.cout, cc = i - r * L.cout; split(__ldg(w + i), b + (size_t)r * L.bld + cc, bl + (size_t)r * L.bld + cc); }
     }
   }
 }
@@ -422,7 +422,7 @@ static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, c
   const ParamLayout& L = layout();
   static WPrepLayer h[kNumConv];   // static: a captured CUDA graph re-reads this host table at every replay
   for (int i = 0; i < kNumConv; ++i) {
-    h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout;
+    h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout; h[i].bld = ws.wt_bwd_ld[i];
     h[i].w = (long long)L.conv[i].w; h[i].f = (long long)ws.wt_fwd[i]; h[i].b = (long long)ws.wt_bwd[i];
     h[i].fl = (long long)ws.wt_fwd_lo[i]; h[i].bl = (long long)ws.wt_bwd_lo[i];
   }
@@ -572,7 +572,8 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   double* red = reinterpret_cast<double*>(wsp + ws.red);
   const float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
   float* G[kBlocks] = {wsp + ws.gbuf[0], wsp + ws.gbuf[1], d_annotation};
-  float* dy1v[2] = {wsp + ws.dy1, wsp + ws.dy1b}; float* dy2v[2] = {wsp + ws.dy2, wsp + ws.dy2b};
+  constexpr int kDy1Ld = 2 * kBottle;
+  float* dy1v[2] = {wsp + ws.dy1b, wsp + ws.dy1}; float* dy2v[2] = {wsp + ws.dy2, wsp + ws.dy2b};     // dy1: odd level -> columns 0..95
   float* da1 = wsp + ws.da1; float* dytr = wsp + ws.dytr;
   // Weight gradients only feed `grads`, so they run on a side stream next to the dgrad -> BN-backward chain of the
   // following levels (which leaves most SMs idle in blocks 1 and 2: 64 and 16 row tiles).  dy1 / dy2 ping-pong between two
@@ -666,24 +667,38 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * kBottle, dy2, sizeof(float) * (size_t)M * kDy2Ld, cudaMemcpyDeviceToDevice, st));
       }
       WAP_TRY(join(2 + par));
-      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, kBottle, true)));
+      WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, kDy1Ld, true)));
       WAP_TRY(fork());
       if (k1 == g_dbg_layer && g_dbg_buf != nullptr)     // [.. | dy1 (M*96)]
-        WAP_CHECK(cudaMemcpyAsync(g_dbg_buf + (size_t)M * (kBottle + kDy2Ld), dy1, sizeof(float) * (size_t)M * kBottle, cudaMemcpyDeviceToDevice, st));
+        WAP_CHECK(cudaMemcpy2DAsync(g_dbg_buf + (size_t)M * (kBottle + kDy2Ld), sizeof(float) * kBottle, dy1, sizeof(float) * kDy1Ld, sizeof(float) * kBottle, M,
+                                    cudaMemcpyDeviceToDevice, st));
       if (tc && (g_tc_debug_mask & 64)) {   // wgrad 1x1: dW[C,96] += buf[:, :C]^T * dy1
-        WAP_TRY(tc_wgrad_1x1(sw, buf[b], ld, dy1, kBottle, M, C, kBottle, grads + c1.w, kBottle, x3, kProfConv1Wgrad));
+        WAP_TRY(tc_wgrad_1x1(sw, buf[b], ld, dy1, kDy1Ld, M, C, kBottle, grads + c1.w, kBottle, x3, kProfConv1Wgrad));
       } else {
         AColMajor A{buf[b], ld, C, M};
-        BRowMajor Bd{dy1, kBottle, M, kBottle};
+        BRowMajor Bd{dy1, kDy1Ld, M, kBottle};
         EpiAtomic e{grads + c1.w, kBottle};
         const int tiles = cdiv(C, 128);
         WAP_TRY((launch_gemm<Cfg128x96>(sw, A, Bd, e, C, kBottle, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv1Wgrad)));
       }
       WAP_TRY(mark(2 + par));
-      if (tc && (g_tc_debug_mask & 4)) {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
-        WAP_TRY(tc_gemm(st, dy1, kBottle, wsp + ws.wt_bwd[k1], lo(ws.wt_bwd_lo[k1]), kBottle, M, C, kBottle, TcEpi{G[b], ld, 1, nullptr, nullptr, 0}, kProfConv1Dgrad));
+      if (tc && (g_tc_debug_mask & 4) && (g_tc_debug_mask & 128)) {
+        // dgrad 1x1, two levels per pass over the block gradient buffer.  The read-modify-write of G[b][:, :C] is what this
+        // K = 96 GEMM costs, so the odd level of a pair only updates the 24 channels the next level's backward reads right
+        // away (its own input slice [C-24, C)) and the even level applies BOTH contributions to [0, C_even) in one K = 192
+        // GEMM: A = [dy1_odd | dy1_even] (adjacent columns of one buffer), B = the pair weight buffer [C][192].
+        const int bld = ws.wt_bwd_ld[k1];
+        if (j & 1) {
+          WAP_TRY(tc_gemm(st, dy1, kDy1Ld, wsp + ws.wt_bwd[k1] + (size_t)(C - kGrowth) * bld, x3 ? wsp + ws.wt_bwd_lo[k1] + (size_t)(C - kGrowth) * bld : nullptr,
+                          bld, M, kGrowth, kBottle, TcEpi{G[b] + (C - kGrowth), ld, 1, nullptr, nullptr, 0}, kProfConv1Dgrad));
+        } else {
+          WAP_TRY(tc_gemm(st, dy1v[1], kDy1Ld, wsp + ws.wt_bwd[k1 + 2], lo(ws.wt_bwd_lo[k1 + 2]), bld, M, C, 2 * kBottle,
+                          TcEpi{G[b], ld, 1, nullptr, nullptr, 0}, kProfConv1Dgrad));
+        }
+      } else if (tc && (g_tc_debug_mask & 4)) {   // dgrad 1x1: G[b][:, :C] += dy1 * W1^T
+        WAP_TRY(tc_gemm(st, dy1, kDy1Ld, wsp + ws.wt_bwd[k1], lo(ws.wt_bwd_lo[k1]), ws.wt_bwd_ld[k1], M, C, kBottle, TcEpi{G[b], ld, 1, nullptr, nullptr, 0}, kProfConv1Dgrad));
       } else {
-        ARowMajor A{dy1, kBottle, M, kBottle};
+        ARowMajor A{dy1, kDy1Ld, M, kBottle};
         BColMajor Bw{params + c1.w, kBottle, kBottle, C};
         EpiStore e{G[b], ld, nullptr, true, nullptr};
         WAP_TRY((launch_gemm<Cfg128x128>(st, A, Bw, e, M, C, kBottle, 1, kProfConv1Dgrad)));

@@ -124,10 +124,10 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
   }
   if (training) {
     for (int b = 0; b < kBlocks - 1; ++b) ws.gbuf[b] = take((size_t)g.M[b] * g.Ctot[b]);
-    ws.dy1 = take((size_t)g.M[0] * kBottle);
+    ws.dy1 = take((size_t)g.M[0] * 2 * kBottle);      // [M, 192]: odd levels in columns 0..95, even levels in 96..191 (ping-pong + pair GEMM)
     ws.da1 = take((size_t)g.M[0] * kBottle);
     ws.dy2 = take((size_t)g.M[0] * kDy2Ld);
-    ws.dy1b = take((size_t)g.M[0] * kBottle);
+    ws.dy1b = ws.dy1 + kBottle;
     ws.dy2b = take((size_t)g.M[0] * kDy2Ld);
     size_t tr = 0;
     for (int b = 0; b < kBlocks - 1; ++b) tr = std::max(tr, (size_t)g.M[b] * (g.Ctot[b] / 2));
@@ -136,9 +136,20 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
   }
   for (int i = 0; i < kNumConv; ++i) {       // tcgen05 weight copies: fwd [N(pad)][K], bwd (dgrad) [Cin][K']
     const ConvLayer& c = L.conv[i];
+    ws.wt_bwd_ld[i] = c.cout;
     if (c.kind == kC1 || c.kind == kTr) {
       ws.wt_fwd[i] = take((size_t)c.cout * c.cin); ws.wt_fwd_lo[i] = take((size_t)c.cout * c.cin);
-      if (training) { ws.wt_bwd[i] = take((size_t)c.cin * c.cout); ws.wt_bwd_lo[i] = take((size_t)c.cin * c.cout); }
+      if (training && c.kind == kTr) { ws.wt_bwd[i] = take((size_t)c.cin * c.cout); ws.wt_bwd_lo[i] = take((size_t)c.cin * c.cout); }
+      if (training && c.kind == kC1) {
+        const int level = (i - (1 + c.block * (2 * kLevels + 1))) / 2;     // 1x1 of level j has conv index base + 2j
+        if ((level & 1) == 0) {          // even level: allocate the pair buffer (rows = Cin of the odd partner = cin + growth)
+          const size_t n = (size_t)(c.cin + kGrowth) * 2 * kBottle;
+          const size_t hi = take(n), lo = take(n);
+          ws.wt_bwd[i] = hi + kBottle; ws.wt_bwd_lo[i] = lo + kBottle;           // even level: columns 96..191
+          ws.wt_bwd[i + 2] = hi; ws.wt_bwd_lo[i + 2] = lo;                       // odd level : columns 0..95
+        }
+        ws.wt_bwd_ld[i] = 2 * kBottle;
+      }
     } else if (c.kind == kC3) {
       ws.wt_fwd[i] = take((size_t)32 * 9 * kBottle); ws.wt_fwd_lo[i] = take((size_t)32 * 9 * kBottle);
       if (training) { ws.wt_bwd[i] = take((size_t)kBottle * 9 * kDy2Ld); ws.wt_bwd_lo[i] = take((size_t)kBottle * 9 * kDy2Ld); }

@@ -69,6 +69,8 @@ struct EncWorkspace {
   //     // largest-block sized scratch (dy2 has row stride kDy2Ld = 32)
   size_t wt_fwd[kNumConv], wt_bwd[kNumConv];   // TF32-rounded K-major weight copies for the tcgen05 path (hi parts)
   size_t wt_fwd_lo[kNumConv], wt_bwd_lo[kNumConv];   // residuals rna(w - hi) for the 3xTF32 mode
+  int wt_bwd_ld[kNumConv];               // row stride of the dgrad copy: 1x1 layers of a level pair (2j+1, 2j) share one [Cin][192] buffer
+                                         // (odd level in columns 0..95, even level in 96..191) so that ONE K=192 GEMM applies both
   size_t red;                            // doubles [2][kMaxBnC]
   size_t total;                          // floats
 };
