@@ -247,6 +247,7 @@ struct BnBwdArgs {
   const float* saved; const float* gamma; const float* beta;
   float* g; int ld_g;                        // [B*Hi*Wi, ld_g]
   double* red;                               // [2][C]: sum g, sum g*xhat
+  double* red_next;                          // the apply kernel zeroes this buffer (2*kMaxBnC doubles) for the next BN backward
   float* dgamma; float* dbeta;               // += (pass 2)
   int dropout; uint32_t seed, site;
   const uint32_t* seed_src;
@@ -340,6 +341,8 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, c
 
 __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   pdl_sync();
+  if (blockIdx.x == 0 && a.red_next != nullptr)
+    for (int i = threadIdx.x; i < 2 * kMaxBnC; i += blockDim.x) a.red_next[i] = 0.0;
   __shared__ float s_k[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC], s_mg[kMaxBnC], s_mgx[kMaxBnC];
   const double cnt = (double)a.B * a.Hi * a.Wi;
   for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
@@ -452,7 +455,8 @@ static int run_bn_act(cudaStream_t st, int pool, const BnActArgs& a) {
 }
 
 static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
-  WAP_CHECK(cudaMemsetAsync(a.red, 0, sizeof(double) * 2 * a.C, st));
+  // a.red was zeroed by the previous BN backward's apply kernel (or by the memset at the start of encoder_backward): a memset
+  // node here would sit between two kernels 110 times per step and break their programmatic dependency
   const size_t npix = (size_t)a.B * a.Hi * a.Wi;
   int ppc = (int)std::max<size_t>(64, cdivz(npix, 148 * 4));
   const int grid = (int)cdivz(npix, ppc);
@@ -569,7 +573,9 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   const EncGeom g = make_geom(B, H, W);
   const EncWorkspace ws = make_enc_workspace(g, true);
   float* saved = wsp + ws.saved;
-  double* red = reinterpret_cast<double*>(wsp + ws.red);
+  double* red2[2] = {reinterpret_cast<double*>(wsp + ws.red), reinterpret_cast<double*>(wsp + ws.red) + 2 * kMaxBnC};
+  int bn_no = 0;
+  WAP_CHECK(cudaMemsetAsync(red2[0], 0, sizeof(double) * 4 * kMaxBnC, st));
   const float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
   float* G[kBlocks] = {wsp + ws.gbuf[0], wsp + ws.gbuf[1], d_annotation};
   constexpr int kDy1Ld = 2 * kBottle;
@@ -597,7 +603,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     a.raw = raw; a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = c.cout;
     a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
     a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
-    a.g = gbuf; a.ld_g = ld_g; a.red = red; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
+    a.g = gbuf; a.ld_g = ld_g; a.red = red2[bn_no & 1]; a.red_next = red2[(bn_no + 1) & 1]; ++bn_no; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
     a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = g_seed_src; a.site = (uint32_t)k;
     a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;

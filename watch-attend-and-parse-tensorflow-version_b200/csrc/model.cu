@@ -102,7 +102,7 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
   auto take = [&](size_t n) { size_t o = off; off += pad4(n); return o; };
   const ParamLayout& L = layout();
   ws.stats = take((size_t)kNumConv * 2 * kMaxBnC * 2);   // doubles (offset is a multiple of 4 floats = 16 B)
-  ws.red = take(2 * kMaxBnC * 2);
+  ws.red = take(2 * kMaxBnC * 2 * 2);     // two [2][kMaxBnC] double buffers: BN backward n uses buffer n&1 and zeroes the other for n+1
   ws.saved = take((size_t)kNumConv * 2 * kMaxBnC);
   ws.stem_raw = take((size_t)g.B * g.Hs * g.Ws * kStemC);
   for (int b = 0; b < kBlocks; ++b) ws.buf[b] = take((size_t)g.M[b] * g.Ctot[b]);
