@@ -273,8 +273,17 @@ def run_ours(args):
         else "tc_gemm_kernel (tcgen05 TF32 implicit GEMM, TMA + TMEM)"
     # These are skinny GEMMs (N = 96 or 24 output channels): 20-50 FLOP per algorithmic byte against a machine balance of
     # ~210 FLOP/B (measured bf16 peak / measured HBM bandwidth), i.e. HBM-bound kernels; the tensor-core figure is kept per class.
+    traffic, traffic_note = None, None
+    try:                                  # measured DRAM traffic of a captured instance of this class (ncu --set full, committed summary)
+        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as fh:
+            tj = json.load(fh)
+        if top in tj:
+            traffic, traffic_note = tj[top]["dram_bytes_per_launch"], {k: v for k, v in tj[top].items() if k != "dram_bytes_per_launch"}
+    except Exception:
+        pass
     roof = {"bound": "hbm", "kernel": f"{kname} [{top}]", "achieved": prof[top]["gbs"], "peak": pk["hbm_gbs"],
-            "unit": "GB/s", "frac": prof[top]["gbs"] / pk["hbm_gbs"], "traffic": None, "peak_source": pk["src"],
+            "unit": "GB/s", "frac": prof[top]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "traffic_instance": traffic_note,
+            "peak_source": pk["src"],
             "tensor_tflops": prof[top]["tflops"], "tensor_peak_tflops": pk["tf"],
             "share_of_step": prof[top]["ms_per_step"] / (ms / args.steps),
             "all_gemm_share_of_step": gemm_ms / (ms / args.steps), "classes": prof,

@@ -168,6 +168,11 @@ int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const fl
  * k = tap*C + ci; rows >= N zero) -> D[B*H*W, N] */
 int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
                    float* D, int ldd, double* stats);
+/* 3x3 SAME conv 96 -> 24 channels in "row tile" form (W <= 128): Wt3[96][288] with Wt3[24*j + co][96*dy + ci] = w[dy][j][ci][co]
+ * (rows 72..95 zero), Wt3_lo its 3xTF32 residual or NULL; D [B*H*W, 24] (ldd), optional statistics [2][24] as in wap_tc_gemm */
+int wap_tc_conv3x3_rowtile(void* stream, const float* x, int ldx, int B, int H, int W, const float* Wt3, const float* Wt3_lo, float* D, int ldd,
+                           double* stats);
+
 /* weight gradients on tensor cores (MN-major operands, split over pixels, RED.ADD into dW):
  * 1x1: dW[C,N] (ldo) += X[Mpix,C](ldx)^T dY[Mpix,N](ldy), N <= 96;
  * 3x3: dW[9*C,N] += im2col3x3(X[B,H,W,C])^T dY[B,H,W,32-padded], N <= 32, ldy = 32.  x3 != 0: 3xTF32. */

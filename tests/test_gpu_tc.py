@@ -106,6 +106,41 @@ def test_tc_conv3x3(report, B, H, W, C, N, x3):
     assert e <= tol and es <= 1e-5 and eq <= 1e-5, (e, es, eq)
 
 
+@pytest.mark.parametrize("x3", [0, 1])
+@pytest.mark.parametrize("B,H,W", [(2, 8, 16), (1, 5, 9), (3, 4, 32), (1, 32, 128), (2, 16, 64), (2, 7, 100), (1, 3, 1)])
+def test_tc_conv3x3_rowtile(report, B, H, W, x3):
+    """Row-tile form of the 96 -> 24 channel 3x3 conv (3 vertical taps in K, horizontal taps added in the epilogue)."""
+    lib, L = _L()
+    C, N = 96, 24
+    g = torch.Generator().manual_seed(B * 100 + H + W)
+    ldx = C + 8
+    xfull = torch.randn(B, H, W, ldx, generator=g).cuda()
+    w = torch.randn(3, 3, C, N, generator=g).cuda()                       # HWIO
+    Wt3 = torch.zeros(96, 3 * C, device="cuda")
+    for dy in range(3):
+        for j in range(3):
+            Wt3[24 * j: 24 * j + 24, C * dy: C * dy + C] = w[dy, j].t()
+    D = torch.full((B * H * W, N), float("nan"), device="cuda")
+    st = torch.zeros(2, N, dtype=torch.float64, device="cuda")
+    x = xfull[..., :C]
+    tol = 3e-6 if x3 else 2e-5
+    if x3:
+        hi = _rna_tf32(Wt3); lo = _rna_tf32(Wt3 - hi)
+        lib.check(L.wap_tc_conv3x3_rowtile(_st(), p(xfull), ldx, B, H, W, p(hi), p(lo), p(D), N, p(st)), "wap_tc_conv3x3_rowtile")
+        ref = torch.nn.functional.conv2d(x.double().permute(0, 3, 1, 2), w.double().permute(3, 2, 0, 1), padding=1)
+    else:
+        lib.check(L.wap_tc_conv3x3_rowtile(_st(), p(xfull), ldx, B, H, W, p(Wt3), None, p(D), N, p(st)), "wap_tc_conv3x3_rowtile")
+        ref = torch.nn.functional.conv2d(_trunc_tf32(x).double().permute(0, 3, 1, 2), _trunc_tf32(w).double().permute(3, 2, 0, 1), padding=1)
+    torch.cuda.synchronize()
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, N)
+    e = rel_err(D.cpu().numpy(), ref.cpu().numpy())
+    tag = f"tc_conv3x3_rowtile_B{B}_{H}x{W}_x3{x3}"
+    report.add("tc", tag, e, tol)
+    es = rel_err(st[0].cpu().numpy(), D.double().sum(0).cpu().numpy()); eq = rel_err(st[1].cpu().numpy(), (D.double() ** 2).sum(0).cpu().numpy())
+    report.add("tc", tag + "_stats", max(es, eq), 1e-5)
+    assert e <= tol and es <= 1e-5 and eq <= 1e-5, (e, es, eq)
+
+
 # --------------------------------------------------------------------------------------
 # whole-encoder / whole-step parity of the tensor-core modes.
 #   'tf32x3' (error-compensated 3xTF32): the tensor-core PARITY mode, held to the same 1e-3 as the FFMA path;

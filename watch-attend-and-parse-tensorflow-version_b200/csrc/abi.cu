@@ -288,6 +288,11 @@ int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, i
   return tc_conv3x3(ST(stream), x, ldx, B, H, W, C, Wt, Wt_lo, Nrows, N, e, kProfOtherGemm);
 }
 int wap_debug_wgrad(float* buf, int idesc_xor) { g_wg_dbg = buf; g_wg_xor = idesc_xor; return 0; }
+int wap_tc_conv3x3_rowtile(void* stream, const float* x, int ldx, int B, int H, int W, const float* Wt3, const float* Wt3_lo, float* D, int ldd,
+                           double* stats) {
+  WAP_REQUIRE(x && Wt3 && D, "wap_tc_conv3x3_rowtile: bad arguments");
+  return tc_conv3x3_rowtile(ST(stream), x, ldx, B, H, W, Wt3, Wt3_lo, TcEpi{D, ldd, 0, stats, nullptr, 0}, kProfConv3Fwd);
+}
 int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_1x1(ST(stream), X, ldx, dY, ldy, Mpix, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }

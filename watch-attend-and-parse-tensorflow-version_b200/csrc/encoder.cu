@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
 //   bwd copy : 1x1 / transition: the HWIO matrix itself [Cin][Cout] (B operand of dgrad, K = Cout)
 //              3x3: [Cin=96][tap'*32 + co], tap' mirrored, co >= 24 zero  (dy2 rows are 32 floats)
 // =====================================================================================
-struct WPrepLayer { int kind, cin, cout, bld; long long w, f, b, fl, bl; };
+struct WPrepLayer { int kind, cin, cout, bld, rowtile; long long w, f, b, fl, bl; };
 __constant__ WPrepLayer c_wprep[kNumConv];
 
 __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __restrict__ params, float* __restrict__ wsp, int with_bwd) {
@@ -392,6 +392,13 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
   auto split = [](float v, float* hi, float* lo) { const float h = tf32_rna(v); *hi = h; *lo = tf32_rna(v - h); };
   if (L.kind == kC3) {
     const int K = 9 * L.cin;                                  // 864
+    if (L.rowtile) {                                          // [96][288]: row 24 j + co, column 96 dy + ci  <-  w[dy][j][ci][co]
+      const int K3 = 3 * L.cin;
+      for (int i = t0; i < 96 * K3; i += stride) {
+        const int n = i / K3, k = i - n * K3, dy = k / L.cin, ci = k - dy * L.cin, j = n / L.cout, co = n - j * L.cout;
+        split(n < 3 * L.cout ? __ldg(w + ((size_t)(dy * 3 + j) * L.cin + ci) * L.cout + co) : 0.f, f + i, fl + i);
+      }
+    } else
     for (int i = t0; i < 32 * K; i += stride) {
       const int n = i / K, k = i - n * K;
       split(n < L.cout ? __ldg(w + (size_t)k * L.cout + n) : 0.f, f + i, fl + i);
@@ -415,17 +422,18 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
 
 static int g_conv_precision = 0;          // 0: fp32 FFMA   1: TF32 tcgen05 (single pass, RNA-rounded operands)   2: 3xTF32 tcgen05 (fp32-grade)
 int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
-int g_tc_debug_mask = 0xFF;               // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd
+int g_tc_debug_mask = 0x1FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd
 const uint32_t* g_seed_src = nullptr;     // wap_set_dropout_seed_source(): device word holding the dropout seed (overrides the by-value seed)
 void set_conv_precision(int mode) { g_conv_precision = mode; }
 int get_conv_precision() { return g_conv_precision; }
 
-static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, const EncWorkspace& ws, bool with_bwd) {
+static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, const EncWorkspace& ws, bool with_bwd, int rowtile_blocks) {
   static bool uploaded = false;
   const ParamLayout& L = layout();
   static WPrepLayer h[kNumConv];   // static: a captured CUDA graph re-reads this host table at every replay
   for (int i = 0; i < kNumConv; ++i) {
     h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout; h[i].bld = ws.wt_bwd_ld[i];
+    h[i].rowtile = (L.conv[i].kind == kC3 && ((rowtile_blocks >> L.conv[i].block) & 1)) ? 1 : 0;
     h[i].w = (long long)L.conv[i].w; h[i].f = (long long)ws.wt_fwd[i]; h[i].b = (long long)ws.wt_bwd[i];
     h[i].fl = (long long)ws.wt_fwd_lo[i]; h[i].bl = (long long)ws.wt_bwd_lo[i];
   }
@@ -483,9 +491,12 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
   float* saved = wsp + ws.saved;
   if (training) WAP_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * kNumConv * 2 * kMaxBnC, st));
   const bool tc = g_conv_precision != 0, x3 = g_conv_precision == 2;
+  int rowtile_blocks = 0;
   if (tc) {
     WAP_REQUIRE(tc_available(), "TF32 tensor-core mode requested but cuTensorMapEncodeTiled is unavailable");
-    WAP_TRY(prep_conv_weights(st, params, wsp, ws, training != 0));
+    // 3x3 convs of a block whose rows fit one 128-pixel tile use the row-tile form (one third of the MMAs): bit b of the mask
+    for (int b = 0; b < kBlocks; ++b) if (g.w[b] <= 128 && (g_tc_debug_mask & 256)) rowtile_blocks |= 1 << b;
+    WAP_TRY(prep_conv_weights(st, params, wsp, ws, training != 0, rowtile_blocks));
   }
   auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
   float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
@@ -535,7 +546,10 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       {   // 3x3 growth  96 -> 24, written in place at channel offset C
         double* sk = training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr;
         if (tc) {
-          WAP_TRY(tc_conv3x3(st, a1, kBottle, B, h, w, kBottle, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), 32, kGrowth, TcEpi{y2, kGrowth, 0, sk, nullptr, 0}, kProfConv3Fwd));
+          if ((rowtile_blocks >> b) & 1)
+            WAP_TRY(tc_conv3x3_rowtile(st, a1, kBottle, B, h, w, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), TcEpi{y2, kGrowth, 0, sk, nullptr, 0}, kProfConv3Fwd));
+          else
+            WAP_TRY(tc_conv3x3(st, a1, kBottle, B, h, w, kBottle, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), 32, kGrowth, TcEpi{y2, kGrowth, 0, sk, nullptr, 0}, kProfConv3Fwd));
         } else {
           AIm2col3 A{a1, kBottle, B, h, w, kBottle, false};
           BRowMajor Bw{params + c3.w, kGrowth, 9 * kBottle, kGrowth};

@@ -200,7 +200,9 @@ __device__ __forceinline__ float tf32_rna_dev(float x) {
 // pipe plus the TMEM stores of the split, ~1100 cycles per k-block, see DESIGN 3.2 - and with 3 stages a group that skips
 // k-blocks can alias mbarrier parities.  One group of four warps observes every phase of every stage.)
 template <bool X3> struct TcThreads { static constexpr int kN = kTcThreads; };
-template <int BN, bool IM2COL, bool X3>
+// IM2COL: 0 plain 2-D A operand; 1 3x3 SAME im2col (9 taps in K); 2 "row tile" 3x3 (3 vertical taps in K, the horizontal
+// taps are 3 x 24 output columns whose results the epilogue adds with a +-1 pixel shift, see tc_conv3x3_rowtile)
+template <int BN, int IM2COL, bool X3>
 __global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
@@ -265,7 +267,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(&full_bar[s], S::kABytes + (X3 ? 2 : 1) * S::kBBytes);
         if (IM2COL) {
           const int tap = kb / sh.kb_per_tap, cb = kb - tap * sh.kb_per_tap;
-          tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
+          if (IM2COL == 2) tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0, y0 + tap - 1, bimg);
+          else tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
         } else {
           tma_load_2d(sa, &tmA, &full_bar[s], kb * kTcBK, m0);
         }
@@ -349,6 +352,76 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_wait(tmem_full, 0, 4);
     tc_fence_after();
+    if constexpr (IM2COL == 2) {
+      // Row-tile 3x3 epilogue.  Accumulator column 24 j + c of tile row q holds the contribution of INPUT pixel q through the
+      // horizontal tap dx = j - 1 (all three vertical taps already summed by the K loop), i.e. it belongs to OUTPUT pixel
+      // q - dx:  D[p, c] = acc[p-1, c] + acc[p, 24 + c] + acc[p+1, 48 + c], neighbours taken within the image row (the tile is
+      // TW = pow2 >= W pixels wide, so a row never continues in another tile; columns >= W are zero A rows).
+      constexpr int kG = 24;
+      float v[96];
+#pragma unroll
+      for (int c = 0; c < 96; c += 32) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v + c);
+        if (X3) {
+          float v2[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + kAcc2 + (uint32_t)c, v2);
+#pragma unroll
+          for (int i = 0; i < 32; ++i) v[c + i] += v2[i];
+        }
+      }
+      float* s_bnd = reinterpret_cast<float*>(smem);          // [4 warps][2][24]: pipeline buffers are free once tmem_full has fired
+      if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < kG; ++c) s_bnd[(q * 2 + 0) * kG + c] = v[c];              // slot 0 of my last row -> first row of the next warp
+      }
+      if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < kG; ++c) s_bnd[(q * 2 + 1) * kG + c] = v[2 * kG + c];     // slot 2 of my first row -> last row of the previous warp
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int tw = r % sh.TW;
+      float o[32];
+#pragma unroll
+      for (int c = 0; c < kG; ++c) {
+        float left = __shfl_up_sync(0xffffffffu, v[c], 1);             // acc[p-1, slot 0]
+        float right = __shfl_down_sync(0xffffffffu, v[2 * kG + c], 1); // acc[p+1, slot 2]
+        if (lane == 0) left = q > 0 ? s_bnd[((q - 1) * 2 + 0) * kG + c] : 0.f;
+        if (lane == 31) right = q < 3 ? s_bnd[((q + 1) * 2 + 1) * kG + c] : 0.f;
+        if (tw == 0) left = 0.f;
+        if (tw == sh.TW - 1) right = 0.f;
+        o[c] = left + v[kG + c] + right;
+      }
+#pragma unroll
+      for (int c = kG; c < 32; ++c) o[c] = 0.f;
+      if (valid) {
+        float* dst = epi.out + mrow * epi.ld;
+#pragma unroll
+        for (int j = 0; j < kG; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
+      if (epi.stats != nullptr) {
+        float a[32], b[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { a[i] = valid ? o[i] : 0.f; b[i] = a[i] * a[i]; }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int i = 0; i < off; ++i) {
+            const float sa_ = upper ? a[i] : a[i + off], ka = upper ? a[i + off] : a[i];
+            const float sb_ = upper ? b[i] : b[i + off], kb_ = upper ? b[i + off] : b[i];
+            a[i] = ka + __shfl_xor_sync(0xffffffffu, sa_, off);
+            b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, off);
+          }
+        }
+        if (lane < kG) { atomicAdd(&s_stat[lane], a[0]); atomicAdd(&s_stat[BN + lane], b[0]); }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        const int t = threadIdx.x - 64;
+        if (t < kG) {
+          atomicAdd(epi.stats + t, (double)s_stat[t]);
+          atomicAdd(epi.stats + sh.N + t, (double)s_stat[BN + t]);
+        }
+      }
+    } else {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
       float v[32];
@@ -412,6 +485,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           atomicAdd(epi.stats + sh.N + n, (double)s_stat[BN + i]);
         }
       }
+    }
     }
     }
   }
@@ -662,7 +736,7 @@ const int* trap_note_host() {
   }
   return g_trap_host;
 }
-template <int BN, bool IM2COL, bool X3>
+template <int BN, int IM2COL, bool X3>
 static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
                       const TcShape& sh, dim3 grid, int prof_cls, double flops) {
   static bool configured = false;
@@ -677,7 +751,7 @@ static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap&
   WAP_LAUNCH_CHECK();
   return 0;
 }
-template <int BN, bool IM2COL>
+template <int BN, int IM2COL>
 static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tblo, const TcEpi& epi,
                      const TcShape& sh, dim3 grid, int prof_cls, double flops) {
   if (tblo != nullptr) return launch_tc1<BN, IM2COL, true>(st, ta, tb, *tblo, epi, sh, grid, prof_cls, flops);
@@ -724,9 +798,9 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
   const double flops = 2.0 * M * N * K;
   const CUtensorMap* pl = Bt_lo != nullptr ? &tbl : nullptr;
   prof_set_bytes(4.0 * ((double)M * K + (double)N * K * (Bt_lo != nullptr ? 2 : 1) + (double)M * N * (epi.accumulate ? 2 : 1)));
-  if (BN == 32) return launch_tc<32, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
-  if (BN == 96) return launch_tc<96, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
-  return launch_tc<128, false>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 32) return launch_tc<32, 0>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 96) return launch_tc<96, 0>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  return launch_tc<128, 0>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
 }
 
 int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N, const TcEpi& epi, int prof_cls) {
@@ -753,11 +827,42 @@ int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, in
   dim3 grid(sh.tiles_x * sh.tiles_y * B, cdiv(N, BN));
   const double flops = 2.0 * sh.M * N * K;
   prof_set_bytes(4.0 * ((double)sh.M * C + (double)Nrows * K * (Wt_lo != nullptr ? 2 : 1) + (double)sh.M * N));   // every input element once
-  if (BN == 32) return launch_tc<32, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
-  if (BN == 96) return launch_tc<96, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
-  return launch_tc<128, true>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 32) return launch_tc<32, 1>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 96) return launch_tc<96, 1>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  return launch_tc<128, 1>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
 }
 
+
+// 3x3 SAME conv of a [B,H,W,96] activation with 24 output channels as a "row tile" GEMM: K runs over the 3 vertical taps x 96
+// channels (9 k-blocks instead of 27), N = 3 horizontal taps x 24 channels (72, padded to 96 rows of Wt3[96][288]:
+// Wt3[24 j + co][96 dy + ci] = w[dy][j][ci][co]); the epilogue adds the three 24-column groups with a -1/0/+1 pixel shift.
+// One third of the MMAs, A-operand splits and L2->SM traffic of the 9-tap im2col form.  Requires W <= 128 (a tile row must
+// hold a whole image row) - the caller falls back to tc_conv3x3 otherwise.
+int tc_conv3x3_rowtile(cudaStream_t st, const float* x, int ldx, int B, int H, int W, const float* Wt3, const float* Wt3_lo, const TcEpi& epi, int prof_cls) {
+  constexpr int C = 96, N = 24;
+  WAP_REQUIRE(W <= kTcBM && (ldx & 3) == 0 && (epi.ld & 3) == 0, "tc_conv3x3_rowtile: W=%d must be <= %d", W, kTcBM);
+  int TW = 1; while (TW < W) TW <<= 1;
+  const int TH = kTcBM / TW;
+  CUtensorMap ta, tb, tbl;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldx * 4, (uint64_t)W * ldx * 4, (uint64_t)H * W * ldx * 4};
+    const uint32_t box[4] = {kTcBK, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&ta, x, 4, dims, str, box));
+  }
+  const int K = 3 * C;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, 96}; const uint64_t str[1] = {(uint64_t)K * 4}; const uint32_t box[2] = {kTcBK, 96};
+    WAP_TRY(make_map(&tb, Wt3, 2, dims, str, box));
+    if (Wt3_lo != nullptr) WAP_TRY(make_map(&tbl, Wt3_lo, 2, dims, str, box));
+  }
+  const CUtensorMap* pl = Wt3_lo != nullptr ? &tbl : nullptr;
+  TcShape sh{}; sh.M = B * H * W; sh.N = N; sh.K = K; sh.nkb = K / kTcBK;
+  sh.B = B; sh.H = H; sh.W = W; sh.kb_per_tap = C / kTcBK; sh.TW = TW; sh.TH = TH; sh.tiles_x = 1; sh.tiles_y = cdiv(H, TH);
+  dim3 grid(sh.tiles_y * B, 1);
+  prof_set_bytes(4.0 * ((double)sh.M * C + 96.0 * K * (Wt3_lo != nullptr ? 2 : 1) + (double)sh.M * N));
+  return launch_tc<96, 2>(st, ta, tb, pl, epi, sh, grid, prof_cls, 2.0 * sh.M * N * 9 * C);
+}
 
 extern float* g_wg_dbg; extern int g_wg_xor;
 template <int NBB, bool IM2COL>

@@ -40,6 +40,7 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
 // 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) * Wt[Nrows, 9*C]^T -> D[B*H*W, N]  (Nrows >= N rows allocated, extra rows zero)
 int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N, const TcEpi& epi, int prof_cls);
 // weight gradients (reduction over pixels, both operands MN-major): dW += X^T dY ; x3 selects 3xTF32 (both operands split on the fly)
+int tc_conv3x3_rowtile(cudaStream_t st, const float* x, int ldx, int B, int H, int W, const float* Wt3, const float* Wt3_lo, const TcEpi& epi, int prof_cls);
 int tc_wgrad_1x1(cudaStream_t st, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, bool x3, int prof_cls);
 int tc_wgrad_3x3(cudaStream_t st, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, bool x3,
                  int prof_cls);
