@@ -196,6 +196,8 @@ int wap_debug_tc_trace(long long* trace);
  * memory, later calls return them: out[1] = count, then notes of 8 ints from out[8]: {site + 100*k-block, blockIdx.x, blockIdx.y, warp,
  * parity, gridDim.x, gridDim.y, blockDim.x} */
 int wap_debug_trap_info(int* out256);
+/* ---- debug: 0 = the training scan launches the GRU gate kernels separately instead of evaluating them inside the skinny GEMMs */
+int wap_debug_set_fuse_gates(int on);
 /* ---- weight-gradient kernels on side streams (forked/joined with events inside one call; default on) */
 int wap_set_overlap(int on);
 int wap_get_overlap(void);

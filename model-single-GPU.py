@@ -9,7 +9,7 @@ test_caption.txt}), same outputs (<path>/log-bs-6.txt, <path>/result/valid_decod
 maxlen 100, patience 15, lr/10 twice, then early stop; S:609-734) — but every FLOP runs in
 libwap_b200.so on the B200.  Under torchrun (WORLD_SIZE > 1) it trains data-parallel with a NCCL
 gradient all-reduce (semantics of model-distributed.py:704-717); rank 0 validates.
-Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --save CKPT.npz (written by rank 0 whenever the
+Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --cuda_graphs, --save CKPT.npz (written by rank 0 whenever the
 validation WER improves - the reference's tf.train.Saver is constructed but never called), --resume CKPT.npz.
 """
 import argparse
@@ -41,6 +41,7 @@ def main(args):
     print('train lenght is ', len(train))
     eng = wap_b200.WAPEngine(seed=args.seed)
     eng.world_size = world
+    eng.use_graphs = bool(args.cuda_graphs); eng.max_graphs = 64
     if args.resume:
         eng.load(args.resume)
     dp.broadcast_params(eng.P.flat); dp.broadcast_params(eng.P.moving)
@@ -141,6 +142,7 @@ if __name__ == "__main__":
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--greedy_valid", action="store_true")
     parser.add_argument("--save", default="")
+    parser.add_argument("--cuda_graphs", action="store_true", help="capture forward+backward once per batch shape and replay it")
     parser.add_argument("--resume", default="")
     (args, unknown) = parser.parse_known_args()
     main(args)

@@ -14,6 +14,7 @@ static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
 int g_pdl = 1;
 extern long long* g_tc_trace;
+extern int g_fuse_gates;
 const int* trap_note_host();
 static int g_overlap = 1;
 SideStreams* side_streams() {
@@ -306,6 +307,7 @@ int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies
   return 0;
 }
 int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
+int wap_debug_set_fuse_gates(int on) { wap::g_fuse_gates = on ? 1 : 0; return 0; }
 int wap_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }
 int wap_get_overlap(void) { return g_overlap; }
 int wap_set_pdl(int on) { wap::g_pdl = on ? 1 : 0; return 0; }

@@ -20,6 +20,14 @@ struct SkinnyArgs {
   int Bn, K, nseg;
   SkinnySeg seg[4];
   int tile0[5];
+  // X generator (training scan): instead of reading X, every CTA evaluates the GRU gate that produces it for its own 16-wide K
+  // chunk (cheap, redundant across column tiles) and the CTAs of column tile 0 also store what the backward pass needs.  Removes
+  // the gate kernel from the dependent chain of the time step.
+  //   gen 1: X = pre_h  from (G1 raw [ld 3kN], UH, h_prev, mask)          stores r|z -> oRZ [ld 2kN], prop -> oProp, pre_h -> oX
+  //   gen 2: X = h_new  from (G2 raw [ld 2kN], PH2, CH, pre_h, mask)       stores r|z -> oRZ,        prop -> oProp, h    -> oX
+  int gen = 0;
+  const float *gG = nullptr, *gA = nullptr, *gB = nullptr, *gC = nullptr, *gmask = nullptr;
+  float *oRZ = nullptr, *oProp = nullptr, *oX = nullptr;
 };
 int skinny_gemm(cudaStream_t st, SkinnyArgs a);
 
@@ -58,10 +66,18 @@ struct StepCtx {
   int tc_mode; float* Ppat; const float* qfT_hi; const float* qfT_lo;
   // training scan: the bias rows of all T steps are filled by one launch before the loop
   int skip_fill = 0;
+  // training scan: GRU gates evaluated inside the consuming skinny GEMMs (see SkinnyArgs::gen); r|z go to RZ1/RZ2 (ld 2kN).
+  // prev_* describe step t-1 (whose GRU-2 gate produces this step's h_prev = c.h_prev, stored by the generator); null at t = 0.
+  int fuse_gates = 0;
+  float *RZ1 = nullptr, *RZ2 = nullptr;
+  const float *prev_G2 = nullptr, *prev_PH2 = nullptr, *prev_CH = nullptr, *prev_pre_h = nullptr, *prev_mask = nullptr;
+  float *prev_RZ2 = nullptr, *prev_prop2 = nullptr;
   // training scan: coverage chain (im2col + GEMM, depends only on ap_in) on a side stream, next to the GRU-1 half of the step
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 int decoder_step(cudaStream_t st, const StepCtx& c);
+int gru2_gate(cudaStream_t st, float* G2, const float* PH2, const float* CH, const float* pre_h, const float* y_mask, float* prop2, float* h_new,
+              int Bn, float* rz_out);
 int attention_tail(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* a_mask, int shared, int Bn, int L,
                    const float* SP, const float* ap_in, float* COV, float* TANH, float* E, float* alpha, float* ap_out, float* ctx);
 int attention_core(cudaStream_t st, const float* p, const float* ann, const float* watch, const float* qf, const float* a_mask, int shared,

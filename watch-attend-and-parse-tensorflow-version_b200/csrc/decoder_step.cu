@@ -7,6 +7,21 @@ namespace wap {
 // =====================================================================================
 // skinny GEMM
 // =====================================================================================
+// GRU-1 (S:273-289) / GRU-2 (S:292-306) gate of one element; shared by the gate kernels and the X generators
+__device__ __forceinline__ void gru1_eval(float gr, float gz, float eh, float uh, float h, float m, bool masked,
+                                          float& r, float& z, float& p, float& ph) {
+  r = sigmoidf_(gr); z = sigmoidf_(gz);
+  p = tanhf(fmaf(uh, r, eh));
+  ph = z * h + (1.f - z) * p;
+  if (masked) ph = m * ph + (1.f - m) * h;
+}
+__device__ __forceinline__ void gru2_eval(float gr, float gz, float ph2, float ch, float preh, float m, bool masked,
+                                          float& r, float& z, float& p, float& h) {
+  r = sigmoidf_(gr); z = sigmoidf_(gz);
+  p = tanhf(fmaf(ph2, r, ch));
+  h = z * preh + (1.f - z) * p;
+  if (masked) h = m * h + (1.f - m) * preh;
+}
 __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
   pdl_sync();
   __shared__ float xs[kSkRows][kSkKC];
@@ -40,7 +55,23 @@ __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
       const int b = b0 + bb, k = k0 + kk;
       float v = 0.f;
       if (b < a.Bn && k < a.K) {
-        if (a.ids != nullptr) { const int id = a.ids[b]; if (id >= 0) v = __ldg(a.X + (size_t)id * a.ldx + k); }
+        if (a.gen != 0) {
+          const bool masked = a.gmask != nullptr;
+          const float m = masked ? a.gmask[b] : 1.f;
+          const size_t e = (size_t)b * kN + k;
+          float r, z, p;
+          if (a.gen == 1) {
+            const float* g = a.gG + (size_t)b * 3 * kN;
+            gru1_eval(g[k], g[kN + k], g[2 * kN + k], a.gA[e], a.gB[e], m, masked, r, z, p, v);
+          } else {
+            const float* g = a.gG + (size_t)b * 2 * kN;
+            gru2_eval(g[k], g[kN + k], a.gA[e], a.gB[e], a.gC[e], m, masked, r, z, p, v);
+          }
+          if (blockIdx.x == 0) {
+            a.oRZ[(size_t)b * 2 * kN + k] = r; a.oRZ[(size_t)b * 2 * kN + kN + k] = z;
+            a.oProp[e] = p; a.oX[e] = v;
+          }
+        } else if (a.ids != nullptr) { const int id = a.ids[b]; if (id >= 0) v = __ldg(a.X + (size_t)id * a.ldx + k); }
         else v = __ldg(a.X + (size_t)b * a.ldx + k);
       }
       xs[bb][kk] = v;
@@ -104,18 +135,16 @@ int fill_rows(cudaStream_t st, const FillArgs& a) {
 // =====================================================================================
 __global__ void __launch_bounds__(256)
 gru1_gate_kernel(float* __restrict__ G1, const float* __restrict__ UH, const float* __restrict__ h_prev,
-                 const float* __restrict__ y_mask, float* __restrict__ prop1, float* __restrict__ pre_h, int Bn) {
+                 const float* __restrict__ y_mask, float* __restrict__ prop1, float* __restrict__ pre_h, int Bn, float* __restrict__ rz_out) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * kN) return;
   const int b = i / kN, j = i - b * kN;
   float* g = G1 + (size_t)b * 3 * kN;
-  const float r = sigmoidf_(g[j]), z = sigmoidf_(g[kN + j]);
-  g[j] = r; g[kN + j] = z;
-  const float p = tanhf(fmaf(UH[i], r, g[2 * kN + j]));
-  const float h = h_prev[i];
-  float ph = z * h + (1.f - z) * p;
-  if (y_mask != nullptr) { const float m = y_mask[b]; ph = m * ph + (1.f - m) * h; }
+  float r, z, p, ph;
+  gru1_eval(g[j], g[kN + j], g[2 * kN + j], UH[i], h_prev[i], y_mask != nullptr ? y_mask[b] : 1.f, y_mask != nullptr, r, z, p, ph);
+  if (rz_out != nullptr) { rz_out[(size_t)b * 2 * kN + j] = r; rz_out[(size_t)b * 2 * kN + kN + j] = z; }
+  else { g[j] = r; g[kN + j] = z; }
   prop1[i] = p; pre_h[i] = ph;
 }
 
@@ -123,19 +152,23 @@ gru1_gate_kernel(float* __restrict__ G1, const float* __restrict__ UH, const flo
 __global__ void __launch_bounds__(256)
 gru2_gate_kernel(float* __restrict__ G2, const float* __restrict__ PH2, const float* __restrict__ CH,
                  const float* __restrict__ pre_h, const float* __restrict__ y_mask,
-                 float* __restrict__ prop2, float* __restrict__ h_new, int Bn) {
+                 float* __restrict__ prop2, float* __restrict__ h_new, int Bn, float* __restrict__ rz_out) {
   pdl_sync();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= Bn * kN) return;
   const int b = i / kN, j = i - b * kN;
   float* g = G2 + (size_t)b * 2 * kN;
-  const float r = sigmoidf_(g[j]), z = sigmoidf_(g[kN + j]);
-  g[j] = r; g[kN + j] = z;
-  const float p = tanhf(fmaf(PH2[i], r, CH[i]));
-  const float ph = pre_h[i];
-  float h = z * ph + (1.f - z) * p;
-  if (y_mask != nullptr) { const float m = y_mask[b]; h = m * h + (1.f - m) * ph; }
+  float r, z, p, h;
+  gru2_eval(g[j], g[kN + j], PH2[i], CH[i], pre_h[i], y_mask != nullptr ? y_mask[b] : 1.f, y_mask != nullptr, r, z, p, h);
+  if (rz_out != nullptr) { rz_out[(size_t)b * 2 * kN + j] = r; rz_out[(size_t)b * 2 * kN + kN + j] = z; }
+  else { g[j] = r; g[kN + j] = z; }
   prop2[i] = p; h_new[i] = h;
+}
+int gru2_gate(cudaStream_t st, float* G2, const float* PH2, const float* CH, const float* pre_h, const float* y_mask, float* prop2, float* h_new,
+              int Bn, float* rz_out) {
+  WAP_CHECK(launch_pdl(gru2_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, G2, PH2, CH, pre_h, y_mask, prop2, h_new, Bn, rz_out));
+  WAP_LAUNCH_CHECK();
+  return 0;
 }
 
 // =====================================================================================
@@ -312,16 +345,26 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
                     TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
     WAP_CHECK(cudaEventRecord(c.ev_join, c.side));
   }
-  {   // h_prev * [U_hz_hr | U_rh]
+  {   // h_prev * [U_hz_hr | U_rh]     (fused scan: h_prev itself is the GRU-2 gate of the previous step, evaluated here)
     SkinnyArgs a; a.X = c.h_prev; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 2;
     a.seg[0] = {p + P.U_hz_hr, 2 * kN, 2 * kN, c.G1, 3 * kN};
     a.seg[1] = {p + P.U_rh, kN, kN, c.UH, kN};
+    if (c.fuse_gates && c.prev_G2 != nullptr) {
+      a.gen = 2; a.gG = c.prev_G2; a.gA = c.prev_PH2; a.gB = c.prev_CH; a.gC = c.prev_pre_h; a.gmask = c.prev_mask;
+      a.oRZ = c.prev_RZ2; a.oProp = c.prev_prop2; a.oX = const_cast<float*>(c.h_prev);
+    }
     WAP_TRY(skinny_gemm(st, a));
   }
-  WAP_CHECK(launch_pdl(gru1_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, c.G1, c.UH, c.h_prev, c.y_mask, c.prop1, c.pre_h, Bn));
-  WAP_LAUNCH_CHECK();
+  if (!c.fuse_gates) {
+    WAP_CHECK(launch_pdl(gru1_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, c.G1, c.UH, c.h_prev, c.y_mask, c.prop1, c.pre_h, Bn, c.RZ1));
+    WAP_LAUNCH_CHECK();
+  }
   {   // pre_h * [W_a | U_hz_hr_nl | U_rh_nl]
     SkinnyArgs a; a.X = c.pre_h; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 3;
+    if (c.fuse_gates) {
+      a.gen = 1; a.gG = c.G1; a.gA = c.UH; a.gB = c.h_prev; a.gmask = c.y_mask;
+      a.oRZ = c.RZ1; a.oProp = c.prop1; a.oX = c.pre_h;
+    }
     a.seg[0] = {p + P.W_a, kNA, kNA, c.SP, kNA};
     a.seg[1] = {p + P.U_hz_hr_nl, 2 * kN, 2 * kN, c.G2, 2 * kN};
     a.seg[2] = {p + P.U_rh_nl, kN, kN, c.PH2, kN};
@@ -346,8 +389,10 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     if (c.has_extra_ctx) { a.seg[2] = c.extra_ctx; a.nseg = 3; }
     WAP_TRY(skinny_gemm(st, a));
   }
-  WAP_CHECK(launch_pdl(gru2_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, c.G2, c.PH2, c.CH, c.pre_h, c.y_mask, c.prop2, c.h_new, Bn));
-  WAP_LAUNCH_CHECK();
+  if (!c.fuse_gates) {      // fused scan: the next step's first GEMM (or the caller after the last step) evaluates this gate
+    WAP_CHECK(launch_pdl(gru2_gate_kernel, cdiv(Bn * kN, 256), 256, 0, st, c.G2, c.PH2, c.CH, c.pre_h, c.y_mask, c.prop2, c.h_new, Bn, c.RZ2));
+    WAP_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -24,9 +24,11 @@ int attn_precompute(cudaStream_t st, const float* params, const float* ann, cons
 
 // ------------------------------------------------------------------------------------ workspace
 constexpr int kLdA = 4 * kN, kLdB = 3 * kN;
+int g_fuse_gates = 1;       // wap_debug_set_fuse_gates()
 struct DecTrainWs {
   // forward (saved)
   float *EMB, *G1, *H, *UH, *PROP1, *PREH, *SP, *G2, *PH2, *CH, *PROP2, *TANH, *ALPHA, *AP, *CTX;
+  float *RZ1, *RZ2;          // sigmoid gates r|z of GRU-1 / GRU-2 per step [TB, 512] (G1 / G2 keep the raw pre-activations)
   float *watch, *qf, *mean, *COV, *E, *LG, *MO, *LO;
   double* cost;
   // backward
@@ -44,6 +46,7 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.EMB = take(TB * kMw); w.G1 = take(TB * 3 * kN); w.H = take((TB + B) * kN); w.UH = take(TB * kN);
   w.PROP1 = take(TB * kN); w.PREH = take(TB * kN); w.SP = take(TB * kNA); w.G2 = take(TB * 2 * kN);
   w.PH2 = take(TB * kN); w.CH = take(TB * kN); w.PROP2 = take(TB * kN); w.TANH = take(TB * L * kNA);
+  w.RZ1 = take(TB * 2 * kN); w.RZ2 = take(TB * 2 * kN);
   w.ALPHA = take(TB * L); w.AP = take((TB + B) * L); w.CTX = take(TB * kD);
   w.watch = take(BL * kNA); w.qf = take((size_t)kCovTaps * kNA); w.mean = take((size_t)B * kD);
   w.COV = take(BL * kNA); w.E = take(BL); w.LG = take(TB * kMw); w.MO = take(TB * kMw / 2); w.LO = take(TB * kVocab);
@@ -246,6 +249,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
     WAP_TRY(fill_rows(st, f));
   }
   SideStreams* sl = (tc && overlap_enabled()) ? side_streams() : nullptr;
+  const bool fuse = g_fuse_gates != 0;     // GRU gates evaluated inside the consuming skinny GEMMs (2 kernels less per time step)
   for (int t = 0; t < T; ++t) {
     const size_t r = (size_t)t * B;
     StepCtx c;
@@ -257,8 +261,19 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
     c.ctx = W.CTX + r * kD; c.h_new = W.H + (r + B) * kN; c.has_extra_ctx = 0;
     c.tc_mode = tc ? prec : 0; c.Ppat = W.Ppat; c.qfT_hi = W.qfT_hi; c.qfT_lo = W.qfT_lo;
     c.skip_fill = 1;
+    c.fuse_gates = fuse ? 1 : 0; c.RZ1 = W.RZ1 + r * 2 * kN; c.RZ2 = W.RZ2 + r * 2 * kN;
+    if (fuse && t > 0) {
+      const size_t q = r - B;
+      c.prev_G2 = W.G2 + q * 2 * kN; c.prev_PH2 = W.PH2 + q * kN; c.prev_CH = W.CH + q * kN; c.prev_pre_h = W.PREH + q * kN; c.prev_mask = y_mask + q;
+      c.prev_RZ2 = W.RZ2 + q * 2 * kN; c.prev_prop2 = W.PROP2 + q * kN;
+    }
     if (sl != nullptr) { c.side = sl->s[2]; c.ev_fork = sl->fork[2]; c.ev_join = sl->done[6]; }
     WAP_TRY(decoder_step(st, c));
+  }
+  if (fuse) {   // the GRU-2 gate of the last step has no following step to evaluate it
+    const size_t q = (size_t)(T - 1) * B;
+    WAP_TRY(gru2_gate(st, W.G2 + q * 2 * kN, W.PH2 + q * kN, W.CH + q * kN, W.PREH + q * kN, y_mask + q, W.PROP2 + q * kN, W.H + (q + B) * kN, B,
+                      W.RZ2 + q * 2 * kN));
   }
   // logits for all steps (S:354-364)
   WAP_CHECK(launch_pdl(bias3_rows_kernel, cdiv(TB * kMw, 256), 256, 0, st, W.LG, TB, params + P.by, params + P.bc, params + P.bh));
@@ -290,7 +305,7 @@ gru2_bwd_kernel(const float* __restrict__ dh_in, const float* __restrict__ dHlog
   const int b = i / kN, j = i - b * kN;
   const float m = y_mask != nullptr ? y_mask[b] : 1.f;
   const float dh = dh_in[i] + dHlog[i];
-  const float r = G2[(size_t)b * 2 * kN + j], z = G2[(size_t)b * 2 * kN + kN + j];
+  const float r = G2[(size_t)b * 2 * kN + j], z = G2[(size_t)b * 2 * kN + kN + j];       // G2 = the saved gates RZ2
   const float p = prop2[i], ph = pre_h[i];
   const float dhn = m * dh;
   const float dz = dhn * (ph - p), dp = dhn * (1.f - z);
@@ -313,7 +328,7 @@ gru1_bwd_kernel(const float* __restrict__ dpre_h, const float* __restrict__ G1, 
   const int b = i / kN, j = i - b * kN;
   const float m = y_mask != nullptr ? y_mask[b] : 1.f;
   const float d = dpre_h[i];
-  const float r = G1[(size_t)b * 3 * kN + j], z = G1[(size_t)b * 3 * kN + kN + j];
+  const float r = G1[(size_t)b * 2 * kN + j], z = G1[(size_t)b * 2 * kN + kN + j];       // G1 = the saved gates RZ1 (ld 2kN)
   const float p = prop1[i], h = h_prev[i];
   const float dp_ = m * d;
   const float dz = dp_ * (h - p), dprop = dp_ * (1.f - z);
@@ -558,7 +573,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     const size_t r = (size_t)t * B;
     const float* ym = y_mask + r;
     float* dctx = W.dCTX + r * kD;                 // holds the logit-path part already
-    WAP_CHECK(launch_pdl(gru2_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, dh_in, W.dHlog + r * kN, W.G2 + r * 2 * kN, W.PROP2 + r * kN, W.PH2 + r * kN,
+    WAP_CHECK(launch_pdl(gru2_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, dh_in, W.dHlog + r * kN, W.RZ2 + r * 2 * kN, W.PROP2 + r * kN, W.PH2 + r * kN,
                          W.PREH + r * kN, ym, W.dG2 + r * kLdA, W.dCH + r * kLdA, W.dPH2 + r * kLdA, W.dpre_h, B));
     WAP_LAUNCH_CHECK();
     WAP_TRY(fork2(2));
@@ -595,7 +610,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       WAP_TRY(skinny_gemm(st, a));
     }
     if (sl != nullptr) WAP_CHECK(cudaStreamWaitEvent(st, sl->done[6], 0));
-    WAP_CHECK(launch_pdl(gru1_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, W.dpre_h, W.G1 + r * 3 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
+    WAP_CHECK(launch_pdl(gru1_bwd_kernel, cdiv(B * kN, 256), 256, 0, st, W.dpre_h, W.RZ1 + r * 2 * kN, W.PROP1 + r * kN, W.UH + r * kN, W.H + r * kN, ym,
                          W.dG1 + r * kLdB, W.dEh + r * kN, W.dUH + r * kLdB, dh_out, B));
     WAP_LAUNCH_CHECK();
     {   // dh_prev += [dG1|dUH] * [U_hz_hr^T; U_rh^T]
