@@ -207,13 +207,14 @@ energy_kernel(const float* COV, const float* __restrict__ watch, const float* __
 // masked softmax over the L positions of one image + alpha_past update + context (S:190-203)
 // grid = (ceil(684/64), Bn); every CTA recomputes the (cheap) softmax and owns 64 context channels.
 // =====================================================================================
-constexpr int kCtxChunk = 64;
+constexpr int kCtxChunk = 32;          // context channels per CTA: 22 x Bn CTAs (176 at B = 8) instead of 88
+constexpr int kCtxLanes = kCtxChunk / 4, kCtxGroups = 256 / kCtxLanes;
 __global__ void __launch_bounds__(256)
 softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask, const float* __restrict__ ap_in,
                    const float* __restrict__ ann, float* __restrict__ alpha, float* __restrict__ ap_out,
                    float* __restrict__ ctx, int L, int shared) {
   pdl_sync();
-  extern __shared__ float sm[];          // alpha[L] | red[64] | part[16][64]
+  extern __shared__ float sm[];          // alpha[L] | red[64] | part[kCtxGroups][kCtxChunk]
   float* s_alpha = sm;
   float* red = sm + ((L + 3) & ~3);      // keep `part` 16-byte aligned for the float4 stores
   float* part = red + 64;
@@ -239,23 +240,24 @@ softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask
   }
   __syncthreads();
   const int c0 = blockIdx.x * kCtxChunk;
-  const int cq = tid & 15, lg = tid >> 4;            // 16 float4 lanes x 16 position groups
+  const int cq = tid % kCtxLanes, lg = tid / kCtxLanes;     // float4 lanes x position groups
   const int c = c0 + cq * 4;
   float4 acc = make4(0.f);
   if (c < kD) {
     const float* base = ann + (size_t)(shared ? 0 : b) * L * kD + c;
-    for (int l = lg; l < L; l += 16) {
+#pragma unroll 8
+    for (int l = lg; l < L; l += kCtxGroups) {
       const float4 v = ldg4(base + (size_t)l * kD);
       const float al = s_alpha[l];
       acc.x = fmaf(al, v.x, acc.x); acc.y = fmaf(al, v.y, acc.y); acc.z = fmaf(al, v.z, acc.z); acc.w = fmaf(al, v.w, acc.w);
     }
   }
-  *reinterpret_cast<float4*>(&part[lg * 64 + cq * 4]) = acc;
+  *reinterpret_cast<float4*>(&part[lg * kCtxChunk + cq * 4]) = acc;
   __syncthreads();
   if (tid < kCtxChunk && c0 + tid < kD) {
     float s = 0.f;
 #pragma unroll
-    for (int g = 0; g < 16; ++g) s += part[g * 64 + tid];
+    for (int g = 0; g < kCtxGroups; ++g) s += part[g * kCtxChunk + tid];
     ctx[(size_t)b * kD + c0 + tid] = s;
   }
 }
@@ -301,7 +303,7 @@ int attention_tail(cudaStream_t st, const float* p, const float* ann, const floa
   const ParamLayout& P = layout();
   WAP_CHECK(launch_pdl(energy_kernel, cdiv(Bn * L * 32, 256), 256, 0, st, COV, watch, SP, p + P.V_a, p + P.V_a_b, TANH, E, Bn, L, shared));
   WAP_LAUNCH_CHECK();
-  const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + 16 * 64);
+  const size_t smem = sizeof(float) * (((L + 3) & ~3) + 64 + kCtxGroups * kCtxChunk);
   WAP_REQUIRE(smem <= 48 * 1024, "annotation grid too large for softmax_ctx_kernel: L=%d", L);
   dim3 grid(cdiv(kD, kCtxChunk), Bn);
   WAP_CHECK(launch_pdl(softmax_ctx_kernel, grid, 256, smem, st, E, a_mask, ap_in, ann, alpha, ap_out, ctx, L, shared));
