@@ -405,7 +405,7 @@ def test_checkpoint_roundtrip(tmp_path):
     eng2.load(path)
     assert eng2.step_count == 1
     c2 = float(eng2.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=4))
-    assert abs(c1 - c2) <= 1e-6 * abs(c1), (c1, c2)
+    assert abs(c1 - c2) <= 2e-5 * abs(c1), (c1, c2)      # two fp32 runs: atomic-order noise only
     z = np.load(path)
     assert "conv2d_98/kernel" in z.files and "batch_normalization_50/moving_variance" in z.files and "__opt__/accum/embed" in z.files
 
@@ -424,9 +424,10 @@ def test_cuda_graph_replay_matches_stream_launches():
         cg = float(eng.forward_backward(x, y, xm, ym, True, seed)); gg = eng.grads.clone()
         eng.use_graphs = False
         ce = float(eng.forward_backward(x, y, xm, ym, True, seed)); ge = eng.grads.clone()
-        assert abs(cg - ce) <= 1e-6 * abs(ce), (seed, cg, ce)
+        # two fp32 runs differ by the order of their atomic adds (~1e-6); a wrong seed or mask would differ by O(1)
+        assert abs(cg - ce) <= 2e-5 * abs(ce), (seed, cg, ce)
         if seed == 5:                         # the other seeds are not kink-checked: compare the cost only
-            assert rel_l2(gg.cpu().numpy(), ge.cpu().numpy()) < 1e-4, seed
+            assert rel_l2(gg.cpu().numpy(), ge.cpu().numpy()) < 1e-3, seed
         got[seed] = cg
     assert eng.replayed_launches > 0 and len(eng._graphs) == 1
     assert abs(got[5] - got[6]) > 1e-4 * abs(got[5]) and abs(got[6] - got[7]) > 1e-4 * abs(got[6])   # the seed really changed
@@ -434,6 +435,6 @@ def test_cuda_graph_replay_matches_stream_launches():
     x2, xm2, y2, ym2 = make_batch(12, 2, 32, 48, 3, True)
     eng.use_graphs = True
     c1 = float(eng.forward_backward(x2, y2, xm2, ym2, True, 9)); c2 = float(eng.forward_backward(x2, y2, xm2, ym2, True, 9))
-    assert abs(c1 - c2) <= 1e-6 * abs(c1) and len(eng._graphs) == 2
+    assert abs(c1 - c2) <= 2e-5 * abs(c1) and len(eng._graphs) == 2
     p0 = eng.P.flat.clone(); eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=5)
     assert float((eng.P.flat - p0).abs().max()) > 0
