@@ -222,3 +222,46 @@ def test_scorer_matches_reference_definition(tmp_path):
     wer, sacc = scorer.process(str(tmp_path / "r.txt"), str(tmp_path / "l.txt"), str(tmp_path / "o.wer"))
     lines = (tmp_path / "o.wer").read_text().splitlines()
     assert lines[0] == f"WER {wer}" and lines[1] == f"ExpRate {sacc}"     # format parsed at model-single-GPU.py:702-705
+
+
+def test_reference_initialisers():
+    """ParamStore.init_reference reproduces the reference's initialiser families (model-single-GPU.py:25-42, 67-70, 81):
+    Glorot-uniform limits, orthogonal GRU recurrences, gamma ~ U(+-1/sqrt(C)), zero biases / beta, unit moving variance.
+    (ParamStore only needs the library's parameter table, so this runs without a GPU.)"""
+    import math
+    import torch
+    import wap_b200
+    from wap_b200.engine import ParamStore
+    ps = ParamStore(torch.device("cpu"))
+    ps.init_reference(seed=3)
+    sd = ps.state_dict()
+    # Glorot limits: dense matrix [in, out], conv kernels with k^2 fans
+    for name, fin, fout in (("W_a", 256, 512), ("U_a", 684, 512), ("Wc", 684, 256), ("embed", 111, 256)):
+        lim = math.sqrt(6.0 / (fin + fout))
+        w = sd[name]
+        assert w.shape == (fin, fout) and np.abs(w).max() <= lim * (1 + 1e-6) and np.abs(w).max() > 0.97 * lim, name
+        assert abs(w.std() - lim / math.sqrt(3.0)) < 0.03 * lim, name                  # uniform: std = lim / sqrt(3)
+    k3 = sd["conv2d_2/kernel"]                                                        # 3x3, 96 -> 24
+    assert k3.shape == (3, 3, 96, 24) and np.abs(k3).max() <= math.sqrt(6.0 / (9 * 96 + 9 * 24)) * (1 + 1e-6)
+    k0 = sd["conv2d/kernel"] if "conv2d/kernel" in sd else sd["conv2d_0/kernel"]
+    assert k0.shape == (7, 7, 1, 48)
+    # orthogonal recurrences (ortho_weight): U U^T = I, and the 512-wide ones are two orthogonal blocks side by side
+    for name in ("U_rh", "U_rh_nl"):
+        u = sd[name].astype(np.float64)
+        assert np.abs(u @ u.T - np.eye(256)).max() < 1e-5, name
+    for name in ("U_hz_hr", "U_hz_hr_nl"):
+        u = sd[name].astype(np.float64)
+        for half in (u[:, :256], u[:, 256:]):
+            assert np.abs(half @ half.T - np.eye(256)).max() < 1e-5, name
+    # batch norm and biases
+    g = sd["batch_normalization_50/gamma"]
+    assert np.abs(g).max() <= 1.0 / math.sqrt(g.shape[0]) + 1e-7
+    assert not sd["batch_normalization_50/beta"].any() and not sd["batch_normalization_50/moving_mean"].any()
+    assert (sd["batch_normalization_50/moving_variance"] == 1.0).all()
+    for name in ("U_f_b", "W_a_b", "b_yz_yr", "bo", "ba2h"):
+        assert not sd[name].any(), name
+    # a different seed gives different weights, the same seed the same
+    ps2 = ParamStore(torch.device("cpu")); ps2.init_reference(seed=3)
+    assert np.array_equal(ps2.state_dict()["W_a"], sd["W_a"])
+    ps2.init_reference(seed=4)
+    assert not np.array_equal(ps2.state_dict()["W_a"], sd["W_a"])
