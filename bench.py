@@ -134,7 +134,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Bs = 2   # bounded sample per step: 2 of the 8 images of the config (same H x W, same caption length)
+    Bs = B_PER_GPU   # the full per-GPU batch of the config (a smaller sample would understate the CPU: ~1.7 s per step on 16 cores);
+                     # the run is bounded by wall-clock instead: it stops after 240 s with at least one timed step
     v, cores, sps, nrun = cpu_oracle_images_per_s(Bs, args.steps, args.warmup, budget_s=240.0)
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
