@@ -9,7 +9,7 @@ P = O.lively_params(8)
 def run(mode, mask):
     eng = engine_with(P); eng.set_conv_precision(mode); eng.L.wap_debug_set_tc_mask(mask)
     eng.forward_backward(x, y, xm, ym, dropout=True, seed=777)
-    g = eng.P.unpack(eng.grads); eng.L.wap_debug_set_tc_mask(0xFF); return g
+    g = eng.P.unpack(eng.grads); eng.L.wap_debug_set_tc_mask(0x1FF); return g
 ref = run("fp32", 0xFF)
 for mask in (0, 1, 2, 4):
     g = run("tf32x3", mask | 0x38)

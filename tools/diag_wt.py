@@ -25,7 +25,8 @@ def check(tag):
                 exp[:, tap, :co] = wf[8 - tap]
             exp = exp.reshape(ci, 288)
         hi = rna(exp); lo = rna(exp - hi)
-        got = ws[offb: offb + exp.numel()].view_as(exp); gotl = ws[offbl: offbl + exp.numel()].view_as(exp)
+        ld = 192 if (kh == 1 and co == 96) else exp.shape[1]      # dense-level 1x1 layers live in a [Cin][192] pair buffer (odd level | even level)
+        got = torch.as_strided(ws, exp.shape, (ld, 1), offb); gotl = torch.as_strided(ws, exp.shape, (ld, 1), offbl)
         e = (got - hi).abs().max().item(); el = (gotl - lo).abs().max().item()
         if e > 0 or el > 0: bad.append((k, e, el))
     print(tag, "bad bwd weight copies:", bad[:10], len(bad))
