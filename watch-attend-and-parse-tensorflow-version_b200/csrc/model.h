@@ -66,7 +66,7 @@ struct EncWorkspace {
   // backward scratch
   size_t gbuf[kBlocks - 1];              // d block buffer 0,1
   size_t dy1, da1, dy2, dytr, gstem, dy1b, dy2b;   // dy1b/dy2b: ping-pong partners (weight gradients run on a side stream)
-  //     // largest-block sized scratch (dy2 has row stride kDy2Ld = 32)
+  //   largest-block sized scratch: dy1 is [M,192] (odd level | even level), dy2 has row stride kDy2Ld = 32
   size_t wt_fwd[kNumConv], wt_bwd[kNumConv];   // TF32-rounded K-major weight copies for the tcgen05 path (hi parts)
   size_t wt_fwd_lo[kNumConv], wt_bwd_lo[kNumConv];   // residuals rna(w - hi) for the 3xTF32 mode
   int wt_bwd_ld[kNumConv];               // row stride of the dgrad copy: 1x1 layers of a level pair (2j+1, 2j) share one [Cin][192] buffer

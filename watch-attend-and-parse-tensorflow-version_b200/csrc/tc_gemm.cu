@@ -336,7 +336,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 127) == 64) sh.trace[kb * 4 + 2] = clock64();
       }
     }
-    if (warp >= 6) goto tail;                // second splitter group: no epilogue role
+    if (warp >= 6) goto tail;                // (no such warps with 192 threads; kept for experiments with extra splitter warps)
     {
     const int q = warp & 3;                  // TMEM lane quadrant this warp may access
     const int r = q * 32 + lane;             // output row within the tile

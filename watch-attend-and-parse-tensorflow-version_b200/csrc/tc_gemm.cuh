@@ -15,7 +15,13 @@
 // MMA issuer (one elected lane), warps 2..5 = epilogue (tcgen05.ld 32x32b, one TMEM lane = one
 // output row per thread): store / accumulate, and optional per-column sum and sum of squares
 // (batch-norm statistics) via a 31-shuffle transposing reduction per 32 columns.
-// Two CTAs are resident per SM so one tile's epilogue overlaps the other's main loop.
+// Single-pass TF32: two CTAs are resident per SM so one tile's epilogue overlaps the other's main loop.
+// 3xTF32 (X3, the parity mode): the epilogue warps double as operand splitters in the main loop - they read the raw fp32 A
+// tile from shared memory, write a_hi / a_lo into a ring in TENSOR MEMORY (tcgen05.st) and the MMAs take A from there
+// (TS form), B hi/lo tiles come pre-split from global memory; a_hi*b_hi accumulates in one TMEM accumulator, the two
+// correction products in a second one; one CTA per SM (TMEM: 2 accumulators + 4 x 64 ring columns = 512).
+// IM2COL == 2 is the "row tile" 3x3 conv: vertical taps in K, horizontal taps as 3 x 24 accumulator columns summed with a
+// pixel shift in the epilogue (tc_conv3x3_rowtile).
 #pragma once
 #include <cuda.h>
 
