@@ -265,3 +265,47 @@ def test_reference_initialisers():
     assert np.array_equal(ps2.state_dict()["W_a"], sd["W_a"])
     ps2.init_reference(seed=4)
     assert not np.array_equal(ps2.state_dict()["W_a"], sd["W_a"])
+
+
+def test_param_store_roundtrip_and_checkpoint_names():
+    """ParamStore.load / state_dict / pack_into / unpack are exact inverses, keyed by the TF variable names (the checkpoint
+    format of WAPEngine.save is state_dict + '__opt__/accum/<name>' + '__opt__/accum_update/<name>')."""
+    import torch
+    from helpers import O
+    from wap_b200.engine import ParamStore
+    P = O.lively_params(4)
+    ps = ParamStore(torch.device("cpu"))
+    ps.load(P)
+    sd = ps.state_dict()
+    assert set(sd) == set(P)
+    for n in P:
+        assert np.array_equal(sd[n], np.asarray(P[n], np.float32)), n
+    flat = torch.zeros_like(ps.flat)
+    tr = {n: np.asarray(P[n], np.float32) * 2 for n in ps.names(trainable_only=True)}
+    ps.pack_into(flat, tr)
+    back = ps.unpack(flat)
+    assert set(back) == set(tr) and all(np.array_equal(back[n], tr[n]) for n in tr)
+    # L2-decayed tensors come first: everything before n_decay is a non-batch-norm variable
+    for name, off, shape, flags in ps.table:
+        if not flags & 2:
+            assert (off < ps.n_decay) == (not name.startswith("batch_normalization")), name
+
+
+def test_well_posed_cache_entries_are_valid():
+    """The cached batch indices of tests/golden/well_posed_cache.json (used by the GPU gradient tests) satisfy the kink margin:
+    a stale cache would silently cost ~300 oracle forwards on the GPU box."""
+    import json
+    from helpers import O, make_batch, _WP_CACHE
+    cache = json.load(open(_WP_CACHE))
+    assert len(cache) >= 12
+    checked = 0
+    for key, idx in cache.items():
+        crc, seed, B, H, W, cap, ragged, drop_seed, margin = key.split("_")
+        if crc != "8c69829b" or checked >= 4:        # lively_params(8): the parameter set of test_full_gradients
+            continue
+        P = O.lively_params(8)
+        x, xm, y, ym = make_batch(int(seed) + 1000 * idx, int(B), int(H), int(W), int(cap), bool(int(ragged)))
+        drop = O.hash_drop_fn(int(drop_seed)) if drop_seed != "None" else None
+        assert O.relu_kink_margin(P, x, xm, drop) > float(margin), key
+        checked += 1
+    assert checked >= 3
