@@ -285,7 +285,7 @@ def run_ours(args):
     roof = {"bound": "hbm", "kernel": f"{kname} [{top}]", "achieved": prof[top]["gbs"], "peak": pk["hbm_gbs"],
             "unit": "GB/s", "frac": prof[top]["gbs"] / pk["hbm_gbs"], "traffic": traffic, "traffic_instance": traffic_note,
             "peak_source": pk["src"],
-            "tensor_tflops": prof[top]["tflops"], "tensor_peak_tflops": pk["tf"],
+            "tensor_tflops": prof[top]["tflops"], "tensor_peak_tflops": pk["tf"], "tensor_frac": prof[top]["tflops"] / pk["tf"],
             "share_of_step": prof[top]["ms_per_step"] / (ms / args.steps),
             "all_gemm_share_of_step": gemm_ms / (ms / args.steps), "classes": prof,
             "note": "algorithmic bytes (every operand element read once, result written - or read+written when accumulated - once, fp32) "
