@@ -9,7 +9,7 @@ test_caption.txt}), same outputs (<path>/log-bs-6.txt, <path>/result/valid_decod
 maxlen 100, patience 15, lr/10 twice, then early stop; S:609-734) — but every FLOP runs in
 libwap_b200.so on the B200.  Under torchrun (WORLD_SIZE > 1) it trains data-parallel with a NCCL
 gradient all-reduce (semantics of model-distributed.py:704-717); rank 0 validates.
-Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --cuda_graphs, --save CKPT.npz (written by rank 0 whenever the
+Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --cuda_graphs, --prefetch N, --save CKPT.npz (written by rank 0 whenever the
 validation WER improves - the reference's tf.train.Saver is constructed but never called), --resume CKPT.npz.
 """
 import argparse
@@ -61,10 +61,11 @@ def main(args):
 
     for epoch in range(args.max_epoch):
         rng.shuffle(train)                                   # same permutation on every rank; shards are disjoint
-        for batch_x, batch_y in dp.shard_batches(train, rank, world):
-            if not batch_x:
-                continue
-            x, x_m, y, y_m = wap_b200.prepare_data(batch_x, batch_y, pinned=True)
+        shard = dp.shard_batches(train, rank, world)
+        # --prefetch N: padding / masks / pinned staging of the next N batches on a background thread (off by default)
+        prepared = wap_b200.Prefetcher(shard, pinned=True, depth=args.prefetch) if args.prefetch > 0 else \
+            (wap_b200.prepare_data(bx, by, pinned=True) for bx, by in shard if bx)
+        for x, x_m, y, y_m in prepared:
             uidx += 1
             cost_i = float(eng.train_step(x, y, x_m, y_m, lr=lrate))
             cost_s += cost_i
@@ -142,6 +143,7 @@ if __name__ == "__main__":
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--greedy_valid", action="store_true")
     parser.add_argument("--save", default="")
+    parser.add_argument("--prefetch", type=int, default=0, help="prepare this many batches ahead on a background thread")
     parser.add_argument("--cuda_graphs", action="store_true", help="capture forward+backward once per batch shape and replay it")
     parser.add_argument("--resume", default="")
     (args, unknown) = parser.parse_known_args()

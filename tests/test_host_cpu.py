@@ -309,3 +309,38 @@ def test_well_posed_cache_entries_are_valid():
         assert O.relu_kink_margin(P, x, xm, drop) > float(margin), key
         checked += 1
     assert checked >= 3
+
+
+def test_prefetcher_order_errors_and_early_close():
+    """data.Prefetcher: same batches, same order and same arrays as calling prepare_data inline; empty batches skipped; a worker
+    exception reaches the consumer; close() lets the worker exit."""
+    import time
+    import wap_b200
+    from wap_b200 import synth
+    batches = []
+    for i in range(7):
+        imgs, caps = synth.synth_batch(10 + i, 1 + i % 3, 16 + 4 * i, 24 + 8 * (i % 4), 2 + i % 5, ragged=True)
+        batches.append((imgs, caps))
+    batches.insert(3, ([], []))                                   # an empty shard slot (dp.shard_batches pads with these)
+    got = list(wap_b200.Prefetcher(batches, pinned=False, depth=2))
+    ref = [wap_b200.prepare_data(bx, by) for bx, by in batches if bx]
+    assert len(got) == len(ref) == 7
+    for g, r in zip(got, ref):
+        assert all(np.array_equal(a, b) for a, b in zip(g, r))
+
+    def bad():
+        yield batches[0]
+        raise ValueError("corrupt record")
+    it = iter(wap_b200.Prefetcher(bad(), pinned=False, depth=1))
+    next(it)
+    with pytest.raises(ValueError):
+        next(it)
+
+    def endless():
+        while True:
+            yield batches[1]
+    pf = wap_b200.Prefetcher(endless(), pinned=False, depth=2)
+    it = iter(pf); next(it); next(it)
+    pf.close()
+    time.sleep(0.5)
+    assert not pf._thread.is_alive()

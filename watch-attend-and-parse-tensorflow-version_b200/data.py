@@ -13,7 +13,7 @@ from __future__ import annotations
 
 import pickle
 import sys
-from typing import Dict, List, Sequence, Tuple
+from typing import Dict, Iterable, List, Sequence, Tuple
 
 import numpy as np
 
@@ -128,3 +128,54 @@ def prepare_data(images_x: Sequence[np.ndarray], seqs_y: Sequence[Sequence[int]]
     if pinned:
         return tx, txm, ty, tym
     return x, x_mask, y, y_mask
+
+
+class Prefetcher:
+    """Runs `prepare_data` (padding, /255, masks, optional pinned staging) for the next batches on a background thread while
+    the GPU works on the current one (the reference prepares every batch synchronously inside the step loop,
+    model-single-GPU.py:637-640).  Iterating yields (x, x_mask, y, y_mask) in the order of `batches`; empty batches are skipped;
+    an exception in the worker is re-raised in the consumer.  depth = number of prepared batches kept ahead."""
+
+    _END = object()
+
+    def __init__(self, batches: Iterable[Tuple[Sequence[np.ndarray], Sequence[Sequence[int]]]], pinned: bool = False, depth: int = 2):
+        import queue
+        import threading
+        self._q: "queue.Queue" = queue.Queue(maxsize=max(1, int(depth)))
+        self._stop = threading.Event()
+        self._thread = threading.Thread(target=self._work, args=(iter(batches), pinned), daemon=True)
+        self._thread.start()
+
+    def _put(self, item) -> bool:
+        import queue
+        while not self._stop.is_set():
+            try:
+                self._q.put(item, timeout=0.1)
+                return True
+            except queue.Full:
+                continue
+        return False
+
+    def _work(self, it, pinned):
+        try:
+            for batch_x, batch_y in it:
+                if not batch_x:
+                    continue
+                if not self._put(prepare_data(batch_x, batch_y, pinned=pinned)):
+                    return
+            self._put(self._END)
+        except BaseException as e:                         # noqa: BLE001 - handed to the consumer
+            self._put(e)
+
+    def __iter__(self):
+        while True:
+            item = self._q.get()
+            if item is self._END:
+                return
+            if isinstance(item, BaseException):
+                raise item
+            yield item
+
+    def close(self):
+        """Stop early (e.g. on early stopping): the worker exits at its next queue operation."""
+        self._stop.set()
