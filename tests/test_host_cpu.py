@@ -344,3 +344,103 @@ def test_prefetcher_order_errors_and_early_close():
     pf.close()
     time.sleep(0.5)
     assert not pf._thread.is_alive()
+
+
+def _reference_functions(path, names, extra_globals=None):
+    """Compiles the named top-level functions of a reference source file WITHOUT importing it (the module imports TensorFlow 1.6,
+    which cannot be installed here).  The source is read from /root/reference at test time; nothing is copied into the repo."""
+    import ast
+    src = open(path).read().replace("\t", "    ")
+    tree = ast.parse(src)
+    keep = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in names]
+    assert {n.name for n in keep} == set(names), [n.name for n in keep]
+    ns = {"np": np}
+    ns.update(extra_globals or {})
+    exec(compile(ast.Module(body=keep, type_ignores=[]), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def test_scorer_matches_the_references_own_code(tmp_path):
+    """WER / ExpRate: wap_b200.scorer and the oracle's wer_exprate against model-distributed.py:30-78 itself (cmp_result, process),
+    executed from /root/reference, on random recognition results incl. empty hypotheses and exact matches."""
+    from wap_b200 import scorer
+    cmp_result, process = _reference_functions("/root/reference/model-distributed.py", ["cmp_result", "process"])
+    rs = np.random.RandomState(5)
+    rec, lab = {}, {}
+    for i in range(60):
+        lab[f"u{i}"] = [str(t) for t in rs.randint(0, 7, size=rs.randint(1, 12))]
+        rec[f"u{i}"] = lab[f"u{i}"] if i % 4 == 0 else [str(t) for t in rs.randint(0, 7, size=rs.randint(0, 12))]
+    for k in rec:                                                   # edit distance of every pair
+        d_ref, n_ref = cmp_result(lab[k], rec[k])
+        assert (scorer.edit_distance(lab[k], rec[k]) if hasattr(scorer, "edit_distance") else None) in (None, int(d_ref))
+        assert n_ref == len(lab[k])
+    (tmp_path / "r.txt").write_text("".join(k + " " + " ".join(v) + "\n" for k, v in rec.items()))
+    (tmp_path / "l.txt").write_text("".join(k + "\t" + " ".join(v) + "\n" for k, v in lab.items()))
+    process(str(tmp_path / "r.txt"), str(tmp_path / "l.txt"), str(tmp_path / "ref.wer"))
+    wer, sacc = scorer.process(str(tmp_path / "r.txt"), str(tmp_path / "l.txt"), str(tmp_path / "ours.wer"))
+    assert (tmp_path / "ref.wer").read_text() == (tmp_path / "ours.wer").read_text()           # byte-identical result file
+    ow, oe = O.wer_exprate(rec, lab)
+    assert ow == pytest.approx(wer) and oe == pytest.approx(sacc)
+
+
+def test_initialiser_families_match_the_references_own_code():
+    """norm_weight / conv_norm_weight / ortho_weight of model-single-GPU.py:25-42, executed from /root/reference: same shapes,
+    the same uniform limits and orthogonality as ParamStore.init_reference / oracle.init_params produce."""
+    import math
+    norm_weight, conv_norm_weight, ortho_weight = _reference_functions(
+        "/root/reference/model-single-GPU.py", ["norm_weight", "conv_norm_weight", "ortho_weight"], {"rng": np.random.RandomState(1)})
+    P = O.init_params(0)
+    for name, fin, fout in (("W_a", 256, 512), ("U_a", 684, 512), ("Wo", 128, 111)):
+        r = norm_weight(fin, fout)
+        assert r.shape == P[name].shape and r.dtype == np.float32
+        lim = math.sqrt(6.0 / (fin + fout))
+        assert abs(np.abs(r).max() - lim) < 0.02 * lim and np.abs(P[name]).max() <= lim * (1 + 1e-6) and abs(np.abs(P[name]).max() - lim) < 0.02 * lim
+        assert abs(r.std() - P[name].std()) < 0.03 * lim
+    rk = conv_norm_weight(96, 24, [3, 3])
+    assert rk.shape == P["conv2d_2/kernel"].shape == (3, 3, 96, 24)
+    assert abs(np.abs(rk).max() - np.abs(P["conv2d_2/kernel"]).max()) < 0.02 * np.abs(rk).max()
+    u = ortho_weight(256).astype(np.float64)
+    assert np.abs(u @ u.T - np.eye(256)).max() < 1e-4
+    for name in ("U_rh", "U_rh_nl"):
+        v = P[name].astype(np.float64)
+        assert v.shape == (256, 256) and np.abs(v @ v.T - np.eye(256)).max() < 1e-4
+
+
+def test_beam_search_restatement_against_the_references_own_get_sample():
+    """Row a14: the reference's OWN beam-search bookkeeping (WAP.get_sample, model-single-GPU.py:442-542, compiled from
+    /root/reference without importing TensorFlow) is run with a fake `session` whose `run` is the oracle's get_word; the hypotheses
+    and scores it returns must equal the oracle's restatement (oracle.beam_decode), which is what the GPU tests compare
+    WAPEngine.get_sample with.  Also pins the -1 => zero-embedding start and the length-normalised pick (S:671-672)."""
+    import ast
+    import copy
+    import torch
+    path = "/root/reference/model-single-GPU.py"
+    tree = ast.parse(open(path).read().replace("\t", "    "))
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "WAP")
+    fn = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "get_sample")
+    sent = {k: k for k in ("anno", "infer_y", "alpha_past", "h_pre", "if_trainning")}       # feed_dict keys: module globals of the reference
+    ns = {"np": np, "copy": copy, "argmax": False, **sent}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), path, "exec"), ns)
+    ref_get_sample = ns["get_sample"]
+
+    P = O.lively_params(6)
+    Pt = O.to_torch(P)
+
+    class Session:                                     # sess.run([p, w, h, alpha], feed_dict) of S:473 served by the oracle step
+        def run(self, fetches, feed_dict):
+            assert fetches == ["p", "w", "h", "alpha"] and feed_dict["if_trainning"] is False
+            p, h, ap, _ = O.get_word(Pt, torch.as_tensor(feed_dict["infer_y"]), torch.as_tensor(feed_dict["h_pre"], dtype=torch.float64),
+                                     torch.as_tensor(feed_dict["alpha_past"], dtype=torch.float64), torch.as_tensor(feed_dict["anno"], dtype=torch.float64))
+            p32 = p.detach().to(torch.float32).numpy()
+            return p32, p32.argmax(1), h.detach().numpy(), ap.detach().numpy()
+
+    rs = np.random.RandomState(11)
+    for case, (h, w, k, maxlen) in enumerate([(4, 8, 10, 12), (3, 5, 3, 8), (5, 9, 10, 6)]):
+        ann = np.maximum(rs.randn(1, h, w, O.ANNOT_C), 0).astype(np.float32) * 0.5
+        h0 = O.hidden_state_0(Pt, torch.as_tensor(ann, dtype=torch.float64)).numpy()
+        samples, scores = ref_get_sample(None, "p", "w", "h", "alpha", ann, h0, k, maxlen, False, Session(), False)
+        best, o_samples, o_scores = O.beam_decode(Pt, torch.as_tensor(ann, dtype=torch.float64), k, maxlen)
+        assert [list(map(int, s)) for s in samples] == [list(map(int, s)) for s in o_samples], case
+        assert np.allclose(np.array(scores, np.float64), np.array(o_scores, np.float64), rtol=1e-6, atol=1e-6), case
+        norm = np.array(scores) / np.array([len(s) for s in samples])                     # S:671-672
+        assert list(map(int, samples[int(norm.argmin())])) == list(map(int, best)), case
