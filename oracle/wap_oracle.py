@@ -1,14 +1,22 @@
 """CPU oracle for the Watch-Attend-and-Parse hot path.  TEST INFRASTRUCTURE ONLY.
 
-    *** parity unpinned ***
+    *** parity: structure pinned to the reference's own code, TF op semantics unpinned ***
     The reference (wwjwhen/Watch-Attend-and-Parse-tensorflow-version) is a TensorFlow-1.6
     graph.  TensorFlow 1.6 cannot be imported in this environment (Python 3.12, no network),
     the reference ships no tests / golden vectors, and its .pkl inputs are git-LFS pointers.
     This file therefore *restates* the graph op-for-op from the reference source and from the
-    documented TF-1.6 op semantics (SAME padding, fused batch-norm, tf.scan ...).  Nothing pins it
-    to real TensorFlow output; what pins it internally is tests/test_oracle_*.py (brute-force
-    numpy loops for the SAME ops, fp64 finite-difference gradient checks, golden .npz files
-    under tests/golden/ produced by oracle/make_golden.py).
+    documented TF-1.6 op semantics (SAME padding, fused batch-norm, tf.scan ...).
+    What pins it:
+      * tests/test_reference_graph_cpu.py executes the reference's OWN classes (Watcher_train.dense_net,
+        Attender.get_context, Parser.one_time_step / get_ht_ctx, WAP.get_cost, WAP.get_word, WAP.get_sample)
+        from /root/reference on top of oracle/tf16_shim.py - an eager stand-in for the ~40 TF ops they call -
+        and requires agreement with this file to 1e-10: variable names and creation order, every slice,
+        gate order, bias placement, maxout pairing, embedding shift, masks, scan carry, moving-statistic
+        updates, dropout sites, beam-search bookkeeping.  Only the per-op semantics inside the shim remain a
+        restatement (nothing here can be compared with real TensorFlow output);
+      * tests/test_oracle_cpu.py: brute-force loops for the SAME ops and batch norm, fp64 finite-difference
+        gradient checks, golden .npz files under tests/golden/ produced by oracle/make_golden.py;
+      * tests/test_host_cpu.py: the reference's data.py, scorer, initialisers and get_sample run as shipped.
 
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg may
 import this module.  The product package never imports it.

@@ -1,0 +1,152 @@
+"""Runs the reference's OWN model classes (model-single-GPU.py, read from /root/reference at test time) on top of
+oracle/tf16_shim.py - an eager torch-fp64 stand-in for the TF-1.6 ops they call - and compares them with oracle/wap_oracle.py.
+
+This pins the STRUCTURE of the oracle (what is convolved with what, slices, gate order, where the biases sit, maxout pairing,
+embedding shift, scan carry, masks, which variables get which TF names in which order) to the reference source itself.  The
+semantics of the individual TF ops stay a documented restatement (the shim), cross-checked against brute-force loops in
+tests/test_oracle_cpu.py.  CPU only; /root/reference is not needed on the GPU box."""
+import importlib.util
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import O, make_batch, rel_err
+
+REF = "/root/reference/model-single-GPU.py"
+pytestmark = pytest.mark.skipif(not os.path.exists(REF), reason="reference checkout not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    from oracle import tf16_shim as tf
+    tf.install()
+    sys.path.insert(0, "/root/reference")
+    try:
+        spec = importlib.util.spec_from_file_location("ref_model_single_gpu", REF)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)                      # classes + initialisers only: main() sits behind the __main__ guard
+        yield mod, tf
+    finally:
+        sys.path.remove("/root/reference")
+        sys.modules.pop("data", None)                     # the reference's data.py must not shadow anything afterwards
+        tf.uninstall()
+
+
+def _build(mod, tf, P, training, drop=None):
+    tf.STATE.reset(preset=P, drop=drop)
+    watcher = mod.Watcher_train(blocks=3, level=16, growth_rate=24, training=training)
+    attender = mod.Attender(684, 256, 512)
+    parser = mod.Parser(256, 256, attender, 684)
+    wap = mod.WAP(watcher, attender, parser, 256, 256, 684, 111, training)
+    return watcher, attender, parser, wap
+
+
+def t64(a):
+    return torch.as_tensor(np.asarray(a), dtype=torch.float64)
+
+
+def test_variable_names_and_creation_order(ref):
+    """The variables the reference code creates (tf.Variable names + tf.layers default names) are exactly the oracle's / the
+    library's parameter set, and every one is found in the preset (i.e. nothing was initialised randomly)."""
+    mod, tf = ref
+    P = O.lively_params(1)
+    x, xm, y, ym = make_batch(3, 1, 32, 48, 2, False)
+    watcher, attender, parser, wap = _build(mod, tf, P, False)
+    with torch.no_grad():
+        watcher.dense_net(t64(x), t64(xm))
+    assert set(tf.STATE.variables) == set(P), set(tf.STATE.variables) ^ set(P)
+    assert tf.STATE.n_conv == 99 and tf.STATE.n_bn == 99 and tf.STATE.n_drop == 98
+
+
+@pytest.mark.parametrize("training,drop_seed", [(False, None), (True, None), (True, 7)])
+def test_dense_net_and_get_cost_match_oracle(ref, training, drop_seed):
+    """Watcher_train.dense_net + WAP.get_cost of the reference == oracle.dense_net + oracle.get_cost (fp64): annotation, mask,
+    cost and - in training mode - the moving-statistic updates, with and without (hash-keyed) dropout."""
+    mod, tf = ref
+    P = O.lively_params(5)
+    x, xm, y, ym = make_batch(21, 2, 40, 56, 4, True)
+    drop = O.hash_drop_fn(drop_seed) if drop_seed is not None else None
+    watcher, attender, parser, wap = _build(mod, tf, P, training, drop)
+    with torch.no_grad():
+        ann, am = watcher.dense_net(t64(x), t64(xm))
+        cost = wap.get_cost(ann, torch.as_tensor(y), am, t64(ym))
+        Pt = O.to_torch(P)
+        o_ann, o_am, o_moving = O.dense_net(Pt, t64(x), t64(xm), training, drop)
+        o_cost = O.get_cost(Pt, o_ann, torch.as_tensor(y), o_am, t64(ym), drop if training else None)
+    assert tuple(ann.shape) == tuple(o_ann.shape) and torch.equal(am, o_am)
+    assert rel_err(ann.numpy(), o_ann.numpy()) < 1e-10
+    assert abs(float(cost) - float(o_cost)) < 1e-10 * abs(float(o_cost))
+    if training:
+        assert set(tf.STATE.moving_updates) == set(o_moving)
+        for n, v in o_moving.items():
+            assert rel_err(tf.STATE.moving_updates[n].numpy(), v.numpy()) < 1e-10, n
+
+
+def test_get_context_and_one_time_step_match_oracle(ref):
+    """Attender.get_context and Parser.one_time_step / get_ht_ctx of the reference == the oracle, with both masks."""
+    mod, tf = ref
+    P = O.lively_params(2)
+    watcher, attender, parser, wap = _build(mod, tf, P, False)
+    Pt = O.to_torch(P)
+    rs = np.random.RandomState(4)
+    B, h, w, T = 3, 4, 6, 3
+    ann = t64(np.maximum(rs.randn(B, h, w, 684), 0) * 0.5)
+    am = torch.ones(B, h, w, dtype=torch.float64); am[1, 2:, :] = 0; am[2, :, 4:] = 0
+    hp = t64(np.tanh(rs.randn(B, 256))); ap = t64(rs.rand(B, h, w) * 0.2)
+    emb = t64(rs.randn(T, B, 256) * 0.3)
+    ym = torch.ones(T, B, dtype=torch.float64); ym[2, 1] = 0
+    with torch.no_grad():
+        for mask in (None, am):
+            c, a, apn = attender.get_context(ann, hp, ap.clone(), mask)          # the reference updates alpha_past in place
+            oc, oa, oap = O.get_context(Pt, ann, hp, ap, mask)
+            assert rel_err(c.numpy(), oc.numpy()) < 1e-12 and rel_err(a.numpy(), oa.numpy()) < 1e-12 and rel_err(apn.numpy(), oap.numpy()) < 1e-12
+        hs, cs, als, aps, anns, ams = parser.get_ht_ctx(emb, hp, ann, am, ym)
+        assert tuple(anns.shape) == (T, B, h, w, 684)                             # tf.scan stacks every carry, also the annotation
+        oh, oap = hp, torch.zeros(B, h, w, dtype=torch.float64)
+        for t in range(T):
+            oh, oc, oa, oap = O.one_time_step(Pt, oh, oap, ann, am, emb[t], ym[t])
+            assert rel_err(hs[t].numpy(), oh.numpy()) < 1e-12 and rel_err(cs[t].numpy(), oc.numpy()) < 1e-12
+            assert rel_err(als[t].numpy(), oa.numpy()) < 1e-12 and rel_err(aps[t].numpy(), oap.numpy()) < 1e-12
+
+
+def test_get_word_and_full_beam_search_of_the_reference(ref):
+    """WAP.get_word (S:379-439; it reads the module global `wap`, which main() would have to provide) against oracle.get_word, and
+    then the reference's get_sample driven by the reference's get_word - no oracle code in the loop - against oracle.beam_decode."""
+    mod, tf = ref
+    P = O.lively_params(6)
+    watcher, attender, parser, wap = _build(mod, tf, P, False)
+    mod.wap = wap
+    Pt = O.to_torch(P)
+    rs = np.random.RandomState(8)
+    h, w = 4, 7
+    ann1 = t64(np.maximum(rs.randn(1, h, w, 684), 0) * 0.5)
+    with torch.no_grad():
+        h0 = O.hidden_state_0(Pt, ann1)
+        # first step: y = -1 => zero embedding, one row
+        p, _, hn, apn = wap.get_word(torch.tensor([-1]), h0, torch.zeros(1, h, w, dtype=torch.float64), ann1)
+        op, oh, oap, _ = O.get_word(Pt, torch.tensor([-1]), h0, torch.zeros(1, h, w, dtype=torch.float64), ann1)
+        assert rel_err(p.numpy(), op.numpy()) < 1e-12 and rel_err(hn.numpy(), oh.numpy()) < 1e-12 and rel_err(apn.numpy(), oap.numpy()) < 1e-12
+        # later step: k = 3 live hypotheses sharing the annotation
+        y3 = torch.tensor([5, 17, 88]); h3 = t64(np.tanh(rs.randn(3, 256))); ap3 = t64(rs.rand(3, h, w) * 0.3)
+        p, _, hn, apn = wap.get_word(y3, h3, ap3.clone(), ann1.expand(3, -1, -1, -1))
+        op, oh, oap, _ = O.get_word(Pt, y3, h3, ap3, ann1.expand(3, -1, -1, -1))
+        assert rel_err(p.numpy(), op.numpy()) < 1e-12 and rel_err(hn.numpy(), oh.numpy()) < 1e-12 and rel_err(apn.numpy(), oap.numpy()) < 1e-12
+
+    class Session:                                             # session.run([p, w, h, alpha], feed_dict) served by the reference's get_word
+        def run(self, fetches, feed_dict):
+            with torch.no_grad():
+                p, wd, hh, ap = wap.get_word(torch.as_tensor(feed_dict[mod.infer_y]), t64(feed_dict[mod.h_pre]),
+                                             t64(feed_dict[mod.alpha_past]), t64(feed_dict[mod.anno]))
+            return p.to(torch.float32).numpy(), wd.numpy(), hh.numpy(), ap.numpy()
+
+    for name in ("anno", "infer_y", "alpha_past", "h_pre", "if_trainning"):       # the feed_dict keys get_sample looks up as globals
+        setattr(mod, name, name)
+    mod.argmax = False
+    for k, maxlen in ((10, 10), (3, 7)):
+        samples, scores = wap.get_sample("p", "w", "h", "alpha", ann1.numpy().astype(np.float32), h0.numpy(), k, maxlen, False, Session(), False)
+        best, o_samples, o_scores = O.beam_decode(Pt, t64(ann1.numpy().astype(np.float32)), k, maxlen)
+        assert [list(map(int, s)) for s in samples] == [list(map(int, s)) for s in o_samples]
+        assert np.allclose(np.array(scores, np.float64), np.array(o_scores, np.float64), rtol=1e-6, atol=1e-6)
