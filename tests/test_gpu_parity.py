@@ -438,3 +438,48 @@ def test_cuda_graph_replay_matches_stream_launches():
     assert abs(c1 - c2) <= 2e-5 * abs(c1) and len(eng._graphs) == 2
     p0 = eng.P.flat.clone(); eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=5)
     assert float((eng.P.flat - p0).abs().max()) > 0
+
+
+def test_engine_matches_reference_generated_golden(report):
+    """The CUDA path against tests/golden/ref_graph_cfg1.npz: vectors produced by the REFERENCE's own classes (dense_net, get_cost,
+    get_word, get_sample of /root/reference/model-single-GPU.py) running on oracle/tf16_shim.py - see oracle/make_reference_golden.py.
+    The reference cannot travel to the GPU box; these vectors do.  Workload: SURVEY 8d cfg1 (one 64 x 256 image, 10-token caption)."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_graph_cfg1.npz"))
+    x, xm, y, ym = make_batch(int(g["data_seed"]), 1, 64, 256, int(g["cap_len"]), False)
+    P = O.calibrate_moving(O.lively_params(int(g["param_seed"])), x, xm)
+    eng = engine_with(P)
+    fails = []
+    # ---- inference graph
+    ann, am = eng.dense_net(x, xm, training=False)
+    _check(report, "ref_golden", "annotation", ann.cpu().numpy(), g["annotation"], REL_TOL, fails)
+    _check(report, "ref_golden", "annotation_mask", am.cpu().numpy(), g["annotation_mask"], 0.0, fails)
+    cost = float(eng.get_cost(ann, y, am, ym))
+    e = abs(cost - float(g["cost"])) / abs(float(g["cost"]))
+    report.add("ref_golden", "cost", e, REL_TOL, extra=dict(got=cost, ref=float(g["cost"])))
+    if e > REL_TOL:
+        fails.append(("cost", cost, float(g["cost"])))
+    h0 = eng.hidden_state_0(ann)
+    probs, word, hn, apn = eng.get_word(np.full((1,), -1, np.int64), h0.cpu().numpy(), np.zeros((1,) + tuple(ann.shape[1:3]), np.float32), ann)
+    _check(report, "ref_golden", "probs0", probs.cpu().numpy(), g["probs0"], REL_TOL, fails)
+    _check(report, "ref_golden", "h1", hn.cpu().numpy(), g["h1"], REL_TOL, fails)
+    _check(report, "ref_golden", "alpha_past1", apn.cpu().numpy(), g["alpha_past1"], REL_TOL, fails)
+    best = [int(t) for t in g["beam_best"] if t >= 0]
+    got = [int(t) for t in eng.get_sample(ann, int(g["beam_k"]), int(g["beam_maxlen"]))[0]]
+    report.add("ref_golden", "beam_identical", 0.0 if got == best else 1.0, 0.0, extra=dict(got=got, ref=best))
+    if got != best:
+        fails.append(("beam", got, best))
+    # ---- training graph (batch statistics, hash-keyed dropout)
+    seed = int(g["drop_seed"])
+    ann_t, am_t = eng.dense_net(x, xm, training=True, dropout=True, seed=seed)
+    _check(report, "ref_golden", "train_annotation", ann_t.cpu().numpy(), g["train_annotation"], REL_TOL, fails)
+    cost_t = float(eng.get_cost(ann_t, y, am_t, ym, dropout=True, seed=seed))
+    e = abs(cost_t - float(g["train_cost"])) / abs(float(g["train_cost"]))
+    report.add("ref_golden", "train_cost", e, REL_TOL, extra=dict(got=cost_t, ref=float(g["train_cost"])))
+    if e > REL_TOL:
+        fails.append(("train_cost", cost_t, float(g["train_cost"])))
+    sd = eng.P.state_dict()
+    for key in g.files:
+        if key.startswith("new::"):
+            _check(report, "ref_golden", key[5:], sd[key[5:]], g[key], REL_TOL, fails)
+    assert not fails, fails

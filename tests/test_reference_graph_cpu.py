@@ -150,3 +150,35 @@ def test_get_word_and_full_beam_search_of_the_reference(ref):
         best, o_samples, o_scores = O.beam_decode(Pt, t64(ann1.numpy().astype(np.float32)), k, maxlen)
         assert [list(map(int, s)) for s in samples] == [list(map(int, s)) for s in o_samples]
         assert np.allclose(np.array(scores, np.float64), np.array(o_scores, np.float64), rtol=1e-6, atol=1e-6)
+
+
+def test_reference_golden_is_reproducible_and_matches_oracle(ref):
+    """tests/golden/ref_graph_cfg1.npz (what the GPU box compares the CUDA path with) is exactly what oracle/make_reference_golden.py
+    produces from the reference's classes today, and the oracle reproduces it."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    try:
+        import make_reference_golden as G
+    finally:
+        sys.path.pop(0)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_graph_cfg1.npz"))
+    out = G.generate()
+    assert set(out) == set(g.files)
+    for k in g.files:
+        assert np.array_equal(np.asarray(out[k]), g[k]), k
+    # the oracle against the fixture
+    x, xm, y, ym = make_batch(int(g["data_seed"]), 1, 64, 256, int(g["cap_len"]), False)
+    P = O.calibrate_moving(O.lively_params(int(g["param_seed"])), x, xm)
+    Pt = O.to_torch(P)
+    with torch.no_grad():
+        ann, am, _ = O.dense_net(Pt, t64(x), t64(xm), False)
+        assert rel_err(ann.numpy(), g["annotation"]) < 1e-6
+        assert abs(float(O.get_cost(Pt, ann, torch.as_tensor(y), am, t64(ym))) - float(g["cost"])) < 1e-9 * abs(float(g["cost"]))
+        best = O.beam_decode(Pt, t64(ann.numpy().astype(np.float32)), int(g["beam_k"]), int(g["beam_maxlen"]))[0]
+        assert [int(t) for t in best] == [int(t) for t in g["beam_best"] if t >= 0]
+        drop = O.hash_drop_fn(int(g["drop_seed"]))
+        ann_t, am_t, nm = O.dense_net(Pt, t64(x), t64(xm), True, drop)
+        assert rel_err(ann_t.numpy(), g["train_annotation"]) < 1e-6
+        assert abs(float(O.get_cost(Pt, ann_t, torch.as_tensor(y), am_t, t64(ym), drop)) - float(g["train_cost"])) < 1e-9 * abs(float(g["train_cost"]))
+        for k in g.files:
+            if k.startswith("new::"):
+                assert rel_err(nm[k[5:]].numpy(), g[k]) < 1e-6, k
