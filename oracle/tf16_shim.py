@@ -34,9 +34,10 @@ class _State:
     def __init__(self):
         self.reset()
 
-    def reset(self, preset: Optional[Dict[str, np.ndarray]] = None, drop: Optional[Callable] = None):
+    def reset(self, preset: Optional[Dict[str, np.ndarray]] = None, drop: Optional[Callable] = None, requires_grad: bool = False):
         self.preset = dict(preset or {})
         self.drop = drop
+        self.requires_grad = requires_grad                    # trainable variables become autograd leaves (tf.gradients stand-in)
         self.variables: Dict[str, torch.Tensor] = {}          # every variable created, by TF name
         self.moving_updates: Dict[str, torch.Tensor] = {}     # UPDATE_OPS results: new moving statistics
         self.n_conv = 0; self.n_bn = 0; self.n_drop = 0
@@ -62,6 +63,8 @@ def _var(name, make):
         v = torch.as_tensor(np.asarray(STATE.preset[name])).to(DT).clone()
     else:
         v = _f(make())
+    if STATE.requires_grad and not name.endswith(("moving_mean", "moving_variance")):
+        v.requires_grad_(True)
     STATE.variables[name] = v
     return v
 

@@ -35,8 +35,8 @@ def ref():
         tf.uninstall()
 
 
-def _build(mod, tf, P, training, drop=None):
-    tf.STATE.reset(preset=P, drop=drop)
+def _build(mod, tf, P, training, drop=None, requires_grad=False):
+    tf.STATE.reset(preset=P, drop=drop, requires_grad=requires_grad)
     watcher = mod.Watcher_train(blocks=3, level=16, growth_rate=24, training=training)
     attender = mod.Attender(684, 256, 512)
     parser = mod.Parser(256, 256, attender, 684)
@@ -182,3 +182,30 @@ def test_reference_golden_is_reproducible_and_matches_oracle(ref):
         for k in g.files:
             if k.startswith("new::"):
                 assert rel_err(nm[k[5:]].numpy(), g[k]) < 1e-6, k
+
+
+def test_gradients_of_the_reference_graph_match_oracle(ref):
+    """tf.gradients stand-in: torch autograd THROUGH the reference's dense_net + get_cost (training mode, hash-keyed dropout) gives the
+    same gradient for every one of the 329 trainable variables as autograd through the oracle - the gradients the CUDA path is tested
+    against (test_full_gradients).  Tensors whose gradient vanishes identically (V_a_b: the softmax is shift-invariant) are compared on
+    the global scale."""
+    mod, tf = ref
+    P = O.lively_params(5)
+    x, xm, y, ym = make_batch(21, 2, 40, 56, 4, True)
+    drop = O.hash_drop_fn(7)
+    watcher, attender, parser, wap = _build(mod, tf, P, True, drop, requires_grad=True)
+    ann, am = watcher.dense_net(t64(x), t64(xm))
+    cost = wap.get_cost(ann, torch.as_tensor(y), am, t64(ym))
+    names = [n for n, v in tf.STATE.variables.items() if v.requires_grad]
+    grads = dict(zip(names, torch.autograd.grad(cost, [tf.STATE.variables[n] for n in names])))
+    Pt = O.to_torch(P, torch.float64, requires_grad=True)
+    o_ann, o_am, _ = O.dense_net(Pt, t64(x), t64(xm), True, drop)
+    o_cost = O.get_cost(Pt, o_ann, torch.as_tensor(y), o_am, t64(ym), drop)
+    o_names = O.trainable_names(Pt)
+    o_grads = dict(zip(o_names, torch.autograd.grad(o_cost, [Pt[n] for n in o_names])))
+    assert set(names) == set(o_names) and len(names) == 329
+    assert abs(float(cost.detach()) - float(o_cost.detach())) < 1e-10 * abs(float(o_cost.detach()))
+    gmax = max(float(g.abs().max()) for g in o_grads.values())
+    for n in names:
+        scale = max(float(o_grads[n].abs().max()), 1e-6 * gmax)
+        assert float((grads[n] - o_grads[n]).abs().max()) / scale < 1e-9, n
