@@ -200,3 +200,27 @@ def test_wer_exprate_scorer():
     wer, exp = O.wer_exprate(rec, lab)
     assert abs(wer - (1 + 0 + 1) / 5) < 1e-12 and abs(exp - 1 / 3) < 1e-12
     assert O.edit_distance([1, 2, 3], [1, 3]) == 1 and O.edit_distance([], [1, 2]) == 2
+
+
+def test_adadelta_update_matches_an_independent_implementation():
+    """The oracle's Adadelta (tf.train.AdadeltaOptimizer, S:602: rho = 0.95, epsilon = 1e-8, learning_rate fed = 1.0) against
+    torch.optim.Adadelta(rho=0.95, eps=1e-8, lr=1.0) - an independent implementation of the same published update rule - over
+    three steps of a full oracle train_step (the gradient includes the L2 term, as in the reference's `cost`)."""
+    P = O.lively_params(3)
+    imgs, caps = O.synth_batch(9, 2, 24, 40, 3, ragged=True)
+    x, xm, y, ym = O.prepare_data(imgs, caps)
+    names = O.trainable_names(P)
+    acc = {n: np.zeros(P[n].shape, np.float64) for n in names}
+    accd = {n: np.zeros(P[n].shape, np.float64) for n in names}
+    tp = {n: torch.nn.Parameter(torch.as_tensor(P[n], dtype=torch.float64)) for n in names}
+    opt = torch.optim.Adadelta([tp[n] for n in names], lr=1.0, rho=0.95, eps=1e-8)
+    Pn = dict(P)
+    for step in range(3):
+        _, G, Pn, acc, accd = O.train_step(Pn, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(50 + step))
+        for n in names:
+            tp[n].grad = torch.as_tensor(G[n], dtype=torch.float64)
+        opt.step()
+        # same gradient stream -> the parameters must follow the same trajectory (the oracle rounds parameters to fp32 each step)
+        for n in ("conv2d_5/kernel", "U_a", "embed", "batch_normalization_7/gamma", "bo"):
+            got, ref = Pn[n].astype(np.float64), tp[n].detach().numpy()
+            assert np.abs(got - ref).max() <= 2e-7 * max(np.abs(ref).max(), 1e-3) * (step + 1), (n, step)
