@@ -224,3 +224,40 @@ def test_adadelta_update_matches_an_independent_implementation():
         for n in ("conv2d_5/kernel", "U_a", "embed", "batch_normalization_7/gamma", "bo"):
             got, ref = Pn[n].astype(np.float64), tp[n].detach().numpy()
             assert np.abs(got - ref).max() <= 2e-7 * max(np.abs(ref).max(), 1e-3) * (step + 1), (n, step)
+
+
+# ------------------------------------------------------------------ the TF-1.6 op shim against the same brute-force loops
+@pytest.mark.parametrize("H,W,k,s,pad", [(6, 7, 7, 2, "SAME"), (7, 6, 7, 2, "SAME"), (5, 4, 3, 1, "SAME"), (4, 5, 11, 1, "SAME"), (3, 3, 1, 1, "VALID")])
+def test_shim_ops_match_loops(H, W, k, s, pad):
+    """oracle/tf16_shim.py (the stand-in the reference's own classes run on) implements the documented TF semantics: conv SAME /
+    VALID, 2x2 SAME max / average pooling with valid-count divisor, fused batch norm, dropout keep-scale."""
+    from oracle import tf16_shim as tf
+    rs = np.random.RandomState(H * 10 + W)
+    x = rs.randn(2, H, W, 2); w = rs.randn(k, k, 2, 3)
+    tf.STATE.reset(preset={"conv2d/kernel": w})
+    got = tf.layers.conv2d(t64(x), filters=3, kernel_size=[k, k], strides=s, padding=pad, use_bias=False).numpy()
+    np.testing.assert_allclose(got, _conv_same_loops(x, w, s), atol=1e-10)           # k = 1: SAME == VALID
+    np.testing.assert_allclose(tf.nn.conv2d(t64(x), filter=t64(w), strides=[1, 1, 1, 1], padding="SAME").numpy(), _conv_same_loops(x, w, 1), atol=1e-10)
+    Ho, Wo = -(-H // 2), -(-W // 2)
+    mx = np.full((2, Ho, Wo, 2), -np.inf); sm = np.zeros((2, Ho, Wo, 2)); cnt = np.zeros((Ho, Wo))
+    for i in range(H):
+        for j in range(W):
+            mx[:, i // 2, j // 2] = np.maximum(mx[:, i // 2, j // 2], x[:, i, j])
+            sm[:, i // 2, j // 2] += x[:, i, j]; cnt[i // 2, j // 2] += 1
+    np.testing.assert_allclose(tf.layers.max_pooling2d(t64(x), pool_size=[2, 2], strides=2, padding="SAME").numpy(), mx, atol=1e-12)
+    np.testing.assert_allclose(tf.layers.average_pooling2d(t64(x), pool_size=[2, 2], strides=2, padding="SAME").numpy(), sm / cnt[None, :, :, None], atol=1e-12)
+    # batch norm (training): biased batch variance for the normalisation, Bessel-corrected for the moving update
+    g, b = rs.randn(2), rs.randn(2); mm, mv = rs.randn(2), rs.rand(2) + 0.5
+    tf.STATE.reset(preset={"batch_normalization/gamma": g, "batch_normalization/beta": b, "batch_normalization/moving_mean": mm,
+                           "batch_normalization/moving_variance": mv})
+    y = tf.layers.batch_normalization(t64(x), training=True, momentum=0.9, scale=True, epsilon=1e-4).numpy()
+    mean = x.reshape(-1, 2).mean(0); var = x.reshape(-1, 2).var(0); n = x.size // 2
+    np.testing.assert_allclose(y, (x - mean) / np.sqrt(var + 1e-4) * g + b, atol=1e-10)
+    np.testing.assert_allclose(tf.STATE.moving_updates["batch_normalization/moving_variance"].numpy(), 0.9 * mv + 0.1 * var * n / (n - 1), atol=1e-12)
+    np.testing.assert_allclose(tf.STATE.moving_updates["batch_normalization/moving_mean"].numpy(), 0.9 * mm + 0.1 * mean, atol=1e-12)
+    # dropout: keep-mask scaled by 1 / (1 - rate), identity when not training
+    tf.STATE.reset(drop=lambda key, shape: torch.as_tensor((np.arange(int(np.prod(shape))) % 5 != 0).astype(np.float64).reshape(shape)))
+    d = tf.layers.dropout(t64(x), rate=0.2, training=True).numpy()
+    keep = (np.arange(x.size) % 5 != 0).reshape(x.shape)
+    np.testing.assert_allclose(d, x * keep / 0.8, atol=1e-12)
+    assert np.array_equal(tf.layers.dropout(t64(x), rate=0.2, training=False).numpy(), x)
