@@ -209,3 +209,22 @@ def test_gradients_of_the_reference_graph_match_oracle(ref):
     for n in names:
         scale = max(float(o_grads[n].abs().max()), 1e-6 * gmax)
         assert float((grads[n] - o_grads[n]).abs().max()) / scale < 1e-9, n
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 37, 75), (1, 33, 65), (3, 18, 50)])
+def test_dense_net_on_odd_and_ragged_sizes(ref, B, H, W):
+    """Odd heights / widths exercise the asymmetric stem padding, the ceil-mode pools, the valid-count average pool and the
+    `[:, 0::2, 0::2]` mask subsampling of the reference (S:80, 87, 130) against the oracle; ragged batches exercise the masks."""
+    mod, tf = ref
+    P = O.lively_params(4)
+    x, xm, y, ym = make_batch(31 + B, B, H, W, 3, True)
+    for training in (False, True):
+        watcher, attender, parser, wap = _build(mod, tf, P, training)
+        with torch.no_grad():
+            ann, am = watcher.dense_net(t64(x), t64(xm))
+            cost = wap.get_cost(ann, torch.as_tensor(y), am, t64(ym))
+            Pt = O.to_torch(P)
+            o_ann, o_am, _ = O.dense_net(Pt, t64(x), t64(xm), training)
+            o_cost = O.get_cost(Pt, o_ann, torch.as_tensor(y), o_am, t64(ym))
+        assert tuple(ann.shape) == tuple(o_ann.shape) == (B, -(-H // 16), -(-W // 16), 684) and torch.equal(am, o_am)
+        assert rel_err(ann.numpy(), o_ann.numpy()) < 1e-10 and abs(float(cost) - float(o_cost)) < 1e-10 * abs(float(o_cost))
