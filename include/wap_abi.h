@@ -31,6 +31,20 @@ extern "C" {
 int wap_abi_version(void);
 const char* wap_last_error(void);
 
+/* ---- handles (wap_create / wap_destroy).  A handle owns what the reference keeps per tf.Session (S:609-611):
+ * the arithmetic mode of the convolutions, the launch switches (PDL, side-stream overlap), the side streams / events and
+ * the device source of the dropout seed.  wap_make_current binds a handle to the CALLING HOST THREAD (like
+ * cudaSetDevice): every wap_* call made by that thread afterwards runs under it; NULL rebinds the process-wide default
+ * handle, which is also what a thread uses before its first wap_make_current.  One handle per engine; two engines with
+ * different precision modes may coexist in one process.  A handle is used by one host thread at a time.
+ * There is no wap_repack: weight repacking (K-major hi/lo copies, Q' = Q*U_f) is part of every forward call, from the live
+ * weights, so there is no stale packed state to refresh after an optimiser step. */
+typedef struct wap_handle wap_handle;
+int wap_create(wap_handle** out);
+int wap_destroy(wap_handle* h);
+int wap_make_current(wap_handle* h);
+wap_handle* wap_current(void);   /* NULL = the default handle */
+
 /* ---- parameter layout (variables of S:562-607 under their TF names: conv2d[_k]/kernel,
  *      batch_normalization[_k]/{gamma,beta,moving_mean,moving_variance}, U_f ... bo) */
 int wap_param_count(void);
@@ -44,6 +58,13 @@ int64_t wap_moving_floats(void);
 int wap_annotation_hw(int H, int W, int* h, int* w);
 /* a_mask[b,i,j] = x_mask[b,16i,16j]   (S:80,86,130: four [:,0::2,0::2] slices) */
 int wap_mask_subsample(void* stream, const float* x_mask, int B, int H, int W, float* a_mask);
+
+/* ---- data.py prepare_data (DATA:100-122) on the device.  `pixels`: the B uint8 images of a batch packed back to back
+ * (image b = hw[2b] x hw[2b+1] bytes at byte offset offs[b]); all three arrays in DEVICE memory (one small H2D copy of the
+ * raw bytes instead of the padded fp32 tensors).  x [B,Hmax,Wmax,1] = pixel/255. (computed in double, rounded to fp32: the
+ * value numpy stores) inside the image and 0 in the padding; x_mask [B,Hmax,Wmax] = 1 inside, 0 in the padding. */
+int wap_prepare_batch(void* stream, const uint8_t* pixels, const int64_t* offs, const int32_t* hw, int B, int Hmax, int Wmax,
+                      float* x, float* x_mask);
 
 /* ---- Watcher_train.dense_net (S:73-132)
  * x [B,H,W,1]; annotation [B,h,w,684].  training != 0: batch statistics (+ moving-stat update,
@@ -153,7 +174,8 @@ int wap_tc_available(void);
 /* precision of the dense-block / transition convolutions (forward and dgrad) of wap_encoder_*:
  * 0 = fp32 FFMA (CUDA cores), 1 = TF32 tcgen05 tensor cores, single pass with RNA-rounded operands
  * (10-bit mantissa products), 2 = error-compensated 3xTF32 tcgen05 (a_hi*b_hi + a_lo*b_hi + a_hi*b_lo,
- * fp32-grade accuracy: the tensor-core parity mode) */
+ * fp32-grade accuracy: the tensor-core parity mode and the DEFAULT of every handle), 3 = bf16 speed mode (bf16 storage of
+ * activations and weights, tcgen05 kind::f16, fp32 accumulation and statistics; BASELINE configs[2]).  Per handle. */
 int wap_set_conv_precision(int mode);
 int wap_get_conv_precision(void);
 /* debugging aid: bit mask of the conv classes allowed on the tensor-core path (default all) */
@@ -182,7 +204,7 @@ int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int
 /* ---- dropout seed from device memory: when seed_dev != NULL every dropout site (S:89-93, S:361) reads its seed from
  * *seed_dev at kernel run time instead of the by-value `seed` argument, so that a training step captured once in a CUDA
  * graph can be replayed with a fresh seed per step (tf.layers.dropout draws new masks on every sess.run).  NULL restores
- * the by-value behaviour.  Library-global. */
+ * the by-value behaviour.  Per handle. */
 int wap_set_dropout_seed_source(const uint32_t* seed_dev);
 
 /* ---- programmatic dependent launch (default on): kernels are launched with the programmatic-stream-serialization

@@ -9,8 +9,11 @@ test_caption.txt}), same outputs (<path>/log-bs-6.txt, <path>/result/valid_decod
 maxlen 100, patience 15, lr/10 twice, then early stop; S:609-734) — but every FLOP runs in
 libwap_b200.so on the B200.  Under torchrun (WORLD_SIZE > 1) it trains data-parallel with a NCCL
 gradient all-reduce (semantics of model-distributed.py:704-717); rank 0 validates.
-Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --cuda_graphs, --prefetch N, --save CKPT.npz (written by rank 0 whenever the
-validation WER improves - the reference's tf.train.Saver is constructed but never called), --resume CKPT.npz.
+Extra flags (not in the reference): --max_epoch, --seed, --greedy_valid, --precision, --no_cuda_graphs, --prefetch N (default 2; 0 = synchronous
+host prepare_data as in the reference), --save CKPT.npz (written by rank 0 whenever the validation WER improves - the reference's tf.train.Saver
+is constructed but never called), --resume CKPT.npz (restores weights, Adadelta slots AND the lr / patience schedule).
+CUDA-graph replay targets repeated batch shapes: a shape is captured the second time it is seen (fixed-shape workloads replay every step;
+on the reference's area-bucketed batches most steps run as plain stream launches).
 """
 import argparse
 import os
@@ -39,38 +42,55 @@ def main(args):
     valid, valid_uid_list = wap_b200.dataIterator(args.path + '/data/offline-test.pkl', args.path + '/data/test_caption.txt', worddicts,
                                                   batch_size=args.batch_size, batch_Imagesize=400000, maxlen=100, maxImagesize=400000)
     print('train lenght is ', len(train))
-    eng = wap_b200.WAPEngine(seed=args.seed)
-    eng.world_size = world
-    eng.use_graphs = bool(args.cuda_graphs); eng.max_graphs = 64
-    if args.resume:
-        eng.load(args.resume)
+    eng = wap_b200.WAPEngine(seed=args.seed, precision=args.precision, use_graphs=not args.no_cuda_graphs)
+    eng.world_size, eng.rank = world, rank                 # rank enters the dropout seed: replicas draw different masks
+    sched = eng.load(args.resume) if args.resume else {}
     dp.broadcast_params(eng.P.flat); dp.broadcast_params(eng.P.moving)
     if args.resume and world > 1:
         dp.broadcast_params(eng.accum); dp.broadcast_params(eng.accum_update)
 
+    train = [b for b in train if b[0]]                       # drop empty batches BEFORE sharding: every rank runs the same number of steps
     uidx, cost_s, dispFreq = 0, 0.0, 100
     validFreq = sampleFreq = max(len(train) // world, 1)
     history_errs, estop, halfLrFlag, patience, lrate, bad_counter = [], False, 0, 15, 1.0, 0
+    first_epoch = 0
+    if sched:                                                # --resume continues the schedule instead of restarting it at lr 1.0
+        lrate, halfLrFlag, bad_counter = float(sched.get("lrate", lrate)), int(sched.get("halfLrFlag", 0)), int(sched.get("bad_counter", 0))
+        history_errs = [float(v) for v in np.atleast_1d(sched.get("history_errs", []))]
+        first_epoch, uidx = int(sched.get("epoch", 0)), int(sched.get("uidx", 0))
     log = open(args.path + '/log-bs-6.txt', 'w') if rank == 0 else None
     os.makedirs(args.path + '/result', exist_ok=True)
     rng = random.Random(args.seed)
+    for _ in range(first_epoch):                             # resume: replay the shuffles of the finished epochs
+        rng.shuffle(train)
 
     def say(msg):
         if rank == 0:
             print(msg); log.write(msg + '\n'); log.flush()
 
-    for epoch in range(args.max_epoch):
+    bad = torch.zeros(1, device=eng.device)
+    for epoch in range(first_epoch, args.max_epoch):
         rng.shuffle(train)                                   # same permutation on every rank; shards are disjoint
         shard = dp.shard_batches(train, rank, world)
-        # --prefetch N: padding / masks / pinned staging of the next N batches on a background thread (off by default)
-        prepared = wap_b200.Prefetcher(shard, pinned=True, depth=args.prefetch) if args.prefetch > 0 else \
-            (wap_b200.prepare_data(bx, by, pinned=True) for bx, by in shard if bx)
-        for x, x_m, y, y_m in prepared:
+        # --prefetch N (default 2): the next N batches are packed (raw uint8 pixels + captions, one pinned buffer each) on a background
+        # thread; /255, padding and masks happen on the GPU (wap_prepare_batch).  --prefetch 0: the reference's synchronous host path.
+        prepared = wap_b200.Prefetcher(shard, pinned=True, depth=args.prefetch, packed=True) if args.prefetch > 0 else \
+            (wap_b200.prepare_data(bx, by, pinned=True) for bx, by in shard)
+        for item in prepared:
             uidx += 1
-            cost_i = float(eng.train_step(x, y, x_m, y_m, lr=lrate))
+            if args.prefetch > 0:
+                cost_i = float(eng.train_step_packed(item, lr=lrate))
+            else:
+                x, x_m, y, y_m = item
+                cost_i = float(eng.train_step(x, y, x_m, y_m, lr=lrate))
             cost_s += cost_i
-            if np.isnan(cost_i) or np.isinf(cost_i):
+            bad[0] = float(np.isnan(cost_i) or np.isinf(cost_i))
+            if world > 1:                                    # every rank must leave together, or the others hang in the next all-reduce
+                torch.distributed.all_reduce(bad, op=torch.distributed.ReduceOp.MAX)
+            if float(bad[0]) > 0:
                 print('invalid cost value detected')
+                if world > 1:
+                    torch.distributed.destroy_process_group()
                 sys.exit(0)
             if uidx % dispFreq == 0:
                 cost_s /= dispFreq
@@ -116,7 +136,8 @@ def main(args):
                 if valid_per <= np.array(history_errs).min():
                     bad_counter = 0
                     if args.save:
-                        eng.save(args.save)
+                        eng.save(args.save, schedule=dict(lrate=lrate, halfLrFlag=halfLrFlag, bad_counter=bad_counter, history_errs=history_errs,
+                                                          epoch=epoch + 1, uidx=uidx))
                 else:
                     bad_counter += 1
                     if bad_counter > patience:
@@ -143,8 +164,10 @@ if __name__ == "__main__":
     parser.add_argument("--seed", type=int, default=0)
     parser.add_argument("--greedy_valid", action="store_true")
     parser.add_argument("--save", default="")
-    parser.add_argument("--prefetch", type=int, default=0, help="prepare this many batches ahead on a background thread")
-    parser.add_argument("--cuda_graphs", action="store_true", help="capture forward+backward once per batch shape and replay it")
+    parser.add_argument("--prefetch", type=int, default=2, help="pack this many batches ahead on a background thread (GPU-side /255 + masks); 0 = host prepare_data")
+    parser.add_argument("--no_cuda_graphs", action="store_true", help="never capture/replay forward+backward (default: shapes seen twice are captured)")
+    parser.add_argument("--cuda_graphs", action="store_true", help="(kept for round-1 command lines; graph replay is the default now)")
+    parser.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32", "tf32x3", "bf16"])
     parser.add_argument("--resume", default="")
     (args, unknown) = parser.parse_known_args()
     main(args)

@@ -256,6 +256,7 @@ def dense_net(P, x, mask_x, training: bool, drop: DropFn = None, taps: Optional[
         new_moving[bn_name(k, "moving_variance")] = nv
         if taps is not None:
             taps[f"minpre{k}"] = float(y.detach().abs().min())     # distance of the closest element to the ReLU kink
+            taps[f"minpre_c{k}"] = y.detach().abs().amin(dim=(0, 1, 2))   # ... per output channel
         y = torch.relu(y)
         if do_drop and training:
             y = _dropout(y, f"drop{k}", drop)
@@ -581,6 +582,23 @@ def hash_drop_fn(seed: int) -> Callable:
         n = int(np.prod(shape))
         return torch.as_tensor(drop_hash_keep(seed & 0xFFFFFFFF, site, n).reshape(shape))
     return fn
+
+
+def kink_channels(P_np, x, x_mask, drop: DropFn = None, tau: float = 5e-5) -> Dict[int, List[int]]:
+    """{conv index k: [output channels c]} whose BN output has an element within `tau` of the ReLU kink in a training-mode
+    forward.  fp32 arithmetic (1e-5 ... 2e-5 away from fp64 deep in the 99-layer net) may gate such an element differently
+    from fp64 - legitimately - and the flip moves the gradients of conv2d_k/kernel[..., c] and batch_normalization_k/{gamma,beta}[c]
+    by O(1/pixels-per-channel); nothing else moves measurably.  The gradient tests exclude exactly those entries."""
+    P = to_torch(P_np, torch.float64)
+    taps: dict = {}
+    dense_net(P, torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(x_mask, dtype=torch.float64), True, drop, taps=taps)
+    out: Dict[int, List[int]] = {}
+    for key, v in taps.items():
+        if key.startswith("minpre_c"):
+            cs = torch.nonzero(v < tau).flatten().tolist()
+            if cs:
+                out[int(key[len("minpre_c"):])] = cs
+    return out
 
 
 def relu_kink_margin(P_np, x, x_mask, drop: DropFn = None) -> float:

@@ -32,9 +32,9 @@ def make_batch(seed, B, H, W, cap_len, ragged=False):
     return O.prepare_data(imgs, caps)
 
 
-def engine_with(P_np):
+def engine_with(P_np, precision="tf32x3", use_graphs=True):
     import wap_b200
-    eng = wap_b200.WAPEngine(init=False)
+    eng = wap_b200.WAPEngine(init=False, precision=precision, use_graphs=use_graphs)
     eng.P.load(P_np)
     return eng
 
@@ -43,60 +43,54 @@ def t64(a):
     return torch.as_tensor(np.asarray(a), dtype=torch.float64)
 
 
-_WP_CACHE = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "well_posed_cache.json")
+def kink_excluded(P, x, xm, drop_seed=None, tau=5e-5, max_channels=64):
+    """Entries of the parameter gradients that a legitimate fp32-vs-fp64 ReLU gating difference may move (see
+    oracle.kink_channels): {variable name: channel indices along its LAST axis}.  Everything else must match the oracle on
+    THIS batch - there is no retry on another batch.  A cap on the number of excluded channels (of ~6000 BN channels) keeps
+    the exclusion from hiding a broad failure."""
+    drop = O.hash_drop_fn(drop_seed) if drop_seed is not None else None
+    kc = O.kink_channels(P, x, xm, drop, tau)
+    n = sum(len(v) for v in kc.values())
+    assert n <= max_channels, f"{n} near-kink channels: choose another seed for this test batch"
+    ex = {}
+    for k, cs in kc.items():
+        for name in (O.conv_name(k), O.bn_name(k, "gamma"), O.bn_name(k, "beta")):
+            ex[name] = np.asarray(cs, dtype=np.int64)
+    return ex
 
 
-def _wp_key(P, seed, B, H, W, cap_len, ragged, drop_seed, margin):
-    import zlib
-    crc = 0
-    for n in ("conv2d_1/kernel", "conv2d_98/kernel", "batch_normalization_50/gamma", "W_a"):
-        crc = zlib.crc32(np.ascontiguousarray(P[n], dtype=np.float32).tobytes(), crc)
-    return f"{crc:08x}_{seed}_{B}_{H}_{W}_{cap_len}_{int(ragged)}_{drop_seed}_{margin:g}"
+def grad_errors(names, got_by_name, ref_by_name, excluded, tol=2e-3):
+    """Per-tensor max-norm error (tensors whose gradient is tiny relative to the largest one are compared on the global
+    scale: they are dominated by fp32 rounding of large cancelling sums), with the near-kink channels masked out.
+    Returns (failures, worst_err, worst_name, median_rel_l2, n_masked_entries)."""
+    gmax = max(float(np.max(np.abs(ref_by_name[n]))) for n in names)
+    fails, worst, worst_name, l2s, masked = [], 0.0, None, [], 0
+    for n in names:
+        got = np.asarray(got_by_name[n], dtype=np.float64); ref = np.asarray(ref_by_name[n], dtype=np.float64)
+        d = np.abs(got - ref)
+        if n in excluded:
+            d[..., excluded[n]] = 0.0
+            masked += int(np.prod(d.shape[:-1])) * len(excluded[n])
+        scale = max(float(np.max(np.abs(ref))), 1e-4 * gmax)
+        err = float(np.max(d)) / scale
+        l2s.append(float(np.linalg.norm(d) / max(np.linalg.norm(ref), 1e-30)))
+        if err > worst:
+            worst, worst_name = err, n
+        if err > tol:
+            fails.append((n, err))
+    return fails, worst, worst_name, float(np.median(l2s)), masked
 
 
-def well_posed_batch(P, seed, B, H, W, cap_len, ragged, drop_seed=None, margin=4e-6, tries=2000):
-    """First batch (seeds seed, seed+1000, ...) none of whose ~1e6 BN outputs lies within `margin`
-    (a few fp32 ulps of an O(1) value; the CUDA forward is within ~2e-6 of fp64) of the ReLU kink (see
-    oracle.relu_kink_margin).  An element on the kink is gated differently by fp32 and fp64 arithmetic -
-    legitimately - and with only a few dozen pixels per channel in block 2 of these small test images one
-    flipped element moves that channel's gradients by ~1e-2, which says nothing about the kernels.
-    The index of the batch found is cached in tests/golden/well_posed_cache.json (the search costs up to
-    ~300 oracle forwards); a cached index is re-verified with one oracle forward."""
-    import json
-    drop = (lambda: O.hash_drop_fn(drop_seed)) if drop_seed is not None else (lambda: None)
-    key = _wp_key(P, seed, B, H, W, cap_len, ragged, drop_seed, margin)
-    try:
-        cache = json.load(open(_WP_CACHE))
-    except (OSError, ValueError):
-        cache = {}
-    if key in cache:
-        x, xm, y, ym = make_batch(seed + 1000 * cache[key], B, H, W, cap_len, ragged)
-        if O.relu_kink_margin(P, x, xm, drop()) > margin:
-            return x, xm, y, ym
-    for i in range(tries):
-        x, xm, y, ym = make_batch(seed + 1000 * i, B, H, W, cap_len, ragged)
-        if O.relu_kink_margin(P, x, xm, drop()) > margin:
-            cache[key] = i
-            for path in (_WP_CACHE, os.path.join(os.path.dirname(_WP_CACHE), "..", "..", "gpurun_out", "well_posed_cache.json")):
-                try:
-                    os.makedirs(os.path.dirname(path), exist_ok=True)
-                    json.dump(cache, open(path, "w"), indent=0, sort_keys=True)
-                except OSError:
-                    pass
-            return x, xm, y, ym
-    raise RuntimeError("no well-posed batch found")
+def oracle_grads(P, x, xm, y, ym, drop_seed=None, dtype=torch.float64):
+    """(cost, {name: d cost / d name}) of the oracle's training-mode forward (no L2 term)."""
+    Pt = O.to_torch(P, dtype, requires_grad=True)
+    dfn = O.hash_drop_fn(drop_seed) if drop_seed is not None else None
+    ann, am, _ = O.dense_net(Pt, torch.as_tensor(x, dtype=dtype), torch.as_tensor(xm, dtype=dtype), True, dfn)
+    cost = O.get_cost(Pt, ann, torch.as_tensor(y), am, torch.as_tensor(ym, dtype=dtype), dfn)
+    names = O.trainable_names(Pt)
+    grads = torch.autograd.grad(cost, [Pt[n] for n in names])
+    return float(cost.detach()), {n: g.numpy() for n, g in zip(names, grads)}, names
 
 
-def any_batch(run, attempts=3):
-    """run(attempt) -> list of failures for the attempt-th well-posed batch; passes when one batch matches.
-    Why this is a sound kernel test: a wrong kernel fails on EVERY batch, while a ReLU-kink flip fails on one.  The margin
-    of well_posed_batch (4e-6) guards the first layers; deep in the 99-layer net the fp32 forward deviates from fp64 by up
-    to ~1e-5 of the activation scale (measured: annotation 1e-5 ... 2e-5), a margin no random batch satisfies, so an
-    element can still be gated differently by the two precisions; one such element moves its channel's gradients by ~1e-2
-    (a few dozen pixels per channel in the last block of these small images)."""
-    last = None
-    for a in range(attempts):
-        last = run(a)
-        if not last:
-            return
-    assert not last, last[:20]
+def engine_grads(eng):
+    return eng.P.unpack(eng.grads)

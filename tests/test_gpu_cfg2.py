@@ -1,0 +1,247 @@
+"""Parity of the path that bench.py times, at the shape bench.py times it (BASELINE configs[1]):
+8 x 128x512 images, 40-token captions (T = 41), conv precision tf32x3, CUDA-graph replay, side-stream overlap and
+programmatic dependent launch on, dropout on.  Everything is compared with the CPU oracle (fp64 autograd), not with
+another mode of the engine.  Plus: a ragged CROHME-style batch (mixed H x W, odd sizes, rows wider than one 128-pixel
+tile so the 9-tap 3x3 fallback and partial tiles run), the data-parallel update on one GPU and under NCCL, workspace
+memory over many shapes, and two engines with different precision modes in one process.
+
+Reference being matched: one `sess.run([cost, trainer])` (model-single-GPU.py:640-641), the mean-of-replica-gradients
+update (model-distributed.py:704-717, per-replica batch norm :140)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (O, REL_TOL, ROOT, engine_grads, engine_with, grad_errors, kink_excluded, make_batch, oracle_grads, rel_err, t64)
+
+pytestmark = pytest.mark.gpu
+
+CFG2 = dict(B=8, H=128, W=512, cap=40)
+
+
+def _adadelta_formula(P, g_l2, acc, accd, lr=1.0):
+    out = {}
+    for n, g in g_l2.items():
+        a = O.ADADELTA_RHO * acc[n] + (1 - O.ADADELTA_RHO) * g * g
+        d = np.sqrt(accd[n] + O.ADADELTA_EPS) / np.sqrt(a + O.ADADELTA_EPS) * g
+        u = O.ADADELTA_RHO * accd[n] + (1 - O.ADADELTA_RHO) * d * d
+        out[n] = (P[n].astype(np.float64) - lr * d, a, u, d)
+    return out
+
+
+def test_cfg2_train_step_exactly_as_benchmarked(report):
+    """cost, annotation, all 329 gradients and one full Adadelta step of the GRAPH-REPLAYED tf32x3 step at cfg2."""
+    import wap_b200
+    P = O.lively_params(4)
+    eng = engine_with(P)                                   # defaults = what bench.py runs
+    L = wap_b200._lib.lib()
+    assert eng.use_graphs and eng.conv_precision() == "tf32x3" and eng.L.wap_get_pdl() == 1 and eng.L.wap_get_overlap() == 1
+    x, xm, y, ym = make_batch(2, CFG2["B"], CFG2["H"], CFG2["W"], CFG2["cap"])
+    assert x.shape == (8, 128, 512, 1) and y.shape == (41, 8)
+    seed = 31337
+    ex = kink_excluded(P, x, xm, seed)
+    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed)
+    costs = []
+    for i in range(3):                                     # 1: stream launches, 2: eager + capture, 3: REPLAY
+        costs.append(float(eng.forward_backward(x, y, xm, ym, dropout=True, seed=seed)))
+    assert len(eng._graphs) == 1 and eng.replayed_launches > 1000, (len(eng._graphs), eng.replayed_launches)
+    e = abs(costs[2] - ref_cost) / abs(ref_cost)
+    report.add("cfg2", "cost_replayed", e, REL_TOL, extra=dict(got=costs, ref=ref_cost))
+    fails, worst, worst_name, med, masked = grad_errors(names, engine_grads(eng), G, ex)
+    report.add("cfg2", "grad_worst_maxnorm", worst, 2e-3, extra=dict(name=worst_name, masked_entries=masked))
+    report.add("cfg2", "grad_median_rel_l2", med, 1e-3)
+    # annotation of the same training-mode forward (saved in the engine's role-keyed buffer)
+    Pt = O.to_torch(P)
+    ann_ref, am_ref, _ = O.dense_net(Pt, t64(x), t64(xm), True, O.hash_drop_fn(seed))
+    ann = eng._ws[("ann",)][: 8 * 8 * 32 * 684].view(8, 8, 32, 684).cpu().numpy()
+    ea = rel_err(ann, ann_ref.numpy())
+    report.add("cfg2", "annotation_training_mode", ea, REL_TOL)
+    assert e <= REL_TOL and ea <= REL_TOL and not fails and med <= 1e-3, (e, ea, fails[:10], med)
+    # ---- one full optimiser step through the replay path (train_step), from zero Adadelta state
+    zeros = {n: np.zeros(P[n].shape, np.float64) for n in names}
+    eng.P.load(P)                                          # moving statistics were updated by the three forwards above
+    cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
+    ref_cost2, G2, P2, acc2, accd2 = O.train_step(P, zeros, dict(zeros), x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
+    e2 = abs(cost - ref_cost2) / abs(ref_cost2)
+    report.add("cfg2", "cost_incl_l2_train_step", e2, REL_TOL, extra=dict(got=cost, ref=ref_cost2))
+    l2set = set(O.l2_names(P))
+    g_l2 = {n: engine_grads(eng)[n].astype(np.float64) + (2 * O.L2_COEF * P[n].astype(np.float64) if n in l2set else 0.0) for n in names}
+    f2, worst2, wn2, _, _ = grad_errors(names, g_l2, G2, ex)
+    report.add("cfg2", "gradient_incl_l2_vs_oracle", worst2, 2e-3, extra=dict(name=wn2))
+    form = _adadelta_formula(P, g_l2, zeros, zeros)
+    sd = eng.P.state_dict(); acc_e = eng.P.unpack(eng.accum); accd_e = eng.P.unpack(eng.accum_update)
+    worst_a = max(max(rel_err(acc_e[n], form[n][1]), rel_err(accd_e[n], form[n][2])) for n in names)
+    worst_p = max(float(np.max(np.abs(sd[n] - form[n][0]))) / max(float(np.max(np.abs(form[n][3]))), 1e-12) for n in names)
+    mv = max(rel_err(sd[n], P2[n]) for n in P if n.endswith("moving_variance") or n.endswith("moving_mean"))
+    report.add("cfg2", "adadelta_state_vs_formula", worst_a, 1e-4)
+    report.add("cfg2", "param_update_vs_formula", worst_p, 1e-3)
+    report.add("cfg2", "moving_stats", mv, 1e-3)
+    assert e2 <= REL_TOL and not f2 and worst_a <= 1e-4 and worst_p <= 1e-3 and mv <= 1e-3, (e2, f2[:10], worst_a, worst_p, mv)
+    del L
+
+
+def test_cfg2_inference_get_cost_and_greedy_L256(report):
+    """Inference encoder, get_cost (no dropout) and the persistent greedy decoder at B = 8, L = 8 x 32 = 256."""
+    x, xm, y, ym = make_batch(2, CFG2["B"], CFG2["H"], CFG2["W"], CFG2["cap"])
+    P = O.calibrate_moving(O.lively_params(5), x, xm)
+    eng = engine_with(P)
+    Pt = O.to_torch(P)
+    ann, am = eng.dense_net(x, xm, training=False)
+    ann_ref, am_ref, _ = O.dense_net(Pt, t64(x), t64(xm), False)
+    ea = rel_err(ann.cpu().numpy(), ann_ref.numpy())
+    report.add("cfg2", "annotation_inference", ea, REL_TOL)
+    assert np.array_equal(am.cpu().numpy(), am_ref.numpy())
+    cost = float(eng.get_cost(ann, y, am, ym, dropout=False))
+    ref = float(O.get_cost(Pt, ann_ref, torch.as_tensor(y), am_ref, t64(ym), None))
+    ec = abs(cost - ref) / abs(ref)
+    report.add("cfg2", "get_cost_T41_L256", ec, REL_TOL, extra=dict(got=cost, ref=ref))
+    toks, lens, _ = eng.greedy_decode(ann, 24)
+    bad = []
+    for b in range(CFG2["B"]):
+        ref_toks = O.greedy_decode(Pt, ann_ref[b:b + 1], 24)
+        got = toks[b, : int(lens[b])].cpu().tolist()
+        if got != ref_toks:
+            bad.append((b, got, ref_toks))
+    report.add("cfg2", "greedy_identical_8_images_L256", float(len(bad)), 0.0, extra=dict(mismatch=bad[:2]))
+    assert ea <= REL_TOL and ec <= REL_TOL and not bad, (ea, ec, bad[:2])
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+def test_ragged_crohme_style_batch(report, precision):
+    """Mixed H x W with odd sizes; the widest image is 70 x 610 -> block-0 rows of 153 pixels (> one 128-pixel tile: 9-tap 3x3 conv
+    fallback, partial M tiles), captions of different lengths, masks everywhere."""
+    rng = np.random.default_rng(7)
+    sizes = [(70, 610), (53, 333), (37, 141), (66, 475)]
+    imgs = [((rng.random((h, w)) < 0.1) * 255).astype(np.uint8)[None] for h, w in sizes]
+    caps = [[int(t) for t in rng.integers(1, 111, size=n)] for n in (9, 4, 1, 6)]
+    x, xm, y, ym = O.prepare_data(imgs, caps)
+    P = O.lively_params(6)
+    eng = engine_with(P, precision=precision)
+    seed = 99
+    ex = kink_excluded(P, x, xm, seed)
+    cost = float(eng.forward_backward(x, y, xm, ym, dropout=True, seed=seed))
+    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed)
+    e = abs(cost - ref_cost) / abs(ref_cost)
+    fails, worst, wn, med, masked = grad_errors(names, engine_grads(eng), G, ex)
+    report.add("ragged", f"cost_{precision}", e, REL_TOL)
+    report.add("ragged", f"grad_worst_maxnorm_{precision}", worst, 2e-3, extra=dict(name=wn, masked_entries=masked))
+    assert e <= REL_TOL and not fails and med <= 1e-3, (e, fails[:10], med)
+
+
+def test_dp_update_equals_mean_of_replica_gradients(report):
+    """a19 on one GPU: two image shards through forward_backward, summed gradients, apply_update with world_size = 2
+    == the oracle's train_step fed the other replica's gradient with inv_world = 1/2 (D:704-717); each shard's batch norm
+    used its own batch statistics (D:140)."""
+    P = O.lively_params(2)
+    names = O.trainable_names(P)
+    A = make_batch(21, 2, 40, 72, 4, True); Bt = make_batch(22, 2, 40, 72, 4, True)
+    sa, sb = 71, 72
+    eng = engine_with(P)
+    eng.world_size = 2
+    eng.forward_backward(A[0], A[2], A[1], A[3], dropout=True, seed=sa); ga = eng.grads.clone()
+    eng.P.load(P)                                          # replica B starts from the same weights / moving statistics
+    eng.forward_backward(Bt[0], Bt[2], Bt[1], Bt[3], dropout=True, seed=sb)
+    eng.grads += ga                                        # what the NCCL all-reduce(sum) leaves on every rank
+    eng.apply_update(1.0)
+    zeros = {n: np.zeros(P[n].shape, np.float64) for n in names}
+    _, Gb, _, _, _ = O.train_step(P, zeros, dict(zeros), Bt[0], Bt[1], Bt[2], Bt[3], 1.0, O.hash_drop_fn(sb))
+    _, G, P2, acc2, accd2 = O.train_step(P, zeros, dict(zeros), A[0], A[1], A[2], A[3], 1.0, O.hash_drop_fn(sa), extra_grads=Gb, inv_world=0.5)
+    ex = kink_excluded(P, A[0], A[1], sa)
+    for k, v in kink_excluded(P, Bt[0], Bt[1], sb).items():
+        ex[k] = np.union1d(ex[k], v) if k in ex else v
+    l2set = set(O.l2_names(P))
+    g_mean = {n: 0.5 * engine_grads(eng)[n].astype(np.float64) + (2 * O.L2_COEF * P[n].astype(np.float64) if n in l2set else 0.0) for n in names}
+    fails, worst, wn, med, _ = grad_errors(names, g_mean, G, ex)
+    report.add("dp", "mean_gradient_vs_oracle", worst, 2e-3, extra=dict(name=wn))
+    form = _adadelta_formula(P, g_mean, zeros, zeros)
+    sd = eng.P.state_dict()
+    worst_p = max(float(np.max(np.abs(sd[n] - form[n][0]))) / max(float(np.max(np.abs(form[n][3]))), 1e-12) for n in names)
+    report.add("dp", "update_vs_formula_on_mean_gradient", worst_p, 1e-3)
+    # accumulators of the oracle's update (a = 0.05 g^2) against the engine's
+    acc_e = eng.P.unpack(eng.accum)
+    wa = max(rel_err(np.delete(acc_e[n], ex[n], axis=-1) if n in ex else acc_e[n], np.delete(acc2[n], ex[n], axis=-1) if n in ex else acc2[n])
+             for n in names)
+    report.add("dp", "adadelta_accum_vs_oracle", wa, 4e-3)
+    assert not fails and worst_p <= 1e-3 and wa <= 4e-3, (fails[:10], worst_p, wa)
+
+
+@pytest.mark.skipif(torch.cuda.is_available() and torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_dp_two_ranks_nccl(report, tmp_path):
+    """The same statement under torchrun with 2 NCCL ranks: every rank ends with identical weights that equal the
+    single-process update on the summed gradients (tests/dp_nccl_worker.py prints the deviations)."""
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29655", os.path.join(ROOT, "tests", "dp_nccl_worker.py")], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, NCCL_NET_DISABLE="1"))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    assert out.stdout.count("DP_NCCL_OK") == 2, out.stdout[-3000:]
+
+
+def test_workspace_memory_is_bounded_over_many_shapes():
+    """the reference's area-bucketed batches give almost every step its own (B,H,W,T).  Workspaces are keyed
+    by role and grown to the largest size seen; 50 distinct shapes must not grow device memory beyond the largest one."""
+    eng = engine_with(O.lively_params(1))
+    rng = np.random.default_rng(0)
+    shapes = [(int(rng.integers(1, 4)), int(rng.integers(24, 72)), int(rng.integers(40, 200)), int(rng.integers(1, 9))) for _ in range(50)]
+    big = (3, 72, 200, 9)
+    x, xm, y, ym = make_batch(1, big[0], big[1], big[2], big[3])
+    for _ in range(2):
+        eng.train_step(x, y, xm, ym)
+    torch.cuda.synchronize()
+    base = torch.cuda.memory_allocated()
+    peak_seen = base
+    for i, (B, H, W, cap) in enumerate(shapes):
+        x, xm, y, ym = make_batch(100 + i, B, H, W, cap, True)
+        eng.train_step(x, y, xm, ym)
+        if i % 10 == 9:
+            torch.cuda.synchronize()
+            peak_seen = max(peak_seen, torch.cuda.memory_allocated())
+    torch.cuda.synchronize()
+    grown = max(peak_seen, torch.cuda.memory_allocated()) - base
+    assert grown < 64 << 20, f"device memory grew by {grown / 2**20:.1f} MiB over 50 shapes"
+    assert len(eng._ws) < 16, list(eng._ws)
+
+
+def test_two_engines_with_different_precision_coexist(report):
+    """Per-handle state (wap_create / wap_make_current): an fp32 engine and a 3xTF32 engine used alternately in one process
+    keep their own precision mode, launch switches and side streams, and both match the oracle."""
+    P = O.lively_params(3)
+    x, xm, y, ym = make_batch(31, 2, 40, 72, 4, True)
+    a = engine_with(P, precision="fp32", use_graphs=False)
+    b = engine_with(P, precision="tf32x3")
+    assert a.conv_precision() == "fp32" and b.conv_precision() == "tf32x3" and a.conv_precision() == "fp32"
+    a.L.wap_set_pdl(0)
+    assert b.L.wap_get_pdl() == 1 and a.L.wap_get_pdl() == 0
+    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, 5)
+    ex = kink_excluded(P, x, xm, 5)
+    for rep in range(3):                                   # interleaved; b captures a graph on its second step and replays on the third
+        ca = float(a.forward_backward(x, y, xm, ym, True, 5)); cb = float(b.forward_backward(x, y, xm, ym, True, 5))
+        for nm, eng, c in (("fp32", a, ca), ("tf32x3", b, cb)):
+            fails, worst, wn, med, _ = grad_errors(names, engine_grads(eng), G, ex)
+            report.add("handles", f"{nm}_rep{rep}", worst, 2e-3, extra=dict(name=wn))
+            assert abs(c - ref_cost) <= REL_TOL * abs(ref_cost) and not fails, (nm, rep, c, ref_cost, fails[:5])
+    assert len(b._graphs) == 1 and len(a._graphs) == 0
+
+
+def test_prepare_batch_on_device_is_bit_exact():
+    """wap_prepare_batch (GPU half of data.py prepare_data, DATA:100-122) == the host prepare_data, bit for bit."""
+    import wap_b200
+    rng = np.random.default_rng(3)
+    sizes = [(31, 77), (48, 64), (17, 99), (48, 99), (1, 1)]
+    imgs = [rng.integers(0, 256, size=(1, h, w), dtype=np.uint8) for h, w in sizes]
+    caps = [[int(t) for t in rng.integers(1, 111, size=n)] for n in (3, 7, 1, 5, 2)]
+    x, xm, y, ym = wap_b200.prepare_data(imgs, caps)
+    eng = engine_with(O.lively_params(1))
+    for pinned in (False, True):
+        pb = wap_b200.pack_batch(imgs, caps, pinned=pinned)
+        dx, dxm, dy, dym = eng.upload(pb)
+        assert np.array_equal(dx.cpu().numpy(), x) and np.array_equal(dxm.cpu().numpy(), xm)
+        assert np.array_equal(dy.cpu().numpy(), y.astype(np.int32)) and np.array_equal(dym.cpu().numpy(), ym)
+    c1 = float(eng.train_step_packed(pb, lr=1.0, dropout=True, seed=3))
+    eng2 = engine_with(O.lively_params(1))
+    c2 = float(eng2.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=3))
+    assert abs(c1 - c2) <= 2e-5 * abs(c2)
+    with pytest.raises(ValueError):
+        eng.forward_backward(x, np.full_like(y, 111), xm, ym)

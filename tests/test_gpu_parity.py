@@ -9,7 +9,8 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import O, REL_TOL, any_batch, engine_with, make_batch, rel_err, rel_l2, t64, well_posed_batch
+from helpers import (O, REL_TOL, engine_grads, engine_with, grad_errors, kink_excluded, make_batch, oracle_grads, rel_err, rel_l2,
+                     t64)
 
 pytestmark = pytest.mark.gpu
 
@@ -217,42 +218,26 @@ def test_get_cost_forward(report, B, h, w, T, drop):
     assert e <= REL_TOL, (float(cost), float(ref))
 
 
-@pytest.mark.parametrize("B,H,W,cap,drop", [(2, 32, 48, 3, False), (2, 40, 72, 5, True)])
-def test_full_gradients(report, B, H, W, cap, drop):
-    """Every one of the 329 parameter gradients of cost (no L2) vs fp64 autograd of the oracle."""
+@pytest.mark.parametrize("precision", ["tf32x3", "fp32"])
+@pytest.mark.parametrize("B,H,W,cap,drop,bseed", [(2, 32, 48, 3, False, 52), (2, 40, 72, 5, True, 52), (2, 40, 72, 5, True, 152)])
+def test_full_gradients(report, B, H, W, cap, drop, bseed, precision):
+    """Every one of the 329 parameter gradients of cost (no L2) vs fp64 autograd of the oracle, in the default 3xTF32
+    tensor-core mode and in the fp32 FFMA mode.  EVERY batch must pass; only the entries a legitimate fp32-vs-fp64 ReLU
+    gating difference can move (helpers.kink_excluded: channels with a BN output within 5e-5 of the kink) are masked."""
     P = O.lively_params(8)
     seed = 777
-    eng = engine_with(P)
-
-    def run(attempt):
-        x, xm, y, ym = well_posed_batch(P, 50 + B + 100 * attempt, B, H, W, cap, True, seed if drop else None)
-        cost = eng.forward_backward(x, y, xm, ym, dropout=drop, seed=seed)
-        Pt = O.to_torch(P, torch.float64, requires_grad=True)
-        dfn = O.hash_drop_fn(seed) if drop else None
-        ann, am, _ = O.dense_net(Pt, t64(x), t64(xm), True, dfn)
-        ref_cost = O.get_cost(Pt, ann, torch.as_tensor(y), am, t64(ym), dfn)
-        names = O.trainable_names(Pt)
-        grads = torch.autograd.grad(ref_cost, [Pt[n] for n in names])
-        tag = f"grads_B{B}_{H}x{W}_T{cap + 1}_drop{int(drop)}" + (f"_batch{attempt}" if attempt else "")
-        e = abs(float(cost) - float(ref_cost.detach())) / abs(float(ref_cost.detach()))
-        report.add(tag, "cost", e, REL_TOL, extra=dict(got=float(cost), ref=float(ref_cost.detach())))
-        fails = [] if e <= REL_TOL else [("cost", e)]
-        table = {n: (off, shape) for n, off, shape, fl in eng.P.table if not fl & 2}
-        gflat = eng.grads.cpu().numpy()
-        gmax = max(float(g.abs().max()) for g in grads)
-        for n, g in zip(names, grads):
-            off, shape = table[n]
-            got = gflat[off: off + int(np.prod(shape))].reshape(shape)
-            ref = g.numpy()
-            # per-tensor relative error; tensors whose gradient is tiny relative to the largest one are
-            # compared on the global scale (they are dominated by fp32 rounding of large cancelling sums)
-            scale = max(float(np.max(np.abs(ref))), 1e-4 * gmax)
-            err = float(np.max(np.abs(got - ref))) / scale
-            report.add(tag, n, err, 2e-3, extra=dict(ref_max=float(np.max(np.abs(ref)))))
-            if err > 2e-3:
-                fails.append((n, err))
-        return fails
-    any_batch(run)
+    eng = engine_with(P, precision=precision)
+    x, xm, y, ym = make_batch(bseed, B, H, W, cap, True)
+    ex = kink_excluded(P, x, xm, seed if drop else None)
+    cost = float(eng.forward_backward(x, y, xm, ym, dropout=drop, seed=seed))
+    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed if drop else None)
+    tag = f"grads_{precision}_B{B}_{H}x{W}_T{cap + 1}_drop{int(drop)}_b{bseed}"
+    e = abs(cost - ref_cost) / abs(ref_cost)
+    report.add(tag, "cost", e, REL_TOL, extra=dict(got=cost, ref=ref_cost))
+    fails, worst, worst_name, med, masked = grad_errors(names, engine_grads(eng), G, ex)
+    report.add(tag, "grad_worst_maxnorm", worst, 2e-3, extra=dict(name=worst_name, masked_entries=masked, masked_vars=len(ex)))
+    report.add(tag, "grad_median_rel_l2", med, 1e-3)
+    assert e <= REL_TOL and not fails and med <= 1e-3, (e, fails[:10], med)
 
 
 def test_adadelta_l2_step(report):
@@ -294,51 +279,42 @@ def test_train_steps_match_oracle(report):
     accd = {n: np.zeros(P[n].shape, np.float64) for n in names}
     Pn = dict(P)
     l2set = set(O.l2_names(P))
+    fails = []
     for step in range(2):
         seed = 500 + step
-        state = {}
-
-        def run(attempt, step=step, seed=seed):
-            nonlocal Pn, acc, accd
-            fails = []
-            x, xm, y, ym = well_posed_batch(Pn, 60 + step + 100 * attempt, B, H, W, cap, True, seed)
-            Pn_, acc_, accd_ = Pn, acc, accd
-            eng.P.load(Pn_); eng.P.pack_into(eng.accum, acc_); eng.P.pack_into(eng.accum_update, accd_)
-            Pprev, acc_prev, accd_prev = Pn_, acc_, accd_
-            cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
-            ref_cost, G, Pn2, acc2, accd2 = O.train_step(Pprev, acc_prev, accd_prev, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
-            e = abs(cost - ref_cost) / abs(ref_cost)
-            report.add("train_step", f"cost_step{step}", e, REL_TOL, extra=dict(got=cost, ref=ref_cost))
-            if e > REL_TOL:
-                fails.append(("cost", step, cost, ref_cost))
-            sd = eng.P.state_dict()
-            g_eng = eng.P.unpack(eng.grads); acc_e = eng.P.unpack(eng.accum); accd_e = eng.P.unpack(eng.accum_update)
-            gmax = max(float(np.max(np.abs(G[n]))) for n in names)
-            worst_g = worst_p = worst_a = 0.0; worst_name = None
-            for n in names:
-                g = g_eng[n].astype(np.float64) + (2 * O.L2_COEF * Pprev[n].astype(np.float64) if n in l2set else 0.0)
-                eg = float(np.max(np.abs(g - G[n]))) / max(float(np.max(np.abs(G[n]))), 1e-4 * gmax)
-                if eg > worst_g:
-                    worst_g, worst_name = eg, n
-                a = O.ADADELTA_RHO * acc_prev[n] + (1 - O.ADADELTA_RHO) * g * g
-                d = np.sqrt(accd_prev[n] + O.ADADELTA_EPS) / np.sqrt(a + O.ADADELTA_EPS) * g
-                u = O.ADADELTA_RHO * accd_prev[n] + (1 - O.ADADELTA_RHO) * d * d
-                pnew = Pprev[n].astype(np.float64) - d
-                worst_a = max(worst_a, rel_err(acc_e[n], a), rel_err(accd_e[n], u))
-                worst_p = max(worst_p, float(np.max(np.abs(sd[n] - pnew))) / max(float(np.max(np.abs(d))), 1e-12))
-            report.add("train_step", f"gradient_incl_l2_vs_oracle_step{step}", worst_g, 2e-3, extra=dict(name=worst_name))
-            report.add("train_step", f"adadelta_state_vs_formula_step{step}", worst_a, 1e-4)
-            report.add("train_step", f"param_update_vs_formula_step{step}", worst_p, 1e-3)
-            if worst_g > 2e-3 or worst_a > 1e-4 or worst_p > 1e-3:
-                fails.append(("update", step, worst_g, worst_a, worst_p))
-            mv = max(rel_err(sd[n], Pn2[n]) for n in P if n.endswith("moving_variance") or n.endswith("moving_mean"))
-            report.add("train_step", f"moving_stats_step{step}", mv, 1e-3)
-            if mv > 1e-3:
-                fails.append(("moving", step, mv))
-            state['next'] = (Pn2, acc2, accd2)
-            return fails
-        any_batch(run)
-        Pn, acc, accd = state['next']
+        x, xm, y, ym = make_batch(60 + step, B, H, W, cap, True)
+        ex = kink_excluded(Pn, x, xm, seed)
+        eng.P.load(Pn); eng.P.pack_into(eng.accum, acc); eng.P.pack_into(eng.accum_update, accd)
+        cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
+        ref_cost, G, Pn2, acc2, accd2 = O.train_step(Pn, acc, accd, x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
+        e = abs(cost - ref_cost) / abs(ref_cost)
+        report.add("train_step", f"cost_step{step}", e, REL_TOL, extra=dict(got=cost, ref=ref_cost))
+        if e > REL_TOL:
+            fails.append(("cost", step, cost, ref_cost))
+        sd = eng.P.state_dict()
+        g_eng = eng.P.unpack(eng.grads); acc_e = eng.P.unpack(eng.accum); accd_e = eng.P.unpack(eng.accum_update)
+        g_l2 = {n: g_eng[n].astype(np.float64) + (2 * O.L2_COEF * Pn[n].astype(np.float64) if n in l2set else 0.0) for n in names}
+        gf, worst_g, worst_name, _, masked = grad_errors(names, g_l2, G, ex)
+        worst_p = worst_a = 0.0
+        for n in names:
+            g = g_l2[n]
+            a = O.ADADELTA_RHO * acc[n] + (1 - O.ADADELTA_RHO) * g * g
+            d = np.sqrt(accd[n] + O.ADADELTA_EPS) / np.sqrt(a + O.ADADELTA_EPS) * g
+            u = O.ADADELTA_RHO * accd[n] + (1 - O.ADADELTA_RHO) * d * d
+            pnew = Pn[n].astype(np.float64) - d
+            worst_a = max(worst_a, rel_err(acc_e[n], a), rel_err(accd_e[n], u))
+            worst_p = max(worst_p, float(np.max(np.abs(sd[n] - pnew))) / max(float(np.max(np.abs(d))), 1e-12))
+        report.add("train_step", f"gradient_incl_l2_vs_oracle_step{step}", worst_g, 2e-3, extra=dict(name=worst_name, masked_entries=masked))
+        report.add("train_step", f"adadelta_state_vs_formula_step{step}", worst_a, 1e-4)
+        report.add("train_step", f"param_update_vs_formula_step{step}", worst_p, 1e-3)
+        if gf or worst_a > 1e-4 or worst_p > 1e-3:
+            fails.append(("update", step, gf[:5], worst_a, worst_p))
+        mv = max(rel_err(sd[n], Pn2[n]) for n in P if n.endswith("moving_variance") or n.endswith("moving_mean"))
+        report.add("train_step", f"moving_stats_step{step}", mv, 1e-3)
+        if mv > 1e-3:
+            fails.append(("moving", step, mv))
+        Pn, acc, accd = Pn2, acc2, accd2
+    assert not fails, fails
 
 
 @pytest.mark.parametrize("B,h,w", [(8, 8, 32), (16, 5, 9), (1, 4, 16), (3, 20, 50)])
@@ -411,33 +387,44 @@ def test_checkpoint_roundtrip(tmp_path):
 
 
 def test_cuda_graph_replay_matches_stream_launches():
-    """use_graphs: the captured forward+backward, replayed with a fresh device-side dropout seed, equals stream launches
-    with the same by-value seed on the same weights (run-to-run noise of the atomics only).  Whole training trajectories
-    are not compared: on these tiny batches two *eager* runs already diverge by 30% in the gradient after one Adadelta
-    step (sign-like first update), which says nothing about the replay."""
+    """use_graphs (the default): a shape is captured the SECOND time it is seen; the captured forward+backward, replayed with a
+    fresh device-side dropout seed, equals stream launches with the same by-value seed on the same weights (run-to-run noise of
+    the atomics only).  Whole training trajectories are not compared: on these tiny batches two *eager* runs already diverge by
+    30% in the gradient after one Adadelta step (sign-like first update), which says nothing about the replay."""
     P = O.lively_params(3)
-    x, xm, y, ym = well_posed_batch(P, 11, 3, 32, 64, 4, True, drop_seed=5)
+    x, xm, y, ym = make_batch(11, 3, 32, 64, 4, True)
     eng = engine_with(P)
+    assert eng.use_graphs and eng.conv_precision() == "tf32x3"
+    eng.forward_backward(x, y, xm, ym, True, 1)            # first sighting: plain stream launches, nothing captured
+    assert len(eng._graphs) == 0
     got = {}
-    for seed in (5, 6, 7, 5):                 # first call captures (and runs eagerly), the others replay
+    for seed in (5, 6, 7, 5):                 # second sighting captures (and runs eagerly), the others replay
         eng.use_graphs = True
         cg = float(eng.forward_backward(x, y, xm, ym, True, seed)); gg = eng.grads.clone()
         eng.use_graphs = False
         ce = float(eng.forward_backward(x, y, xm, ym, True, seed)); ge = eng.grads.clone()
         # two fp32 runs differ by the order of their atomic adds (~1e-6); a wrong seed or mask would differ by O(1)
         assert abs(cg - ce) <= 2e-5 * abs(ce), (seed, cg, ce)
-        if seed == 5:                         # the other seeds are not kink-checked: compare the cost only
-            assert rel_l2(gg.cpu().numpy(), ge.cpu().numpy()) < 1e-3, seed
+        assert rel_l2(gg.cpu().numpy(), ge.cpu().numpy()) < 1e-3, seed
         got[seed] = cg
     assert eng.replayed_launches > 0 and len(eng._graphs) == 1
     assert abs(got[5] - got[6]) > 1e-4 * abs(got[5]) and abs(got[6] - got[7]) > 1e-4 * abs(got[6])   # the seed really changed
-    # a different shape gets its own graph; a full train_step through the replay path still matches the Adadelta formula
+    # a different shape gets its own graph; a full train_step through the replay path still changes the weights
     x2, xm2, y2, ym2 = make_batch(12, 2, 32, 48, 3, True)
     eng.use_graphs = True
-    c1 = float(eng.forward_backward(x2, y2, xm2, ym2, True, 9)); c2 = float(eng.forward_backward(x2, y2, xm2, ym2, True, 9))
-    assert abs(c1 - c2) <= 2e-5 * abs(c1) and len(eng._graphs) == 2
+    cs = [float(eng.forward_backward(x2, y2, xm2, ym2, True, 9)) for _ in range(3)]
+    assert abs(cs[0] - cs[2]) <= 2e-5 * abs(cs[0]) and len(eng._graphs) == 2
     p0 = eng.P.flat.clone(); eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=5)
     assert float((eng.P.flat - p0).abs().max()) > 0
+    # LRU eviction and invalidation when a workspace grows
+    eng.max_graphs = 2
+    x3, xm3, y3, ym3 = make_batch(13, 2, 24, 40, 2, True)
+    for _ in range(2):
+        eng.forward_backward(x3, y3, xm3, ym3, True, 3)
+    assert len(eng._graphs) == 2 and (tuple(x2.shape), tuple(y2.shape), True, 2) not in eng._graphs
+    xb, xmb, yb, ymb = make_batch(14, 4, 64, 128, 6, True)   # larger than anything seen: workspaces are reallocated
+    eng.forward_backward(xb, yb, xmb, ymb, True, 3)
+    assert len(eng._graphs) == 0
 
 
 def test_engine_matches_reference_generated_golden(report):

@@ -291,24 +291,52 @@ def test_param_store_roundtrip_and_checkpoint_names():
             assert (off < ps.n_decay) == (not name.startswith("batch_normalization")), name
 
 
-def test_well_posed_cache_entries_are_valid():
-    """The cached batch indices of tests/golden/well_posed_cache.json (used by the GPU gradient tests) satisfy the kink margin:
-    a stale cache would silently cost ~300 oracle forwards on the GPU box."""
-    import json
-    from helpers import O, make_batch, _WP_CACHE
-    cache = json.load(open(_WP_CACHE))
-    assert len(cache) >= 12
-    checked = 0
-    for key, idx in cache.items():
-        crc, seed, B, H, W, cap, ragged, drop_seed, margin = key.split("_")
-        if crc != "8c69829b" or checked >= 4:        # lively_params(8): the parameter set of test_full_gradients
-            continue
-        P = O.lively_params(8)
-        x, xm, y, ym = make_batch(int(seed) + 1000 * idx, int(B), int(H), int(W), int(cap), bool(int(ragged)))
-        drop = O.hash_drop_fn(int(drop_seed)) if drop_seed != "None" else None
-        assert O.relu_kink_margin(P, x, xm, drop) > float(margin), key
-        checked += 1
-    assert checked >= 3
+def test_pack_batch_layout_and_packed_prefetcher():
+    """data.pack_batch (host half of the GPU-side prepare_data): offsets, sizes, captions and raw pixels are where
+    wap_prepare_batch / WAPEngine.upload read them; Prefetcher(packed=True) yields the same buffers in order."""
+    import wap_b200
+    rng = np.random.default_rng(5)
+    sizes = [(9, 14), (12, 7), (3, 20)]
+    imgs = [rng.integers(0, 256, size=(1, h, w), dtype=np.uint8) for h, w in sizes]
+    caps = [[5, 6, 7], [1], [9, 8, 7, 6]]
+    pb = wap_b200.pack_batch(imgs, caps)
+    assert (pb.B, pb.H, pb.W, pb.T) == (3, 12, 20, 5) and pb.off_pix % 16 == 0
+    buf = pb.buf
+    offs = buf[:pb.off_hw].view(np.int64); hw = buf[pb.off_hw:pb.off_y].view(np.int32).reshape(3, 2)
+    assert hw.tolist() == [list(s) for s in sizes] and offs.tolist() == [0, 126, 210]
+    _, _, y, ym = wap_b200.prepare_data(imgs, caps)
+    assert np.array_equal(buf[pb.off_y:pb.off_ym].view(np.int32).reshape(5, 3), y.astype(np.int32))
+    assert np.array_equal(buf[pb.off_ym:pb.off_ym + 60].view(np.float32).reshape(5, 3), ym)
+    for b, im in enumerate(imgs):
+        n = im.shape[1] * im.shape[2]
+        assert np.array_equal(buf[pb.off_pix + offs[b]: pb.off_pix + offs[b] + n], im.reshape(-1))
+    with pytest.raises(ValueError):
+        wap_b200.pack_batch(imgs, [[111], [1], [2]])
+    got = list(wap_b200.Prefetcher([(imgs, caps), ([], []), (imgs[:1], caps[:1])], packed=True, depth=1))
+    assert len(got) == 2 and np.array_equal(got[0].buf, buf) and got[1].B == 1
+
+
+def test_handles_create_destroy_and_defaults():
+    """wap_create / wap_make_current / wap_destroy (host-only: no device needed): per-handle precision and switches, default
+    mode 3xTF32, the default handle is untouched by a private one."""
+    import ctypes as C
+    import wap_b200
+    L = wap_b200._lib.lib()
+    L.wap_make_current(None)
+    d0 = L.wap_get_conv_precision(); p0 = L.wap_get_pdl()
+    h1, h2 = C.c_void_p(), C.c_void_p()
+    assert L.wap_create(C.byref(h1)) == 0 and L.wap_create(C.byref(h2)) == 0 and h1.value != h2.value
+    L.wap_make_current(h1)
+    assert L.wap_get_conv_precision() == 2 and L.wap_get_pdl() == 1 and L.wap_get_overlap() == 1
+    L.wap_set_pdl(0); L.wap_set_overlap(0)
+    L.wap_make_current(h2)
+    assert L.wap_get_pdl() == 1 and L.wap_get_overlap() == 1 and L.wap_current() == h2.value
+    L.wap_make_current(h1)
+    assert L.wap_get_pdl() == 0 and L.wap_get_overlap() == 0
+    assert L.wap_set_conv_precision(7) != 0 and b"mode" in L.wap_last_error()
+    L.wap_make_current(None)
+    assert L.wap_get_conv_precision() == d0 and L.wap_get_pdl() == p0 and not L.wap_current()
+    assert L.wap_destroy(h1) == 0 and L.wap_destroy(h2) == 0
 
 
 def test_prefetcher_order_errors_and_early_close():

@@ -4,7 +4,7 @@ The directory name follows the reference repository; import it as `wap_b200` (se
 repository root) or via importlib.import_module("watch-attend-and-parse-tensorflow-version_b200").
 """
 from . import _lib  # noqa: F401
-from .data import Prefetcher, dataIterator, load_dict, prepare_data  # noqa: F401
+from .data import PackedBatch, Prefetcher, dataIterator, load_dict, pack_batch, prepare_data  # noqa: F401
 
 
 def __getattr__(name):          # engine needs torch + the built extension: import lazily, fail loudly

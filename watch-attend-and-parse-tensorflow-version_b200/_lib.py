@@ -21,6 +21,11 @@ _ip = C.POINTER(C.c_int)
 SIGNATURES = {
     "wap_abi_version": (_i, []),
     "wap_last_error": (C.c_char_p, []),
+    "wap_create": (_i, [C.POINTER(_vp)]),
+    "wap_destroy": (_i, [_vp]),
+    "wap_make_current": (_i, [_vp]),
+    "wap_current": (_vp, []),
+    "wap_prepare_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "wap_param_count": (_i, []),
     "wap_param_info": (_i, [_i, C.c_char_p, _i, C.POINTER(_i64), _ip, C.POINTER(_i64), _ip]),
     "wap_param_floats": (_i64, []),

@@ -1,6 +1,7 @@
 // extern "C" surface of libwap_b200.so (declared in include/wap_abi.h).
 #include <stdarg.h>
 
+#include <new>
 #include <vector>
 
 #include "../../include/wap_abi.h"
@@ -12,20 +13,23 @@ namespace wap {
 
 static thread_local char g_err[1024] = "";
 unsigned long long g_launches = 0;
-int g_pdl = 1;
+static Context g_default_ctx;
+static thread_local Context* t_ctx = nullptr;
+Context* cur() { return t_ctx != nullptr ? t_ctx : &g_default_ctx; }
+bool pdl_enabled() { return cur()->pdl != 0; }
+int upload_wprep_table();
 extern long long* g_tc_trace;
 extern int g_fuse_gates;
 const int* trap_note_host();
-static int g_overlap = 1;
 SideStreams* side_streams() {
-  static SideStreams ss; static int state = 0;     // 0: not created, 1: ok, -1: failed
-  if (state == 0) {
-    state = 1;
-    for (int i = 0; i < 3 && state == 1; ++i) if (cudaStreamCreateWithFlags(&ss.s[i], cudaStreamNonBlocking) != cudaSuccess) state = -1;
-    for (int i = 0; i < 4 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.fork[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
-    for (int i = 0; i < 8 && state == 1; ++i) if (cudaEventCreateWithFlags(&ss.done[i], cudaEventDisableTiming) != cudaSuccess) state = -1;
+  Context* c = cur();
+  if (c->ss_state == 0) {
+    c->ss_state = 1;
+    for (int i = 0; i < 3 && c->ss_state == 1; ++i) if (cudaStreamCreateWithFlags(&c->ss.s[i], cudaStreamNonBlocking) != cudaSuccess) c->ss_state = -1;
+    for (int i = 0; i < 4 && c->ss_state == 1; ++i) if (cudaEventCreateWithFlags(&c->ss.fork[i], cudaEventDisableTiming) != cudaSuccess) c->ss_state = -1;
+    for (int i = 0; i < 8 && c->ss_state == 1; ++i) if (cudaEventCreateWithFlags(&c->ss.done[i], cudaEventDisableTiming) != cudaSuccess) c->ss_state = -1;
   }
-  return state == 1 ? &ss : nullptr;
+  return c->ss_state == 1 ? &c->ss : nullptr;
 }
 
 // ---- per-class device timing
@@ -38,7 +42,7 @@ static cudaEvent_t ev_get() {
   if (!g_ev_pool.empty()) { cudaEvent_t e = g_ev_pool.back(); g_ev_pool.pop_back(); return e; }
   cudaEvent_t e; cudaEventCreate(&e); return e;
 }
-bool overlap_enabled() { return g_overlap != 0 && !g_prof_on; }
+bool overlap_enabled() { return cur()->overlap != 0 && !g_prof_on; }
 void prof_set_bytes(double bytes) { g_prof_next_bytes = bytes; }
 void prof_begin(cudaStream_t st, int cls, double flops) {
   if (!g_prof_on) { g_prof_next_bytes = 0.0; return; }
@@ -94,6 +98,7 @@ extern int g_tc_debug_mask;
 extern int g_dbg_layer; extern float* g_dbg_buf;
 int mask_subsample(cudaStream_t st, const float* xm, int B, int H, int W, int h, int w, float* am);
 int dropout_mask(cudaStream_t st, uint32_t seed, uint32_t site, size_t n, float* mask);
+int prepare_batch(cudaStream_t st, const uint8_t* pix, const long long* offs, const int* hw, int B, int H, int W, float* x, float* xm);
 
 }  // namespace wap
 
@@ -158,6 +163,11 @@ int wap_annotation_hw(int H, int W, int* h, int* w) {
 int wap_mask_subsample(void* stream, const float* x_mask, int B, int H, int W, float* a_mask) {
   const EncGeom g = make_geom(B, H, W);
   return mask_subsample(ST(stream), x_mask, B, H, W, g.h[kBlocks - 1], g.w[kBlocks - 1], a_mask);
+}
+
+int wap_prepare_batch(void* stream, const uint8_t* pixels, const int64_t* offs, const int32_t* hw, int B, int Hmax, int Wmax, float* x, float* x_mask) {
+  WAP_REQUIRE(pixels && offs && hw && x && x_mask && B > 0 && Hmax > 0 && Wmax > 0, "wap_prepare_batch: bad arguments");
+  return prepare_batch(ST(stream), pixels, reinterpret_cast<const long long*>(offs), hw, B, Hmax, Wmax, x, x_mask);
 }
 
 int64_t wap_encoder_workspace_floats(int B, int H, int W, int training) {
@@ -270,7 +280,7 @@ int wap_gemm_tn_atomic(void* stream, const float* A, int lda, const float* B, in
 }
 int wap_tc_available(void) { return tc_available() ? 1 : 0; }
 int wap_set_conv_precision(int mode) {
-  WAP_REQUIRE(mode >= 0 && mode <= 2, "wap_set_conv_precision: mode must be 0 (fp32), 1 (tf32) or 2 (3xtf32)");
+  WAP_REQUIRE(mode >= 0 && mode <= 3, "wap_set_conv_precision: mode must be 0 (fp32), 1 (tf32), 2 (3xtf32) or 3 (bf16)");
   WAP_REQUIRE(mode == 0 || tc_available(), "TF32 tensor-core mode needs cuTensorMapEncodeTiled from the driver");
   set_conv_precision(mode);
   return 0;
@@ -308,11 +318,38 @@ int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies
 }
 int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
 int wap_debug_set_fuse_gates(int on) { wap::g_fuse_gates = on ? 1 : 0; return 0; }
-int wap_set_overlap(int on) { g_overlap = on ? 1 : 0; return 0; }
-int wap_get_overlap(void) { return g_overlap; }
-int wap_set_pdl(int on) { wap::g_pdl = on ? 1 : 0; return 0; }
-int wap_get_pdl(void) { return wap::g_pdl; }
-int wap_set_dropout_seed_source(const uint32_t* seed_dev) { wap::g_seed_src = seed_dev; return 0; }
+int wap_set_overlap(int on) { cur()->overlap = on ? 1 : 0; return 0; }
+int wap_get_overlap(void) { return cur()->overlap; }
+int wap_set_pdl(int on) { cur()->pdl = on ? 1 : 0; return 0; }
+int wap_get_pdl(void) { return cur()->pdl; }
+int wap_set_dropout_seed_source(const uint32_t* seed_dev) { cur()->seed_src = seed_dev; return 0; }
+
+/* ---- handles: per-engine state (precision mode, PDL / overlap switches, side streams, dropout-seed source) */
+int wap_create(wap_handle** out) {
+  WAP_REQUIRE(out != nullptr, "wap_create: out is NULL");
+  Context* c = new (std::nothrow) Context();
+  WAP_REQUIRE(c != nullptr, "wap_create: out of host memory");
+  *out = reinterpret_cast<wap_handle*>(c);
+  int dev = -1;
+  if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0) { int n = 0; if (cudaGetDeviceCount(&n) == cudaSuccess && n > 0) return upload_wprep_table(); }
+  cudaGetLastError();            // no device (host-only use of the geometry / layout functions): nothing to upload
+  return 0;
+}
+int wap_destroy(wap_handle* h) {
+  Context* c = reinterpret_cast<Context*>(h);
+  if (c == nullptr) return 0;
+  WAP_REQUIRE(c != &g_default_ctx, "wap_destroy: not a handle from wap_create");
+  if (t_ctx == c) t_ctx = nullptr;
+  if (c->ss_state == 1) {
+    for (int i = 0; i < 3; ++i) cudaStreamDestroy(c->ss.s[i]);
+    for (int i = 0; i < 4; ++i) cudaEventDestroy(c->ss.fork[i]);
+    for (int i = 0; i < 8; ++i) cudaEventDestroy(c->ss.done[i]);
+  }
+  delete c;
+  return 0;
+}
+int wap_make_current(wap_handle* h) { t_ctx = reinterpret_cast<Context*>(h); return 0; }
+wap_handle* wap_current(void) { return reinterpret_cast<wap_handle*>(t_ctx); }
 int wap_dropout_mask(void* stream, uint32_t seed, uint32_t site, int64_t n, float* mask) {
   return dropout_mask(ST(stream), seed, site, (size_t)n, mask);
 }

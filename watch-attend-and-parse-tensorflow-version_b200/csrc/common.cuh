@@ -28,7 +28,7 @@ extern unsigned long long g_launches;          // abi.cu: kernels launched by th
 // start-up overlap the current kernel's execution.  Every kernel of this library calls pdl_sync() first:
 // griddepcontrol.wait returns when the preceding grids have completed and their writes are visible (immediately when the
 // kernel was launched without the attribute), and launch_dependents then lets the successor start queueing.
-extern int g_pdl;                              // abi.cu: wap_set_pdl()
+bool pdl_enabled();                            // abi.cu: wap_set_pdl() of the current context
 // (Measured and rejected: triggering before the wait - so that barrier/TMEM set-up or weight prefetch overlap the predecessor -
 // gained nothing in the skinny GEMMs, cost 0.2 ms/step in the tcgen05 kernels, and both together ended in launch failures.)
 __device__ __forceinline__ void pdl_sync() {
@@ -42,7 +42,7 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 

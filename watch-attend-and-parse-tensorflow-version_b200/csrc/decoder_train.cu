@@ -224,7 +224,8 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   const int L = h * w, TB = T * B;
   DecTrainWs W = carve_train(wsp, B, L, T, nullptr);
   const int prec = get_conv_precision();
-  const bool tc = prec != 0 && tc_available();
+  const bool tc = prec != 0;
+  WAP_REQUIRE(!tc || tc_available(), "tensor-core conv precision requested but cuTensorMapEncodeTiled is unavailable (no silent FFMA fallback)");
   if (tc) {   // hoisted watch GEMM [B*L,684]x[684,512] on tensor cores; h0 and Q' as usual
     WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, nullptr, W.H, W.qf, W.mean));
     WAP_TRY(tc_prep_bt(st, params + P.U_a, kD, kNA, 1, W.UaT_hi, W.UaT_lo));
@@ -281,7 +282,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
   WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
   WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.Wy, kMw, W.LG, kMw, TB, kMw, kMw, nullptr, true));
-  WAP_CHECK(launch_pdl(maxout_drop_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.MO, TB, dropout, seed, g_seed_src));
+  WAP_CHECK(launch_pdl(maxout_drop_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.MO, TB, dropout, seed, seed_src()));
   WAP_LAUNCH_CHECK();
   WAP_CHECK(launch_pdl(wo_fwd_kernel, cdiv(TB * kVocab, 256), 256, 0, st, W.MO, params + P.Wo, params + P.bo, W.LO, TB));
   WAP_LAUNCH_CHECK();
@@ -502,13 +503,12 @@ dann_mean_kernel(const float* __restrict__ dmean, const float* __restrict__ a_ma
 
 // ------------------------------------------------------------------------------------ backward
 // grads (flat) accumulated (+=); d_ann [B,L,684] is written (=).
-static bool g_dec_join_pending = false;
 // the caller's stream waits for the decoder weight gradients still running on the side stream
 int decoder_join(cudaStream_t st) {
-  if (g_dec_join_pending) {
+  if (cur()->dec_join_pending) {
     SideStreams* ss = side_streams();
     if (ss != nullptr) WAP_CHECK(cudaStreamWaitEvent(st, ss->done[5], 0));
-    g_dec_join_pending = false;
+    cur()->dec_join_pending = false;
   }
   return 0;
 }
@@ -528,7 +528,8 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_TRY(transpose(st, p + P.U_hz_hr, W.T_Uhzhr, kN, 2 * kN));
   WAP_TRY(transpose(st, p + P.U_rh, W.T_Urh, kN, kN));
   const int prec = get_conv_precision();
-  const bool tc = prec != 0 && tc_available();
+  const bool tc = prec != 0;
+  WAP_REQUIRE(!tc || tc_available(), "tensor-core conv precision requested but cuTensorMapEncodeTiled is unavailable (no silent FFMA fallback)");
   if (tc) {
     WAP_TRY(tc_prep_bt(st, W.qf, kNA, kCovTaps, 0, W.qf_hi, W.qf_lo));
     WAP_TRY(tc_prep_bt(st, p + P.U_a, kNA, kD, 0, W.Ua_hi, W.Ua_lo));
@@ -538,7 +539,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_LAUNCH_CHECK();
   WAP_CHECK(launch_pdl(wo_bwd_weight_kernel, cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, st, W.MO, W.LO, g + P.Wo, g + P.bo, TB));
   WAP_LAUNCH_CHECK();
-  WAP_CHECK(launch_pdl(maxout_drop_bwd_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.dMO, W.dLG, TB, dropout, seed, g_seed_src));
+  WAP_CHECK(launch_pdl(maxout_drop_bwd_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.dMO, W.dLG, TB, dropout, seed, seed_src()));
   WAP_LAUNCH_CHECK();
   {   // weight gradients of the logit layer: side stream (joined together with the tail, see below)
     SideStreams* sh = overlap_enabled() ? side_streams() : nullptr;
@@ -665,7 +666,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     WAP_TRY(gemm_tn_atomic(sw, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
   }
   WAP_TRY(gemm_tn_atomic(sw, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));     // dU_a += ann^T * dWatch
-  if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->done[5], sw)); g_dec_join_pending = true; }
+  if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->done[5], sw)); cur()->dec_join_pending = true; }
   // d ann = dWatch * U_a^T
   if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));

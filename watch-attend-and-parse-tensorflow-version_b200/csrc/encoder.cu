@@ -378,10 +378,11 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
 //   bwd copy : 1x1 / transition: the HWIO matrix itself [Cin][Cout] (B operand of dgrad, K = Cout)
 //              3x3: [Cin=96][tap'*32 + co], tap' mirrored, co >= 24 zero  (dy2 rows are 32 floats)
 // =====================================================================================
-struct WPrepLayer { int kind, cin, cout, bld, rowtile; long long w, f, b, fl, bl; };
+struct WPrepLayer { int kind, cin, cout, bld, block; long long w, f, b, fl, bl; };
 __constant__ WPrepLayer c_wprep[kNumConv];
 
-__global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __restrict__ params, float* __restrict__ wsp, int with_bwd) {
+// rowtile_blocks: bit b set = the 3x3 convs of dense block b use the row-tile weight layout (image rows fit one 128-pixel tile)
+__global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __restrict__ params, float* __restrict__ wsp, int with_bwd, int rowtile_blocks) {
   pdl_sync();
   const WPrepLayer L = c_wprep[blockIdx.y];
   if (L.kind == kStem) return;
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
   auto split = [](float v, float* hi, float* lo) { const float h = tf32_rna(v); *hi = h; *lo = tf32_rna(v - h); };
   if (L.kind == kC3) {
     const int K = 9 * L.cin;                                  // 864
-    if (L.rowtile) {                                          // [96][288]: row 24 j + co, column 96 dy + ci  <-  w[dy][j][ci][co]
+    if ((rowtile_blocks >> L.block) & 1) {                    // [96][288]: row 24 j + co, column 96 dy + ci  <-  w[dy][j][ci][co]
       const int K3 = 3 * L.cin;
       for (int i = t0; i < 96 * K3; i += stride) {
         const int n = i / K3, k = i - n * K3, dy = k / L.cin, ci = k - dy * L.cin, j = n / L.cout, co = n - j * L.cout;
@@ -420,27 +421,34 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
   }
 }
 
-static int g_conv_precision = 0;          // 0: fp32 FFMA   1: TF32 tcgen05 (single pass, RNA-rounded operands)   2: 3xTF32 tcgen05 (fp32-grade)
 int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
 int g_tc_debug_mask = 0x1FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd
-const uint32_t* g_seed_src = nullptr;     // wap_set_dropout_seed_source(): device word holding the dropout seed (overrides the by-value seed)
-void set_conv_precision(int mode) { g_conv_precision = mode; }
-int get_conv_precision() { return g_conv_precision; }
+void set_conv_precision(int mode) { cur()->precision = mode; }
+int get_conv_precision() { return cur()->precision; }
 
-static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, const EncWorkspace& ws, bool with_bwd, int rowtile_blocks) {
+// The weight-copy region sits at the START of every encoder workspace (make_enc_workspace), so the layer table is the same
+// for every geometry: it is uploaded ONCE (synchronously, outside any stream capture - wap_create / the first eager call)
+// and never touched again.  (Round 1 re-uploaded a geometry-dependent host table at every call: a captured graph re-read
+// that table at replay time, after a different geometry had overwritten it.)
+int upload_wprep_table() {
   static bool uploaded = false;
+  if (uploaded) return 0;
   const ParamLayout& L = layout();
-  static WPrepLayer h[kNumConv];   // static: a captured CUDA graph re-reads this host table at every replay
+  const EncWorkspace ws = make_enc_workspace(make_geom(1, 16, 16), true);
+  WPrepLayer h[kNumConv];
   for (int i = 0; i < kNumConv; ++i) {
-    h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout; h[i].bld = ws.wt_bwd_ld[i];
-    h[i].rowtile = (L.conv[i].kind == kC3 && ((rowtile_blocks >> L.conv[i].block) & 1)) ? 1 : 0;
+    h[i].kind = L.conv[i].kind; h[i].cin = L.conv[i].cin; h[i].cout = L.conv[i].cout; h[i].bld = ws.wt_bwd_ld[i]; h[i].block = L.conv[i].block;
     h[i].w = (long long)L.conv[i].w; h[i].f = (long long)ws.wt_fwd[i]; h[i].b = (long long)ws.wt_bwd[i];
     h[i].fl = (long long)ws.wt_fwd_lo[i]; h[i].bl = (long long)ws.wt_bwd_lo[i];
   }
-  // offsets depend on the geometry (workspace layout): refresh the table on every call (cheap, 4 KB)
-  (void)uploaded;
-  WAP_CHECK(cudaMemcpyToSymbolAsync(c_wprep, h, sizeof(h), 0, cudaMemcpyHostToDevice, st));
-  WAP_CHECK(launch_pdl(prep_conv_weights_kernel, dim3(24, kNumConv), 256, 0, st, params, wsp, with_bwd ? 1 : 0));
+  WAP_CHECK(cudaMemcpyToSymbol(c_wprep, h, sizeof(h), 0, cudaMemcpyHostToDevice));
+  uploaded = true;
+  return 0;
+}
+
+static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, bool with_bwd, int rowtile_blocks) {
+  WAP_TRY(upload_wprep_table());
+  WAP_CHECK(launch_pdl(prep_conv_weights_kernel, dim3(24, kNumConv), 256, 0, st, params, wsp, with_bwd ? 1 : 0, rowtile_blocks));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -490,13 +498,14 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
   double* stats = reinterpret_cast<double*>(wsp + ws.stats);
   float* saved = wsp + ws.saved;
   if (training) WAP_CHECK(cudaMemsetAsync(stats, 0, sizeof(double) * kNumConv * 2 * kMaxBnC, st));
-  const bool tc = g_conv_precision != 0, x3 = g_conv_precision == 2;
+  const int prec = get_conv_precision();
+  const bool tc = prec != 0, x3 = prec == 2;
   int rowtile_blocks = 0;
   if (tc) {
     WAP_REQUIRE(tc_available(), "TF32 tensor-core mode requested but cuTensorMapEncodeTiled is unavailable");
     // 3x3 convs of a block whose rows fit one 128-pixel tile use the row-tile form (one third of the MMAs): bit b of the mask
     for (int b = 0; b < kBlocks; ++b) if (g.w[b] <= 128 && (g_tc_debug_mask & 256)) rowtile_blocks |= 1 << b;
-    WAP_TRY(prep_conv_weights(st, params, wsp, ws, training != 0, rowtile_blocks));
+    WAP_TRY(prep_conv_weights(st, params, wsp, training != 0, rowtile_blocks));
   }
   auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
   float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
@@ -509,7 +518,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
     a.mmean = moving + c.mmean; a.mvar = moving + c.mvar;
     a.gamma = params + c.gamma; a.beta = params + c.beta;
     a.saved = training ? saved + (size_t)k * 2 * kMaxBnC : nullptr;
-    a.training = training; a.dropout = (training && dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = g_seed_src; a.site = (uint32_t)k;
+    a.training = training; a.dropout = (training && dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = seed_src(); a.site = (uint32_t)k;
     a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;
   };
@@ -607,7 +616,8 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   };
   auto mark = [&](int e) -> int { if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->done[e], sw)); pend[e] = true; } return 0; };
   auto join = [&](int e) -> int { if (ss != nullptr && pend[e]) { WAP_CHECK(cudaStreamWaitEvent(st, ss->done[e], 0)); pend[e] = false; } return 0; };
-  const bool tc = g_conv_precision != 0, x3 = g_conv_precision == 2;
+  const int prec = get_conv_precision();
+  const bool tc = prec != 0, x3 = prec == 2;
   auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
   // dy2 rows are 32 floats (24 channels + zero pad) so that one row is one 128-byte TMA/UMMA row
   for (int i = 0; i < 2; ++i) WAP_CHECK(cudaMemsetAsync(dy2v[i], 0, sizeof(float) * (size_t)g.M[0] * kDy2Ld, st));
@@ -618,7 +628,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
     a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
     a.g = gbuf; a.ld_g = ld_g; a.red = red2[bn_no & 1]; a.red_next = red2[(bn_no + 1) & 1]; ++bn_no; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
-    a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = g_seed_src; a.site = (uint32_t)k;
+    a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = seed_src(); a.site = (uint32_t)k;
     a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;
   };

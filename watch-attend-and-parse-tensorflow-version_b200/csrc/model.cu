@@ -101,6 +101,29 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
   size_t off = 0;
   auto take = [&](size_t n) { size_t o = off; off += pad4(n); return o; };
   const ParamLayout& L = layout();
+  // tcgen05 weight copies FIRST and always complete (forward + dgrad copies): their offsets then do not depend on the geometry
+  // or on `training`, so the device-side layer table (encoder.cu: c_wprep) is a constant of the model (~13 M floats).
+  for (int i = 0; i < kNumConv; ++i) {       // tcgen05 weight copies: fwd [N(pad)][K], bwd (dgrad) [Cin][K']
+    const ConvLayer& c = L.conv[i];
+    ws.wt_bwd_ld[i] = c.cout;
+    if (c.kind == kC1 || c.kind == kTr) {
+      ws.wt_fwd[i] = take((size_t)c.cout * c.cin); ws.wt_fwd_lo[i] = take((size_t)c.cout * c.cin);
+      if (c.kind == kTr) { ws.wt_bwd[i] = take((size_t)c.cin * c.cout); ws.wt_bwd_lo[i] = take((size_t)c.cin * c.cout); }
+      if (c.kind == kC1) {
+        const int level = (i - (1 + c.block * (2 * kLevels + 1))) / 2;     // 1x1 of level j has conv index base + 2j
+        if ((level & 1) == 0) {          // even level: allocate the pair buffer (rows = Cin of the odd partner = cin + growth)
+          const size_t n = (size_t)(c.cin + kGrowth) * 2 * kBottle;
+          const size_t hi = take(n), lo = take(n);
+          ws.wt_bwd[i] = hi + kBottle; ws.wt_bwd_lo[i] = lo + kBottle;           // even level: columns 96..191
+          ws.wt_bwd[i + 2] = hi; ws.wt_bwd_lo[i + 2] = lo;                       // odd level : columns 0..95
+        }
+        ws.wt_bwd_ld[i] = 2 * kBottle;
+      }
+    } else if (c.kind == kC3) {
+      ws.wt_fwd[i] = take((size_t)32 * 9 * kBottle); ws.wt_fwd_lo[i] = take((size_t)32 * 9 * kBottle);
+      { ws.wt_bwd[i] = take((size_t)kBottle * 9 * kDy2Ld); ws.wt_bwd_lo[i] = take((size_t)kBottle * 9 * kDy2Ld); }
+    }
+  }
   ws.stats = take((size_t)kNumConv * 2 * kMaxBnC * 2);   // doubles (offset is a multiple of 4 floats = 16 B)
   ws.red = take(2 * kMaxBnC * 2 * 2);     // two [2][kMaxBnC] double buffers: BN backward n uses buffer n&1 and zeroes the other for n+1
   ws.saved = take((size_t)kNumConv * 2 * kMaxBnC);
@@ -133,27 +156,6 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
     for (int b = 0; b < kBlocks - 1; ++b) tr = std::max(tr, (size_t)g.M[b] * (g.Ctot[b] / 2));
     ws.dytr = take(tr);
     ws.gstem = take((size_t)g.B * g.Hs * g.Ws * kStemC);
-  }
-  for (int i = 0; i < kNumConv; ++i) {       // tcgen05 weight copies: fwd [N(pad)][K], bwd (dgrad) [Cin][K']
-    const ConvLayer& c = L.conv[i];
-    ws.wt_bwd_ld[i] = c.cout;
-    if (c.kind == kC1 || c.kind == kTr) {
-      ws.wt_fwd[i] = take((size_t)c.cout * c.cin); ws.wt_fwd_lo[i] = take((size_t)c.cout * c.cin);
-      if (training && c.kind == kTr) { ws.wt_bwd[i] = take((size_t)c.cin * c.cout); ws.wt_bwd_lo[i] = take((size_t)c.cin * c.cout); }
-      if (training && c.kind == kC1) {
-        const int level = (i - (1 + c.block * (2 * kLevels + 1))) / 2;     // 1x1 of level j has conv index base + 2j
-        if ((level & 1) == 0) {          // even level: allocate the pair buffer (rows = Cin of the odd partner = cin + growth)
-          const size_t n = (size_t)(c.cin + kGrowth) * 2 * kBottle;
-          const size_t hi = take(n), lo = take(n);
-          ws.wt_bwd[i] = hi + kBottle; ws.wt_bwd_lo[i] = lo + kBottle;           // even level: columns 96..191
-          ws.wt_bwd[i + 2] = hi; ws.wt_bwd_lo[i + 2] = lo;                       // odd level : columns 0..95
-        }
-        ws.wt_bwd_ld[i] = 2 * kBottle;
-      }
-    } else if (c.kind == kC3) {
-      ws.wt_fwd[i] = take((size_t)32 * 9 * kBottle); ws.wt_fwd_lo[i] = take((size_t)32 * 9 * kBottle);
-      if (training) { ws.wt_bwd[i] = take((size_t)kBottle * 9 * kDy2Ld); ws.wt_bwd_lo[i] = take((size_t)kBottle * 9 * kDy2Ld); }
-    }
   }
   ws.total = off;
   return ws;

@@ -84,7 +84,18 @@ struct SideStreams {
   cudaEvent_t fork[4];        // recorded on the main stream, waited by a side stream
   cudaEvent_t done[8];        // recorded on a side stream, waited by the main stream
 };
-SideStreams* side_streams();  // lazily created; nullptr on failure
+// Per-handle state (wap_create / wap_destroy / wap_make_current, include/wap_abi.h): everything that used to be process-global
+// in round 1.  Two engines in one process (say a validation engine in fp32 next to a training engine in 3xTF32) each own one.
+struct Context {
+  int precision = 2;                 // conv arithmetic: 0 fp32 FFMA | 1 TF32 tcgen05 single pass | 2 3xTF32 tcgen05 (default: the tensor-core parity mode) | 3 bf16 tcgen05
+  int pdl = 1;                       // programmatic dependent launch attribute on every launch
+  int overlap = 1;                   // side streams for work off the critical path
+  const uint32_t* seed_src = nullptr;   // device word overriding the by-value dropout seed (CUDA-graph replay draws fresh masks)
+  SideStreams ss; int ss_state = 0;  // 0: not created, 1: ok, -1: failed
+  bool dec_join_pending = false;     // decoder weight gradients still running on ss.s[1] (wap_train_backward joins them)
+};
+Context* cur();               // the calling host thread's current context (the process default one unless wap_make_current was called)
+SideStreams* side_streams();  // of the current context; lazily created; nullptr on failure
 bool overlap_enabled();
-extern const uint32_t* g_seed_src;   // device word overriding the by-value dropout seed (null: by-value)
+inline const uint32_t* seed_src() { return cur()->seed_src; }
 }  // namespace wap

@@ -1,6 +1,7 @@
 // L2 regulariser (model-single-GPU.py:594-598) + Adadelta (tf.train.AdadeltaOptimizer, :602-607)
 // as ONE multi-tensor kernel over the flat parameter buffer; also the mask subsample and the
 // dropout-mask export used by the tests.
+#include <algorithm>
 #include "common.cuh"
 
 namespace wap {
@@ -58,6 +59,27 @@ __global__ void mask_subsample_kernel(const float* __restrict__ xm, float* __res
 }
 int mask_subsample(cudaStream_t st, const float* xm, int B, int H, int W, int h, int w, float* am) {
   WAP_CHECK(launch_pdl(mask_subsample_kernel, cdiv(B * h * w, 256), 256, 0, st, xm, am, B, H, W, h, w));
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+// data.py prepare_data (DATA:100-122) on the device: pad to the batch maximum, /255, masks
+__global__ void __launch_bounds__(256) prepare_batch_kernel(const uint8_t* __restrict__ pix, const long long* __restrict__ offs, const int* __restrict__ hw,
+                                                            int B, int H, int W, float* __restrict__ x, float* __restrict__ xm) {
+  pdl_sync();
+  const size_t n = (size_t)B * H * W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % W); const size_t t = i / W; const int r = (int)(t % H), b = (int)(t / H);
+    const int hb = __ldg(hw + 2 * b), wb = __ldg(hw + 2 * b + 1);
+    const bool in = r < hb && c < wb;
+    float v = 0.f;
+    if (in) v = (float)((double)__ldg(pix + __ldg(offs + b) + (size_t)r * wb + c) / 255.0);
+    x[i] = v; xm[i] = in ? 1.f : 0.f;
+  }
+}
+int prepare_batch(cudaStream_t st, const uint8_t* pix, const long long* offs, const int* hw, int B, int H, int W, float* x, float* xm) {
+  const size_t n = (size_t)B * H * W;
+  WAP_CHECK(launch_pdl(prepare_batch_kernel, (unsigned)std::min<size_t>(cdivz(n, 256), 148 * 8), 256, 0, st, pix, offs, hw, B, H, W, x, xm));
   WAP_LAUNCH_CHECK();
   return 0;
 }

@@ -130,6 +130,56 @@ def prepare_data(images_x: Sequence[np.ndarray], seqs_y: Sequence[Sequence[int]]
     return x, x_mask, y, y_mask
 
 
+class PackedBatch:
+    """One batch staged for the GPU-side `prepare_data` (wap_prepare_batch): ONE host buffer
+    [offs int64 x B | hw int32 x 2B | y int32 x T*B | y_mask f32 x T*B | pad to 16 | raw uint8 pixels of the B images back to back]
+    so that a step needs a single H2D copy of B*H*W bytes + a few hundred bytes instead of the padded fp32 x and x_mask
+    (8 bytes per padded pixel).  /255, NHWC placement and both masks are produced on the device."""
+    __slots__ = ("buf", "B", "H", "W", "T", "off_hw", "off_y", "off_ym", "off_pix", "nbytes")
+
+    def __init__(self, buf, B, H, W, T, off_hw, off_y, off_ym, off_pix):
+        self.buf, self.B, self.H, self.W, self.T = buf, B, H, W, T
+        self.off_hw, self.off_y, self.off_ym, self.off_pix = off_hw, off_y, off_ym, off_pix
+        self.nbytes = int(buf.numel() if hasattr(buf, "numel") else buf.size)
+
+
+def pack_batch(images_x: Sequence[np.ndarray], seqs_y: Sequence[Sequence[int]], pinned: bool = False) -> PackedBatch:
+    """Host half of the device-side prepare_data: same inputs as `prepare_data` (uint8 [1,H,W] images, id lists)."""
+    B = len(images_x)
+    H = max(im.shape[1] for im in images_x)
+    W = max(im.shape[2] for im in images_x)
+    T = max(len(s) for s in seqs_y) + 1
+    off_hw = 8 * B
+    off_y = off_hw + 8 * B
+    off_ym = off_y + 4 * T * B
+    off_pix = (off_ym + 4 * T * B + 15) & ~15
+    npix = sum(int(im.shape[1]) * int(im.shape[2]) for im in images_x)
+    total = off_pix + npix
+    if pinned:
+        import torch
+        tbuf = torch.empty(total, dtype=torch.uint8).pin_memory()
+        buf = tbuf.numpy()
+    else:
+        tbuf = None
+        buf = np.empty(total, np.uint8)
+    offs = buf[:off_hw].view(np.int64); hw = buf[off_hw:off_y].view(np.int32)
+    y = buf[off_y:off_ym].view(np.int32).reshape(T, B); ym = buf[off_ym:off_ym + 4 * T * B].view(np.float32).reshape(T, B)
+    y[:] = 0; ym[:] = 0.
+    o = 0
+    for b, (im, seq) in enumerate(zip(images_x, seqs_y)):
+        hh, ww, n = int(im.shape[1]), int(im.shape[2]), len(seq)
+        if im.dtype != np.uint8:
+            raise TypeError("pack_batch expects the loader's uint8 images")
+        offs[b] = o; hw[2 * b] = hh; hw[2 * b + 1] = ww
+        buf[off_pix + o: off_pix + o + hh * ww] = np.ascontiguousarray(im[0]).reshape(-1)
+        o += hh * ww
+        if n and (min(seq) < 0 or max(seq) >= 111):
+            raise ValueError("token id out of range [0, 111)")
+        y[:n, b] = seq
+        ym[:n + 1, b] = 1.
+    return PackedBatch(tbuf if pinned else buf, B, H, W, T, off_hw, off_y, off_ym, off_pix)
+
+
 class Prefetcher:
     """Runs `prepare_data` (padding, /255, masks, optional pinned staging) for the next batches on a background thread while
     the GPU works on the current one (the reference prepares every batch synchronously inside the step loop,
@@ -138,11 +188,15 @@ class Prefetcher:
 
     _END = object()
 
-    def __init__(self, batches: Iterable[Tuple[Sequence[np.ndarray], Sequence[Sequence[int]]]], pinned: bool = False, depth: int = 2):
+    def __init__(self, batches: Iterable[Tuple[Sequence[np.ndarray], Sequence[Sequence[int]]]], pinned: bool = False, depth: int = 2,
+                 packed: bool = False):
+        """packed: yield `PackedBatch` objects (raw bytes for the GPU-side prepare_data) instead of the padded host tensors."""
         import queue
         import threading
         self._q: "queue.Queue" = queue.Queue(maxsize=max(1, int(depth)))
         self._stop = threading.Event()
+        self._prep = (lambda bx, by, pinned: pack_batch(bx, by, pinned=pinned)) if packed else \
+            (lambda bx, by, pinned: prepare_data(bx, by, pinned=pinned))
         self._thread = threading.Thread(target=self._work, args=(iter(batches), pinned), daemon=True)
         self._thread.start()
 
@@ -161,7 +215,7 @@ class Prefetcher:
             for batch_x, batch_y in it:
                 if not batch_x:
                     continue
-                if not self._put(prepare_data(batch_x, batch_y, pinned=pinned)):
+                if not self._put(self._prep(batch_x, batch_y, pinned)):
                     return
             self._put(self._END)
         except BaseException as e:                         # noqa: BLE001 - handed to the consumer

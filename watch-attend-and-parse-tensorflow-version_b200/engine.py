@@ -14,6 +14,7 @@ in libwap_b200.so.  There is no CPU / eager fallback.
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import math
 from typing import Dict, Optional
@@ -118,11 +119,20 @@ class ParamStore:
 class WAPEngine:
     """Owns parameters, optimiser state and workspaces of one GPU replica."""
 
-    def __init__(self, device: Optional[torch.device] = None, seed: int = 0, init: bool = True):
+    PRECISIONS = {"fp32": 0, "tf32": 1, "tf32x3": 2, "bf16": 3}
+
+    def __init__(self, device: Optional[torch.device] = None, seed: int = 0, init: bool = True, precision: str = "tf32x3",
+                 use_graphs: bool = True):
+        """precision / use_graphs default to the benchmarked path: error-compensated 3xTF32 tcgen05 convolutions (the
+        tensor-core parity mode) and CUDA-graph replay of forward+backward for batch shapes seen at least twice."""
         if not torch.cuda.is_available():
             raise _lib.WapError("WAPEngine needs a CUDA device (B200, sm_100a); there is no CPU path")
         self.device = device or torch.device("cuda", torch.cuda.current_device())
-        self.L = _lib.lib()
+        self._lib = _lib.lib()
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._lib.wap_create(C.byref(h)), "wap_create")
+        self._h = h                      # per-engine handle: precision mode, launch switches, side streams, dropout-seed source
         self.P = ParamStore(self.device)
         if init:
             self.P.init_reference(seed)
@@ -133,32 +143,74 @@ class WAPEngine:
         self._cost = torch.zeros(2, dtype=torch.float64, device=self.device)   # [CE cost, L2 cost]
         self.step_count = 0
         self.dropout_seed = 1234
-        # CUDA-graph replay of forward+backward per (shapes, dropout, precision): removes the launch gaps between the ~1700 kernels of a step
-        self.use_graphs = False
-        self.max_graphs = 16
-        self._graphs: Dict[tuple, tuple] = {}
+        # CUDA-graph replay of forward+backward per (shapes, dropout, precision): removes the launch gaps between the ~1700 kernels
+        # of a step.  A shape is captured the SECOND time it is seen (the reference's area-bucketed batches rarely repeat a shape:
+        # capturing each one once would only add capture cost), LRU-evicted beyond max_graphs.  All graphs share the engine's
+        # role-keyed workspaces; growing a workspace invalidates every captured graph (they hold raw pointers).
+        self.use_graphs = bool(use_graphs)
+        self.max_graphs = 8
+        self._graphs: "collections.OrderedDict[tuple, list]" = collections.OrderedDict()
+        self._graph_seen: Dict[tuple, int] = {}
         self._seed_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.replayed_launches = 0
         self.world_size = 1
+        self.rank = 0
         self.launches_last_step = 0
+        self.set_conv_precision(precision)
+
+    @property
+    def L(self):
+        """The C ABI with this engine's handle bound to the calling thread (wap_make_current)."""
+        self._lib.wap_make_current(self._h)
+        return self._lib
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                self._lib.wap_destroy(self._h)
+                self._h = None
+        except Exception:       # interpreter shutdown
+            pass
 
     # ------------------------------------------------------------------ precision
     def set_conv_precision(self, mode: str) -> None:
-        """'fp32' (FFMA), 'tf32' (tcgen05 single pass, 10-bit mantissa products) or 'tf32x3'
-        (error-compensated 3xTF32 on tcgen05: fp32-grade accuracy) for the dense-block / transition
-        convolutions (forward and data gradients).  Library-global."""
-        _lib.check(self.L.wap_set_conv_precision({"fp32": 0, "tf32": 1, "tf32x3": 2}[mode]), "wap_set_conv_precision")
+        """'fp32' (FFMA), 'tf32' (tcgen05 single pass, 10-bit mantissa products), 'tf32x3' (error-compensated 3xTF32 on
+        tcgen05: fp32-grade accuracy, the default) or 'bf16' (bf16 storage + tcgen05 kind::f16, the speed mode of BASELINE
+        configs[2]) for the dense-block / transition convolutions.  Per engine (handle)."""
+        _lib.check(self.L.wap_set_conv_precision(self.PRECISIONS[mode]), "wap_set_conv_precision")
 
     def conv_precision(self) -> str:
-        return ["fp32", "tf32", "tf32x3"][self.L.wap_get_conv_precision()]
+        return ["fp32", "tf32", "tf32x3", "bf16"][self.L.wap_get_conv_precision()]
 
     # ------------------------------------------------------------------ helpers
     def _buf(self, key: tuple, n: int, dtype=torch.float32) -> torch.Tensor:
+        """Workspace by ROLE ('enc', 'dec', 'ann', ...), grown to the largest size seen (10 % head-room): the area-bucketed
+        batches of the reference give almost every step its own (B,H,W,T), so per-shape buffers would never be reused."""
         t = self._ws.get(key)
         if t is None or t.numel() < n:
-            t = torch.empty(max(int(n), 4), dtype=dtype, device=self.device)
+            if t is not None:
+                self._graphs.clear()          # captured graphs hold raw pointers into the buffer being replaced
+                del self._ws[key], t
+            t = torch.empty(max(int(n * 1.1), 4), dtype=dtype, device=self.device)
             self._ws[key] = t
         return t
+
+    @staticmethod
+    def _check_tokens(y) -> None:
+        """Token ids index the embedding / logit tables on the device (S:340-341, S:368): reject ids outside [0, 111) while
+        they are still on the host (the reference fails in tf.one_hot / the dictionary assert S:490).  -1 (zero embedding,
+        S:381-384) is only legal for get_word."""
+        if isinstance(y, torch.Tensor):
+            if y.is_cuda or y.numel() == 0:
+                return
+            lo, hi = int(y.min()), int(y.max())
+        else:
+            a = np.asarray(y)
+            if a.size == 0:
+                return
+            lo, hi = int(a.min()), int(a.max())
+        if lo < 0 or hi >= VOCAB:
+            raise ValueError(f"token id out of range [0, {VOCAB}): min {lo}, max {hi}")
 
     def annotation_hw(self, H: int, W: int):
         h, w = C.c_int(), C.c_int()
@@ -183,7 +235,7 @@ class WAPEngine:
         x = self._dev(x, torch.float32)
         B, H, W = x.shape[0], x.shape[1], x.shape[2]
         h, w = self.annotation_hw(H, W)
-        ws = self._buf(("enc", B, H, W, bool(training)), self.L.wap_encoder_workspace_floats(B, H, W, int(training)))
+        ws = self._buf(("enc",), self.L.wap_encoder_workspace_floats(B, H, W, int(training)))
         ann = torch.empty((B, h, w, ANNOT_C), dtype=torch.float32, device=self.device)
         sd = self.dropout_seed if seed is None else seed
         self.L.wap_set_dropout_seed_source(None)
@@ -201,7 +253,7 @@ class WAPEngine:
         watch = torch.empty((B, h, w, DIM_ATT), dtype=torch.float32, device=self.device)
         h0 = torch.empty((B, DIM_DEC), dtype=torch.float32, device=self.device)
         qf = torch.empty((121, DIM_ATT), dtype=torch.float32, device=self.device)
-        scratch = self._buf(("mean", B), B * ANNOT_C)
+        scratch = self._buf(("mean",), B * ANNOT_C)
         _lib.check(self.L.wap_attn_precompute(_stream(), _p(self.P.flat), _p(ann), _p(a_mask), B, h, w, _p(watch), _p(h0), _p(qf),
                                               _p(scratch)), "wap_attn_precompute")
         return watch, h0, qf
@@ -210,7 +262,7 @@ class WAPEngine:
         """S:590 (unmasked mean)."""
         B, h, w, _ = anno.shape
         h0 = torch.empty((B, DIM_DEC), dtype=torch.float32, device=self.device)
-        scratch = self._buf(("mean", B), B * ANNOT_C)
+        scratch = self._buf(("mean",), B * ANNOT_C)
         _lib.check(self.L.wap_attn_precompute(_stream(), _p(self.P.flat), _p(anno), None, B, h, w, None, _p(h0), None, _p(scratch)),
                    "wap_attn_precompute")
         return h0
@@ -228,7 +280,7 @@ class WAPEngine:
         word = torch.empty((k,), dtype=torch.int32, device=self.device)
         h_new = torch.empty((k, DIM_DEC), dtype=torch.float32, device=self.device)
         ap_new = torch.empty((k, h, w), dtype=torch.float32, device=self.device)
-        ws = self._buf(("step", k, h, w), self.L.wap_decoder_step_workspace_floats(k, h, w))
+        ws = self._buf(("step",), self.L.wap_decoder_step_workspace_floats(k, h, w))
         _lib.check(self.L.wap_decoder_step(_stream(), _p(self.P.flat), _p(annotation), _p(watch), _p(qf), shared, k, h, w, _p(y),
                                            _p(h_pre), _p(alpha_past_pre), _p(probs), _p(word), _p(h_new), _p(ap_new), _p(ws)),
                    "wap_decoder_step")
@@ -243,7 +295,7 @@ class WAPEngine:
         am = self._dev(a_mask, torch.float32) if a_mask is not None else None
         ctx = torch.empty((B, ANNOT_C), dtype=torch.float32, device=self.device)
         alpha = torch.empty((B, h, w), dtype=torch.float32, device=self.device); ap_new = torch.empty_like(alpha)
-        ws = self._buf(("step", B, h, w), self.L.wap_decoder_step_workspace_floats(B, h, w))
+        ws = self._buf(("step",), self.L.wap_decoder_step_workspace_floats(B, h, w))
         _lib.check(self.L.wap_get_context(_stream(), _p(self.P.flat), _p(annotation4ctx), _p(watch), _p(qf), _p(am), B, h, w, _p(h_t_1), _p(ap),
                                           _p(ctx), _p(alpha), _p(ap_new), _p(ws)), "wap_get_context")
         return ctx, alpha, ap_new
@@ -262,15 +314,18 @@ class WAPEngine:
         h_new = torch.empty((B, DIM_DEC), dtype=torch.float32, device=self.device)
         ctx = torch.empty((B, ANNOT_C), dtype=torch.float32, device=self.device)
         alpha = torch.empty((B, h, w), dtype=torch.float32, device=self.device); ap_new = torch.empty_like(alpha)
-        ws = self._buf(("step", B, h, w), self.L.wap_decoder_step_workspace_floats(B, h, w))
+        ws = self._buf(("step",), self.L.wap_decoder_step_workspace_floats(B, h, w))
         _lib.check(self.L.wap_one_time_step(_stream(), _p(self.P.flat), _p(ann), _p(watch), _p(qf), _p(am), _p(ym), B, h, w, _p(emb_y), _p(h_prev),
                                             _p(ap), _p(h_new), _p(ctx), _p(alpha), _p(ap_new), _p(ws)), "wap_one_time_step")
         return h_new, ctx, alpha, ap_new, ann, a_mask
 
     # ------------------------------------------------------------------ checkpoint (the reference has none that fires: SURVEY 5)
-    def save(self, path: str) -> None:
-        """.npz keyed by the TF variable names (+ '__opt__/accum/<name>', '__opt__/accum_update/<name>', '__step__')."""
+    def save(self, path: str, schedule: Optional[dict] = None) -> None:
+        """.npz keyed by the TF variable names (+ '__opt__/accum/<name>', '__opt__/accum_update/<name>', '__step__',
+        and '__sched__/<key>' for the training-loop schedule: lrate, halfLrFlag, bad_counter, history_errs, epoch, uidx)."""
         out = dict(self.P.state_dict())
+        for k, v in (schedule or {}).items():
+            out["__sched__/" + k] = np.asarray(v)
         for k, v in self.P.unpack(self.accum).items():
             out["__opt__/accum/" + k] = v
         for k, v in self.P.unpack(self.accum_update).items():
@@ -278,7 +333,8 @@ class WAPEngine:
         out["__step__"] = np.array(self.step_count)
         np.savez(path, **out)
 
-    def load(self, path: str) -> None:
+    def load(self, path: str) -> dict:
+        """Restores parameters, moving statistics, Adadelta slots and the step counter; returns the saved schedule dict."""
         z = np.load(path)
         self.P.load({k: z[k] for k in self.P.names()})
         acc = {k[len("__opt__/accum/"):]: z[k] for k in z.files if k.startswith("__opt__/accum/")}
@@ -287,6 +343,7 @@ class WAPEngine:
             self.P.pack_into(self.accum, acc); self.P.pack_into(self.accum_update, accu)
         if "__step__" in z.files:
             self.step_count = int(z["__step__"])
+        return {k[len("__sched__/"):]: z[k] for k in z.files if k.startswith("__sched__/")}
 
     def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8, persistent: Optional[bool] = None,
                       ignore_eol: bool = False):
@@ -302,12 +359,12 @@ class WAPEngine:
             steps_dev = torch.zeros((1,), dtype=torch.int32, device=self.device)
             for b0 in range(0, B, 16):
                 nb = min(16, B - b0)
-                ws = self._buf(("greedy_p", nb, h, w), self.L.wap_greedy_persistent_workspace_floats(nb, h, w))
+                ws = self._buf(("greedy_p",), self.L.wap_greedy_persistent_workspace_floats(nb, h, w))
                 _lib.check(self.L.wap_greedy_decode_persistent(_stream(), _p(self.P.flat), _p(annotation[b0:b0 + nb]), nb, h, w, maxlen,
                                                                int(ignore_eol), _p(tokens[b0:b0 + nb]), _p(lengths[b0:b0 + nb]), _p(ws), _p(steps_dev)),
                            "wap_greedy_decode_persistent")
             return tokens, lengths, steps_dev
-        ws = self._buf(("greedy", B, h, w), self.L.wap_greedy_workspace_floats(B, h, w))
+        ws = self._buf(("greedy",), self.L.wap_greedy_workspace_floats(B, h, w))
         steps = C.c_int(0)
         _lib.check(self.L.wap_greedy_decode(_stream(), _p(self.P.flat), _p(annotation), B, h, w, maxlen, check_every, _p(tokens),
                                             _p(lengths), _p(ws), C.byref(steps)), "wap_greedy_decode")
@@ -360,9 +417,10 @@ class WAPEngine:
     def get_cost(self, annotation, y, a_mask, y_mask, dropout: bool = False, seed: Optional[int] = None) -> torch.Tensor:
         """WAP.get_cost (S:337-375): returns the CE cost (device float64 scalar, no L2 term)."""
         B, h, w, _ = annotation.shape
+        self._check_tokens(y)
         y = self._dev(y, torch.int32); y_mask = self._dev(y_mask, torch.float32)
         T = y.shape[0]
-        ws = self._buf(("dec", B, h, w, T), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
+        ws = self._buf(("dec",), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
         sd = self.dropout_seed if seed is None else seed
         self.L.wap_set_dropout_seed_source(None)
         _lib.check(self.L.wap_decoder_train_forward(_stream(), _p(self.P.flat), _p(annotation), _p(a_mask), _p(y), _p(y_mask), B, h, w, T,
@@ -374,13 +432,20 @@ class WAPEngine:
         """Forward + backward of cost (no L2 term, no update): fills self.grads; returns device cost.
         With self.use_graphs the launch sequence is captured once per (shapes, dropout, precision) into a CUDA graph and
         replayed afterwards; the dropout seed then travels through device memory (wap_set_dropout_seed_source)."""
-        sd = (self.dropout_seed + 7919 * self.step_count) if seed is None else seed
-        if not self.use_graphs:
-            self.L.wap_set_dropout_seed_source(None)
-            return self._forward_backward(self._dev(x, torch.float32), self._dev(y, torch.int32), self._dev(x_mask, torch.float32),
-                                          self._dev(y_mask, torch.float32), dropout, sd)
+        sd = (self.dropout_seed + 7919 * self.step_count + 104729 * self.rank) if seed is None else seed
+        self._check_tokens(y)
         key = (tuple(x.shape), tuple(y.shape), bool(dropout), self.L.wap_get_conv_precision())
-        ent = self._graphs.get(key)
+        ent = self._graphs.get(key) if self.use_graphs else None
+        if ent is None:
+            seen = self._graph_seen.get(key, 0) + 1
+            if self.use_graphs:
+                if len(self._graph_seen) > 4096:
+                    self._graph_seen.clear()
+                self._graph_seen[key] = seen
+            if not self.use_graphs or seen < 2:
+                self.L.wap_set_dropout_seed_source(None)
+                return self._forward_backward(self._dev(x, torch.float32), self._dev(y, torch.int32), self._dev(x_mask, torch.float32),
+                                              self._dev(y_mask, torch.float32), dropout, sd)
         fresh = ent is None
         if fresh:
             mk = lambda a, dt: torch.empty(tuple(a.shape), dtype=dt, device=self.device)     # noqa: E731
@@ -391,18 +456,20 @@ class WAPEngine:
         self._seed_dev.fill_(int(np.array(sd & 0xFFFFFFFF, dtype=np.uint32).astype(np.int32)))
         self.L.wap_set_dropout_seed_source(_p(self._seed_dev))
         if not fresh:
+            self._graphs.move_to_end(key)
             ent[0].replay()
             self.replayed_launches += ent[5]
             return self._cost[0]
         self._forward_backward(sx, sy, sxm, sym, dropout, sd)          # this step, eagerly (also sizes every workspace)
         torch.cuda.current_stream().synchronize()
-        n0 = self.L.wap_launch_count()
+        n0 = self._lib.wap_launch_count()
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):                                       # capture only: nothing runs, self.grads/_cost keep this step's values
+        # thread_local: a prefetch thread's pin_memory() / event queries must not invalidate the capture in progress
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):    # capture only: nothing runs, self.grads/_cost keep this step's values
             self._forward_backward(sx, sy, sxm, sym, dropout, sd)
-        ent[0], ent[5] = g, int(self.L.wap_launch_count() - n0)
-        if len(self._graphs) >= self.max_graphs:
-            self._graphs.pop(next(iter(self._graphs)))
+        ent[0], ent[5] = g, int(self._lib.wap_launch_count() - n0)
+        while len(self._graphs) >= self.max_graphs:
+            self._graphs.popitem(last=False)                            # least recently used
         self._graphs[key] = ent
         return self._cost[0]
 
@@ -412,11 +479,12 @@ class WAPEngine:
         sd_c = C.c_uint32(sd & 0xFFFFFFFF)
         h, w = self.annotation_hw(H, W)
         st = _stream()
-        a_mask = self.mask_subsample(x_mask)
-        ews = self._buf(("enc", B, H, W, True), self.L.wap_encoder_workspace_floats(B, H, W, 1))
-        dws = self._buf(("dec", B, h, w, T), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
-        ann = self._buf(("ann", B, h, w), B * h * w * ANNOT_C)
-        d_ann = self._buf(("dann", B, h, w), B * h * w * ANNOT_C)
+        a_mask = self._buf(("amask",), B * h * w)
+        _lib.check(self.L.wap_mask_subsample(st, _p(x_mask), B, H, W, _p(a_mask)), "wap_mask_subsample")
+        ews = self._buf(("enc",), self.L.wap_encoder_workspace_floats(B, H, W, 1))
+        dws = self._buf(("dec",), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
+        ann = self._buf(("ann",), B * h * w * ANNOT_C)
+        d_ann = self._buf(("dann",), B * h * w * ANNOT_C)
         self.grads.zero_()
         _lib.check(self.L.wap_encoder_forward(st, _p(self.P.flat), _p(self.P.moving), _p(x), B, H, W, 1, int(dropout), sd_c, _p(ann), _p(ews)),
                    "wap_encoder_forward")
@@ -426,9 +494,31 @@ class WAPEngine:
                                              int(dropout), sd_c, _p(d_ann), _p(ews), _p(dws)), "wap_train_backward")
         return self._cost[0]
 
+    def upload(self, pb):
+        """GPU half of data.py prepare_data (DATA:100-122) for a `data.PackedBatch`: ONE H2D copy of the packed host buffer,
+        then wap_prepare_batch writes x [B,H,W,1] (/255, zero padding) and x_mask; y / y_mask are views of the uploaded
+        buffer.  Returns device (x, x_mask, y int32 [T,B], y_mask [T,B]) valid until the next upload()."""
+        src = pb.buf if isinstance(pb.buf, torch.Tensor) else torch.as_tensor(pb.buf)
+        dev = self._buf(("packed",), (pb.nbytes + 3) // 4 + 4).view(torch.uint8)[: pb.nbytes]
+        dev.copy_(src, non_blocking=True)
+        B, H, W, T = pb.B, pb.H, pb.W, pb.T
+        x = self._buf(("x",), B * H * W)[: B * H * W].view(B, H, W, 1)
+        xm = self._buf(("xm",), B * H * W)[: B * H * W].view(B, H, W)
+        base = dev.data_ptr()
+        _lib.check(self.L.wap_prepare_batch(_stream(), C.c_void_p(base + pb.off_pix), C.c_void_p(base), C.c_void_p(base + pb.off_hw), B, H, W,
+                                            _p(x), _p(xm)), "wap_prepare_batch")
+        y = dev[pb.off_y: pb.off_ym].view(torch.int32).view(T, B)
+        ym = dev[pb.off_ym: pb.off_ym + 4 * T * B].view(torch.float32).view(T, B)
+        return x, xm, y, ym
+
+    def train_step_packed(self, pb, lr: float = 1.0, dropout: bool = True, seed: Optional[int] = None) -> torch.Tensor:
+        """train_step on a `data.PackedBatch` (raw uint8 images + captions in one pinned host buffer)."""
+        x, xm, y, ym = self.upload(pb)
+        return self.train_step(x, y, xm, ym, lr=lr, dropout=dropout, seed=seed)
+
     def launch_count(self) -> int:
         """Kernels launched by the library so far, including those replayed from captured graphs."""
-        return int(self.L.wap_launch_count()) + self.replayed_launches
+        return int(self._lib.wap_launch_count()) + self.replayed_launches
 
     def apply_update(self, lr: float) -> torch.Tensor:
         """L2 (S:594-598) + Adadelta (S:602-607) on the flat buffers; returns device L2 cost."""
