@@ -122,26 +122,29 @@ def host_cores():
     return n
 
 
-def best_cpu_threads(x, xm):
+def best_cpu_threads(x, xm, y, ym):
     """The CPU arm must not be handicapped by oversubscription (round 1: 4.7 images/s on 16 threads, 2.9 on 96): time one
-    oracle encoder forward of the workload at a few thread counts and keep the fastest."""
+    full oracle training step on a 2-image, 11-step slice of the workload at a few thread counts and keep the fastest."""
+    import numpy as np
     import torch
     from oracle import wap_oracle as O
     cores = host_cores()
-    cands = sorted({c for c in (8, 16, 24, 32, 48, 64, cores) if c <= cores}) or [cores]
-    P = O.to_torch(O.init_params(0), torch.float32)
-    xt, xmt = torch.as_tensor(x[:2], dtype=torch.float32), torch.as_tensor(xm[:2], dtype=torch.float32)
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores}) or [cores]
+    P = O.init_params(0)
+    names = O.trainable_names(P)
+    z = {n: np.zeros(P[n].shape, np.float32) for n in names}
+    xs, xms, ys, yms = x[:2], xm[:2], y[:11, :2], ym[:11, :2]
     best, best_t, table = cands[0], 1e30, {}
     for c in cands:
         torch.set_num_threads(c)
-        with torch.no_grad():
-            O.dense_net(P, xt, xmt, True)
-            t0 = time.perf_counter(); O.dense_net(P, xt, xmt, True); dt = time.perf_counter() - t0
-        table[c] = round(dt, 4)
+        t0 = time.perf_counter()
+        O.train_step(P, z, z, xs, xms, ys, yms, 1.0, None, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+        table[c] = round(dt, 3)
         if dt < best_t:
             best, best_t = c, dt
     torch.set_num_threads(best)
-    log(f"cpu thread calibration (s per 2-image encoder forward): {table} -> {best} threads")
+    log(f"cpu thread calibration (s per 2-image training step): {table} -> {best} threads")
     return best, cores
 
 
@@ -153,7 +156,7 @@ def cpu_oracle_images_per_s(B, steps, warmup, budget_s=90.0):
     import torch
     from oracle import wap_oracle as O
     _, _, (x, xm, y, ym) = make_workload(2, B)
-    threads, cores = best_cpu_threads(x, xm)
+    threads, cores = best_cpu_threads(x, xm, y, ym)
     P = O.init_params(0)
     names = O.trainable_names(P)
     acc = {n: np.zeros(P[n].shape, np.float32) for n in names}
