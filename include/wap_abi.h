@@ -121,6 +121,16 @@ int wap_greedy_decode_persistent(void* stream, const float* params, const float*
                                  int maxlen, int ignore_eol, int32_t* tokens, int32_t* lengths, float* workspace,
                                  int32_t* steps_run_dev);
 
+/* ---- WAP.get_sample(k, maxlen, stochastic=False) (S:442-542) + the length-normalised pick of the validation loop
+ * (S:671-672) for ONE image, annotation [1,h,w,684], as one persistent cooperative kernel: the k live hypotheses are the rows of
+ * the step (shared annotation, S:463), the candidate ranking / hypothesis bookkeeping (S:485-533) runs on the device.  No host
+ * synchronisation and no device->host traffic inside the token loop.  k <= 16, maxlen <= 128, h*w <= 2048.
+ * tokens [k,maxlen], lengths [k], scores [k] (accumulated -log p): the samples - finished hypotheses in order of completion,
+ * then the rows still alive; meta [4] = {number of samples, index of argmin(score/len), steps executed, live rows at the end}.
+ * workspace: wap_greedy_persistent_workspace_floats(k, h, w). */
+int wap_beam_decode_persistent(void* stream, const float* params, const float* annotation, int h, int w, int k, int maxlen,
+                               int32_t* tokens, int32_t* lengths, float* scores, int32_t* meta, float* workspace);
+
 /* ---- WAP.get_cost (S:337-375) forward over the whole caption (tf.scan of Parser.one_time_step,
  *      S:246-308) and its gradient.  y int32 [T,B], y_mask [T,B], a_mask [B,h,w].
  *      cost (device double) = mean_B sum_T mask*CE  (no L2 term; see wap_adadelta_l2_step).
@@ -178,6 +188,11 @@ int wap_tc_available(void);
  * activations and weights, tcgen05 kind::f16, fp32 accumulation and statistics; BASELINE configs[2]).  Per handle. */
 int wap_set_conv_precision(int mode);
 int wap_get_conv_precision(void);
+/* test support: gates[pixel, c] = (batch-norm output of conv layer k > 0) for the training-mode forward whose raw conv outputs and
+ * batch statistics are still in `encoder_workspace` (B, H, W as passed to wap_encoder_forward), evaluated with the very expression
+ * of the forward kernels.  [B*h_k*w_k, Cout_k] bytes (stem: [B*Hs*Ws, 48] before the max-pool).  The gradient tests hand the gates to
+ * the fp64 oracle so that elements within fp32 rounding of the ReLU kink are gated identically on both sides. */
+int wap_debug_bn_gates(void* stream, const float* params, const float* encoder_workspace, int B, int H, int W, int k, uint8_t* gates);
 /* debugging aid: bit mask of the conv classes allowed on the tensor-core path (default all) */
 int wap_debug_set_tc_mask(int mask);
 /* debugging aid: during wap_encoder_backward copy [d a1 | d y2 (ld 32) | d y1] of the dense level whose 1x1 conv index is `layer` into buf */

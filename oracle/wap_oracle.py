@@ -242,8 +242,11 @@ def _dropout(x, key: str, drop: DropFn):
 # --------------------------------------------------------------------------------------
 # Watcher  (S:73-132)
 # --------------------------------------------------------------------------------------
-def dense_net(P, x, mask_x, training: bool, drop: DropFn = None, taps: Optional[dict] = None):
-    """x [B,H,W,1], mask_x [B,H,W] → annotation [B,h,w,684], mask [B,h,w], new moving stats."""
+def dense_net(P, x, mask_x, training: bool, drop: DropFn = None, taps: Optional[dict] = None, gates: Optional[dict] = None):
+    """x [B,H,W,1], mask_x [B,H,W] → annotation [B,h,w,684], mask [B,h,w], new moving stats.
+    gates (test support): {conv index k: 0/1 tensor of the BN-output shape}; where given, ReLU(y) is evaluated as y * gate, i.e.
+    with gating decisions supplied from outside (the fp32 engine's), so that elements within fp32 rounding of the kink do not make
+    a cross-precision gradient comparison ill-posed.  The forward value changes by at most the magnitude of such elements."""
     new_moving: Dict[str, torch.Tensor] = {}
 
     def cbr(x, k, stride=1, do_drop=True):
@@ -256,8 +259,10 @@ def dense_net(P, x, mask_x, training: bool, drop: DropFn = None, taps: Optional[
         new_moving[bn_name(k, "moving_variance")] = nv
         if taps is not None:
             taps[f"minpre{k}"] = float(y.detach().abs().min())     # distance of the closest element to the ReLU kink
-            taps[f"minpre_c{k}"] = y.detach().abs().amin(dim=(0, 1, 2))   # ... per output channel
-        y = torch.relu(y)
+        if gates is not None and k in gates:
+            y = y * gates[k].to(y.dtype).reshape(y.shape)
+        else:
+            y = torch.relu(y)
         if do_drop and training:
             y = _dropout(y, f"drop{k}", drop)
         return y
@@ -453,12 +458,12 @@ def beam_decode(P, annotation, k: int = 10, maxlen: int = 100):
 # one training step: cost (+L2), gradients, Adadelta, BN moving-stat update  (S:592-607, S:640)
 # --------------------------------------------------------------------------------------
 def train_step(P_np, acc, acc_delta, x, x_mask, y, y_mask, lr: float, drop: DropFn = None,
-               dtype=torch.float64, inv_world: float = 1.0, extra_grads=None):
-    """Returns cost (incl. L2), grads (numpy, incl. L2 term), new params, new acc, new acc_delta."""
+               dtype=torch.float64, inv_world: float = 1.0, extra_grads=None, gates=None):
+    """Returns cost (incl. L2), grads (numpy, incl. L2 term), new params, new acc, new acc_delta.  gates: see dense_net."""
     P = to_torch(P_np, dtype, requires_grad=True)
     xt, xm = torch.as_tensor(x, dtype=dtype), torch.as_tensor(x_mask, dtype=dtype)
     yt, ym = torch.as_tensor(y, dtype=torch.int64), torch.as_tensor(y_mask, dtype=dtype)
-    ann, am, new_moving = dense_net(P, xt, xm, True, drop)
+    ann, am, new_moving = dense_net(P, xt, xm, True, drop, gates=gates)
     cost = get_cost(P, ann, yt, am, ym, drop) + l2_penalty(P)
     names = trainable_names(P)
     grads = torch.autograd.grad(cost, [P[n] for n in names])
@@ -582,23 +587,6 @@ def hash_drop_fn(seed: int) -> Callable:
         n = int(np.prod(shape))
         return torch.as_tensor(drop_hash_keep(seed & 0xFFFFFFFF, site, n).reshape(shape))
     return fn
-
-
-def kink_channels(P_np, x, x_mask, drop: DropFn = None, tau: float = 5e-5) -> Dict[int, List[int]]:
-    """{conv index k: [output channels c]} whose BN output has an element within `tau` of the ReLU kink in a training-mode
-    forward.  fp32 arithmetic (1e-5 ... 2e-5 away from fp64 deep in the 99-layer net) may gate such an element differently
-    from fp64 - legitimately - and the flip moves the gradients of conv2d_k/kernel[..., c] and batch_normalization_k/{gamma,beta}[c]
-    by O(1/pixels-per-channel); nothing else moves measurably.  The gradient tests exclude exactly those entries."""
-    P = to_torch(P_np, torch.float64)
-    taps: dict = {}
-    dense_net(P, torch.as_tensor(x, dtype=torch.float64), torch.as_tensor(x_mask, dtype=torch.float64), True, drop, taps=taps)
-    out: Dict[int, List[int]] = {}
-    for key, v in taps.items():
-        if key.startswith("minpre_c"):
-            cs = torch.nonzero(v < tau).flatten().tolist()
-            if cs:
-                out[int(key[len("minpre_c"):])] = cs
-    return out
 
 
 def relu_kink_margin(P_np, x, x_mask, drop: DropFn = None) -> float:

@@ -43,26 +43,42 @@ def t64(a):
     return torch.as_tensor(np.asarray(a), dtype=torch.float64)
 
 
-def kink_excluded(P, x, xm, drop_seed=None, tau=5e-5, max_channels=64):
-    """Entries of the parameter gradients that a legitimate fp32-vs-fp64 ReLU gating difference may move (see
-    oracle.kink_channels): {variable name: channel indices along its LAST axis}.  Everything else must match the oracle on
-    THIS batch - there is no retry on another batch.  A cap on the number of excluded channels (of ~6000 BN channels) keeps
-    the exclusion from hiding a broad failure."""
-    drop = O.hash_drop_fn(drop_seed) if drop_seed is not None else None
-    kc = O.kink_channels(P, x, xm, drop, tau)
-    n = sum(len(v) for v in kc.values())
-    assert n <= max_channels, f"{n} near-kink channels: choose another seed for this test batch"
-    ex = {}
-    for k, cs in kc.items():
-        for name in (O.conv_name(k), O.bn_name(k, "gamma"), O.bn_name(k, "beta")):
-            ex[name] = np.asarray(cs, dtype=np.int64)
-    return ex
+def engine_gates(eng, B, H, W, params=None):
+    """{conv index k: uint8 [pixels, Cout_k]} ReLU gates of the training-mode forward the engine has just run (forward_backward /
+    train_step on a (B,H,W) batch), exported by wap_debug_bn_gates from the raw conv outputs + statistics in its workspace.
+    params: flat parameter tensor that forward used (default: the engine's current one; pass a pre-step clone after train_step,
+    whose optimiser update has already changed gamma / beta)."""
+    params = eng.P.flat if params is None else params
+    import ctypes as C
+    from wap_b200 import _lib
+    ws = eng._ws[("enc",)]
+    out = {}
+    geom = []
+    hs, ws_ = -(-H // 2), -(-W // 2)
+    geom.append(B * hs * ws_)
+    h, w = -(-hs // 2), -(-ws_ // 2)
+    for b in range(3):
+        geom.append(B * h * w); h, w = -(-h // 2), -(-w // 2)
+    plan = O.encoder_plan()
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for k in range(99):
+        cout = int(eng.P.views[O.conv_name(k)].shape[-1])
+        block = 0 if k == 0 else (0 if k <= 33 else 1 if k <= 66 else 2)
+        npix = geom[0] if k == 0 else geom[1 + block]
+        g = torch.empty(npix * cout, dtype=torch.uint8, device=eng.device)
+        _lib.check(eng.L.wap_debug_bn_gates(st, C.c_void_p(params.data_ptr()), C.c_void_p(ws.data_ptr()), B, H, W, k, C.c_void_p(g.data_ptr())),
+                   "wap_debug_bn_gates")
+        out[k] = g.cpu()
+    del plan
+    return out
 
 
-def grad_errors(names, got_by_name, ref_by_name, excluded, tol=2e-3):
+def grad_errors(names, got_by_name, ref_by_name, excluded=None, tol=2e-3):
     """Per-tensor max-norm error (tensors whose gradient is tiny relative to the largest one are compared on the global
-    scale: they are dominated by fp32 rounding of large cancelling sums), with the near-kink channels masked out.
+    scale: they are dominated by fp32 rounding of large cancelling sums).  Nothing is masked (excluded stays empty: the oracle
+    is evaluated with the engine's ReLU gates, helpers.engine_gates).
     Returns (failures, worst_err, worst_name, median_rel_l2, n_masked_entries)."""
+    excluded = excluded or {}
     gmax = max(float(np.max(np.abs(ref_by_name[n]))) for n in names)
     fails, worst, worst_name, l2s, masked = [], 0.0, None, [], 0
     for n in names:
@@ -81,11 +97,11 @@ def grad_errors(names, got_by_name, ref_by_name, excluded, tol=2e-3):
     return fails, worst, worst_name, float(np.median(l2s)), masked
 
 
-def oracle_grads(P, x, xm, y, ym, drop_seed=None, dtype=torch.float64):
-    """(cost, {name: d cost / d name}) of the oracle's training-mode forward (no L2 term)."""
+def oracle_grads(P, x, xm, y, ym, drop_seed=None, dtype=torch.float64, gates=None):
+    """(cost, {name: d cost / d name}, names) of the oracle's training-mode forward (no L2 term); gates: see engine_gates."""
     Pt = O.to_torch(P, dtype, requires_grad=True)
     dfn = O.hash_drop_fn(drop_seed) if drop_seed is not None else None
-    ann, am, _ = O.dense_net(Pt, torch.as_tensor(x, dtype=dtype), torch.as_tensor(xm, dtype=dtype), True, dfn)
+    ann, am, _ = O.dense_net(Pt, torch.as_tensor(x, dtype=dtype), torch.as_tensor(xm, dtype=dtype), True, dfn, gates=gates)
     cost = O.get_cost(Pt, ann, torch.as_tensor(y), am, torch.as_tensor(ym, dtype=dtype), dfn)
     names = O.trainable_names(Pt)
     grads = torch.autograd.grad(cost, [Pt[n] for n in names])

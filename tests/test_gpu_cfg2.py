@@ -15,7 +15,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (O, REL_TOL, ROOT, engine_grads, engine_with, grad_errors, kink_excluded, make_batch, oracle_grads, rel_err, t64)
+from helpers import (O, REL_TOL, ROOT, engine_gates, engine_grads, engine_with, grad_errors, make_batch, oracle_grads, rel_err, t64)
 
 pytestmark = pytest.mark.gpu
 
@@ -42,20 +42,20 @@ def test_cfg2_train_step_exactly_as_benchmarked(report):
     x, xm, y, ym = make_batch(2, CFG2["B"], CFG2["H"], CFG2["W"], CFG2["cap"])
     assert x.shape == (8, 128, 512, 1) and y.shape == (41, 8)
     seed = 31337
-    ex = kink_excluded(P, x, xm, seed)
-    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed)
     costs = []
     for i in range(3):                                     # 1: stream launches, 2: eager + capture, 3: REPLAY
         costs.append(float(eng.forward_backward(x, y, xm, ym, dropout=True, seed=seed)))
     assert len(eng._graphs) == 1 and eng.replayed_launches > 1000, (len(eng._graphs), eng.replayed_launches)
+    gates = engine_gates(eng, 8, 128, 512)                 # ReLU gates of the replayed forward (see helpers.engine_gates)
+    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed, gates=gates)
     e = abs(costs[2] - ref_cost) / abs(ref_cost)
     report.add("cfg2", "cost_replayed", e, REL_TOL, extra=dict(got=costs, ref=ref_cost))
-    fails, worst, worst_name, med, masked = grad_errors(names, engine_grads(eng), G, ex)
+    fails, worst, worst_name, med, masked = grad_errors(names, engine_grads(eng), G)
     report.add("cfg2", "grad_worst_maxnorm", worst, 2e-3, extra=dict(name=worst_name, masked_entries=masked))
     report.add("cfg2", "grad_median_rel_l2", med, 1e-3)
     # annotation of the same training-mode forward (saved in the engine's role-keyed buffer)
     Pt = O.to_torch(P)
-    ann_ref, am_ref, _ = O.dense_net(Pt, t64(x), t64(xm), True, O.hash_drop_fn(seed))
+    ann_ref, am_ref, _ = O.dense_net(Pt, t64(x), t64(xm), True, O.hash_drop_fn(seed), gates=gates)
     ann = eng._ws[("ann",)][: 8 * 8 * 32 * 684].view(8, 8, 32, 684).cpu().numpy()
     ea = rel_err(ann, ann_ref.numpy())
     report.add("cfg2", "annotation_training_mode", ea, REL_TOL)
@@ -63,13 +63,15 @@ def test_cfg2_train_step_exactly_as_benchmarked(report):
     # ---- one full optimiser step through the replay path (train_step), from zero Adadelta state
     zeros = {n: np.zeros(P[n].shape, np.float64) for n in names}
     eng.P.load(P)                                          # moving statistics were updated by the three forwards above
+    flat0 = eng.P.flat.clone()
     cost = float(eng.train_step(x, y, xm, ym, lr=1.0, dropout=True, seed=seed))
-    ref_cost2, G2, P2, acc2, accd2 = O.train_step(P, zeros, dict(zeros), x, xm, y, ym, 1.0, O.hash_drop_fn(seed))
+    gates = engine_gates(eng, 8, 128, 512, params=flat0)
+    ref_cost2, G2, P2, acc2, accd2 = O.train_step(P, zeros, dict(zeros), x, xm, y, ym, 1.0, O.hash_drop_fn(seed), gates=gates)
     e2 = abs(cost - ref_cost2) / abs(ref_cost2)
     report.add("cfg2", "cost_incl_l2_train_step", e2, REL_TOL, extra=dict(got=cost, ref=ref_cost2))
     l2set = set(O.l2_names(P))
     g_l2 = {n: engine_grads(eng)[n].astype(np.float64) + (2 * O.L2_COEF * P[n].astype(np.float64) if n in l2set else 0.0) for n in names}
-    f2, worst2, wn2, _, _ = grad_errors(names, g_l2, G2, ex)
+    f2, worst2, wn2, _, _ = grad_errors(names, g_l2, G2)
     report.add("cfg2", "gradient_incl_l2_vs_oracle", worst2, 2e-3, extra=dict(name=wn2))
     form = _adadelta_formula(P, g_l2, zeros, zeros)
     sd = eng.P.state_dict(); acc_e = eng.P.unpack(eng.accum); accd_e = eng.P.unpack(eng.accum_update)
@@ -121,11 +123,10 @@ def test_ragged_crohme_style_batch(report, precision):
     P = O.lively_params(6)
     eng = engine_with(P, precision=precision)
     seed = 99
-    ex = kink_excluded(P, x, xm, seed)
     cost = float(eng.forward_backward(x, y, xm, ym, dropout=True, seed=seed))
-    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed)
+    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, seed, gates=engine_gates(eng, x.shape[0], x.shape[1], x.shape[2]))
     e = abs(cost - ref_cost) / abs(ref_cost)
-    fails, worst, wn, med, masked = grad_errors(names, engine_grads(eng), G, ex)
+    fails, worst, wn, med, masked = grad_errors(names, engine_grads(eng), G)
     report.add("ragged", f"cost_{precision}", e, REL_TOL)
     report.add("ragged", f"grad_worst_maxnorm_{precision}", worst, 2e-3, extra=dict(name=wn, masked_entries=masked))
     assert e <= REL_TOL and not fails and med <= 1e-3, (e, fails[:10], med)
@@ -142,19 +143,19 @@ def test_dp_update_equals_mean_of_replica_gradients(report):
     eng = engine_with(P)
     eng.world_size = 2
     eng.forward_backward(A[0], A[2], A[1], A[3], dropout=True, seed=sa); ga = eng.grads.clone()
+    gates_a = engine_gates(eng, 2, A[0].shape[1], A[0].shape[2])
     eng.P.load(P)                                          # replica B starts from the same weights / moving statistics
     eng.forward_backward(Bt[0], Bt[2], Bt[1], Bt[3], dropout=True, seed=sb)
+    gates_b = engine_gates(eng, 2, Bt[0].shape[1], Bt[0].shape[2])
     eng.grads += ga                                        # what the NCCL all-reduce(sum) leaves on every rank
     eng.apply_update(1.0)
     zeros = {n: np.zeros(P[n].shape, np.float64) for n in names}
-    _, Gb, _, _, _ = O.train_step(P, zeros, dict(zeros), Bt[0], Bt[1], Bt[2], Bt[3], 1.0, O.hash_drop_fn(sb))
-    _, G, P2, acc2, accd2 = O.train_step(P, zeros, dict(zeros), A[0], A[1], A[2], A[3], 1.0, O.hash_drop_fn(sa), extra_grads=Gb, inv_world=0.5)
-    ex = kink_excluded(P, A[0], A[1], sa)
-    for k, v in kink_excluded(P, Bt[0], Bt[1], sb).items():
-        ex[k] = np.union1d(ex[k], v) if k in ex else v
+    _, Gb, _, _, _ = O.train_step(P, zeros, dict(zeros), Bt[0], Bt[1], Bt[2], Bt[3], 1.0, O.hash_drop_fn(sb), gates=gates_b)
+    _, G, P2, acc2, accd2 = O.train_step(P, zeros, dict(zeros), A[0], A[1], A[2], A[3], 1.0, O.hash_drop_fn(sa), extra_grads=Gb, inv_world=0.5,
+                                         gates=gates_a)
     l2set = set(O.l2_names(P))
     g_mean = {n: 0.5 * engine_grads(eng)[n].astype(np.float64) + (2 * O.L2_COEF * P[n].astype(np.float64) if n in l2set else 0.0) for n in names}
-    fails, worst, wn, med, _ = grad_errors(names, g_mean, G, ex)
+    fails, worst, wn, med, _ = grad_errors(names, g_mean, G)
     report.add("dp", "mean_gradient_vs_oracle", worst, 2e-3, extra=dict(name=wn))
     form = _adadelta_formula(P, g_mean, zeros, zeros)
     sd = eng.P.state_dict()
@@ -162,8 +163,7 @@ def test_dp_update_equals_mean_of_replica_gradients(report):
     report.add("dp", "update_vs_formula_on_mean_gradient", worst_p, 1e-3)
     # accumulators of the oracle's update (a = 0.05 g^2) against the engine's
     acc_e = eng.P.unpack(eng.accum)
-    wa = max(rel_err(np.delete(acc_e[n], ex[n], axis=-1) if n in ex else acc_e[n], np.delete(acc2[n], ex[n], axis=-1) if n in ex else acc2[n])
-             for n in names)
+    wa = max(rel_err(acc_e[n], acc2[n]) for n in names)
     report.add("dp", "adadelta_accum_vs_oracle", wa, 4e-3)
     assert not fails and worst_p <= 1e-3 and wa <= 4e-3, (fails[:10], worst_p, wa)
 
@@ -214,12 +214,14 @@ def test_two_engines_with_different_precision_coexist(report):
     assert a.conv_precision() == "fp32" and b.conv_precision() == "tf32x3" and a.conv_precision() == "fp32"
     a.L.wap_set_pdl(0)
     assert b.L.wap_get_pdl() == 1 and a.L.wap_get_pdl() == 0
-    ref_cost, G, names = oracle_grads(P, x, xm, y, ym, 5)
-    ex = kink_excluded(P, x, xm, 5)
+    ref = {}
     for rep in range(3):                                   # interleaved; b captures a graph on its second step and replays on the third
         ca = float(a.forward_backward(x, y, xm, ym, True, 5)); cb = float(b.forward_backward(x, y, xm, ym, True, 5))
         for nm, eng, c in (("fp32", a, ca), ("tf32x3", b, cb)):
-            fails, worst, wn, med, _ = grad_errors(names, engine_grads(eng), G, ex)
+            if nm not in ref:                              # each engine's own ReLU gates (same inputs every repetition)
+                ref[nm] = oracle_grads(P, x, xm, y, ym, 5, gates=engine_gates(eng, 2, x.shape[1], x.shape[2]))
+            ref_cost, G, names = ref[nm]
+            fails, worst, wn, med, _ = grad_errors(names, engine_grads(eng), G)
             report.add("handles", f"{nm}_rep{rep}", worst, 2e-3, extra=dict(name=wn))
             assert abs(c - ref_cost) <= REL_TOL * abs(ref_cost) and not fails, (nm, rep, c, ref_cost, fails[:5])
     assert len(b._graphs) == 1 and len(a._graphs) == 0

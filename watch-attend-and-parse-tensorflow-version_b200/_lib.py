@@ -45,6 +45,7 @@ SIGNATURES = {
     "wap_greedy_decode": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _ip]),
     "wap_greedy_persistent_workspace_floats": (_i64, [_i, _i, _i]),
     "wap_greedy_decode_persistent": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "wap_beam_decode_persistent": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp]),
     "wap_decoder_train_workspace_floats": (_i64, [_i, _i, _i, _i]),
     "wap_decoder_train_forward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
     "wap_decoder_train_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _u32, _vp, _vp]),
@@ -61,6 +62,7 @@ SIGNATURES = {
     "wap_tc_available": (_i, []),
     "wap_set_conv_precision": (_i, [_i]),
     "wap_get_conv_precision": (_i, []),
+    "wap_debug_bn_gates": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "wap_debug_set_tc_mask": (_i, [_i]),
     "wap_debug_capture": (_i, [_i, _vp]),
     "wap_debug_wgrad": (_i, [_vp, _i]),

@@ -90,12 +90,15 @@ int decoder_join(cudaStream_t st);
 size_t greedy_persist_ws_floats(int Bn, int L);
 int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
                              int* tokens, int* lengths, float* wsp, int* steps_run_dev);
+int beam_decode_persistent(cudaStream_t st, const float* params, const float* ann, int h, int w, int k, int maxlen,
+                           int* tokens, int* lengths, float* scores, int* meta, float* wsp);
 int adadelta_l2_step(cudaStream_t st, float* p, const float* g, float* acc, float* accu, size_t n, size_t n_decay,
                      float lr, float rho, float eps, float l2, float gscale, double* l2_cost);
 void set_conv_precision(int mode);
 int get_conv_precision();
 extern int g_tc_debug_mask;
 extern int g_dbg_layer; extern float* g_dbg_buf;
+int debug_bn_gates(cudaStream_t st, const float* params, const float* wsp, int B, int H, int W, int k, uint8_t* out);
 int mask_subsample(cudaStream_t st, const float* xm, int B, int H, int W, int h, int w, float* am);
 int dropout_mask(cudaStream_t st, uint32_t seed, uint32_t site, size_t n, float* mask);
 int prepare_batch(cudaStream_t st, const uint8_t* pix, const long long* offs, const int* hw, int B, int H, int W, float* x, float* xm);
@@ -232,6 +235,12 @@ int wap_greedy_decode_persistent(void* stream, const float* params, const float*
   return greedy_decode_persistent(ST(stream), params, annotation, Bn, h, w, maxlen, ignore_eol, tokens, lengths, workspace, steps_run_dev);
 }
 
+int wap_beam_decode_persistent(void* stream, const float* params, const float* annotation, int h, int w, int k, int maxlen,
+                               int32_t* tokens, int32_t* lengths, float* scores, int32_t* meta, float* workspace) {
+  WAP_REQUIRE(params && annotation && tokens && lengths && scores && meta && workspace, "wap_beam_decode_persistent: bad arguments");
+  return beam_decode_persistent(ST(stream), params, annotation, h, w, k, maxlen, tokens, lengths, scores, meta, workspace);
+}
+
 int64_t wap_decoder_train_workspace_floats(int B, int h, int w, int T) { return (int64_t)decoder_train_ws_floats(B, h * w, T); }
 int wap_decoder_train_forward(void* stream, const float* params, const float* annotation, const float* a_mask,
                               const int32_t* y, const float* y_mask, int B, int h, int w, int T,
@@ -286,6 +295,10 @@ int wap_set_conv_precision(int mode) {
   return 0;
 }
 int wap_get_conv_precision(void) { return get_conv_precision(); }
+int wap_debug_bn_gates(void* stream, const float* params, const float* encoder_workspace, int B, int H, int W, int k, uint8_t* gates) {
+  WAP_REQUIRE(params && encoder_workspace && gates, "wap_debug_bn_gates: bad arguments");
+  return debug_bn_gates(ST(stream), params, encoder_workspace, B, H, W, k, gates);
+}
 int wap_debug_set_tc_mask(int mask) { g_tc_debug_mask = mask; return 0; }
 int wap_debug_capture(int layer, float* buf) { g_dbg_layer = layer; g_dbg_buf = buf; return 0; }
 int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,

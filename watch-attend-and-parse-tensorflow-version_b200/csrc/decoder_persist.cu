@@ -17,6 +17,14 @@
 //      the termination decision are known CTA-locally: no host round trip, no extra barrier.
 // Per step the only HBM/L2 traffic is the annotation (context), the hoisted watch tensor, alpha_past and
 // a few KB of vectors: the algorithmic bytes of SURVEY 8d minus the (now on-chip) weights.
+//
+// BEAM MODE (beam_k > 0) = WAP.get_sample(stochastic=False) (model-single-GPU.py:442-542) + the length-normalised pick
+// (:671-672) for ONE image: the rows are the live hypotheses, all sharing the image's annotation / watch tensor (the reference
+// tiles ctx0, S:463).  Phase G then does the reference's numpy bookkeeping on the device, redundantly in every CTA so that all of
+// them agree on the next rows without another barrier: cand = hyp_scores - log softmax (S:485-487), the (k - dead_k) smallest of the
+// live_k x 111 candidates in rank order (S:488-494), finished hypotheses (word 0) moved to the sample list, the others become
+// the new rows (S:500-519).  States are not copied: row i reads h / alpha_past of its parent through `src` from ping-pong buffers.
+// Token lists are back-pointers in shared memory; CTA 0 unrolls them once at the end.  The host sees nothing until then.
 #include <algorithm>
 
 #include "decoder.cuh"
@@ -34,6 +42,10 @@ constexpr int kMaxL = 2048;               // annotation positions per image supp
 constexpr int kPadMax = 6144;             // floats of the zero-bordered alpha_past image (H+10)*(W+10) staged in smem
 constexpr int kCG = 4, kCGW = kNA / kCG;  // coverage channel groups: 4 x 128
 constexpr int kMinCtas = 128;             // ownership scheme needs >= 128 CTAs (<= 2 hidden units per CTA)
+constexpr int kBeamMaxLen = 128;          // beam mode: token positions kept as back-pointers in shared memory
+// beam bookkeeping in shared memory (floats): src[16] | hs[16] | cand cost [16][16] | cand idx [16][16] | sel cost[16] | sel idx[16] |
+// dead {t, parent, score}[16] x 3 | counters[8] | back-pointers + words (2 x kBeamMaxLen x 16 bytes)
+constexpr int kBeamSmemFloats = 16 + 16 + 256 + 256 + 16 + 16 + 48 + 8 + 2 * kBeamMaxLen * 16 / 4;
 
 struct DecOff {   // offsets (floats) into the flat parameter buffer
   int U_f_b, W_a, W_a_b, V_a, V_a_b, W_yz_yr, b_yz_yr, U_hz_hr, W_yh, b_yh, U_rh, U_hz_hr_nl, b_hz_hr_nl, W_c_z_r, U_rh_nl,
@@ -44,12 +56,14 @@ struct PersistArgs {
   const float* params; const float* ann; const float* watch; const float* qf; const float* h0;
   DecOff o;
   int Bn, H, W, L, maxlen, ignore_eol;
+  int beam_k;       // 0: greedy over Bn images; > 0: beam search over ONE image with beam_k (= Bn) hypothesis rows
+  float* bscore; int* bmeta;   // beam outputs: scores [beam_k]; {n_samples, best, steps_run, live_at_end}
   // global scratch (cross-CTA); read with ld.global.cg after a barrier
   float* hbuf;      // [2][Bn][256]  ping-pong hidden state
   float* pre_h;     // [Bn][256]
   float* SP;        // [Bn][512]
   float* E;         // [2][Bn][L]    energies (ping-pong: the buffer of step t+1 is zeroed during step t)
-  float* ap;        // [Bn][L]       alpha_past
+  float* ap;        // [2][Bn][L]    alpha_past (ping-pong: step t reads buffer (t-1)&1 through `src`, writes buffer t&1)
   float* ctx;       // [Bn][684]
   float* MO;        // [Bn][128]
   float* LOg;       // [2][Bn][112]  output logits accumulated by the pair owners (ping-pong, pre-set to bo)
@@ -96,7 +110,8 @@ __device__ __forceinline__ void stage_cg(float* dst, const float* src, int n4) {
 }
 
 constexpr int kSmemFloats = kCovTaps * kCGW + 2 * 6 * kN + 2 * 3 * kN + 2 * 3 * kD + 4 * kN + 2 * kMw + 2 * kD + 2 * kN +
-                            kMaxB * kD + 2 * kMaxB * 8 + kPadMax + 64 + 16 * 64 + kMaxB * 112 + 2 * kMaxB + 2 * 112;
+                            kMaxB * kD + 2 * kMaxB * 8 + kPadMax + 64 + 16 * 64 + kMaxB * 112 + 2 * kMaxB + 2 * 112 +
+                            kBeamSmemFloats;
 
 __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const PersistArgs a) {
   extern __shared__ __align__(16) float sm[];
@@ -121,6 +136,18 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
   int* sy = reinterpret_cast<int*>(LO + kMaxB * 112);   // [kMaxB] current token
   int* sfin = sy + kMaxB;                           // [kMaxB] finished flag
   float* WoR = reinterpret_cast<float*>(sfin + kMaxB);  // [112] row `cta` of Wo (the maxout unit this CTA owns)
+  int* src = reinterpret_cast<int*>(WoR + 2 * 112);     // [16] row whose h / alpha_past of the previous step this row continues
+  float* hs = reinterpret_cast<float*>(src + 16);       // [16] hyp_scores (S:454)
+  float* cc = hs + 16;                                  // [16][16] per-row candidate costs (ascending)
+  int* ci = reinterpret_cast<int*>(cc + 256);           // [16][16] their flat indices row * 111 + word
+  float* selc = reinterpret_cast<float*>(ci + 256);     // [16] merged candidates in rank order
+  int* seli = reinterpret_cast<int*>(selc + 16);
+  int* dead_t = seli + 16; int* dead_p = dead_t + 16; float* dead_s = reinterpret_cast<float*>(dead_p + 16);   // finished hypotheses (S:505-508)
+  int* cnt = reinterpret_cast<int*>(dead_s + 16);       // [0] live_k, [1] dead_k
+  unsigned char* bk = reinterpret_cast<unsigned char*>(cnt + 8);   // [kBeamMaxLen][16] parent row of live row i at step t
+  unsigned char* wd = bk + kBeamMaxLen * 16;                         // [kBeamMaxLen][16] its word
+  const bool beam = a.beam_k > 0;
+  const int shared_img = beam ? 1 : 0;                  // every row reads image 0's annotation / watch / h0
 
   // ---- ownership
   const int nu = (cta < kN) ? 1 + ((cta + nC) < kN ? 1 : 0) : 0;       // hidden units cta, cta+nC
@@ -163,9 +190,10 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
       load_col(WPh + c * kN, P + o.Wh, kN, kMw, 2 * cta + c);
     }
   if (has_pair) for (int j = tid; j < kVocab; j += kPT) WoR[j] = __ldg(P + o.Wo + (size_t)cta * kVocab + j);
-  if (tid < kMaxB) { sy[tid] = -1; sfin[tid] = 0; }
-  // zero the step-0 energy buffer and alpha_past (ownerless: strided over the grid)
-  for (int i = cta * kPT + tid; i < npos; i += nC * kPT) { a.E[i] = 0.f; a.ap[i] = 0.f; }
+  if (tid < kMaxB) { sy[tid] = -1; sfin[tid] = 0; src[tid] = beam ? 0 : tid; hs[tid] = 0.f; }
+  if (tid == 0) { cnt[0] = beam ? 1 : Bn; cnt[1] = 0; }
+  // zero the step-0 energy buffer and both alpha_past buffers (ownerless: strided over the grid)
+  for (int i = cta * kPT + tid; i < npos; i += nC * kPT) { a.E[i] = 0.f; a.ap[i] = 0.f; a.ap[npos + i] = 0.f; }
   for (int i = cta * kPT + tid; i < Bn * 112; i += nC * kPT) a.LOg[i] = (i % 112) < kVocab ? __ldg(P + o.bo + (i % 112)) : 0.f;
   unsigned epoch = 0;
   long long tprev = clock64();
@@ -182,21 +210,24 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     float* Enext = a.E + (size_t)((t + 1) & 1) * npos;
     float* LOcur = a.LOg + (size_t)(t & 1) * Bn * 112;
     float* LOnext = a.LOg + (size_t)((t + 1) & 1) * Bn * 112;
+    const float* ap_old = a.ap + (size_t)((t + 1) & 1) * npos;     // written by step t-1 (zero for t = 0)
+    float* ap_new = a.ap + (size_t)(t & 1) * npos;
+    const int rows = cnt[0];                                       // live rows of this step (greedy: Bn)
     // ====================================================== A: GRU-1 for the owned units
     {   // X[b] = [emb(y_b) | h_prev[b]]   (independent 128-bit loads)
       float4* X4 = reinterpret_cast<float4*>(X);
 #pragma unroll 4
-      for (int i = tid; i < Bn * (2 * kN / 4); i += kPT) {
+      for (int i = tid; i < rows * (2 * kN / 4); i += kPT) {
         const int b = i / (2 * kN / 4), k4 = i - b * (2 * kN / 4);
         float4 v = make4(0.f);
         if (k4 < kMw / 4) { const int y = sy[b]; if (y >= 0) v = ldg4(P + o.embed + (size_t)y * kMw + k4 * 4); }
-        else v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)b * kN) + (k4 - kMw / 4));
+        else v = __ldcg(reinterpret_cast<const float4*>(hprev + (size_t)((t == 0 && shared_img) ? 0 : src[b]) * kN) + (k4 - kMw / 4));
         X4[i] = v;
       }
     }
     __syncthreads();
-    for (int p = warp; p < nu * Bn; p += kPT / 32) {
-      const int s = p / Bn, b = p - s * Bn, j = unit[s];
+    for (int p = warp; p < nu * rows; p += kPT / 32) {
+      const int s = p / rows, b = p - s * rows, j = unit[s];
       const float* xe = X + b * 2 * kN; const float* xh = xe + kMw;
       const float* w = WA + s * 6 * kN;
       const float er = warp_dot(xe, w, kMw, lane), ez = warp_dot(xe, w + kN, kMw, lane), eh = warp_dot(xe, w + 2 * kN, kMw, lane);
@@ -215,10 +246,10 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     grid_barrier(a.barrier, nC, epoch);
     mark(0);
     // ====================================================== B: pre_h-side products
-    stage_cg(X, a.pre_h, Bn * kN / 4);
+    stage_cg(X, a.pre_h, rows * kN / 4);
     __syncthreads();
-    for (int p = warp; p < (nu * 3 + nsp) * Bn; p += kPT / 32) {
-      const int q = p / Bn, b = p - q * Bn;
+    for (int p = warp; p < (nu * 3 + nsp) * rows; p += kPT / 32) {
+      const int q = p / rows, b = p - q * rows;
       const float* x = X + b * kN;
       if (q < nu * 3) {
         const int s = q / 3, c = q - s * 3, j = unit[s];
@@ -246,12 +277,13 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
       int bcur = -1;
       for (int pbase = pos0; pbase < pos1;) {
         const int b = pbase / L;
+        if (b >= rows) break;                          // rows beyond the live hypotheses: nothing to do (uniform per CTA)
         const int pend = min(min(pos1, (b + 1) * L), pbase + 64);
         __syncthreads();
         if (b != bcur) {                               // stage alpha_past of image b with a zero border of 5
           for (int i = tid; i < PH * PW; i += kPT) {
             const int yy = i / PW - kCovK / 2, xx = i % PW - kCovK / 2;
-            sal[i] = ((unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W) ? __ldcg(a.ap + (size_t)b * L + yy * a.W + xx) : 0.f;
+            sal[i] = ((unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W) ? __ldcg(ap_old + (size_t)src[b] * L + yy * a.W + xx) : 0.f;
           }
           __syncthreads();
           bcur = b;
@@ -284,7 +316,7 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
 #pragma unroll
           for (int i = 0; i < 8; ++i) {                // all watch rows in flight before any of them is used
             const int pos = min(pbase + warp * 8 + i, pend - 1);
-            w4[i] = ldg4(a.watch + (size_t)pos * kNA + c0);
+            w4[i] = ldg4(a.watch + (size_t)(shared_img ? pos - b * L : pos) * kNA + c0);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -302,7 +334,7 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     grid_barrier(a.barrier, nC, epoch);
     mark(2);
     // ====================================================== D: softmax over L, alpha_past update, context chunk
-    if (db < Bn) {
+    if (db < rows) {
       const float vab = __ldg(P + o.V_a_b);
       float mx = -INFINITY;
       for (int l = tid; l < L; l += kPT) { const float e = __ldcg(Ecur + (size_t)db * L + l) + vab; sal[l] = e; mx = fmaxf(mx, e); }
@@ -314,7 +346,7 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
       for (int l = tid; l < L; l += kPT) {
         const float al = sal[l] * inv;
         sal[l] = al;
-        if (dchunk == 0) a.ap[(size_t)db * L + l] += al;       // next read is phase C of step t+1 (4 barriers away)
+        if (dchunk == 0) ap_new[(size_t)db * L + l] = __ldcg(ap_old + (size_t)src[db] * L + l) + al;   // next read: phase C of step t+1
       }
       __syncthreads();
       const int cq = tid & 15, lg = tid >> 4;                  // 16 float4 columns x 16 position groups
@@ -322,7 +354,7 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
         const int c4 = dchunk * c4_per + q0 + cq;
         float4 acc = make4(0.f);
         if (q0 + cq < c4_per && c4 < kD / 4) {
-          const float* base = a.ann + (size_t)db * L * kD + c4 * 4;
+          const float* base = a.ann + (size_t)(shared_img ? 0 : db) * L * kD + c4 * 4;
           for (int l = lg; l < L; l += 16) {
             const float4 v = ldg4(base + (size_t)l * kD);
             const float al = sal[l];
@@ -346,10 +378,10 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     grid_barrier(a.barrier, nC, epoch);
     mark(3);
     // ====================================================== E: GRU-2 for the owned units + emb/ctx part of the logit pair
-    stage_cg(X, a.ctx, Bn * kD / 4);
+    stage_cg(X, a.ctx, rows * kD / 4);
     __syncthreads();
-    for (int p = warp; p < (nu + (has_pair ? 2 : 0)) * Bn; p += kPT / 32) {
-      const int q = p / Bn, b = p - q * Bn;
+    for (int p = warp; p < (nu + (has_pair ? 2 : 0)) * rows; p += kPT / 32) {
+      const int q = p / rows, b = p - q * rows;
       const float* xc = X + b * kD;
       if (q < nu) {
         const int s = q, j = unit[s];
@@ -376,16 +408,16 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     mark(4);
     // ====================================================== F: h part of the logit pair, maxout
     if (has_pair) {
-      stage_cg(X, hnew, Bn * kN / 4);
+      stage_cg(X, hnew, rows * kN / 4);
       __syncthreads();
-      for (int p = warp; p < 2 * Bn; p += kPT / 32) {
-        const int c = p / Bn, b = p - c * Bn;
+      for (int p = warp; p < 2 * rows; p += kPT / 32) {
+        const int c = p / rows, b = p - c * rows;
         const float v = warp_dot(X + b * kN, WPh + c * kN, kN, lane);
         if (lane == 0) own[(c * kMaxB + b) * 8 + 5] = v + own[(c * kMaxB + b) * 8 + 4];
       }
       __syncthreads();
       // maxout of the owned pair, then its rank-1 contribution MO[b,cta] * Wo[cta,:] to the output logits (RED.ADD)
-      for (int i = tid; i < Bn * kVocab; i += kPT) {
+      for (int i = tid; i < rows * kVocab; i += kPT) {
         const int b = i / kVocab, j = i - b * kVocab;
         const float m = fmaxf(own[(0 * kMaxB + b) * 8 + 5], own[(1 * kMaxB + b) * 8 + 5]);
         atomicAdd(LOcur + b * 112 + j, m * WoR[j]);
@@ -396,28 +428,134 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     // ====================================================== G: argmax + stop rule (redundant in every CTA; logits were accumulated in F)
     stage_cg(LO, LOcur, Bn * 112 / 4);
     __syncthreads();
-    for (int b = warp; b < Bn; b += kPT / 32) {
-      float mx = -INFINITY; int am = 0x7fffffff;
-      for (int j = lane; j < kVocab; j += 32) { const float v = LO[b * 112 + j]; if (v > mx) { mx = v; am = j; } }
+    if (!beam) {
+      for (int b = warp; b < Bn; b += kPT / 32) {
+        float mx = -INFINITY; int am = 0x7fffffff;
+        for (int j = lane; j < kVocab; j += 32) { const float v = LO[b * 112 + j]; if (v > mx) { mx = v; am = j; } }
 #pragma unroll
-      for (int off = 16; off > 0; off >>= 1) {
-        const float om = __shfl_xor_sync(0xffffffffu, mx, off);
-        const int oa = __shfl_xor_sync(0xffffffffu, am, off);
-        if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
-      }
-      if (lane == 0) {
-        if (!sfin[b]) {
-          if (cta == 0) a.tokens[(size_t)b * a.maxlen + t] = am;
-          if ((am == 0 && !a.ignore_eol) || t == a.maxlen - 1) { sfin[b] = 1; if (cta == 0) a.lengths[b] = t + 1; }
+        for (int off = 16; off > 0; off >>= 1) {
+          const float om = __shfl_xor_sync(0xffffffffu, mx, off);
+          const int oa = __shfl_xor_sync(0xffffffffu, am, off);
+          if (om > mx || (om == mx && oa < am)) { mx = om; am = oa; }
         }
-        sy[b] = am;
+        if (lane == 0) {
+          if (!sfin[b]) {
+            if (cta == 0) a.tokens[(size_t)b * a.maxlen + t] = am;
+            if ((am == 0 && !a.ignore_eol) || t == a.maxlen - 1) { sfin[b] = 1; if (cta == 0) a.lengths[b] = t + 1; }
+          }
+          sy[b] = am;
+        }
       }
+      __syncthreads();
+      mark(6);
+      int alive = 0;
+      for (int b = 0; b < Bn; ++b) alive += sfin[b] ? 0 : 1;
+      if (alive == 0) { ++t; break; }
+    } else {
+      // ---- beam bookkeeping of get_sample (S:485-533).  nr = k - dead_k candidates survive this step.
+      const int live = rows, dead = cnt[1], nr = a.beam_k - dead;
+      // (1) per live row: cost[j] = hyp_score + (logsumexp - logit[j]) = hyp_score - log softmax[j]; its nr smallest, ascending
+      for (int b = warp; b < live; b += kPT / 32) {
+        float v[4]; float mx = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const int j = lane + 32 * i; v[i] = j < kVocab ? LO[b * 112 + j] : -INFINITY; mx = fmaxf(mx, v[i]); }
+        mx = warp_max(mx);
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) sum += (lane + 32 * i < kVocab) ? expf(v[i] - mx) : 0.f;
+        sum = warp_sum(sum);
+        const float base = hs[b] + mx + logf(sum);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) v[i] = (lane + 32 * i < kVocab) ? base - v[i] : INFINITY;
+        for (int r = 0; r < nr; ++r) {
+          float m = v[0]; int mi = lane;
+#pragma unroll
+          for (int i = 1; i < 4; ++i) if (v[i] < m) { m = v[i]; mi = lane + 32 * i; }
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, m, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, mi, off);
+            if (om < m || (om == m && oi < mi)) { m = om; mi = oi; }
+          }
+          if ((mi & 31) == lane) {                                 // remove the winner from its owner's registers
+#pragma unroll
+            for (int i = 0; i < 4; ++i) if ((mi >> 5) == i) v[i] = INFINITY;
+          }
+          if (lane == 0) { cc[b * 16 + r] = m; ci[b * 16 + r] = b * kVocab + mi; }
+        }
+      }
+      __syncthreads();
+      // (2) merge the live x nr per-row winners: the nr smallest overall, in rank order (flat.argsort()[:k-dead_k], S:488-489)
+      if (warp == 0) {
+        float v[8]; int vi[8];
+        const int n = live * nr;                                   // <= 16 * 16
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int q = lane + 32 * i;
+          const bool ok = q < n;
+          const int b = ok ? q / nr : 0, r = ok ? q - b * nr : 0;
+          v[i] = ok ? cc[b * 16 + r] : INFINITY; vi[i] = ok ? ci[b * 16 + r] : 0x7fffffff;
+        }
+        for (int r = 0; r < nr; ++r) {
+          float m = v[0]; int mi = vi[0]; int slot = 0;
+#pragma unroll
+          for (int i = 1; i < 8; ++i) if (v[i] < m || (v[i] == m && vi[i] < mi)) { m = v[i]; mi = vi[i]; slot = i; }
+          float bm = m; int bi = mi;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, bm, off);
+            const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+            if (om < bm || (om == bm && oi < bi)) { bm = om; bi = oi; }
+          }
+          if (bi == mi && bm == m && mi != 0x7fffffff) {          // flat indices are unique: exactly one lane owns the winner
+#pragma unroll
+            for (int i = 0; i < 8; ++i) if (i == slot) { v[i] = INFINITY; vi[i] = 0x7fffffff; }
+          }
+          if (lane == 0) { selc[r] = bm; seli[r] = bi; }
+        }
+        __syncwarp();
+        // (3) split into finished / continuing hypotheses (S:500-519), one thread: <= 16 entries
+        if (lane == 0) {
+          int nl = 0, nd = dead;
+          int nsrc[16], nw[16]; float nsc[16];
+          for (int r = 0; r < nr; ++r) {
+            const int par = seli[r] / kVocab, word = seli[r] - par * kVocab;
+            if (word == 0) { dead_t[nd] = t; dead_p[nd] = par; dead_s[nd] = selc[r]; ++nd; }
+            else { nsrc[nl] = par; nw[nl] = word; nsc[nl] = selc[r]; ++nl; }
+          }
+          for (int i = 0; i < nl; ++i) {
+            src[i] = nsrc[i]; sy[i] = nw[i]; hs[i] = nsc[i];
+            if (t < kBeamMaxLen) { bk[t * 16 + i] = (unsigned char)nsrc[i]; wd[t * 16 + i] = (unsigned char)nw[i]; }
+          }
+          cnt[0] = nl; cnt[1] = nd;
+        }
+      }
+      __syncthreads();
+      mark(6);
+      if (cnt[0] < 1 || cnt[1] >= a.beam_k) { ++t; break; }        // S:521-524
+    }
+  }
+  if (beam && cta == 0) {
+    // ---- samples = finished hypotheses in order of death, then the rows still alive (S:535-540); unroll the back-pointers;
+    //      pick argmin(score / len) (S:671-672).  One thread per sample, then thread 0 picks.
+    __syncthreads();
+    const int nd = cnt[1], nl = cnt[0], ns = nd + nl, tl = t - 1;       // tl = last executed step
+    if (tid < ns) {
+      int len, row, tt;
+      int* out = a.tokens + (size_t)tid * a.maxlen;
+      if (tid < nd) { len = dead_t[tid] + 1; out[len - 1] = 0; row = dead_p[tid]; tt = dead_t[tid] - 1; }
+      else { len = tl + 1; row = tid - nd; tt = tl; }
+      for (; tt >= 0; --tt) { out[tt] = wd[tt * 16 + row]; row = bk[tt * 16 + row]; }
+      a.lengths[tid] = len;
+      a.bscore[tid] = tid < nd ? dead_s[tid] : hs[tid - nd];
+      cc[tid] = a.bscore[tid] / (float)len;
     }
     __syncthreads();
-    mark(6);
-    int alive = 0;
-    for (int b = 0; b < Bn; ++b) alive += sfin[b] ? 0 : 1;
-    if (alive == 0) { ++t; break; }
+    if (tid == 0) {
+      int best = 0;
+      for (int i = 1; i < ns; ++i) if (cc[i] < cc[best]) best = i;
+      a.bmeta[0] = ns; a.bmeta[1] = best; a.bmeta[2] = t; a.bmeta[3] = nl;
+    }
   }
   if (cta == 0 && tid == 0 && a.steps_run != nullptr) *a.steps_run = t;
   if (cta == 0 && tid == 0 && a.prof != nullptr)
@@ -429,19 +567,19 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
 size_t greedy_persist_ws_floats(int Bn, int L) {
   size_t o = 0;
   auto take = [&](size_t n) { o += (n + 3) & ~(size_t)3; };
-  take((size_t)2 * Bn * kN); take((size_t)Bn * kN); take((size_t)Bn * kNA); take((size_t)2 * Bn * L); take((size_t)Bn * L);
+  take((size_t)2 * Bn * kN); take((size_t)Bn * kN); take((size_t)Bn * kNA); take((size_t)2 * Bn * L); take((size_t)2 * Bn * L);
   take((size_t)Bn * kD); take((size_t)Bn * (kMw / 2)); take(8 * 160 + 24); take((size_t)2 * Bn * 112);
   take((size_t)Bn * L * kNA); take((size_t)kCovTaps * kNA); take((size_t)Bn * kN); take((size_t)Bn * kD); take(4);
   return o;
 }
 
-// Greedy decode of Bn <= 16 images in one persistent cooperative kernel (plus the hoisted precompute).
-// steps_run_dev: optional device int.  Never synchronises the host.
-int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
-                             int* tokens, int* lengths, float* wsp, int* steps_run_dev) {
+// Shared launcher.  beam_k == 0: greedy decode of Bn <= 16 images.  beam_k > 0: beam search over ONE image (ann [1,h,w,684]) with
+// beam_k hypothesis rows.  Plus the hoisted precompute.  Never synchronises the host.
+static int launch_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol, int beam_k,
+                             int* tokens, int* lengths, float* bscore, int* bmeta, float* wsp, int* steps_run_dev) {
   const int L = h * w;
   WAP_REQUIRE(Bn >= 1 && Bn <= kMaxB && L <= kMaxL && (h + 10) * (w + 10) <= kPadMax,
-              "greedy_decode_persistent: Bn=%d (<=%d), L=%d (<=%d), padded grid %d (<=%d)", Bn, kMaxB, L, kMaxL, (h + 10) * (w + 10), kPadMax);
+              "persistent decoder: rows=%d (<=%d), L=%d (<=%d), padded grid %d (<=%d)", Bn, kMaxB, L, kMaxL, (h + 10) * (w + 10), kPadMax);
   static int num_ctas = 0;
   const size_t smem = sizeof(float) * kSmemFloats;
   if (num_ctas == 0) {
@@ -456,12 +594,14 @@ int greedy_decode_persistent(cudaStream_t st, const float* params, const float* 
     num_ctas = std::min(160, (sms / kCG) * kCG);
     WAP_REQUIRE(num_ctas >= kMinCtas, "persistent decoder needs >= %d SMs (have %d)", kMinCtas, sms);
   }
+  const int nimg = beam_k > 0 ? 1 : Bn;             // images behind the rows
   size_t o = 0;
   auto take = [&](size_t n) { float* p = wsp + o; o += (n + 3) & ~(size_t)3; return p; };
   PersistArgs a;
   a.params = params; a.ann = ann; a.Bn = Bn; a.H = h; a.W = w; a.L = L; a.maxlen = maxlen; a.ignore_eol = ignore_eol;
+  a.beam_k = beam_k; a.bscore = bscore; a.bmeta = bmeta;
   a.hbuf = take((size_t)2 * Bn * kN); a.pre_h = take((size_t)Bn * kN); a.SP = take((size_t)Bn * kNA);
-  a.E = take((size_t)2 * Bn * L); a.ap = take((size_t)Bn * L); a.ctx = take((size_t)Bn * kD); a.MO = take((size_t)Bn * (kMw / 2));
+  a.E = take((size_t)2 * Bn * L); a.ap = take((size_t)2 * Bn * L); a.ctx = take((size_t)Bn * kD); a.MO = take((size_t)Bn * (kMw / 2));
   a.barrier = reinterpret_cast<unsigned*>(take(8 * 160 + 24));   // barrier counter (+ padding), then the profile words
   a.LOg = take((size_t)2 * Bn * 112);
   float* watch = take((size_t)Bn * L * kNA); float* qf = take((size_t)kCovTaps * kNA); float* h0 = take((size_t)Bn * kN);
@@ -475,13 +615,28 @@ int greedy_decode_persistent(cudaStream_t st, const float* params, const float* 
   d.U_rh = (int)P.U_rh; d.U_hz_hr_nl = (int)P.U_hz_hr_nl; d.b_hz_hr_nl = (int)P.b_hz_hr_nl; d.W_c_z_r = (int)P.W_c_z_r;
   d.U_rh_nl = (int)P.U_rh_nl; d.b_rh_nl = (int)P.b_rh_nl; d.W_c_h_nl = (int)P.W_c_h_nl; d.embed = (int)P.embed; d.Wc = (int)P.Wc;
   d.bc = (int)P.bc; d.Wh = (int)P.Wh; d.bh = (int)P.bh; d.Wy = (int)P.Wy; d.by = (int)P.by; d.Wo = (int)P.Wo; d.bo = (int)P.bo;
-  WAP_TRY(attn_precompute(st, params, ann, nullptr, Bn, h, w, watch, h0, qf, mean));     // hidden_state_0 is unmasked (S:590)
+  WAP_TRY(attn_precompute(st, params, ann, nullptr, nimg, h, w, watch, h0, qf, mean));     // hidden_state_0 is unmasked (S:590)
   WAP_CHECK(cudaMemsetAsync(a.barrier, 0, (8 * 160 + 24) * sizeof(unsigned), st));
   WAP_CHECK(cudaMemsetAsync(lengths, 0, sizeof(int) * Bn, st));
   void* args[] = {(void*)&a};
   WAP_CHECK(cudaLaunchCooperativeKernel((const void*)greedy_persistent_kernel, dim3(num_ctas), dim3(kPT), args, smem, st));
   ++g_launches;
   return 0;
+}
+
+int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
+                             int* tokens, int* lengths, float* wsp, int* steps_run_dev) {
+  return launch_persistent(st, params, ann, Bn, h, w, maxlen, ignore_eol, 0, tokens, lengths, nullptr, nullptr, wsp, steps_run_dev);
+}
+
+// WAP.get_sample(k, maxlen, stochastic=False) + the length-normalised pick, wholly on the device (see the file header).
+// tokens [k][maxlen], lengths [k], scores [k]: the samples (finished first, in order of death; then the live rows); meta [4] =
+// {number of samples, index of the picked one, steps executed, live rows at the end}.
+int beam_decode_persistent(cudaStream_t st, const float* params, const float* ann, int h, int w, int k, int maxlen,
+                           int* tokens, int* lengths, float* scores, int* meta, float* wsp) {
+  WAP_REQUIRE(k >= 1 && k <= kMaxB && maxlen >= 1 && maxlen <= kBeamMaxLen, "beam_decode_persistent: k=%d (1..%d), maxlen=%d (1..%d)", k, kMaxB, maxlen,
+              kBeamMaxLen);
+  return launch_persistent(st, params, ann, k, h, w, maxlen, 0, k, tokens, lengths, scores, meta, wsp, nullptr);
 }
 
 }  // namespace wap

@@ -454,6 +454,40 @@ static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, b
 }
 
 // =====================================================================================
+// test support: the ReLU gate (BN output > 0) of every element of conv layer k, evaluated with the SAME expression as the
+// forward / backward kernels (fmaf(raw, gamma*invstd, beta - mean*gamma*invstd)) from the raw outputs and statistics a
+// training-mode forward left in the workspace.  The gradient tests hand these gates to the fp64 oracle: an element within
+// fp32 rounding of the kink is then gated identically on both sides and the comparison is well posed for every element.
+// =====================================================================================
+__global__ void __launch_bounds__(256) bn_gate_kernel(const float* __restrict__ raw, const float* __restrict__ saved, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int C, size_t n, uint8_t* __restrict__ out) {
+  pdl_sync();
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const float sc = __ldg(gamma + c) * saved[kMaxBnC + c];
+    const float sh = __ldg(beta + c) - saved[c] * sc;
+    out[i] = fmaf(raw[i], sc, sh) > 0.f ? 1 : 0;
+  }
+}
+int debug_bn_gates(cudaStream_t st, const float* params, const float* wsp, int B, int H, int W, int k, uint8_t* out) {
+  WAP_REQUIRE(k >= 0 && k < kNumConv && get_conv_precision() != 3, "wap_debug_bn_gates: layer %d / precision mode not supported", k);
+  const ParamLayout& L = layout();
+  const EncGeom g = make_geom(B, H, W);
+  const EncWorkspace ws = make_enc_workspace(g, true);
+  const ConvLayer& c = L.conv[k];
+  const float* raw; size_t npix;
+  if (c.kind == kStem) { raw = wsp + ws.stem_raw; npix = (size_t)B * g.Hs * g.Ws; }
+  else if (c.kind == kC1) { raw = wsp + ws.y1[k]; npix = g.M[c.block]; }
+  else if (c.kind == kC3) { raw = wsp + ws.y2[k]; npix = g.M[c.block]; }
+  else { raw = wsp + ws.ytr[c.block]; npix = g.M[c.block]; }
+  const size_t n = npix * c.cout;
+  WAP_CHECK(launch_pdl(bn_gate_kernel, (unsigned)std::min<size_t>(cdivz(n, 256), 148 * 8), 256, 0, st, raw, wsp + ws.saved + (size_t)k * 2 * kMaxBnC,
+                       params + c.gamma, params + c.beta, c.cout, n, out));
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+// =====================================================================================
 // host orchestration
 // =====================================================================================
 static inline int ew_grid(size_t total_vec) {

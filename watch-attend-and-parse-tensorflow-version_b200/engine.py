@@ -370,10 +370,38 @@ class WAPEngine:
                                             _p(lengths), _p(ws), C.byref(steps)), "wap_greedy_decode")
         return tokens, lengths, steps.value
 
-    def get_sample(self, annotation: torch.Tensor, k: int = 10, maxlen: int = 100):
-        """Beam search of WAP.get_sample(stochastic=False) (S:442-542) + the length-normalised pick
-        (S:671-672) for ONE image [1,h,w,684].  The step runs on the GPU for all live hypotheses at
-        once (shared annotation); the k x 111 candidate bookkeeping follows the reference on the host."""
+    def beam_supported(self, h: int, w: int, k: int, maxlen: int) -> bool:
+        return h * w <= 2048 and (h + 10) * (w + 10) <= 6144 and 1 <= k <= 16 and 1 <= maxlen <= 128
+
+    def get_sample(self, annotation: torch.Tensor, k: int = 10, maxlen: int = 100, on_device: Optional[bool] = None):
+        """Beam search of WAP.get_sample(stochastic=False) (S:442-542) + the length-normalised pick (S:671-672) for ONE image
+        [1,h,w,684]: returns (picked token list, all samples, their scores).  Default: ONE persistent cooperative kernel runs the
+        whole search on the device (wap_beam_decode_persistent: live hypotheses = rows of the step, candidate ranking and hypothesis
+        bookkeeping in the kernel); the host reads the finished samples once.  Shapes beyond the kernel's shared-memory carve-up
+        (h*w > 2048) take the step-by-step kernels with the bookkeeping on the host."""
+        assert annotation.shape[0] == 1
+        _, h, w, _ = annotation.shape
+        if on_device is None:
+            on_device = self.beam_supported(h, w, k, maxlen)
+        if not on_device:
+            return self._get_sample_host(annotation, k, maxlen)
+        tokens = torch.zeros((k, maxlen), dtype=torch.int32, device=self.device)
+        lengths = torch.zeros((k,), dtype=torch.int32, device=self.device)
+        scores = torch.zeros((k,), dtype=torch.float32, device=self.device)
+        meta = torch.zeros((4,), dtype=torch.int32, device=self.device)
+        ws = self._buf(("greedy_p",), self.L.wap_greedy_persistent_workspace_floats(k, h, w))
+        _lib.check(self.L.wap_beam_decode_persistent(_stream(), _p(self.P.flat), _p(annotation), h, w, k, maxlen, _p(tokens), _p(lengths),
+                                                     _p(scores), _p(meta), _p(ws)), "wap_beam_decode_persistent")
+        m = meta.cpu().numpy()                                   # the ONE device->host synchronisation of the search
+        ns, best = int(m[0]), int(m[1])
+        tk, ln, sc = tokens[:ns].cpu().numpy(), lengths[:ns].cpu().numpy(), scores[:ns].cpu().numpy()
+        sample = [tk[i, : ln[i]].tolist() for i in range(ns)]
+        return sample[best], sample, [np.float32(v) for v in sc]
+
+    def _get_sample_host(self, annotation: torch.Tensor, k: int = 10, maxlen: int = 100):
+        """The same search with the k x 111 candidate bookkeeping on the host (numpy, as the reference does it) and one
+        wap_decoder_step + D2H of the probabilities per token: kept for annotation grids beyond the persistent kernel's limits
+        and as the cross-check of the device search."""
         assert annotation.shape[0] == 1
         watch, h0, qf = self.precompute(annotation)
         _, h, w, _ = annotation.shape
