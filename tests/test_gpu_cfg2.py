@@ -163,7 +163,8 @@ def test_dp_update_equals_mean_of_replica_gradients(report):
     report.add("dp", "update_vs_formula_on_mean_gradient", worst_p, 1e-3)
     # accumulators of the oracle's update (a = 0.05 g^2) against the engine's
     acc_e = eng.P.unpack(eng.accum)
-    wa = max(rel_err(acc_e[n], acc2[n]) for n in names)
+    gmax = max(float(np.max(np.abs(G[n]))) for n in names)    # tensors with tiny gradients are compared on the global scale, as in grad_errors
+    wa = max(float(np.max(np.abs(acc_e[n] - acc2[n]))) / max(float(np.max(np.abs(acc2[n]))), 0.05 * (1e-2 * gmax) ** 2) for n in names)
     report.add("dp", "adadelta_accum_vs_oracle", wa, 4e-3)
     assert not fails and worst_p <= 1e-3 and wa <= 4e-3, (fails[:10], worst_p, wa)
 
@@ -214,13 +215,12 @@ def test_two_engines_with_different_precision_coexist(report):
     assert a.conv_precision() == "fp32" and b.conv_precision() == "tf32x3" and a.conv_precision() == "fp32"
     a.L.wap_set_pdl(0)
     assert b.L.wap_get_pdl() == 1 and a.L.wap_get_pdl() == 0
-    ref = {}
     for rep in range(3):                                   # interleaved; b captures a graph on its second step and replays on the third
         ca = float(a.forward_backward(x, y, xm, ym, True, 5)); cb = float(b.forward_backward(x, y, xm, ym, True, 5))
         for nm, eng, c in (("fp32", a, ca), ("tf32x3", b, cb)):
-            if nm not in ref:                              # each engine's own ReLU gates (same inputs every repetition)
-                ref[nm] = oracle_grads(P, x, xm, y, ym, 5, gates=engine_gates(eng, 2, x.shape[1], x.shape[2]))
-            ref_cost, G, names = ref[nm]
+            # each run's own ReLU gates: two runs of the same step differ by the order of their atomic adds (~1e-7), enough to
+            # flip an element that sits on the kink (seen in round 2: one flip between repetitions moved one channel by 2e-2)
+            ref_cost, G, names = oracle_grads(P, x, xm, y, ym, 5, gates=engine_gates(eng, 2, x.shape[1], x.shape[2]))
             fails, worst, wn, med, _ = grad_errors(names, engine_grads(eng), G)
             report.add("handles", f"{nm}_rep{rep}", worst, 2e-3, extra=dict(name=wn))
             assert abs(c - ref_cost) <= REL_TOL * abs(ref_cost) and not fails, (nm, rep, c, ref_cost, fails[:5])

@@ -108,7 +108,7 @@ def test_encoder_inference(report, B, H, W, ragged):
     _check(report, tag, "mask", am.cpu().numpy(), ref_m.numpy(), 0.0, fails)
     # intermediate block buffers (diagnostics; same tolerance)
     lib = _lib(); L = lib.lib()
-    ws = eng._ws[("enc", B, H, W, False)]
+    ws = eng._ws[("enc",)]
     hw = [(taps["block0"].shape[1], taps["block0"].shape[2]), (taps["block1"].shape[1], taps["block1"].shape[2])]
     for b in range(2):
         off = L.wap_encoder_workspace_offset(B, H, W, 0, 1, b)

@@ -2,6 +2,7 @@
 #include "tc_gemm.cuh"
 
 #include <cudaTypedefs.h>
+#include <cuda_bf16.h>
 
 #include <algorithm>
 
@@ -94,6 +95,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// D[tmem] (+)= A[smem desc] * B[smem desc]   (kind::f16 with bf16 operands, fp32 accumulate; K = 16 per instruction)
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
 // D[tmem] (+)= A[tmem: lane = row, column = k] * B[smem desc]   (A operand staged in tensor memory)
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -157,6 +166,18 @@ __host__ __device__ constexpr uint32_t make_idesc_tf32(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
 
+// instruction descriptor: D=f32, A=B=bf16 (kind::f16 format 1), both K-major, M=128, N=BN
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+// 8 fp32 -> 8 bf16 (round to nearest even) as one 16-byte store
+__device__ __forceinline__ void store_bf16x8(void* dst, const float* v) {
+  uint32_t w[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
+  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ------------------------------------------------------------------------------------ kernel
 struct TcShape {
   int M, N, K;            // logical GEMM (K = total reduction length; for conv: 9*C)
@@ -202,13 +223,17 @@ __device__ __forceinline__ float tf32_rna_dev(float x) {
 template <bool X3> struct TcThreads { static constexpr int kN = kTcThreads; };
 // IM2COL: 0 plain 2-D A operand; 1 3x3 SAME im2col (9 taps in K); 2 "row tile" 3x3 (3 vertical taps in K, the horizontal
 // taps are 3 x 24 output columns whose results the epilogue adds with a +-1 pixel shift, see tc_conv3x3_rowtile)
-template <int BN, int IM2COL, bool X3>
+// BF16: operands are bf16 in global / shared memory (a stage row is still one 128-byte swizzle span = 64 elements), the MMAs are
+// kind::f16 with K = 16 (again four per stage), accumulation fp32 in TMEM; epi.out_bf16 stores the result as bf16.
+template <int BN, int IM2COL, bool X3, bool BF16>
 __global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
   pdl_sync();
+  static_assert(!(X3 && BF16), "3xTF32 splitting applies to fp32 operands only");
   using S = TcSmem<BN, X3>;
   constexpr int kTcStages = S::kStages;
+  constexpr int kElK = BF16 ? kTcRowB / 2 : kTcBK;            // elements of K per stage row (64 bf16 or 32 fp32)
   // X3 keeps the two small correction products in a SECOND accumulator (columns [kAcc2, kAcc2+BN)) so that their
   // fp32 accumulation error is relative to their own 2^-11-times smaller magnitude; the epilogue adds the two.
   constexpr uint32_t kAcc2 = BN <= 32 ? 32 : BN <= 64 ? 64 : 128;
@@ -267,19 +292,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_expect_tx(&full_bar[s], S::kABytes + (X3 ? 2 : 1) * S::kBBytes);
         if (IM2COL) {
           const int tap = kb / sh.kb_per_tap, cb = kb - tap * sh.kb_per_tap;
-          if (IM2COL == 2) tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0, y0 + tap - 1, bimg);
-          else tma_load_4d(sa, &tmA, &full_bar[s], cb * kTcBK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
+          if (IM2COL == 2) tma_load_4d(sa, &tmA, &full_bar[s], cb * kElK, x0, y0 + tap - 1, bimg);
+          else tma_load_4d(sa, &tmA, &full_bar[s], cb * kElK, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
         } else {
-          tma_load_2d(sa, &tmA, &full_bar[s], kb * kTcBK, m0);
+          tma_load_2d(sa, &tmA, &full_bar[s], kb * kElK, m0);
         }
-        tma_load_2d(sb, &tmB, &full_bar[s], kb * kTcBK, n0);
-        if (X3) tma_load_2d(sb + S::kBBytes, &tmBlo, &full_bar[s], kb * kTcBK, n0);
+        tma_load_2d(sb, &tmB, &full_bar[s], kb * kElK, n0);
+        if (X3) tma_load_2d(sb + S::kBBytes, &tmBlo, &full_bar[s], kb * kElK, n0);
       }
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BN);
+      constexpr uint32_t idesc = BF16 ? make_idesc_bf16(BN) : make_idesc_tf32(BN);
       for (int kb = 0; kb < sh.nkb; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
@@ -299,7 +324,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             umma_tf32_ts(tmem_base + kAcc2, ah, bld, idesc, 1u);                        // a_hi * b_lo
           } else {
             const uint64_t ad = make_kmajor_sw128_desc(sa + k * 32);
-            umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (BF16) umma_bf16(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_tf32(tmem_base, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
           }
         }
         umma_commit(&empty_bar[s]);          // frees the smem slot once these MMAs have read it
@@ -394,9 +420,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
       for (int c = kG; c < 32; ++c) o[c] = 0.f;
       if (valid) {
-        float* dst = epi.out + mrow * epi.ld;
+        if (epi.out_bf16) {
+          uint8_t* dst = reinterpret_cast<uint8_t*>(epi.out) + (mrow * epi.ld) * 2;
 #pragma unroll
-        for (int j = 0; j < kG; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          for (int j = 0; j < kG; j += 8) store_bf16x8(dst + j * 2, o + j);
+        } else {
+          float* dst = epi.out + mrow * epi.ld;
+#pragma unroll
+          for (int j = 0; j < kG; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
       }
       if (epi.stats != nullptr) {
         float a[32], b[32];
@@ -440,6 +472,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (n0 + c + j < sh.N) epi.out[(size_t)(n0 + c + j) * epi.ld + mrow] = v[j];
+      } else if (valid && epi.out_bf16) {         // bf16 result (no accumulate): N is a multiple of 8 for every caller
+        uint8_t* dst = reinterpret_cast<uint8_t*>(epi.out) + (mrow * epi.ld + n0 + c) * 2;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          if (n0 + c + j + 7 < sh.N) store_bf16x8(dst + j * 2, v + j);
+          else {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj)
+              if (n0 + c + j + jj < sh.N) reinterpret_cast<__nv_bfloat16*>(dst)[j + jj] = __float2bfloat16_rn(v[j + jj]);
+          }
+        }
       } else if (valid) {
         float* dst = epi.out + mrow * epi.ld + n0 + c;
 #pragma unroll
@@ -709,14 +752,14 @@ static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
 }
 bool tc_available() { return get_encode() != nullptr; }
 
-static int make_map(CUtensorMap* map, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
-                    CUtensorMapSwizzle swz = (kTcRowB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)) {
+static int make_map(CUtensorMap* map, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box,
+                    CUtensorMapSwizzle swz = (kTcRowB == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B), bool bf16 = false) {
   PFN_cuTensorMapEncodeTiled_v12000 enc = get_encode();
   WAP_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from the driver");
   cuuint64_t gdim[5]; cuuint64_t gstr[4]; cuuint32_t bdim[5]; cuuint32_t estr[5];
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bdim[i] = box[i]; estr[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr, bdim, estr,
+  CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bdim, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   WAP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): rank=%d dims=%llu,%llu stride0=%llu box=%u,%u", (int)r, rank,
@@ -736,24 +779,25 @@ const int* trap_note_host() {
   }
   return g_trap_host;
 }
-template <int BN, int IM2COL, bool X3>
+template <int BN, int IM2COL, bool X3, bool BF16 = false>
 static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
                       const TcShape& sh, dim3 grid, int prof_cls, double flops) {
   static bool configured = false;
   if (!configured) {
-    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3>::kTotal));
+    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3>::kTotal));
     configured = true;
   }
   TcShape sh2 = sh; sh2.trace = g_tc_trace;
   prof_begin(st, prof_cls, flops);
-  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3>, grid, TcThreads<X3>::kN, TcSmem<BN, X3>::kTotal, st, ta, tb, tblo, epi, sh2));
+  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3, BF16>, grid, TcThreads<X3>::kN, TcSmem<BN, X3>::kTotal, st, ta, tb, tblo, epi, sh2));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
 }
 template <int BN, int IM2COL>
 static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tblo, const TcEpi& epi,
-                     const TcShape& sh, dim3 grid, int prof_cls, double flops) {
+                     const TcShape& sh, dim3 grid, int prof_cls, double flops, bool bf16 = false) {
+  if (bf16) return launch_tc1<BN, IM2COL, false, true>(st, ta, tb, tb, epi, sh, grid, prof_cls, flops);
   if (tblo != nullptr) return launch_tc1<BN, IM2COL, true>(st, ta, tb, *tblo, epi, sh, grid, prof_cls, flops);
   return launch_tc1<BN, IM2COL, false>(st, ta, tb, tb, epi, sh, grid, prof_cls, flops);
 }
@@ -862,6 +906,89 @@ int tc_conv3x3_rowtile(cudaStream_t st, const float* x, int ldx, int B, int H, i
   dim3 grid(sh.tiles_y * B, 1);
   prof_set_bytes(4.0 * ((double)sh.M * C + 96.0 * K * (Wt3_lo != nullptr ? 2 : 1) + (double)sh.M * N));
   return launch_tc<96, 2>(st, ta, tb, pl, epi, sh, grid, prof_cls, 2.0 * sh.M * N * 9 * C);
+}
+
+// ------------------------------------------------------------------------------------ bf16 variants (precision mode 3)
+// Same kernels with BF16 = true: operands are bf16 in global memory (strides in ELEMENTS, byte strides must be multiples of 16),
+// a stage row holds 64 elements of K, kind::f16 MMAs, fp32 accumulation; epi.out_bf16 selects a bf16 result.
+constexpr int kBfK = kTcRowB / 2;      // 64
+
+int tc_gemm_bf16(cudaStream_t st, const void* A, int lda, const void* Bt, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
+  WAP_REQUIRE(kTcRowB == 128, "bf16 kernels need 128-byte stage rows");
+  WAP_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0 && ((epi.ld & (epi.out_bf16 ? 7 : 3)) == 0), "tc_gemm_bf16: strides must be multiples of 16 bytes (lda=%d ldb=%d ldd=%d)", lda, ldb, epi.ld);
+  WAP_REQUIRE(!(epi.out_bf16 && (epi.accumulate || epi.transpose_out || epi.bias)), "tc_gemm_bf16: bf16 output is store-only");
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)lda * 2}; const uint32_t box[2] = {kBfK, kTcBM};
+    WAP_TRY(make_map(&ta, A, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  const int BN = N <= 32 ? 32 : N <= 96 ? 96 : 128;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; const uint64_t str[1] = {(uint64_t)ldb * 2}; const uint32_t box[2] = {kBfK, (uint32_t)BN};
+    WAP_TRY(make_map(&tb, Bt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  TcShape sh{}; sh.M = M; sh.N = N; sh.K = K; sh.nkb = cdiv(K, kBfK);
+  dim3 grid(cdiv(M, kTcBM), cdiv(N, BN));
+  const double flops = 2.0 * M * N * K;
+  prof_set_bytes(2.0 * ((double)M * K + (double)N * K) + (epi.out_bf16 ? 2.0 : 4.0) * (double)M * N * (epi.accumulate ? 2 : 1));
+  if (BN == 32) return launch_tc<32, 0>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, flops, true);
+  if (BN == 96) return launch_tc<96, 0>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, flops, true);
+  return launch_tc<128, 0>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, flops, true);
+}
+
+// 9-tap 3x3 SAME conv of bf16 x[B,H,W,C] (pixel stride ldx elements) with Wt[Nrows][9*Cpad] (k = tap*Cpad + ci, Cpad = C rounded up to 64:
+// every tap starts a fresh 64-element k-block, the tail of a partial block is zero in Wt and zero-filled by TMA in x)
+int tc_conv3x3_bf16(cudaStream_t st, const void* x, int ldx, int B, int H, int W, int C, const void* Wt, int Nrows, int N, const TcEpi& epi, int prof_cls) {
+  WAP_REQUIRE((ldx & 7) == 0 && (C & 7) == 0, "tc_conv3x3_bf16: ldx=%d C=%d must be multiples of 8", ldx, C);
+  int TW = 1; while (TW < W && TW < kTcBM) TW <<= 1;
+  const int TH = kTcBM / TW;
+  const int kbt = cdiv(C, kBfK), Cpad = kbt * kBfK;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
+    const uint32_t box[4] = {kBfK, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&ta, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  const int BN = N <= 32 ? 32 : N <= 96 ? 96 : 128;
+  const int K = 9 * Cpad;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, (uint64_t)Nrows}; const uint64_t str[1] = {(uint64_t)K * 2}; const uint32_t box[2] = {kBfK, (uint32_t)BN};
+    WAP_TRY(make_map(&tb, Wt, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  TcShape sh{}; sh.M = B * H * W; sh.N = N; sh.K = K; sh.nkb = 9 * kbt;
+  sh.B = B; sh.H = H; sh.W = W; sh.kb_per_tap = kbt; sh.TW = TW; sh.TH = TH; sh.tiles_x = cdiv(W, TW); sh.tiles_y = cdiv(H, TH);
+  dim3 grid(sh.tiles_x * sh.tiles_y * B, cdiv(N, BN));
+  prof_set_bytes(2.0 * ((double)sh.M * C + (double)Nrows * K) + (epi.out_bf16 ? 2.0 : 4.0) * (double)sh.M * N);
+  const double flops = 2.0 * sh.M * N * 9 * C;
+  if (BN == 32) return launch_tc<32, 1>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, flops, true);
+  if (BN == 96) return launch_tc<96, 1>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, flops, true);
+  return launch_tc<128, 1>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, flops, true);
+}
+
+// row-tile 3x3 conv 96 -> 24 (W <= 128) in bf16: Wt3[96][3 * 128] with Wt3[24 j + co][128 dy + ci] = w[dy][j][ci][co] (ci >= 96 zero)
+int tc_conv3x3_rowtile_bf16(cudaStream_t st, const void* x, int ldx, int B, int H, int W, const void* Wt3, const TcEpi& epi, int prof_cls) {
+  constexpr int C = 96, N = 24, Cpad = 128;
+  WAP_REQUIRE(W <= kTcBM && (ldx & 7) == 0, "tc_conv3x3_rowtile_bf16: W=%d must be <= %d", W, kTcBM);
+  int TW = 1; while (TW < W) TW <<= 1;
+  const int TH = kTcBM / TW;
+  CUtensorMap ta, tb;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
+    const uint32_t box[4] = {kBfK, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&ta, x, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  const int K = 3 * Cpad;
+  {
+    const uint64_t dims[2] = {(uint64_t)K, 96}; const uint64_t str[1] = {(uint64_t)K * 2}; const uint32_t box[2] = {kBfK, 96};
+    WAP_TRY(make_map(&tb, Wt3, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  TcShape sh{}; sh.M = B * H * W; sh.N = N; sh.K = K; sh.nkb = K / kBfK;
+  sh.B = B; sh.H = H; sh.W = W; sh.kb_per_tap = Cpad / kBfK; sh.TW = TW; sh.TH = TH; sh.tiles_x = 1; sh.tiles_y = cdiv(H, TH);
+  dim3 grid(sh.tiles_y * B, 1);
+  prof_set_bytes(2.0 * ((double)sh.M * C + 96.0 * K) + (epi.out_bf16 ? 2.0 : 4.0) * (double)sh.M * N);
+  return launch_tc<96, 2>(st, ta, tb, nullptr, epi, sh, grid, prof_cls, 2.0 * sh.M * N * 9 * C, true);
 }
 
 extern float* g_wg_dbg; extern int g_wg_xor;

@@ -35,6 +35,7 @@ struct TcEpi {
   double* stats;             // [2][N] column sum / sum of squares of the raw accumulators, or null
   const float* bias;         // optional [N] added to the stored value (not to the statistics)
   int transpose_out;         // store D[m,n] at out[n*ld + m] (coalesced: one TMEM lane = one row m per thread)
+  int out_bf16;              // `out` points to bf16 elements (ld in elements); store only (no accumulate / transpose / bias)
 };
 
 // Bt_hi/lo[N][K] = split(transpose(W[K][N])) (transpose != 0) or split(W[N][K]) : operand preparation for tc_gemm's 3xTF32 mode
@@ -50,6 +51,12 @@ int tc_conv3x3_rowtile(cudaStream_t st, const float* x, int ldx, int B, int H, i
 int tc_wgrad_1x1(cudaStream_t st, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, bool x3, int prof_cls);
 int tc_wgrad_3x3(cudaStream_t st, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, bool x3,
                  int prof_cls);
+// bf16 variants (precision mode 3): bf16 operands in global memory (strides in elements), fp32 accumulation; see tc_gemm.cu
+int tc_gemm_bf16(cudaStream_t st, const void* A, int lda, const void* Bt, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls);
+int tc_conv3x3_bf16(cudaStream_t st, const void* x, int ldx, int B, int H, int W, int C, const void* Wt, int Nrows, int N, const TcEpi& epi, int prof_cls);
+int tc_conv3x3_rowtile_bf16(cudaStream_t st, const void* x, int ldx, int B, int H, int W, const void* Wt3, const TcEpi& epi, int prof_cls);
+int tc_wgrad_1x1_bf16(cudaStream_t st, const void* X, int ldx, const void* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int prof_cls);
+int tc_wgrad_3x3_bf16(cudaStream_t st, const void* X, int ldx, const void* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int prof_cls);
 bool tc_available();
 
 }  // namespace wap
