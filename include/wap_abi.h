@@ -216,6 +216,21 @@ int wap_tc_conv3x3_rowtile(void* stream, const float* x, int ldx, int B, int H, 
 int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int x3);
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo,
                      int x3);
+/* ---- bf16 tensor-core primitives of precision mode 3 (exported for the kernel-level parity tests).  Operands are bf16 in device
+ * memory, strides in ELEMENTS (byte strides multiples of 16), fp32 accumulation; out_bf16 != 0 stores D as bf16 (store only).
+ *   gemm          : D[M,N] (=|+=) A[M,K](lda) * Bt[N,K](ldb)^T ; optional fp64 column statistics [2][N] of the fp32 accumulators
+ *   conv3x3       : x[B,H,W,C] * Wt[Nrows][9*Cpad] (k = tap*Cpad + ci, Cpad = C rounded up to 64, padding zero) -> D[B*H*W, N]
+ *   conv3x3_rowtile: 96 -> 24 channels, W <= 128; Wt3[96][384], Wt3[24*j + co][128*dy + ci] = w[dy][j][ci][co]
+ *   wgrad_1x1     : dW[C,N] (fp32, ldo) += X[Mpix,C]^T dY[Mpix,N], N <= 128
+ *   wgrad_3x3     : dW[9*C,N] (fp32) += im2col3x3(X[B,H,W,C])^T dY[B,H,W,:N] (ldy elements per pixel), C <= 128, N <= 32 */
+int wap_tc_gemm_bf16(void* stream, const void* A, int lda, const void* Bt, int ldb, void* D, int ldd, int M, int N, int K, int accumulate, int out_bf16,
+                     double* stats);
+int wap_tc_conv3x3_bf16(void* stream, const void* x, int ldx, int B, int H, int W, int C, const void* Wt, int Nrows, int N, void* D, int ldd, int out_bf16,
+                        double* stats);
+int wap_tc_conv3x3_rowtile_bf16(void* stream, const void* x, int ldx, int B, int H, int W, const void* Wt3, void* D, int ldd, int out_bf16, double* stats);
+int wap_tc_wgrad_1x1_bf16(void* stream, const void* X, int ldx, const void* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo);
+int wap_tc_wgrad_3x3_bf16(void* stream, const void* X, int ldx, const void* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo);
+
 /* ---- dropout seed from device memory: when seed_dev != NULL every dropout site (S:89-93, S:361) reads its seed from
  * *seed_dev at kernel run time instead of the by-value `seed` argument, so that a training step captured once in a CUDA
  * graph can be replayed with a fresh seed per step (tf.layers.dropout draws new masks on every sess.run).  NULL restores

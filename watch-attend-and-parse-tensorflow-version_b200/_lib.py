@@ -71,6 +71,11 @@ SIGNATURES = {
     "wap_tc_conv3x3_rowtile": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "wap_tc_wgrad_1x1": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i]),
     "wap_tc_wgrad_3x3": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i, _i]),
+    "wap_tc_gemm_bf16": (_i, [_vp, _vp, _i, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
+    "wap_tc_conv3x3_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _i, _i, _vp, _i, _i, _vp]),
+    "wap_tc_conv3x3_rowtile_bf16": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp]),
+    "wap_tc_wgrad_1x1_bf16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
+    "wap_tc_wgrad_3x3_bf16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "wap_set_dropout_seed_source": (_i, [_vp]),
     "wap_set_pdl": (_i, [_i]),
     "wap_get_pdl": (_i, []),

@@ -323,6 +323,27 @@ int wap_tc_wgrad_1x1(void* stream, const float* X, int ldx, const float* dY, int
 int wap_tc_wgrad_3x3(void* stream, const float* X, int ldx, const float* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int x3) {
   return tc_wgrad_3x3(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, x3 != 0, kProfOtherGemm);
 }
+/* ---- bf16 tensor-core primitives (exported for the kernel-level parity tests) */
+int wap_tc_gemm_bf16(void* stream, const void* A, int lda, const void* Bt, int ldb, void* D, int ldd, int M, int N, int K, int accumulate, int out_bf16,
+                     double* stats) {
+  TcEpi e{reinterpret_cast<float*>(D), ldd, accumulate, stats, nullptr, 0, out_bf16};
+  return tc_gemm_bf16(ST(stream), A, lda, Bt, ldb, M, N, K, e, kProfOtherGemm);
+}
+int wap_tc_conv3x3_bf16(void* stream, const void* x, int ldx, int B, int H, int W, int C, const void* Wt, int Nrows, int N, void* D, int ldd, int out_bf16,
+                        double* stats) {
+  TcEpi e{reinterpret_cast<float*>(D), ldd, 0, stats, nullptr, 0, out_bf16};
+  return tc_conv3x3_bf16(ST(stream), x, ldx, B, H, W, C, Wt, Nrows, N, e, kProfOtherGemm);
+}
+int wap_tc_conv3x3_rowtile_bf16(void* stream, const void* x, int ldx, int B, int H, int W, const void* Wt3, void* D, int ldd, int out_bf16, double* stats) {
+  TcEpi e{reinterpret_cast<float*>(D), ldd, 0, stats, nullptr, 0, out_bf16};
+  return tc_conv3x3_rowtile_bf16(ST(stream), x, ldx, B, H, W, Wt3, e, kProfOtherGemm);
+}
+int wap_tc_wgrad_1x1_bf16(void* stream, const void* X, int ldx, const void* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo) {
+  return tc_wgrad_1x1_bf16(ST(stream), X, ldx, dY, ldy, Mpix, C, N, dW, ldo, kProfOtherGemm);
+}
+int wap_tc_wgrad_3x3_bf16(void* stream, const void* X, int ldx, const void* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo) {
+  return tc_wgrad_3x3_bf16(ST(stream), X, ldx, dY, ldy, B, H, W, C, N, dW, ldo, kProfOtherGemm);
+}
 int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies them: [1] = count, notes of 8 ints from [8] */
   const int* h = wap::trap_note_host();
   if (h == nullptr) return -1;

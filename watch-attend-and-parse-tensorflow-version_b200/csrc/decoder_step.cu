@@ -343,7 +343,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     WAP_CHECK(cudaEventRecord(c.ev_fork, st)); WAP_CHECK(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
     WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, c.side, c.ap_in, c.Ppat, Bn, c.h, c.w));
     WAP_LAUNCH_CHECK();
-    WAP_TRY(tc_gemm(c.side, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
+    WAP_TRY(tc_gemm(c.side, c.Ppat, 128, c.qfT_hi, c.tc_mode >= 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
                     TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
     WAP_CHECK(cudaEventRecord(c.ev_join, c.side));
   }
@@ -378,7 +378,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
   } else if (c.tc_mode != 0) {   // coverage on tensor cores: im2col patches [Bn*L,128] x Q'^T[512][128]  (+ U_f_b)
     WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, st, c.ap_in, c.Ppat, Bn, c.h, c.w));
     WAP_LAUNCH_CHECK();
-    WAP_TRY(tc_gemm(st, c.Ppat, 128, c.qfT_hi, c.tc_mode == 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
+    WAP_TRY(tc_gemm(st, c.Ppat, 128, c.qfT_hi, c.tc_mode >= 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
                     TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
     WAP_TRY(attention_tail(st, p, c.ann, c.watch, c.a_mask, c.shared, Bn, L, c.SP, c.ap_in, c.COV, c.TANH, c.E, c.alpha, c.ap_out, c.ctx));
   } else {

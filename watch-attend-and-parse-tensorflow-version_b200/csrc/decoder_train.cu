@@ -229,7 +229,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   if (tc) {   // hoisted watch GEMM [B*L,684]x[684,512] on tensor cores; h0 and Q' as usual
     WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, nullptr, W.H, W.qf, W.mean));
     WAP_TRY(tc_prep_bt(st, params + P.U_a, kD, kNA, 1, W.UaT_hi, W.UaT_lo));
-    WAP_TRY(tc_gemm(st, ann, kD, W.UaT_hi, prec == 2 ? W.UaT_lo : nullptr, kD, B * L, kNA, kD, TcEpi{W.watch, kNA, 0, nullptr, params + P.U_a_b, 0}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, ann, kD, W.UaT_hi, prec >= 2 ? W.UaT_lo : nullptr, kD, B * L, kNA, kD, TcEpi{W.watch, kNA, 0, nullptr, params + P.U_a_b, 0}, kProfOtherGemm));
     WAP_TRY(prep_qfT(st, W.qf, W.qfT_hi, W.qfT_lo));
   } else {
     WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, W.watch, W.H, W.qf, W.mean));   // H[0] = h0 (masked mean, S:345-347)
@@ -600,7 +600,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     WAP_LAUNCH_CHECK();
     WAP_TRY(fork2(3));
     // side: coverage backward: DF[B*L,121] = DZ * Q'^T ; dAP_out = dAP_in + transposed stencil
-    if (tc) WAP_TRY(tc_gemm(s2, DZt, kNA, W.qf_hi, prec == 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
+    if (tc) WAP_TRY(tc_gemm(s2, DZt, kNA, W.qf_hi, prec >= 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{W.DF, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm));   // tap-major DF^T [121][B*L]
     else WAP_TRY(gemm_nt(s2, DZt, kNA, W.qf, kNA, W.DF, 124, B * L, kCovTaps, kNA, nullptr, false));
     WAP_CHECK(launch_pdl(cov_bwd_gather_kernel, cdiv(B * L, 32), 32 * kGatherWarps, 0, s2, W.DF, dAP_in, dAP_out, B, h, w, tc ? 1 : 0));
     WAP_LAUNCH_CHECK();
@@ -668,7 +668,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_TRY(gemm_tn_atomic(sw, ann, kD, W.dWatch, kNA, g + P.U_a, kNA, kD, kNA, B * L));     // dU_a += ann^T * dWatch
   if (ss != nullptr) { WAP_CHECK(cudaEventRecord(ss->done[5], sw)); cur()->dec_join_pending = true; }
   // d ann = dWatch * U_a^T
-  if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec == 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
+  if (tc) WAP_TRY(tc_gemm(st, W.dWatch, kNA, W.Ua_hi, prec >= 2 ? W.Ua_lo : nullptr, kNA, B * L, kD, kNA, TcEpi{d_ann, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   else WAP_TRY(gemm_nt(st, W.dWatch, kNA, p + P.U_a, kNA, d_ann, kD, B * L, kD, kNA, nullptr, false));
   // context path
   WAP_CHECK(launch_pdl(dann_ctx_kernel, (unsigned)cdivz((size_t)B * L * (kD / 4), 256), 256, 0, st, W.ALPHA, W.dCTX, d_ann, T, B, L));

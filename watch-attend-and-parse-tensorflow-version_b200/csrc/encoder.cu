@@ -11,6 +11,7 @@
 #include "gemm.cuh"
 #include "model.h"
 #include "tc_gemm.cuh"
+#include "bn_kernels.cuh"
 
 namespace wap {
 
@@ -127,247 +128,6 @@ stem_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, flo
   for (int i = 0; i < kOutPerThread; ++i) {
     const int o = tid + i * 256;
     if (o < 49 * kStemC) atomicAdd(dw + o, s[i]);
-  }
-}
-
-// =====================================================================================
-// batch-norm (+ReLU +dropout +optional 2x2 SAME pool) forward
-// =====================================================================================
-struct BnActArgs {
-  const float* raw; int B, Hi, Wi, C;        // raw conv output [B,Hi,Wi,C]
-  float* out; int Ho, Wo, ld_out;            // destination pixels [B,Ho,Wo] x channel slice (row stride ld_out)
-  const double* stats;                       // [2][C] sum / sum of squares (training), else null
-  float* mmean; float* mvar;                 // moving statistics (read when !training; updated when training)
-  const float* gamma; const float* beta;
-  float* saved;                              // [2][kMaxBnC]: mean, invstd (training) or null
-  int training, dropout; uint32_t seed, site;
-  const uint32_t* seed_src;                  // non-null: the seed is read from device memory (CUDA-graph replay with a fresh seed)
-  int round_tf32;                            // round the stored activation to TF32 (RNA): operand of a tcgen05 conv
-};
-
-__device__ __forceinline__ float tf32_rna(float x) {
-  uint32_t u;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
-  return __uint_as_float(u);
-}
-
-__device__ __forceinline__ void bn_prologue(const BnActArgs& a, float* s_scale, float* s_shift) {
-  const double cnt = (double)a.B * a.Hi * a.Wi;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    double mean, var;
-    if (a.training) {
-      mean = a.stats[c] / cnt;
-      var = a.stats[a.C + c] / cnt - mean * mean;
-      if (var < 0.0) var = 0.0;
-    } else {
-      mean = a.mmean[c]; var = a.mvar[c];
-    }
-    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
-    const float sc = __ldg(a.gamma + c) * invstd;
-    s_scale[c] = sc;
-    s_shift[c] = __ldg(a.beta + c) - (float)mean * sc;
-    if (a.training && blockIdx.x == 0) {
-      if (a.saved != nullptr) { a.saved[c] = (float)mean; a.saved[kMaxBnC + c] = invstd; }
-      const double unb = var * (cnt / fmax(cnt - 1.0, 1.0));      // FusedBatchNorm: Bessel-corrected moving variance
-      a.mmean[c] = a.mmean[c] * kBnMomentum + (float)mean * (1.f - kBnMomentum);
-      a.mvar[c] = a.mvar[c] * kBnMomentum + (float)unb * (1.f - kBnMomentum);
-    }
-  }
-}
-
-__device__ __forceinline__ float bn_relu_drop(float v, float sc, float sh, bool dropout, uint32_t seed, uint32_t site, uint32_t idx) {
-  float y = fmaxf(fmaf(v, sc, sh), 0.f);
-  if (dropout) y = drop_keep(seed, site, idx) ? y * (1.f / (1.f - kDropRate)) : 0.f;
-  return y;
-}
-
-// POOL: 0 none, 1 max 2x2 SAME, 2 avg 2x2 SAME (valid-count divisor)
-template <int POOL>
-__global__ void __launch_bounds__(256) bn_act_kernel(const BnActArgs a) {
-  pdl_sync();
-  const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
-  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC];
-  bn_prologue(a, s_scale, s_shift);
-  __syncthreads();
-  const int C4 = a.C / 4;
-  const size_t total = (size_t)a.B * a.Ho * a.Wo * C4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    const size_t po = i / C4;
-    float r[4];
-    if (POOL == 0) {
-      const float4 v = ldg4(a.raw + po * a.C + c);
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-        r[j] = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, seed, a.site, (uint32_t)(po * a.C + c + j));
-    } else {
-      const int xo = (int)(po % a.Wo); const size_t t = po / a.Wo; const int yo = (int)(t % a.Ho); const int b = (int)(t / a.Ho);
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = (POOL == 1) ? -INFINITY : 0.f;
-      int cnt = 0;
-#pragma unroll
-      for (int dy = 0; dy < 2; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int yi = yo * 2 + dy, xi = xo * 2 + dx;
-          if (yi < a.Hi && xi < a.Wi) {
-            const size_t pi = ((size_t)b * a.Hi + yi) * a.Wi + xi;
-            const float4 v = ldg4(a.raw + pi * a.C + c);
-            const float vv[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const float y = bn_relu_drop(vv[j], s_scale[c + j], s_shift[c + j], a.dropout, seed, a.site, (uint32_t)(pi * a.C + c + j));
-              r[j] = (POOL == 1) ? fmaxf(r[j], y) : r[j] + y;
-            }
-            ++cnt;
-          }
-        }
-      if (POOL == 2) {
-        const float inv = 1.f / (float)cnt;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) r[j] *= inv;
-      }
-    }
-    if (a.round_tf32) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) r[j] = tf32_rna(r[j]);
-    }
-    *reinterpret_cast<float4*>(a.out + po * a.ld_out + c) = make_float4(r[0], r[1], r[2], r[3]);
-  }
-}
-
-// =====================================================================================
-// batch-norm (+ReLU +dropout +pool) backward: pass 1 = upstream gradient at the BN output (g) and
-// the two per-channel reductions; pass 2 = d raw in place, d gamma / d beta.
-// =====================================================================================
-struct BnBwdArgs {
-  const float* raw; int B, Hi, Wi, C;
-  const float* dout; int Ho, Wo, ld_dout;    // gradient wrt the (pooled) activated output, channel slice
-  const float* saved; const float* gamma; const float* beta;
-  float* g; int ld_g;                        // [B*Hi*Wi, ld_g]
-  double* red;                               // [2][C]: sum g, sum g*xhat
-  double* red_next;                          // the apply kernel zeroes this buffer (2*kMaxBnC doubles) for the next BN backward
-  float* dgamma; float* dbeta;               // += (pass 2)
-  int dropout; uint32_t seed, site;
-  const uint32_t* seed_src;
-  int round_tf32;                            // round d raw to TF32 (operand of the tcgen05 dgrad)
-};
-
-template <int POOL>
-__global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, const int pix_per_cta) {
-  pdl_sync();
-  const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
-  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC];
-  __shared__ float s_sg[kMaxBnC], s_sgx[kMaxBnC];
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float mean = a.saved[c], inv = a.saved[kMaxBnC + c];
-    const float sc = __ldg(a.gamma + c) * inv;
-    s_scale[c] = sc; s_shift[c] = __ldg(a.beta + c) - mean * sc; s_mean[c] = mean; s_inv[c] = inv;
-    s_sg[c] = 0.f; s_sgx[c] = 0.f;
-  }
-  __syncthreads();
-  const int C4 = a.C / 4, rows = blockDim.x / C4;
-  const int c = (threadIdx.x % C4) * 4, prow = threadIdx.x / C4;
-  const size_t npix = (size_t)a.B * a.Hi * a.Wi;
-  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
-  const size_t p1 = min(npix, p0 + (size_t)pix_per_cta);
-  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
-  if (prow < rows) {
-    for (size_t p = p0 + prow; p < p1; p += rows) {
-      const float4 v = ldg4(a.raw + p * a.C + c);
-      const float vv[4] = {v.x, v.y, v.z, v.w};
-      float up[4];
-      if (POOL == 0) {
-        const float4 d = ldg4(a.dout + p * a.ld_dout + c);
-        up[0] = d.x; up[1] = d.y; up[2] = d.z; up[3] = d.w;
-      } else {
-        const int xi = (int)(p % a.Wi); const size_t t = p / a.Wi; const int yi = (int)(t % a.Hi); const int b = (int)(t / a.Hi);
-        const int yo = yi >> 1, xo = xi >> 1;
-        const float4 d = ldg4(a.dout + (((size_t)b * a.Ho + yo) * a.Wo + xo) * a.ld_dout + c);
-        const float dd[4] = {d.x, d.y, d.z, d.w};
-        if (POOL == 2) {
-          const int cnt = min(2, a.Hi - yo * 2) * min(2, a.Wi - xo * 2);
-          const float inv = 1.f / (float)cnt;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) up[j] = dd[j] * inv;
-        } else {
-          // max pool: the gradient goes to the first window cell (row-major) attaining the maximum
-#pragma unroll
-          for (int j = 0; j < 4; ++j) up[j] = 0.f;
-          float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
-          int arg[4] = {0, 0, 0, 0};
-#pragma unroll
-          for (int wy = 0; wy < 2; ++wy)
-#pragma unroll
-            for (int wx = 0; wx < 2; ++wx) {
-              const int y2 = yo * 2 + wy, x2 = xo * 2 + wx;
-              if (y2 < a.Hi && x2 < a.Wi) {
-                const float4 q = ldg4(a.raw + (((size_t)b * a.Hi + y2) * a.Wi + x2) * a.C + c);
-                const float qq[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float y = fmaxf(fmaf(qq[j], s_scale[c + j], s_shift[c + j]), 0.f);
-                  if (y > best[j]) { best[j] = y; arg[j] = wy * 2 + wx; }
-                }
-              }
-            }
-          const int me = (yi & 1) * 2 + (xi & 1);
-#pragma unroll
-          for (int j = 0; j < 4; ++j) if (arg[j] == me) up[j] = dd[j];
-        }
-      }
-      float gg[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float pre = fmaf(vv[j], s_scale[c + j], s_shift[c + j]);
-        float gj = (pre > 0.f) ? up[j] : 0.f;
-        if (a.dropout) gj = drop_keep(seed, a.site, (uint32_t)(p * a.C + c + j)) ? gj * (1.f / (1.f - kDropRate)) : 0.f;
-        gg[j] = gj;
-        sg[j] += gj;
-        sgx[j] = fmaf(gj, (vv[j] - s_mean[c + j]) * s_inv[c + j], sgx[j]);
-      }
-      *reinterpret_cast<float4*>(a.g + p * a.ld_g + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) { atomicAdd(&s_sg[c + j], sg[j]); atomicAdd(&s_sgx[c + j], sgx[j]); }
-  }
-  __syncthreads();
-  for (int cc = threadIdx.x; cc < a.C; cc += blockDim.x) {
-    atomicAdd(a.red + cc, (double)s_sg[cc]);
-    atomicAdd(a.red + a.C + cc, (double)s_sgx[cc]);
-  }
-}
-
-__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
-  pdl_sync();
-  if (blockIdx.x == 0 && a.red_next != nullptr)
-    for (int i = threadIdx.x; i < 2 * kMaxBnC; i += blockDim.x) a.red_next[i] = 0.0;
-  __shared__ float s_k[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC], s_mg[kMaxBnC], s_mgx[kMaxBnC];
-  const double cnt = (double)a.B * a.Hi * a.Wi;
-  for (int c = threadIdx.x; c < a.C; c += blockDim.x) {
-    const float inv = a.saved[kMaxBnC + c];
-    s_mean[c] = a.saved[c]; s_inv[c] = inv; s_k[c] = __ldg(a.gamma + c) * inv;
-    s_mg[c] = (float)(a.red[c] / cnt); s_mgx[c] = (float)(a.red[a.C + c] / cnt);
-    if (blockIdx.x == 0) { a.dbeta[c] += (float)a.red[c]; a.dgamma[c] += (float)a.red[a.C + c]; }
-  }
-  __syncthreads();
-  const int C4 = a.C / 4;
-  const size_t total = (size_t)a.B * a.Hi * a.Wi * C4;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C4) * 4;
-    const size_t p = i / C4;
-    const float4 v = ldg4(a.raw + p * a.C + c);
-    float4 g = *reinterpret_cast<const float4*>(a.g + p * a.ld_g + c);
-    const float vv[4] = {v.x, v.y, v.z, v.w};
-    float gg[4] = {g.x, g.y, g.z, g.w};
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float xh = (vv[j] - s_mean[c + j]) * s_inv[c + j];
-      gg[j] = s_k[c + j] * (gg[j] - s_mg[c + j] - xh * s_mgx[c + j]);
-      if (a.round_tf32) gg[j] = tf32_rna(gg[j]);
-    }
-    *reinterpret_cast<float4*>(a.g + p * a.ld_g + c) = make_float4(gg[0], gg[1], gg[2], gg[3]);
   }
 }
 
@@ -490,42 +250,33 @@ int debug_bn_gates(cudaStream_t st, const float* params, const float* wsp, int B
 // =====================================================================================
 // host orchestration
 // =====================================================================================
-static inline int ew_grid(size_t total_vec) {
-  return (int)std::min<size_t>(cdivz(total_vec, 256), 148 * 8);
-}
-
-static int run_bn_act(cudaStream_t st, int pool, const BnActArgs& a) {
-  const size_t total = (size_t)a.B * a.Ho * a.Wo * (a.C / 4);
-  const int grid = ew_grid(total);
-  if (pool == 0) WAP_CHECK(launch_pdl(bn_act_kernel<0>, grid, 256, 0, st, a));
-  else if (pool == 1) WAP_CHECK(launch_pdl(bn_act_kernel<1>, grid, 256, 0, st, a));
-  else WAP_CHECK(launch_pdl(bn_act_kernel<2>, grid, 256, 0, st, a));
-  WAP_LAUNCH_CHECK();
-  return 0;
-}
-
-static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
-  // a.red was zeroed by the previous BN backward's apply kernel (or by the memset at the start of encoder_backward): a memset
-  // node here would sit between two kernels 110 times per step and break their programmatic dependency
-  const size_t npix = (size_t)a.B * a.Hi * a.Wi;
-  int ppc = (int)std::max<size_t>(64, cdivz(npix, 148 * 4));
-  const int grid = (int)cdivz(npix, ppc);
-  if (pool == 0) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<0>, grid, 256, 0, st, a, ppc));
-  else if (pool == 1) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<1>, grid, 256, 0, st, a, ppc));
-  else WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<2>, grid, 256, 0, st, a, ppc));
-  WAP_LAUNCH_CHECK();
-  WAP_CHECK(launch_pdl(bn_bwd_apply_kernel, ew_grid(npix * (a.C / 4)), 256, 0, st, a));
-  WAP_LAUNCH_CHECK();
-  return 0;
-}
-
 static void stem_pad(int n_in, int n_out, int* before) {
   const int total = std::max((n_out - 1) * 2 + 7 - n_in, 0);
   *before = total / 2;
 }
+// stem conv (+statistics) / stem weight gradient launchers, shared with encoder_bf16.cu
+int run_stem_conv(cudaStream_t st, const float* x, const float* w, float* out, double* stats, int B, int H, int W, const EncGeom& g) {
+  int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
+  dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
+  WAP_CHECK(launch_pdl(stem_conv_kernel, grid, 256, 0, st, x, w, out, stats, H, W, g.Hs, g.Ws, pt, pl));
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+int run_stem_wgrad(cudaStream_t st, const float* x, const float* gstem, float* dw, int B, int H, int W, const EncGeom& g) {
+  int pt, pl; stem_pad(H, g.Hs, &pt); stem_pad(W, g.Ws, &pl);
+  dim3 grid(cdiv(g.Ws, kStemTile), cdiv(g.Hs, kStemTile), B);
+  WAP_CHECK(launch_pdl(stem_wgrad_kernel, grid, 256, 0, st, x, gstem, dw, H, W, g.Hs, g.Ws, pt, pl));
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+int encoder_forward_bf16(cudaStream_t st, const float* params, float* moving, const float* x, int B, int H, int W,
+                         int training, int dropout, uint32_t seed, float* annotation, float* wsp);
+int encoder_backward_bf16(cudaStream_t st, const float* params, float* grads, const float* x, int B, int H, int W,
+                          int dropout, uint32_t seed, const float* annotation, float* d_annotation, float* wsp);
 
 int encoder_forward(cudaStream_t st, const float* params, float* moving, const float* x, int B, int H, int W,
                     int training, int dropout, uint32_t seed, float* annotation, float* wsp) {
+  if (get_conv_precision() == 3) return encoder_forward_bf16(st, params, moving, x, B, H, W, training, dropout, seed, annotation, wsp);
   const ParamLayout& L = layout();
   const EncGeom g = make_geom(B, H, W);
   const EncWorkspace ws = make_enc_workspace(g, training != 0);
@@ -626,6 +377,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
 // buffer of block 2 and is clobbered.  grads (flat, same layout as params) is accumulated (+=).
 int encoder_backward(cudaStream_t st, const float* params, float* grads, const float* x, int B, int H, int W,
                      int dropout, uint32_t seed, const float* annotation, float* d_annotation, float* wsp) {
+  if (get_conv_precision() == 3) return encoder_backward_bf16(st, params, grads, x, B, H, W, dropout, seed, annotation, d_annotation, wsp);
   const ParamLayout& L = layout();
   const EncGeom g = make_geom(B, H, W);
   const EncWorkspace ws = make_enc_workspace(g, true);

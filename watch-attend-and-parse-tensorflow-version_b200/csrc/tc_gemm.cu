@@ -171,11 +171,13 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int n) {
   return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
 }
 // 8 fp32 -> 8 bf16 (round to nearest even) as one 16-byte store
+// (two 8-byte stores: rows of 300 bf16 channels are only 8-byte aligned)
 __device__ __forceinline__ void store_bf16x8(void* dst, const float* v) {
   uint32_t w[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(w[i]) : "f"(v[2 * i + 1]), "f"(v[2 * i]));
-  *reinterpret_cast<uint4*>(dst) = make_uint4(w[0], w[1], w[2], w[3]);
+  reinterpret_cast<uint2*>(dst)[0] = make_uint2(w[0], w[1]);
+  reinterpret_cast<uint2*>(dst)[1] = make_uint2(w[2], w[3]);
 }
 
 // ------------------------------------------------------------------------------------ kernel
@@ -736,6 +738,137 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
+// =====================================================================================
+// bf16 weight-gradient GEMM (precision mode 3):  dW[M, N] += sum over pixels p of X[p, m] * dY[p, n], bf16 operands, fp32 result.
+// 16-bit MN-major operands use the plain SWIZZLE_128B canonical layout: an atom is 8 pixel rows x 64 channels (128 B per row,
+// 16-byte chunk c of row r stored at chunk c ^ (r & 7) - what TMA SWIZZLE_128B writes); SBO = next 8-row group (1024 B),
+// LBO = next 64-channel block.  A stage holds 64 pixel rows: A = 2 channel blocks (M = 128), B = NBLK blocks; four K = 16 MMAs.
+// IM2COL (3x3 conv): one M tile per tap, its two blocks are channels [0,64) and [64,128) of the tap-shifted input box (channels
+// >= C are zero-filled by TMA); the result row (tap, ch) goes to dW row tap*C + ch.
+// =====================================================================================
+constexpr int kWbRows = 64;                       // pixel rows per stage
+constexpr int kWbBlk = kWbRows * 128;             // bytes of one 64-channel block of a stage (8192)
+constexpr int kWbStages = 4;
+
+template <int NBLK> struct WbSmem {
+  static constexpr int kABytes = 2 * kWbBlk, kBBytes = NBLK * kWbBlk, kStage = kABytes + kBBytes;
+  static constexpr int kBarOff = kWbStages * kStage, kTotal = kBarOff + 256 + 1024;
+};
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc16(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;             // leading byte offset: next 64-channel block
+  d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: next 8-row (K) group
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t make_idesc_bf16_mn(int n) {   // both operands MN-major
+  return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(kTcBM >> 4) << 24);
+}
+
+template <int NMMA, bool IM2COL>
+__global__ void __launch_bounds__(kTcThreads, 1)
+tc_wgrad_bf16_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY, float* __restrict__ out, const WgShape sh) {
+  pdl_sync();
+  constexpr int NBLK = (NMMA + 63) / 64;
+  using S = WbSmem<NBLK>;
+  constexpr uint32_t kTmemCols = NMMA <= 32 ? 32 : NMMA <= 64 ? 64 : 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::kBarOff);
+  uint64_t* empty_bar = full_bar + kWbStages;
+  uint64_t* tmem_full = empty_bar + kWbStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * kTcBM;                 // IM2COL: blockIdx.x = tap
+  const int s_beg = blockIdx.z * sh.stages_per_split;
+  const int s_end = min(sh.nstages, s_beg + sh.stages_per_split);
+  const int ns = s_end - s_beg;
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&tmX); prefetch_tmap(&tmY);
+    for (int s = 0; s < kWbStages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(tmem_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (ns <= 0) { __syncthreads(); if (warp == 1) tmem_dealloc(tmem_base, kTmemCols); return; }
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < ns; ++i) {
+        const int st = s_beg + i, s = i % kWbStages;
+        const uint32_t ph = (i / kWbStages) & 1;
+        mbar_wait(&empty_bar[s], ph ^ 1, 21 + 100 * i);
+        uint8_t* sa = smem + s * S::kStage;
+        uint8_t* sb = sa + S::kABytes;
+        mbar_expect_tx(&full_bar[s], S::kABytes + S::kBBytes);
+        if (IM2COL) {
+          int t = st;
+          const int tx = t % sh.tiles_x; t /= sh.tiles_x;
+          const int ty = t % sh.tiles_y; const int bimg = t / sh.tiles_y;
+          const int x0 = tx * sh.TW, y0 = ty * sh.TH;
+          const int tap = blockIdx.x;
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) tma_load_4d(sa + blk * kWbBlk, &tmX, &full_bar[s], blk * 64, x0 + tap % 3 - 1, y0 + tap / 3 - 1, bimg);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) tma_load_4d(sb + blk * kWbBlk, &tmY, &full_bar[s], blk * 64, x0, y0, bimg);
+        } else {
+#pragma unroll
+          for (int blk = 0; blk < 2; ++blk) tma_load_2d(sa + blk * kWbBlk, &tmX, &full_bar[s], m0 + blk * 64, st * kWbRows);
+#pragma unroll
+          for (int blk = 0; blk < NBLK; ++blk) tma_load_2d(sb + blk * kWbBlk, &tmY, &full_bar[s], blk * 64, st * kWbRows);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16_mn(NMMA) ^ (uint32_t)sh.dbg_idesc_xor;
+      for (int i = 0; i < ns; ++i) {
+        const int s = i % kWbStages;
+        const uint32_t ph = (i / kWbStages) & 1;
+        mbar_wait(&full_bar[s], ph, 22 + 100 * i);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + s * S::kStage);
+        const uint32_t sb = sa + S::kABytes;
+#pragma unroll
+        for (int k = 0; k < kWbRows / 16; ++k) {
+          const uint64_t ad = make_mnmajor_sw128_desc16(sa + k * 2048, kWbBlk);
+          const uint64_t bd = make_mnmajor_sw128_desc16(sb + k * 2048, kWbBlk);
+          umma_bf16(tmem_base, ad, bd, idesc, (i | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(tmem_full);
+    }
+  } else {
+    const int q = warp & 3, r = q * 32 + lane;
+    int orow; bool ok;
+    if (IM2COL) { ok = r < sh.C; orow = blockIdx.x * sh.C + r; }
+    else { orow = m0 + r; ok = orow < sh.M; }
+    mbar_wait(tmem_full, 0, 24);
+    tc_fence_after();
+#pragma unroll 1
+    for (int c = 0; c < NMMA; c += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      if (ok) {
+        float* dst = out + (size_t)orow * sh.ldo + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < sh.N) atomicAdd(dst + j, v[j]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
 // ------------------------------------------------------------------------------------ host side
 static PFN_cuTensorMapEncodeTiled_v12000 g_encode = nullptr;
 static bool g_encode_tried = false;
@@ -915,7 +1048,7 @@ constexpr int kBfK = kTcRowB / 2;      // 64
 
 int tc_gemm_bf16(cudaStream_t st, const void* A, int lda, const void* Bt, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
   WAP_REQUIRE(kTcRowB == 128, "bf16 kernels need 128-byte stage rows");
-  WAP_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0 && ((epi.ld & (epi.out_bf16 ? 7 : 3)) == 0), "tc_gemm_bf16: strides must be multiples of 16 bytes (lda=%d ldb=%d ldd=%d)", lda, ldb, epi.ld);
+  WAP_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0 && (epi.ld & 3) == 0, "tc_gemm_bf16: operand strides must be multiples of 16 bytes, the output stride of 4 elements (lda=%d ldb=%d ldd=%d)", lda, ldb, epi.ld);
   WAP_REQUIRE(!(epi.out_bf16 && (epi.accumulate || epi.transpose_out || epi.bias)), "tc_gemm_bf16: bf16 output is store-only");
   CUtensorMap ta, tb;
   {
@@ -1061,6 +1194,71 @@ int tc_wgrad_3x3(cudaStream_t st, const float* X, int ldx, const float* dY, int 
   dim3 grid(mt, 1, cdiv(sh.nstages, sh.stages_per_split));
   prof_set_bytes(4.0 * ((double)B * H * W * (C + 32) + 9.0 * C * N));
   return launch_wg<1, true>(st, tx, ty, dW, sh, grid, x3, prof_cls, 2.0 * B * H * W * 9 * C * N);
+}
+
+template <int NMMA, bool IM2COL>
+static int launch_wb(cudaStream_t st, const CUtensorMap& tx, const CUtensorMap& ty, float* out, const WgShape& sh, dim3 grid, int prof_cls, double flops) {
+  constexpr int NBLK = (NMMA + 63) / 64;
+  static bool configured = false;
+  if (!configured) {
+    WAP_CHECK(cudaFuncSetAttribute(tc_wgrad_bf16_kernel<NMMA, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, WbSmem<NBLK>::kTotal));
+    configured = true;
+  }
+  WgShape sh2 = sh; sh2.dbg = nullptr; sh2.dbg_idesc_xor = g_wg_xor;
+  prof_begin(st, prof_cls, flops);
+  WAP_CHECK(launch_pdl(tc_wgrad_bf16_kernel<NMMA, IM2COL>, grid, kTcThreads, WbSmem<NBLK>::kTotal, st, tx, ty, out, sh2));
+  prof_end(st, prof_cls);
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
+
+// dW[C, N] (ldo, fp32) += X[Mpix, C](ldx)^T * dY[Mpix, N](ldy), bf16 operands, N <= 128
+int tc_wgrad_1x1_bf16(cudaStream_t st, const void* X, int ldx, const void* dY, int ldy, int Mpix, int C, int N, float* dW, int ldo, int prof_cls) {
+  WAP_REQUIRE(N <= 128 && (ldx & 7) == 0 && (ldy & 7) == 0, "tc_wgrad_1x1_bf16: N=%d ldx=%d ldy=%d", N, ldx, ldy);
+  CUtensorMap tx, ty;
+  {
+    const uint64_t dims[2] = {(uint64_t)C, (uint64_t)Mpix}; const uint64_t str[1] = {(uint64_t)ldx * 2}; const uint32_t box[2] = {64, kWbRows};
+    WAP_TRY(make_map(&tx, X, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)N, (uint64_t)Mpix}; const uint64_t str[1] = {(uint64_t)ldy * 2}; const uint32_t box[2] = {64, kWbRows};
+    WAP_TRY(make_map(&ty, dY, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  WgShape sh{}; sh.M = C; sh.N = N; sh.nstages = cdiv(Mpix, kWbRows); sh.ldo = ldo;
+  const int mt = cdiv(C, kTcBM), splits = pick_splits(sh.nstages, mt);
+  sh.stages_per_split = cdiv(sh.nstages, splits);
+  dim3 grid(mt, 1, cdiv(sh.nstages, sh.stages_per_split));
+  prof_set_bytes(2.0 * ((double)Mpix * C + (double)Mpix * N) + 4.0 * (double)C * N);
+  if (N <= 32) return launch_wb<32, false>(st, tx, ty, dW, sh, grid, prof_cls, 2.0 * Mpix * C * N);
+  if (N <= 96) return launch_wb<96, false>(st, tx, ty, dW, sh, grid, prof_cls, 2.0 * Mpix * C * N);
+  return launch_wb<128, false>(st, tx, ty, dW, sh, grid, prof_cls, 2.0 * Mpix * C * N);
+}
+
+// dW[9*C, N] (ldo, fp32) += im2col3x3(X[B,H,W,C] (ldx))^T * dY[B,H,W,:] (ldy elements per pixel, N <= 32 valid), bf16 operands, C <= 128
+int tc_wgrad_3x3_bf16(cudaStream_t st, const void* X, int ldx, const void* dY, int ldy, int B, int H, int W, int C, int N, float* dW, int ldo, int prof_cls) {
+  WAP_REQUIRE(C <= 128 && (C & 7) == 0 && N <= 32 && (ldx & 7) == 0 && (ldy & 7) == 0 && ldy >= N, "tc_wgrad_3x3_bf16: C=%d N=%d ldx=%d ldy=%d", C, N, ldx, ldy);
+  int TW = 1; while (TW < W && TW < kWbRows) TW <<= 1;
+  const int TH = kWbRows / TW;
+  CUtensorMap tx, ty;
+  {
+    const uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldx * 2, (uint64_t)W * ldx * 2, (uint64_t)H * W * ldx * 2};
+    const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&tx, X, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)ldy, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+    const uint64_t str[3] = {(uint64_t)ldy * 2, (uint64_t)W * ldy * 2, (uint64_t)H * W * ldy * 2};
+    const uint32_t box[4] = {64, (uint32_t)TW, (uint32_t)TH, 1};
+    WAP_TRY(make_map(&ty, dY, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, true));
+  }
+  WgShape sh{}; sh.M = 9 * C; sh.N = N; sh.ldo = ldo; sh.C = C; sh.H = H; sh.W = W; sh.TW = TW; sh.TH = TH;
+  sh.tiles_x = cdiv(W, TW); sh.tiles_y = cdiv(H, TH); sh.nstages = sh.tiles_x * sh.tiles_y * B;
+  const int splits = pick_splits(sh.nstages, 9);
+  sh.stages_per_split = cdiv(sh.nstages, splits);
+  dim3 grid(9, 1, cdiv(sh.nstages, sh.stages_per_split));
+  prof_set_bytes(2.0 * ((double)B * H * W * (C + ldy)) + 4.0 * 9.0 * C * N);
+  return launch_wb<32, true>(st, tx, ty, dW, sh, grid, prof_cls, 2.0 * B * H * W * 9 * C * N);
 }
 
 }  // namespace wap
