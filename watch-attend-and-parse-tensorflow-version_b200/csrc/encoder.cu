@@ -219,18 +219,20 @@ static int prep_conv_weights(cudaStream_t st, const float* params, float* wsp, b
 // training-mode forward left in the workspace.  The gradient tests hand these gates to the fp64 oracle: an element within
 // fp32 rounding of the kink is then gated identically on both sides and the comparison is well posed for every element.
 // =====================================================================================
-__global__ void __launch_bounds__(256) bn_gate_kernel(const float* __restrict__ raw, const float* __restrict__ saved, const float* __restrict__ gamma,
+template <typename TRaw>
+__global__ void __launch_bounds__(256) bn_gate_kernel(const TRaw* __restrict__ raw, const float* __restrict__ saved, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, int C, size_t n, uint8_t* __restrict__ out) {
   pdl_sync();
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const float sc = __ldg(gamma + c) * saved[kMaxBnC + c];
     const float sh = __ldg(beta + c) - saved[c] * sc;
-    out[i] = fmaf(raw[i], sc, sh) > 0.f ? 1 : 0;
+    out[i] = fmaf((float)raw[i], sc, sh) > 0.f ? 1 : 0;
   }
 }
 int debug_bn_gates(cudaStream_t st, const float* params, const float* wsp, int B, int H, int W, int k, uint8_t* out) {
-  WAP_REQUIRE(k >= 0 && k < kNumConv && get_conv_precision() != 3, "wap_debug_bn_gates: layer %d / precision mode not supported", k);
+  WAP_REQUIRE(k >= 0 && k < kNumConv, "wap_debug_bn_gates: layer %d out of range", k);
+  const bool b16 = get_conv_precision() == 3 && k > 0;      // bf16 mode keeps the raw conv outputs of the dense blocks in bf16 (same offsets)
   const ParamLayout& L = layout();
   const EncGeom g = make_geom(B, H, W);
   const EncWorkspace ws = make_enc_workspace(g, true);
@@ -241,8 +243,10 @@ int debug_bn_gates(cudaStream_t st, const float* params, const float* wsp, int B
   else if (c.kind == kC3) { raw = wsp + ws.y2[k]; npix = g.M[c.block]; }
   else { raw = wsp + ws.ytr[c.block]; npix = g.M[c.block]; }
   const size_t n = npix * c.cout;
-  WAP_CHECK(launch_pdl(bn_gate_kernel, (unsigned)std::min<size_t>(cdivz(n, 256), 148 * 8), 256, 0, st, raw, wsp + ws.saved + (size_t)k * 2 * kMaxBnC,
-                       params + c.gamma, params + c.beta, c.cout, n, out));
+  const unsigned grid = (unsigned)std::min<size_t>(cdivz(n, 256), 148 * 8);
+  const float* sv = wsp + ws.saved + (size_t)k * 2 * kMaxBnC;
+  if (b16) WAP_CHECK(launch_pdl(bn_gate_kernel<__nv_bfloat16>, grid, 256, 0, st, reinterpret_cast<const __nv_bfloat16*>(raw), sv, params + c.gamma, params + c.beta, c.cout, n, out));
+  else WAP_CHECK(launch_pdl(bn_gate_kernel<float>, grid, 256, 0, st, raw, sv, params + c.gamma, params + c.beta, c.cout, n, out));
   WAP_LAUNCH_CHECK();
   return 0;
 }
