@@ -329,8 +329,10 @@ def run_train(args):
     rank, world, dev = env.rank, env.world, env.dev
     L = wap_b200._lib.lib()
     precision = args.precision or ("bf16" if args.workload == "cfg3" else "tf32x3")
-    eng = wap_b200.WAPEngine(device=dev, seed=0, init=True, precision=precision,
-                             use_graphs=not (args.no_graphs or args.profile_run))     # same seed on every rank: replicated weights
+    # cfg3 visits a different padded shape every step (as the reference's area-bucketed batches do, ~1500 shapes per epoch), so no
+    # shape repeats inside the run: graph capture would only add its cost to the timed region - plain stream launches + PDL there
+    graphs = not (args.no_graphs or args.profile_run or args.workload == "cfg3")
+    eng = wap_b200.WAPEngine(device=dev, seed=0, init=True, precision=precision, use_graphs=graphs)     # same seed on every rank: replicated weights
     eng.world_size, eng.rank = world, rank
     B = 16 if args.workload in ("cfg2b16", "cfg3") else 8
     if args.workload == "cfg3":
@@ -392,7 +394,7 @@ def run_train(args):
     L.wap_profile_enable(0)
     prof = read_profile(L, psteps)
     L.wap_profile_reset()
-    eng.use_graphs = not args.no_graphs
+    eng.use_graphs = graphs
     decode = None
     if not args.no_decode and args.workload != "cfg3":       # every rank runs it (keeps the ranks in lock-step); rank 0 reports
         decode = decode_leg(env, eng, resident[0][0], B)
@@ -454,7 +456,7 @@ def run_train(args):
                    "parallelism": f"dp{world}" + (" (NCCL all-reduce of 5.4M fp32 grads)" if world > 1 else ""),
                    "l2_flush": "none needed: per-step working set (>= 1.3 GB of saved activations) exceeds the 126 MB L2",
                    "dropout": 0.2, "final_cost": cost, "conv_precision": precision,
-                   "cuda_graph": not args.no_graphs, "graphs_captured": len(eng._graphs)},
+                   "cuda_graph": graphs, "graphs_captured": len(eng._graphs)},
         "clocks": clocks,
         "e2e": {"value": world * images_timed / (ms_e2e * 1e-3), "unit": "images/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                 "ms_per_step": ms_e2e / args.steps,
@@ -491,8 +493,19 @@ def run_cfg5(args):
     env = Env(); torch = env.torch
     n_img = args.images
     eng = wap_b200.WAPEngine(device=env.dev, seed=0, init=True, precision=args.precision or "tf32x3", use_graphs=False)
+    rs = np.random.RandomState(1)                                     # non-degenerate batch-norm terms (the reference initialises gamma ~ 1/sqrt(C),
+    for name, _, shape, _ in eng.P.table:                             # beta = 0, moving statistics (0, 1): the annotation would be ~0 for every image)
+        if name.endswith("/gamma"):
+            eng.P.views[name].copy_(torch.as_tensor(rs.uniform(0.5, 1.5, shape) * rs.choice([-1.0, 1.0], shape), dtype=torch.float32))
+        elif name.endswith(("/beta", "/moving_mean")):
+            eng.P.views[name].copy_(torch.as_tensor(rs.uniform(-0.3, 0.3, shape), dtype=torch.float32))
+        elif name.endswith("/moving_variance"):
+            eng.P.views[name].copy_(torch.as_tensor(rs.uniform(0.5, 1.5, shape), dtype=torch.float32))
     images, captions = synth.synth_crohme(5, n_img)
-    eol_bias = calibrate_eol_bias(eng, images[:48])
+    # Seeded random weights never emit <eol> (their logits settle into a fixed point within a few steps), and the real offline-test.pkl is an
+    # LFS pointer: every image is therefore decoded for the length of ITS synthetic caption + 1 (maxlen_i = len + 1, lengths drawn from the
+    # empirical CROHME caption lengths), i.e. the token counts of a real test set, with the stop decided on the device (<eol> or maxlen_i).
+    maxlens = [min(100, len(c) + 1) for c in captions]
     dev_imgs = [torch.as_tensor(np.moveaxis(im, 0, -1).astype(np.float32) / 255.).unsqueeze(0).to(env.dev) for im in images]
     pinned = [torch.as_tensor(np.ascontiguousarray(im[0])).pin_memory() for im in images]
 
@@ -504,13 +517,13 @@ def run_cfg5(args):
             else:
                 x = dev_imgs[i]
             ann, _ = eng.dense_net(x, None, training=False)
-            toks, lens, _ = eng.greedy_decode(ann, 100)
+            toks, lens, _ = eng.greedy_decode(ann, maxlens[i])
             out.append((toks, lens))
         if from_host:
             return [t[0, : int(n[0])].cpu().tolist() for t, n in out]   # D2H of every result
         return out
     for i in range(min(n_img, 20)):                                   # warm-up
-        ann, _ = eng.dense_net(dev_imgs[i], None, training=False); eng.greedy_decode(ann, 100)
+        ann, _ = eng.dense_net(dev_imgs[i], None, training=False); eng.greedy_decode(ann, maxlens[i])
     torch.cuda.synchronize()
     sampler = ClockSampler(env.local); sampler.start()
     n0 = eng.launch_count()
@@ -534,7 +547,7 @@ def run_cfg5(args):
     for i in sample:
         x64 = torch.as_tensor(np.moveaxis(images[i], 0, -1) / 255., dtype=torch.float64)[None]
         ann_ref, _, _ = O.dense_net(Pt, x64, torch.ones(x64.shape[:3], dtype=torch.float64), False)
-        ref = O.greedy_decode(Pt, ann_ref, 100)
+        ref = O.greedy_decode(Pt, ann_ref, maxlens[i])
         rec[str(i)] = [str(t) for t in seqs[i] if t != 0]; lab[str(i)] = [str(t) for t in ref if t != 0]
         if seqs[i] != ref:
             mism.append({"image": i, "hw": list(images[i].shape[1:]), "first_diff": next((k for k, (a, b) in enumerate(zip(seqs[i], ref)) if a != b),
@@ -549,8 +562,8 @@ def run_cfg5(args):
         "data": "synthetic",
         "config": {"workload": f"cfg5: greedy decode of {n_img} CROHME-distributed synthetic images (SURVEY 8d), one unpadded image at a time, maxlen 100 "
                                "(BASELINE configs[4]); encoder inference + persistent on-device token loop",
-                   "weights": f"seeded reference initialisers; <eol> bias bo[0] raised to {eol_bias:.3f} so that greedy sequences terminate (the real "
-                              "offline-test.pkl is an LFS pointer and random weights never emit <eol>; a genuinely trained checkpoint does not exist)",
+                   "weights": "seeded reference initialisers (lively BN terms); random weights never emit <eol>, so image i is decoded for len(caption_i) + 1 "
+                              "steps (maxlen_i), caption lengths ~ the empirical CROHME lengths; the real offline-test.pkl is an LFS pointer",
                    "tokens": int(ntok), "mean_len": float(lens.mean()), "max_len": int(lens.max()), "hit_maxlen": int((lens >= 100).sum())},
         "clocks": clocks, "us_per_token": ms * 1e3 / max(ntok, 1), "images_per_s": n_img / (ms * 1e-3),
         "e2e": {"value": ntok / (ms_e2e * 1e-3), "unit": "tokens/s", "h2d_bytes_per_step": int(np.mean([im.size for im in images])),
@@ -560,30 +573,6 @@ def run_cfg5(args):
                               "note": "engine token sequences scored against the fp64 CPU oracle's (scorer.py = model-distributed.py:30-78); identity expected"},
     }
     print(json.dumps(line), flush=True)
-
-
-def calibrate_eol_bias(eng, images, target_mean=16.0):
-    """Random-init weights never emit <eol>: raise its output bias until the mean greedy length over a few images is CROHME-like
-    (median caption 13, mean 15.5).  Bisection on bo[0]; deterministic for a given seed."""
-    import numpy as np
-    import torch
-    xs = [torch.as_tensor(np.moveaxis(im, 0, -1).astype(np.float32) / 255.).unsqueeze(0).to(eng.device) for im in images]
-    anns = [eng.dense_net(x, None, training=False)[0] for x in xs]
-    bo = eng.P.views["bo"]
-
-    def mean_len(b):
-        bo[0] = b
-        return float(np.mean([int(eng.greedy_decode(a, 100)[1][0]) for a in anns]))
-    lo, hi = 0.0, 12.0
-    for _ in range(10):
-        mid = 0.5 * (lo + hi)
-        if mean_len(mid) > target_mean:
-            lo = mid
-        else:
-            hi = mid
-    bo[0] = hi
-    log(f"eol bias {hi:.3f}: mean greedy length {mean_len(hi):.1f} over {len(anns)} images")
-    return hi
 
 
 def finish(dist):
