@@ -312,12 +312,24 @@ def decode_leg(env, eng, xd, B):
     bytes_step = 4 * B * Ld * 684 + 4 * B * Ld * 512 + 12 * B * Ld + 4 * 1632496 + 4 * B * 879
     pkd = peaks()
     log(f"decode leg: {us_step:.1f} us/step at B={B}, L={Ld}")
-    return {"us_per_step": us_step, "us_per_token": us_step / B, "tokens_per_s": B / (us_step * 1e-6), "batch": B, "L": Ld,
+    grid_us = None
+    try:                                   # A/B: the grid-wide weight-stationary kernel of round 1 (six grid barriers per token)
+        eng.L.wap_debug_set_greedy_impl(1)
+        eng.greedy_decode(ann, nsteps, ignore_eol=True)
+        e0.record()
+        for _ in range(reps):
+            eng.greedy_decode(ann, nsteps, ignore_eol=True)
+        e1.record(); torch.cuda.synchronize()
+        grid_us = e0.elapsed_time(e1) * 1e3 / (reps * nsteps)
+    finally:
+        eng.L.wap_debug_set_greedy_impl(0)
+    return {"us_per_step": us_step, "kernel": "greedy_cluster_kernel (one 16-CTA cluster per image, DSMEM + cluster barriers)",
+            "us_per_step_grid_wide_persistent_kernel": grid_us, "us_per_token": us_step / B, "tokens_per_s": B / (us_step * 1e-6), "batch": B, "L": Ld,
             "launches_per_step": (eng.launch_count() - n1) / (reps * nsteps),
             "roofline": {"bound": "hbm", "achieved": bytes_step / (us_step * 1e-6) / 1e9, "peak": pkd["hbm_gbs"], "unit": "GB/s",
                          "frac": bytes_step / (us_step * 1e-6) / 1e9 / pkd["hbm_gbs"], "algorithmic_bytes_per_step": bytes_step,
-                         "note": "one persistent cooperative kernel for all 40 steps; includes the one-off precompute (watch GEMM, h0, "
-                                 "weight slicing into shared memory) amortised over the 40 steps"}}
+                         "note": "one kernel for all 40 steps; includes the one-off precompute (watch GEMM, h0, weight slicing into shared "
+                                 "memory) amortised over the 40 steps"}}
 
 
 def run_train(args):

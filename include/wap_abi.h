@@ -112,8 +112,10 @@ int wap_greedy_decode(void* stream, const float* params, const float* annotation
                       int maxlen, int check_every, int32_t* tokens, int32_t* lengths, float* workspace,
                       int* steps_run);
 
-/* ---- the same greedy decode as ONE persistent cooperative kernel (all decoder weights resident in shared
- * memory, grid-wide barriers between the phases of a step, termination decided on the device).
+/* ---- the same greedy decode with the whole token loop on the device and the stop decided there.  Two kernels behind it:
+ * (default, h*w <= 1024) one thread-block cluster of 16 CTAs per image, every per-step exchange through distributed shared memory +
+ * cluster barriers, no grid-wide synchronisation, images independent; (larger grids) ONE persistent cooperative kernel with all decoder
+ * weights resident in shared memory across the grid and grid-wide barriers between the phases of a step.
  * Bn <= 16, h*w <= 2048.  Never synchronises the host; steps_run_dev (device int, may be NULL) receives
  * the number of steps executed.  ignore_eol != 0 (benchmarking): never stop early, always run maxlen steps. */
 int64_t wap_greedy_persistent_workspace_floats(int Bn, int h, int w);
@@ -250,6 +252,9 @@ int wap_debug_tc_trace(long long* trace);
 int wap_debug_trap_info(int* out256);
 /* ---- debug: 0 = the training scan launches the GRU gate kernels separately instead of evaluating them inside the skinny GEMMs */
 int wap_debug_set_fuse_gates(int on);
+/* ---- debug / A-B: which kernel wap_greedy_decode_persistent uses: 0 (default) = one 16-CTA cluster per image, no grid barrier
+ * (csrc/decoder_cluster.cu) whenever the annotation grid fits it, 1 = always the grid-wide weight-stationary kernel (csrc/decoder_persist.cu) */
+int wap_debug_set_greedy_impl(int impl);
 /* ---- weight-gradient kernels on side streams (forked/joined with events inside one call; default on) */
 int wap_set_overlap(int on);
 int wap_get_overlap(void);

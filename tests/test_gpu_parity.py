@@ -341,6 +341,36 @@ def test_train_steps_match_oracle(report):
     assert not fails, fails
 
 
+@pytest.mark.parametrize("B,h,w,maxlen", [(8, 8, 32, 30), (16, 5, 9, 20), (1, 4, 16, 25), (3, 20, 50, 12), (2, 1, 1, 6), (5, 7, 13, 40), (1, 16, 61, 10)])
+def test_greedy_cluster_kernel(report, B, h, w, maxlen):
+    """The cluster-per-image greedy kernel (csrc/decoder_cluster.cu: 16 CTAs per image, DSMEM exchanges, no grid barrier) against the
+    oracle's greedy decode, token for token, and against the grid-wide persistent kernel; an <eol> bias makes the images stop at
+    different steps (each cluster leaves its loop on its own)."""
+    import wap_b200
+    P = dict(O.lively_params(6))
+    P["bo"] = P["bo"].copy(); P["bo"][0] += 2.5
+    eng = engine_with(P)
+    L = wap_b200._lib.lib()
+    ann = _rand_annotation(500 + B * h + w, B, h, w)
+    ann_d = torch.as_tensor(ann).cuda()
+    Pt = O.to_torch(P)
+    try:
+        L.wap_debug_set_greedy_impl(0)
+        toks, lens, steps = eng.greedy_decode(ann_d, maxlen, persistent=True)
+        L.wap_debug_set_greedy_impl(1)
+        toks1, lens1, _ = eng.greedy_decode(ann_d, maxlen, persistent=True)
+    finally:
+        L.wap_debug_set_greedy_impl(0)
+    bad = []
+    for b in range(B):
+        ref = O.greedy_decode(Pt, t64(ann[b:b + 1]), maxlen)
+        got = toks[b, : int(lens[b])].cpu().tolist(); got1 = toks1[b, : int(lens1[b])].cpu().tolist()
+        if got != ref or got1 != ref:
+            bad.append((b, got, got1, ref))
+    report.add("greedy_cluster", f"B{B}_{h}x{w}_T{maxlen}", float(len(bad)), 0.0, extra=dict(mismatch=bad[:2], lens=lens.cpu().tolist()))
+    assert not bad and int(steps[0]) == int(lens.max()), (bad[:2], int(steps[0]), lens.cpu().tolist())
+
+
 @pytest.mark.parametrize("B,h,w", [(8, 8, 32), (16, 5, 9), (1, 4, 16), (3, 20, 50)])
 def test_greedy_persistent_matches_stepwise(report, B, h, w):
     """The single-launch persistent decoder emits exactly the token sequences of the step-by-step kernels

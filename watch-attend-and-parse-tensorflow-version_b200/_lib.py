@@ -82,6 +82,7 @@ SIGNATURES = {
     "wap_debug_tc_trace": (_i, [_vp]),
     "wap_debug_trap_info": (_i, [_vp]),
     "wap_debug_set_fuse_gates": (_i, [_i]),
+    "wap_debug_set_greedy_impl": (_i, [_i]),
     "wap_set_overlap": (_i, [_i]),
     "wap_get_overlap": (_i, []),
     "wap_dropout_mask": (_i, [_vp, _u32, _u32, _i64, _vp]),

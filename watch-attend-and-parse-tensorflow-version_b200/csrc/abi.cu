@@ -351,7 +351,10 @@ int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies
   return 0;
 }
 int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
+extern "C" int wap_debug_set_greedy_impl(int impl);
 int wap_debug_set_fuse_gates(int on) { wap::g_fuse_gates = on ? 1 : 0; return 0; }
+namespace wap { extern int g_greedy_impl; }
+int wap_debug_set_greedy_impl(int impl) { wap::g_greedy_impl = impl; return 0; }
 int wap_set_overlap(int on) { cur()->overlap = on ? 1 : 0; return 0; }
 int wap_get_overlap(void) { return cur()->overlap; }
 int wap_set_pdl(int on) { cur()->pdl = on ? 1 : 0; return 0; }

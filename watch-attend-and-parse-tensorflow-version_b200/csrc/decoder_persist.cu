@@ -624,8 +624,16 @@ static int launch_persistent(cudaStream_t st, const float* params, const float* 
   return 0;
 }
 
+int greedy_decode_cluster(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
+                          int* tokens, int* lengths, float* wsp, int* steps_run_dev);
+int g_greedy_impl = 0;      // wap_debug_set_greedy_impl: 0 = cluster-per-image kernel when the shape allows (default), 1 = always the grid-wide persistent kernel
+
 int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
                              int* tokens, int* lengths, float* wsp, int* steps_run_dev) {
+  if (g_greedy_impl == 0) {
+    const int r = greedy_decode_cluster(st, params, ann, Bn, h, w, maxlen, ignore_eol, tokens, lengths, wsp, steps_run_dev);
+    if (r <= 0) return r;       // 0 done, < 0 error; 1: shape / device not supported by the cluster kernel
+  }
   return launch_persistent(st, params, ann, Bn, h, w, maxlen, ignore_eol, 0, tokens, lengths, nullptr, nullptr, wsp, steps_run_dev);
 }
 
