@@ -21,6 +21,7 @@ int upload_wprep_table();
 extern long long* g_tc_trace;
 extern int g_fuse_gates;
 extern int g_greedy_impl;
+extern int g_cluster_prof;
 const int* trap_note_host();
 SideStreams* side_streams() {
   Context* c = cur();
@@ -353,7 +354,7 @@ int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies
 }
 int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
 int wap_debug_set_fuse_gates(int on) { wap::g_fuse_gates = on ? 1 : 0; return 0; }
-int wap_debug_set_greedy_impl(int impl) { wap::g_greedy_impl = impl; return 0; }
+int wap_debug_set_greedy_impl(int impl) { wap::g_greedy_impl = impl & 1; wap::g_cluster_prof = (impl >> 1) & 1; return 0; }
 int wap_set_overlap(int on) { cur()->overlap = on ? 1 : 0; return 0; }
 int wap_get_overlap(void) { return cur()->overlap; }
 int wap_set_pdl(int on) { cur()->pdl = on ? 1 : 0; return 0; }

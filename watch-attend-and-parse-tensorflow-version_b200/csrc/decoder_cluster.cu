@@ -30,6 +30,7 @@ namespace wap {
 int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
                     float* watch, float* h0, float* qf, float* mean_scratch);
 
+int g_cluster_prof = 0;      // debug: per-stage cycle counters of cluster 0 into the workspace tail
 namespace {
 
 constexpr int kCL = 16;                    // CTAs per cluster (non-portable size: opt-in attribute)
@@ -50,6 +51,7 @@ struct CArgs {
   COff o;
   int H, W, L, maxlen, ignore_eol;
   int* tokens; int* lengths; int* steps_run;     // [rows][maxlen], [rows], max steps over rows (atomicMax)
+  long long* prof;                               // optional [12]: SM cycles of cluster 0 / rank 0 per stage (setup, 1..8, barriers)
 };
 
 // shared-memory carve-up (floats)
@@ -127,7 +129,12 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
   for (int i = tid; i < kN; i += kT) v_h[i] = __ldg(a.h0 + (size_t)row * kN + i);
   int y = -1;                                           // current token (uniform over the cluster)
   int t = 0;
+  long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+  auto mark = [&](int ph) { const long long now = clock64(); pacc[ph] += now - tprev; tprev = now; };
+  auto csync = [&]() { const long long t0 = clock64(); cluster.sync(); const long long t1 = clock64(); pacc[9] += t1 - t0; tprev = t1; };
   cluster.sync();                                       // every CTA of the cluster is running before the first remote store
+  mark(0);
 
   for (; t < a.maxlen; ++t) {
     // ================================================= 1: GRU-1 for the 16 owned units -> pre_h (all-gather)
@@ -150,7 +157,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
       const int dst = tid >> 4, u = tid & 15;
       cluster.map_shared_rank(v_pre, dst)[j0 + u] = own[u * 4 + 0];
     }
-    cluster.sync();
+    mark(1);
+    csync();
     // ================================================= 2: pre_h-side GRU-2 products (resident) + speller columns (streamed) -> sp (all-gather)
     for (int d = warp; d < kUPC * 3; d += kT / 32) {
       const int u = d / 3, q = d - u * 3, j = j0 + u;
@@ -173,7 +181,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     }
     __syncthreads();
     for (int i = tid; i < kSPC * kCL; i += kT) cluster.map_shared_rank(v_sp, i >> 5)[c * kSPC + (i & 31)] = misc[i & 31];
-    cluster.sync();
+    mark(2);
+    csync();
     // ================================================= 3: attention energies of ALL positions for the 32 owned channels (reduce-scatter)
     {
       const int q = lane & 7, slot = warp * 4 + (lane >> 3);          // channel quad (4 channels), tile slot (32 per pass)
@@ -225,7 +234,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
         }
       }
     }
-    cluster.sync();
+    mark(3);
+    csync();
     // ================================================= 4: owner-local softmax pieces (all-gather of u = exp(e - m_local) and of (m, s))
     {
       const int l0 = c * LPC, nown = max(0, min(L, l0 + LPC) - l0);
@@ -243,7 +253,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
       for (int i = tid; i < nown * kCL; i += kT) cluster.map_shared_rank(alpha, i / nown)[l0 + (i % nown)] = misc[i % nown];
       if (tid < kCL) { float* d = cluster.map_shared_rank(ms, tid); d[2 * c] = nown > 0 ? m : -INFINITY; d[2 * c + 1] = s; }
     }
-    cluster.sync();
+    mark(4);
+    csync();
     // ================================================= 5: alpha, alpha_past (every CTA), context slice (all-gather)
     {
       float M = -INFINITY;
@@ -284,7 +295,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
       __syncthreads();
       for (int i = tid; i < nf * 4 * kCL; i += kT) cluster.map_shared_rank(v_ctx, i / (nf * 4))[f0 * 4 + (i % (nf * 4))] = misc[i % (nf * 4)];
     }
-    cluster.sync();
+    mark(5);
+    csync();
     // ================================================= 6: GRU-2 for the owned units (context-side columns streamed) + ctx / emb part of the logits
     {
       // per context row k four 64-byte segments: W_c_z_r[k][j0..] (r), W_c_z_r[k][256 + j0..] (z), W_c_h_nl[k][j0..], Wc[k][n0..];
@@ -322,7 +334,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
       const int dst = tid >> 4, u = tid & 15;
       cluster.map_shared_rank(v_h, dst)[j0 + u] = misc[64 + u];
     }
-    cluster.sync();
+    mark(6);
+    csync();
     // ================================================= 7: emb / h part of the 16 owned logit columns, maxout, partial output logits (all-gather)
     {
       // rows k of Wy (x = emb) and Wh (x = h_t): two 64-byte segments per k; 8 lanes per row, a warp-load covers four rows
@@ -358,7 +371,8 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     }
     __syncthreads();
     for (int i = tid; i < 112 * kCL; i += kT) cluster.map_shared_rank(lpart, i / 112)[c * 112 + (i % 112)] = v_sp2[32 + (i % 112)];
-    cluster.sync();
+    mark(7);
+    csync();
     // ================================================= 8: output logits, arg-max, stop rule (every CTA, redundantly)
     if (warp == 0) {
       float mx = -INFINITY; int am = 0x7fffffff;
@@ -378,10 +392,13 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     }
     __syncthreads();
     y = reinterpret_cast<int*>(misc)[255];
+    mark(8);
     if (c == 0 && tid == 0) a.tokens[(size_t)row * a.maxlen + t] = y;
     if ((y == 0 && !a.ignore_eol) || t == a.maxlen - 1) { ++t; break; }
     __syncthreads();
   }
+  if (c == 0 && tid == 0 && row == 0 && a.prof != nullptr)
+    for (int i = 0; i < 12; ++i) a.prof[i] = pacc[i];
   if (c == 0 && tid == 0) {
     a.lengths[row] = t;
     if (a.steps_run != nullptr) atomicMax(a.steps_run, t);
@@ -400,7 +417,7 @@ bool cluster_decoder_supports(int h, int w) {
 size_t greedy_cluster_ws_floats(int Bn, int L) {
   size_t o = 0;
   auto take = [&](size_t n) { o += (n + 3) & ~(size_t)3; };
-  take((size_t)Bn * L * kNA); take((size_t)kCovTaps * kNA); take((size_t)Bn * kN); take((size_t)Bn * kD); take(4);
+  take((size_t)Bn * L * kNA); take((size_t)kCovTaps * kNA); take((size_t)Bn * kN); take((size_t)Bn * kD); take(32);
   return o;
 }
 
@@ -429,7 +446,9 @@ int greedy_decode_cluster(cudaStream_t st, const float* params, const float* ann
   auto take = [&](size_t n) { float* p = wsp + o; o += (n + 3) & ~(size_t)3; return p; };
   float* watch = take((size_t)Bn * L * kNA); float* qf = take((size_t)kCovTaps * kNA); float* h0 = take((size_t)Bn * kN);
   float* mean = take((size_t)Bn * kD);
+  long long* prof = reinterpret_cast<long long*>(take(32));
   CArgs a;
+  a.prof = g_cluster_prof ? prof : nullptr;
   a.params = params; a.ann = ann; a.watch = watch; a.qf = qf; a.h0 = h0; a.H = h; a.W = w; a.L = L; a.maxlen = maxlen; a.ignore_eol = ignore_eol;
   a.tokens = tokens; a.lengths = lengths; a.steps_run = steps_run_dev;
   const ParamLayout& P = layout();
