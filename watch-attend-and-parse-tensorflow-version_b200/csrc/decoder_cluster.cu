@@ -61,7 +61,7 @@ constexpr int kQS = kCovTaps * kSPC;       // Q' slice                3872
 constexpr int kWO = (kLPC / 2) * 112;      // Wo rows                  896
 constexpr int kVec = 256 + 256 + 256 + 512 + 688 + 256;   // emb | h | pre_h | sp | ctx | (spare)
 constexpr int kSmemFloatsC = kWA + kWB + kQS + kWO + kVec + kPadC + kMaxLc /*alpha*/ + kCL * kOwnMax /*epart*/ + 2 * kCL /*ms*/ +
-                             kCL * 112 /*lpart*/ + 8 * 64 /*red*/ + 64 /*own gate values*/ + 256 /*misc*/;
+                             kCL * 112 /*lpart*/ + 8 * 64 /*red*/ + 64 /*own gate values*/ + 256 /*misc*/ + 320 /*biases*/;
 
 __device__ __forceinline__ float wdot(const float* x, const float* w, int n, int lane) {
   float s = 0.f;
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
   float* red = lpart + kCL * 112;                       // [8][64]
   float* own = red + 8 * 64;                            // [16][4]: pre_h, g2r, g2z, ph2 of the owned units
   float* misc = own + 64;
+  float* bia = misc + 256;                              // [0,48) GRU-1 r|z|h  [48,96) GRU-2 r|z|h  [96,128) speller  [128,144) logit columns  [144,256) bo  [256] V_a_b
   const int j0 = c * kUPC;                              // first owned hidden unit
   const int n0 = c * kLPC;                              // first owned pre-maxout logit column
 
@@ -127,6 +128,17 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
   }
   for (int i = tid; i < kPadC; i += kT) apad[i] = 0.f;
   for (int i = tid; i < kN; i += kT) v_h[i] = __ldg(a.h0 + (size_t)row * kN + i);
+  if (tid < kUPC) {
+    const int j = j0 + tid;
+    bia[tid] = __ldg(P + o.b_yz_yr + j); bia[16 + tid] = __ldg(P + o.b_yz_yr + kN + j); bia[32 + tid] = __ldg(P + o.b_yh + j);
+    bia[48 + tid] = __ldg(P + o.b_hz_hr_nl + j); bia[64 + tid] = __ldg(P + o.b_hz_hr_nl + kN + j); bia[80 + tid] = __ldg(P + o.b_rh_nl + j);
+    bia[128 + tid] = __ldg(P + o.by + n0 + tid) + __ldg(P + o.bc + n0 + tid) + __ldg(P + o.bh + n0 + tid);
+  }
+  if (tid < kSPC) bia[96 + tid] = __ldg(P + o.W_a_b + c * kSPC + tid);
+  if (tid < 112) bia[144 + tid] = tid < kVocab ? __ldg(P + o.bo + tid) : 0.f;
+  if (tid == 0) bia[256] = __ldg(P + o.V_a_b);
+  // per-thread constants of the attention stage (channel quad q of the 32 owned channels)
+  const float4 att_ub = ldg4(P + o.U_f_b + c * kSPC + (lane & 7) * 4), att_va = ldg4(P + o.V_a + c * kSPC + (lane & 7) * 4);
   int y = -1;                                           // current token (uniform over the cluster)
   int t = 0;
   long long pacc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -138,46 +150,79 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
 
   for (; t < a.maxlen; ++t) {
     // ================================================= 1: GRU-1 for the 16 owned units -> pre_h (all-gather)
+    // streamed weights of stage 2 (the 32 speller columns: rows warp + 8 i) go into registers now; they do not depend on the data
+    float wsp[32];
+    {
+      const float* wcol = P + o.W_a + c * kSPC + lane;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) wsp[i] = __ldg(wcol + (size_t)(warp + 8 * i) * kNA);
+    }
     for (int i = tid; i < kMw; i += kT) v_emb[i] = y >= 0 ? __ldg(P + o.embed + (size_t)y * kMw + i) : 0.f;
     __syncthreads();
-    for (int d = warp; d < kUPC * 6; d += kT / 32) {
-      const int u = d / 6, q = d - u * 6;
-      const float v = wdot(q < 3 ? v_emb : v_h, WA + (u * 6 + q) * kN, kN, lane);
-      if (lane == 0) red[u * 8 + q] = v;
-    }
-    __syncthreads();
-    if (tid < kUPC) {
-      const int j = j0 + tid; const float* r8 = red + tid * 8;
-      const float r = sigmoidf_(r8[0] + r8[3] + __ldg(P + o.b_yz_yr + j)), z = sigmoidf_(r8[1] + r8[4] + __ldg(P + o.b_yz_yr + kN + j));
-      const float prop = tanhf(fmaf(r8[5], r, r8[2] + __ldg(P + o.b_yh + j)));
-      own[tid * 4 + 0] = z * v_h[j] + (1.f - z) * prop;
-    }
-    __syncthreads();
-    {   // 16 values -> 16 CTAs
-      const int dst = tid >> 4, u = tid & 15;
-      cluster.map_shared_rank(v_pre, dst)[j0 + u] = own[u * 4 + 0];
+    {   // warp w owns units 2w, 2w+1: twelve 256-long dot products with independent accumulators, one interleaved butterfly
+      float acc[12];
+#pragma unroll
+      for (int i = 0; i < 12; ++i) acc[i] = 0.f;
+      const float* w0 = WA + (2 * warp) * 6 * kN;
+#pragma unroll
+      for (int k8 = 0; k8 < 8; ++k8) {
+        const int k = lane + 32 * k8;
+        const float xe = v_emb[k], xh = v_h[k];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] = fmaf((i % 6) < 3 ? xe : xh, w0[i * kN + k], acc[i]);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < 12; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+      float ph[2];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int u = 2 * warp + s2; const float* r6 = acc + 6 * s2;
+        const float r = sigmoidf_(r6[0] + r6[3] + bia[u]), z = sigmoidf_(r6[1] + r6[4] + bia[16 + u]);
+        const float prop = tanhf(fmaf(r6[5], r, r6[2] + bia[32 + u]));
+        ph[s2] = z * v_h[j0 + u] + (1.f - z) * prop;
+      }
+      if (lane == 0) { own[(2 * warp) * 4] = ph[0]; own[(2 * warp + 1) * 4] = ph[1]; }
+      if (lane < kCL) { float* d = cluster.map_shared_rank(v_pre, lane); d[j0 + 2 * warp] = ph[0]; d[j0 + 2 * warp + 1] = ph[1]; }
     }
     mark(1);
     csync();
-    // ================================================= 2: pre_h-side GRU-2 products (resident) + speller columns (streamed) -> sp (all-gather)
-    for (int d = warp; d < kUPC * 3; d += kT / 32) {
-      const int u = d / 3, q = d - u * 3, j = j0 + u;
-      const float v = wdot(v_pre, WB + (u * 3 + q) * kN, kN, lane);
-      if (lane == 0) own[u * 4 + 1 + q] = v + (q == 0 ? __ldg(P + o.b_hz_hr_nl + j) : q == 1 ? __ldg(P + o.b_hz_hr_nl + kN + j) : __ldg(P + o.b_rh_nl + j));
-    }
-    {   // sp[32c + lane] = sum_k pre_h[k] W_a[k][32c + lane]: warp w takes rows k = w, w+8, ...; one coalesced 128-byte row segment per load
-      const float* wcol = P + o.W_a + c * kSPC + lane;
-      float acc = 0.f;
-#pragma unroll 8
-      for (int k = warp; k < kN; k += kT / 32) acc = fmaf(v_pre[k], __ldg(wcol + (size_t)k * kNA), acc);
-      red[warp * 64 + lane] = acc;
+    // ================================================= 2: pre_h-side GRU-2 products (resident) + speller columns (registers) -> sp (all-gather)
+    {
+      float acc[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) acc[i] = 0.f;
+      const float* w0 = WB + (2 * warp) * 3 * kN;
+#pragma unroll
+      for (int k8 = 0; k8 < 8; ++k8) {
+        const int k = lane + 32 * k8;
+        const float x = v_pre[k];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[i] = fmaf(x, w0[i * kN + k], acc[i]);
+      }
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+        for (int i = 0; i < 6; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+      if (lane == 0) {
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          const int u = 2 * warp + s2;
+          own[u * 4 + 1] = acc[3 * s2 + 0] + bia[48 + u]; own[u * 4 + 2] = acc[3 * s2 + 1] + bia[64 + u]; own[u * 4 + 3] = acc[3 * s2 + 2] + bia[80 + u];
+        }
+      }
+      float sacc = 0.f;                                    // sp[32c + lane]: rows warp + 8 i of W_a held in wsp
+#pragma unroll
+      for (int i = 0; i < 32; ++i) sacc = fmaf(v_pre[warp + 8 * i], wsp[i], sacc);
+      red[warp * 64 + lane] = sacc;
     }
     __syncthreads();
     if (tid < kSPC) {
-      float s = __ldg(P + o.W_a_b + c * kSPC + tid);
+      float s2 = bia[96 + tid];
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 64 + tid];
-      misc[tid] = s;
+      for (int w8 = 0; w8 < 8; ++w8) s2 += red[w8 * 64 + tid];
+      misc[tid] = s2;
     }
     __syncthreads();
     for (int i = tid; i < kSPC * kCL; i += kT) cluster.map_shared_rank(v_sp, i >> 5)[c * kSPC + (i & 31)] = misc[i & 31];
@@ -188,7 +233,7 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
       const int q = lane & 7, slot = warp * 4 + (lane >> 3);          // channel quad (4 channels), tile slot (32 per pass)
       const int tiles_x = W8 >> 3, ntiles = Hd * tiles_x;
       const int ch = c * kSPC + q * 4;
-      const float4 ub = ldg4(P + o.U_f_b + ch), va = ldg4(P + o.V_a + ch);
+      const float4 ub = att_ub, va = att_va;
       const float4 sp4 = *reinterpret_cast<const float4*>(v_sp + ch);
       for (int tb = 0; tb < ntiles; tb += 32) {
         const int tile = tb + slot;
@@ -237,11 +282,21 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     mark(3);
     csync();
     // ================================================= 4: owner-local softmax pieces (all-gather of u = exp(e - m_local) and of (m, s))
+    // streamed weights of stage 6: per context row k four 64-byte segments - W_c_z_r[k][j0..] (r), W_c_z_r[k][256 + j0..] (z), W_c_h_nl[k][j0..],
+    // Wc[k][n0..]; 16 lanes (4 segments x 4 float4) cover a row, a warp-load two rows; thread rows k = 2 warp + sub + 16 i, i < 43.  The first
+    // 16 of the 43 float4 of a thread are requested here (stages 4-5 are short and light on registers), the rest inside stage 6.
+    const int s6_sub = lane >> 4, s6_seg = (lane >> 2) & 3, s6_qd = lane & 3;
+    const float* s6_base = (s6_seg == 0 ? P + o.W_c_z_r + j0 : s6_seg == 1 ? P + o.W_c_z_r + kN + j0 : s6_seg == 2 ? P + o.W_c_h_nl + j0 : P + o.Wc + n0) + s6_qd * 4;
+    const int s6_ld = s6_seg < 2 ? 2 * kN : s6_seg == 2 ? kN : kMw;
+    const int s6_k0 = warp * 2 + s6_sub;
+    float4 wq_a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) wq_a[i] = ldg4(s6_base + (size_t)(s6_k0 + 16 * i) * s6_ld);
     {
       const int l0 = c * LPC, nown = max(0, min(L, l0 + LPC) - l0);
       float e = -INFINITY;
       if (tid < nown) {
-        e = __ldg(P + o.V_a_b);
+        e = bia[256];
 #pragma unroll
         for (int r = 0; r < kCL; ++r) e += epart[r * kOwnMax + tid];
       }
@@ -298,22 +353,38 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     mark(5);
     csync();
     // ================================================= 6: GRU-2 for the owned units (context-side columns streamed) + ctx / emb part of the logits
+    // stage 7's streamed weights (rows k = 4 warp + sub + 32 i of Wy | Wh, two 64-byte segments per row) are requested first
+    const int s7_sub = lane >> 3, s7_seg = (lane >> 2) & 1, s7_qd = lane & 3;
+    float4 wq_l[8];
     {
-      // per context row k four 64-byte segments: W_c_z_r[k][j0..] (r), W_c_z_r[k][256 + j0..] (z), W_c_h_nl[k][j0..], Wc[k][n0..];
-      // 16 lanes (4 segments x 4 float4) cover a row, a warp-load covers two rows
-      const int sub = lane >> 4, seg = (lane >> 2) & 3, qd = lane & 3;
-      const float* base = seg == 0 ? P + o.W_c_z_r + j0 : seg == 1 ? P + o.W_c_z_r + kN + j0 : seg == 2 ? P + o.W_c_h_nl + j0 : P + o.Wc + n0;
-      const int ldw = seg < 2 ? 2 * kN : seg == 2 ? kN : kMw;
+      const float* b7 = (s7_seg == 0 ? P + o.Wy : P + o.Wh) + n0 + s7_qd * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) wq_l[i] = ldg4(b7 + (size_t)(warp * 4 + s7_sub + 32 * i) * kMw);
+    }
+    {
       float4 acc = make4(0.f);
-#pragma unroll 8
-      for (int k = warp * 2 + sub; k < kD; k += 16) {
-        const float4 wv = ldg4(base + (size_t)k * ldw + qd * 4);
+      auto fma4 = [&](const float4& wv, int k) {
         const float xv = v_ctx[k];
         acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+      };
+      float4 wq_b[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) wq_b[i] = ldg4(s6_base + (size_t)(s6_k0 + 16 * (16 + i)) * s6_ld);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) fma4(wq_a[i], s6_k0 + 16 * i);
+      float4 wq_c[11];
+#pragma unroll
+      for (int i = 0; i < 11; ++i) {
+        const int k = s6_k0 + 16 * (32 + i);
+        wq_c[i] = k < kD ? ldg4(s6_base + (size_t)k * s6_ld) : make4(0.f);
       }
+#pragma unroll
+      for (int i = 0; i < 16; ++i) fma4(wq_b[i], s6_k0 + 16 * (16 + i));
+#pragma unroll
+      for (int i = 0; i < 11; ++i) { const int k = s6_k0 + 16 * (32 + i); if (k < kD) fma4(wq_c[i], k); }
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
       acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-      if (sub == 0) *reinterpret_cast<float4*>(&red[warp * 64 + seg * 16 + qd * 4]) = acc;
+      if (s6_sub == 0) *reinterpret_cast<float4*>(&red[warp * 64 + s6_seg * 16 + s6_qd * 4]) = acc;
     }
     __syncthreads();
     if (tid < 64) {
@@ -337,27 +408,23 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     mark(6);
     csync();
     // ================================================= 7: emb / h part of the 16 owned logit columns, maxout, partial output logits (all-gather)
-    {
-      // rows k of Wy (x = emb) and Wh (x = h_t): two 64-byte segments per k; 8 lanes per row, a warp-load covers four rows
-      const int sub = lane >> 3, seg = (lane >> 2) & 1, qd = lane & 3;
-      const float* base = (seg == 0 ? P + o.Wy : P + o.Wh) + n0;
-      const float* xv_ = seg == 0 ? v_emb : v_h;
+    {   // rows k of Wy (x = emb) and Wh (x = h_t), weights already in registers (wq_l)
+      const float* xv_ = s7_seg == 0 ? v_emb : v_h;
       float4 acc = make4(0.f);
-#pragma unroll 8
-      for (int k = warp * 4 + sub; k < kN; k += 32) {
-        const float4 wv = ldg4(base + (size_t)k * kMw + qd * 4);
-        const float xv = xv_[k];
-        acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y); acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xv = xv_[warp * 4 + s7_sub + 32 * i];
+        acc.x = fmaf(xv, wq_l[i].x, acc.x); acc.y = fmaf(xv, wq_l[i].y, acc.y); acc.z = fmaf(xv, wq_l[i].z, acc.z); acc.w = fmaf(xv, wq_l[i].w, acc.w);
       }
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 8); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 8);
       acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 8); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 8);
       acc.x += __shfl_xor_sync(0xffffffffu, acc.x, 16); acc.y += __shfl_xor_sync(0xffffffffu, acc.y, 16);
       acc.z += __shfl_xor_sync(0xffffffffu, acc.z, 16); acc.w += __shfl_xor_sync(0xffffffffu, acc.w, 16);
-      if (sub == 0) *reinterpret_cast<float4*>(&red[warp * 64 + seg * 16 + qd * 4]) = acc;
+      if (s7_sub == 0) *reinterpret_cast<float4*>(&red[warp * 64 + s7_seg * 16 + s7_qd * 4]) = acc;
     }
     __syncthreads();
     if (tid < kLPC) {
-      float s = misc[48 + tid] + __ldg(P + o.by + n0 + tid) + __ldg(P + o.bc + n0 + tid) + __ldg(P + o.bh + n0 + tid);
+      float s = misc[48 + tid] + bia[128 + tid];
 #pragma unroll
       for (int w8 = 0; w8 < 8; ++w8) s += red[w8 * 64 + tid] + red[w8 * 64 + 16 + tid];
       v_sp2[tid] = s;                                          // pre-maxout logit n0 + tid
@@ -377,7 +444,7 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
     if (warp == 0) {
       float mx = -INFINITY; int am = 0x7fffffff;
       for (int j = lane; j < kVocab; j += 32) {
-        float v = __ldg(P + o.bo + j);
+        float v = bia[144 + j];
 #pragma unroll
         for (int r = 0; r < kCL; ++r) v += lpart[r * 112 + j];
         if (v > mx) { mx = v; am = j; }
