@@ -341,7 +341,26 @@ def test_train_steps_match_oracle(report):
     assert not fails, fails
 
 
-@pytest.mark.parametrize("B,h,w,maxlen", [(8, 8, 32, 30), (16, 5, 9, 20), (1, 4, 16, 25), (3, 20, 50, 12), (2, 1, 1, 6), (5, 7, 13, 40), (1, 16, 61, 10)])
+@pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
+def test_inference_bn_fold_is_bit_identical(precision):
+    """Inference encoder with batch norm + ReLU folded into the conv epilogues (default) == the conv -> bn_act kernel sequence, bit for bit
+    (same scale / shift expressions), at roughly half the launches."""
+    import wap_b200
+    x, xm, _, _ = make_batch(21, 2, 50, 150, 3, True)
+    P = O.calibrate_moving(O.lively_params(4), x, xm)
+    eng = engine_with(P, precision=precision)
+    L = wap_b200._lib.lib()
+    n0 = eng.launch_count(); a_fused, _ = eng.dense_net(x, xm, training=False); n1 = eng.launch_count()
+    try:
+        L.wap_debug_set_tc_mask(0x1FF)
+        a_plain, _ = eng.dense_net(x, xm, training=False); n2 = eng.launch_count()
+    finally:
+        L.wap_debug_set_tc_mask(0x3FF)
+    assert torch.equal(a_fused, a_plain)
+    assert (n1 - n0) <= (n2 - n1) - 90, (n1 - n0, n2 - n1)
+
+
+@pytest.mark.parametrize("B,h,w,maxlen", [(7, 8, 32, 30), (8, 8, 32, 30), (16, 5, 9, 20), (1, 4, 16, 25), (3, 20, 50, 12), (2, 1, 1, 6), (5, 7, 13, 40), (1, 16, 61, 10)])
 def test_greedy_cluster_kernel(report, B, h, w, maxlen):
     """The cluster-per-image greedy kernel (csrc/decoder_cluster.cu: 16 CTAs per image, DSMEM exchanges, no grid barrier) against the
     oracle's greedy decode, token for token, and against the grid-wide persistent kernel; an <eol> bias makes the images stop at

@@ -630,7 +630,10 @@ int g_greedy_impl = 0;      // wap_debug_set_greedy_impl: 0 = cluster-per-image 
 
 int greedy_decode_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol,
                              int* tokens, int* lengths, float* wsp, int* steps_run_dev) {
-  if (g_greedy_impl == 0) {
+  // One 16-CTA cluster per image, no grid barrier: 25 us per token step however many images run side by side - but only 7 such
+  // clusters are co-resident on a B200 (cudaOccupancyMaxActiveClusters), so a batch of 8+ images would take a second wave (2 x 25 us
+  // > the 44.5 us per step of the grid-wide kernel below, whose step time does not grow up to 16 images).
+  if (g_greedy_impl == 0 && Bn <= 7) {
     const int r = greedy_decode_cluster(st, params, ann, Bn, h, w, maxlen, ignore_eol, tokens, lengths, wsp, steps_run_dev);
     if (r <= 0) return r;       // 0 done, < 0 error; 1: shape / device not supported by the cluster kernel
   }

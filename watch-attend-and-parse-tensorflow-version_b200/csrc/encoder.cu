@@ -181,8 +181,26 @@ __global__ void __launch_bounds__(256) prep_conv_weights_kernel(const float* __r
   }
 }
 
+// Inference: batch norm with moving statistics is an affine map per channel, folded into the conv epilogue of the tensor-core paths:
+// scale = gamma / sqrt(moving_var + eps), shift = beta - moving_mean * scale (same expressions and rounding as bn_prologue, so the fused
+// result equals conv -> bn_act bit for bit).  One launch for all 99 layers into the (unused in inference) `saved` region: [k][2][kMaxBnC].
+struct BnFoldLayer { int cout; long long gamma, beta, mmean, mvar; };
+__constant__ BnFoldLayer c_bnfold[kNumConv];
+__global__ void __launch_bounds__(128) bn_fold_kernel(const float* __restrict__ params, const float* __restrict__ moving, float* __restrict__ out) {
+  pdl_sync();
+  const BnFoldLayer L = c_bnfold[blockIdx.x];
+  float* o = out + (size_t)blockIdx.x * 2 * kMaxBnC;
+  for (int c = threadIdx.x; c < L.cout; c += blockDim.x) {
+    const double mean = moving[L.mmean + c], var = moving[L.mvar + c];
+    const float invstd = (float)(1.0 / sqrt(var + (double)kBnEps));
+    const float sc = __ldg(params + L.gamma + c) * invstd;
+    o[c] = sc;
+    o[kMaxBnC + c] = __ldg(params + L.beta + c) - (float)mean * sc;
+  }
+}
+
 int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
-int g_tc_debug_mask = 0x1FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd
+int g_tc_debug_mask = 0x3FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd, bit8 row-tile 3x3, bit9 inference BN folded into the conv epilogues
 void set_conv_precision(int mode) { cur()->precision = mode; }
 int get_conv_precision() { return cur()->precision; }
 
@@ -202,7 +220,19 @@ int upload_wprep_table() {
     h[i].fl = (long long)ws.wt_fwd_lo[i]; h[i].bl = (long long)ws.wt_bwd_lo[i];
   }
   WAP_CHECK(cudaMemcpyToSymbol(c_wprep, h, sizeof(h), 0, cudaMemcpyHostToDevice));
+  BnFoldLayer f[kNumConv];
+  for (int i = 0; i < kNumConv; ++i) {
+    f[i].cout = L.conv[i].cout; f[i].gamma = (long long)L.conv[i].gamma; f[i].beta = (long long)L.conv[i].beta;
+    f[i].mmean = (long long)L.conv[i].mmean; f[i].mvar = (long long)L.conv[i].mvar;
+  }
+  WAP_CHECK(cudaMemcpyToSymbol(c_bnfold, f, sizeof(f), 0, cudaMemcpyHostToDevice));
   uploaded = true;
+  return 0;
+}
+int bn_fold(cudaStream_t st, const float* params, const float* moving, float* out) {
+  WAP_TRY(upload_wprep_table());
+  WAP_CHECK(launch_pdl(bn_fold_kernel, kNumConv, 128, 0, st, params, moving, out));
+  WAP_LAUNCH_CHECK();
   return 0;
 }
 
@@ -298,6 +328,10 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
   }
   auto lo = [&](size_t off) -> const float* { return x3 ? wsp + off : nullptr; };
   float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
+  // inference in the 3xTF32 mode: batch norm + ReLU of the dense levels folded into the conv epilogues (no bn_act launches, no y1 / y2 round trip)
+  const bool fold = !training && x3 && (g_tc_debug_mask & 512);
+  if (fold) WAP_TRY(bn_fold(st, params, moving, saved));
+  auto fsc = [&](int kk) -> const float* { return saved + (size_t)kk * 2 * kMaxBnC; };
   auto bn_args = [&](int k, const float* raw, int Hi, int Wi, float* out, int Ho, int Wo, int ld_out, bool drop) {
     const ConvLayer& c = L.conv[k];
     BnActArgs a;
@@ -331,7 +365,10 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
       float* y1 = wsp + ws.y1[k]; float* a1 = wsp + ws.a1[k]; float* y2 = wsp + ws.y2[k + 1];
       {   // 1x1 bottleneck  C -> 96
         double* sk = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
-        if (tc) {
+        if (fold) {
+          WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, kBottle, C,
+                          TcEpi{a1, kBottle, 0, nullptr, nullptr, 0, 0, fsc(k), fsc(k) + kMaxBnC}, kProfConv1Fwd));
+        } else if (tc) {
           WAP_TRY(tc_gemm(st, buf[b], ld, wsp + ws.wt_fwd[k], lo(ws.wt_fwd_lo[k]), C, M, kBottle, C, TcEpi{y1, kBottle, 0, sk, nullptr, 0}, kProfConv1Fwd));
         } else {
           ARowMajor A{buf[b], ld, M, C};
@@ -339,11 +376,17 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
           EpiStore e{y1, kBottle, nullptr, false, sk};
           WAP_TRY((launch_gemm<Cfg128x96>(st, A, Bw, e, M, kBottle, C, 1, kProfConv1Fwd)));
         }
-        WAP_TRY(run_bn_act(st, 0, bn_args(k, y1, h, w, a1, h, w, kBottle, true)));
+        if (!fold) WAP_TRY(run_bn_act(st, 0, bn_args(k, y1, h, w, a1, h, w, kBottle, true)));
       }
       {   // 3x3 growth  96 -> 24, written in place at channel offset C
         double* sk = training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr;
-        if (tc) {
+        if (fold) {
+          const TcEpi e3{buf[b] + C, ld, 0, nullptr, nullptr, 0, 0, fsc(k + 1), fsc(k + 1) + kMaxBnC};     // activated output straight into the block buffer
+          if ((rowtile_blocks >> b) & 1)
+            WAP_TRY(tc_conv3x3_rowtile(st, a1, kBottle, B, h, w, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), e3, kProfConv3Fwd));
+          else
+            WAP_TRY(tc_conv3x3(st, a1, kBottle, B, h, w, kBottle, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), 32, kGrowth, e3, kProfConv3Fwd));
+        } else if (tc) {
           if ((rowtile_blocks >> b) & 1)
             WAP_TRY(tc_conv3x3_rowtile(st, a1, kBottle, B, h, w, wsp + ws.wt_fwd[k + 1], lo(ws.wt_fwd_lo[k + 1]), TcEpi{y2, kGrowth, 0, sk, nullptr, 0}, kProfConv3Fwd));
           else
@@ -354,7 +397,7 @@ int encoder_forward(cudaStream_t st, const float* params, float* moving, const f
           EpiStore e{y2, kGrowth, nullptr, false, sk};
           WAP_TRY((launch_gemm<Cfg256x24>(st, A, Bw, e, M, kGrowth, 9 * kBottle, 1, kProfConv3Fwd)));
         }
-        WAP_TRY(run_bn_act(st, 0, bn_args(k + 1, y2, h, w, buf[b] + C, h, w, ld, true)));
+        if (!fold) WAP_TRY(run_bn_act(st, 0, bn_args(k + 1, y2, h, w, buf[b] + C, h, w, ld, true)));
       }
       C += kGrowth;
     }

@@ -24,6 +24,7 @@ using bf16 = __nv_bfloat16;
 int run_stem_conv(cudaStream_t st, const float* x, const float* w, float* out, double* stats, int B, int H, int W, const EncGeom& g);
 int run_stem_wgrad(cudaStream_t st, const float* x, const float* gstem, float* dw, int B, int H, int W, const EncGeom& g);
 int upload_wprep_table();
+int bn_fold(cudaStream_t st, const float* params, const float* moving, float* out);
 extern int g_tc_debug_mask;
 
 constexpr int kLd2 = 688;                 // row stride (elements) of the bf16 block-2 buffer
@@ -137,6 +138,10 @@ int encoder_forward_bf16(cudaStream_t st, const float* params, float* moving, co
   WAP_TRY(prep_conv_weights_bf16(st, params, wsp, training != 0, rowtile_blocks));
   bf16* buf[kBlocks] = {B16(wsp, ws.buf[0]), B16(wsp, ws.buf[1]), B16(wsp, ws.buf[2])};
   const int ldb[kBlocks] = {g.Ctot[0], g.Ctot[1], kLd2};
+  // inference: batch norm + ReLU of the dense levels folded into the conv epilogues (see encoder.cu bn_fold_kernel)
+  const bool fold = !training && (g_tc_debug_mask & 512);
+  if (fold) WAP_TRY(bn_fold(st, params, moving, saved));
+  auto fsc = [&](int kk) -> const float* { return saved + (size_t)kk * 2 * kMaxBnC; };
   auto bn_args = [&](int k, const void* raw, int Hi, int Wi, void* out, int Ho, int Wo, int ld_out, bool drop) {
     const ConvLayer& c = L.conv[k];
     BnActArgs a;
@@ -161,6 +166,15 @@ int encoder_forward_bf16(cudaStream_t st, const float* params, float* moving, co
       bf16* y1 = B16(wsp, ws.y1[k]); bf16* a1 = B16(wsp, ws.a1[k]); bf16* y2 = B16(wsp, ws.y2[k + 1]);
       double* s1 = training ? stats + (size_t)k * 2 * kMaxBnC : nullptr;
       double* s3 = training ? stats + (size_t)(k + 1) * 2 * kMaxBnC : nullptr;
+      if (fold) {
+        WAP_TRY(tc_gemm_bf16(st, buf[b], ld, B16(wsp, ws.wt_fwd[k]), pad8(C), M, kBottle, C,
+                             TcEpi{reinterpret_cast<float*>(a1), kBottle, 0, nullptr, nullptr, 0, 1, fsc(k), fsc(k) + kMaxBnC}, kProfConv1Fwd));
+        const TcEpi e3{reinterpret_cast<float*>(buf[b] + C), ld, 0, nullptr, nullptr, 0, 1, fsc(k + 1), fsc(k + 1) + kMaxBnC};
+        if ((rowtile_blocks >> b) & 1) WAP_TRY(tc_conv3x3_rowtile_bf16(st, a1, kBottle, B, h, w, B16(wsp, ws.wt_fwd[k + 1]), e3, kProfConv3Fwd));
+        else WAP_TRY(tc_conv3x3_bf16(st, a1, kBottle, B, h, w, kBottle, B16(wsp, ws.wt_fwd[k + 1]), 32, kGrowth, e3, kProfConv3Fwd));
+        C += kGrowth;
+        continue;
+      }
       WAP_TRY(tc_gemm_bf16(st, buf[b], ld, B16(wsp, ws.wt_fwd[k]), pad8(C), M, kBottle, C, TcEpi{reinterpret_cast<float*>(y1), kBottle, 0, s1, nullptr, 0, 1}, kProfConv1Fwd));
       WAP_TRY((run_bn_act<bf16, bf16>(st, 0, bn_args(k, y1, h, w, a1, h, w, kBottle, true))));
       if ((rowtile_blocks >> b) & 1)

@@ -275,6 +275,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (epi.stats != nullptr)
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
+  if (epi.bn_scale != nullptr)      // folded inference batch norm: scale | shift of this tile's columns
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+      const bool ok = n0 + i < sh.N;
+      s_stat[i] = ok ? __ldg(epi.bn_scale + n0 + i) : 0.f; s_stat[BN + i] = ok ? __ldg(epi.bn_shift + n0 + i) : 0.f;
+    }
   if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
   tc_fence_before();
   __syncthreads();
@@ -421,6 +426,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll
       for (int c = kG; c < 32; ++c) o[c] = 0.f;
+      if (epi.bn_scale != nullptr) {
+#pragma unroll
+        for (int c = 0; c < kG; ++c) o[c] = fmaxf(fmaf(o[c], s_stat[c], s_stat[BN + c]), 0.f);
+      }
       if (valid) {
         if (epi.out_bf16) {
           uint8_t* dst = reinterpret_cast<uint8_t*>(epi.out) + (mrow * epi.ld) * 2;
@@ -469,6 +478,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (epi.bias != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) v[j] += __ldg(epi.bias + n0 + c + j);
+      }
+      if (epi.bn_scale != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], s_stat[c + j], s_stat[BN + c + j]), 0.f);
       }
       if (valid && epi.transpose_out) {
 #pragma unroll
@@ -957,6 +970,7 @@ int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, flo
 int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
   WAP_REQUIRE(epi.bias == nullptr || epi.stats == nullptr, "tc_gemm: bias and statistics cannot be combined");
   WAP_REQUIRE(!epi.transpose_out || !epi.accumulate, "tc_gemm: transposed store cannot accumulate");
+  WAP_REQUIRE(epi.bn_scale == nullptr || (epi.stats == nullptr && !epi.accumulate && !epi.transpose_out && epi.bias == nullptr), "tc_gemm: folded batch norm is store-only");
   WAP_REQUIRE((lda & 3) == 0 && (ldb & 3) == 0 && ((epi.ld & 3) == 0 || epi.transpose_out), "tc_gemm: strides must be multiples of 4 floats");
   WAP_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)Bt & 15) == 0 && ((uintptr_t)epi.out & 15) == 0, "tc_gemm: pointers must be 16-byte aligned");
   CUtensorMap ta, tb, tbl;
@@ -1050,6 +1064,7 @@ int tc_gemm_bf16(cudaStream_t st, const void* A, int lda, const void* Bt, int ld
   WAP_REQUIRE(kTcRowB == 128, "bf16 kernels need 128-byte stage rows");
   WAP_REQUIRE((lda & 7) == 0 && (ldb & 7) == 0 && (epi.ld & 3) == 0, "tc_gemm_bf16: operand strides must be multiples of 16 bytes, the output stride of 4 elements (lda=%d ldb=%d ldd=%d)", lda, ldb, epi.ld);
   WAP_REQUIRE(!(epi.out_bf16 && (epi.accumulate || epi.transpose_out || epi.bias)), "tc_gemm_bf16: bf16 output is store-only");
+  WAP_REQUIRE(epi.bn_scale == nullptr || (epi.stats == nullptr && !epi.accumulate && !epi.transpose_out && epi.bias == nullptr), "tc_gemm_bf16: folded batch norm is store-only");
   CUtensorMap ta, tb;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)lda * 2}; const uint32_t box[2] = {kBfK, kTcBM};

@@ -36,6 +36,8 @@ struct TcEpi {
   const float* bias;         // optional [N] added to the stored value (not to the statistics)
   int transpose_out;         // store D[m,n] at out[n*ld + m] (coalesced: one TMEM lane = one row m per thread)
   int out_bf16;              // `out` points to bf16 elements (ld in elements); store only (no accumulate / transpose / bias)
+  const float* bn_scale;     // inference-mode batch norm folded into the epilogue: D = relu(acc * bn_scale[n] + bn_shift[n]) (both [N]); with
+  const float* bn_shift;     //   statistics == nullptr, no accumulate / transpose / bias
 };
 
 // Bt_hi/lo[N][K] = split(transpose(W[K][N])) (transpose != 0) or split(W[N][K]) : operand preparation for tc_gemm's 3xTF32 mode
