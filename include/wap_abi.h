@@ -240,6 +240,12 @@ int wap_tc_wgrad_3x3_bf16(void* stream, const void* X, int ldx, const void* dY, 
  * the by-value behaviour.  Per handle. */
 int wap_set_dropout_seed_source(const uint32_t* seed_dev);
 
+/* ---- decoding with frozen weights: qfused != NULL (a [121,512] buffer filled by wap_attn_precompute) makes wap_greedy_decode_persistent /
+ * wap_beam_decode_persistent use it instead of recomputing Q' = alpha_past_filter * U_f (63 MFLOP) at every call - the reference decodes
+ * ~1000 validation images one by one with the same weights (S:661-683).  The caller must pass NULL again (or refresh the buffer) before the
+ * weights change.  Per handle. */
+int wap_set_fused_coverage_filter(const float* qfused);
+
 /* ---- programmatic dependent launch (default on): kernels are launched with the programmatic-stream-serialization
  * attribute so that launch latency overlaps the predecessor's execution; 0 restores plain stream ordering. */
 int wap_set_pdl(int on);

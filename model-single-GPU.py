@@ -99,7 +99,7 @@ def main(args):
             if uidx % sampleFreq == 0:
                 dp.sync_moving_stats(eng.P.moving)
             if uidx % sampleFreq == 0 and rank == 0:
-                with open(args.path + '/result/valid_decode_result-bs-6.txt', 'w') as fpp:
+                with open(args.path + '/result/valid_decode_result-bs-6.txt', 'w') as fpp, eng.decoding():
                     idx = 0
                     for vx, _ in valid:
                         for xx in vx:

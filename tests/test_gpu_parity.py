@@ -341,6 +341,23 @@ def test_train_steps_match_oracle(report):
     assert not fails, fails
 
 
+def test_decoding_context_caches_the_fused_coverage_filter():
+    """WAPEngine.decoding(): Q' = Q*U_f computed once and handed to the decode kernels (wap_set_fused_coverage_filter) - same tokens and
+    beam samples as the per-call recomputation, for the cluster kernel (B <= 7), the grid-wide kernel and the beam search."""
+    P = dict(O.lively_params(6)); P["bo"] = P["bo"].copy(); P["bo"][0] += 2.5
+    eng = engine_with(P)
+    for B in (3, 9):
+        ann = torch.as_tensor(_rand_annotation(900 + B, B, 6, 20)).cuda()
+        t0, l0, _ = eng.greedy_decode(ann, 20)
+        with eng.decoding():
+            t1, l1, _ = eng.greedy_decode(ann, 20)
+            b1 = eng.get_sample(ann[:1], 5, 15)
+        b0 = eng.get_sample(ann[:1], 5, 15)
+        assert torch.equal(t0, t1) and torch.equal(l0, l1)
+        assert b0[1] == b1[1] and np.allclose(b0[2], b1[2], rtol=1e-6)
+    assert not eng.L.wap_current() is None
+
+
 @pytest.mark.parametrize("precision", ["tf32x3", "bf16"])
 def test_inference_bn_fold_is_bit_identical(precision):
     """Inference encoder with batch norm + ReLU folded into the conv epilogues (default) == the conv -> bn_act kernel sequence, bit for bit

@@ -77,6 +77,7 @@ SIGNATURES = {
     "wap_tc_wgrad_1x1_bf16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i]),
     "wap_tc_wgrad_3x3_bf16": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp, _i]),
     "wap_set_dropout_seed_source": (_i, [_vp]),
+    "wap_set_fused_coverage_filter": (_i, [_vp]),
     "wap_set_pdl": (_i, [_i]),
     "wap_get_pdl": (_i, []),
     "wap_debug_tc_trace": (_i, [_vp]),

@@ -360,6 +360,7 @@ int wap_get_overlap(void) { return cur()->overlap; }
 int wap_set_pdl(int on) { cur()->pdl = on ? 1 : 0; return 0; }
 int wap_get_pdl(void) { return cur()->pdl; }
 int wap_set_dropout_seed_source(const uint32_t* seed_dev) { cur()->seed_src = seed_dev; return 0; }
+int wap_set_fused_coverage_filter(const float* qfused) { cur()->qf_cached = qfused; return 0; }
 
 /* ---- handles: per-engine state (precision mode, PDL / overlap switches, side streams, dropout-seed source) */
 int wap_create(wap_handle** out) {

@@ -516,7 +516,7 @@ int greedy_decode_cluster(cudaStream_t st, const float* params, const float* ann
   long long* prof = reinterpret_cast<long long*>(take(32));
   CArgs a;
   a.prof = g_cluster_prof ? prof : nullptr;
-  a.params = params; a.ann = ann; a.watch = watch; a.qf = qf; a.h0 = h0; a.H = h; a.W = w; a.L = L; a.maxlen = maxlen; a.ignore_eol = ignore_eol;
+  a.params = params; a.ann = ann; a.watch = watch; a.qf = cur()->qf_cached != nullptr ? cur()->qf_cached : qf; a.h0 = h0; a.H = h; a.W = w; a.L = L; a.maxlen = maxlen; a.ignore_eol = ignore_eol;
   a.tokens = tokens; a.lengths = lengths; a.steps_run = steps_run_dev;
   const ParamLayout& P = layout();
   COff& d = a.o;
@@ -525,7 +525,7 @@ int greedy_decode_cluster(cudaStream_t st, const float* params, const float* ann
   d.U_rh = (int)P.U_rh; d.U_hz_hr_nl = (int)P.U_hz_hr_nl; d.b_hz_hr_nl = (int)P.b_hz_hr_nl; d.W_c_z_r = (int)P.W_c_z_r;
   d.U_rh_nl = (int)P.U_rh_nl; d.b_rh_nl = (int)P.b_rh_nl; d.W_c_h_nl = (int)P.W_c_h_nl; d.embed = (int)P.embed; d.Wc = (int)P.Wc;
   d.bc = (int)P.bc; d.Wh = (int)P.Wh; d.bh = (int)P.bh; d.Wy = (int)P.Wy; d.by = (int)P.by; d.Wo = (int)P.Wo; d.bo = (int)P.bo;
-  WAP_TRY(attn_precompute(st, params, ann, nullptr, Bn, h, w, watch, h0, qf, mean));     // hidden_state_0 is unmasked (S:590)
+  WAP_TRY(attn_precompute(st, params, ann, nullptr, Bn, h, w, watch, h0, cur()->qf_cached != nullptr ? nullptr : qf, mean));     // hidden_state_0 is unmasked (S:590)
   WAP_CHECK(cudaMemsetAsync(lengths, 0, sizeof(int) * Bn, st));
   if (steps_run_dev != nullptr) WAP_CHECK(cudaMemsetAsync(steps_run_dev, 0, sizeof(int), st));
   cudaLaunchConfig_t cfg = {};

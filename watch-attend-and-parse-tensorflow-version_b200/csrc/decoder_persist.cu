@@ -606,7 +606,7 @@ static int launch_persistent(cudaStream_t st, const float* params, const float* 
   a.LOg = take((size_t)2 * Bn * 112);
   float* watch = take((size_t)Bn * L * kNA); float* qf = take((size_t)kCovTaps * kNA); float* h0 = take((size_t)Bn * kN);
   float* mean = take((size_t)Bn * kD);
-  a.watch = watch; a.qf = qf; a.h0 = h0; a.tokens = tokens; a.lengths = lengths; a.steps_run = steps_run_dev;
+  a.watch = watch; a.qf = cur()->qf_cached != nullptr ? cur()->qf_cached : qf; a.h0 = h0; a.tokens = tokens; a.lengths = lengths; a.steps_run = steps_run_dev;
   a.prof = reinterpret_cast<long long*>(a.barrier + 8 * 160);   // 8 x int64 after the barrier slots
   const ParamLayout& P = layout();
   DecOff& d = a.o;
@@ -615,7 +615,7 @@ static int launch_persistent(cudaStream_t st, const float* params, const float* 
   d.U_rh = (int)P.U_rh; d.U_hz_hr_nl = (int)P.U_hz_hr_nl; d.b_hz_hr_nl = (int)P.b_hz_hr_nl; d.W_c_z_r = (int)P.W_c_z_r;
   d.U_rh_nl = (int)P.U_rh_nl; d.b_rh_nl = (int)P.b_rh_nl; d.W_c_h_nl = (int)P.W_c_h_nl; d.embed = (int)P.embed; d.Wc = (int)P.Wc;
   d.bc = (int)P.bc; d.Wh = (int)P.Wh; d.bh = (int)P.bh; d.Wy = (int)P.Wy; d.by = (int)P.by; d.Wo = (int)P.Wo; d.bo = (int)P.bo;
-  WAP_TRY(attn_precompute(st, params, ann, nullptr, nimg, h, w, watch, h0, qf, mean));     // hidden_state_0 is unmasked (S:590)
+  WAP_TRY(attn_precompute(st, params, ann, nullptr, nimg, h, w, watch, h0, cur()->qf_cached != nullptr ? nullptr : qf, mean));     // hidden_state_0 is unmasked (S:590)
   WAP_CHECK(cudaMemsetAsync(a.barrier, 0, (8 * 160 + 24) * sizeof(unsigned), st));
   WAP_CHECK(cudaMemsetAsync(lengths, 0, sizeof(int) * Bn, st));
   void* args[] = {(void*)&a};

@@ -93,6 +93,7 @@ struct Context {
   const uint32_t* seed_src = nullptr;   // device word overriding the by-value dropout seed (CUDA-graph replay draws fresh masks)
   SideStreams ss; int ss_state = 0;  // 0: not created, 1: ok, -1: failed
   bool dec_join_pending = false;     // decoder weight gradients still running on ss.s[1] (wap_train_backward joins them)
+  const float* qf_cached = nullptr;  // wap_set_fused_coverage_filter(): precomputed Q' = Q*U_f used by the decode entry points instead of recomputing it per call
 };
 Context* cur();               // the calling host thread's current context (the process default one unless wap_make_current was called)
 SideStreams* side_streams();  // of the current context; lazily created; nullptr on failure

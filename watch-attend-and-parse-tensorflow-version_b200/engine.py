@@ -345,6 +345,24 @@ class WAPEngine:
             self.step_count = int(z["__step__"])
         return {k[len("__sched__/"):]: z[k] for k in z.files if k.startswith("__sched__/")}
 
+    def decoding(self):
+        """Context manager for decoding many images with FROZEN weights (the validation loop, S:661-683): the fused coverage filter
+        Q' = alpha_past_filter * U_f is computed once and handed to the decode kernels (wap_set_fused_coverage_filter) instead of being
+        recomputed per image.  Do not update / load weights inside the block."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            qf = torch.empty((121, DIM_ATT), dtype=torch.float32, device=self.device)
+            dummy = torch.zeros((1, 1, 1, ANNOT_C), dtype=torch.float32, device=self.device)
+            _lib.check(self.L.wap_attn_precompute(_stream(), _p(self.P.flat), _p(dummy), None, 1, 1, 1, None, None, _p(qf), None), "wap_attn_precompute")
+            self.L.wap_set_fused_coverage_filter(_p(qf))
+            try:
+                yield self
+            finally:
+                self.L.wap_set_fused_coverage_filter(None)
+        return cm()
+
     def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8, persistent: Optional[bool] = None,
                       ignore_eol: bool = False):
         """Greedy decode of every image in the batch; returns (tokens [B,maxlen] int32, lengths [B] int32, steps).
