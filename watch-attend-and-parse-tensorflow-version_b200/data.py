@@ -165,6 +165,7 @@ def pack_batch(images_x: Sequence[np.ndarray], seqs_y: Sequence[Sequence[int]], 
     offs = buf[:off_hw].view(np.int64); hw = buf[off_hw:off_y].view(np.int32)
     y = buf[off_y:off_ym].view(np.int32).reshape(T, B); ym = buf[off_ym:off_ym + 4 * T * B].view(np.float32).reshape(T, B)
     y[:] = 0; ym[:] = 0.
+    buf[off_ym + 4 * T * B: off_pix] = 0                 # alignment padding: deterministic bytes
     o = 0
     for b, (im, seq) in enumerate(zip(images_x, seqs_y)):
         hh, ww, n = int(im.shape[1]), int(im.shape[2]), len(seq)
