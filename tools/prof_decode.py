@@ -7,10 +7,10 @@ ann = torch.relu(torch.randn(B, h, w, 684, device="cuda"))
 for _ in range(3):
     t, l, s = eng.greedy_decode(ann, 40, ignore_eol=True)
 torch.cuda.synchronize()
-ws = eng._ws[("greedy_p", B, h, w)]
+ws = eng._ws[("greedy_p",)]
 # barrier words live after hbuf,pre_h,SP,E,ap,ctx,MO
 L = h * w
-off = sum(((n + 3) // 4) * 4 for n in (2 * B * 256, B * 256, B * 512, 2 * B * L, B * L, B * 684, B * 128))
+off = sum(((n + 3) // 4) * 4 for n in (2 * B * 256, B * 256, B * 512, 2 * B * L, 2 * B * L, B * 684, B * 128))
 prof = ws[off + 8 * 160: off + 8 * 160 + 16].view(torch.int64).cpu().numpy()
 names = ["A gru1", "B pre_h", "C cover", "D ctx", "E gru2", "F logit", "G argmax", "setup"]
 tot = prof[:7].sum()
