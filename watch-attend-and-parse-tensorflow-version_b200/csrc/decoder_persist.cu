@@ -267,67 +267,63 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     grid_barrier(a.barrier, nC, epoch);
     mark(1);
     // ====================================================== C: coverage stencil + tanh + V_a dot (partial over 128 channels)
-    // im2col GEMM [<=64 positions x 121 taps] x [121 x 128]: warp = 8 positions, lane = 4 channels; per tap two
-    // broadcast 128-bit loads of patch values and one 128-bit load of Q' feed 32 FMAs.
+    // Register-tiled stencil (round 2; the round-1 form materialised a [121][64] im2col tile per pass): a warp takes a tile of 8 consecutive
+    // positions of one image row, a lane 4 of the CTA's 128 channels; per filter row the 18-wide alpha_past window of the tile is read once
+    // (broadcast loads) and reused by the 11 horizontal taps - 29 shared-memory loads per 352 FMAs, the loop runs at the FFMA issue rate.
     {
-      const int PW = a.W + 2 * (kCovK / 2), PH = a.H + 2 * (kCovK / 2);
-      float* Apat = X;                                  // [121][64] im2col tile (X is free between phases B and E)
+      const int W8 = (a.W + 7) & ~7, PW = W8 + 2 * (kCovK / 2), PH = a.H + 2 * (kCovK / 2);
+      const int tiles_x = W8 >> 3, ntile = a.H * tiles_x;
       const int c0 = cg * kCGW + lane * 4;
       const float4 ub4 = ldg4(P + o.U_f_b + c0), va4 = ldg4(P + o.V_a + c0);
-      int bcur = -1;
-      for (int pbase = pos0; pbase < pos1;) {
-        const int b = pbase / L;
-        if (b >= rows) break;                          // rows beyond the live hypotheses: nothing to do (uniform per CTA)
-        const int pend = min(min(pos1, (b + 1) * L), pbase + 64);
+      if (c_active && cimg < rows) {
+        const int b = cimg;
+        const int t0 = (int)((long long)ntile * cgrp / gpi), t1 = (int)((long long)ntile * (cgrp + 1) / gpi);
         __syncthreads();
-        if (b != bcur) {                               // stage alpha_past of image b with a zero border of 5
-          for (int i = tid; i < PH * PW; i += kPT) {
-            const int yy = i / PW - kCovK / 2, xx = i % PW - kCovK / 2;
-            sal[i] = ((unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W) ? __ldcg(ap_old + (size_t)src[b] * L + yy * a.W + xx) : 0.f;
-          }
-          __syncthreads();
-          bcur = b;
-        }
-        for (int i = tid; i < kCovTaps * 64; i += kPT) {       // im2col: Apat[tap][p]
-          const int tap = i >> 6, pp = i & 63, pos = pbase + pp;
-          float v = 0.f;
-          if (pos < pend) { const int l = pos - b * L, y = l / a.W, x = l - y * a.W; v = sal[(y + tap / kCovK) * PW + x + tap % kCovK]; }
-          Apat[i] = v;
+        for (int i = tid; i < PH * PW; i += kPT) {            // alpha_past of image b with a zero border of 5 (and zero columns up to W8)
+          const int yy = i / PW - kCovK / 2, xx = i % PW - kCovK / 2;
+          sal[i] = ((unsigned)yy < (unsigned)a.H && (unsigned)xx < (unsigned)a.W) ? __ldcg(ap_old + (size_t)src[b] * L + yy * a.W + xx) : 0.f;
         }
         __syncthreads();
         const float4 sp4 = __ldcg(reinterpret_cast<const float4*>(a.SP + (size_t)b * kNA + c0));
-        float acc[8][4];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
-        if (pbase + warp * 8 < pend) {
-#pragma unroll 2
-          for (int tap = 0; tap < kCovTaps; ++tap) {
-            const float4 q = *reinterpret_cast<const float4*>(Qs + tap * kCGW + lane * 4);
-            const float4 p0 = *reinterpret_cast<const float4*>(Apat + tap * 64 + warp * 8);
-            const float4 p1 = *reinterpret_cast<const float4*>(Apat + tap * 64 + warp * 8 + 4);
-            const float pv[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              acc[i][0] = fmaf(pv[i], q.x, acc[i][0]); acc[i][1] = fmaf(pv[i], q.y, acc[i][1]);
-              acc[i][2] = fmaf(pv[i], q.z, acc[i][2]); acc[i][3] = fmaf(pv[i], q.w, acc[i][3]);
-            }
-          }
+        for (int tb = t0; tb < t1; tb += kPT / 32) {
+          const int tile = tb + warp;
+          const bool act = tile < t1;
+          const int ty0 = act ? tile / tiles_x : 0, x0 = act ? (tile - ty0 * tiles_x) * 8 : 0;
           float4 w4[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {                // all watch rows in flight before any of them is used
-            const int pos = min(pbase + warp * 8 + i, pend - 1);
-            w4[i] = ldg4(a.watch + (size_t)(shared_img ? pos - b * L : pos) * kNA + c0);
+          for (int i = 0; i < 8; ++i) {                       // all watch rows in flight before the stencil
+            const int l = ty0 * a.W + min(x0 + i, a.W - 1);
+            w4[i] = ldg4(a.watch + (size_t)(shared_img ? l : b * L + l) * kNA + c0);
+          }
+          float acc[8][4];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { acc[i][0] = 0.f; acc[i][1] = 0.f; acc[i][2] = 0.f; acc[i][3] = 0.f; }
+          if (act) {
+#pragma unroll 1
+            for (int fy = 0; fy < kCovK; ++fy) {
+              const float* prow = sal + (ty0 + fy) * PW + x0;
+              float pv[18];
+#pragma unroll
+              for (int i = 0; i < 18; ++i) pv[i] = prow[i];
+#pragma unroll
+              for (int fx = 0; fx < kCovK; ++fx) {
+                const float4 q = *reinterpret_cast<const float4*>(Qs + (fy * kCovK + fx) * kCGW + lane * 4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                  acc[i][0] = fmaf(pv[i + fx], q.x, acc[i][0]); acc[i][1] = fmaf(pv[i + fx], q.y, acc[i][1]);
+                  acc[i][2] = fmaf(pv[i + fx], q.z, acc[i][2]); acc[i][3] = fmaf(pv[i + fx], q.w, acc[i][3]);
+                }
+              }
+            }
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const int pos = pbase + warp * 8 + i;
             float e = va4.x * tanhf(acc[i][0] + ub4.x + w4[i].x + sp4.x) + va4.y * tanhf(acc[i][1] + ub4.y + w4[i].y + sp4.y) +
                       va4.z * tanhf(acc[i][2] + ub4.z + w4[i].z + sp4.z) + va4.w * tanhf(acc[i][3] + ub4.w + w4[i].w + sp4.w);
             e = warp_sum(e);
-            if (lane == 0 && pos < pend) atomicAdd(Ecur + pos, e);
+            if (lane == 0 && act && x0 + i < a.W) atomicAdd(Ecur + (size_t)b * L + ty0 * a.W + x0 + i, e);
           }
         }
-        pbase = pend;
       }
       __syncthreads();
     }
@@ -578,8 +574,8 @@ size_t greedy_persist_ws_floats(int Bn, int L) {
 static int launch_persistent(cudaStream_t st, const float* params, const float* ann, int Bn, int h, int w, int maxlen, int ignore_eol, int beam_k,
                              int* tokens, int* lengths, float* bscore, int* bmeta, float* wsp, int* steps_run_dev) {
   const int L = h * w;
-  WAP_REQUIRE(Bn >= 1 && Bn <= kMaxB && L <= kMaxL && (h + 10) * (w + 10) <= kPadMax,
-              "persistent decoder: rows=%d (<=%d), L=%d (<=%d), padded grid %d (<=%d)", Bn, kMaxB, L, kMaxL, (h + 10) * (w + 10), kPadMax);
+  WAP_REQUIRE(Bn >= 1 && Bn <= kMaxB && L <= kMaxL && (h + 10) * (((w + 7) & ~7) + 10) <= kPadMax,
+              "persistent decoder: rows=%d (<=%d), L=%d (<=%d), padded grid %d (<=%d)", Bn, kMaxB, L, kMaxL, (h + 10) * (((w + 7) & ~7) + 10), kPadMax);
   static int num_ctas = 0;
   const size_t smem = sizeof(float) * kSmemFloats;
   if (num_ctas == 0) {

@@ -372,7 +372,7 @@ class WAPEngine:
         tokens = torch.zeros((B, maxlen), dtype=torch.int32, device=self.device)
         lengths = torch.zeros((B,), dtype=torch.int32, device=self.device)
         if persistent is None:
-            persistent = h * w <= 2048 and (h + 10) * (w + 10) <= 6144
+            persistent = h * w <= 2048 and (h + 10) * (((w + 7) // 8) * 8 + 10) <= 6144
         if persistent:
             steps_dev = torch.zeros((1,), dtype=torch.int32, device=self.device)
             for b0 in range(0, B, 16):
@@ -389,7 +389,7 @@ class WAPEngine:
         return tokens, lengths, steps.value
 
     def beam_supported(self, h: int, w: int, k: int, maxlen: int) -> bool:
-        return h * w <= 2048 and (h + 10) * (w + 10) <= 6144 and 1 <= k <= 16 and 1 <= maxlen <= 128
+        return h * w <= 2048 and (h + 10) * (((w + 7) // 8) * 8 + 10) <= 6144 and 1 <= k <= 16 and 1 <= maxlen <= 128
 
     def get_sample(self, annotation: torch.Tensor, k: int = 10, maxlen: int = 100, on_device: Optional[bool] = None):
         """Beam search of WAP.get_sample(stochastic=False) (S:442-542) + the length-normalised pick (S:671-672) for ONE image
