@@ -1,6 +1,7 @@
 """Per-segment device time of one training step (stream launches + PDL): encoder fwd / decoder fwd / decoder bwd / encoder bwd / update."""
 import sys, ctypes as C
-sys.path.insert(0, "/root/repo")
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import wap_b200
 from wap_b200 import synth
@@ -14,8 +15,8 @@ x, xm = torch.as_tensor(x).cuda(), torch.as_tensor(xm).cuda(); y, ym = torch.as_
 T = y.shape[0]
 h, w = eng.annotation_hw(H, W)
 a_mask = eng.mask_subsample(xm)
-ews = eng._buf(("enc", B, H, W, True), L.wap_encoder_workspace_floats(B, H, W, 1)); dws = eng._buf(("dec", B, h, w, T), L.wap_decoder_train_workspace_floats(B, h, w, T))
-ann = eng._buf(("ann", B, h, w), B * h * w * ANNOT_C); d_ann = eng._buf(("dann", B, h, w), B * h * w * ANNOT_C)
+ews = eng._buf(("enc",), L.wap_encoder_workspace_floats(B, H, W, 1)); dws = eng._buf(("dec",), L.wap_decoder_train_workspace_floats(B, h, w, T))
+ann = eng._buf(("ann",), B * h * w * ANNOT_C); d_ann = eng._buf(("dann",), B * h * w * ANNOT_C)
 sd = C.c_uint32(5)
 segs = [("enc_fwd", lambda st: L.wap_encoder_forward(st, _p(eng.P.flat), _p(eng.P.moving), _p(x), B, H, W, 1, 1, sd, _p(ann), _p(ews))),
         ("dec_fwd", lambda st: L.wap_decoder_train_forward(st, _p(eng.P.flat), _p(ann), _p(a_mask), _p(y), _p(ym), B, h, w, T, 1, sd, _p(eng._cost), _p(dws))),

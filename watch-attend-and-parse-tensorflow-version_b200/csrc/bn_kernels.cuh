@@ -6,6 +6,7 @@
 #include <cuda_bf16.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -295,7 +296,10 @@ static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
   // a.red was zeroed by the previous BN backward's apply kernel (or by the memset at the start of encoder_backward): a memset
   // node here would sit between two kernels 110 times per step and break their programmatic dependency
   const size_t npix = (size_t)a.B * a.Hi * a.Wi;
-  int ppc = (int)std::max<size_t>(64, cdivz(npix, 148 * 4));
+  // CTAs per SM of the reduce pass: every CTA ends with 2*C fp64 atomics onto the same 2*C addresses, so more CTAs = more contention
+  // (tunable for experiments: WAP_BN_BWD_CTAS_PER_SM)
+  static const int per_sm = [] { const char* e = getenv("WAP_BN_BWD_CTAS_PER_SM"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  int ppc = (int)std::max<size_t>(64, cdivz(npix, (size_t)148 * per_sm));
   const int grid = (int)cdivz(npix, ppc);
   if (pool == 0) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<0, TRaw, TG>, grid, 256, 0, st, a, ppc));
   else if (pool == 1) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<1, TRaw, TG>, grid, 256, 0, st, a, ppc));
