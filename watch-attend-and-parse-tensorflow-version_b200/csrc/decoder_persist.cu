@@ -96,6 +96,13 @@ __device__ __forceinline__ float warp_dot(const float* x, const float* w, int n,
   for (int k = lane; k < n; k += 32) s = fmaf(x[k], w[k], s);
   return warp_sum(s);
 }
+// N independent partial sums reduced across the warp with ONE interleaved butterfly (N sequential warp_sum chains are latency-bound)
+template <int N> __device__ __forceinline__ void warp_sum_n(float (&v)[N]) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], off);
+}
 // column `col` of a row-major [K][N] matrix -> contiguous smem
 __device__ __forceinline__ void load_col(float* dst, const float* W, int K, int N, int col) {
   for (int k = threadIdx.x; k < K; k += kPT) dst[k] = __ldg(W + (size_t)k * N + col);
@@ -230,11 +237,18 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
       const int s = p / rows, b = p - s * rows, j = unit[s];
       const float* xe = X + b * 2 * kN; const float* xh = xe + kMw;
       const float* w = WA + s * 6 * kN;
-      const float er = warp_dot(xe, w, kMw, lane), ez = warp_dot(xe, w + kN, kMw, lane), eh = warp_dot(xe, w + 2 * kN, kMw, lane);
-      const float hr = warp_dot(xh, w + 3 * kN, kN, lane), hz = warp_dot(xh, w + 4 * kN, kN, lane), hu = warp_dot(xh, w + 5 * kN, kN, lane);
+      float d6[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};           // er ez eh | hr hz hu
+#pragma unroll
+      for (int k8 = 0; k8 < kN / 32; ++k8) {
+        const int k = lane + 32 * k8;
+        const float ve = xe[k], vh = xh[k];
+        d6[0] = fmaf(ve, w[k], d6[0]); d6[1] = fmaf(ve, w[kN + k], d6[1]); d6[2] = fmaf(ve, w[2 * kN + k], d6[2]);
+        d6[3] = fmaf(vh, w[3 * kN + k], d6[3]); d6[4] = fmaf(vh, w[4 * kN + k], d6[4]); d6[5] = fmaf(vh, w[5 * kN + k], d6[5]);
+      }
+      warp_sum_n(d6);
       if (lane == 0) {
-        const float r = sigmoidf_(er + hr + __ldg(P + o.b_yz_yr + j)), z = sigmoidf_(ez + hz + __ldg(P + o.b_yz_yr + kN + j));
-        const float prop = tanhf(fmaf(hu, r, eh + __ldg(P + o.b_yh + j)));
+        const float r = sigmoidf_(d6[0] + d6[3] + __ldg(P + o.b_yz_yr + j)), z = sigmoidf_(d6[1] + d6[4] + __ldg(P + o.b_yz_yr + kN + j));
+        const float prop = tanhf(fmaf(d6[5], r, d6[2] + __ldg(P + o.b_yh + j)));
         const float hp = xh[j];
         const float ph = z * hp + (1.f - z) * prop;
         own[(s * kMaxB + b) * 8 + 0] = ph;
@@ -248,20 +262,37 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
     // ====================================================== B: pre_h-side products
     stage_cg(X, a.pre_h, rows * kN / 4);
     __syncthreads();
-    for (int p = warp; p < (nu * 3 + nsp) * rows; p += kPT / 32) {
-      const int q = p / rows, b = p - q * rows;
-      const float* x = X + b * kN;
-      if (q < nu * 3) {
-        const int s = q / 3, c = q - s * 3, j = unit[s];
-        const float v = warp_dot(x, WB + (s * 3 + c) * kN, kN, lane);
-        if (lane == 0) {
-          const float bias = c == 0 ? __ldg(P + o.b_hz_hr_nl + j) : c == 1 ? __ldg(P + o.b_hz_hr_nl + kN + j) : __ldg(P + o.b_rh_nl + j);
-          own[(s * kMaxB + b) * 8 + 1 + c] = v + bias;
-        }
-      } else {
-        const int i = q - nu * 3, col = cta + i * nC;
-        const float v = warp_dot(x, WS + i * kN, kN, lane);
-        if (lane == 0) a.SP[(size_t)b * kNA + col] = v + __ldg(P + o.W_a_b + col);
+    for (int p = warp; p < nu * rows; p += kPT / 32) {            // GRU-2 pre_h-side: three dot products per (unit, row), one butterfly
+      const int s = p / rows, b = p - s * rows, j = unit[s];
+      const float* x = X + b * kN; const float* w = WB + s * 3 * kN;
+      float d3[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k8 = 0; k8 < kN / 32; ++k8) {
+        const int k = lane + 32 * k8;
+        const float v = x[k];
+        d3[0] = fmaf(v, w[k], d3[0]); d3[1] = fmaf(v, w[kN + k], d3[1]); d3[2] = fmaf(v, w[2 * kN + k], d3[2]);
+      }
+      warp_sum_n(d3);
+      if (lane == 0) {
+        float* ow = own + (s * kMaxB + b) * 8;
+        ow[1] = d3[0] + __ldg(P + o.b_hz_hr_nl + j); ow[2] = d3[1] + __ldg(P + o.b_hz_hr_nl + kN + j); ow[3] = d3[2] + __ldg(P + o.b_rh_nl + j);
+      }
+    }
+    for (int p = 2 * warp; p < nsp * rows; p += 2 * (kPT / 32)) {   // speller columns: two (column, row) items per pass
+      float d2[2] = {0.f, 0.f};
+      int ii[2], bb[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { const int q = min(p + e, nsp * rows - 1); ii[e] = q / rows; bb[e] = q - ii[e] * rows; }
+#pragma unroll
+      for (int k8 = 0; k8 < kN / 32; ++k8) {
+        const int k = lane + 32 * k8;
+        d2[0] = fmaf(X[bb[0] * kN + k], WS[ii[0] * kN + k], d2[0]); d2[1] = fmaf(X[bb[1] * kN + k], WS[ii[1] * kN + k], d2[1]);
+      }
+      warp_sum_n(d2);
+      if (lane == 0) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+          if (p + e < nsp * rows) { const int col = cta + ii[e] * nC; a.SP[(size_t)bb[e] * kNA + col] = d2[e] + __ldg(P + o.W_a_b + col); }
       }
     }
     grid_barrier(a.barrier, nC, epoch);
@@ -381,23 +412,27 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
       const float* xc = X + b * kD;
       if (q < nu) {
         const int s = q, j = unit[s];
-        const float cr = warp_dot(xc, WE + (s * 3 + 0) * kD, kD, lane), cz = warp_dot(xc, WE + (s * 3 + 1) * kD, kD, lane);
-        const float ch = warp_dot(xc, WE + (s * 3 + 2) * kD, kD, lane);
+        const float* w = WE + s * 3 * kD;
+        float d3[3] = {0.f, 0.f, 0.f};
+        for (int k = lane; k < kD; k += 32) {
+          const float v = xc[k];
+          d3[0] = fmaf(v, w[k], d3[0]); d3[1] = fmaf(v, w[kD + k], d3[1]); d3[2] = fmaf(v, w[2 * kD + k], d3[2]);
+        }
+        warp_sum_n(d3);
         if (lane == 0) {
           const float* ow = own + (s * kMaxB + b) * 8;
-          const float r = sigmoidf_(ow[1] + cr), z = sigmoidf_(ow[2] + cz);
-          const float prop = tanhf(fmaf(ow[3], r, ch));
+          const float r = sigmoidf_(ow[1] + d3[0]), z = sigmoidf_(ow[2] + d3[1]);
+          const float prop = tanhf(fmaf(ow[3], r, d3[2]));
           hnew[(size_t)b * kN + j] = z * ow[0] + (1.f - z) * prop;
         }
       } else {
         const int c = q - nu, n = 2 * cta + c;
-        float v = warp_dot(xc, WPc + c * kD, kD, lane);
-        // embedding part: gather directly (256 floats)
+        float d2[2] = {0.f, 0.f};                               // ctx part | embedding part (gathered from the table)
         const int y = sy[b];
-        float e = 0.f;
-        if (y >= 0) for (int k = lane; k < kMw; k += 32) e = fmaf(__ldg(P + o.embed + (size_t)y * kMw + k), WPy[c * kMw + k], e);
-        e = warp_sum(e);
-        if (lane == 0) own[(c * kMaxB + b) * 8 + 4] = v + e + __ldg(P + o.by + n) + __ldg(P + o.bc + n) + __ldg(P + o.bh + n);
+        for (int k = lane; k < kD; k += 32) d2[0] = fmaf(xc[k], WPc[c * kD + k], d2[0]);
+        if (y >= 0) for (int k = lane; k < kMw; k += 32) d2[1] = fmaf(__ldg(P + o.embed + (size_t)y * kMw + k), WPy[c * kMw + k], d2[1]);
+        warp_sum_n(d2);
+        if (lane == 0) own[(c * kMaxB + b) * 8 + 4] = d2[0] + d2[1] + __ldg(P + o.by + n) + __ldg(P + o.bc + n) + __ldg(P + o.bh + n);
       }
     }
     grid_barrier(a.barrier, nC, epoch);

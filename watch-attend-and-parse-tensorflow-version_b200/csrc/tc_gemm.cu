@@ -195,13 +195,15 @@ struct TcShape {
 // X3 kernels (~1390 cycles per k-block at 128 B/clk).  So the splitter warps write a_hi / a_lo into TENSOR MEMORY (lane =
 // tile row, 32 columns each) and the MMAs take A from TMEM: shared memory then only sees the TMA write, one read of A by the
 // splitter and the B reads.  Stage layout in smem: [A raw] [B hi] [B lo] (B lo only when X3).
-template <int BN, bool X3> struct TcSmem {
+template <int BN, bool X3, bool BF16 = false> struct TcSmem {
   // These kernels are bound by bytes in flight per SM (Little's law over the ~1.5 us L2->smem TMA latency), so the X3 variants
   // (one CTA per SM) take as many stages as the 227 KB of shared memory hold; single-pass variants are sized for 2 CTAs/SM.
 #ifndef WAP_TC_X3_DEEP
 #define WAP_TC_X3_DEEP 1
 #endif
-  static constexpr int kStages = kTcBK == 16 ? (X3 ? 3 : 4)
+  // bf16: one CTA per SM with SIX stages (28-32 KB each): the small grids of blocks 1-2 (16 ... 64 CTAs) are bound by the TMA round trip
+  // (~1500+ cycles), not by the 192 cycles of MMA per stage (ncu r02: 13 us for 10 k-blocks with three stages)
+  static constexpr int kStages = BF16 ? 6 : kTcBK == 16 ? (X3 ? 3 : 4)
                                : (X3 ? (BN <= 96 ? 4 : 3) : (BN <= 32 ? 4 : 3));     // X3: 4 x 64 TMEM columns of A ring + 2 x 128 accumulator columns = 512
   static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
   static constexpr int kBBytes = BN * kTcBK * 4;
@@ -228,12 +230,12 @@ template <bool X3> struct TcThreads { static constexpr int kN = kTcThreads; };
 // BF16: operands are bf16 in global / shared memory (a stage row is still one 128-byte swizzle span = 64 elements), the MMAs are
 // kind::f16 with K = 16 (again four per stage), accumulation fp32 in TMEM; epi.out_bf16 stores the result as bf16.
 template <int BN, int IM2COL, bool X3, bool BF16>
-__global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
+__global__ void __launch_bounds__(TcThreads<X3>::kN, ((X3 && kTcBK == 32) || BF16) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
   pdl_sync();
   static_assert(!(X3 && BF16), "3xTF32 splitting applies to fp32 operands only");
-  using S = TcSmem<BN, X3>;
+  using S = TcSmem<BN, X3, BF16>;
   constexpr int kTcStages = S::kStages;
   constexpr int kElK = BF16 ? kTcRowB / 2 : kTcBK;            // elements of K per stage row (64 bf16 or 32 fp32)
   // X3 keeps the two small correction products in a SECOND accumulator (columns [kAcc2, kAcc2+BN)) so that their
@@ -761,7 +763,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // =====================================================================================
 constexpr int kWbRows = 64;                       // pixel rows per stage
 constexpr int kWbBlk = kWbRows * 128;             // bytes of one 64-channel block of a stage (8192)
-constexpr int kWbStages = 4;
+constexpr int kWbStages = 6;                        // 24-32 KB each: deep enough to cover the TMA round trip with one CTA per SM
 
 template <int NBLK> struct WbSmem {
   static constexpr int kABytes = 2 * kWbBlk, kBBytes = NBLK * kWbBlk, kStage = kABytes + kBBytes;
@@ -930,12 +932,12 @@ static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap&
                       const TcShape& sh, dim3 grid, int prof_cls, double flops) {
   static bool configured = false;
   if (!configured) {
-    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3>::kTotal));
+    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3, BF16>::kTotal));
     configured = true;
   }
   TcShape sh2 = sh; sh2.trace = g_tc_trace;
   prof_begin(st, prof_cls, flops);
-  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3, BF16>, grid, TcThreads<X3>::kN, TcSmem<BN, X3>::kTotal, st, ta, tb, tblo, epi, sh2));
+  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3, BF16>, grid, TcThreads<X3>::kN, TcSmem<BN, X3, BF16>::kTotal, st, ta, tb, tblo, epi, sh2));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
