@@ -201,9 +201,9 @@ template <int BN, bool X3, bool BF16 = false> struct TcSmem {
 #ifndef WAP_TC_X3_DEEP
 #define WAP_TC_X3_DEEP 1
 #endif
-  // bf16: one CTA per SM with SIX stages (28-32 KB each): the small grids of blocks 1-2 (16 ... 64 CTAs) are bound by the TMA round trip
-  // (~1500+ cycles), not by the 192 cycles of MMA per stage (ncu r02: 13 us for 10 k-blocks with three stages)
-  static constexpr int kStages = BF16 ? 6 : kTcBK == 16 ? (X3 ? 3 : 4)
+  // (bf16 with SIX stages and one CTA per SM was measured in round 2: 3 % slower end to end than 3-4 stages x 2 CTAs per SM - the second CTA's
+  // epilogue overlapping the first one's main loop matters more in block 0 than deeper prefetch does in blocks 1-2)
+  static constexpr int kStages = kTcBK == 16 ? (X3 ? 3 : 4)
                                : (X3 ? (BN <= 96 ? 4 : 3) : (BN <= 32 ? 4 : 3));     // X3: 4 x 64 TMEM columns of A ring + 2 x 128 accumulator columns = 512
   static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
   static constexpr int kBBytes = BN * kTcBK * 4;
@@ -230,7 +230,7 @@ template <bool X3> struct TcThreads { static constexpr int kN = kTcThreads; };
 // BF16: operands are bf16 in global / shared memory (a stage row is still one 128-byte swizzle span = 64 elements), the MMAs are
 // kind::f16 with K = 16 (again four per stage), accumulation fp32 in TMEM; epi.out_bf16 stores the result as bf16.
 template <int BN, int IM2COL, bool X3, bool BF16>
-__global__ void __launch_bounds__(TcThreads<X3>::kN, ((X3 && kTcBK == 32) || BF16) ? 1 : 2)
+__global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
   pdl_sync();
@@ -763,7 +763,7 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
 // =====================================================================================
 constexpr int kWbRows = 64;                       // pixel rows per stage
 constexpr int kWbBlk = kWbRows * 128;             // bytes of one 64-channel block of a stage (8192)
-constexpr int kWbStages = 6;                        // 24-32 KB each: deep enough to cover the TMA round trip with one CTA per SM
+constexpr int kWbStages = 4;
 
 template <int NBLK> struct WbSmem {
   static constexpr int kABytes = 2 * kWbBlk, kBBytes = NBLK * kWbBlk, kStage = kABytes + kBBytes;
