@@ -341,6 +341,25 @@ def test_train_steps_match_oracle(report):
     assert not fails, fails
 
 
+def test_fused_bn_backward_reduce_matches_separate_kernels(report):
+    """The first pass of the 1x1 output's BN backward inside the 3x3 dgrad epilogue (default, debug-mask bit 10) == dgrad3 -> bn_bwd_reduce as
+    separate kernels: same gradients up to the order of the fp32 sums, 48 launches fewer."""
+    import wap_b200
+    P = O.lively_params(5)
+    x, xm, y, ym = make_batch(33, 2, 50, 150, 4, True)
+    eng = engine_with(P, use_graphs=False)
+    L = wap_b200._lib.lib()
+    n0 = eng.launch_count(); c1 = float(eng.forward_backward(x, y, xm, ym, True, 9)); g1 = eng.grads.clone(); n1 = eng.launch_count()
+    try:
+        L.wap_debug_set_tc_mask(0x7FF & ~1024)
+        c0 = float(eng.forward_backward(x, y, xm, ym, True, 9)); g0 = eng.grads.clone(); n2 = eng.launch_count()
+    finally:
+        L.wap_debug_set_tc_mask(0x7FF)
+    e = rel_l2(g1.cpu().numpy(), g0.cpu().numpy())
+    report.add("bn_bwd_fused", "grads_rel_l2_vs_unfused", e, 1e-5)
+    assert abs(c1 - c0) <= 2e-6 * abs(c0) and e <= 1e-5 and (n1 - n0) == (n2 - n1) - 48, (c1, c0, e, n1 - n0, n2 - n1)
+
+
 def test_decoding_context_caches_the_fused_coverage_filter():
     """WAPEngine.decoding(): Q' = Q*U_f computed once and handed to the decode kernels (wap_set_fused_coverage_filter) - same tokens and
     beam samples as the per-call recomputation, for the cluster kernel (B <= 7), the grid-wide kernel and the beam search."""
@@ -372,7 +391,7 @@ def test_inference_bn_fold_is_bit_identical(precision):
         L.wap_debug_set_tc_mask(0x1FF)
         a_plain, _ = eng.dense_net(x, xm, training=False); n2 = eng.launch_count()
     finally:
-        L.wap_debug_set_tc_mask(0x3FF)
+        L.wap_debug_set_tc_mask(0x7FF)
     if precision == "bf16":      # the unfused bf16 path rounds the raw conv output to bf16 BEFORE the batch norm, the fused one applies it to the fp32 accumulator
         assert rel_l2(a_fused.cpu().numpy(), a_plain.cpu().numpy()) < 2e-1      # two bf16 roundings of every raw conv output apart (inference mode amplifies: 9-12 % vs the oracle)
     else:

@@ -291,6 +291,14 @@ static int run_bn_act(cudaStream_t st, int pool, const BnActArgs& a) {
   return 0;
 }
 
+// second pass only (the first one ran inside the producing GEMM's epilogue, TcEpi::bnb_*)
+template <typename TRaw = float, typename TG = float>
+static int run_bn_bwd_apply(cudaStream_t st, const BnBwdArgs& a) {
+  const size_t npix = (size_t)a.B * a.Hi * a.Wi;
+  WAP_CHECK(launch_pdl(bn_bwd_apply_kernel<TRaw, TG>, ew_grid(npix * (a.C / 4)), 256, 0, st, a));
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
 template <typename TRaw = float, typename TG = float>
 static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
   // a.red was zeroed by the previous BN backward's apply kernel (or by the memset at the start of encoder_backward): a memset

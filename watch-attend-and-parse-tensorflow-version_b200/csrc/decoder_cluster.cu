@@ -63,11 +63,6 @@ constexpr int kVec = 256 + 256 + 256 + 512 + 688 + 256;   // emb | h | pre_h | s
 constexpr int kSmemFloatsC = kWA + kWB + kQS + kWO + kVec + kPadC + kMaxLc /*alpha*/ + kCL * kOwnMax /*epart*/ + 2 * kCL /*ms*/ +
                              kCL * 112 /*lpart*/ + 8 * 64 /*red*/ + 64 /*own gate values*/ + 256 /*misc*/ + 320 /*biases*/;
 
-__device__ __forceinline__ float wdot(const float* x, const float* w, int n, int lane) {
-  float s = 0.f;
-  for (int k = lane; k < n; k += 32) s = fmaf(x[k], w[k], s);
-  return warp_sum(s);
-}
 __device__ __forceinline__ void lcol(float* dst, const float* W, int K, int N, int col) {
   for (int k = threadIdx.x; k < K; k += kT) dst[k] = __ldg(W + (size_t)k * N + col);
 }
@@ -81,7 +76,7 @@ __global__ void __launch_bounds__(kT, 1) greedy_cluster_kernel(const CArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float* P = a.params; const COff& o = a.o;
   const int L = a.L, Wd = a.W, Hd = a.H;
-  const int W8 = (Wd + 7) & ~7, PW = W8 + 10, PH = Hd + 10;
+  const int W8 = (Wd + 7) & ~7, PW = W8 + 10;
   const int LPC = (L + kCL - 1) / kCL;                 // positions owned per CTA (softmax)
   // ---- carve-up
   float* WA = sm;

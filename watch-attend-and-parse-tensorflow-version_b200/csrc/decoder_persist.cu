@@ -166,8 +166,6 @@ __global__ void __launch_bounds__(kPT, 1) greedy_persistent_kernel(const Persist
   // position groups never span two images: gpi groups per image (one alpha_past staging, one im2col pass per <= 64 positions)
   const int gpi = max(1, npg / Bn), cimg = pg / gpi, cgrp = pg % gpi;
   const bool c_active = cimg < Bn;
-  const int pos0 = c_active ? cimg * L + (int)((long long)L * cgrp / gpi) : 0;
-  const int pos1 = c_active ? cimg * L + (int)((long long)L * (cgrp + 1) / gpi) : 0;
   const int cpb = max(1, nC / Bn);                                      // context: CTAs per image
   const int db = cta / cpb, dchunk = cta % cpb;                         // image / chunk (only if db < Bn)
   const int c4_per = (kD / 4 + cpb - 1) / cpb;                          // float4 columns per chunk

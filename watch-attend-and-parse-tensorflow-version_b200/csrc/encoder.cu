@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) bn_fold_kernel(const float* __restrict__ 
 }
 
 int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
-int g_tc_debug_mask = 0x3FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd, bit8 row-tile 3x3, bit9 inference BN folded into the conv epilogues
+int g_tc_debug_mask = 0x7FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd, bit8 row-tile 3x3, bit9 inference BN folded into the conv epilogues, bit10 BN-backward reduce of the 1x1 output fused into the 3x3 dgrad epilogue
 void set_conv_precision(int mode) { cur()->precision = mode; }
 int get_conv_precision() { return cur()->precision; }
 
@@ -517,6 +517,16 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
         WAP_TRY((launch_gemm<Cfg128x32>(sw, A, Bd, e, 9 * kBottle, kGrowth, M, std::max(1, std::min(cdiv(M, 64), cdiv(592, tiles))), kProfConv3Wgrad)));
       }
       WAP_TRY(mark(par));
+      const bool fuse_bnb = tc && (g_tc_debug_mask & 2) && (g_tc_debug_mask & 1024) && !(k1 == g_dbg_layer && g_dbg_buf != nullptr);
+      if (fuse_bnb) {
+        // dgrad 3x3 with the FIRST pass of the 1x1 output's BN backward in its epilogue: the accumulator (d a1) is gated by the ReLU / dropout of
+        // that BN, stored as g into dy1 and column-summed (sum g, sum g*xhat) - d a1 is never written, bn_bwd_reduce is not launched
+        WAP_TRY(join(2 + par));                 // dy1[par] is free once the 1x1 weight gradient of two levels ago has read it
+        const BnBwdArgs ab = bwd_args(k1, y1, h, w, nullptr, h, w, kBottle, dy1, kDy1Ld, true);
+        TcEpi e{dy1, kDy1Ld, 0, ab.red, nullptr, 0, 0, nullptr, nullptr, y1, kBottle, ab.saved, ab.gamma, ab.beta, ab.dropout, ab.seed, ab.site, ab.seed_src};
+        WAP_TRY(tc_conv3x3(st, dy2, kDy2Ld, B, h, w, kDy2Ld, wsp + ws.wt_bwd[k3], lo(ws.wt_bwd_lo[k3]), kBottle, kBottle, e, kProfConv3Dgrad));
+        WAP_TRY(run_bn_bwd_apply(st, ab));
+      } else {
       if (tc && (g_tc_debug_mask & 2)) {   // dgrad 3x3: d a1[M,96]
         WAP_TRY(tc_conv3x3(st, dy2, kDy2Ld, B, h, w, kDy2Ld, wsp + ws.wt_bwd[k3], lo(ws.wt_bwd_lo[k3]), kBottle, kBottle, TcEpi{da1, kBottle, 0, nullptr, nullptr, 0}, kProfConv3Dgrad));
       } else {
@@ -531,6 +541,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
       }
       WAP_TRY(join(2 + par));
       WAP_TRY(run_bn_bwd(st, 0, bwd_args(k1, y1, h, w, da1, h, w, kBottle, dy1, kDy1Ld, true)));
+      }
       WAP_TRY(fork());
       if (k1 == g_dbg_layer && g_dbg_buf != nullptr)     // [.. | dy1 (M*96)]
         WAP_CHECK(cudaMemcpy2DAsync(g_dbg_buf + (size_t)M * (kBottle + kDy2Ld), sizeof(float) * kBottle, dy1, sizeof(float) * kDy1Ld, sizeof(float) * kBottle, M,

@@ -119,7 +119,6 @@ __global__ void __launch_bounds__(256) bf16_rows_to_f32_kernel(const bf16* __res
 }
 
 static inline bf16* B16(float* base, size_t off) { return reinterpret_cast<bf16*>(base + off); }
-static inline const bf16* B16(const float* base, size_t off) { return reinterpret_cast<const bf16*>(base + off); }
 
 // ------------------------------------------------------------------------------------ forward
 int encoder_forward_bf16(cudaStream_t st, const float* params, float* moving, const float* x, int B, int H, int W,

@@ -210,7 +210,7 @@ template <int BN, bool X3, bool BF16 = false> struct TcSmem {
   static constexpr int kStage = kABytes + (X3 ? 2 : 1) * kBBytes;
   static constexpr int kBarOff = kStages * kStage;
   static constexpr int kStatOff = kBarOff + 256;                    // barriers + tmem slot
-  static constexpr int kTotal = kStatOff + 2 * BN * 4 + 1024;       // + alignment slack
+  static constexpr int kTotal = kStatOff + 6 * BN * 4 + 1024;       // statistics (2 BN) + fused BN-backward constants (4 BN) + alignment slack
 };
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -277,6 +277,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (epi.stats != nullptr)
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
+  if (epi.bnb_raw != nullptr)       // fused BN-backward reduce: scale | shift | mean | invstd of this tile's channels behind the two sums
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) {
+      const bool ok = n0 + i < sh.N;
+      const float mean = ok ? epi.bnb_saved[n0 + i] : 0.f, inv = ok ? epi.bnb_saved[kMaxBnC + n0 + i] : 0.f;
+      const float sc = ok ? __ldg(epi.bnb_gamma + n0 + i) * inv : 0.f;
+      s_stat[2 * BN + i] = sc; s_stat[3 * BN + i] = ok ? __ldg(epi.bnb_beta + n0 + i) - mean * sc : 0.f;
+      s_stat[4 * BN + i] = mean; s_stat[5 * BN + i] = inv;
+    }
   if (epi.bn_scale != nullptr)      // folded inference batch norm: scale | shift of this tile's columns
     for (int i = threadIdx.x; i < BN; i += blockDim.x) {
       const bool ok = n0 + i < sh.N;
@@ -485,6 +493,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], s_stat[c + j], s_stat[BN + c + j]), 0.f);
       }
+      float xh[32];                      // (fused BN backward only) normalised raw output of the element, for the second sum
+      if (epi.bnb_raw != nullptr) {
+        const uint32_t seed = (epi.bnb_dropout && epi.bnb_seed_src != nullptr) ? __ldg(epi.bnb_seed_src) : epi.bnb_seed;
+        const float* rawp = epi.bnb_raw + mrow * epi.bnb_ld + n0 + c;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (valid && n0 + c + j + 3 < sh.N) rv = __ldg(reinterpret_cast<const float4*>(rawp + j));
+          const float rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+          for (int jj = 0; jj < 4; ++jj) {
+            const int i = c + j + jj;
+            const float pre = fmaf(rr[jj], s_stat[2 * BN + i], s_stat[3 * BN + i]);
+            float g = (pre > 0.f) ? v[j + jj] : 0.f;
+            if (epi.bnb_dropout) g = drop_keep(seed, epi.bnb_site, (uint32_t)(mrow * (size_t)sh.N + n0 + i)) ? g * (1.f / (1.f - kDropRate)) : 0.f;
+            v[j + jj] = g;
+            xh[j + jj] = (rr[jj] - s_stat[4 * BN + i]) * s_stat[5 * BN + i];
+          }
+        }
+      }
       if (valid && epi.transpose_out) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
@@ -518,7 +546,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (epi.stats != nullptr) {
         float a[32], b[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { a[i] = valid ? v[i] : 0.f; b[i] = a[i] * a[i]; }
+        for (int i = 0; i < 32; ++i) { a[i] = valid ? v[i] : 0.f; b[i] = a[i] * (epi.bnb_raw != nullptr ? xh[i] : a[i]); }
         // transposing butterfly: after the 5 rounds lane L holds the sum over the 32 rows of column L
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -998,6 +1026,8 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
 
 int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N, const TcEpi& epi, int prof_cls) {
   WAP_REQUIRE(C % kTcBK == 0 && (ldx & 3) == 0 && (epi.ld & 3) == 0, "tc_conv3x3: C=%d must be a multiple of %d", C, kTcBK);
+  WAP_REQUIRE(epi.bnb_raw == nullptr || (epi.stats != nullptr && N <= 96 && !epi.accumulate && !epi.transpose_out && epi.bias == nullptr && (epi.bnb_ld & 3) == 0),
+              "tc_conv3x3: the fused BN-backward epilogue needs statistics, one column tile (N <= 96) and a plain store");
   int TW = 1; while (TW < W && TW < kTcBM) TW <<= 1;     // power of two >= W, at most 128
   const int TH = kTcBM / TW;
   CUtensorMap ta, tb, tbl;

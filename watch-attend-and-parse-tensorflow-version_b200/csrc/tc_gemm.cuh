@@ -38,6 +38,14 @@ struct TcEpi {
   int out_bf16;              // `out` points to bf16 elements (ld in elements); store only (no accumulate / transpose / bias)
   const float* bn_scale;     // inference-mode batch norm folded into the epilogue: D = relu(acc * bn_scale[n] + bn_shift[n]) (both [N]); with
   const float* bn_shift;     //   statistics == nullptr, no accumulate / transpose / bias
+  // Fused first pass of the batch-norm backward of the layer that PRODUCED this GEMM's "input gradient" (the 3x3 dgrad writes d a1, the
+  // gradient wrt the activated output of the 1x1 conv's BN): with bnb_raw != nullptr the epilogue turns the accumulator u = d a1 into
+  // g = u * [BN output > 0] * dropout, stores g (instead of u) and adds the column sums of g and g * xhat into `stats` ([2][N] doubles) -
+  // exactly what bn_bwd_reduce_kernel<0> does, without the separate pass over d a1 and the raw output.  N must be <= 96, one column tile.
+  const float* bnb_raw; int bnb_ld;      // raw conv output [M, bnb_ld] of that layer (fp32)
+  const float* bnb_saved;                // its saved batch mean [kMaxBnC] | inverse std [kMaxBnC]
+  const float* bnb_gamma; const float* bnb_beta;
+  int bnb_dropout; uint32_t bnb_seed, bnb_site; const uint32_t* bnb_seed_src;
 };
 
 // Bt_hi/lo[N][K] = split(transpose(W[K][N])) (transpose != 0) or split(W[N][K]) : operand preparation for tc_gemm's 3xTF32 mode
