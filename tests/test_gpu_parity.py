@@ -342,22 +342,36 @@ def test_train_steps_match_oracle(report):
 
 
 def test_fused_bn_backward_reduce_matches_separate_kernels(report):
-    """The first pass of the 1x1 output's BN backward inside the 3x3 dgrad epilogue (default, debug-mask bit 10) == dgrad3 -> bn_bwd_reduce as
-    separate kernels: same gradients up to the order of the fp32 sums, 48 launches fewer."""
+    """The first pass of the 1x1 output's BN backward inside the 3x3 dgrad epilogue (debug-mask bit 10; off by default - it measured slower,
+    DESIGN 3.2) == dgrad3 -> bn_bwd_reduce as separate kernels.  ONE forward, then the backward twice on the same saved activations (a second
+    forward could gate an on-kink element differently): same gradients up to the order of the fp32 sums, 48 launches fewer."""
+    import ctypes as C
     import wap_b200
+    from wap_b200.engine import _p, _stream
     P = O.lively_params(5)
     x, xm, y, ym = make_batch(33, 2, 50, 150, 4, True)
     eng = engine_with(P, use_graphs=False)
     L = wap_b200._lib.lib()
-    n0 = eng.launch_count(); c1 = float(eng.forward_backward(x, y, xm, ym, True, 9)); g1 = eng.grads.clone(); n1 = eng.launch_count()
+    c0 = float(eng.forward_backward(x, y, xm, ym, True, 9)); g0 = eng.grads.clone()
+    xd, yd, xmd, ymd = eng._dev(x, torch.float32), eng._dev(y, torch.int32), eng._dev(xm, torch.float32), eng._dev(ym, torch.float32)
+    B, H, W, T = x.shape[0], x.shape[1], x.shape[2], y.shape[0]
+
+    def backward_again():
+        eng.grads.zero_()
+        n0 = eng.launch_count()
+        wap_b200._lib.check(eng.L.wap_train_backward(_stream(), _p(eng.P.flat), _p(eng.grads), _p(xd), B, H, W, _p(eng._ws[("ann",)]), _p(eng._ws[("amask",)]),
+                                                     _p(yd), _p(ymd), T, 1, C.c_uint32(9), _p(eng._ws[("dann",)]), _p(eng._ws[("enc",)]), _p(eng._ws[("dec",)])),
+                            "wap_train_backward")
+        return eng.grads.clone(), eng.launch_count() - n0
+    g_plain, n_plain = backward_again()
     try:
-        L.wap_debug_set_tc_mask(0x7FF & ~1024)
-        c0 = float(eng.forward_backward(x, y, xm, ym, True, 9)); g0 = eng.grads.clone(); n2 = eng.launch_count()
+        L.wap_debug_set_tc_mask(0x3FF | 1024)
+        g_fused, n_fused = backward_again()
     finally:
-        L.wap_debug_set_tc_mask(0x7FF)
-    e = rel_l2(g1.cpu().numpy(), g0.cpu().numpy())
-    report.add("bn_bwd_fused", "grads_rel_l2_vs_unfused", e, 1e-5)
-    assert abs(c1 - c0) <= 2e-6 * abs(c0) and e <= 1e-5 and (n1 - n0) == (n2 - n1) - 48, (c1, c0, e, n1 - n0, n2 - n1)
+        L.wap_debug_set_tc_mask(0x3FF)
+    e0 = rel_l2(g_plain.cpu().numpy(), g0.cpu().numpy()); e = rel_l2(g_fused.cpu().numpy(), g_plain.cpu().numpy())
+    report.add("bn_bwd_fused", "grads_rel_l2_vs_unfused", e, 2e-5, extra=dict(rerun_noise=e0, launches=(n_plain, n_fused)))
+    assert e0 <= 2e-5 and e <= 2e-5 and n_fused == n_plain - 48, (c0, e0, e, n_plain, n_fused)
 
 
 def test_decoding_context_caches_the_fused_coverage_filter():
@@ -391,7 +405,7 @@ def test_inference_bn_fold_is_bit_identical(precision):
         L.wap_debug_set_tc_mask(0x1FF)
         a_plain, _ = eng.dense_net(x, xm, training=False); n2 = eng.launch_count()
     finally:
-        L.wap_debug_set_tc_mask(0x7FF)
+        L.wap_debug_set_tc_mask(0x3FF)
     if precision == "bf16":      # the unfused bf16 path rounds the raw conv output to bf16 BEFORE the batch norm, the fused one applies it to the fp32 accumulator
         assert rel_l2(a_fused.cpu().numpy(), a_plain.cpu().numpy()) < 2e-1      # two bf16 roundings of every raw conv output apart (inference mode amplifies: 9-12 % vs the oracle)
     else:
