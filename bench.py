@@ -530,15 +530,8 @@ def run_cfg5(args):
     pinned = [torch.as_tensor(np.ascontiguousarray(im[0])).pin_memory() for im in images]
 
     def decode_all(from_host):
-        out = []
-        for i in range(n_img):
-            if from_host:                                            # H2D of the raw uint8 image, /255 on the GPU
-                x = (pinned[i].to(env.dev, non_blocking=True).to(torch.float32) / 255.)[None, :, :, None]
-            else:
-                x = dev_imgs[i]
-            ann, _ = eng.dense_net(x, None, training=False)
-            toks, lens, _ = eng.greedy_decode(ann, maxlens[i])
-            out.append((toks, lens))
+        # two-stream pipeline of the engine: encoder of image i+1 next to the token loop of image i (WAPEngine.greedy_decode_images)
+        out = eng.greedy_decode_images(pinned if from_host else dev_imgs, maxlens, from_host=from_host)
         if from_host:
             return [t[0, : int(n[0])].cpu().tolist() for t, n in out]   # D2H of every result
         return out
@@ -582,7 +575,7 @@ def run_cfg5(args):
         "ms_per_step": ms / n_img, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": DTYPE_OF[args.precision or "tf32x3"],
         "data": "synthetic",
         "config": {"workload": f"cfg5: greedy decode of {n_img} CROHME-distributed synthetic images (SURVEY 8d), one unpadded image at a time, maxlen 100 "
-                               "(BASELINE configs[4]); encoder inference + persistent on-device token loop",
+                               "(BASELINE configs[4]); encoder inference (folded BN) on one stream, the on-device token loop of the previous image on another",
                    "weights": "seeded reference initialisers (lively BN terms); random weights never emit <eol>, so image i is decoded for len(caption_i) + 1 "
                               "steps (maxlen_i), caption lengths ~ the empirical CROHME lengths; the real offline-test.pkl is an LFS pointer",
                    "tokens": int(ntok), "mean_len": float(lens.mean()), "max_len": int(lens.max()), "hit_maxlen": int((lens >= 100).sum())},

@@ -101,23 +101,27 @@ def main(args):
             if uidx % sampleFreq == 0 and rank == 0:
                 with open(args.path + '/result/valid_decode_result-bs-6.txt', 'w') as fpp, eng.decoding():
                     idx = 0
-                    for vx, _ in valid:
-                        for xx in vx:
-                            xx_pad = (np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]
-                            annot, _ = eng.dense_net(xx_pad, None, training=False)
-                            if args.greedy_valid:
-                                toks, lens, _ = eng.greedy_decode(annot, 100)
-                                ss = toks[0, :int(lens[0])].tolist()
-                            else:
+                    def emit(ss):
+                        nonlocal idx
+                        fpp.write(valid_uid_list[idx]); idx += 1
+                        if idx % 100 == 0:
+                            say('gen %d samples' % idx)
+                        for vv in ss:
+                            if vv == 0:
+                                break
+                            fpp.write(' ' + worddicts_r[vv])
+                        fpp.write('\n')
+                    if args.greedy_valid:          # two-stream pipeline: encoder of image i+1 next to the token loop of image i
+                        imgs = [torch.as_tensor((np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]).to(eng.device) for vx, _ in valid for xx in vx]
+                        for toks, lens in eng.greedy_decode_images(imgs, 100):
+                            emit(toks[0, :int(lens[0])].tolist())
+                    else:
+                        for vx, _ in valid:
+                            for xx in vx:
+                                xx_pad = (np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]
+                                annot, _ = eng.dense_net(xx_pad, None, training=False)
                                 ss, _, _ = eng.get_sample(annot, 10, 100)
-                            fpp.write(valid_uid_list[idx]); idx += 1
-                            if idx % 100 == 0:
-                                say('gen %d samples' % idx)
-                            for vv in ss:
-                                if vv == 0:
-                                    break
-                                fpp.write(' ' + worddicts_r[vv])
-                            fpp.write('\n')
+                                emit(ss)
                 say('valid set decode done')
             if uidx % validFreq == 0 and rank == 0:
                 probs = []

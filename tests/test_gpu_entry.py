@@ -12,7 +12,10 @@ from helpers import ROOT
 pytestmark = pytest.mark.gpu
 
 
-def test_model_single_gpu_entry_point(tmp_path):
+@pytest.mark.parametrize("extra", [[], ["--greedy_valid", "--prefetch", "0", "--save", "ckpt.npz"]])
+def test_model_single_gpu_entry_point(tmp_path, extra):
+    """Default run (beam-search validation on the device, packed prefetch, graph replay for repeated shapes) and a run with the greedy
+    two-stream validation pipeline, the reference's synchronous host prepare_data and a checkpoint written on improvement."""
     from wap_b200 import synth
     d = tmp_path; (d / "data").mkdir()
     vocab = [f"tok{i}" for i in range(1, 111)]
@@ -22,7 +25,8 @@ def test_model_single_gpu_entry_point(tmp_path):
         feats = {f"{split}{i}": im for i, im in enumerate(imgs)}
         (d / "data" / f"offline-{split}.pkl").write_bytes(pickle.dumps(feats))
         (d / "data" / f"{split}_caption.txt").write_text("".join(f"{split}{i}\t" + " ".join(vocab[t - 1] for t in c) + "\n" for i, c in enumerate(caps)))
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "model-single-GPU.py"), "--path", str(d), "--batch_size", "4", "--max_epoch", "2"],
+    extra = [str(d / a) if a.endswith(".npz") else a for a in extra]
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "model-single-GPU.py"), "--path", str(d), "--batch_size", "4", "--max_epoch", "2"] + extra,
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     log = (d / "log-bs-6.txt").read_text()
@@ -31,3 +35,6 @@ def test_model_single_gpu_entry_point(tmp_path):
     assert [ln.split()[0] for ln in dec] == sorted(f"test{i}" for i in range(3)) or len(dec) == 3
     wer = (d / "result" / "valid-bs-6.wer").read_text()
     assert wer.startswith("WER ") and "ExpRate " in wer
+    if any(a.endswith(".npz") for a in extra):
+        z = np.load(d / "ckpt.npz")
+        assert "__sched__/lrate" in z.files and "conv2d_98/kernel" in z.files

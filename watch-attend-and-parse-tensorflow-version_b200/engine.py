@@ -363,6 +363,32 @@ class WAPEngine:
                 self.L.wap_set_fused_coverage_filter(None)
         return cm()
 
+    def greedy_decode_images(self, images, maxlen=100, from_host: bool = False):
+        """Greedy decode of a sequence of single images the way the reference validates (one unpadded image at a time, S:661-683), as a TWO-STREAM
+        PIPELINE: the encoder of image i+1 runs on one stream while the token loop of image i (16 SMs in the cluster kernel) runs on another -
+        the two halves use disjoint workspaces and the annotation handed over is a fresh tensor per image.  `images`: device tensors [1,H,W,1] in
+        [0,1], or (from_host) pinned uint8 [H,W] host tensors that are uploaded and scaled on the encoder stream.  `maxlen`: int or per-image
+        list.  Returns [(tokens [1,maxlen_i] int32, lengths [1] int32)] on the device; call inside `with eng.decoding():` for frozen weights."""
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_pipe_streams"):
+            self._pipe_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        s_enc, s_dec = self._pipe_streams
+        s_enc.wait_stream(cur); s_dec.wait_stream(cur)
+        out = []
+        for i, im in enumerate(images):
+            ml = maxlen[i] if isinstance(maxlen, (list, tuple)) else maxlen
+            with torch.cuda.stream(s_enc):
+                x = (im.to(self.device, non_blocking=True).to(torch.float32) / 255.)[None, :, :, None] if from_host else im
+                ann, _ = self.dense_net(x, None, training=False)
+                ev = torch.cuda.Event(); ev.record(s_enc)
+            with torch.cuda.stream(s_dec):
+                s_dec.wait_event(ev)
+                ann.record_stream(s_dec)
+                toks, lens, _ = self.greedy_decode(ann, ml)
+            out.append((toks, lens))
+        cur.wait_stream(s_enc); cur.wait_stream(s_dec)
+        return out
+
     def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8, persistent: Optional[bool] = None,
                       ignore_eol: bool = False):
         """Greedy decode of every image in the batch; returns (tokens [B,maxlen] int32, lengths [B] int32, steps).
