@@ -111,17 +111,15 @@ def main(args):
                                 break
                             fpp.write(' ' + worddicts_r[vv])
                         fpp.write('\n')
-                    if args.greedy_valid:          # two-stream pipeline: encoder of image i+1 next to the token loop of image i
-                        imgs = [torch.as_tensor((np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]).to(eng.device) for vx, _ in valid for xx in vx]
+                    # one unpadded image at a time as in the reference (S:661-672), as a two-stream pipeline: the encoder of image i+1 runs next to
+                    # the search / token loop of image i; results are read from the device once per validation pass
+                    imgs = [torch.as_tensor((np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]).to(eng.device) for vx, _ in valid for xx in vx]
+                    if args.greedy_valid:
                         for toks, lens in eng.greedy_decode_images(imgs, 100):
                             emit(toks[0, :int(lens[0])].tolist())
                     else:
-                        for vx, _ in valid:
-                            for xx in vx:
-                                xx_pad = (np.moveaxis(xx, 0, -1) / 255.).astype(np.float32)[None]
-                                annot, _ = eng.dense_net(xx_pad, None, training=False)
-                                ss, _, _ = eng.get_sample(annot, 10, 100)
-                                emit(ss)
+                        for ss in eng.get_sample_images(imgs, 10, 100):
+                            emit(ss)
                 say('valid set decode done')
             if uidx % validFreq == 0 and rank == 0:
                 probs = []

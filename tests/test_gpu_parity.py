@@ -374,6 +374,27 @@ def test_fused_bn_backward_reduce_matches_separate_kernels(report):
     assert e0 <= 2e-5 and e <= 2e-5 and n_fused == n_plain - 48, (c0, e0, e, n_plain, n_fused)
 
 
+def test_two_stream_decode_pipelines_match_per_image_calls():
+    """greedy_decode_images / get_sample_images (encoder of image i+1 overlapping the decode of image i on a second stream) return exactly what the
+    per-image calls return."""
+    imgs = []
+    for i, (H, W) in enumerate([(40, 120), (33, 75), (64, 200), (48, 90), (40, 120)]):
+        x, _, _, _ = make_batch(700 + i, 1, H, W, 3)
+        imgs.append(x)
+    P = O.calibrate_moving(O.lively_params(6), imgs[0], np.ones(imgs[0].shape[:3], np.float32))
+    P = dict(P); P["bo"] = P["bo"].copy(); P["bo"][0] += 2.0
+    eng = engine_with(P)
+    dev = [torch.as_tensor(x).cuda() for x in imgs]
+    with eng.decoding():
+        pipe = eng.greedy_decode_images(dev, [10, 12, 14, 16, 18])
+        beams = eng.get_sample_images(dev, 5, 15)
+        for i, x in enumerate(dev):
+            ann, _ = eng.dense_net(x, None, training=False)
+            t, l, _ = eng.greedy_decode(ann, [10, 12, 14, 16, 18][i])
+            assert torch.equal(pipe[i][0], t) and torch.equal(pipe[i][1], l), i
+            assert list(eng.get_sample(ann, 5, 15)[0]) == beams[i], i
+
+
 def test_decoding_context_caches_the_fused_coverage_filter():
     """WAPEngine.decoding(): Q' = Q*U_f computed once and handed to the decode kernels (wap_set_fused_coverage_filter) - same tokens and
     beam samples as the per-call recomputation, for the cluster kernel (B <= 7), the grid-wide kernel and the beam search."""

@@ -389,6 +389,45 @@ class WAPEngine:
         cur.wait_stream(s_enc); cur.wait_stream(s_dec)
         return out
 
+    def get_sample_images(self, images, k: int = 10, maxlen: int = 100):
+        """Beam search (get_sample + pick, S:669-672) over a sequence of single images [1,H,W,1] with the same two-stream pipeline as
+        greedy_decode_images; the per-image results stay on the device until the end (one synchronisation for the whole list).  Images whose
+        annotation grid exceeds the persistent kernel's limits take the host-bookkeeping path in place.  Returns [picked token list]."""
+        cur = torch.cuda.current_stream()
+        if not hasattr(self, "_pipe_streams"):
+            self._pipe_streams = (torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        s_enc, s_dec = self._pipe_streams
+        s_enc.wait_stream(cur); s_dec.wait_stream(cur)
+        pend = []
+        for im in images:
+            with torch.cuda.stream(s_enc):
+                ann, _ = self.dense_net(im, None, training=False)
+                ev = torch.cuda.Event(); ev.record(s_enc)
+            _, h, w, _ = ann.shape
+            with torch.cuda.stream(s_dec):
+                s_dec.wait_event(ev)
+                ann.record_stream(s_dec)
+                if not self.beam_supported(h, w, k, maxlen):
+                    pend.append(self._get_sample_host(ann, k, maxlen)[0]); continue
+                tokens = torch.zeros((k, maxlen), dtype=torch.int32, device=self.device)
+                lengths = torch.zeros((k,), dtype=torch.int32, device=self.device)
+                scores = torch.zeros((k,), dtype=torch.float32, device=self.device)
+                meta = torch.zeros((4,), dtype=torch.int32, device=self.device)
+                ws = self._buf(("greedy_p",), self.L.wap_greedy_persistent_workspace_floats(k, h, w))
+                _lib.check(self.L.wap_beam_decode_persistent(_stream(), _p(self.P.flat), _p(ann), h, w, k, maxlen, _p(tokens), _p(lengths), _p(scores),
+                                                             _p(meta), _p(ws)), "wap_beam_decode_persistent")
+                pend.append((tokens, lengths, meta))
+        cur.wait_stream(s_enc); cur.wait_stream(s_dec)
+        torch.cuda.current_stream().synchronize()
+        out = []
+        for p in pend:
+            if isinstance(p, tuple):
+                tokens, lengths, meta = p
+                best = int(meta[1]); out.append(tokens[best, : int(lengths[best])].tolist())
+            else:
+                out.append(list(p))
+        return out
+
     def greedy_decode(self, annotation: torch.Tensor, maxlen: int = 100, check_every: int = 8, persistent: Optional[bool] = None,
                       ignore_eol: bool = False):
         """Greedy decode of every image in the batch; returns (tokens [B,maxlen] int32, lengths [B] int32, steps).
