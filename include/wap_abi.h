@@ -206,6 +206,10 @@ int wap_debug_capture(int layer, float* buf);
 int wap_debug_wgrad(float* buf, int idesc_xor);
 int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
                 int accumulate, double* stats);
+/* the same with the transposed store (D[n*ldd + m]), a bias row and split-K (K spread over grid.z, partial sums ADDED with fp32 atomics into a
+ * zero-filled D) - the form the BPTT's coverage-backward GEMM uses */
+int wap_tc_gemm_ex(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
+                   int transpose_out, int splitk, const float* bias);
 /* 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) with Wt[Nrows, 9*C] (K-major, row n = output channel,
  * k = tap*C + ci; rows >= N zero) -> D[B*H*W, N] */
 int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
@@ -253,14 +257,17 @@ int wap_set_fused_coverage_filter(const float* qfused);
 int wap_set_pdl(int on);
 int wap_get_pdl(void);
 /* ---- debug: CTA (0,0) of every following tcgen05 GEMM launch writes clock64() stamps [k-block][TMA issue, data landed, split done,
- * MMA issued] into trace (device int64, >= 4 * k-blocks); NULL turns it off */
+ * MMA issued] into trace (device int64, >= 1028 entries), and at [1024..1027] the stamps kernel entry (after the PDL wait), set-up done,
+ * accumulator ready (epilogue start) and epilogue done; NULL turns it off */
 int wap_debug_tc_trace(long long* trace);
 /* ---- debug: the bounded mbarrier waits of the tcgen05 kernels trap instead of hanging; the first call arms a note in host-mapped
  * memory, later calls return them: out[1] = count, then notes of 8 ints from out[8]: {site + 100*k-block, blockIdx.x, blockIdx.y, warp,
  * parity, gridDim.x, gridDim.y, blockDim.x} */
 int wap_debug_trap_info(int* out256);
-/* ---- debug: 0 = the training scan launches the GRU gate kernels separately instead of evaluating them inside the skinny GEMMs */
-int wap_debug_set_fuse_gates(int on);
+/* ---- debug / A-B: fusion of the training scans (default 3).  bit 0: the forward scan evaluates the GRU gates inside the consuming skinny
+ * GEMMs; bit 1: the BPTT does the same for the GRU backward passes and runs dalpha / softmax backward / dz as one kernel (four dependent
+ * kernels per time step instead of eight).  0 = every elementwise stage is its own launch. */
+int wap_debug_set_fuse_gates(int mask);
 /* ---- debug / A-B: which kernel wap_greedy_decode_persistent uses: 0 (default) = one 16-CTA cluster per image, no grid barrier
  * (csrc/decoder_cluster.cu) whenever the annotation grid fits it, 1 = always the grid-wide weight-stationary kernel (csrc/decoder_persist.cu) */
 int wap_debug_set_greedy_impl(int impl);

@@ -374,6 +374,44 @@ def test_fused_bn_backward_reduce_matches_separate_kernels(report):
     assert e0 <= 2e-5 and e <= 2e-5 and n_fused == n_plain - 48, (c0, e0, e, n_plain, n_fused)
 
 
+@pytest.mark.parametrize("B,H,W,cap,ragged", [(2, 50, 150, 4, True), (8, 128, 512, 12, False), (3, 64, 100, 7, True)])
+def test_fused_bptt_matches_separate_kernels(report, B, H, W, cap, ragged):
+    """BPTT with the GRU backward passes evaluated inside the consuming skinny GEMMs and dalpha / softmax backward / dz as one kernel (the
+    default, wap_debug_set_fuse_gates bit 1) == the eight separate launches per time step.  ONE forward, backward twice on the same saved
+    activations: same gradients up to the order of the fp32 atomics, 5 launches per time step fewer (11 -> 6; dependent chain 8 -> 4)."""
+    import ctypes as C
+    import wap_b200
+    from wap_b200.engine import _p, _stream
+    P = O.lively_params(5)
+    x, xm, y, ym = make_batch(34, B, H, W, cap, ragged)
+    eng = engine_with(P, use_graphs=False)
+    L = wap_b200._lib.lib()
+    c0 = float(eng.forward_backward(x, y, xm, ym, True, 9)); g0 = eng.grads.clone()
+    xd, yd, xmd, ymd = eng._dev(x, torch.float32), eng._dev(y, torch.int32), eng._dev(xm, torch.float32), eng._dev(ym, torch.float32)
+    T = y.shape[0]
+
+    def backward_again():
+        eng.grads.zero_()
+        n0 = eng.launch_count()
+        wap_b200._lib.check(eng.L.wap_train_backward(_stream(), _p(eng.P.flat), _p(eng.grads), _p(xd), B, H, W, _p(eng._ws[("ann",)]), _p(eng._ws[("amask",)]),
+                                                     _p(yd), _p(ymd), T, 1, C.c_uint32(9), _p(eng._ws[("dann",)]), _p(eng._ws[("enc",)]), _p(eng._ws[("dec",)])),
+                            "wap_train_backward")
+        return eng.grads.clone(), eng.launch_count() - n0
+    g_fused, n_fused = backward_again()
+    try:
+        L.wap_debug_set_fuse_gates(1)
+        g_plain, n_plain = backward_again()
+    finally:
+        L.wap_debug_set_fuse_gates(3)
+    e0 = rel_l2(g_fused.cpu().numpy(), g0.cpu().numpy()); e = rel_l2(g_fused.cpu().numpy(), g_plain.cpu().numpy())
+    names = {n: (o, int(np.prod(sh))) for n, o, sh, f in eng.P.table if not f & 2}
+    gmax = float(g_plain.abs().max())      # V_a_b shifts every energy of a softmax: its gradient is analytically 0 and numerically pure noise
+    worst = max((rel_l2(g_fused[o:o + k].cpu().numpy(), g_plain[o:o + k].cpu().numpy()), n) for n, (o, k) in names.items()
+                if float(g_plain[o:o + k].abs().max()) > 1e-6 * gmax)
+    report.add("bptt_fused", f"grads_rel_l2_vs_unfused_B{B}", e, 2e-5, extra=dict(rerun_noise=e0, worst=worst, launches=(n_plain, n_fused)))
+    assert e0 <= 2e-5 and e <= 2e-5 and worst[0] <= 2e-4 and n_fused == n_plain - 5 * T, (c0, e0, e, worst, n_plain, n_fused)
+
+
 def test_two_stream_decode_pipelines_match_per_image_calls():
     """greedy_decode_images / get_sample_images (encoder of image i+1 overlapping the decode of image i on a second stream) return exactly what the
     per-image calls return."""

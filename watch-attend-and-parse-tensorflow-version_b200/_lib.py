@@ -67,6 +67,7 @@ SIGNATURES = {
     "wap_debug_capture": (_i, [_i, _vp]),
     "wap_debug_wgrad": (_i, [_vp, _i]),
     "wap_tc_gemm": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _vp]),
+    "wap_tc_gemm_ex": (_i, [_vp, _vp, _i, _vp, _vp, _i, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "wap_tc_conv3x3": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _i, _i, _vp, _i, _vp]),
     "wap_tc_conv3x3_rowtile": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp, _i, _vp]),
     "wap_tc_wgrad_1x1": (_i, [_vp, _vp, _i, _vp, _i, _i, _i, _i, _vp, _i, _i]),

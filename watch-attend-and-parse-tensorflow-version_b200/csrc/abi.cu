@@ -308,6 +308,11 @@ int wap_tc_gemm(void* stream, const float* A, int lda, const float* Bt, const fl
   TcEpi e{D, ldd, accumulate, stats, nullptr, 0};
   return tc_gemm(ST(stream), A, lda, Bt, Bt_lo, ldb, M, N, K, e, kProfOtherGemm);
 }
+int wap_tc_gemm_ex(void* stream, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, float* D, int ldd, int M, int N, int K,
+                   int transpose_out, int splitk, const float* bias) {
+  TcEpi e{D, ldd, 0, nullptr, bias, transpose_out};
+  return tc_gemm(ST(stream), A, lda, Bt, Bt_lo, ldb, M, N, K, e, kProfOtherGemm, splitk);
+}
 int wap_tc_conv3x3(void* stream, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N,
                    float* D, int ldd, double* stats) {
   TcEpi e{D, ldd, 0, stats, nullptr, 0};
@@ -353,7 +358,7 @@ int wap_debug_trap_info(int* out256) {   /* arms the notes on first call; copies
   return 0;
 }
 int wap_debug_tc_trace(long long* trace) { wap::g_tc_trace = trace; return 0; }
-int wap_debug_set_fuse_gates(int on) { wap::g_fuse_gates = on ? 1 : 0; return 0; }
+int wap_debug_set_fuse_gates(int mask) { wap::g_fuse_gates = mask & 3; return 0; }
 int wap_debug_set_greedy_impl(int impl) { wap::g_greedy_impl = impl & 1; wap::g_cluster_prof = (impl >> 1) & 1; return 0; }
 int wap_set_overlap(int on) { cur()->overlap = on ? 1 : 0; return 0; }
 int wap_get_overlap(void) { return cur()->overlap; }

@@ -13,7 +13,7 @@ namespace wap {
 // 16x256 weight block exactly once with 16 independent 128-bit loads per thread in flight, and
 // adds its partial products with fp32 atomics into outputs pre-initialised with the bias.
 constexpr int kSkRows = 16, kSkKC = 16, kSkCols = 256;
-struct SkinnySeg { const float* W; int ldw, N; float* out; int ldo; };
+struct SkinnySeg { const float* W; int ldw, N; float* out; int ldo; int koff = 0, kcount = 0; };   // this segment multiplies X[koff : koff + kcount] (kcount 0 = K)
 struct SkinnyArgs {
   const float* X; int ldx;      // X[b*ldx + k]   (or gathered rows: table + ids[b]*ldx, zero row if ids[b] < 0)
   const int* ids;
@@ -25,9 +25,15 @@ struct SkinnyArgs {
   // the gate kernel from the dependent chain of the time step.
   //   gen 1: X = pre_h  from (G1 raw [ld 3kN], UH, h_prev, mask)          stores r|z -> oRZ [ld 2kN], prop -> oProp, pre_h -> oX
   //   gen 2: X = h_new  from (G2 raw [ld 2kN], PH2, CH, pre_h, mask)       stores r|z -> oRZ,        prop -> oProp, h    -> oX
+  // BPTT: the elementwise GRU backward evaluated the same way (X = a row of gate gradients); the direct (non-GEMM) term of the carried
+  // gradient is ADDED atomically into oAcc, which the caller zero-fills (its other contributions arrive by atomics as well).
+  //   gen 3: X = [dPH2 | dG2 r | dG2 z | dCH] (1024) from (dh_in = gA, dHlog = gB, RZ2 = gG [ld 2kN], prop2 = gC, pre_h = gD, PH2 = gE, mask);
+  //          seg[0] must be the dctx segment (koff 256), seg[1] the dpre_h segment (koff 0); X -> oX [ld 4kN]; direct term -> oAcc (dpre_h)
+  //   gen 4: X = [dG1 r | dG1 z | dUH] (768) from (dpre_h = gA, RZ1 = gG, prop1 = gC, UH = gD, h_prev = gE, mask);
+  //          X -> oX [ld 3kN]; dE_h -> oProp; direct term -> oAcc (dh_prev)
   int gen = 0;
-  const float *gG = nullptr, *gA = nullptr, *gB = nullptr, *gC = nullptr, *gmask = nullptr;
-  float *oRZ = nullptr, *oProp = nullptr, *oX = nullptr;
+  const float *gG = nullptr, *gA = nullptr, *gB = nullptr, *gC = nullptr, *gD = nullptr, *gE = nullptr, *gmask = nullptr;
+  float *oRZ = nullptr, *oProp = nullptr, *oX = nullptr, *oAcc = nullptr;
 };
 int skinny_gemm(cudaStream_t st, SkinnyArgs a);
 
@@ -74,6 +80,9 @@ struct StepCtx {
   float *prev_RZ2 = nullptr, *prev_prop2 = nullptr;
   // training scan: coverage chain (im2col + GEMM, depends only on ap_in) on a side stream, next to the GRU-1 half of the step
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // ... and one step ahead: alpha_past of step t+1 is final after softmax_ctx of step t, so step t forks the coverage chain of step t+1
+  // right there (cov_next) instead of step t+1 forking it after the ctx GEMM of step t; cov_ready = the previous step already did
+  int cov_next = 0, cov_ready = 0;
 };
 int decoder_step(cudaStream_t st, const StepCtx& c);
 int gru2_gate(cudaStream_t st, float* G2, const float* PH2, const float* CH, const float* pre_h, const float* y_mask, float* prop2, float* h_new,

@@ -1,4 +1,6 @@
 // Decoder time-step kernels (forward).  See decoder.cuh for the data flow.
+#include <algorithm>
+
 #include "decoder.cuh"
 #include "tc_gemm.cuh"
 
@@ -28,15 +30,18 @@ __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
   int s = 0;
   while (s + 1 < a.nseg && (int)blockIdx.x >= a.tile0[s + 1]) ++s;
   const SkinnySeg sg = a.seg[s];
+  const bool first_tile = (int)blockIdx.x == a.tile0[s];
   const int n = ((int)blockIdx.x - a.tile0[s]) * kSkCols + threadIdx.x * 4;
   const int k0 = blockIdx.y * kSkKC;
+  const int Ks = sg.kcount > 0 ? sg.kcount : a.K;
+  if (k0 >= Ks) return;
   const bool vec = ((sg.ldw & 3) == 0) && (n + 3 < sg.N);
   float4 wv[kSkKC];
 #pragma unroll
   for (int kk = 0; kk < kSkKC; ++kk) {
     const int k = k0 + kk;
     float4 v = make4(0.f);
-    if (k < a.K && n < sg.N) {
+    if (k < Ks && n < sg.N) {
       const float* q = sg.W + (size_t)k * sg.ldw + n;
       if (vec) v = ldg4(q);
       else {
@@ -52,10 +57,10 @@ __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
     __syncthreads();
     for (int i = threadIdx.x; i < kSkRows * kSkKC; i += 64) {
       const int bb = i / kSkKC, kk = i % kSkKC;
-      const int b = b0 + bb, k = k0 + kk;
+      const int b = b0 + bb, k = k0 + kk + sg.koff;       // k indexes X
       float v = 0.f;
-      if (b < a.Bn && k < a.K) {
-        if (a.gen != 0) {
+      if (b < a.Bn && k0 + kk < Ks) {
+        if (a.gen == 1 || a.gen == 2) {
           const bool masked = a.gmask != nullptr;
           const float m = masked ? a.gmask[b] : 1.f;
           const size_t e = (size_t)b * kN + k;
@@ -70,6 +75,32 @@ __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
           if (blockIdx.x == 0) {
             a.oRZ[(size_t)b * 2 * kN + k] = r; a.oRZ[(size_t)b * 2 * kN + kN + k] = z;
             a.oProp[e] = p; a.oX[e] = v;
+          }
+        } else if (a.gen == 3) {       // GRU-2 backward (S:292-306 differentiated)
+          const int part = k / kN, j = k - part * kN;
+          const size_t e = (size_t)b * kN + j;
+          const float m = a.gmask != nullptr ? a.gmask[b] : 1.f;
+          const float dh = a.gA[e] + a.gB[e];
+          const float r = a.gG[(size_t)b * 2 * kN + j], z = a.gG[(size_t)b * 2 * kN + kN + j];
+          const float p = a.gC[e], ph = a.gD[e];
+          const float dhn = m * dh;
+          const float dpp = dhn * (1.f - z) * (1.f - p * p);
+          v = part == 0 ? dpp * r : part == 1 ? dpp * a.gE[e] * r * (1.f - r) : part == 2 ? dhn * (ph - p) * z * (1.f - z) : dpp;
+          if (first_tile && (s == 0 || part == 0)) a.oX[(size_t)b * 4 * kN + k] = v;
+          if (first_tile && s == 1 && part == 0) atomicAdd(a.oAcc + e, (1.f - m) * dh + dhn * z);
+        } else if (a.gen == 4) {       // GRU-1 backward (S:273-289 differentiated)
+          const int part = k / kN, j = k - part * kN;
+          const size_t e = (size_t)b * kN + j;
+          const float m = a.gmask != nullptr ? a.gmask[b] : 1.f;
+          const float d = a.gA[e];
+          const float r = a.gG[(size_t)b * 2 * kN + j], z = a.gG[(size_t)b * 2 * kN + kN + j];
+          const float p = a.gC[e];
+          const float dp_ = m * d;
+          const float dpp = dp_ * (1.f - z) * (1.f - p * p);
+          v = part == 0 ? dpp * a.gD[e] * r * (1.f - r) : part == 1 ? dp_ * (a.gE[e] - p) * z * (1.f - z) : dpp * r;
+          if (first_tile) {
+            a.oX[(size_t)b * 3 * kN + k] = v;
+            if (part == 2) { a.oProp[e] = dpp; atomicAdd(a.oAcc + e, (1.f - m) * d + dp_ * z); }
           }
         } else if (a.ids != nullptr) { const int id = a.ids[b]; if (id >= 0) v = __ldg(a.X + (size_t)id * a.ldx + k); }
         else v = __ldg(a.X + (size_t)b * a.ldx + k);
@@ -101,8 +132,14 @@ __global__ void __launch_bounds__(64) skinny_gemm_kernel(const SkinnyArgs a) {
 int skinny_gemm(cudaStream_t st, SkinnyArgs a) {
   WAP_REQUIRE(a.nseg >= 1 && a.nseg <= 4, "skinny_gemm: nseg=%d", a.nseg);
   a.tile0[0] = 0;
-  for (int s = 0; s < a.nseg; ++s) a.tile0[s + 1] = a.tile0[s] + cdiv(a.seg[s].N, kSkCols);
-  dim3 grid(a.tile0[a.nseg], cdiv(a.K, kSkKC));
+  int kmax = 0;
+  for (int s = 0; s < a.nseg; ++s) {
+    a.tile0[s + 1] = a.tile0[s] + cdiv(a.seg[s].N, kSkCols);
+    const int ks = a.seg[s].kcount > 0 ? a.seg[s].kcount : a.K;
+    WAP_REQUIRE(a.seg[s].koff >= 0 && a.seg[s].koff + ks <= a.K, "skinny_gemm: segment %d reads X[%d:%d] of %d", s, a.seg[s].koff, a.seg[s].koff + ks, a.K);
+    kmax = std::max(kmax, ks);
+  }
+  dim3 grid(a.tile0[a.nseg], cdiv(kmax, kSkKC));
   WAP_CHECK(launch_pdl(skinny_gemm_kernel, grid, 64, 0, st, a));
   WAP_LAUNCH_CHECK();
   return 0;
@@ -339,14 +376,16 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
     WAP_TRY(fill_rows(st, f));
   }
   const bool side_cov = c.tc_mode != 0 && c.side != nullptr;
-  if (side_cov) {   // ap_in is final (previous step's softmax): start the coverage chain next to the GRU-1 half
+  auto fork_cov = [&](const float* ap) -> int {     // coverage chain of one step on the side stream: im2col + GEMM -> COV
     WAP_CHECK(cudaEventRecord(c.ev_fork, st)); WAP_CHECK(cudaStreamWaitEvent(c.side, c.ev_fork, 0));
-    WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, c.side, c.ap_in, c.Ppat, Bn, c.h, c.w));
+    WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, c.side, ap, c.Ppat, Bn, c.h, c.w));
     WAP_LAUNCH_CHECK();
     WAP_TRY(tc_gemm(c.side, c.Ppat, 128, c.qfT_hi, c.tc_mode >= 2 ? c.qfT_lo : nullptr, 128, Bn * L, kNA, 128,
                     TcEpi{c.COV, kNA, 0, nullptr, p + P.U_f_b, 0}, kProfCovGemm));
     WAP_CHECK(cudaEventRecord(c.ev_join, c.side));
-  }
+    return 0;
+  };
+  if (side_cov && !c.cov_ready) WAP_TRY(fork_cov(c.ap_in));   // ap_in is final (previous step's softmax): next to the GRU-1 half
   {   // h_prev * [U_hz_hr | U_rh]     (fused scan: h_prev itself is the GRU-2 gate of the previous step, evaluated here)
     SkinnyArgs a; a.X = c.h_prev; a.ldx = kN; a.ids = nullptr; a.Bn = Bn; a.K = kN; a.nseg = 2;
     a.seg[0] = {p + P.U_hz_hr, 2 * kN, 2 * kN, c.G1, 3 * kN};
@@ -375,6 +414,7 @@ int decoder_step(cudaStream_t st, const StepCtx& c) {
   if (side_cov) {
     WAP_CHECK(cudaStreamWaitEvent(st, c.ev_join, 0));
     WAP_TRY(attention_tail(st, p, c.ann, c.watch, c.a_mask, c.shared, Bn, L, c.SP, c.ap_in, c.COV, c.TANH, c.E, c.alpha, c.ap_out, c.ctx));
+    if (c.cov_next) WAP_TRY(fork_cov(c.ap_out));      // COV / Ppat of this step are consumed: the next step's chain starts beside the ctx GEMM
   } else if (c.tc_mode != 0) {   // coverage on tensor cores: im2col patches [Bn*L,128] x Q'^T[512][128]  (+ U_f_b)
     WAP_CHECK(launch_pdl(cov_im2col_kernel, cdiv(Bn * L * 32, 256), 256, 0, st, c.ap_in, c.Ppat, Bn, c.h, c.w));
     WAP_LAUNCH_CHECK();

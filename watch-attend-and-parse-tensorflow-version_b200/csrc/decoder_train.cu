@@ -10,6 +10,7 @@
 //   * every weight gradient is ONE GEMM over all T*B rows after the time loop instead of T
 //     rank-B updates inside it; only the data gradients stay in the sequential loop.
 #include <algorithm>
+#include <cstdlib>
 
 #include "decoder.cuh"
 #include "tc_gemm.cuh"
@@ -24,7 +25,7 @@ int attn_precompute(cudaStream_t st, const float* params, const float* ann, cons
 
 // ------------------------------------------------------------------------------------ workspace
 constexpr int kLdA = 4 * kN, kLdB = 3 * kN;
-int g_fuse_gates = 1;       // wap_debug_set_fuse_gates()
+int g_fuse_gates = 3;       // wap_debug_set_fuse_gates(): bit 0 forward GRU gates inside the consuming skinny GEMMs, bit 1 the same for the BPTT + fused attention backward
 struct DecTrainWs {
   // forward (saved)
   float *EMB, *G1, *H, *UH, *PROP1, *PREH, *SP, *G2, *PH2, *CH, *PROP2, *TANH, *ALPHA, *AP, *CTX;
@@ -34,6 +35,7 @@ struct DecTrainWs {
   // backward
   float *dLG, *dMO, *dHlog, *dCTX, *dEMB, *dG1, *dEh, *dUH, *dSP, *dG2, *dCH, *dPH2, *DZ, *dWatch, *DF;
   float *dAP0, *dAP1, *dalpha, *de, *dh0, *dh1, *dpre_h, *dQf, *dmean;
+  float *DH, *DPREH;         // fused BPTT: per-step carried gradients [(T+1)B, 256] / [TB, 256], zero-filled once (every contribution is an atomic add)
   float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
   float *qf_hi, *qf_lo, *Ua_hi, *Ua_lo, *UaT_hi, *UaT_lo;    // tensor-core operand copies (3xTF32 hi/lo parts)
   float *Ppat, *qfT_hi, *qfT_lo;                              // coverage im2col patches [B*L,128], Q'^T [512][128]
@@ -55,10 +57,11 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   //   DA row (kLdA = 1024): [dPH2 | dG2 (r|z) | dCH]     DB row (kLdB = 768): [dG1 (r|z) | dUH]
   w.dPH2 = take(TB * kLdA); w.dG2 = w.dPH2 + kN; w.dCH = w.dPH2 + 3 * kN;
   w.dG1 = take(TB * kLdB); w.dUH = w.dG1 + 2 * kN;
-  w.dEh = take(TB * kN); w.dSP = take(TB * kNA); w.DZ = take(TB * L * kNA); w.dWatch = take(BL * kNA); w.DF = take(BL * 124);
+  w.dEh = take(TB * kN); w.dSP = take(TB * kNA); w.DZ = take(TB * L * kNA); w.dWatch = take(BL * kNA); w.DF = take(BL * 124 * 2);     // two DF buffers (split-K ping-pong of the fused BPTT)
   w.dAP0 = take(BL); w.dAP1 = take(BL); w.dalpha = take(BL); w.de = take(BL);
   w.dh0 = take((size_t)B * kN); w.dh1 = take((size_t)B * kN); w.dpre_h = take((size_t)B * kN);
   w.dQf = take((size_t)kCovTaps * kNA); w.dmean = take((size_t)B * kD);
+  w.DH = take((TB + B) * kN); w.DPREH = take(TB * kN);
   // stacked transposes matching the concatenated operands: [T_Wczr; T_Wchnl] (768x684), [T_Urhnl; T_Uhzhrnl] (768x256), [T_Uhzhr; T_Urh] (768x256)
   w.T_Wczr = take((size_t)2 * kN * kD); w.T_Wchnl = take((size_t)kN * kD); w.T_Urhnl = take((size_t)kN * kN);
   w.T_Uhzhrnl = take((size_t)2 * kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
@@ -250,7 +253,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
     WAP_TRY(fill_rows(st, f));
   }
   SideStreams* sl = (tc && overlap_enabled()) ? side_streams() : nullptr;
-  const bool fuse = g_fuse_gates != 0;     // GRU gates evaluated inside the consuming skinny GEMMs (2 kernels less per time step)
+  const bool fuse = (g_fuse_gates & 1) != 0;     // GRU gates evaluated inside the consuming skinny GEMMs (2 kernels less per time step)
   for (int t = 0; t < T; ++t) {
     const size_t r = (size_t)t * B;
     StepCtx c;
@@ -268,7 +271,7 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
       c.prev_G2 = W.G2 + q * 2 * kN; c.prev_PH2 = W.PH2 + q * kN; c.prev_CH = W.CH + q * kN; c.prev_pre_h = W.PREH + q * kN; c.prev_mask = y_mask + q;
       c.prev_RZ2 = W.RZ2 + q * 2 * kN; c.prev_prop2 = W.PROP2 + q * kN;
     }
-    if (sl != nullptr) { c.side = sl->s[2]; c.ev_fork = sl->fork[2]; c.ev_join = sl->done[6]; }
+    if (sl != nullptr) { c.side = sl->s[2]; c.ev_fork = sl->fork[2]; c.ev_join = sl->done[6]; c.cov_ready = t > 0; c.cov_next = t + 1 < T; }
     WAP_TRY(decoder_step(st, c));
   }
   if (fuse) {   // the GRU-2 gate of the last step has no following step to evaluate it
@@ -403,6 +406,76 @@ dz_kernel(const float* __restrict__ TANH, const float* __restrict__ de, const fl
   atomicAdd(s, sp.x); atomicAdd(s + 1, sp.y); atomicAdd(s + 2, sp.z); atomicAdd(s + 3, sp.w);
   atomicAdd(dVa + c, dv.x); atomicAdd(dVa + c + 1, dv.y); atomicAdd(dVa + c + 2, dv.z); atomicAdd(dVa + c + 3, dv.w);
   if (threadIdx.x == 0) atomicAdd(dVab, sde);
+}
+// Attention backward of one time step in ONE kernel (dalpha_kernel + softmax_bwd_kernel + dz_kernel).  The softmax backward needs
+// s_b = sum_l alpha_l * dalpha_l over the whole image, but dalpha_l = a_l . dctx + dAP_l and sum_l alpha_l a_l is the context vector the
+// forward saved, so s_b = ctx_b . dctx_b + sum_l alpha_l dAP_l: a 684 + L term dot product every CTA recomputes - no grid-wide reduction.
+// One CTA = 16 positions of one image: warp w owns the annotation dot products of positions 4w..4w+3 (4 independent accumulators, one
+// interleaved butterfly), then the dz body as above with the tanh rows already in flight.
+template <int PIX> __global__ void __launch_bounds__(128)
+attn_bwd_kernel(const float* __restrict__ ann, const float* __restrict__ dctx, const float* __restrict__ ctx,
+                const float* __restrict__ alpha, const float* __restrict__ dAP, const float* __restrict__ TANH,
+                const float* __restrict__ Va, float* __restrict__ DZ, float* __restrict__ dSP, float* __restrict__ dVa,
+                float* __restrict__ dVab, int L, float4* __restrict__ zero, int zero_n4) {
+  pdl_sync();
+  constexpr int PW = PIX / 4;           // positions per warp
+  __shared__ __align__(16) float s_d[kD];
+  __shared__ float red[33];
+  __shared__ float s_de[PIX];
+  const int b = blockIdx.y, l0 = blockIdx.x * PIX, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, c = tid * 4;
+  float4 t[PIX];
+#pragma unroll
+  for (int j = 0; j < PIX; ++j) t[j] = ldg4(TANH + ((size_t)b * L + min(l0 + j, L - 1)) * kNA + c);
+  float s = 0.f;
+  for (int i = tid; i < kD; i += 128) { const float d = dctx[(size_t)b * kD + i]; s_d[i] = d; s = fmaf(ctx[(size_t)b * kD + i], d, s); }
+  for (int l = tid; l < L; l += 128) s = fmaf(alpha[(size_t)b * L + l], dAP[(size_t)b * L + l], s);
+  s = block_sum(s, red);
+  // split-K coverage-backward GEMM: this step's kernel clears the DF buffer the step after next accumulates into (see the BPTT loop)
+  for (int i = (blockIdx.y * gridDim.x + blockIdx.x) * 128 + tid; i < zero_n4; i += gridDim.x * gridDim.y * 128) zero[i] = make4(0.f);
+  float acc[PW];
+  const float* arow[PW];
+#pragma unroll
+  for (int q = 0; q < PW; ++q) { acc[q] = 0.f; arow[q] = ann + ((size_t)b * L + min(l0 + warp * PW + q, L - 1)) * kD; }
+  for (int i = lane * 4; i < kD; i += 128) {
+    const float4 dv = *reinterpret_cast<const float4*>(s_d + i);
+#pragma unroll
+    for (int q = 0; q < PW; ++q) {
+      const float4 av = ldg4(arow[q] + i);
+      acc[q] = fmaf(av.x, dv.x, acc[q]); acc[q] = fmaf(av.y, dv.y, acc[q]); acc[q] = fmaf(av.z, dv.z, acc[q]); acc[q] = fmaf(av.w, dv.w, acc[q]);
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1)
+#pragma unroll
+    for (int q = 0; q < PW; ++q) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+  if (lane < PW) {
+    const int l = l0 + warp * PW + lane;
+    float da = acc[0];
+#pragma unroll
+    for (int q = 1; q < PW; ++q) if (lane == q) da = acc[q];
+    s_de[warp * PW + lane] = l < L ? alpha[(size_t)b * L + l] * (da + dAP[(size_t)b * L + l] - s) : 0.f;
+  }
+  __syncthreads();
+  const float4 va = ldg4(Va + c);
+  float4 sp = make4(0.f), dv = make4(0.f);
+  float sde = 0.f;
+#pragma unroll
+  for (int j = 0; j < PIX; ++j) {
+    if (l0 + j >= L) break;
+    const size_t row = (size_t)b * L + l0 + j;
+    const float d = s_de[j];
+    float4 z;
+    z.x = d * va.x * (1.f - t[j].x * t[j].x); z.y = d * va.y * (1.f - t[j].y * t[j].y);
+    z.z = d * va.z * (1.f - t[j].z * t[j].z); z.w = d * va.w * (1.f - t[j].w * t[j].w);
+    *reinterpret_cast<float4*>(DZ + row * kNA + c) = z;
+    sp.x += z.x; sp.y += z.y; sp.z += z.z; sp.w += z.w;
+    dv.x = fmaf(d, t[j].x, dv.x); dv.y = fmaf(d, t[j].y, dv.y); dv.z = fmaf(d, t[j].z, dv.z); dv.w = fmaf(d, t[j].w, dv.w);
+    sde += d;
+  }
+  float* o = dSP + (size_t)b * kNA + c;
+  atomicAdd(o, sp.x); atomicAdd(o + 1, sp.y); atomicAdd(o + 2, sp.z); atomicAdd(o + 3, sp.w);
+  atomicAdd(dVa + c, dv.x); atomicAdd(dVa + c + 1, dv.y); atomicAdd(dVa + c + 2, dv.z); atomicAdd(dVa + c + 3, dv.w);
+  if (tid == 0) atomicAdd(dVab, sde);
 }
 // dWatch[i] = sum_t DZ[t][i]   (one pass after the scan instead of a read-modify-write of dWatch every step)
 __global__ void __launch_bounds__(256)
@@ -560,9 +633,6 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_CHECK(cudaMemsetAsync(W.dAP0, 0, sizeof(float) * B * L, st));
   WAP_CHECK(cudaMemsetAsync(W.dSP, 0, sizeof(float) * TB * kNA, st));
   float* dh_in = W.dh0; float* dh_out = W.dh1; float* dAP_in = W.dAP0; float* dAP_out = W.dAP1;
-  // Two chains per step.  Main stream: gru2_bwd -> [dG2|dCH] -> dctx -> dalpha -> softmax_bwd -> dz -> dSP -> dpre_h -> gru1_bwd ->
-  // [dG1|dUH] -> dh.  Side stream: [dPH2|dG2] -> dpre_h (joins before gru1_bwd) and the coverage backward DZ -> DF -> dAP (joins before
-  // the next step's dalpha).
   SideStreams* sl = overlap_enabled() ? side_streams() : nullptr;
   cudaStream_t s2 = sl != nullptr ? sl->s[2] : st;
   auto fork2 = [&](int e) -> int {
@@ -570,6 +640,70 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     return 0;
   };
   bool pend_ap = false;
+  const bool fuse_bptt = (g_fuse_gates & 2) != 0;
+  if (fuse_bptt) {
+    // Four dependent kernels per step (eight before): the elementwise GRU backward passes are evaluated inside the skinny GEMMs that
+    // consume them, dalpha / softmax backward / dz are one kernel.  Every contribution to the carried gradients is an atomic add into
+    // per-step rows zero-filled here; DH[T] = 0 is the initial carry.  Side stream: the coverage backward DZ -> DF -> dAP only.
+    WAP_CHECK(cudaMemsetAsync(W.DH, 0, sizeof(float) * ((size_t)(TB + B) * kN + (size_t)TB * kN), st));     // DH and DPREH are adjacent
+    static const int env_split = getenv("WAP_BPTT_SPLITK") != nullptr ? atoi(getenv("WAP_BPTT_SPLITK")) : 0;
+    static const int env_pix = getenv("WAP_ATTN_BWD_PIX") != nullptr ? atoi(getenv("WAP_ATTN_BWD_PIX")) : 16;
+    const int mtiles = cdiv(B * L, 128);
+    const int splitk = env_split > 0 ? env_split : std::max(1, std::min(8, 148 / mtiles));
+    const int pix = env_pix == 8 ? 8 : 16;
+    const size_t BL = (size_t)B * L;
+    if (tc && splitk > 1) WAP_CHECK(cudaMemsetAsync(W.DF, 0, sizeof(float) * BL * 124 * 2, st));
+    for (int t = T - 1; t >= 0; --t) {
+      const size_t r = (size_t)t * B;
+      const float* ym = y_mask + r;
+      float* dctx = W.dCTX + r * kD;                 // holds the logit-path part already
+      float* dpre = W.DPREH + r * kN;
+      {   // [dG2|dCH] -> dctx and [dPH2|dG2] -> dpre_h in one launch; X = the GRU-2 backward of (DH[t+1] + dHlog[t])
+        SkinnyArgs a; a.X = nullptr; a.ldx = 0; a.ids = nullptr; a.Bn = B; a.K = 4 * kN; a.nseg = 2;
+        a.seg[0] = {W.T_Wczr, kD, kD, dctx, kD, kN, 3 * kN};
+        a.seg[1] = {W.T_Urhnl, kN, kN, dpre, kN, 0, 3 * kN};
+        a.gen = 3; a.gA = W.DH + (r + B) * kN; a.gB = W.dHlog + r * kN; a.gG = W.RZ2 + r * 2 * kN; a.gC = W.PROP2 + r * kN;
+        a.gD = W.PREH + r * kN; a.gE = W.PH2 + r * kN; a.gmask = ym; a.oX = W.dPH2 + r * kLdA; a.oAcc = dpre;
+        WAP_TRY(skinny_gemm(st, a));
+      }
+      if (sl != nullptr && pend_ap) WAP_CHECK(cudaStreamWaitEvent(st, sl->done[7], 0));     // dAP_in of this step (side-stream gather of step t+1)
+      float* DZt = W.DZ + r * L * kNA;
+      // coverage backward GEMM DF^T[121][B*L] = (DZ_t * Q'^T)^T: few output tiles, long reduction and on the recurrence cycle
+      // (attn_bwd -> DF -> gather -> attn_bwd), so it runs split-K with atomics into one of two DF buffers; the attention kernel of this
+      // step clears the buffer that step t-1 will use (its last reader, the gather of step t+1, has finished: this kernel waited for it).
+      float* DFt = W.DF + (size_t)(t & 1) * BL * 124;
+      float* DFnext = W.DF + (size_t)((t + 1) & 1) * BL * 124;
+      const int zero_n4 = (tc && splitk > 1) ? (int)(BL * 124 / 4) : 0;
+      if (pix == 8) WAP_CHECK(launch_pdl(attn_bwd_kernel<8>, dim3(cdiv(L, 8), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
+                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, g + P.V_a, g + P.V_a_b, L, reinterpret_cast<float4*>(DFnext), zero_n4));
+      else WAP_CHECK(launch_pdl(attn_bwd_kernel<16>, dim3(cdiv(L, 16), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
+                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, g + P.V_a, g + P.V_a_b, L, reinterpret_cast<float4*>(DFnext), zero_n4));
+      WAP_LAUNCH_CHECK();
+      WAP_TRY(fork2(3));
+      if (tc) WAP_TRY(tc_gemm(s2, DZt, kNA, W.qf_hi, prec >= 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{DFt, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm, splitk));
+      else WAP_TRY(gemm_nt(s2, DZt, kNA, W.qf, kNA, DFt, 124, B * L, kCovTaps, kNA, nullptr, false));
+      WAP_CHECK(launch_pdl(cov_bwd_gather_kernel, cdiv(B * L, 32), 32 * kGatherWarps, 0, s2, DFt, dAP_in, dAP_out, B, h, w, tc ? 1 : 0));
+      WAP_LAUNCH_CHECK();
+      if (sl != nullptr) { WAP_CHECK(cudaEventRecord(sl->done[7], s2)); pend_ap = true; }
+      {   // dpre_h += dSP*W_a^T
+        SkinnyArgs a; a.ids = nullptr; a.Bn = B; a.X = W.dSP + r * kNA; a.ldx = kNA; a.K = kNA; a.nseg = 1;
+        a.seg[0] = {W.T_Wa, kN, kN, dpre, kN};
+        WAP_TRY(skinny_gemm(st, a));
+      }
+      {   // DH[t] = direct term + [dG1|dUH] * [U_hz_hr^T; U_rh^T]; X = the GRU-1 backward of dpre_h
+        SkinnyArgs a; a.X = nullptr; a.ldx = 0; a.ids = nullptr; a.Bn = B; a.K = 3 * kN; a.nseg = 1;
+        a.seg[0] = {W.T_Uhzhr, kN, kN, W.DH + r * kN, kN};
+        a.gen = 4; a.gA = dpre; a.gG = W.RZ1 + r * 2 * kN; a.gC = W.PROP1 + r * kN; a.gD = W.UH + r * kN; a.gE = W.H + r * kN; a.gmask = ym;
+        a.oX = W.dG1 + r * kLdB; a.oProp = W.dEh + r * kN; a.oAcc = W.DH + r * kN;
+        WAP_TRY(skinny_gemm(st, a));
+      }
+      std::swap(dAP_in, dAP_out);
+    }
+    dh_in = W.DH;          // d h0
+  } else {
+  // Two chains per step.  Main stream: gru2_bwd -> [dG2|dCH] -> dctx -> dalpha -> softmax_bwd -> dz -> dSP -> dpre_h -> gru1_bwd ->
+  // [dG1|dUH] -> dh.  Side stream: [dPH2|dG2] -> dpre_h (joins before gru1_bwd) and the coverage backward DZ -> DF -> dAP (joins before
+  // the next step's dalpha).
   for (int t = T - 1; t >= 0; --t) {
     const size_t r = (size_t)t * B;
     const float* ym = y_mask + r;
@@ -620,6 +754,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       WAP_TRY(skinny_gemm(st, a));
     }
     std::swap(dh_in, dh_out); std::swap(dAP_in, dAP_out);
+  }
   }
   if (sl != nullptr && pend_ap) WAP_CHECK(cudaStreamWaitEvent(st, sl->done[7], 0));
   // watch path: dWatch = sum_t DZ_t

@@ -184,6 +184,7 @@ __device__ __forceinline__ void store_bf16x8(void* dst, const float* v) {
 struct TcShape {
   int M, N, K;            // logical GEMM (K = total reduction length; for conv: 9*C)
   int nkb;                // number of 32-wide K blocks
+  int kps;                // split-K: k-blocks per grid.z slice (0 = no split, every CTA runs all nkb)
   // im2col mode
   int B, H, W, kb_per_tap, TW, TH, tiles_x, tiles_y;
   long long* trace;       // debug: CTA 0 records clock64() per k-block: [kb][0 TMA issue, 1 data landed (splitter/MMA saw full), 2 split done, 3 MMA issued]
@@ -229,12 +230,18 @@ template <bool X3> struct TcThreads { static constexpr int kN = kTcThreads; };
 // taps are 3 x 24 output columns whose results the epilogue adds with a +-1 pixel shift, see tc_conv3x3_rowtile)
 // BF16: operands are bf16 in global / shared memory (a stage row is still one 128-byte swizzle span = 64 elements), the MMAs are
 // kind::f16 with K = 16 (again four per stage), accumulation fp32 in TMEM; epi.out_bf16 stores the result as bf16.
-template <int BN, int IM2COL, bool X3, bool BF16>
+// EPI selects which epilogue features are COMPILED IN (the all-in-one epilogue was ~100 KB of SASS per instantiation; the small per-time-step
+// GEMMs of the scans spent more time fetching it than executing it):  0 = store / accumulate / bias / folded inference BN,  1 = store + BN
+// statistics,  2 = transposed store, split-K atomics (+ bias),  3 = statistics + fused BN-backward reduce (debug-mask bit 10).
+template <int BN, int IM2COL, bool X3, bool BF16, int EPI>
 __global__ void __launch_bounds__(TcThreads<X3>::kN, (X3 && kTcBK == 32) ? 1 : 2)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const TcEpi epi, const TcShape sh) {
   pdl_sync();
+  const bool tr0 = sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (tr0 && threadIdx.x == 0) sh.trace[1024] = clock64();
   static_assert(!(X3 && BF16), "3xTF32 splitting applies to fp32 operands only");
+  constexpr bool kEStats = EPI == 1 || EPI == 3, kEBnb = EPI == 3, kETr = EPI == 2, kEPlain = EPI == 0;
   using S = TcSmem<BN, X3, BF16>;
   constexpr int kTcStages = S::kStages;
   constexpr int kElK = BF16 ? kTcRowB / 2 : kTcBK;            // elements of K per stage row (64 bf16 or 32 fp32)
@@ -267,6 +274,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     m0 = blockIdx.x * kTcBM;
   }
   const int n0 = blockIdx.y * BN;
+  const int kbb = (kETr && sh.kps > 0) ? (int)blockIdx.z * sh.kps : 0;                       // split-K: this CTA reduces k-blocks [kbb, kbb + nloc)
+  const int nloc = (kETr && sh.kps > 0) ? min(sh.kps, sh.nkb - kbb) : sh.nkb;
 
   if (threadIdx.x == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -275,9 +284,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     mbar_init(tmem_full, 1);
     fence_barrier_init();
   }
-  if (epi.stats != nullptr)
+  if (kEStats && epi.stats != nullptr)
     for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) s_stat[i] = 0.f;
-  if (epi.bnb_raw != nullptr)       // fused BN-backward reduce: scale | shift | mean | invstd of this tile's channels behind the two sums
+  if (kEBnb && epi.bnb_raw != nullptr)       // fused BN-backward reduce: scale | shift | mean | invstd of this tile's channels behind the two sums
     for (int i = threadIdx.x; i < BN; i += blockDim.x) {
       const bool ok = n0 + i < sh.N;
       const float mean = ok ? epi.bnb_saved[n0 + i] : 0.f, inv = ok ? epi.bnb_saved[kMaxBnC + n0 + i] : 0.f;
@@ -285,7 +294,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       s_stat[2 * BN + i] = sc; s_stat[3 * BN + i] = ok ? __ldg(epi.bnb_beta + n0 + i) - mean * sc : 0.f;
       s_stat[4 * BN + i] = mean; s_stat[5 * BN + i] = inv;
     }
-  if (epi.bn_scale != nullptr)      // folded inference batch norm: scale | shift of this tile's columns
+  if (kEPlain && epi.bn_scale != nullptr)      // folded inference batch norm: scale | shift of this tile's columns
     for (int i = threadIdx.x; i < BN; i += blockDim.x) {
       const bool ok = n0 + i < sh.N;
       s_stat[i] = ok ? __ldg(epi.bn_scale + n0 + i) : 0.f; s_stat[BN + i] = ok ? __ldg(epi.bn_shift + n0 + i) : 0.f;
@@ -295,13 +304,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (tr0 && threadIdx.x == 0) sh.trace[1025] = clock64();
 
   if (warp == 0) {
     // ================================================= TMA producer
     if (lane == 0) {
-      for (int kb = 0; kb < sh.nkb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
+      for (int it = 0; it < nloc; ++it) {
+        const int kb = kbb + it;
+        const int s = it % kTcStages;
+        const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(&empty_bar[s], ph ^ 1, 1 + 100 * kb);
         if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) sh.trace[kb * 4 + 0] = clock64();
         uint8_t* sa = smem + s * S::kStage;
@@ -322,9 +333,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ================================================= MMA issuer
     if (lane == 0) {
       constexpr uint32_t idesc = BF16 ? make_idesc_bf16(BN) : make_idesc_tf32(BN);
-      for (int kb = 0; kb < sh.nkb; ++kb) {
-        const int s = kb % kTcStages;
-        const uint32_t ph = (kb / kTcStages) & 1;
+      for (int it = 0; it < nloc; ++it) {
+        const int kb = it;                   // (only "first k-block of this CTA" matters below)
+        const int s = it % kTcStages;
+        const uint32_t ph = (it / kTcStages) & 1;
         mbar_wait(X3 ? &split_bar[s] : &full_bar[s], ph, 2 + 100 * kb);
         tc_fence_after();
         if (sh.trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0) sh.trace[kb * 4 + 3] = clock64();
@@ -356,7 +368,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // 128B swizzle: 16-byte chunk c of row r sits at chunk c ^ (r & 7)), splits it into hi = rna_tf32(a) and lo = a - hi
       // and stores both into the TMEM ring of this stage; the MMAs take A from there.
       const int qq = warp & 3, rr = qq * 32 + lane;
-      for (int kb = 0; kb < sh.nkb; ++kb) {
+      for (int kb = 0; kb < nloc; ++kb) {
         const int s = kb % kTcStages;
         const uint32_t ph = (kb / kTcStages) & 1;
         mbar_wait(&full_bar[s], ph, 3 + 100 * kb);
@@ -395,6 +407,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_wait(tmem_full, 0, 4);
     tc_fence_after();
+    if (tr0 && threadIdx.x == 64) sh.trace[1026] = clock64();
     if constexpr (IM2COL == 2) {
       // Row-tile 3x3 epilogue.  Accumulator column 24 j + c of tile row q holds the contribution of INPUT pixel q through the
       // horizontal tap dx = j - 1 (all three vertical taps already summed by the K loop), i.e. it belongs to OUTPUT pixel
@@ -436,7 +449,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
 #pragma unroll
       for (int c = kG; c < 32; ++c) o[c] = 0.f;
-      if (epi.bn_scale != nullptr) {
+      if (kEPlain && epi.bn_scale != nullptr) {
 #pragma unroll
         for (int c = 0; c < kG; ++c) o[c] = fmaxf(fmaf(o[c], s_stat[c], s_stat[BN + c]), 0.f);
       }
@@ -451,7 +464,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < kG; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
         }
       }
-      if (epi.stats != nullptr) {
+      if (kEStats && epi.stats != nullptr) {
         float a[32], b[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { a[i] = valid ? o[i] : 0.f; b[i] = a[i] * a[i]; }
@@ -477,6 +490,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else {
 #pragma unroll 1
     for (int c = 0; c < BN; c += 32) {
+      if (tr0 && threadIdx.x == 64) sh.trace[1028 + c / 32] = clock64();
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
       if (X3) {
@@ -485,16 +499,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += v2[i];
       }
-      if (epi.bias != nullptr) {
+      if ((kEPlain || kETr) && epi.bias != nullptr && kbb == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) v[j] += __ldg(epi.bias + n0 + c + j);
       }
-      if (epi.bn_scale != nullptr) {
+      if (kEPlain && epi.bn_scale != nullptr) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = fmaxf(fmaf(v[j], s_stat[c + j], s_stat[BN + c + j]), 0.f);
       }
       float xh[32];                      // (fused BN backward only) normalised raw output of the element, for the second sum
-      if (epi.bnb_raw != nullptr) {
+      if (kEBnb && epi.bnb_raw != nullptr) {
         const uint32_t seed = (epi.bnb_dropout && epi.bnb_seed_src != nullptr) ? __ldg(epi.bnb_seed_src) : epi.bnb_seed;
         const float* rawp = epi.bnb_raw + mrow * epi.bnb_ld + n0 + c;
 #pragma unroll
@@ -513,7 +527,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
-      if (valid && epi.transpose_out) {
+      if (kETr && valid && sh.kps > 0) {                   // split-K: partial sums added into the zero-filled (or pre-loaded) output
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (n0 + c + j < sh.N) atomicAdd(epi.transpose_out ? epi.out + (size_t)(n0 + c + j) * epi.ld + mrow : epi.out + mrow * epi.ld + n0 + c + j, v[j]);
+      } else if (kETr && valid && epi.transpose_out) {
 #pragma unroll
         for (int j = 0; j < 32; ++j)
           if (n0 + c + j < sh.N) epi.out[(size_t)(n0 + c + j) * epi.ld + mrow] = v[j];
@@ -534,19 +552,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; j += 4) {
           if (n0 + c + j + 3 < sh.N) {
             float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (epi.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+            if (kEPlain && epi.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
             *reinterpret_cast<float4*>(dst + j) = o;
           } else {
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
-              if (n0 + c + j + jj < sh.N) dst[j + jj] = epi.accumulate ? dst[j + jj] + v[j + jj] : v[j + jj];
+              if (n0 + c + j + jj < sh.N) dst[j + jj] = (kEPlain && epi.accumulate) ? dst[j + jj] + v[j + jj] : v[j + jj];
           }
         }
       }
-      if (epi.stats != nullptr) {
+      if (kEStats && epi.stats != nullptr) {
         float a[32], b[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { a[i] = valid ? v[i] : 0.f; b[i] = a[i] * (epi.bnb_raw != nullptr ? xh[i] : a[i]); }
+        for (int i = 0; i < 32; ++i) { a[i] = valid ? v[i] : 0.f; b[i] = a[i] * ((kEBnb && epi.bnb_raw != nullptr) ? xh[i] : a[i]); }
         // transposing butterfly: after the 5 rounds lane L holds the sum over the 32 rows of column L
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
@@ -563,7 +581,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         atomicAdd(&s_stat[BN + c + lane], b[0]);
       }
     }
-    if (epi.stats != nullptr) {
+    if (kEStats && epi.stats != nullptr) {
       asm volatile("bar.sync 1, 128;" ::: "memory");       // the four epilogue warps
       const int t = threadIdx.x - 64;
       for (int i = t; i < BN; i += 128) {
@@ -580,6 +598,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 tail:
   tc_fence_before();
   __syncthreads();
+  if (tr0 && threadIdx.x == 64) sh.trace[1027] = clock64();
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
@@ -955,20 +974,39 @@ const int* trap_note_host() {
   }
   return g_trap_host;
 }
-template <int BN, int IM2COL, bool X3, bool BF16 = false>
-static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
+template <int BN, int IM2COL, bool X3, bool BF16, int EPI>
+static int launch_tc2(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
                       const TcShape& sh, dim3 grid, int prof_cls, double flops) {
   static bool configured = false;
   if (!configured) {
-    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3, BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3, BF16>::kTotal));
+    WAP_CHECK(cudaFuncSetAttribute(tc_gemm_kernel<BN, IM2COL, X3, BF16, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<BN, X3, BF16>::kTotal));
     configured = true;
   }
   TcShape sh2 = sh; sh2.trace = g_tc_trace;
   prof_begin(st, prof_cls, flops);
-  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3, BF16>, grid, TcThreads<X3>::kN, TcSmem<BN, X3, BF16>::kTotal, st, ta, tb, tblo, epi, sh2));
+  WAP_CHECK(launch_pdl(tc_gemm_kernel<BN, IM2COL, X3, BF16, EPI>, grid, TcThreads<X3>::kN, TcSmem<BN, X3, BF16>::kTotal, st, ta, tb, tblo, epi, sh2));
   prof_end(st, prof_cls);
   WAP_LAUNCH_CHECK();
   return 0;
+}
+// picks the epilogue variant the call needs (see tc_gemm_kernel); only the combinations the library uses are instantiated
+template <int BN, int IM2COL, bool X3, bool BF16 = false>
+static int launch_tc1(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tblo, const TcEpi& epi,
+                      const TcShape& sh, dim3 grid, int prof_cls, double flops) {
+  if (epi.bnb_raw != nullptr) {
+    if constexpr (BN == 96 && IM2COL == 1) return launch_tc2<BN, IM2COL, X3, BF16, 3>(st, ta, tb, tblo, epi, sh, grid, prof_cls, flops);
+    else WAP_REQUIRE(false, "tc_gemm: the fused BN-backward epilogue exists for the 3x3 im2col kernel with one 96-column tile only");
+  }
+  if (epi.stats != nullptr) {
+    WAP_REQUIRE(!epi.accumulate && epi.bias == nullptr && epi.bn_scale == nullptr && !epi.transpose_out && sh.kps == 0,
+                "tc_gemm: the statistics epilogue is a plain store (no accumulate / bias / folded BN / transposed / split-K)");
+    return launch_tc2<BN, IM2COL, X3, BF16, 1>(st, ta, tb, tblo, epi, sh, grid, prof_cls, flops);
+  }
+  if (epi.transpose_out || sh.kps > 0) {
+    if constexpr (IM2COL == 0 && !BF16) return launch_tc2<BN, IM2COL, X3, BF16, 2>(st, ta, tb, tblo, epi, sh, grid, prof_cls, flops);
+    else WAP_REQUIRE(false, "tc_gemm: transposed / split-K output exists for the plain fp32 GEMM only");
+  }
+  return launch_tc2<BN, IM2COL, X3, BF16, 0>(st, ta, tb, tblo, epi, sh, grid, prof_cls, flops);
 }
 template <int BN, int IM2COL>
 static int launch_tc(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap* tblo, const TcEpi& epi,
@@ -997,7 +1035,7 @@ int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, flo
   return 0;
 }
 
-int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls) {
+int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls, int splitk) {
   WAP_REQUIRE(epi.bias == nullptr || epi.stats == nullptr, "tc_gemm: bias and statistics cannot be combined");
   WAP_REQUIRE(!epi.transpose_out || !epi.accumulate, "tc_gemm: transposed store cannot accumulate");
   WAP_REQUIRE(epi.bn_scale == nullptr || (epi.stats == nullptr && !epi.accumulate && !epi.transpose_out && epi.bias == nullptr), "tc_gemm: folded batch norm is store-only");
@@ -1016,6 +1054,11 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
   }
   TcShape sh{}; sh.M = M; sh.N = N; sh.K = K; sh.nkb = cdiv(K, kTcBK);
   dim3 grid(cdiv(M, kTcBM), cdiv(N, BN));
+  if (splitk > 1) {      // latency-critical GEMMs with few output tiles: the reduction is spread over grid.z, partial sums meet by fp32 atomics
+    WAP_REQUIRE(epi.stats == nullptr && !epi.accumulate && !epi.out_bf16 && epi.bn_scale == nullptr, "tc_gemm: split-K is store-only (onto a zero-filled output)");
+    sh.kps = cdiv(sh.nkb, std::min(splitk, sh.nkb));
+    grid.z = cdiv(sh.nkb, sh.kps);
+  }
   const double flops = 2.0 * M * N * K;
   const CUtensorMap* pl = Bt_lo != nullptr ? &tbl : nullptr;
   prof_set_bytes(4.0 * ((double)M * K + (double)N * K * (Bt_lo != nullptr ? 2 : 1) + (double)M * N * (epi.accumulate ? 2 : 1)));

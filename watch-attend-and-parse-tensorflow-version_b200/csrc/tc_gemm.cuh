@@ -53,7 +53,9 @@ int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, flo
 
 // D[M,N] = A[M,K](lda) * Bt[N,K](ldb)^T ; N <= 256 per launch column tile (grid.y tiles of BN)
 // Bt_lo != null selects the error-compensated 3xTF32 variant: Bt = rna_tf32(W), Bt_lo = rna_tf32(W - Bt); A is split on the fly.
-int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls);
+// splitk > 1: the K reduction is spread over grid.z and the partial sums are ADDED into `out` with fp32 atomics (the caller zero-fills it)
+int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const float* Bt_lo, int ldb, int M, int N, int K, const TcEpi& epi, int prof_cls,
+            int splitk = 1);
 // 3x3 SAME conv: x[B,H,W,C] (pixel stride ldx) * Wt[Nrows, 9*C]^T -> D[B*H*W, N]  (Nrows >= N rows allocated, extra rows zero)
 int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, int C, const float* Wt, const float* Wt_lo, int Nrows, int N, const TcEpi& epi, int prof_cls);
 // weight gradients (reduction over pixels, both operands MN-major): dW += X^T dY ; x3 selects 3xTF32 (both operands split on the fly)
