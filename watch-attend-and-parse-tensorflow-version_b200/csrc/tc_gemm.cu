@@ -294,6 +294,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       s_stat[2 * BN + i] = sc; s_stat[3 * BN + i] = ok ? __ldg(epi.bnb_beta + n0 + i) - mean * sc : 0.f;
       s_stat[4 * BN + i] = mean; s_stat[5 * BN + i] = inv;
     }
+  if ((kEPlain || kETr) && epi.bias != nullptr)      // bias row of this tile's columns (zero beyond N)
+    for (int i = threadIdx.x; i < BN; i += blockDim.x) s_stat[2 * BN + i] = (n0 + i < sh.N) ? __ldg(epi.bias + n0 + i) : 0.f;
   if (kEPlain && epi.bn_scale != nullptr)      // folded inference batch norm: scale | shift of this tile's columns
     for (int i = threadIdx.x; i < BN; i += blockDim.x) {
       const bool ok = n0 + i < sh.N;
@@ -499,9 +501,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += v2[i];
       }
+      const bool full = n0 + c + 32 <= sh.N;        // whole chunk inside the matrix: straight-line stores (the guarded forms cost a branch per group)
       if ((kEPlain || kETr) && epi.bias != nullptr && kbb == 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) v[j] += __ldg(epi.bias + n0 + c + j);
+        for (int j = 0; j < 32; ++j) v[j] += s_stat[2 * BN + c + j];
       }
       if (kEPlain && epi.bn_scale != nullptr) {
 #pragma unroll
@@ -528,15 +531,30 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       if (kETr && valid && sh.kps > 0) {                   // split-K: partial sums added into the zero-filled (or pre-loaded) output
+        float* dst = epi.transpose_out ? epi.out + (size_t)(n0 + c) * epi.ld + mrow : epi.out + mrow * epi.ld + n0 + c;
+        const size_t step = epi.transpose_out ? (size_t)epi.ld : 1;
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c + j < sh.N) atomicAdd(epi.transpose_out ? epi.out + (size_t)(n0 + c + j) * epi.ld + mrow : epi.out + mrow * epi.ld + n0 + c + j, v[j]);
+          for (int j = 0; j < 32; ++j) atomicAdd(dst + j * step, v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) atomicAdd(dst + j * step, v[j]);
+        }
       } else if (kETr && valid && epi.transpose_out) {
+        float* dst = epi.out + (size_t)(n0 + c) * epi.ld + mrow;
+        if (full) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (n0 + c + j < sh.N) epi.out[(size_t)(n0 + c + j) * epi.ld + mrow] = v[j];
+          for (int j = 0; j < 32; ++j) dst[(size_t)j * epi.ld] = v[j];
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) dst[(size_t)j * epi.ld] = v[j];
+        }
       } else if (valid && epi.out_bf16) {         // bf16 result (no accumulate): N is a multiple of 8 for every caller
         uint8_t* dst = reinterpret_cast<uint8_t*>(epi.out) + (mrow * epi.ld + n0 + c) * 2;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) store_bf16x8(dst + j * 2, v + j);
+        } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
           if (n0 + c + j + 7 < sh.N) store_bf16x8(dst + j * 2, v + j);
@@ -546,18 +564,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (n0 + c + j + jj < sh.N) reinterpret_cast<__nv_bfloat16*>(dst)[j + jj] = __float2bfloat16_rn(v[j + jj]);
           }
         }
+        }
       } else if (valid) {
         float* dst = epi.out + mrow * epi.ld + n0 + c;
+        if (full && !(kEPlain && epi.accumulate)) {
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          if (n0 + c + j + 3 < sh.N) {
-            float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            if (kEPlain && epi.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-            *reinterpret_cast<float4*>(dst + j) = o;
-          } else {
+          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else if (full) {
+          float4 pv[8];
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj)
-              if (n0 + c + j + jj < sh.N) dst[j + jj] = (kEPlain && epi.accumulate) ? dst[j + jj] + v[j + jj] : v[j + jj];
+          for (int j = 0; j < 8; ++j) pv[j] = *reinterpret_cast<const float4*>(dst + 4 * j);
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(dst + 4 * j) = make_float4(v[4 * j] + pv[j].x, v[4 * j + 1] + pv[j].y, v[4 * j + 2] + pv[j].z, v[4 * j + 3] + pv[j].w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            if (n0 + c + j + 3 < sh.N) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              if (kEPlain && epi.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+              *reinterpret_cast<float4*>(dst + j) = o;
+            } else {
+#pragma unroll
+              for (int jj = 0; jj < 4; ++jj)
+                if (n0 + c + j + jj < sh.N) dst[j + jj] = (kEPlain && epi.accumulate) ? dst[j + jj] + v[j + jj] : v[j + jj];
+            }
           }
         }
       }
