@@ -378,7 +378,7 @@ def test_fused_bn_backward_reduce_matches_separate_kernels(report):
 def test_fused_bptt_matches_separate_kernels(report, B, H, W, cap, ragged):
     """BPTT with the GRU backward passes evaluated inside the consuming skinny GEMMs and dalpha / softmax backward / dz as one kernel (the
     default, wap_debug_set_fuse_gates bit 1) == the eight separate launches per time step.  ONE forward, backward twice on the same saved
-    activations: same gradients up to the order of the fp32 atomics, 5 launches per time step fewer (11 -> 6; dependent chain 8 -> 4)."""
+    activations: same gradients up to the order of the fp32 atomics, 5 launches per time step fewer (11 -> 6; dependent chain 8 -> 4), two column sums more after the loop (dV_a / dV_a_b partial rows)."""
     import ctypes as C
     import wap_b200
     from wap_b200.engine import _p, _stream
@@ -409,7 +409,7 @@ def test_fused_bptt_matches_separate_kernels(report, B, H, W, cap, ragged):
     worst = max((rel_l2(g_fused[o:o + k].cpu().numpy(), g_plain[o:o + k].cpu().numpy()), n) for n, (o, k) in names.items()
                 if float(g_plain[o:o + k].abs().max()) > 1e-6 * gmax)
     report.add("bptt_fused", f"grads_rel_l2_vs_unfused_B{B}", e, 2e-5, extra=dict(rerun_noise=e0, worst=worst, launches=(n_plain, n_fused)))
-    assert e0 <= 2e-5 and e <= 2e-5 and worst[0] <= 2e-4 and n_fused == n_plain - 5 * T, (c0, e0, e, worst, n_plain, n_fused)
+    assert e0 <= 2e-5 and e <= 2e-5 and worst[0] <= 2e-4 and n_fused == n_plain - 5 * T + 2, (c0, e0, e, worst, n_plain, n_fused)
 
 
 def test_two_stream_decode_pipelines_match_per_image_calls():

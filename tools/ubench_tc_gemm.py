@@ -31,7 +31,7 @@ def run(M, N, K, tr, splitk, x3=True, reps=200):
     t0 = t[1024]
     st = [(t[1024 + i] - t0) / CLK for i in range(4)]
     chunks = [round((t[1028 + i] - t0) / CLK, 2) for i in range(4) if t[1028 + i] > 0]
-    kb = [[(t[k * 4 + j] - t0) / CLK for j in range(4)] for k in range(min(nkb, 3))]
+    kb = [[(t[k * 4 + j] - t0) / CLK for j in range(4)] for k in range(min(nkb, 24 if os.environ.get('ALLKB') else 3))]
     D.zero_(); go(); torch.cuda.synchronize()
     ref = (A.double() @ W.double())
     got = (D.t() if tr else D[:, :N]).double()
@@ -40,6 +40,8 @@ def run(M, N, K, tr, splitk, x3=True, reps=200):
           f"k-blocks [tma, landed, split, mma] {[[round(v, 2) for v in r] for r in kb]} | rel err {err:.1e}")
 
 
+if os.environ.get('ALLKB'):
+    run(8192, 96, 608, 0, 1); run(8192, 96, 608, 0, 1, x3=False); sys.exit(0)
 run(128, 121, 32, 1, 1); run(128, 121, 32, 0, 1); run(128, 32, 32, 0, 1); run(128, 121, 32, 0, 1, x3=False)
 sys.exit(0)
 

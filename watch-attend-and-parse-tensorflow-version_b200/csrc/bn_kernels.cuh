@@ -179,7 +179,40 @@ __global__ void __launch_bounds__(256) bn_bwd_reduce_kernel(const BnBwdArgs a, c
   const size_t p1 = min(npix, p0 + (size_t)pix_per_cta);
   float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
   if (prow < rows) {
-    for (size_t p = p0 + prow; p < p1; p += rows) {
+    size_t pstart = p0 + prow;
+    if (POOL == 0) {
+      // four pixels per round with all eight loads issued before the first use: in blocks 1-2 a CTA's slice is a handful of pixels per
+      // thread and the loop was a chain of dependent load latencies (8 us per launch, 64 launches per step on the backward's critical path)
+      for (; pstart < p1; pstart += 4 * (size_t)rows) {
+        float vv[4][4], up[4][4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t p = pstart + (size_t)u * rows;
+          if (p < p1) {
+            ld4<TRaw>(a.raw, p * a.C + c, vv[u]);
+            const float4 d = ldg4(a.dout + p * a.ld_dout + c);
+            up[u][0] = d.x; up[u][1] = d.y; up[u][2] = d.z; up[u][3] = d.w;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const size_t p = pstart + (size_t)u * rows;
+          if (p >= p1) break;
+          float gg[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float pre = fmaf(vv[u][j], s_scale[c + j], s_shift[c + j]);
+            float gj = (pre > 0.f) ? up[u][j] : 0.f;
+            if (a.dropout) gj = drop_keep(seed, a.site, (uint32_t)(p * a.C + c + j)) ? gj * (1.f / (1.f - kDropRate)) : 0.f;
+            gg[j] = gj;
+            sg[j] += gj;
+            sgx[j] = fmaf(gj, (vv[u][j] - s_mean[c + j]) * s_inv[c + j], sgx[j]);
+          }
+          st4<TG>(a.g, p * a.ld_g + c, gg);
+        }
+      }
+    }
+    for (size_t p = pstart; p < p1; p += rows) {
       float vv[4];
       ld4<TRaw>(a.raw, p * a.C + c, vv);
       float up[4];
@@ -308,6 +341,8 @@ static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
   // (tunable for experiments: WAP_BN_BWD_CTAS_PER_SM)
   static const int per_sm = [] { const char* e = getenv("WAP_BN_BWD_CTAS_PER_SM"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
   int ppc = (int)std::max<size_t>(64, cdivz(npix, (size_t)148 * per_sm));
+  const int round = 4 * (256 / (a.C / 4));            // one unrolled round of the reduce loop = 4 pixels per thread row: avoid a nearly empty last round
+  if (round <= ppc) ppc = cdiv(ppc, round) * round;
   const int grid = (int)cdivz(npix, ppc);
   if (pool == 0) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<0, TRaw, TG>, grid, 256, 0, st, a, ppc));
   else if (pool == 1) WAP_CHECK(launch_pdl(bn_bwd_reduce_kernel<1, TRaw, TG>, grid, 256, 0, st, a, ppc));

@@ -35,6 +35,7 @@ struct DecTrainWs {
   // backward
   float *dLG, *dMO, *dHlog, *dCTX, *dEMB, *dG1, *dEh, *dUH, *dSP, *dG2, *dCH, *dPH2, *DZ, *dWatch, *DF;
   float *dAP0, *dAP1, *dalpha, *de, *dh0, *dh1, *dpre_h, *dQf, *dmean;
+  float *dVaP, *dVabP;       // fused BPTT: per-(step, image) partial sums of dV_a [TB, 512] / dV_a_b [TB] (16 CTAs per address instead of all 128), column-summed after the loop
   float *DH, *DPREH;         // fused BPTT: per-step carried gradients [(T+1)B, 256] / [TB, 256], zero-filled once (every contribution is an atomic add)
   float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
   float *qf_hi, *qf_lo, *Ua_hi, *Ua_lo, *UaT_hi, *UaT_lo;    // tensor-core operand copies (3xTF32 hi/lo parts)
@@ -61,7 +62,7 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.dAP0 = take(BL); w.dAP1 = take(BL); w.dalpha = take(BL); w.de = take(BL);
   w.dh0 = take((size_t)B * kN); w.dh1 = take((size_t)B * kN); w.dpre_h = take((size_t)B * kN);
   w.dQf = take((size_t)kCovTaps * kNA); w.dmean = take((size_t)B * kD);
-  w.DH = take((TB + B) * kN); w.DPREH = take(TB * kN);
+  w.DH = take((TB + B) * kN); w.DPREH = take(TB * kN); w.dVaP = take(TB * kNA); w.dVabP = take(TB);
   // stacked transposes matching the concatenated operands: [T_Wczr; T_Wchnl] (768x684), [T_Urhnl; T_Uhzhrnl] (768x256), [T_Uhzhr; T_Urh] (768x256)
   w.T_Wczr = take((size_t)2 * kN * kD); w.T_Wchnl = take((size_t)kN * kD); w.T_Urhnl = take((size_t)kN * kN);
   w.T_Uhzhrnl = take((size_t)2 * kN * kN); w.T_Wa = take((size_t)kNA * kN); w.T_Uhzhr = take((size_t)2 * kN * kN); w.T_Urh = take((size_t)kN * kN);
@@ -474,8 +475,9 @@ attn_bwd_kernel(const float* __restrict__ ann, const float* __restrict__ dctx, c
   }
   float* o = dSP + (size_t)b * kNA + c;
   atomicAdd(o, sp.x); atomicAdd(o + 1, sp.y); atomicAdd(o + 2, sp.z); atomicAdd(o + 3, sp.w);
-  atomicAdd(dVa + c, dv.x); atomicAdd(dVa + c + 1, dv.y); atomicAdd(dVa + c + 2, dv.z); atomicAdd(dVa + c + 3, dv.w);
-  if (tid == 0) atomicAdd(dVab, sde);
+  float* dva = dVa + (size_t)b * kNA + c;          // per-image partial rows (column-summed after the loop)
+  atomicAdd(dva, dv.x); atomicAdd(dva + 1, dv.y); atomicAdd(dva + 2, dv.z); atomicAdd(dva + 3, dv.w);
+  if (tid == 0) atomicAdd(dVab + b, sde);
 }
 // dWatch[i] = sum_t DZ[t][i]   (one pass after the scan instead of a read-modify-write of dWatch every step)
 __global__ void __launch_bounds__(256)
@@ -645,7 +647,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     // Four dependent kernels per step (eight before): the elementwise GRU backward passes are evaluated inside the skinny GEMMs that
     // consume them, dalpha / softmax backward / dz are one kernel.  Every contribution to the carried gradients is an atomic add into
     // per-step rows zero-filled here; DH[T] = 0 is the initial carry.  Side stream: the coverage backward DZ -> DF -> dAP only.
-    WAP_CHECK(cudaMemsetAsync(W.DH, 0, sizeof(float) * ((size_t)(TB + B) * kN + (size_t)TB * kN), st));     // DH and DPREH are adjacent
+    WAP_CHECK(cudaMemsetAsync(W.DH, 0, sizeof(float) * ((size_t)(TB + B) * kN + (size_t)TB * kN + (size_t)TB * kNA + (((size_t)TB + 3) & ~(size_t)3)), st));     // DH, DPREH, dVaP, dVabP are adjacent
     static const int env_split = getenv("WAP_BPTT_SPLITK") != nullptr ? atoi(getenv("WAP_BPTT_SPLITK")) : 0;
     static const int env_pix = getenv("WAP_ATTN_BWD_PIX") != nullptr ? atoi(getenv("WAP_ATTN_BWD_PIX")) : 16;
     const int mtiles = cdiv(B * L, 128);
@@ -675,9 +677,9 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       float* DFnext = W.DF + (size_t)((t + 1) & 1) * BL * 124;
       const int zero_n4 = (tc && splitk > 1) ? (int)(BL * 124 / 4) : 0;
       if (pix == 8) WAP_CHECK(launch_pdl(attn_bwd_kernel<8>, dim3(cdiv(L, 8), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
-                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, g + P.V_a, g + P.V_a_b, L, reinterpret_cast<float4*>(DFnext), zero_n4));
+                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, W.dVaP + r * kNA, W.dVabP + r, L, reinterpret_cast<float4*>(DFnext), zero_n4));
       else WAP_CHECK(launch_pdl(attn_bwd_kernel<16>, dim3(cdiv(L, 16), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
-                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, g + P.V_a, g + P.V_a_b, L, reinterpret_cast<float4*>(DFnext), zero_n4));
+                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, W.dVaP + r * kNA, W.dVabP + r, L, reinterpret_cast<float4*>(DFnext), zero_n4));
       WAP_LAUNCH_CHECK();
       WAP_TRY(fork2(3));
       if (tc) WAP_TRY(tc_gemm(s2, DZt, kNA, W.qf_hi, prec >= 2 ? W.qf_lo : nullptr, kNA, B * L, kCovTaps, kNA, TcEpi{DFt, B * L, 0, nullptr, nullptr, 1}, kProfOtherGemm, splitk));
@@ -777,6 +779,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.W_a_b));
   WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.U_f_b));
   WAP_TRY(colsum(sw, W.dSP, kNA, TB, kNA, g + P.U_a_b));
+  if (fuse_bptt) { WAP_TRY(colsum(sw, W.dVaP, kNA, TB, kNA, g + P.V_a)); WAP_TRY(colsum(sw, W.dVabP, 1, TB, 1, g + P.V_a_b)); }
   WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dG2, kLdA, g + P.U_hz_hr_nl, 2 * kN, kN, 2 * kN, TB));
   WAP_TRY(colsum(sw, W.dG2, kLdA, TB, 2 * kN, g + P.b_hz_hr_nl));
   WAP_TRY(gemm_tn_atomic(sw, W.PREH, kN, W.dPH2, kLdA, g + P.U_rh_nl, kN, kN, kN, TB));
