@@ -36,6 +36,28 @@ def _st():
 p = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
 
 
+@pytest.mark.parametrize("M,N,K,tr,splitk,bias", [(2048, 121, 512, 1, 8, 0), (2048, 121, 512, 1, 1, 0), (300, 121, 512, 1, 5, 1), (2048, 512, 128, 0, 1, 1),
+                                                   (700, 96, 608, 0, 4, 1), (128, 32, 64, 0, 16, 0), (1000, 200, 332, 1, 3, 0)])
+def test_tc_gemm_transposed_split_k_bias(report, M, N, K, tr, splitk, bias):
+    """wap_tc_gemm_ex, the form of the scans' per-time-step GEMMs: transposed store D^T[N][M], split-K (grid.z slices added with fp32 atomics into a
+    zero-filled output), bias row (added once, by slice 0), chunks partly outside N; 3xTF32 -> fp32-grade against the fp64 product."""
+    lib, L = _L()
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    A = torch.randn(M, K, generator=g).cuda(); Bt = torch.randn(N, K, generator=g).cuda()
+    b = torch.randn(N, generator=g).cuda() if bias else None
+    hi = _rna_tf32(Bt); lo = _rna_tf32(Bt - hi)
+    Np = (N + 3) // 4 * 4
+    D = torch.zeros((N, M) if tr else (M, Np), device="cuda")
+    lib.check(L.wap_tc_gemm_ex(_st(), p(A), K, p(hi), p(lo), K, p(D), M if tr else Np, M, N, K, tr, splitk, p(b)), "wap_tc_gemm_ex")
+    torch.cuda.synchronize()
+    ref = A.double() @ Bt.double().t() + (b.double() if bias else 0)
+    got = D.t() if tr else D[:, :N]
+    e = rel_err(got.cpu().numpy(), ref.cpu().numpy())
+    report.add("tc", f"tc_gemm_ex_{M}x{N}x{K}_tr{tr}_split{splitk}_bias{bias}", e, 3e-6)
+    assert e <= 3e-6, e
+    if not tr and Np > N: assert float(D[:, N:].abs().max()) == 0.0      # columns beyond N untouched
+
+
 @pytest.mark.parametrize("x3", [0, 1])
 @pytest.mark.parametrize("M,N,K,lda_pad,acc,stats", [
     (128, 96, 32, 0, 0, 0), (128, 96, 64, 0, 0, 1), (300, 96, 72, 360, 0, 1), (1000, 24, 864, 0, 0, 1),

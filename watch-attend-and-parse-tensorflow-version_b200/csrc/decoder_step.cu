@@ -302,9 +302,9 @@ softmax_ctx_kernel(const float* __restrict__ E, const float* __restrict__ a_mask
 // Ppat[pos][tap (128, taps >= 121 zero)] = alpha_past[b, y + dy, x + dx]   (11x11 SAME patches, float4 per thread)
 __global__ void __launch_bounds__(256) cov_im2col_kernel(const float* __restrict__ ap, float* __restrict__ Ppat, int Bn, int H, int W) {
   pdl_sync();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= Bn * H * W * 32) return;
-  const int pos = i >> 5, t4 = (i & 31) * 4;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)Bn * H * W * 32) return;
+  const int pos = (int)(i >> 5), t4 = (int)(i & 31) * 4;
   const int x = pos % W, t = pos / W, y = t % H;
   float v[4];
 #pragma unroll
@@ -313,6 +313,11 @@ __global__ void __launch_bounds__(256) cov_im2col_kernel(const float* __restrict
     v[j] = (tap < kCovTaps && (unsigned)(y + dy) < (unsigned)H && (unsigned)(x + dx) < (unsigned)W) ? __ldg(ap + pos + dy * W + dx) : 0.f;
   }
   *reinterpret_cast<float4*>(Ppat + (size_t)pos * 128 + t4) = make_float4(v[0], v[1], v[2], v[3]);
+}
+int cov_im2col(cudaStream_t st, const float* ap, float* Ppat, int Bn, int H, int W) {
+  WAP_CHECK(launch_pdl(cov_im2col_kernel, (unsigned)cdivz((size_t)Bn * H * W * 32, 256), 256, 0, st, ap, Ppat, Bn, H, W));
+  WAP_LAUNCH_CHECK();
+  return 0;
 }
 // Q'^T hi/lo [512][128] (taps >= 121 zero) for the tensor-core coverage GEMM
 __global__ void prep_qfT_kernel(const float* __restrict__ qf, float* __restrict__ hi, float* __restrict__ lo) {

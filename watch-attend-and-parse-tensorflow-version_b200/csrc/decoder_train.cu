@@ -19,6 +19,7 @@ namespace wap {
 
 int get_conv_precision();
 int prep_qfT(cudaStream_t st, const float* qf, float* hi, float* lo);
+int cov_im2col(cudaStream_t st, const float* ap, float* Ppat, int Bn, int H, int W);
 size_t step_ws_floats(int Bn, int L);
 int attn_precompute(cudaStream_t st, const float* params, const float* ann, const float* a_mask, int B, int h, int w,
                     float* watch, float* h0, float* qf, float* mean_scratch);
@@ -40,6 +41,7 @@ struct DecTrainWs {
   float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
   float *qf_hi, *qf_lo, *Ua_hi, *Ua_lo, *UaT_hi, *UaT_lo;    // tensor-core operand copies (3xTF32 hi/lo parts)
   float *Ppat, *qfT_hi, *qfT_lo;                              // coverage im2col patches [B*L,128], Q'^T [512][128]
+  float *PpatAll;                                             // patches of all T steps [T*B*L, 128] for the tensor-core dQ' weight gradient
 };
 static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   DecTrainWs w; size_t o = 0;
@@ -69,6 +71,7 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.qf_hi = take((size_t)kCovTaps * kNA); w.qf_lo = take((size_t)kCovTaps * kNA);
   w.Ua_hi = take((size_t)kD * kNA); w.Ua_lo = take((size_t)kD * kNA); w.UaT_hi = take((size_t)kD * kNA); w.UaT_lo = take((size_t)kD * kNA);
   w.Ppat = take(BL * 128); w.qfT_hi = take((size_t)kNA * 128); w.qfT_lo = take((size_t)kNA * 128);
+  w.PpatAll = take(TB * L * 128);
   if (total != nullptr) *total = o;
   return w;
 }
@@ -794,11 +797,20 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   // fused coverage filter: dQ' = sum_t patches(AP_t)^T * DZ_t  (one GEMM over T*B images)
   {
     WAP_CHECK(cudaMemsetAsync(W.dQf, 0, sizeof(float) * kCovTaps * kNA, sw));
+    if (tc) {
+      // tensor cores: materialise the patches of every step once (im2col of all T*B alpha_past images), then dQ'[121,512] += P^T * DZ as the
+      // weight-gradient GEMM the encoder uses (both operands MN-major, reduction over T*B*L rows split over grid.z), 96 columns per launch.
+      // The FFMA form of this GEMM held all 148 SMs for ~0.5 ms next to the latency-bound encoder backward.
+      WAP_TRY(cov_im2col(sw, W.AP, W.PpatAll, T * B, h, w));
+      for (int n0 = 0; n0 < kNA; n0 += 96)
+        WAP_TRY(tc_wgrad_1x1(sw, W.PpatAll, 128, W.DZ + n0, kNA, TB * L, kCovTaps, std::min(96, kNA - n0), W.dQf + n0, kNA, prec >= 2, kProfOtherGemm));
+    } else {
     ACovPatchT A{W.AP, T * B, h, w};
     BRowMajor Bd{W.DZ, kNA, TB * L, kNA};
     EpiAtomic e{W.dQf, kNA};
     const int K = ((TB * L + 3) / 4) * 4;
     WAP_TRY((launch_gemm<Cfg128x128>(sw, A, Bd, e, kCovTaps, kNA, K, std::max(1, std::min(cdiv(K, 64), 148)))));
+    }
     // dQ += dQ' * U_f^T ; dU_f += Q^T * dQ'
     WAP_TRY(gemm_nt(sw, W.dQf, kNA, p + P.U_f, kNA, g + P.Q, kNA, kCovTaps, kNA, kNA, nullptr, true));
     WAP_TRY(gemm_tn_atomic(sw, p + P.Q, kNA, W.dQf, kNA, g + P.U_f, kNA, kNA, kNA, kCovTaps));
