@@ -41,6 +41,8 @@ struct DecTrainWs {
   float *T_Wczr, *T_Wchnl, *T_Uhzhrnl, *T_Urhnl, *T_Wa, *T_Uhzhr, *T_Urh;
   float *qf_hi, *qf_lo, *Ua_hi, *Ua_lo, *UaT_hi, *UaT_lo;    // tensor-core operand copies (3xTF32 hi/lo parts)
   float *Ppat, *qfT_hi, *qfT_lo;                              // coverage im2col patches [B*L,128], Q'^T [512][128]
+  // hi/lo operand copies of the head's weights (tensor-core form of the small dense GEMMs): forward uses W^T ([N][K] of a [K][N] matrix)
+  float *UfT[2], *WyzrT[2], *WyhT[2], *WhT[2], *WcT[2], *WyT[2], *WhN[2], *WcN[2], *WyN[2];
   float *PpatAll;                                             // patches of all T steps [T*B*L, 128] for the tensor-core dQ' weight gradient
 };
 static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
@@ -72,6 +74,10 @@ static DecTrainWs carve_train(float* base, int B, int L, int T, size_t* total) {
   w.Ua_hi = take((size_t)kD * kNA); w.Ua_lo = take((size_t)kD * kNA); w.UaT_hi = take((size_t)kD * kNA); w.UaT_lo = take((size_t)kD * kNA);
   w.Ppat = take(BL * 128); w.qfT_hi = take((size_t)kNA * 128); w.qfT_lo = take((size_t)kNA * 128);
   w.PpatAll = take(TB * L * 128);
+  for (int i = 0; i < 2; ++i) {
+    w.UfT[i] = take((size_t)kNA * kNA); w.WyzrT[i] = take((size_t)2 * kN * kMw); w.WyhT[i] = take((size_t)kN * kMw); w.WhT[i] = take((size_t)kMw * kN);
+    w.WcT[i] = take((size_t)kMw * kD); w.WyT[i] = take((size_t)kMw * kMw); w.WhN[i] = take((size_t)kN * kMw); w.WcN[i] = take((size_t)kD * kMw); w.WyN[i] = take((size_t)kMw * kMw);
+  }
   if (total != nullptr) *total = o;
   return w;
 }
@@ -233,9 +239,20 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   const int prec = get_conv_precision();
   const bool tc = prec != 0;
   WAP_REQUIRE(!tc || tc_available(), "tensor-core conv precision requested but cuTensorMapEncodeTiled is unavailable (no silent FFMA fallback)");
-  if (tc) {   // hoisted watch GEMM [B*L,684]x[684,512] on tensor cores; h0 and Q' as usual
-    WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, nullptr, W.H, W.qf, W.mean));
-    WAP_TRY(tc_prep_bt(st, params + P.U_a, kD, kNA, 1, W.UaT_hi, W.UaT_lo));
+  auto lo = [&](float* const* pair) -> const float* { return prec >= 2 ? pair[1] : nullptr; };
+  if (tc) {   // hoisted watch GEMM [B*L,684]x[684,512] on tensor cores, and every small dense GEMM of the head as well: the FFMA tiles took
+              // 30-110 us each at M = T*B rows (0.3 ms of serial work before and after the scan); one launch splits all their weights into hi/lo
+    TcPrepBatch pb; pb.n = 7;
+    pb.e[0] = {params + P.U_a, kD, kNA, 1, W.UaT_hi, W.UaT_lo};
+    pb.e[1] = {params + P.U_f, kNA, kNA, 1, W.UfT[0], W.UfT[1]};
+    pb.e[2] = {params + P.W_yz_yr, kMw, 2 * kN, 1, W.WyzrT[0], W.WyzrT[1]};
+    pb.e[3] = {params + P.W_yh, kMw, kN, 1, W.WyhT[0], W.WyhT[1]};
+    pb.e[4] = {params + P.Wh, kN, kMw, 1, W.WhT[0], W.WhT[1]};
+    pb.e[5] = {params + P.Wc, kD, kMw, 1, W.WcT[0], W.WcT[1]};
+    pb.e[6] = {params + P.Wy, kMw, kMw, 1, W.WyT[0], W.WyT[1]};
+    WAP_TRY(tc_prep_multi(st, pb));
+    WAP_TRY(attn_precompute(st, params, ann, a_mask, B, h, w, nullptr, W.H, nullptr, W.mean));
+    WAP_TRY(tc_gemm(st, params + P.Q, kNA, W.UfT[0], lo(W.UfT), kNA, kCovTaps, kNA, kNA, TcEpi{W.qf, kNA, 0, nullptr, nullptr, 0}, kProfOtherGemm));   // Q' = Q U_f
     WAP_TRY(tc_gemm(st, ann, kD, W.UaT_hi, prec >= 2 ? W.UaT_lo : nullptr, kD, B * L, kNA, kD, TcEpi{W.watch, kNA, 0, nullptr, params + P.U_a_b, 0}, kProfOtherGemm));
     WAP_TRY(prep_qfT(st, W.qf, W.qfT_hi, W.qfT_lo));
   } else {
@@ -244,8 +261,13 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   WAP_CHECK(launch_pdl(emb_shift_kernel, cdiv(TB * kMw, 256), 256, 0, st, params + P.embed, y, W.EMB, T, B));
   WAP_LAUNCH_CHECK();
   // emb-dependent GRU-1 pre-activations for all steps at once
-  WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yz_yr, 2 * kN, W.G1, 3 * kN, TB, 2 * kN, kMw, params + P.b_yz_yr, false));
-  WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yh, kN, W.G1 + 2 * kN, 3 * kN, TB, kN, kMw, params + P.b_yh, false));
+  if (tc) {
+    WAP_TRY(tc_gemm(st, W.EMB, kMw, W.WyzrT[0], lo(W.WyzrT), kMw, TB, 2 * kN, kMw, TcEpi{W.G1, 3 * kN, 0, nullptr, params + P.b_yz_yr, 0}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, W.EMB, kMw, W.WyhT[0], lo(W.WyhT), kMw, TB, kN, kMw, TcEpi{W.G1 + 2 * kN, 3 * kN, 0, nullptr, params + P.b_yh, 0}, kProfOtherGemm));
+  } else {
+    WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yz_yr, 2 * kN, W.G1, 3 * kN, TB, 2 * kN, kMw, params + P.b_yz_yr, false));
+    WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.W_yh, kN, W.G1 + 2 * kN, 3 * kN, TB, kN, kMw, params + P.b_yh, false));
+  }
   WAP_CHECK(cudaMemsetAsync(W.AP, 0, sizeof(float) * B * L, st));
   {   // bias rows of the atomically accumulated per-step buffers, all T steps at once
     FillArgs f; f.rows = TB; f.nseg = 5;
@@ -286,9 +308,15 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   // logits for all steps (S:354-364)
   WAP_CHECK(launch_pdl(bias3_rows_kernel, cdiv(TB * kMw, 256), 256, 0, st, W.LG, TB, params + P.by, params + P.bc, params + P.bh));
   WAP_LAUNCH_CHECK();
-  WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
-  WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
-  WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.Wy, kMw, W.LG, kMw, TB, kMw, kMw, nullptr, true));
+  if (tc) {
+    WAP_TRY(tc_gemm(st, W.H + (size_t)B * kN, kN, W.WhT[0], lo(W.WhT), kN, TB, kMw, kN, TcEpi{W.LG, kMw, 1, nullptr, nullptr, 0}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, W.CTX, kD, W.WcT[0], lo(W.WcT), kD, TB, kMw, kD, TcEpi{W.LG, kMw, 1, nullptr, nullptr, 0}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, W.EMB, kMw, W.WyT[0], lo(W.WyT), kMw, TB, kMw, kMw, TcEpi{W.LG, kMw, 1, nullptr, nullptr, 0}, kProfOtherGemm));
+  } else {
+    WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
+    WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
+    WAP_TRY(gemm_nn(st, W.EMB, kMw, params + P.Wy, kMw, W.LG, kMw, TB, kMw, kMw, nullptr, true));
+  }
   WAP_CHECK(launch_pdl(maxout_drop_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.MO, TB, dropout, seed, seed_src()));
   WAP_LAUNCH_CHECK();
   WAP_CHECK(launch_pdl(wo_fwd_kernel, cdiv(TB * kVocab, 256), 256, 0, st, W.MO, params + P.Wo, params + P.bo, W.LO, TB));
@@ -609,8 +637,13 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   const bool tc = prec != 0;
   WAP_REQUIRE(!tc || tc_available(), "tensor-core conv precision requested but cuTensorMapEncodeTiled is unavailable (no silent FFMA fallback)");
   if (tc) {
-    WAP_TRY(tc_prep_bt(st, W.qf, kNA, kCovTaps, 0, W.qf_hi, W.qf_lo));
-    WAP_TRY(tc_prep_bt(st, p + P.U_a, kNA, kD, 0, W.Ua_hi, W.Ua_lo));
+    TcPrepBatch pb; pb.n = 5;
+    pb.e[0] = {W.qf, kNA, kCovTaps, 0, W.qf_hi, W.qf_lo};
+    pb.e[1] = {p + P.U_a, kNA, kD, 0, W.Ua_hi, W.Ua_lo};
+    pb.e[2] = {p + P.Wh, kMw, kN, 0, W.WhN[0], W.WhN[1]};
+    pb.e[3] = {p + P.Wc, kMw, kD, 0, W.WcN[0], W.WcN[1]};
+    pb.e[4] = {p + P.Wy, kMw, kMw, 0, W.WyN[0], W.WyN[1]};
+    WAP_TRY(tc_prep_multi(st, pb));
   }
   // ---- head (LO holds dLO after the forward CE kernel)
   WAP_CHECK(launch_pdl(wo_bwd_data_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LO, p + P.Wo, W.dMO, TB));
@@ -630,9 +663,15 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     WAP_TRY(colsum(swh, W.dLG, kMw, TB, kMw, g + P.bc));
     WAP_TRY(colsum(swh, W.dLG, kMw, TB, kMw, g + P.by));
   }
-  WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wh, kMw, W.dHlog, kN, TB, kN, kMw, nullptr, false));
-  WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wc, kMw, W.dCTX, kD, TB, kD, kMw, nullptr, false));
-  WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wy, kMw, W.dEMB, kMw, TB, kMw, kMw, nullptr, false));
+  if (tc) {     // data gradients of the logit layer on tensor cores (the FFMA tiles took 30-60 us each at M = T*B rows, in front of the BPTT)
+    WAP_TRY(tc_gemm(st, W.dLG, kMw, W.WhN[0], prec >= 2 ? W.WhN[1] : nullptr, kMw, TB, kN, kMw, TcEpi{W.dHlog, kN, 0, nullptr, nullptr, 0}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, W.dLG, kMw, W.WcN[0], prec >= 2 ? W.WcN[1] : nullptr, kMw, TB, kD, kMw, TcEpi{W.dCTX, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
+    WAP_TRY(tc_gemm(st, W.dLG, kMw, W.WyN[0], prec >= 2 ? W.WyN[1] : nullptr, kMw, TB, kMw, kMw, TcEpi{W.dEMB, kMw, 0, nullptr, nullptr, 0}, kProfOtherGemm));
+  } else {
+    WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wh, kMw, W.dHlog, kN, TB, kN, kMw, nullptr, false));
+    WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wc, kMw, W.dCTX, kD, TB, kD, kMw, nullptr, false));
+    WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wy, kMw, W.dEMB, kMw, TB, kMw, kMw, nullptr, false));
+  }
   // ---- BPTT
   WAP_CHECK(cudaMemsetAsync(W.dh0, 0, sizeof(float) * B * kN, st));
   WAP_CHECK(cudaMemsetAsync(W.dAP0, 0, sizeof(float) * B * L, st));

@@ -1060,6 +1060,28 @@ __global__ void tc_prep_bt_kernel(const float* __restrict__ W, int K, int N, int
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - h));
   lo[i] = __uint_as_float(u);
 }
+__global__ void tc_prep_multi_kernel(const TcPrepBatch b) {
+  pdl_sync();
+  const TcPrepEntry e = b.e[blockIdx.y];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.N * e.K; i += gridDim.x * blockDim.x) {
+    const int n = i / e.K, k = i - n * e.K;
+    const float v = e.transpose ? __ldg(e.W + (size_t)k * e.N + n) : __ldg(e.W + i);
+    uint32_t u;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+    const float h = __uint_as_float(u);
+    e.hi[i] = h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v - h));
+    e.lo[i] = __uint_as_float(u);
+  }
+}
+int tc_prep_multi(cudaStream_t st, const TcPrepBatch& b) {
+  WAP_REQUIRE(b.n >= 1 && b.n <= 8, "tc_prep_multi: n=%d", b.n);
+  int mx = 1;
+  for (int i = 0; i < b.n; ++i) mx = std::max(mx, b.e[i].N * b.e[i].K);
+  WAP_CHECK(launch_pdl(tc_prep_multi_kernel, dim3(std::min(cdiv(mx, 256), 256), b.n), 256, 0, st, b));
+  WAP_LAUNCH_CHECK();
+  return 0;
+}
 int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, float* hi, float* lo) {
   WAP_CHECK(launch_pdl(tc_prep_bt_kernel, cdiv(N * K, 256), 256, 0, st, W, K, N, transpose, hi, lo));
   WAP_LAUNCH_CHECK();

@@ -50,6 +50,10 @@ struct TcEpi {
 
 // Bt_hi/lo[N][K] = split(transpose(W[K][N])) (transpose != 0) or split(W[N][K]) : operand preparation for tc_gemm's 3xTF32 mode
 int tc_prep_bt(cudaStream_t st, const float* W, int K, int N, int transpose, float* hi, float* lo);
+// the same for up to 8 matrices in one launch (the decoder head's weights)
+struct TcPrepEntry { const float* W; int K, N, transpose; float* hi; float* lo; };
+struct TcPrepBatch { TcPrepEntry e[8]; int n; };
+int tc_prep_multi(cudaStream_t st, const TcPrepBatch& b);
 
 // D[M,N] = A[M,K](lda) * Bt[N,K](ldb)^T ; N <= 256 per launch column tile (grid.y tiles of BN)
 // Bt_lo != null selects the error-compensated 3xTF32 variant: Bt = rna_tf32(W), Bt_lo = rna_tf32(W - Bt); A is split on the fly.
