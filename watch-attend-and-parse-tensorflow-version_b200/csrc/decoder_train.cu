@@ -204,17 +204,24 @@ static int colsum(cudaStream_t st, const float* X, int ld, int rows, int n, floa
   WAP_LAUNCH_CHECK();
   return 0;
 }
-__global__ void transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int R, int C) {
+// up to 8 transposes in one launch (blockIdx.z = matrix)
+struct TransposeBatch { const float* src[8]; float* dst[8]; int R[8], C[8]; int n; };
+__global__ void transpose_multi_kernel(const TransposeBatch b) {
   pdl_sync();
   __shared__ float t[32][33];
+  const int m = blockIdx.z, R = b.R[m], C = b.C[m];
+  if ((int)blockIdx.x * 32 >= C || (int)blockIdx.y * 32 >= R) return;
+  const float* src = b.src[m]; float* dst = b.dst[m];
   const int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
   for (int i = threadIdx.y; i < 32; i += 8) if (r0 + i < R && c < C) t[i][threadIdx.x] = src[(size_t)(r0 + i) * C + c];
   __syncthreads();
   const int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
   for (int i = threadIdx.y; i < 32; i += 8) if (c0 + i < C && r < R) dst[(size_t)(c0 + i) * R + r] = t[threadIdx.x][i];
 }
-static int transpose(cudaStream_t st, const float* src, float* dst, int R, int C) {
-  WAP_CHECK(launch_pdl(transpose_kernel, dim3(cdiv(C, 32), cdiv(R, 32)), dim3(32, 8), 0, st, src, dst, R, C));
+static int transpose_multi(cudaStream_t st, const TransposeBatch& b) {
+  int mc = 1, mr = 1;
+  for (int i = 0; i < b.n; ++i) { mc = std::max(mc, cdiv(b.C[i], 32)); mr = std::max(mr, cdiv(b.R[i], 32)); }
+  WAP_CHECK(launch_pdl(transpose_multi_kernel, dim3(mc, mr, b.n), dim3(32, 8), 0, st, b));
   WAP_LAUNCH_CHECK();
   return 0;
 }
@@ -309,9 +316,11 @@ int decoder_train_forward(cudaStream_t st, const float* params, const float* ann
   WAP_CHECK(launch_pdl(bias3_rows_kernel, cdiv(TB * kMw, 256), 256, 0, st, W.LG, TB, params + P.by, params + P.bc, params + P.bh));
   WAP_LAUNCH_CHECK();
   if (tc) {
-    WAP_TRY(tc_gemm(st, W.H + (size_t)B * kN, kN, W.WhT[0], lo(W.WhT), kN, TB, kMw, kN, TcEpi{W.LG, kMw, 1, nullptr, nullptr, 0}, kProfOtherGemm));
-    WAP_TRY(tc_gemm(st, W.CTX, kD, W.WcT[0], lo(W.WcT), kD, TB, kMw, kD, TcEpi{W.LG, kMw, 1, nullptr, nullptr, 0}, kProfOtherGemm));
-    WAP_TRY(tc_gemm(st, W.EMB, kMw, W.WyT[0], lo(W.WyT), kMw, TB, kMw, kMw, TcEpi{W.LG, kMw, 1, nullptr, nullptr, 0}, kProfOtherGemm));
+    // few output tiles (T*B rows x 256 columns), long reductions: split-K, the partial sums added atomically onto the bias rows
+    const int sk = TB <= 1024 ? 4 : 1;
+    WAP_TRY(tc_gemm(st, W.H + (size_t)B * kN, kN, W.WhT[0], lo(W.WhT), kN, TB, kMw, kN, TcEpi{W.LG, kMw, sk > 1 ? 0 : 1, nullptr, nullptr, 0}, kProfOtherGemm, sk));
+    WAP_TRY(tc_gemm(st, W.CTX, kD, W.WcT[0], lo(W.WcT), kD, TB, kMw, kD, TcEpi{W.LG, kMw, sk > 1 ? 0 : 1, nullptr, nullptr, 0}, kProfOtherGemm, sk > 1 ? 2 * sk : 1));
+    WAP_TRY(tc_gemm(st, W.EMB, kMw, W.WyT[0], lo(W.WyT), kMw, TB, kMw, kMw, TcEpi{W.LG, kMw, sk > 1 ? 0 : 1, nullptr, nullptr, 0}, kProfOtherGemm, sk));
   } else {
     WAP_TRY(gemm_nn(st, W.H + (size_t)B * kN, kN, params + P.Wh, kMw, W.LG, kMw, TB, kMw, kN, nullptr, true));
     WAP_TRY(gemm_nn(st, W.CTX, kD, params + P.Wc, kMw, W.LG, kMw, TB, kMw, kD, nullptr, true));
@@ -626,13 +635,14 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   DecTrainWs W = carve_train(wsp, B, L, T, nullptr);
   const float* p = params; float* g = grads;
   // transposed copies for the in-loop data gradients
-  WAP_TRY(transpose(st, p + P.W_c_z_r, W.T_Wczr, kD, 2 * kN));
-  WAP_TRY(transpose(st, p + P.W_c_h_nl, W.T_Wchnl, kD, kN));
-  WAP_TRY(transpose(st, p + P.U_hz_hr_nl, W.T_Uhzhrnl, kN, 2 * kN));
-  WAP_TRY(transpose(st, p + P.U_rh_nl, W.T_Urhnl, kN, kN));
-  WAP_TRY(transpose(st, p + P.W_a, W.T_Wa, kN, kNA));
-  WAP_TRY(transpose(st, p + P.U_hz_hr, W.T_Uhzhr, kN, 2 * kN));
-  WAP_TRY(transpose(st, p + P.U_rh, W.T_Urh, kN, kN));
+  {
+    TransposeBatch tb; tb.n = 7;
+    const float* src[7] = {p + P.W_c_z_r, p + P.W_c_h_nl, p + P.U_hz_hr_nl, p + P.U_rh_nl, p + P.W_a, p + P.U_hz_hr, p + P.U_rh};
+    float* dst[7] = {W.T_Wczr, W.T_Wchnl, W.T_Uhzhrnl, W.T_Urhnl, W.T_Wa, W.T_Uhzhr, W.T_Urh};
+    const int R[7] = {kD, kD, kN, kN, kN, kN, kN}, C[7] = {2 * kN, kN, 2 * kN, kN, kNA, 2 * kN, kN};
+    for (int i = 0; i < 7; ++i) { tb.src[i] = src[i]; tb.dst[i] = dst[i]; tb.R[i] = R[i]; tb.C[i] = C[i]; }
+    WAP_TRY(transpose_multi(st, tb));
+  }
   const int prec = get_conv_precision();
   const bool tc = prec != 0;
   WAP_REQUIRE(!tc || tc_available(), "tensor-core conv precision requested but cuTensorMapEncodeTiled is unavailable (no silent FFMA fallback)");
@@ -648,14 +658,16 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   // ---- head (LO holds dLO after the forward CE kernel)
   WAP_CHECK(launch_pdl(wo_bwd_data_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LO, p + P.Wo, W.dMO, TB));
   WAP_LAUNCH_CHECK();
-  WAP_CHECK(launch_pdl(wo_bwd_weight_kernel, cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, st, W.MO, W.LO, g + P.Wo, g + P.bo, TB));
-  WAP_LAUNCH_CHECK();
   WAP_CHECK(launch_pdl(maxout_drop_bwd_kernel, cdiv(TB * kMw / 2, 256), 256, 0, st, W.LG, W.dMO, W.dLG, TB, dropout, seed, seed_src()));
   WAP_LAUNCH_CHECK();
   {   // weight gradients of the logit layer: side stream (joined together with the tail, see below)
     SideStreams* sh = overlap_enabled() ? side_streams() : nullptr;
     cudaStream_t swh = sh != nullptr ? sh->s[1] : st;
     if (sh != nullptr) { WAP_CHECK(cudaEventRecord(sh->fork[1], st)); WAP_CHECK(cudaStreamWaitEvent(swh, sh->fork[1], 0)); }
+    WAP_CHECK(launch_pdl(wo_bwd_weight_kernel, cdiv((kMw / 2 + 1) * kVocab, 256), 256, 0, swh, W.MO, W.LO, g + P.Wo, g + P.bo, TB));
+    WAP_LAUNCH_CHECK();
+    if (tc)      // d EMB (logit path) is only read after the BPTT (embedding scatter on this stream): keep it off the main chain
+      WAP_TRY(tc_gemm(swh, W.dLG, kMw, W.WyN[0], prec >= 2 ? W.WyN[1] : nullptr, kMw, TB, kMw, kMw, TcEpi{W.dEMB, kMw, 0, nullptr, nullptr, 0}, kProfOtherGemm));
     WAP_TRY(gemm_tn_atomic(swh, W.H + (size_t)B * kN, kN, W.dLG, kMw, g + P.Wh, kMw, kN, kMw, TB));
     WAP_TRY(gemm_tn_atomic(swh, W.CTX, kD, W.dLG, kMw, g + P.Wc, kMw, kD, kMw, TB));
     WAP_TRY(gemm_tn_atomic(swh, W.EMB, kMw, W.dLG, kMw, g + P.Wy, kMw, kMw, kMw, TB));
@@ -666,7 +678,6 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
   if (tc) {     // data gradients of the logit layer on tensor cores (the FFMA tiles took 30-60 us each at M = T*B rows, in front of the BPTT)
     WAP_TRY(tc_gemm(st, W.dLG, kMw, W.WhN[0], prec >= 2 ? W.WhN[1] : nullptr, kMw, TB, kN, kMw, TcEpi{W.dHlog, kN, 0, nullptr, nullptr, 0}, kProfOtherGemm));
     WAP_TRY(tc_gemm(st, W.dLG, kMw, W.WcN[0], prec >= 2 ? W.WcN[1] : nullptr, kMw, TB, kD, kMw, TcEpi{W.dCTX, kD, 0, nullptr, nullptr, 0}, kProfOtherGemm));
-    WAP_TRY(tc_gemm(st, W.dLG, kMw, W.WyN[0], prec >= 2 ? W.WyN[1] : nullptr, kMw, TB, kMw, kMw, TcEpi{W.dEMB, kMw, 0, nullptr, nullptr, 0}, kProfOtherGemm));
   } else {
     WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wh, kMw, W.dHlog, kN, TB, kN, kMw, nullptr, false));
     WAP_TRY(gemm_nt(st, W.dLG, kMw, p + P.Wc, kMw, W.dCTX, kD, TB, kD, kMw, nullptr, false));
