@@ -43,11 +43,12 @@ PROF_NAMES = ["conv1x1_fwd", "conv3x3_fwd", "transition_fwd", "conv3x3_wgrad", "
 # the kernel behind each launch class per precision mode (csrc/tc_gemm.cu, csrc/gemm.cuh)
 KERNEL_OF = {
     "fp32": {k: "gemm_kernel<TileCfg,...> (fp32 FFMA implicit GEMM, csrc/gemm.cuh)" for k in PROF_NAMES},
-    "tc": {"conv1x1_fwd": "tc_gemm_kernel<96,0,X3> (tcgen05 + TMA + TMEM)", "conv3x3_fwd": "tc_gemm_kernel<96,2,X3> row-tile / <32,1,X3> 9-tap",
-           "transition_fwd": "tc_gemm_kernel<128,0,X3>", "conv3x3_wgrad": "tc_wgrad_kernel<1,true,X3> (MN-major tcgen05)",
-           "conv3x3_dgrad": "tc_gemm_kernel<96,1,X3>", "conv1x1_wgrad": "tc_wgrad_kernel<3,false,X3> (MN-major tcgen05)",
-           "conv1x1_dgrad": "tc_gemm_kernel<128,0,X3> (paired K=192, accumulate) / <32,0,X3>", "transition_bwd": "tc_gemm_kernel<128,0,X3> + tc_wgrad_kernel<3,false,X3>",
-           "coverage_gemm": "tc_gemm_kernel<128,0,X3> (coverage patches x Q')", "other_gemm": "gemm_kernel<...> (fp32 FFMA) + tc_gemm_kernel (watch GEMM)"},
+    "tc": {"conv1x1_fwd": "tc_gemm_kernel<96,0,X3,false,EPI=1 store+BN statistics> (tcgen05 + TMA + TMEM)", "conv3x3_fwd": "tc_gemm_kernel<96,2,X3,false,1> row-tile / <32,1,X3> 9-tap",
+           "transition_fwd": "tc_gemm_kernel<128,0,X3,false,1>", "conv3x3_wgrad": "tc_wgrad_kernel<1,true,X3> (MN-major tcgen05)",
+           "conv3x3_dgrad": "tc_gemm_kernel<96,1,X3,false,0>", "conv1x1_wgrad": "tc_wgrad_kernel<3,false,X3> (MN-major tcgen05)",
+           "conv1x1_dgrad": "tc_gemm_kernel<128,0,X3,false,EPI=0> (paired K=192, accumulate) / <32,0,X3,false,0>", "transition_bwd": "tc_gemm_kernel<128,0,X3,false,0> + tc_wgrad_kernel<3,false,X3>",
+           "coverage_gemm": "tc_gemm_kernel<128,0,X3,false,0> (coverage patches x Q')",
+           "other_gemm": "tc_gemm_kernel (watch GEMM, decoder head, <..,EPI=2> split-K coverage backward / logits) + tc_wgrad_kernel (dQ') + gemm_kernel<...> (fp32 FFMA weight gradients over T*B rows)"},
 }
 DTYPE_OF = {"fp32": "f32", "tf32": "tf32 (fp32 storage/accumulate)", "tf32x3": "f32 (3xTF32 tensor-core products, fp32 accumulate)",
             "bf16": "bf16 (bf16 storage + tcgen05 kind::f16 products, fp32 accumulate/statistics; decoder fp32)"}
@@ -373,6 +374,9 @@ def run_train(args):
     shapes = [(pb.B, pb.H, pb.W) for pb in packed]
     step_res = lambda i: eng.train_step(*resident[i % nres], lr=1.0, dropout=True)                    # noqa: E731
     step_e2e = lambda i: float(eng.train_step_packed(packed[i % nres], lr=1.0, dropout=True))         # noqa: E731  (H2D + D2H of cost)
+    if args.workload == "cfg3":      # workspaces pre-sized for the largest bucket, as model-single-GPU.py does from the data set (WAPEngine.reserve)
+        for (bx, by), pb in zip(host[:nres], packed):
+            eng.reserve(pb.B, pb.H, pb.W, max(len(c) for c in by) + 1)
     nwarm = args.warmup if args.profile_run else max(args.warmup, 3)
     for i in range(nwarm):
         step_res(i)

@@ -50,6 +50,11 @@ def main(args):
         dp.broadcast_params(eng.accum); dp.broadcast_params(eng.accum_update)
 
     train = [b for b in train if b[0]]                       # drop empty batches BEFORE sharding: every rank runs the same number of steps
+    # workspaces sized once for the largest bucket (growth - a multi-GB cudaMalloc - would otherwise land inside training steps)
+    dims = [(len(bx), max(im.shape[1] for im in bx), max(im.shape[2] for im in bx), max(len(c) for c in by) + 1) for bx, by in train]
+    if dims:
+        for d in (max(dims, key=lambda d: d[0] * d[1] * d[2] * d[3]), max(dims, key=lambda d: d[0] * d[1] * d[2])):
+            eng.reserve(*d)
     uidx, cost_s, dispFreq = 0, 0.0, 100
     validFreq = sampleFreq = max(len(train) // world, 1)
     history_errs, estop, halfLrFlag, patience, lrate, bad_counter = [], False, 0, 15, 1.0, 0

@@ -584,6 +584,19 @@ class WAPEngine:
         self._graphs[key] = ent
         return self._cost[0]
 
+    def reserve(self, B: int, H: int, W: int, T: int) -> None:
+        """Pre-size every training workspace for the largest batch the caller will feed (B images padded to H x W, T caption rows incl. <eol>).
+        The role buffers otherwise grow on demand (`_buf`), and with the reference's area-bucketed batches a growth step (a multi-GB cudaMalloc)
+        lands inside training steps until the largest bucket has been seen; a trainer knows the maximum from its data set (the reference filters
+        by maxImagesize / maxlen, DATA:15-17), so model-single-GPU.py calls this once before the first epoch."""
+        h, w = self.annotation_hw(H, W)
+        self._buf(("amask",), B * h * w)
+        self._buf(("enc",), self.L.wap_encoder_workspace_floats(B, H, W, 1))
+        self._buf(("dec",), self.L.wap_decoder_train_workspace_floats(B, h, w, T))
+        self._buf(("ann",), B * h * w * ANNOT_C)
+        self._buf(("dann",), B * h * w * ANNOT_C)
+        self._buf(("x",), B * H * W); self._buf(("xm",), B * H * W)
+
     def _forward_backward(self, x, y, x_mask, y_mask, dropout, sd):
         B, H, W = x.shape[0], x.shape[1], x.shape[2]
         T = y.shape[0]
