@@ -206,6 +206,7 @@ template <int BN, bool X3, bool BF16 = false> struct TcSmem {
   // epilogue overlapping the first one's main loop matters more in block 0 than deeper prefetch does in blocks 1-2)
   static constexpr int kStages = kTcBK == 16 ? (X3 ? 3 : 4)
                                : (X3 ? (BN <= 96 ? 4 : 3) : (BN <= 32 ? 4 : 3));     // X3: 4 x 64 TMEM columns of A ring + 2 x 128 accumulator columns = 512
+                                                                       // (six stages for the BN = 48 N-split variant were measured: no gain)
   static constexpr int kABytes = kTcBM * kTcBK * 4;                 // 16384
   static constexpr int kBBytes = BN * kTcBK * 4;
   static constexpr int kStage = kABytes + (X3 ? 2 : 1) * kBBytes;
@@ -501,7 +502,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) v[i] += v2[i];
       }
-      const bool full = n0 + c + 32 <= sh.N;        // whole chunk inside the matrix: straight-line stores (the guarded forms cost a branch per group)
+      const int lim = min(sh.N - n0, BN) - c;          // columns of this chunk that belong to this tile AND to the matrix (BN = 48: the second chunk is half)
+      const bool full = lim >= 32;                   // whole chunk valid: straight-line stores (the guarded forms cost a branch per group)
       if ((kEPlain || kETr) && epi.bias != nullptr && kbb == 0) {
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] += s_stat[2 * BN + c + j];
@@ -538,7 +540,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) atomicAdd(dst + j * step, v[j]);
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) atomicAdd(dst + j * step, v[j]);
+          for (int j = 0; j < 32; ++j) if (j < lim) atomicAdd(dst + j * step, v[j]);
         }
       } else if (kETr && valid && epi.transpose_out) {
         float* dst = epi.out + (size_t)(n0 + c) * epi.ld + mrow;
@@ -547,7 +549,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int j = 0; j < 32; ++j) dst[(size_t)j * epi.ld] = v[j];
         } else {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) if (n0 + c + j < sh.N) dst[(size_t)j * epi.ld] = v[j];
+          for (int j = 0; j < 32; ++j) if (j < lim) dst[(size_t)j * epi.ld] = v[j];
         }
       } else if (valid && epi.out_bf16) {         // bf16 result (no accumulate): N is a multiple of 8 for every caller
         uint8_t* dst = reinterpret_cast<uint8_t*>(epi.out) + (mrow * epi.ld + n0 + c) * 2;
@@ -557,11 +559,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
 #pragma unroll
         for (int j = 0; j < 32; j += 8) {
-          if (n0 + c + j + 7 < sh.N) store_bf16x8(dst + j * 2, v + j);
+          if (j + 7 < lim) store_bf16x8(dst + j * 2, v + j);
           else {
 #pragma unroll
             for (int jj = 0; jj < 8; ++jj)
-              if (n0 + c + j + jj < sh.N) reinterpret_cast<__nv_bfloat16*>(dst)[j + jj] = __float2bfloat16_rn(v[j + jj]);
+              if (j + jj < lim) reinterpret_cast<__nv_bfloat16*>(dst)[j + jj] = __float2bfloat16_rn(v[j + jj]);
           }
         }
         }
@@ -580,14 +582,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
-            if (n0 + c + j + 3 < sh.N) {
+            if (j + 3 < lim) {
               float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
               if (kEPlain && epi.accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst + j); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
               *reinterpret_cast<float4*>(dst + j) = o;
             } else {
 #pragma unroll
               for (int jj = 0; jj < 4; ++jj)
-                if (n0 + c + j + jj < sh.N) dst[j + jj] = (kEPlain && epi.accumulate) ? dst[j + jj] + v[j + jj] : v[j + jj];
+                if (j + jj < lim) dst[j + jj] = (kEPlain && epi.accumulate) ? dst[j + jj] + v[j + jj] : v[j + jj];
             }
           }
         }
@@ -608,8 +610,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             b[i] = kb_ + __shfl_xor_sync(0xffffffffu, sb_, off);
           }
         }
-        atomicAdd(&s_stat[c + lane], a[0]);
-        atomicAdd(&s_stat[BN + c + lane], b[0]);
+        if (c + lane < BN) {
+          atomicAdd(&s_stat[c + lane], a[0]);
+          atomicAdd(&s_stat[BN + c + lane], b[0]);
+        }
       }
     }
     if (kEStats && epi.stats != nullptr) {
@@ -1099,7 +1103,10 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)M}; const uint64_t str[1] = {(uint64_t)lda * 4}; const uint32_t box[2] = {kTcBK, kTcBM};
     WAP_TRY(make_map(&ta, A, 2, dims, str, box));
   }
-  const int BN = N <= 32 ? 32 : N <= 96 ? 96 : 128;
+  // 3xTF32 is tensor-pipe bound per CTA (one CTA per SM): when the row tiles fill less than half of the machine (block 2 of the encoder: 64
+  // tiles), two 48-column CTAs per row tile halve the main loop; the BN statistics are per column, nothing has to be reduced
+  const bool split_n = Bt_lo != nullptr && N > 64 && N <= 96 && 2 * cdiv(M, kTcBM) <= 148 && !epi.transpose_out && splitk <= 1;
+  const int BN = N <= 32 ? 32 : split_n ? 48 : N <= 96 ? 96 : 128;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)N}; const uint64_t str[1] = {(uint64_t)ldb * 4}; const uint32_t box[2] = {kTcBK, (uint32_t)BN};
     WAP_TRY(make_map(&tb, Bt, 2, dims, str, box));
@@ -1116,6 +1123,7 @@ int tc_gemm(cudaStream_t st, const float* A, int lda, const float* Bt, const flo
   const CUtensorMap* pl = Bt_lo != nullptr ? &tbl : nullptr;
   prof_set_bytes(4.0 * ((double)M * K + (double)N * K * (Bt_lo != nullptr ? 2 : 1) + (double)M * N * (epi.accumulate ? 2 : 1)));
   if (BN == 32) return launch_tc<32, 0>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 48) return launch_tc1<48, 0, true>(st, ta, tb, tbl, epi, sh, grid, prof_cls, flops);
   if (BN == 96) return launch_tc<96, 0>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   return launch_tc<128, 0>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
 }
@@ -1133,7 +1141,8 @@ int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, in
     const uint32_t box[4] = {kTcBK, (uint32_t)TW, (uint32_t)TH, 1};
     WAP_TRY(make_map(&ta, x, 4, dims, str, box));
   }
-  const int BN = N <= 32 ? 32 : N <= 96 ? 96 : 128;
+  const bool split_n = Wt_lo != nullptr && N > 64 && N <= 96 && epi.bnb_raw == nullptr && 2 * cdiv(W, TW) * cdiv(H, TH) * B <= 148;
+  const int BN = N <= 32 ? 32 : split_n ? 48 : N <= 96 ? 96 : 128;
   const int K = 9 * C;
   {
     const uint64_t dims[2] = {(uint64_t)K, (uint64_t)Nrows}; const uint64_t str[1] = {(uint64_t)K * 4}; const uint32_t box[2] = {kTcBK, (uint32_t)BN};
@@ -1147,6 +1156,7 @@ int tc_conv3x3(cudaStream_t st, const float* x, int ldx, int B, int H, int W, in
   const double flops = 2.0 * sh.M * N * K;
   prof_set_bytes(4.0 * ((double)sh.M * C + (double)Nrows * K * (Wt_lo != nullptr ? 2 : 1) + (double)sh.M * N));   // every input element once
   if (BN == 32) return launch_tc<32, 1>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
+  if (BN == 48) return launch_tc1<48, 1, true>(st, ta, tb, tbl, epi, sh, grid, prof_cls, flops);
   if (BN == 96) return launch_tc<96, 1>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
   return launch_tc<128, 1>(st, ta, tb, pl, epi, sh, grid, prof_cls, flops);
 }
