@@ -198,7 +198,8 @@ int wap_debug_bn_gates(void* stream, const float* params, const float* encoder_w
 /* debugging aid: bit mask of the conv classes allowed on the tensor-core path (default 0x3FF); bit 8 = row-tile form of the 3x3 convs,
  * bit 9 = inference-mode batch norm + ReLU folded into the conv epilogues (off: conv -> bn_act kernels as in training), bit 10 (NOT in the default: it measured
  * 0.7 ms slower per cfg2 step - four epilogue warps per CTA do what a full-occupancy kernel did) = first pass of the 1x1 output's batch-norm
- * backward fused into the epilogue of the 3x3 dgrad */
+ * backward fused into the epilogue of the 3x3 dgrad, bit 11 (NOT in the default: 0.09 ms slower) = batch-norm backward of the small feature maps as
+ * one kernel (both passes around a grid barrier, elements kept in registers) */
 int wap_debug_set_tc_mask(int mask);
 /* debugging aid: during wap_encoder_backward copy [d a1 | d y2 (ld 32) | d y1] of the dense level whose 1x1 conv index is `layer` into buf */
 int wap_debug_capture(int layer, float* buf);

@@ -13,6 +13,7 @@ from helpers import (O, REL_TOL, engine_gates, engine_grads, engine_with, grad_e
                      t64)
 
 pytestmark = pytest.mark.gpu
+DEFAULT_TC_MASK = 0x3FF      # csrc/encoder.cu g_tc_debug_mask
 
 
 def _check(report, test, name, got, ref, tol=REL_TOL, fails=None):
@@ -372,6 +373,42 @@ def test_fused_bn_backward_reduce_matches_separate_kernels(report):
     e0 = rel_l2(g_plain.cpu().numpy(), g0.cpu().numpy()); e = rel_l2(g_fused.cpu().numpy(), g_plain.cpu().numpy())
     report.add("bn_bwd_fused", "grads_rel_l2_vs_unfused", e, 2e-5, extra=dict(rerun_noise=e0, launches=(n_plain, n_fused)))
     assert e0 <= 2e-5 and e <= 2e-5 and n_fused == n_plain - 48, (c0, e0, e, n_plain, n_fused)
+
+
+@pytest.mark.parametrize("B,H,W,cap", [(2, 50, 150, 4), (8, 128, 512, 6), (3, 64, 100, 5), (1, 33, 47, 3)])
+def test_single_kernel_bn_backward_matches_two_pass(report, B, H, W, cap):
+    """BN backward of the small feature maps as ONE kernel (both passes around a grid barrier, elements kept in registers; debug-mask bit 11)
+    == reduce kernel + apply kernel.  ONE forward, backward twice on the same saved activations: same gradients up to the order of the sums."""
+    import ctypes as C
+    import wap_b200
+    from wap_b200.engine import _p, _stream
+    P = O.lively_params(5)
+    x, xm, y, ym = make_batch(35, B, H, W, cap, True)
+    eng = engine_with(P, use_graphs=False)
+    L = wap_b200._lib.lib()
+    mask0 = 0x3FF
+    L.wap_debug_set_tc_mask(mask0)
+    try:
+        c0 = float(eng.forward_backward(x, y, xm, ym, True, 9))
+        xd, yd, xmd, ymd = eng._dev(x, torch.float32), eng._dev(y, torch.int32), eng._dev(xm, torch.float32), eng._dev(ym, torch.float32)
+        T = y.shape[0]
+
+        def backward_again():
+            eng.grads.zero_()
+            n0 = eng.launch_count()
+            wap_b200._lib.check(eng.L.wap_train_backward(_stream(), _p(eng.P.flat), _p(eng.grads), _p(xd), B, H, W, _p(eng._ws[("ann",)]), _p(eng._ws[("amask",)]),
+                                                         _p(yd), _p(ymd), T, 1, C.c_uint32(9), _p(eng._ws[("dann",)]), _p(eng._ws[("enc",)]), _p(eng._ws[("dec",)])),
+                                "wap_train_backward")
+            return eng.grads.clone(), eng.launch_count() - n0
+        g_two, n_two = backward_again()
+        L.wap_debug_set_tc_mask(mask0 | 2048)
+        g_one, n_one = backward_again()
+        g_one2, _ = backward_again()
+    finally:
+        L.wap_debug_set_tc_mask(DEFAULT_TC_MASK)
+    e = rel_l2(g_one.cpu().numpy(), g_two.cpu().numpy()); e2 = rel_l2(g_one2.cpu().numpy(), g_one.cpu().numpy())
+    report.add("bn_bwd_single_kernel", f"grads_rel_l2_vs_two_pass_B{B}_{H}x{W}", e, 2e-5, extra=dict(rerun=e2, launches=(n_two, n_one)))
+    assert e <= 2e-5 and e2 <= 2e-5 and n_one < n_two, (c0, e, e2, n_two, n_one)
 
 
 @pytest.mark.parametrize("B,H,W,cap,ragged", [(2, 50, 150, 4, True), (8, 128, 512, 12, False), (3, 64, 100, 7, True)])

@@ -157,6 +157,7 @@ struct BnBwdArgs {
   int dropout; uint32_t seed, site;
   const uint32_t* seed_src;
   int round_tf32;                            // round d raw to TF32 (operand of the tcgen05 dgrad)
+  unsigned* bar;                             // zeroed counter of the single-kernel form (bn_bwd_fused_kernel), or null: two kernels
 };
 
 template <int POOL, typename TRaw, typename TG>
@@ -309,6 +310,102 @@ __global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const BnBwdArgs a) {
   }
 }
 
+// Both passes in ONE kernel for feature maps small enough that every thread keeps its elements in registers between them (blocks 1-2, and
+// the 24-channel maps of block 0): pass 1 as above, then a grid-wide barrier (a counter in global memory; the grid is at most 2 CTAs per SM,
+// so all of it is resident - every kernel of this library releases its dependents at its first instruction, when all its CTAs are running), then
+// pass 2 on the registers.  g is written once instead of written, re-read and rewritten, and the backward chain loses one launch per BN.
+constexpr int kBnFusedE = 4;        // pixels per thread row
+template <typename TRaw, typename TG>
+__global__ void __launch_bounds__(256, 2) bn_bwd_fused_kernel(const BnBwdArgs a, const int pix_per_cta) {
+  pdl_sync();
+  const uint32_t seed = (a.dropout && a.seed_src != nullptr) ? __ldg(a.seed_src) : a.seed;
+  __shared__ float s_scale[kMaxBnC], s_shift[kMaxBnC], s_mean[kMaxBnC], s_inv[kMaxBnC];
+  __shared__ float s_sg[kMaxBnC], s_sgx[kMaxBnC];
+  const int C4 = a.C / 4, rows = blockDim.x / C4;
+  const int c = (threadIdx.x % C4) * 4, prow = threadIdx.x / C4;
+  const size_t npix = (size_t)a.B * a.Hi * a.Wi;
+  const size_t p0 = (size_t)blockIdx.x * pix_per_cta;
+  const size_t p1 = min(npix, p0 + (size_t)pix_per_cta);
+  float rv[kBnFusedE][4], gg[kBnFusedE][4];
+  const bool act = prow < rows;
+#pragma unroll
+  for (int u = 0; u < kBnFusedE; ++u) {          // every load of the CTA in flight before the per-channel constants are staged
+    const size_t p = p0 + prow + (size_t)u * rows;
+    if (act && p < p1) {
+      ld4<TRaw>(a.raw, p * a.C + c, rv[u]);
+      const float4 d = ldg4(a.dout + p * a.ld_dout + c);
+      gg[u][0] = d.x; gg[u][1] = d.y; gg[u][2] = d.z; gg[u][3] = d.w;
+    }
+  }
+  for (int cc = threadIdx.x; cc < a.C; cc += blockDim.x) {
+    const float mean = a.saved[cc], inv = a.saved[kMaxBnC + cc];
+    const float sc = __ldg(a.gamma + cc) * inv;
+    s_scale[cc] = sc; s_shift[cc] = __ldg(a.beta + cc) - mean * sc; s_mean[cc] = mean; s_inv[cc] = inv;
+    s_sg[cc] = 0.f; s_sgx[cc] = 0.f;
+  }
+  __syncthreads();
+  float sg[4] = {0.f, 0.f, 0.f, 0.f}, sgx[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int u = 0; u < kBnFusedE; ++u) {
+    const size_t p = p0 + prow + (size_t)u * rows;
+    if (act && p < p1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float pre = fmaf(rv[u][j], s_scale[c + j], s_shift[c + j]);
+        float gj = (pre > 0.f) ? gg[u][j] : 0.f;
+        if (a.dropout) gj = drop_keep(seed, a.site, (uint32_t)(p * a.C + c + j)) ? gj * (1.f / (1.f - kDropRate)) : 0.f;
+        const float xh = (rv[u][j] - s_mean[c + j]) * s_inv[c + j];
+        gg[u][j] = gj; rv[u][j] = xh;                  // keep g and xhat
+        sg[j] += gj;
+        sgx[j] = fmaf(gj, xh, sgx[j]);
+      }
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { atomicAdd(&s_sg[c + j], sg[j]); atomicAdd(&s_sgx[c + j], sgx[j]); }
+  }
+  __syncthreads();
+  for (int cc = threadIdx.x; cc < a.C; cc += blockDim.x) {
+    atomicAdd(a.red + cc, (double)s_sg[cc]);
+    atomicAdd(a.red + a.C + cc, (double)s_sgx[cc]);
+  }
+  // ---- grid barrier: every CTA's partial sums are in a.red
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    atomicAdd(a.bar, 1u);
+    unsigned v;
+    do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(a.bar) : "memory"); } while (v < gridDim.x);
+  }
+  __syncthreads();
+  // ---- pass 2 on the registers
+  const double cnt = (double)npix;
+  float* s_k = s_scale; float* s_mg = s_sg; float* s_mgx = s_sgx;      // reuse
+  for (int cc = threadIdx.x; cc < a.C; cc += blockDim.x) {
+    const double tg = __ldcg(a.red + cc), tgx = __ldcg(a.red + a.C + cc);
+    s_k[cc] = __ldg(a.gamma + cc) * s_inv[cc];
+    s_mg[cc] = (float)(tg / cnt); s_mgx[cc] = (float)(tgx / cnt);
+    if (blockIdx.x == 0) { a.dbeta[cc] += (float)tg; a.dgamma[cc] += (float)tgx; }
+  }
+  if (blockIdx.x == 0 && a.red_next != nullptr)
+    for (int i = threadIdx.x; i < 2 * kMaxBnC; i += blockDim.x) a.red_next[i] = 0.0;
+  __syncthreads();
+#pragma unroll
+  for (int u = 0; u < kBnFusedE; ++u) {
+    const size_t p = p0 + prow + (size_t)u * rows;
+    if (act && p < p1) {
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        o[j] = s_k[c + j] * (gg[u][j] - s_mg[c + j] - rv[u][j] * s_mgx[c + j]);
+        if (a.round_tf32) o[j] = tf32_rna(o[j]);
+      }
+      st4<TG>(a.g, p * a.ld_g + c, o);
+    }
+  }
+}
+
 static inline int ew_grid(size_t total_vec) {
   return (int)std::min<size_t>(cdivz(total_vec, 256), 148 * 8);
 }
@@ -337,6 +434,16 @@ static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
   // a.red was zeroed by the previous BN backward's apply kernel (or by the memset at the start of encoder_backward): a memset
   // node here would sit between two kernels 110 times per step and break their programmatic dependency
   const size_t npix = (size_t)a.B * a.Hi * a.Wi;
+  if (pool == 0 && a.bar != nullptr) {      // single-kernel form when every thread can hold its share in registers (<= kBnFusedE pixels per thread row)
+    const int rows = 256 / (a.C / 4);
+    const int grid = (int)std::min<size_t>(296, cdivz(npix, (size_t)rows));
+    const int ppc = (int)cdivz(npix, (size_t)grid);
+    if (ppc <= kBnFusedE * rows) {
+      WAP_CHECK(launch_pdl(bn_bwd_fused_kernel<TRaw, TG>, (int)cdivz(npix, (size_t)ppc), 256, 0, st, a, ppc));
+      WAP_LAUNCH_CHECK();
+      return 0;
+    }
+  }
   // CTAs per SM of the reduce pass: every CTA ends with 2*C fp64 atomics onto the same 2*C addresses, so more CTAs = more contention
   // (tunable for experiments: WAP_BN_BWD_CTAS_PER_SM)
   static const int per_sm = [] { const char* e = getenv("WAP_BN_BWD_CTAS_PER_SM"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();

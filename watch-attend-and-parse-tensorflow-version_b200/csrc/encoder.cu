@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(128) bn_fold_kernel(const float* __restrict__ 
 }
 
 int g_dbg_layer = -1; float* g_dbg_buf = nullptr;   // debug capture of backward intermediates of one dense level (1x1 index)
-int g_tc_debug_mask = 0x3FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd, bit8 row-tile 3x3, bit9 inference BN folded into the conv epilogues, bit10 (off by default: measured slower) BN-backward reduce of the 1x1 output fused into the 3x3 dgrad epilogue
+int g_tc_debug_mask = 0x3FF;              // debug: bit0 transition dgrad, bit1 3x3 dgrad, bit2 1x1 dgrad, bit3 1x1 fwd, bit4 3x3 fwd, bit5 transition fwd, bit8 row-tile 3x3, bit9 inference BN folded into the conv epilogues, bit10 (off by default: measured slower) BN-backward reduce of the 1x1 output fused into the 3x3 dgrad epilogue, bit11 single-kernel BN backward (grid barrier) for small maps
 void set_conv_precision(int mode) { cur()->precision = mode; }
 int get_conv_precision() { return cur()->precision; }
 
@@ -432,6 +432,9 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
   double* red2[2] = {reinterpret_cast<double*>(wsp + ws.red), reinterpret_cast<double*>(wsp + ws.red) + 2 * kMaxBnC};
   int bn_no = 0;
   WAP_CHECK(cudaMemsetAsync(red2[0], 0, sizeof(double) * 4 * kMaxBnC, st));
+  unsigned* bnbar = reinterpret_cast<unsigned*>(wsp + ws.bnbar);
+  const bool bn_fused = (g_tc_debug_mask & 2048) != 0;     // single-kernel BN backward for the small feature maps (bn_bwd_fused_kernel)
+  if (bn_fused) WAP_CHECK(cudaMemsetAsync(bnbar, 0, sizeof(unsigned) * 256, st));
   const float* buf[kBlocks] = {wsp + ws.buf[0], wsp + ws.buf[1], annotation != nullptr ? annotation : wsp + ws.buf[2]};
   float* G[kBlocks] = {wsp + ws.gbuf[0], wsp + ws.gbuf[1], d_annotation};
   constexpr int kDy1Ld = 2 * kBottle;
@@ -460,7 +463,7 @@ int encoder_backward(cudaStream_t st, const float* params, float* grads, const f
     a.raw = raw; a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = c.cout;
     a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
     a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
-    a.g = gbuf; a.ld_g = ld_g; a.red = red2[bn_no & 1]; a.red_next = red2[(bn_no + 1) & 1]; ++bn_no; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
+    a.g = gbuf; a.ld_g = ld_g; a.red = red2[bn_no & 1]; a.red_next = red2[(bn_no + 1) & 1]; a.bar = bn_fused ? bnbar + bn_no : nullptr; ++bn_no; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
     a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = seed_src(); a.site = (uint32_t)k;
     a.round_tf32 = (tc && !x3) ? 1 : 0;
     return a;

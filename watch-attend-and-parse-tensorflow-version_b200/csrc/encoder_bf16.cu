@@ -238,7 +238,7 @@ int encoder_backward_bf16(cudaStream_t st, const float* params, float* grads, co
     a.raw = raw; a.B = B; a.Hi = Hi; a.Wi = Wi; a.C = c.cout;
     a.dout = dout; a.Ho = Ho; a.Wo = Wo; a.ld_dout = ld_dout;
     a.saved = saved + (size_t)k * 2 * kMaxBnC; a.gamma = params + c.gamma; a.beta = params + c.beta;
-    a.g = gbuf; a.ld_g = ld_g; a.red = red2[bn_no & 1]; a.red_next = red2[(bn_no + 1) & 1]; ++bn_no; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
+    a.g = gbuf; a.ld_g = ld_g; a.red = red2[bn_no & 1]; a.red_next = red2[(bn_no + 1) & 1]; a.bar = nullptr; ++bn_no; a.dgamma = grads + c.gamma; a.dbeta = grads + c.beta;
     a.dropout = (dropout && drop) ? 1 : 0; a.seed = seed; a.seed_src = seed_src(); a.site = (uint32_t)k;
     a.round_tf32 = 0;
     return a;

@@ -127,6 +127,7 @@ EncWorkspace make_enc_workspace(const EncGeom& g, bool training) {
   ws.stats = take((size_t)kNumConv * 2 * kMaxBnC * 2);   // doubles (offset is a multiple of 4 floats = 16 B)
   ws.red = take(2 * kMaxBnC * 2 * 2);     // two [2][kMaxBnC] double buffers: BN backward n uses buffer n&1 and zeroes the other for n+1
   ws.saved = take((size_t)kNumConv * 2 * kMaxBnC);
+  ws.bnbar = take(256);
   ws.stem_raw = take((size_t)g.B * g.Hs * g.Ws * kStemC);
   for (int b = 0; b < kBlocks; ++b) ws.buf[b] = take((size_t)g.M[b] * g.Ctot[b]);
   size_t sy1 = 0, sa1 = 0, sy2 = 0;   // shared scratch for inference

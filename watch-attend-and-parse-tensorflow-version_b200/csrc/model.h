@@ -72,6 +72,7 @@ struct EncWorkspace {
   int wt_bwd_ld[kNumConv];               // row stride of the dgrad copy: 1x1 layers of a level pair (2j+1, 2j) share one [Cin][192] buffer
                                          // (odd level in columns 0..95, even level in 96..191) so that ONE K=192 GEMM applies both
   size_t red;                            // doubles [2][kMaxBnC]
+  size_t bnbar;                          // 256 unsigned counters: grid barriers of the single-kernel BN backward (one per BN layer, zeroed per backward)
   size_t total;                          // floats
 };
 EncWorkspace make_enc_workspace(const EncGeom& g, bool training);
