@@ -1,5 +1,5 @@
 """Latency anatomy of one small tcgen05 GEMM launch (the per-time-step coverage GEMMs of the scans): event-timed back-to-back launches and
-the clock64 stamps of CTA (0,0,0).  usage: python tools/ubench_tc_gemm.py"""
+the clock64 stamps of CTA (0,0,0).  usage: python tools/ubench_tc_gemm.py [anatomy|kblocks|graph]"""
 import sys, os, ctypes as C
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -40,12 +40,6 @@ def run(M, N, K, tr, splitk, x3=True, reps=200):
           f"k-blocks [tma, landed, split, mma] {[[round(v, 2) for v in r] for r in kb]} | rel err {err:.1e}")
 
 
-if os.environ.get('ALLKB'):
-    run(8192, 96, 608, 0, 1); run(8192, 96, 608, 0, 1, x3=False); sys.exit(0)
-run(128, 121, 32, 1, 1); run(128, 121, 32, 0, 1); run(128, 32, 32, 0, 1); run(128, 121, 32, 0, 1, x3=False)
-sys.exit(0)
-
-
 def graph_latency(M, N, K, tr, splitk, interleave, x3=True, reps=50):
     """per-launch time inside a replayed CUDA graph (no host cost): reps x [GEMM (+ a small elementwise kernel when interleave)]"""
     A = torch.randn(M, K, device="cuda"); W = torch.randn(K, N, device="cuda")
@@ -81,8 +75,15 @@ def graph_latency(M, N, K, tr, splitk, interleave, x3=True, reps=50):
           f"CUPTI kernel duration median {durs[len(durs) // 2]:.2f} us, start-to-start median {gaps[len(gaps) // 2]:.2f} us ({len(ev)} kernels)")
 
 
-graph_latency(128, 121, 32, 1, 1, 0); graph_latency(128, 121, 32, 1, 1, 0, x3=False); graph_latency(128, 121, 32, 0, 1, 0); graph_latency(128, 32, 32, 0, 1, 0)
-L.wap_set_pdl(0)
-graph_latency(128, 121, 32, 1, 1, 0); graph_latency(2048, 121, 512, 1, 8, 0)
-L.wap_set_pdl(1)
-graph_latency(2048, 121, 512, 1, 8, 0); graph_latency(2048, 512, 128, 0, 1, 0)
+mode = sys.argv[1] if len(sys.argv) > 1 else "anatomy"
+if mode == "kblocks":        # per-k-block stamps of a block-2-sized 1x1 conv (3xTF32 and single-pass TF32)
+    os.environ["ALLKB"] = "1"
+    run(8192, 96, 608, 0, 1); run(8192, 96, 608, 0, 1, x3=False)
+elif mode == "graph":        # dependent-launch latency inside a replayed graph + CUPTI durations
+    graph_latency(128, 121, 32, 1, 1, 0); graph_latency(128, 121, 32, 1, 1, 0, x3=False); graph_latency(128, 121, 32, 0, 1, 0); graph_latency(128, 32, 32, 0, 1, 0)
+    L.wap_set_pdl(0)
+    graph_latency(128, 121, 32, 1, 1, 0); graph_latency(2048, 121, 512, 1, 8, 0)
+    L.wap_set_pdl(1)
+    graph_latency(2048, 121, 512, 1, 8, 0); graph_latency(2048, 512, 128, 0, 1, 0)
+else:                        # anatomy of one tile: set-up, accumulator ready, each epilogue chunk
+    run(128, 121, 32, 1, 1); run(128, 121, 32, 0, 1); run(128, 32, 32, 0, 1); run(128, 121, 32, 0, 1, x3=False)

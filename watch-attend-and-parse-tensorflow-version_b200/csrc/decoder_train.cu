@@ -10,7 +10,6 @@
 //   * every weight gradient is ONE GEMM over all T*B rows after the time loop instead of T
 //     rank-B updates inside it; only the data gradients stay in the sequential loop.
 #include <algorithm>
-#include <cstdlib>
 
 #include "decoder.cuh"
 #include "tc_gemm.cuh"
@@ -701,11 +700,8 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
     // consume them, dalpha / softmax backward / dz are one kernel.  Every contribution to the carried gradients is an atomic add into
     // per-step rows zero-filled here; DH[T] = 0 is the initial carry.  Side stream: the coverage backward DZ -> DF -> dAP only.
     WAP_CHECK(cudaMemsetAsync(W.DH, 0, sizeof(float) * ((size_t)(TB + B) * kN + (size_t)TB * kN + (size_t)TB * kNA + (((size_t)TB + 3) & ~(size_t)3)), st));     // DH, DPREH, dVaP, dVabP are adjacent
-    static const int env_split = getenv("WAP_BPTT_SPLITK") != nullptr ? atoi(getenv("WAP_BPTT_SPLITK")) : 0;
-    static const int env_pix = getenv("WAP_ATTN_BWD_PIX") != nullptr ? atoi(getenv("WAP_ATTN_BWD_PIX")) : 16;
     const int mtiles = cdiv(B * L, 128);
-    const int splitk = env_split > 0 ? env_split : std::max(1, std::min(8, 148 / mtiles));
-    const int pix = env_pix == 8 ? 8 : 16;
+    const int splitk = std::max(1, std::min(8, 148 / mtiles));      // (4 and 16 measured at 16 row tiles: 8 is the fastest; 8 positions per CTA of the attention kernel: slower)
     const size_t BL = (size_t)B * L;
     if (tc && splitk > 1) WAP_CHECK(cudaMemsetAsync(W.DF, 0, sizeof(float) * BL * 124 * 2, st));
     for (int t = T - 1; t >= 0; --t) {
@@ -729,9 +725,7 @@ int decoder_train_backward(cudaStream_t st, const float* params, float* grads, c
       float* DFt = W.DF + (size_t)(t & 1) * BL * 124;
       float* DFnext = W.DF + (size_t)((t + 1) & 1) * BL * 124;
       const int zero_n4 = (tc && splitk > 1) ? (int)(BL * 124 / 4) : 0;
-      if (pix == 8) WAP_CHECK(launch_pdl(attn_bwd_kernel<8>, dim3(cdiv(L, 8), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
-                           W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, W.dVaP + r * kNA, W.dVabP + r, L, reinterpret_cast<float4*>(DFnext), zero_n4));
-      else WAP_CHECK(launch_pdl(attn_bwd_kernel<16>, dim3(cdiv(L, 16), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
+      WAP_CHECK(launch_pdl(attn_bwd_kernel<16>, dim3(cdiv(L, 16), B), 128, 0, st, ann, dctx, W.CTX + r * kD, W.ALPHA + r * L, dAP_in,
                            W.TANH + r * L * kNA, p + P.V_a, DZt, W.dSP + r * kNA, W.dVaP + r * kNA, W.dVabP + r, L, reinterpret_cast<float4*>(DFnext), zero_n4));
       WAP_LAUNCH_CHECK();
       WAP_TRY(fork2(3));
