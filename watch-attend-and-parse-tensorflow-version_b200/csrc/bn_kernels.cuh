@@ -445,8 +445,9 @@ static int run_bn_bwd(cudaStream_t st, int pool, const BnBwdArgs& a) {
     }
   }
   // CTAs per SM of the reduce pass: every CTA ends with 2*C fp64 atomics onto the same 2*C addresses, so more CTAs = more contention
-  // (tunable for experiments: WAP_BN_BWD_CTAS_PER_SM)
-  static const int per_sm = [] { const char* e = getenv("WAP_BN_BWD_CTAS_PER_SM"); const int v = e ? atoi(e) : 4; return v > 0 ? v : 4; }();
+  // (tunable for experiments: WAP_BN_BWD_CTAS_PER_SM).  2 = what is resident with the kernel's 94 registers: one wave; with 4 the 32768-pixel maps of
+  // block 0 ran 1.4-2 waves of CTAs whose fixed cost (constant staging, shared + global atomics) is half their time: 9.85 vs 9.89 ms per cfg2 step
+  static const int per_sm = [] { const char* e = getenv("WAP_BN_BWD_CTAS_PER_SM"); const int v = e ? atoi(e) : 2; return v > 0 ? v : 2; }();
   int ppc = (int)std::max<size_t>(64, cdivz(npix, (size_t)148 * per_sm));
   const int round = 4 * (256 / (a.C / 4));            // one unrolled round of the reduce loop = 4 pixels per thread row: avoid a nearly empty last round
   if (round <= ppc) ppc = cdiv(ppc, round) * round;
